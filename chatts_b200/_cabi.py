@@ -1,0 +1,221 @@
+"""ctypes binding of libchatts_b200.so (include/chatts_b200.h).
+
+This is the ONLY compute path of the package: there is no Python / torch fallback behind any wrapper, and
+importing the package on a machine where the library is missing or where no sm_100 GPU is visible raises
+as soon as a kernel is requested.  torch is used for device memory, streams and torch.distributed only.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libchatts_b200.so")
+
+OK = 0
+BF16, F16 = 0, 1
+EPI_NONE, EPI_GELU, EPI_SWIGLU, EPI_PARTIAL_F32, EPI_RESIDUAL = 0, 1, 2, 3, 4
+
+# every symbol include/chatts_b200.h declares (tests/test_cabi_symbols.py checks the .so exports them all)
+SYMBOLS = [
+    "cts_version", "cts_arch", "cts_ctx_create", "cts_ctx_destroy", "cts_last_error",
+    "cts_ts_patch_count", "cts_ts_patchify", "cts_gemm", "cts_gemm_suggest_split",
+    "cts_reduce_bias_act", "cts_reduce_residual_rmsnorm", "cts_reduce_swiglu", "cts_qkv_rope_cache",
+    "cts_embed_gather", "cts_attn_prefill", "cts_attn_decode_workspace_floats", "cts_attn_decode",
+    "cts_greedy_advance",
+]
+
+
+class CtsError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("w", C.c_void_p), ("w2", C.c_void_p), ("x", C.c_void_p), ("bias", C.c_void_p),
+        ("residual", C.c_void_p), ("out", C.c_void_p), ("row_map", C.c_void_p),
+        ("n", C.c_longlong), ("k", C.c_longlong), ("t", C.c_longlong),
+        ("w_ld", C.c_longlong), ("x_ld", C.c_longlong), ("out_ld", C.c_longlong),
+        ("dtype", C.c_int), ("epilogue", C.c_int), ("split_k", C.c_int), ("reserved", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree library; raise loudly if it is not there (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CtsError(f"{LIB_PATH} is missing: run `python -m chatts_b200.build` (nvcc, sm_100a). "
+                       "chatts_b200 has no CPU or torch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, ll, f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+    lib.cts_version.restype = i
+    lib.cts_arch.restype = C.c_char_p
+    lib.cts_ctx_create.argtypes = [i, C.POINTER(vp)]
+    lib.cts_ctx_destroy.argtypes = [vp]
+    lib.cts_ctx_destroy.restype = None
+    lib.cts_last_error.argtypes = [vp]
+    lib.cts_last_error.restype = C.c_char_p
+    lib.cts_ts_patch_count.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp]
+    lib.cts_ts_patchify.argtypes = [vp, vp, i, i, i, i, i, i, vp, i, i, vp, vp, vp, i, vp, i, vp]
+    lib.cts_gemm.argtypes = [vp, C.POINTER(GemmArgs), vp]
+    lib.cts_gemm_suggest_split.argtypes = [vp, ll, ll, ll, i]
+    lib.cts_reduce_bias_act.argtypes = [vp, vp, i, ll, ll, vp, i, vp, ll, vp, i, vp]
+    lib.cts_reduce_residual_rmsnorm.argtypes = [vp, vp, i, vp, vp, vp, f, vp, ll, ll, i, vp]
+    lib.cts_reduce_swiglu.argtypes = [vp, vp, i, ll, ll, vp, i, vp]
+    lib.cts_qkv_rope_cache.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, i, i, i, i, vp]
+    lib.cts_embed_gather.argtypes = [vp, vp, vp, vp, ll, ll, ll, i, vp]
+    lib.cts_attn_prefill.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, f, vp, i, vp]
+    lib.cts_attn_decode_workspace_floats.argtypes = [i, i, i, i]
+    lib.cts_attn_decode_workspace_floats.restype = ll
+    lib.cts_attn_decode.argtypes = [vp, vp, vp, vp, vp, i, vp, i, i, i, i, i, f, i, vp, vp, i, vp]
+    lib.cts_greedy_advance.argtypes = [vp, vp, ll, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
+    for name in ("cts_ts_patch_count", "cts_ts_patchify", "cts_gemm", "cts_gemm_suggest_split", "cts_reduce_bias_act",
+                 "cts_reduce_residual_rmsnorm", "cts_reduce_swiglu", "cts_qkv_rope_cache", "cts_embed_gather",
+                 "cts_attn_prefill", "cts_attn_decode", "cts_greedy_advance", "cts_ctx_create"):
+        getattr(lib, name).restype = i
+    _lib = lib
+    return lib
+
+
+def dtype_code(dt):
+    if dt == torch.bfloat16:
+        return BF16
+    if dt == torch.float16:
+        return F16
+    raise CtsError(f"unsupported model dtype {dt}: the sm_100a kernels compute in bf16 or fp16 with fp32 accumulate")
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Context:
+    """One per (process, device).  Raises if the GPU is not sm_100 -- there is nothing else to run on."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise CtsError("no CUDA device visible: chatts_b200 runs on B200 (sm_100a) only, with no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+        h = C.c_void_p()
+        rc = self.lib.cts_ctx_create(self.device, C.byref(h))
+        if rc != OK or not h:
+            raise CtsError(f"cts_ctx_create(device={self.device}) failed with {rc} (needs an sm_100 device)")
+        self.h = h
+        self.arch = self.lib.cts_arch().decode()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cts_ctx_destroy(self.h)
+            self.h = None
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise CtsError(f"chatts_b200 error {rc}: {self.lib.cts_last_error(self.h).decode()}")
+
+    # ------------------------------------------------------------------ TS front end
+    def ts_patch_count(self, x, num_features, patch_size):
+        n = x.shape[0]
+        row_len = x.numel() // max(n, 1)
+        dev = x.device
+        valid = torch.empty(n, dtype=torch.int32, device=dev)
+        cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        off = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        mx = torch.empty(1, dtype=torch.int32, device=dev)
+        self._chk(self.lib.cts_ts_patch_count(self.h, _p(x), dtype_code(x.dtype), n, row_len, num_features, patch_size,
+                                              _p(valid), _p(cnt), _p(off), _p(mx), _stream()))
+        return valid, cnt, off, mx
+
+    def ts_patchify(self, x, num_features, patch_size, mode, pos_table, emb_dim, max_seq_len, valid, off, mx,
+                    max_patches, rows_out):
+        n = x.shape[0]
+        row_len = x.numel() // max(n, 1)
+        self._chk(self.lib.cts_ts_patchify(self.h, _p(x), dtype_code(x.dtype), n, row_len, num_features, patch_size, mode,
+                                           _p(pos_table), emb_dim, max_seq_len, _p(valid), _p(off), _p(mx), max_patches,
+                                           _p(rows_out), rows_out.shape[1], _stream()))
+
+    # ------------------------------------------------------------------ GEMM
+    def suggest_split(self, n, k, t, dual=False):
+        return int(self.lib.cts_gemm_suggest_split(self.h, n, k, t, int(dual)))
+
+    def gemm(self, x, w, out, *, w2=None, bias=None, residual=None, row_map=None, epilogue=EPI_NONE, split_k=1, t=None):
+        """out[T,N] (or fp32 partial [S,T,N]) = x[T,K] @ w[N,K]^T with the fused epilogue."""
+        a = GemmArgs()
+        a.w, a.w2, a.x = w.data_ptr(), (w2.data_ptr() if w2 is not None else None), x.data_ptr()
+        a.bias = bias.data_ptr() if bias is not None else None
+        a.residual = residual.data_ptr() if residual is not None else None
+        a.out = out.data_ptr()
+        a.row_map = row_map.data_ptr() if row_map is not None else None
+        a.n, a.k = w.shape[0], w.shape[1]
+        a.t = x.shape[0] if t is None else t
+        a.w_ld, a.x_ld = w.stride(0), x.stride(0)
+        a.out_ld = out.stride(-2) if epilogue != EPI_PARTIAL_F32 else a.n
+        a.dtype, a.epilogue, a.split_k = dtype_code(x.dtype), epilogue, split_k
+        self._chk(self.lib.cts_gemm(self.h, C.byref(a), _stream()))
+
+    # ------------------------------------------------------------------ fused split-K tails
+    def reduce_bias_act(self, partial, split_k, t, n, bias, act, out, row_map=None):
+        self._chk(self.lib.cts_reduce_bias_act(self.h, _p(partial), split_k, t, n, _p(bias), act, _p(out), out.stride(0),
+                                               _p(row_map), dtype_code(out.dtype), _stream()))
+
+    def reduce_residual_rmsnorm(self, partial, split_k, resid_in, resid_out, norm_w, eps, norm_out, t=None):
+        t = resid_in.shape[0] if t is None else t
+        self._chk(self.lib.cts_reduce_residual_rmsnorm(self.h, _p(partial), split_k, _p(resid_in), _p(resid_out), _p(norm_w),
+                                                       float(eps), _p(norm_out), t, resid_in.shape[-1],
+                                                       dtype_code(resid_in.dtype), _stream()))
+
+    def reduce_swiglu(self, partial, split_k, t, inter, out):
+        self._chk(self.lib.cts_reduce_swiglu(self.h, _p(partial), split_k, t, inter, _p(out), dtype_code(out.dtype), _stream()))
+
+    def qkv_rope_cache(self, src, src_is_partial, split_k, bias, positions, cos, sin, slot_map, q_out, k_cache, v_cache,
+                       k_out, v_out, t, nh, nkv, head_dim, page_size):
+        self._chk(self.lib.cts_qkv_rope_cache(self.h, _p(src), int(src_is_partial), split_k, _p(bias), _p(positions), _p(cos),
+                                              _p(sin), _p(slot_map), _p(q_out), _p(k_cache), _p(v_cache), _p(k_out), _p(v_out),
+                                              t, nh, nkv, head_dim, page_size, dtype_code(q_out.dtype), _stream()))
+
+    def embed_gather(self, table, ids, out, t=None):
+        t = ids.shape[0] if t is None else t
+        self._chk(self.lib.cts_embed_gather(self.h, _p(table), _p(ids), _p(out), t, table.shape[1], table.shape[0],
+                                            dtype_code(table.dtype), _stream()))
+
+    # ------------------------------------------------------------------ attention
+    def attn_prefill(self, q, k, v, cu_seqlens, batch, max_seqlen, nh, nkv, head_dim, scale, out):
+        self._chk(self.lib.cts_attn_prefill(self.h, _p(q), _p(k), _p(v), _p(cu_seqlens), batch, max_seqlen, nh, nkv, head_dim,
+                                            float(scale), _p(out), dtype_code(q.dtype), _stream()))
+
+    def attn_decode_workspace_floats(self, batch, nh, head_dim, num_splits):
+        return int(self.lib.cts_attn_decode_workspace_floats(batch, nh, head_dim, num_splits))
+
+    def attn_decode(self, q, k_cache, v_cache, page_table, seq_lens, batch, nh, nkv, head_dim, page_size, scale, num_splits,
+                    workspace, out):
+        self._chk(self.lib.cts_attn_decode(self.h, _p(q), _p(k_cache), _p(v_cache), _p(page_table), page_table.shape[1],
+                                           _p(seq_lens), batch, nh, nkv, head_dim, page_size, float(scale), num_splits,
+                                           _p(workspace), _p(out), dtype_code(q.dtype), _stream()))
+
+    def greedy_advance(self, logits, batch, out_tokens, step_ptr, cur_ids, positions, seq_lens, slot_map, page_table,
+                       page_size):
+        self._chk(self.lib.cts_greedy_advance(self.h, _p(logits), logits.shape[-1], batch, _p(out_tokens),
+                                              out_tokens.stride(0) if out_tokens is not None else 0, _p(step_ptr), _p(cur_ids),
+                                              _p(positions), _p(seq_lens), _p(slot_map), _p(page_table),
+                                              page_table.shape[1] if page_table is not None else 0, page_size,
+                                              dtype_code(logits.dtype), _stream()))
+
+
+_ctx_cache = {}
+
+
+def get_context(device=None):
+    dev = torch.cuda.current_device() if device is None else (torch.device(device).index or 0)
+    if dev not in _ctx_cache:
+        with torch.cuda.device(dev):
+            _ctx_cache[dev] = Context(dev)
+    return _ctx_cache[dev]

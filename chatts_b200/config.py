@@ -1,0 +1,92 @@
+"""Model configuration, read from the checkpoint's config.json (never hard-coded: SURVEY.md §2.2 dagger).
+
+Mirrors what the reference reads: ``config.ts[...]`` and ``config.ts_token_start_index``
+(chatts/vllm/chatts_vllm.py:64-71,376,384,441) on top of the stock Qwen2 fields."""
+import json
+import os
+from dataclasses import dataclass, field, asdict
+
+
+def _default_ts():
+    return dict(patch_size=16, num_layers=5, hidden_size=5120, num_features=2, max_sequence_length=4096,
+                use_position_embedding=True, use_position_idx=False, embedding_dim=16)
+
+
+@dataclass
+class ChatTSConfig:
+    hidden_size: int = 5120
+    intermediate_size: int = 13824
+    num_hidden_layers: int = 48
+    num_attention_heads: int = 40
+    num_key_value_heads: int = 8
+    head_dim: int = 128
+    vocab_size: int = 152064
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1e6
+    max_position_embeddings: int = 32768
+    tie_word_embeddings: bool = False
+    ts: dict = field(default_factory=_default_ts)
+    ts_token_start_index: int = 151665          # <ts>; <ts/> = +1 (chatts_vllm.py:441)
+    eos_token_id: int = 151645                  # stop ids 151643/151645 (chatts/utils/llm_utils.py:153)
+    pad_token_id: int = 151643
+    model_type: str = "chatts"                  # scripts/start_vllm_server.sh:5
+    torch_dtype: str = "bfloat16"
+
+    @property
+    def ts_token_end_index(self):
+        return self.ts_token_start_index + 1
+
+    @classmethod
+    def chatts_14b(cls):
+        """Public Qwen2.5-14B shape + the TS encoder of the released ChatTS-14B (UNVERIFIED offline; a real
+        checkpoint's config.json overrides every field through from_json)."""
+        return cls()
+
+    @classmethod
+    def tiny(cls, **kw):
+        """Small shape for parity tests (head_dim 64, GQA 2:1, ragged K/N on purpose)."""
+        d = dict(hidden_size=256, intermediate_size=704, num_hidden_layers=2, num_attention_heads=4,
+                 num_key_value_heads=2, head_dim=64, vocab_size=1000, max_position_embeddings=2048,
+                 ts=dict(patch_size=16, num_layers=3, hidden_size=256, num_features=2, max_sequence_length=512,
+                         use_position_embedding=True, use_position_idx=False, embedding_dim=16),
+                 ts_token_start_index=990, eos_token_id=998, pad_token_id=999)
+        d.update(kw)
+        return cls(**d)
+
+    @classmethod
+    def from_dict(cls, d):
+        known = {k: d[k] for k in cls.__dataclass_fields__ if k in d}
+        cfg = cls(**known)
+        if "head_dim" not in d or d.get("head_dim") is None:
+            cfg.head_dim = cfg.hidden_size // cfg.num_attention_heads
+        if "rope_parameters" in d and isinstance(d["rope_parameters"], dict):
+            cfg.rope_theta = d["rope_parameters"].get("rope_theta", cfg.rope_theta)
+        if isinstance(cfg.eos_token_id, (list, tuple)):
+            cfg.eos_token_id = int(cfg.eos_token_id[0])
+        return cfg
+
+    @classmethod
+    def from_json(cls, path):
+        if os.path.isdir(path):
+            path = os.path.join(path, "config.json")
+        with open(path) as f:
+            return cls.from_dict(json.load(f))
+
+    def to_dict(self):
+        return asdict(self)
+
+    def ts_input_size(self):
+        """chatts_vllm.py:73-81."""
+        p = self.ts["patch_size"]
+        if self.ts.get("use_position_embedding", False):
+            return p + self.ts.get("embedding_dim", 16) * p
+        if self.ts.get("use_position_idx", False):
+            return 2 * p
+        return p
+
+    def ts_mode(self):
+        if self.ts.get("use_position_embedding", False):
+            return 1
+        if self.ts.get("use_position_idx", False):
+            return 2
+        return 0

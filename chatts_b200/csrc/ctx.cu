@@ -1,0 +1,92 @@
+// chatts_b200 -- context, error reporting, TMA descriptor encoding.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tensormap.cuh"
+
+int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+extern "C" int cts_version(void) { return 100; }
+
+extern "C" const char* cts_arch(void) {
+#if defined(CTS_BUILD_ARCH)
+  return CTS_BUILD_ARCH;
+#else
+  return "unknown";
+#endif
+}
+
+extern "C" int cts_ctx_create(int device, cts_ctx** out) {
+  if (!out) return CTS_ERR_BAD_ARG;
+  *out = nullptr;
+  cts_ctx* ctx = (cts_ctx*)calloc(1, sizeof(cts_ctx));
+  if (!ctx) return CTS_ERR_CUDA;
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "chatts_b200: cudaSetDevice(%d) failed: %s\n", device, cudaGetErrorString(e));
+    free(ctx);
+    return CTS_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    free(ctx);
+    return CTS_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    fprintf(stderr, "chatts_b200: device %d is sm_%d%d; this library contains sm_100a code only\n", device, prop.major,
+            prop.minor);
+    free(ctx);
+    return CTS_ERR_UNSUPPORTED;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  // cuTensorMapEncodeTiled comes from the driver; resolve it at run time so the library does not link
+  // libcuda (the build container has no driver).
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    fprintf(stderr, "chatts_b200: cannot resolve cuTensorMapEncodeTiled\n");
+    free(ctx);
+    return CTS_ERR_CUDA;
+  }
+  ctx->encode_tiled = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  *out = ctx;
+  return CTS_OK;
+}
+
+extern "C" void cts_ctx_destroy(cts_ctx* ctx) {
+  if (!ctx) return;
+  free(ctx);
+}
+
+extern "C" const char* cts_last_error(const cts_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+// 2-D row-major [rows, cols] tensor of 2-byte elements, box = [box_rows, 64 cols] (128 bytes), 128B swizzle.
+int cts_make_tmap_2d(cts_ctx* ctx, CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld_elems,
+                     int box_rows, int is_bf16) {
+  if (((uintptr_t)base & 15) != 0) return cts_set_error(ctx, CTS_ERR_BAD_ARG, "tensor map: base not 16-byte aligned");
+  if ((ld_elems * 2) % 16 != 0) return cts_set_error(ctx, CTS_ERR_BAD_ARG, "tensor map: row pitch %lld B not a multiple of 16", ld_elems * 2);
+  if (box_rows < 1 || box_rows > 256) return cts_set_error(ctx, CTS_ERR_BAD_ARG, "tensor map: box rows %d", box_rows);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld_elems * 2)};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = ctx->encode_tiled(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                                 const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cts_set_error(ctx, CTS_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+  return CTS_OK;
+}

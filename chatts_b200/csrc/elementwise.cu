@@ -1,0 +1,409 @@
+// chatts_b200 -- the memory-bound glue of the decoder, each fused with the split-K reduction of the GEMM
+// that precedes it so that no projection result makes an extra HBM round trip:
+//   cts_reduce_bias_act          TS-MLP layer tail: sum partials + bias (+ exact-erf GELU), optional row scatter
+//   cts_reduce_residual_rmsnorm  o_proj / down_proj tail: sum partials + residual add + next RMSNorm
+//   cts_reduce_swiglu            gate_up tail (when gate_up ran split-K)
+//   cts_qkv_rope_cache           QKV tail: sum partials + bias + RoPE + paged KV-cache write
+//   cts_embed_gather             token embedding lookup (rows of <ts> patches are skipped: the encoder scatters them)
+//   cts_greedy_advance           argmax + device-side decode bookkeeping (graph-replayable decode loop)
+// Rounding points follow transformers' Qwen2 in the model dtype (modeling_qwen2.py line numbers in the header).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void reduce_bias_act_kernel(const float* __restrict__ part, int S, long long t_total, long long n,
+                                       const T* __restrict__ bias, int act, T* __restrict__ out, long long out_ld,
+                                       const int* __restrict__ row_map) {
+  const long long t = blockIdx.y;
+  long long row = t;
+  if (row_map) {
+    row = row_map[t];
+    if (row < 0) return;
+  }
+  const long long col4 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (col4 >= n) return;
+  const long long stride = t_total * n;
+  const float* p = part + t * n + col4;
+  if (col4 + 3 < n && (n & 3) == 0) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    for (int s = 1; s < S; ++s) {
+      float4 b = *reinterpret_cast<const float4*>(p + s * stride);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r = v[j] + (bias ? DT<T>::to_f(bias[col4 + j]) : 0.f);
+      if (act == CTS_EPI_GELU) r = gelu_erf(rnd<T>(r));
+      out[row * out_ld + col4 + j] = DT<T>::from_f(r);
+    }
+  } else {
+    for (int j = 0; j < 4 && col4 + j < n; ++j) {
+      float a = p[j];
+      for (int s = 1; s < S; ++s) a += p[j + s * stride];
+      float r = a + (bias ? DT<T>::to_f(bias[col4 + j]) : 0.f);
+      if (act == CTS_EPI_GELU) r = gelu_erf(rnd<T>(r));
+      out[row * out_ld + col4 + j] = DT<T>::from_f(r);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one CTA per token; H elements kept in registers between the two passes (H <= 8 * 8 * blockDim)
+constexpr int kNormThreads = 256;
+constexpr int kNormMaxVec = 8;   // up to 8 x 8 elements per thread -> H <= 16384
+
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+reduce_residual_rmsnorm_kernel(const float* __restrict__ part, int S, const T* __restrict__ resid_in,
+                               T* __restrict__ resid_out, const T* __restrict__ norm_w, float eps,
+                               T* __restrict__ norm_out, long long t_total, int h) {
+  const long long t = blockIdx.x;
+  const int nvec = h / 8;
+  float vals[kNormMaxVec][8];
+  float ss = 0.f;
+  const long long stride = t_total * (long long)h;
+#pragma unroll
+  for (int it = 0; it < kNormMaxVec; ++it) {
+    const int v = it * kNormThreads + threadIdx.x;
+    if (v < nvec) {
+      float r[8];
+      unpack8<T>(*reinterpret_cast<const uint4*>(resid_in + t * h + (long long)v * 8), r);
+      if (S > 0) {
+        float a[8];
+        const float* p = part + t * h + (long long)v * 8;
+        float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
+        a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+        for (int s = 1; s < S; ++s) {
+          lo = *reinterpret_cast<const float4*>(p + s * stride);
+          hi = *reinterpret_cast<const float4*>(p + s * stride + 4);
+          a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w; a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = rnd<T>(r[j] + rnd<T>(a[j]));   // residual + dtype(proj)  (:302,:308)
+        if (resid_out) *reinterpret_cast<uint4*>(resid_out + t * h + (long long)v * 8) = pack8<T>(r);
+      } else if (resid_out && resid_out != resid_in) {
+        *reinterpret_cast<uint4*>(resid_out + t * h + (long long)v * 8) = pack8<T>(r);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { vals[it][j] = r[j]; ss += r[j] * r[j]; }
+    }
+  }
+  if (norm_out == nullptr) return;
+  __shared__ float red[kNormThreads / 32];
+  __shared__ float inv_s;
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < kNormThreads / 32 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) inv_s = 1.0f / sqrtf(v / (float)h + eps);   // rsqrt(mean(x^2)+eps)  (:261-262)
+  }
+  __syncthreads();
+  const float inv = inv_s;
+#pragma unroll
+  for (int it = 0; it < kNormMaxVec; ++it) {
+    const int v = it * kNormThreads + threadIdx.x;
+    if (v < nvec) {
+      float w[8], o[8];
+      unpack8<T>(*reinterpret_cast<const uint4*>(norm_w + (long long)v * 8), w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = w[j] * rnd<T>(vals[it][j] * inv);   // weight * x.to(dtype)  (:263)
+      *reinterpret_cast<uint4*>(norm_out + t * h + (long long)v * 8) = pack8<T>(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void reduce_swiglu_kernel(const float* __restrict__ part, int S, long long t_total, long long inter,
+                                     T* __restrict__ out) {
+  const long long t = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= inter) return;
+  const long long n = 2 * inter;
+  float g = 0.f, u = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const float* p = part + ((long long)s * t_total + t) * n;
+    g += p[i];
+    u += p[inter + i];
+  }
+  const float r = rnd<T>(silu_f(rnd<T>(g))) * rnd<T>(u);
+  out[t * inter + i] = DT<T>::from_f(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid (heads_total = nh + 2*nkv, T); block = head_dim/2 threads: thread i owns dims i and i + d/2 (the
+// rotate_half pair, modeling_qwen2.py:116-120,141-145).
+template <typename T>
+__global__ void qkv_rope_cache_kernel(const void* __restrict__ src, int src_is_partial, int S, const T* __restrict__ bias,
+                                      const int* __restrict__ positions, const T* __restrict__ cos_tab,
+                                      const T* __restrict__ sin_tab, const int* __restrict__ slot_map,
+                                      T* __restrict__ q_out, T* __restrict__ k_cache, T* __restrict__ v_cache,
+                                      T* __restrict__ k_out, T* __restrict__ v_out, long long t_total, int nh, int nkv,
+                                      int d, int page_size) {
+  const int head = blockIdx.x;
+  const long long t = blockIdx.y;
+  const int half = d >> 1;
+  const int i = threadIdx.x;
+  if (i >= half) return;
+  const long long width = (long long)(nh + 2 * nkv) * d;
+  const long long c0 = (long long)head * d + i, c1 = c0 + half;
+  float x0, x1;
+  if (src_is_partial) {
+    const float* p = reinterpret_cast<const float*>(src) + t * width;
+    const long long stride = t_total * width;
+    x0 = p[c0]; x1 = p[c1];
+    for (int s = 1; s < S; ++s) { x0 += p[c0 + s * stride]; x1 += p[c1 + s * stride]; }
+    if (bias) { x0 += DT<T>::to_f(bias[c0]); x1 += DT<T>::to_f(bias[c1]); }
+    x0 = rnd<T>(x0); x1 = rnd<T>(x1);                 // nn.Linear output in the model dtype
+  } else {
+    const T* p = reinterpret_cast<const T*>(src) + t * width;
+    x0 = DT<T>::to_f(p[c0]); x1 = DT<T>::to_f(p[c1]);
+  }
+  const bool is_q = head < nh;
+  const bool is_k = !is_q && head < nh + nkv;
+  if (is_q || is_k) {
+    const int pos = positions[t];
+    // cos/sin are [max_pos, d/2]: emb = cat(freqs, freqs) (:110) makes both halves share the same angle
+    const float c = DT<T>::to_f(cos_tab[(long long)pos * half + i]);
+    const float s = DT<T>::to_f(sin_tab[(long long)pos * half + i]);
+    // q_embed = (q * cos) + (rotate_half(q) * sin), every product and the sum rounded to dtype (:144)
+    const float r0 = rnd<T>(rnd<T>(x0 * c) + rnd<T>(-x1 * s));
+    const float r1 = rnd<T>(rnd<T>(x1 * c) + rnd<T>(x0 * s));
+    x0 = r0; x1 = r1;
+  }
+  if (is_q) {
+    T* o = q_out + t * (long long)nh * d + (long long)head * d;
+    o[i] = DT<T>::from_f(x0);
+    o[i + half] = DT<T>::from_f(x1);
+    return;
+  }
+  const int kvh = is_k ? head - nh : head - nh - nkv;
+  T* lin = is_k ? k_out : v_out;
+  if (lin) {
+    T* o = lin + t * (long long)nkv * d + (long long)kvh * d;
+    o[i] = DT<T>::from_f(x0);
+    o[i + half] = DT<T>::from_f(x1);
+  }
+  T* cache = is_k ? k_cache : v_cache;
+  if (cache && slot_map) {
+    const int slot = slot_map[t];
+    if (slot >= 0) {
+      const long long page = slot / page_size, off = slot % page_size;
+      T* o = cache + ((page * nkv + kvh) * page_size + off) * d;     // [num_pages, nkv, page_size, d]
+      o[i] = DT<T>::from_f(x0);
+      o[i + half] = DT<T>::from_f(x1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void embed_gather_kernel(const T* __restrict__ table, const int* __restrict__ ids, T* __restrict__ out,
+                                    long long h, long long vocab) {
+  const long long t = blockIdx.x;
+  const int id = ids[t];
+  if (id < 0 || id >= vocab) return;
+  const uint4* src = reinterpret_cast<const uint4*>(table + (long long)id * h);
+  uint4* dst = reinterpret_cast<uint4*>(out + t * h);
+  for (int v = threadIdx.x; v < h / 8; v += blockDim.x) dst[v] = __ldg(src + v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one CTA per sequence: argmax over the vocabulary (first maximum wins, like torch.argmax), then advance
+template <typename T>
+__global__ void __launch_bounds__(1024)
+greedy_advance_kernel(const T* __restrict__ logits, long long vocab, int* __restrict__ out_tokens, int out_ld,
+                      const int* __restrict__ step_ptr, int* __restrict__ cur_ids, int* __restrict__ positions,
+                      int* __restrict__ seq_lens, int* __restrict__ slot_map, const int* __restrict__ page_table,
+                      int max_pages, int page_size) {
+  const int b = blockIdx.x;
+  const T* row = logits + (long long)b * vocab;
+  float best = -INFINITY;
+  long long best_i = vocab;
+  if ((vocab & 7) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    const uint4* v = reinterpret_cast<const uint4*>(row);
+    for (long long i = threadIdx.x; i < vocab / 8; i += blockDim.x) {
+      float f[8];
+      unpack8<T>(__ldg(v + i), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        // NaN never wins; ties keep the smaller index
+        if (f[j] > best) { best = f[j]; best_i = i * 8 + j; }
+      }
+    }
+  } else {
+    for (long long i = threadIdx.x; i < vocab; i += blockDim.x) {
+      const float f = DT<T>::to_f(row[i]);
+      if (f > best) { best = f; best_i = i; }
+    }
+  }
+  // warp then block argmax (value desc, index asc)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  __shared__ float sb[32];
+  __shared__ long long si[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sb[warp] = best; si[warp] = best_i; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    best = lane < nw ? sb[lane] : -INFINITY;
+    best_i = lane < nw ? si[lane] : vocab;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    if (lane == 0) {
+      const int tok = best_i < vocab ? (int)best_i : 0;
+      const int step = step_ptr ? step_ptr[0] : 0;
+      if (out_tokens) out_tokens[(long long)b * out_ld + step] = tok;
+      if (cur_ids) cur_ids[b] = tok;
+      if (positions) {
+        const int np = positions[b] + 1;
+        positions[b] = np;
+        if (seq_lens) seq_lens[b] = seq_lens[b] + 1;
+        if (slot_map && page_table) {
+          const int pg = np / page_size;
+          slot_map[b] = pg < max_pages ? page_table[(long long)b * max_pages + pg] * page_size + np % page_size : -1;
+        }
+      }
+    }
+  }
+}
+
+__global__ void step_increment_kernel(int* step_ptr) { step_ptr[0] += 1; }
+
+}  // namespace
+
+#define DISPATCH_T(dtype, ...)                      \
+  if ((dtype) == CTS_BF16) {                        \
+    using T = __nv_bfloat16;                        \
+    __VA_ARGS__;                                    \
+  } else {                                          \
+    using T = __half;                               \
+    __VA_ARGS__;                                    \
+  }
+
+extern "C" int cts_reduce_bias_act(cts_ctx* ctx, const float* partial, int split_k, long long t, long long n,
+                                   const void* bias, int act, void* out, long long out_ld, const int* row_map, int dtype,
+                                   void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, partial && out, "null partial / out");
+  CTS_CHECK_ARG(ctx, split_k >= 1 && t >= 0 && n > 0, "sizes");
+  CTS_CHECK_ARG(ctx, act == CTS_EPI_NONE || act == CTS_EPI_GELU, "act must be CTS_EPI_NONE or CTS_EPI_GELU");
+  CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
+  CTS_CHECK_ARG(ctx, t <= 65535, "t > 65535 (use the fused GEMM epilogue for large t)");
+  if (t == 0) return CTS_OK;
+  const int threads = 128;
+  dim3 grid((unsigned)cdiv_ll(cdiv_ll(n, 4), threads), (unsigned)t);
+  DISPATCH_T(dtype, reduce_bias_act_kernel<T><<<grid, threads, 0, (cudaStream_t)stream>>>(
+                        partial, split_k, t, n, (const T*)bias, act, (T*)out, out_ld, row_map));
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+extern "C" int cts_reduce_residual_rmsnorm(cts_ctx* ctx, const float* partial, int split_k, const void* resid_in,
+                                           void* resid_out, const void* norm_w, float eps, void* norm_out, long long t,
+                                           long long h, int dtype, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, resid_in != nullptr, "null resid_in");
+  CTS_CHECK_ARG(ctx, (partial == nullptr) == (split_k == 0), "partial / split_k mismatch");
+  CTS_CHECK_ARG(ctx, (norm_w == nullptr) == (norm_out == nullptr), "norm_w / norm_out mismatch");
+  CTS_CHECK_ARG(ctx, h > 0 && h % 8 == 0 && h <= 8LL * kNormMaxVec * kNormThreads, "h must be a multiple of 8 and <= 16384");
+  CTS_CHECK_ARG(ctx, split_k == 0 || resid_out != nullptr, "resid_out required when reducing partials");
+  CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
+  if (t == 0) return CTS_OK;
+  DISPATCH_T(dtype, reduce_residual_rmsnorm_kernel<T><<<(unsigned)t, kNormThreads, 0, (cudaStream_t)stream>>>(
+                        partial, split_k, (const T*)resid_in, (T*)resid_out, (const T*)norm_w, eps, (T*)norm_out, t, (int)h));
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+extern "C" int cts_reduce_swiglu(cts_ctx* ctx, const float* partial, int split_k, long long t, long long inter, void* out,
+                                 int dtype, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, partial && out && split_k >= 1 && inter > 0, "args");
+  CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
+  CTS_CHECK_ARG(ctx, t <= 65535, "t > 65535");
+  if (t == 0) return CTS_OK;
+  dim3 grid((unsigned)cdiv_ll(inter, 256), (unsigned)t);
+  DISPATCH_T(dtype, reduce_swiglu_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(partial, split_k, t, inter, (T*)out));
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+extern "C" int cts_qkv_rope_cache(cts_ctx* ctx, const void* src, int src_is_partial, int split_k, const void* bias,
+                                  const int* positions, const void* cos_tab, const void* sin_tab, const int* slot_map,
+                                  void* q_out, void* k_cache, void* v_cache, void* k_out, void* v_out, long long t, int nh,
+                                  int nkv, int head_dim, int page_size, int dtype, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, src && positions && cos_tab && sin_tab && q_out, "null pointer");
+  CTS_CHECK_ARG(ctx, nh > 0 && nkv > 0 && head_dim > 0 && head_dim % 2 == 0 && head_dim <= 512, "head config");
+  CTS_CHECK_ARG(ctx, !src_is_partial || split_k >= 1, "split_k");
+  CTS_CHECK_ARG(ctx, page_size > 0, "page_size");
+  CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
+  CTS_CHECK_ARG(ctx, t <= 65535 * 1024LL, "t too large");
+  if (t == 0) return CTS_OK;
+  // t can exceed 65535 in a big prefill: fold into chunks of the y grid dimension
+  const long long width = (long long)(nh + 2 * nkv) * head_dim;
+  const int threads = ((head_dim / 2 + 31) / 32) * 32;
+  for (long long tb = 0; tb < t; tb += 65535) {
+    const long long tc = (t - tb) < 65535 ? (t - tb) : 65535;
+    dim3 grid((unsigned)(nh + 2 * nkv), (unsigned)tc);
+    if (src_is_partial) {
+      CTS_CHECK_ARG(ctx, t <= 65535, "partial input with t > 65535");
+    }
+    const void* src_c = src_is_partial ? src : (const void*)((const char*)src + tb * width * 2);
+    DISPATCH_T(dtype,
+               qkv_rope_cache_kernel<T><<<grid, threads, 0, (cudaStream_t)stream>>>(
+                   src_c, src_is_partial, split_k, (const T*)bias, positions + tb, (const T*)cos_tab, (const T*)sin_tab,
+                   slot_map ? slot_map + tb : nullptr, (T*)q_out + tb * (long long)nh * head_dim, (T*)k_cache, (T*)v_cache,
+                   k_out ? (T*)k_out + tb * (long long)nkv * head_dim : nullptr,
+                   v_out ? (T*)v_out + tb * (long long)nkv * head_dim : nullptr, src_is_partial ? t : tc, nh, nkv, head_dim,
+                   page_size));
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  return CTS_OK;
+}
+
+extern "C" int cts_embed_gather(cts_ctx* ctx, const void* table, const int* ids, void* out, long long t, long long h,
+                                long long vocab, int dtype, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, table && ids && out, "null pointer");
+  CTS_CHECK_ARG(ctx, h > 0 && h % 8 == 0, "h must be a multiple of 8");
+  CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
+  if (t == 0) return CTS_OK;
+  DISPATCH_T(dtype, embed_gather_kernel<T><<<(unsigned)t, 128, 0, (cudaStream_t)stream>>>((const T*)table, ids, (T*)out, h, vocab));
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+extern "C" int cts_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab, int batch, int* out_tokens, int out_ld,
+                                  int* step_ptr, int* cur_ids, int* positions, int* seq_lens, int* slot_map,
+                                  const int* page_table, int max_pages, int page_size, int dtype, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, logits && vocab > 0 && batch >= 0, "args");
+  CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
+  CTS_CHECK_ARG(ctx, page_size > 0 || slot_map == nullptr, "page_size");
+  if (batch == 0) return CTS_OK;
+  DISPATCH_T(dtype, greedy_advance_kernel<T><<<batch, 1024, 0, (cudaStream_t)stream>>>(
+                        (const T*)logits, vocab, out_tokens, out_ld, step_ptr, cur_ids, positions, seq_lens, slot_map,
+                        page_table, max_pages, page_size > 0 ? page_size : 1));
+  CTS_LAUNCH_CHECK(ctx);
+  if (step_ptr) {
+    step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr);
+    CTS_LAUNCH_CHECK(ctx);
+  }
+  return CTS_OK;
+}

@@ -1,0 +1,283 @@
+// chatts_b200 -- weight-streaming tcgen05 GEMM:  Y[T,N] = X[T,K] * W[N,K]^T  (+ fused epilogues)
+//
+// Replaces every nn.Linear on the ChatTS hot path: the TS-encoder MLP (chatts/vllm/chatts_vllm.py:83-91,188)
+// and the Qwen2 projections / lm_head the reference reaches through transformers / vLLM
+// (modeling_qwen2.py:44-48,217-219,245; chatts_vllm.py:595-610).
+//
+// B200-first design ("swap-AB"): the WEIGHT tile is the 128-row MMA operand A (K-major, streamed once from
+// HBM by TMA with an evict-first hint), the TOKENS are the MMA N dimension (operand B, K-major, L2 resident,
+// evict-last).  A decode batch of 1..32 tokens therefore still issues full M=128 tcgen05.mma instructions
+// and the kernel is bound by the HBM stream of W; a prefill of thousands of tokens uses N=256 tiles of the
+// same kernel.  Accumulators live in TMEM (lane = output feature, column = token); the epilogue warps read
+// them with tcgen05.ld and fuse bias / GELU / SwiGLU / residual / split-K partial stores / row scatter.
+//
+//   warp 0      : TMA producer (one elected lane), mbarrier full/empty ring of `stages` slots
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit frees slots
+//   warps 2..5  : epilogue, warp w owns TMEM lanes 32*(w%4) .. +31
+//
+// grid = (ceil(N/128), ceil(T/BN), split_k).
+#include <type_traits>
+
+#include "common.cuh"
+#include "tensormap.cuh"
+
+namespace {
+
+constexpr int kBM = 128;        // weight rows per tile == UMMA M
+constexpr int kBK = 64;         // K elements per stage == 128 bytes == one 128B-swizzle atom
+constexpr int kUmmaK = 16;      // K per tcgen05.mma for 16-bit inputs
+constexpr int kMaxStages = 12;
+constexpr int kThreads = 192;
+
+struct GemmParams {
+  long long n, k, t, out_ld;
+  const void* bias;
+  const void* residual;
+  void* out;
+  const int* row_map;
+  int kb_total;
+  int split_k;
+  int stages;
+  int epilogue;
+};
+
+template <int BN, bool DUAL> __host__ __device__ constexpr int stage_bytes() { return kBM * kBK * 2 * (DUAL ? 2 : 1) + BN * kBK * 2; }
+template <int BN, bool DUAL> __host__ __device__ constexpr int tmem_cols() {
+  int c = BN * (DUAL ? 2 : 1);
+  return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
+}
+
+template <typename T, int BN, bool DUAL>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w2,
+               const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t acc_bar;
+  __shared__ uint32_t tmem_slot;
+
+  constexpr int kStage = stage_bytes<BN, DUAL>();
+  constexpr int kABytes = kBM * kBK * 2;
+  constexpr int kCols = tmem_cols<BN, DUAL>();
+  constexpr bool kIsBf16 = std::is_same<T, __nv_bfloat16>::value;
+
+  // 128B-swizzled tiles need a 1024-byte aligned base
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int f0 = blockIdx.x * kBM;
+  const int t0 = blockIdx.y * BN;
+  const int split = blockIdx.z;
+  const int stages = p.stages;
+
+  // this CTA's K range, in 64-element blocks
+  const int kb0 = (int)(((long long)p.kb_total * split) / p.split_k);
+  const int kb1 = (int)(((long long)p.kb_total * (split + 1)) / p.split_k);
+  const int nkb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_x);
+    if (DUAL) tma_prefetch_desc(&tm_w2);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kCols>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], (uint32_t)kStage);
+        uint8_t* st = smem + (size_t)s * kStage;
+        const int kc = (kb0 + i) * kBK;
+        tma_load_2d(st, &tm_w, &full_bar[s], kc, f0, CTS_L2_EVICT_FIRST);
+        if (DUAL) tma_load_2d(st + kABytes, &tm_w2, &full_bar[s], kc, f0, CTS_L2_EVICT_FIRST);
+        tma_load_2d(st + kABytes * (DUAL ? 2 : 1), &tm_x, &full_bar[s], kc, t0, CTS_L2_EVICT_LAST);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kIsBf16 ? 1 : 0, BN, kBM);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % stages;
+        const uint32_t ph = (uint32_t)(i / stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * kStage);
+        const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+        const uint64_t a2_desc = umma_desc_k_sw128(a_addr + kABytes);
+        const uint64_t b_desc = umma_desc_k_sw128(a_addr + kABytes * (DUAL ? 2 : 1));
+#pragma unroll
+        for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+          // advance 16 elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
+          const uint64_t adv = (uint64_t)(kk * ((kUmmaK * 2) >> 4));
+          const uint32_t acc = (i > 0 || kk > 0) ? 1u : 0u;
+          umma_f16(tmem_base, a_desc + adv, b_desc + adv, idesc, acc);
+          if (DUAL) umma_f16(tmem_base + BN, a2_desc + adv, b_desc + adv, idesc, acc);
+        }
+        umma_commit(&empty_bar[s]);   // slot reusable once these MMAs have read it
+      }
+      umma_commit(&acc_bar);          // accumulator complete
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const long long f = (long long)f0 + q * 32 + lane;
+    const bool f_ok = f < p.n;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float bias = 0.f;
+    if (p.bias != nullptr && f_ok) bias = DT<T>::to_f(reinterpret_cast<const T*>(p.bias)[f]);
+    const int epi = p.epilogue;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      if ((long long)t0 + c >= p.t) break;   // warp-uniform
+      uint32_t v[16], v2[16];
+      tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+      if (DUAL) tmem_ld_32x32b_x16(lane_addr + (uint32_t)(BN + c), v2);
+      tmem_ld_wait();
+      if (nkb == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v[j] = 0u; v2[j] = 0u; }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const long long t = (long long)t0 + c + j;
+        if (t >= p.t || !f_ok) continue;
+        const float acc = __uint_as_float(v[j]);
+        if (epi == CTS_EPI_PARTIAL_F32) {
+          reinterpret_cast<float*>(p.out)[((long long)split * p.t + t) * p.n + f] = acc;
+          continue;
+        }
+        long long row = t;
+        if (p.row_map != nullptr) {
+          row = p.row_map[t];
+          if (row < 0) continue;
+        }
+        float r;
+        if (epi == CTS_EPI_SWIGLU) {
+          const float g = rnd<T>(acc);
+          const float u = rnd<T>(__uint_as_float(v2[j]));
+          r = rnd<T>(silu_f(g)) * u;
+        } else {
+          r = acc + bias;
+          if (epi == CTS_EPI_GELU) {
+            r = gelu_erf(rnd<T>(r));
+          } else if (epi == CTS_EPI_RESIDUAL) {
+            r = rnd<T>(r) + DT<T>::to_f(reinterpret_cast<const T*>(p.residual)[row * p.out_ld + f]);
+          }
+        }
+        reinterpret_cast<T*>(p.out)[row * p.out_ld + f] = DT<T>::from_f(r);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kCols>(tmem_base);
+}
+
+template <typename T, int BN, bool DUAL>
+int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
+  const bool is_bf16 = a->dtype == CTS_BF16;
+  CUtensorMap tm_w, tm_w2, tm_x;
+  int rc = cts_make_tmap_2d(ctx, &tm_w, a->w, a->n, a->k, a->w_ld, kBM, is_bf16);
+  if (rc) return rc;
+  if (DUAL) {
+    rc = cts_make_tmap_2d(ctx, &tm_w2, a->w2, a->n, a->k, a->w_ld, kBM, is_bf16);
+    if (rc) return rc;
+  } else {
+    tm_w2 = tm_w;
+  }
+  rc = cts_make_tmap_2d(ctx, &tm_x, a->x, a->t, a->k, a->x_ld, BN, is_bf16);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.n = a->n; p.k = a->k; p.t = a->t; p.out_ld = a->out_ld;
+  p.bias = a->bias; p.residual = a->residual; p.out = a->out; p.row_map = a->row_map;
+  p.kb_total = (int)cdiv_ll(a->k, kBK);
+  p.split_k = a->split_k;
+  p.epilogue = a->epilogue;
+  constexpr int kStage = stage_bytes<BN, DUAL>();
+  // small-N (decode) tiles: leave room for two CTAs per SM so one CTA's prologue/epilogue overlaps the
+  // other's stream; large-N (prefill) tiles take the whole SM.
+  const int budget = (BN <= 32) ? 100 * 1024 : 200 * 1024;
+  int stages = budget / kStage;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * kStage + 1024;
+  auto kern = gemm_tn_kernel<T, BN, DUAL>;
+  CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)cdiv_ll(a->n, kBM), (unsigned)cdiv_ll(a->t, BN), (unsigned)a->split_k);
+  kern<<<grid, kThreads, smem, stream>>>(tm_w, tm_w2, tm_x, p);
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}
+
+template <typename T, bool DUAL>
+int dispatch_bn(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
+  const long long t = a->t;
+  if (t <= 16) return launch<T, 16, DUAL>(ctx, a, stream);
+  if (t <= 32) return launch<T, 32, DUAL>(ctx, a, stream);
+  if (t <= 64) return launch<T, 64, DUAL>(ctx, a, stream);
+  if (t <= 128) return launch<T, 128, DUAL>(ctx, a, stream);
+  return launch<T, 256, DUAL>(ctx, a, stream);
+}
+
+}  // namespace
+
+extern "C" int cts_gemm(cts_ctx* ctx, const cts_gemm_args* a, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, a != nullptr, "null args");
+  CTS_CHECK_ARG(ctx, a->w && a->x && a->out, "null w/x/out");
+  CTS_CHECK_ARG(ctx, a->n > 0 && a->k > 0 && a->t > 0, "n, k, t must be positive");
+  CTS_CHECK_ARG(ctx, a->dtype == CTS_BF16 || a->dtype == CTS_F16, "dtype must be CTS_BF16 or CTS_F16");
+  CTS_CHECK_ARG(ctx, a->epilogue >= CTS_EPI_NONE && a->epilogue <= CTS_EPI_RESIDUAL, "unknown epilogue");
+  CTS_CHECK_ARG(ctx, a->split_k >= 1, "split_k must be >= 1");
+  CTS_CHECK_ARG(ctx, a->split_k == 1 || a->epilogue == CTS_EPI_PARTIAL_F32, "split_k > 1 needs CTS_EPI_PARTIAL_F32");
+  CTS_CHECK_ARG(ctx, a->split_k <= cdiv_ll(a->k, kBK), "split_k exceeds the number of 64-wide K blocks");
+  CTS_CHECK_ARG(ctx, a->split_k <= 65535 && cdiv_ll(a->t, 16) <= 65535 * 16LL, "grid too large");
+  CTS_CHECK_ARG(ctx, (a->epilogue == CTS_EPI_SWIGLU) == (a->w2 != nullptr), "w2 is required by (and only by) CTS_EPI_SWIGLU");
+  CTS_CHECK_ARG(ctx, a->epilogue != CTS_EPI_RESIDUAL || a->residual != nullptr, "CTS_EPI_RESIDUAL needs residual");
+  CTS_CHECK_ARG(ctx, a->w_ld >= a->k && a->x_ld >= a->k, "leading dimension smaller than k");
+  CTS_CHECK_ARG(ctx, a->epilogue == CTS_EPI_PARTIAL_F32 || a->out_ld >= a->n, "out_ld smaller than n");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool dual = a->epilogue == CTS_EPI_SWIGLU;
+  if (a->dtype == CTS_BF16)
+    return dual ? dispatch_bn<__nv_bfloat16, true>(ctx, a, st) : dispatch_bn<__nv_bfloat16, false>(ctx, a, st);
+  return dual ? dispatch_bn<__half, true>(ctx, a, st) : dispatch_bn<__half, false>(ctx, a, st);
+}
+
+extern "C" int cts_gemm_suggest_split(cts_ctx* ctx, long long n, long long k, long long t, int dual) {
+  if (!ctx || n <= 0 || k <= 0 || t <= 0) return 1;
+  const int bn = t <= 16 ? 16 : t <= 32 ? 32 : t <= 64 ? 64 : t <= 128 ? 128 : 256;
+  const long long tiles = cdiv_ll(n, kBM) * cdiv_ll(t, bn);
+  const long long kb = cdiv_ll(k, kBK);
+  const long long slots = (long long)ctx->sm_count * (bn <= 32 ? 2 : 1);
+  if (tiles >= slots) return 1;
+  long long s = slots / tiles;
+  const long long max_by_k = kb / 8 > 0 ? kb / 8 : 1;   // keep >= 8 K blocks (1 KiB of each weight row) per split
+  if (s > max_by_k) s = max_by_k;
+  if (s > 16) s = 16;
+  if (s < 1) s = 1;
+  (void)dual;
+  return (int)s;
+}

@@ -1,0 +1,87 @@
+"""Request/response shim for the vLLM surface of the reference (demo/demo_vllm.py:18-63,
+chatts/utils/llm_utils.py:147-190): ``LLM(model=...).generate([{"prompt": str, "multi_modal_data":
+{"timeseries": [...]}}], SamplingParams(...)) -> outputs[i].outputs[0].text``.
+
+The reference's plugin file targets vllm 0.8.5 internals that no longer exist; this shim
+keeps the REQUEST SHAPE and drives the B200 engine directly instead of vLLM's plugin ABI."""
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from .config import ChatTSConfig
+from .model import ChatTSForCausalLM
+from .processor import ChatTSProcessor, SimpleTokenizer
+
+MAX_TS_PER_PROMPT = 50      # chatts_vllm.py:219-220
+
+
+@dataclass
+class SamplingParams:
+    max_tokens: int = 16
+    temperature: float = 0.0
+    top_p: float = 1.0
+    stop_token_ids: list = field(default_factory=list)
+    ignore_eos: bool = False
+    seed: int = None
+
+
+@dataclass
+class CompletionOutput:
+    text: str
+    token_ids: list
+
+
+@dataclass
+class RequestOutput:
+    prompt: str
+    outputs: list
+
+
+class LLM:
+    def __init__(self, model=None, tokenizer=None, config=None, state_dict=None, tensor_parallel_size=1, dtype="bfloat16",
+                 max_model_len=2048, max_num_seqs=32, limit_mm_per_prompt=None, trust_remote_code=True, seed=1234, **kw):
+        if tensor_parallel_size != 1:
+            raise NotImplementedError("launch one process per GPU with torchrun for tensor parallelism (bench.py --gpus N)")
+        dt = torch.bfloat16 if str(dtype) in ("bfloat16", "torch.bfloat16") else torch.float16
+        if isinstance(model, ChatTSForCausalLM):
+            self.model = model
+        elif isinstance(model, str):
+            self.model = ChatTSForCausalLM.from_pretrained(model, torch_dtype=dt, max_seq_len=max_model_len, max_batch=max_num_seqs)
+        else:
+            cfg = config or ChatTSConfig.chatts_14b()
+            self.model = (ChatTSForCausalLM(cfg, state_dict, dtype=dt, max_seq_len=max_model_len, max_batch=max_num_seqs)
+                          if state_dict is not None else
+                          ChatTSForCausalLM.from_synthetic(cfg, seed=seed, dtype=dt, max_seq_len=max_model_len, max_batch=max_num_seqs))
+        cfg = self.model.config
+        self.tokenizer = tokenizer or SimpleTokenizer(cfg.ts_token_start_index, cfg.pad_token_id, cfg.eos_token_id)
+        self.processor = ChatTSProcessor(self.tokenizer, cfg, dtype=torch.float32)
+        self.limit = (limit_mm_per_prompt or {}).get("timeseries", MAX_TS_PER_PROMPT)
+
+    def generate(self, inputs, sampling_params=None, use_tqdm=False):
+        sp = sampling_params or SamplingParams()
+        if isinstance(inputs, dict):
+            inputs = [inputs]
+        outs = []
+        bs = self.model.max_batch
+        for i0 in range(0, len(inputs), bs):
+            chunk = inputs[i0:i0 + bs]
+            prompts, series = [], []
+            for req in chunk:
+                ts = (req.get("multi_modal_data") or {}).get("timeseries", [])
+                if len(ts) > self.limit:
+                    raise ValueError(f"at most {self.limit} time series per prompt")
+                for t in ts:
+                    if not isinstance(t, (list, np.ndarray, torch.Tensor)):
+                        raise TypeError(f"Unsupported time series type: {type(t)}")
+                prompts.append(req["prompt"])
+                series.extend(ts)
+            enc = self.processor(text=prompts, timeseries=series, padding=True, return_tensors="pt")
+            S = enc["input_ids"].shape[1]
+            ids = self.model.generate(**enc, max_new_tokens=sp.max_tokens, do_sample=sp.temperature > 0,
+                                      temperature=sp.temperature, top_p=sp.top_p, ignore_eos=sp.ignore_eos, seed=sp.seed,
+                                      eos_token_id=(list(sp.stop_token_ids) or None))
+            for b, req in enumerate(chunk):
+                toks = ids[b, S:].tolist()
+                outs.append(RequestOutput(req["prompt"], [CompletionOutput(self.tokenizer.decode(toks), toks)]))
+        return outs

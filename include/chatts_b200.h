@@ -1,0 +1,173 @@
+/* chatts_b200 -- C-ABI of the B200 (sm_100a) hot path of ChatTS.
+ *
+ * The reference (NetManAIOps/ChatTS @ 09fae34) has NO native boundary for this path: it is Python on
+ * top of torch / vLLM / transformers.  This header is the boundary a maintainer binds from Python with
+ * ctypes; each entry point names the reference code it replaces (file:line relative
+ * to the reference repo, or the third-party file the reference calls).
+ *
+ * Conventions
+ *   - every function returns int: 0 = CTS_OK, negative = error; cts_last_error(ctx) holds the message.
+ *   - the caller owns ALL device memory (plain device pointers + explicit sizes); the library owns nothing
+ *     but the ctx.  No hidden allocation, no hidden synchronisation, every launch takes a cudaStream_t
+ *     (passed as void*).  Launches are CUDA-graph capturable.
+ *   - one host thread per ctx; distinct ctxs are independent.
+ *   - `dtype` is the model dtype of activations and weights: CTS_BF16 or CTS_F16 (fp32 accumulate).
+ *   - there is NO CPU implementation behind any of these symbols.
+ */
+#ifndef CHATTS_B200_H
+#define CHATTS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTS_OK 0
+#define CTS_ERR_BAD_ARG (-1)
+#define CTS_ERR_UNSUPPORTED (-2)
+#define CTS_ERR_CUDA (-3)
+#define CTS_ERR_NCCL (-4)
+
+#define CTS_BF16 0
+#define CTS_F16 1
+
+typedef struct cts_ctx cts_ctx;
+
+/* library identity: cts_arch() must say "sm_100a". */
+int cts_version(void);
+const char* cts_arch(void);
+
+int cts_ctx_create(int device, cts_ctx** out);
+void cts_ctx_destroy(cts_ctx* ctx);
+const char* cts_last_error(const cts_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * A3  mask -> valid length -> patch count            chatts/vllm/chatts_vllm.py:94-100 and :198-207
+ *   x            [n_series, row_len] model dtype; row_len = num_features * Lmax, interleaved
+ *                (value, mask) pairs as produced by sp_encoding (encoding_utils.py:35), zero padded
+ *                (chatts_vllm.py:517-529).
+ *   valid_len    int32[n_series]   = sum(long(mask))
+ *   patch_cnt    int32[n_series]   = ceil(valid_len / patch_size)
+ *   row_offset   int32[n_series+1] = exclusive prefix sum of patch_cnt (row order of :187)
+ *   max_valid    int32[1]          = max(valid_len)   (needed by use_position_idx, :146)
+ */
+int cts_ts_patch_count(cts_ctx* ctx, const void* x, int dtype, int n_series, int row_len, int num_features,
+                       int patch_size, int* valid_len, int* patch_cnt, int* row_offset, int* max_valid,
+                       void* stream);
+
+/* A4+A5  patchify + last-value pad + position features   chatts/vllm/chatts_vllm.py:107-183
+ *   mode: 0 = values only (:157), 1 = use_position_embedding (:135-142,161-183), 2 = use_position_idx (:143-154)
+ *   pos_table    [max_seq_len+1, emb_dim] model dtype (mode 1), padding id = max_seq_len (:76,128)
+ *   rows_out     [total_rows, in0] model dtype, in0 = patch (mode 0) | patch*(1+emb_dim) (1) | 2*patch (2)
+ *   max_patches  grid bound: ceil(Lmax / patch_size)
+ */
+int cts_ts_patchify(cts_ctx* ctx, const void* x, int dtype, int n_series, int row_len, int num_features,
+                    int patch_size, int mode, const void* pos_table, int emb_dim, int max_seq_len,
+                    const int* valid_len, const int* row_offset, const int* max_valid, int max_patches,
+                    void* rows_out, int in0, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * tcgen05 GEMM  Y[T, N] = X[T, K] * W[N, K]^T  (+ fused epilogue)
+ *   replaces nn.Linear in  TimeSeriesEmbedding.mlp (chatts_vllm.py:83-91,188) and every projection of the
+ *   decoder (transformers qwen2/modeling_qwen2.py:44-48,217-219,245; vllm qwen2.py:93-116,159-174;
+ *   lm_head chatts_vllm.py:607-610).
+ *   Weights stream through TMA as the 128-row MMA operand, tokens are the MMA N dimension ("swap-AB"), so
+ *   decode batches of 1..32 tokens still issue full-width tcgen05.mma and the kernel is HBM-bound on W.
+ */
+#define CTS_EPI_NONE 0        /* out = dtype(acc + bias)                                      */
+#define CTS_EPI_GELU 1        /* out = dtype(gelu_erf(dtype(acc + bias)))      chatts_vllm.py:86-87 */
+#define CTS_EPI_SWIGLU 2      /* out = dtype(silu(dtype(acc_w)) * dtype(acc_w2))  modeling_qwen2.py:47 */
+#define CTS_EPI_PARTIAL_F32 3 /* out_f32[split][t][n] = acc   (split-K; reduced by a cts_reduce_* call) */
+#define CTS_EPI_RESIDUAL 4    /* out = dtype(residual + dtype(acc + bias))     modeling_qwen2.py:302,308 */
+
+typedef struct {
+  const void* w;        /* [n, k] row-major, leading dimension w_ld elements */
+  const void* w2;       /* second weight (up_proj) for CTS_EPI_SWIGLU, same shape/ld, else NULL */
+  const void* x;        /* [t, k] row-major, leading dimension x_ld */
+  const void* bias;     /* [n] model dtype or NULL */
+  const void* residual; /* [t, n] (leading dimension out_ld) for CTS_EPI_RESIDUAL; may alias out */
+  void* out;            /* [t, n] model dtype, or fp32 [split_k, t, n] for CTS_EPI_PARTIAL_F32 */
+  const int* row_map;   /* optional: output row of token i is row_map[i] (<0: dropped) -- the sp-mask scatter
+                           of patch rows into the embedding sequence (chatts_vllm.py:569-573) */
+  long long n, k, t;
+  long long w_ld, x_ld, out_ld;
+  int dtype;
+  int epilogue;
+  int split_k;          /* >=1; >1 only with CTS_EPI_PARTIAL_F32 */
+  int reserved;
+} cts_gemm_args;
+
+int cts_gemm(cts_ctx* ctx, const cts_gemm_args* args, void* stream);
+/* heuristic used by the host code: split-K factor that fills the SMs for a weight-streaming GEMM */
+int cts_gemm_suggest_split(cts_ctx* ctx, long long n, long long k, long long t, int dual);
+
+/* split-K reduction fused with the op that follows the projection ------------------------------- */
+
+/* out[row_map?][n] = act(dtype(sum_s partial[s][t][n] + bias[n]))   act: CTS_EPI_NONE | CTS_EPI_GELU
+ * (TS-encoder MLP layers, chatts_vllm.py:83-91; last layer scatters through row_map, :569-573) */
+int cts_reduce_bias_act(cts_ctx* ctx, const float* partial, int split_k, long long t, long long n,
+                        const void* bias, int act, void* out, long long out_ld, const int* row_map, int dtype,
+                        void* stream);
+
+/* h = resid_in + dtype(sum_s partial[s]) ; resid_out = h ; norm_out = w * dtype(h * rsqrt(mean(h^2)+eps))
+ * (modeling_qwen2.py:258-263 RMSNorm, :302/:308 residual adds).  partial may be NULL (split_k = 0): plain
+ * RMSNorm of resid_in.  norm_w may be NULL: only the residual update.  resid_out may alias resid_in. */
+int cts_reduce_residual_rmsnorm(cts_ctx* ctx, const float* partial, int split_k, const void* resid_in,
+                                void* resid_out, const void* norm_w, float eps, void* norm_out, long long t,
+                                long long h, int dtype, void* stream);
+
+/* out[t][i] = dtype(silu(dtype(sum_s p[s][t][i])) * dtype(sum_s p[s][t][inter+i]))   (modeling_qwen2.py:47) */
+int cts_reduce_swiglu(cts_ctx* ctx, const float* partial, int split_k, long long t, long long inter, void* out,
+                      int dtype, void* stream);
+
+/* q/k/v = dtype(sum_s partial + bias); RoPE(q,k) with the fp32-computed cos/sin tables cast to dtype
+ * (modeling_qwen2.py:107-146,217-222); q -> q_out [t, nh*d]; k,v -> paged KV cache slot slot_map[t]
+ * (vllm Attention KV write, qwen2.py:233-235) and, when k_out/v_out != NULL, contiguous [t, nkv*d] copies
+ * for the prefill attention.
+ *   src: fp32 [split_k, t, (nh+2nkv)*d] when src_is_partial, else model-dtype [t, (nh+2nkv)*d] (bias already in)
+ *   cos/sin: [max_pos, d/2] model dtype;  positions int32[t];  slot_map int32[t] (<0: no cache write)
+ *   cache layout: [num_pages, nkv, page_size, d]
+ */
+int cts_qkv_rope_cache(cts_ctx* ctx, const void* src, int src_is_partial, int split_k, const void* bias,
+                       const int* positions, const void* cos_tab, const void* sin_tab, const int* slot_map,
+                       void* q_out, void* k_cache, void* v_cache, void* k_out, void* v_out, long long t, int nh,
+                       int nkv, int head_dim, int page_size, int dtype, void* stream);
+
+/* K4  embedding lookup: out[i] = table[ids[i]] for ids[i] >= 0 (rows with id < 0 are left untouched:
+ * they are the patch rows the TS encoder scatters)            chatts_vllm.py:569 */
+int cts_embed_gather(cts_ctx* ctx, const void* table, const int* ids, void* out, long long t, long long h,
+                     long long vocab, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K8 attention                       modeling_qwen2.py:161-184 ; vllm qwen2.py:188-197,234
+ * prefill: causal GQA over the tokens of this call, variable length, cu_seqlens int32[batch+1]
+ *   q [t, nh, d], k/v [t, nkv, d] (RoPE applied), out [t, nh*d]
+ */
+int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, const void* v, const int* cu_seqlens, int batch,
+                     int max_seqlen, int nh, int nkv, int head_dim, float scale, void* out, int dtype,
+                     void* stream);
+
+/* decode: one query token per sequence against the paged cache (flash-decoding split over KV pages).
+ *   q [batch, nh, d]; page_table int32[batch, max_pages]; seq_lens int32[batch] (tokens incl. the current one)
+ *   workspace: fp32, cts_attn_decode_workspace_floats(...) elements;  out [batch, nh*d]
+ */
+long long cts_attn_decode_workspace_floats(int batch, int nh, int head_dim, int num_splits);
+int cts_attn_decode(cts_ctx* ctx, const void* q, const void* k_cache, const void* v_cache, const int* page_table,
+                    int max_pages, const int* seq_lens, int batch, int nh, int nkv, int head_dim, int page_size,
+                    float scale, int num_splits, float* workspace, void* out, int dtype, void* stream);
+
+/* K13 greedy sampling + device-side bookkeeping of the decode loop, so that a whole step
+ * (embed -> 48 layers -> lm_head -> argmax -> advance) replays as one CUDA graph with no host round trip
+ * (HF GenerationMixin greedy loop, README.md:102; vLLM sampler).
+ *   logits [batch, vocab] model dtype -> next id (first max, like torch.argmax)
+ *   out_tokens int32[batch, out_ld] column `*step_ptr` receives the id; cur_ids int32[batch] = id;
+ *   positions[b] += 1; seq_lens[b] += 1; slot_map[b] = slot of the NEW position in the paged cache;
+ *   *step_ptr += 1 (device counter).
+ */
+int cts_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab, int batch, int* out_tokens, int out_ld,
+                       int* step_ptr, int* cur_ids, int* positions, int* seq_lens, int* slot_map,
+                       const int* page_table, int max_pages, int page_size, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHATTS_B200_H */
