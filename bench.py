@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- ChatTS-14B decode tokens/s on B200 (BASELINE.json metric), with roofline, e2e and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one decode step of the whole batch (one new token per
+sequence) of ChatTS-14B (synthetic bf16 weights at the real shapes -- no checkpoint exists offline) after a
+prefill of prompts that each carry 8 series x 256 points (8 x (46 prefix ids + <ts> + 16 patch rows + <ts/>)
++ 64 prompt ids = 576 merged positions).  `value` = B*K / device time of K steps (CUDA events, inputs
+resident in HBM; the 28 GB weight stream is far larger than the 126 MB L2).  `e2e` = the same metric through
+the public generate() call with HOST tensors (processor output on the CPU, H2D of ids/series, prefill, K new
+tokens streamed back D2H every step).  N>1: tensor parallel over N GPUs (strong scaling, total work fixed).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_SERIES, SERIES_LEN, PREFIX_IDS, PROMPT_IDS = 8, 256, 46, 64
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_series(i, k, length=SERIES_LEN):
+    """SURVEY.md §8d synthetic series: sine + trend + noise + one level shift, seeded per (sample, series)."""
+    rng = np.random.default_rng(1000 * i + k)
+    t = np.arange(length)
+    a = rng.uniform(0.5, 50)
+    s = a * np.sin(2 * np.pi * t / rng.uniform(16, 128)) + rng.uniform(-0.05, 0.05) * t + rng.normal(0, 0.1 * a, length)
+    s[int(rng.uniform(length / 4, 3 * length / 4)):] += rng.choice([-2, 2]) * a
+    return s
+
+
+def make_batch(cfg, batch, seed=0):
+    """Host-side request batch in the reference's processor output format (input_ids, attention_mask, timeseries)."""
+    from chatts_b200.processor import sp_encoding
+    rng = np.random.default_rng(seed)
+    ids = []
+    series = []
+    for b in range(batch):
+        row = []
+        for k in range(N_SERIES):
+            row += rng.integers(0, 150000, PREFIX_IDS).tolist() + [cfg.ts_token_start_index, cfg.ts_token_start_index + 1]
+            series.append(sp_encoding(make_series(b, k))[0])
+        row += rng.integers(0, 150000, PROMPT_IDS).tolist()
+        ids.append(row)
+    ids = torch.tensor(ids, dtype=torch.long)
+    ts = torch.from_numpy(np.stack(series)).to(torch.float32)          # [B*8, 512, 1]
+    return {"input_ids": ids, "attention_mask": torch.ones_like(ids), "timeseries": ts}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(r[3 + j].lower().startswith("active") for r in self.rows if len(r) > 3 + j)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_decode_baseline(batch, ctx_len, steps=3, layers_sample=2, threads=None):
+    """The reference's HF path on the host cores: stock transformers Qwen2ForCausalLM (README.md:88 loads it through
+    the checkpoint's subclass) at the ChatTS-14B layer shapes, bf16, KV cache of `ctx_len` positions, batch decode.
+    Bounded sample: `layers_sample` of the 48 decoder layers + final norm + lm_head are instantiated and timed; the
+    per-layer time is scaled linearly to 48 layers (stated in `sample`)."""
+    from transformers import Qwen2Config, Qwen2ForCausalLM
+    try:
+        from transformers import DynamicCache
+    except ImportError:  # pragma: no cover
+        from transformers.cache_utils import DynamicCache
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    full_layers = 48
+
+    def build(nl):
+        c = Qwen2Config(hidden_size=5120, intermediate_size=13824, num_hidden_layers=nl, num_attention_heads=40,
+                        num_key_value_heads=8, vocab_size=152064, rms_norm_eps=1e-6, rope_theta=1e6,
+                        max_position_embeddings=32768, tie_word_embeddings=False)
+        with torch.device("meta"):
+            m = Qwen2ForCausalLM(c)
+        m = m.to_empty(device="cpu").to(torch.bfloat16).eval()
+        g = torch.Generator().manual_seed(1234)
+        with torch.no_grad():
+            for p in m.parameters():
+                if p.dim() == 1:
+                    p.fill_(1.0)
+                else:
+                    # cheap deterministic fill (randn of 2.1e9 values costs ~20 s of the budget): tile a small random block
+                    blk = (torch.randn(4096, generator=g) * 0.02).to(torch.bfloat16)
+                    p.view(-1)[: (p.numel() // 4096) * 4096].view(-1, 4096).copy_(blk)
+        # rotary buffers live outside parameters and were created on meta: rebuild them
+        for mod in m.modules():
+            if hasattr(mod, "inv_freq") and hasattr(mod, "compute_default_rope_parameters"):
+                inv, _ = mod.compute_default_rope_parameters(c, "cpu")
+                mod.inv_freq = inv
+                mod.original_inv_freq = inv.clone()
+        return m, c
+
+    def time_steps(nl):
+        m, c = build(nl)
+        cache = DynamicCache(config=c) if "config" in DynamicCache.__init__.__code__.co_varnames else DynamicCache()
+        kv = torch.randn(batch, 8, ctx_len, 128).to(torch.bfloat16) * 0.1
+        for l in range(nl):
+            cache.update(kv.clone(), kv.clone(), l)
+        ids = torch.randint(0, 150000, (batch, 1))
+        ts = []
+        with torch.no_grad():
+            for s in range(steps + 1):
+                pos = torch.full((batch, 1), ctx_len + s, dtype=torch.long)
+                t0 = time.perf_counter()
+                out = m(input_ids=ids, past_key_values=cache, position_ids=pos, use_cache=True)
+                ids = out.logits[:, -1].float().argmax(-1, keepdim=True)
+                ts.append(time.perf_counter() - t0)
+        del m
+        return float(np.median(ts[1:]))
+
+    t_s = time_steps(layers_sample)
+    t_0 = time_steps(0) if layers_sample > 0 else 0.0          # embed + final norm + lm_head + argmax
+    per_layer = max(t_s - t_0, 0.0) / max(layers_sample, 1)
+    step = t_0 + per_layer * full_layers
+    return {"value": batch / step, "unit": "tokens/s", "cores": threads, "kind": "reference",
+            "sample": (f"stock transformers Qwen2ForCausalLM (the reference's HF CPU path, README.md:88) bf16, ChatTS-14B layer "
+                       f"shapes, batch {batch}, KV context {ctx_len}: timed {layers_sample} of 48 decoder layers + embed/norm/"
+                       f"lm_head over {steps} decode steps (median), per-layer time scaled x48 "
+                       f"(head {t_0 * 1e3:.0f} ms, layer {per_layer * 1e3:.0f} ms)"),
+            "ms_per_step": step * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ctx_len = N_SERIES * (PREFIX_IDS + 2 + SERIES_LEN // 16) + PROMPT_IDS
+    t0 = time.time()
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 2))):
+        base = cpu_decode_baseline(args.batch, ctx_len, steps=3, layers_sample=2)
+        vals.append(base["value"])
+        if time.time() - t0 > 150:
+            break
+    v = float(np.median(vals))
+    base["value"] = v
+    line = {"impl": "reference", "metric": "decode_tokens_per_s", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": args.batch / v * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args.batch, args.gpus), "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, gpus):
+    return {"workload": (f"ChatTS-14B (Qwen2.5-14B shape + 5-layer TS encoder, synthetic bf16 weights) greedy decode, batch {batch}, "
+                         f"each prompt {N_SERIES} series x {SERIES_LEN} points -> 576 merged positions "
+                         f"({N_SERIES}x({PREFIX_IDS} prefix ids+<ts>+16 patch rows+<ts/>)+{PROMPT_IDS} prompt ids)"),
+            "batch": batch, "context": 576, "parallelism": f"tp{gpus}" if gpus > 1 else "single-gpu",
+            "l2_policy": "inputs larger than L2: 28 GB of weights streamed per step vs 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    from chatts_b200 import ChatTSConfig, _cabi
+    from chatts_b200.model import ChatTSForCausalLM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    cfg = ChatTSConfig.chatts_14b()
+    if args.layers:
+        cfg.num_hidden_layers = args.layers
+    hbm_peak, peak_src = peaks()
+    max_new = args.steps + args.warmup + 8
+    model = ChatTSForCausalLM.from_synthetic(cfg, seed=1234, tp_rank=rank, tp_size=world, max_batch=max(args.batch, 1),
+                                             max_seq_len=1024, page_size=64)
+    ctx = model.ctx
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def measure_decode(batch):
+        """Prefill the batch, then W untimed + K timed decode steps on the device."""
+        enc = make_batch(cfg, batch)
+        ids_cpu, am_cpu, counts, lay = model._prepare_inputs(enc["input_ids"], enc["attention_mask"], enc["timeseries"])
+        pts, held = model._alloc_pages(lay.lens, max_new)
+        try:
+            logits = model._prefill(lay, counts, enc["timeseries"], pts)
+            st = model._decode_state(batch, max_new)
+            lens32 = torch.from_numpy(lay.lens.astype(np.int32))
+            st.page_table.copy_(torch.from_numpy(pts))
+            st.positions.copy_(lens32 - 1)
+            st.seq_lens.copy_(lens32)
+            st.step_ptr.zero_()
+            ctx.greedy_advance(logits, batch, st.out_tokens, st.step_ptr, st.cur_ids, st.positions, st.seq_lens, st.slot_map,
+                               st.page_table, model.page_size)
+            l0 = ctx.launches
+            model._decode_step(st)                      # first call captures the graph (and runs one real step)
+            per_step_launches = None
+            for _ in range(max(args.warmup - 1, 2)):
+                l0 = ctx.launches
+                model._decode_step(st)
+            # launches per step: count them by running the body eagerly once outside the graph bookkeeping
+            l0 = ctx.launches
+            model._decode_body(st, True)
+            per_step_launches = ctx.launches - l0
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                model._decode_step(st)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t)
+            ctx_end = int(lay.lens.max()) + int(st.step_ptr.item())
+        finally:
+            model.pool.release(held)
+        return ms, per_step_launches, ctx_end
+
+    results = {}
+    with ClockSampler(local) as clk:
+        batches = [args.batch] if args.only_batch else sorted(set([1, 8, args.batch]))
+        for b in batches:
+            ms, launches, ctx_end = measure_decode(b)
+            results[b] = dict(ms_total=ms, ms_per_step=ms / args.steps, tokens_per_s=b * args.steps / (ms / 1e3), launches=launches,
+                              ctx_end=ctx_end)
+    clocks = clk.summary()
+    main = results[args.batch]
+
+    # ---- whole-step HBM roofline: streamed weights + KV read per step
+    L = cfg.num_hidden_layers
+    per_layer = (cfg.hidden_size * (cfg.num_attention_heads + 2 * cfg.num_key_value_heads) * cfg.head_dim + cfg.hidden_size * cfg.num_attention_heads * cfg.head_dim +
+                 3 * cfg.hidden_size * cfg.intermediate_size)
+    w_bytes = 2 * (L * per_layer + cfg.hidden_size * cfg.vocab_size) / world
+    kv_tok = L * 2 * cfg.num_key_value_heads * cfg.head_dim * 2 / world
+    ctx_mid = main["ctx_end"] - args.steps / 2
+    step_bytes = w_bytes + args.batch * ctx_mid * kv_tok
+    step_gbs = step_bytes / (main["ms_per_step"] / 1e3) / 1e9
+
+    # ---- dominant kernel alone: gate_up tcgen05 GEMM (2*I*H weights), one launch per layer weight so every launch
+    # streams a different 283 MB from HBM (>> L2), timed with CUDA events on the launching stream
+    roof = None
+    if world == 1:
+        st = model._decode_state(args.batch, max_new)
+        B = args.batch
+        I = model.I
+        sp = st.splits["gu"]
+        n_rep = max(1, args.steps // 4)
+        for _ in range(2):
+            for l in range(L):
+                if sp > 1:
+                    ctx.gemm(st.xn, model.wgu[l], st.ws, epilogue=_cabi.EPI_PARTIAL_F32, split_k=sp, t=B)
+                else:
+                    ctx.gemm(st.xn, model.wgu[l][:I], st.act, w2=model.wgu[l][I:], epilogue=_cabi.EPI_SWIGLU, t=B)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_rep):
+            for l in range(L):
+                if sp > 1:
+                    ctx.gemm(st.xn, model.wgu[l], st.ws, epilogue=_cabi.EPI_PARTIAL_F32, split_k=sp, t=B)
+                else:
+                    ctx.gemm(st.xn, model.wgu[l][:I], st.act, w2=model.wgu[l][I:], epilogue=_cabi.EPI_SWIGLU, t=B)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (n_rep * L)
+        alg = 2 * I * cfg.hidden_size * 2 + B * cfg.hidden_size * 2 + B * I * 2
+        ach = alg / (us * 1e-6) / 1e9
+        roof = {"bound": "hbm", "kernel": "gemm_tn_kernel (gate_up+SwiGLU, tcgen05/TMA, swap-AB)", "achieved": ach, "peak": hbm_peak,
+                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "us_per_launch": us, "algorithmic_bytes": alg,
+                "peak_source": peak_src, "split_k": sp,
+                "whole_step": {"bytes": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / hbm_peak}}
+
+    # ---- e2e through the public API with host tensors
+    e2e = None
+    if world == 1:
+        enc = make_batch(cfg, args.batch, seed=1)
+        enc = {k: v.pin_memory() for k, v in enc.items()}
+        new = args.steps
+        model.generate(**enc, max_new_tokens=4, ignore_eos=True, sync_every=1)          # warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = model.generate(**enc, max_new_tokens=new, ignore_eos=True, sync_every=1)  # D2H of the new ids every step
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h2d = (enc["timeseries"].numel() * 2 + 4 * 576 * args.batch * 4 + args.batch * N_SERIES * 16 * 4)
+        d2h = args.batch * new * 4 + args.batch * N_SERIES * 8
+        e2e = {"value": args.batch * new / dt, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "definition": f"one step = model.generate(**host_tensors, max_new_tokens={new}) incl. H2D, TS encode, prefill of "
+                             f"{args.batch}x576 positions and {new} decode steps with per-step D2H of the new ids; value = B*new/wall",
+               "seconds": dt, "out_shape": list(out.shape)}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cpu = cpu_decode_baseline(args.batch, 576, steps=3, layers_sample=2)
+            except Exception as e:  # pragma: no cover
+                cpu = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {e!r}"}
+        line = {"metric": "decode_tokens_per_s", "value": main["tokens_per_s"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.batch, world),
+                "by_batch": {str(b): {"tokens_per_s": r["tokens_per_s"], "ms_per_step": r["ms_per_step"]} for b, r in results.items()},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(main["launches"] * args.steps), "launches_per_step": main["launches"],
+                "roofline": roof, "cpu_baseline": cpu, "arch": ctx.arch, "lib": os.path.relpath(_cabi.LIB_PATH, ROOT)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=0, help="debug: fewer decoder layers (makes the number INVALID as a benchmark)")
+    ap.add_argument("--only-batch", action="store_true", help="skip the b=1/8 side measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

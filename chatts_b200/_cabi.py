@@ -112,13 +112,15 @@ class Context:
             raise CtsError(f"cts_ctx_create(device={self.device}) failed with {rc} (needs an sm_100 device)")
         self.h = h
         self.arch = self.lib.cts_arch().decode()
+        self.launches = 0          # kernels launched through this ctx (bench.py's gpu_launches evidence)
 
     def close(self):
         if getattr(self, "h", None):
             self.lib.cts_ctx_destroy(self.h)
             self.h = None
 
-    def _chk(self, rc):
+    def _chk(self, rc, n_kernels=1):
+        self.launches += n_kernels
         if rc != OK:
             raise CtsError(f"chatts_b200 error {rc}: {self.lib.cts_last_error(self.h).decode()}")
 
@@ -132,7 +134,7 @@ class Context:
         off = torch.empty(n + 1, dtype=torch.int32, device=dev)
         mx = torch.empty(1, dtype=torch.int32, device=dev)
         self._chk(self.lib.cts_ts_patch_count(self.h, _p(x), dtype_code(x.dtype), n, row_len, num_features, patch_size,
-                                              _p(valid), _p(cnt), _p(off), _p(mx), _stream()))
+                                              _p(valid), _p(cnt), _p(off), _p(mx), _stream()), 2)
         return valid, cnt, off, mx
 
     def ts_patchify(self, x, num_features, patch_size, mode, pos_table, emb_dim, max_seq_len, valid, off, mx,
@@ -199,7 +201,7 @@ class Context:
                     workspace, out):
         self._chk(self.lib.cts_attn_decode(self.h, _p(q), _p(k_cache), _p(v_cache), _p(page_table), page_table.shape[1],
                                            _p(seq_lens), batch, nh, nkv, head_dim, page_size, float(scale), num_splits,
-                                           _p(workspace), _p(out), dtype_code(q.dtype), _stream()))
+                                           _p(workspace), _p(out), dtype_code(q.dtype), _stream()), 2)
 
     def greedy_advance(self, logits, batch, out_tokens, step_ptr, cur_ids, positions, seq_lens, slot_map, page_table,
                        page_size):
@@ -207,7 +209,7 @@ class Context:
                                               out_tokens.stride(0) if out_tokens is not None else 0, _p(step_ptr), _p(cur_ids),
                                               _p(positions), _p(seq_lens), _p(slot_map), _p(page_table),
                                               page_table.shape[1] if page_table is not None else 0, page_size,
-                                              dtype_code(logits.dtype), _stream()))
+                                              dtype_code(logits.dtype), _stream()), 2 if step_ptr is not None else 1)
 
 
 _ctx_cache = {}
