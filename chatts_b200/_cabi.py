@@ -22,7 +22,8 @@ SYMBOLS = [
     "cts_ts_patch_count", "cts_ts_patchify", "cts_gemm", "cts_gemm_suggest_split",
     "cts_reduce_bias_act", "cts_reduce_residual_rmsnorm", "cts_reduce_swiglu", "cts_qkv_rope_cache",
     "cts_embed_gather", "cts_attn_prefill", "cts_attn_decode_workspace_floats", "cts_attn_decode",
-    "cts_greedy_advance",
+    "cts_greedy_advance", "cts_ipc_alloc", "cts_ipc_open", "cts_ipc_close", "cts_ipc_free",
+    "cts_peer_allreduce_residual_rmsnorm",
 ]
 
 
@@ -74,6 +75,13 @@ def load_library():
     lib.cts_attn_decode_workspace_floats.restype = ll
     lib.cts_attn_decode.argtypes = [vp, vp, vp, vp, vp, i, vp, i, i, i, i, i, f, i, vp, vp, i, vp]
     lib.cts_greedy_advance.argtypes = [vp, vp, ll, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.cts_ipc_alloc.argtypes = [vp, ll, C.POINTER(vp), C.c_char_p]
+    lib.cts_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.cts_ipc_close.argtypes = [vp, vp]
+    lib.cts_ipc_free.argtypes = [vp, vp]
+    lib.cts_peer_allreduce_residual_rmsnorm.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
+    for name in ("cts_ipc_alloc", "cts_ipc_open", "cts_ipc_close", "cts_ipc_free", "cts_peer_allreduce_residual_rmsnorm"):
+        getattr(lib, name).restype = i
     for name in ("cts_ts_patch_count", "cts_ts_patchify", "cts_gemm", "cts_gemm_suggest_split", "cts_reduce_bias_act",
                  "cts_reduce_residual_rmsnorm", "cts_reduce_swiglu", "cts_qkv_rope_cache", "cts_embed_gather",
                  "cts_attn_prefill", "cts_attn_decode", "cts_greedy_advance", "cts_ctx_create"):
@@ -210,6 +218,25 @@ class Context:
                                               _p(positions), _p(seq_lens), _p(slot_map), _p(page_table),
                                               page_table.shape[1] if page_table is not None else 0, page_size,
                                               dtype_code(logits.dtype), _stream()), 2 if step_ptr is not None else 1)
+
+
+    # ------------------------------------------------------------------ tensor parallel (peer memory)
+    def ipc_alloc(self, nbytes):
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._chk(self.lib.cts_ipc_alloc(self.h, nbytes, C.byref(ptr), handle), 0)
+        return ptr.value, handle.raw
+
+    def ipc_open(self, handle):
+        ptr = C.c_void_p()
+        self._chk(self.lib.cts_ipc_open(self.h, handle, C.byref(ptr)), 0)
+        return ptr.value
+
+    def peer_allreduce_residual_rmsnorm(self, peer_partials, peer_flags, state, rank, world, resid_in, resid_out, norm_w, eps,
+                                        norm_out, t):
+        self._chk(self.lib.cts_peer_allreduce_residual_rmsnorm(self.h, _p(peer_partials), _p(peer_flags), _p(state), rank, world,
+                                                               _p(resid_in), _p(resid_out), _p(norm_w), float(eps), _p(norm_out), t,
+                                                               resid_in.shape[-1], dtype_code(resid_in.dtype), _stream()))
 
 
 _ctx_cache = {}

@@ -1,0 +1,174 @@
+// chatts_b200 -- tensor-parallel row-parallel tail as ONE kernel over NVLink peer memory:
+//     h = resid + dtype( sum over ranks of partial_r ) ;  norm_out = RMSNorm(h) * w
+// replaces "RowParallelLinear -> NCCL all-reduce -> residual add -> RMSNorm" (vllm qwen2.py:100-116,168-174,
+// 299-311) for the decode-sized messages (b*5120 fp32 = 20..640 KiB) where the
+// collective is latency-bound: every rank's o_proj / down_proj GEMM leaves its fp32 partial in a symmetric
+// (cudaIpc-mapped) buffer; this kernel (1) signals "my partial is complete" into every peer's flag array with a
+// system-scope release store, (2) waits with acquire loads until all peers have signalled this epoch, (3) PULLS
+// the peers' rows over NVLink (plain vectorised peer loads) and reduces them in rank order -- the same order on
+// every rank, so all ranks hold bit-identical h without a broadcast -- fused with the residual add and the next
+// RMSNorm.  No NCCL call, no extra launch, no copy.  The two partial buffers (o_proj / down_proj) alternate, so
+// the barrier of call n+1 is what licenses overwriting the buffer of call n.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int kThreads = 256;
+constexpr int kMaxVec = 8;
+constexpr int kMaxRanks = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+peer_allreduce_residual_rmsnorm_kernel(const float* const* __restrict__ peer_partials, int* const* __restrict__ peer_flags,
+                                       int* __restrict__ state, int rank, int world, const T* __restrict__ resid_in,
+                                       T* __restrict__ resid_out, const T* __restrict__ norm_w, float eps,
+                                       T* __restrict__ norm_out, int h) {
+  const long long t = blockIdx.x;
+  __shared__ const float* src[kMaxRanks];
+  __shared__ float red[kThreads / 32];
+  __shared__ float inv_s;
+  const int epoch = state[0] + 1;      // state[0] is only advanced by the last CTA of this kernel to finish
+  if (threadIdx.x < world) {
+    src[threadIdx.x] = peer_partials[threadIdx.x];
+    if (blockIdx.x == 0) st_release_sys(peer_flags[threadIdx.x] + rank, epoch);     // tell peer: rank's partial is ready
+    const int* mine = peer_flags[rank] + threadIdx.x;                                // my own flag array, slot = peer
+    unsigned spins = 0;
+    while (ld_acquire_sys(mine) < epoch) {
+      if (++spins > (1u << 26)) {
+        printf("chatts_b200: peer all-reduce timed out waiting for rank %d (epoch %d)\n", threadIdx.x, epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+
+  const int nvec = h / 8;
+  float vals[kMaxVec][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int it = 0; it < kMaxVec; ++it) {
+    const int v = it * kThreads + threadIdx.x;
+    if (v < nvec) {
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < world; ++r) {          // fixed rank order: identical fp32 sum on every rank
+        const float* p = src[r] + t * h + (long long)v * 8;
+        const float4 lo = ld_peer_f4(p), hi = ld_peer_f4(p + 4);
+        a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w; a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
+      }
+      float rr[8];
+      unpack8<T>(*reinterpret_cast<const uint4*>(resid_in + t * h + (long long)v * 8), rr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rr[j] = rnd<T>(rr[j] + rnd<T>(a[j]));
+      *reinterpret_cast<uint4*>(resid_out + t * h + (long long)v * 8) = pack8<T>(rr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { vals[it][j] = rr[j]; ss += rr[j] * rr[j]; }
+    }
+  }
+  if (norm_out != nullptr) {
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < kThreads / 32 ? red[threadIdx.x] : 0.f;
+      v = warp_sum(v);
+      if (threadIdx.x == 0) inv_s = 1.0f / sqrtf(v / (float)h + eps);
+    }
+    __syncthreads();
+    const float inv = inv_s;
+#pragma unroll
+    for (int it = 0; it < kMaxVec; ++it) {
+      const int v = it * kThreads + threadIdx.x;
+      if (v < nvec) {
+        float w[8], o[8];
+        unpack8<T>(*reinterpret_cast<const uint4*>(norm_w + (long long)v * 8), w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = w[j] * rnd<T>(vals[it][j] * inv);
+        *reinterpret_cast<uint4*>(norm_out + t * h + (long long)v * 8) = pack8<T>(o);
+      }
+    }
+  }
+  // last CTA to finish publishes the new epoch for the next call (stream-ordered, so no race with its readers)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int done = atomicAdd(&state[1], 1) + 1;
+    if (done == (int)gridDim.x) {
+      state[1] = 0;
+      state[0] = epoch;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int cts_ipc_alloc(cts_ctx* ctx, long long bytes, void** dptr, unsigned char* handle64) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, bytes > 0 && dptr && handle64, "args");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CTS_CUDA(ctx, cudaMalloc(dptr, (size_t)bytes));
+  CTS_CUDA(ctx, cudaMemset(*dptr, 0, (size_t)bytes));
+  cudaIpcMemHandle_t hnd;
+  CTS_CUDA(ctx, cudaIpcGetMemHandle(&hnd, *dptr));
+  memcpy(handle64, &hnd, 64);
+  return CTS_OK;
+}
+
+extern "C" int cts_ipc_open(cts_ctx* ctx, const unsigned char* handle64, void** dptr) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, handle64 && dptr, "args");
+  cudaIpcMemHandle_t hnd;
+  memcpy(&hnd, handle64, 64);
+  CTS_CUDA(ctx, cudaIpcOpenMemHandle(dptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+  return CTS_OK;
+}
+
+extern "C" int cts_ipc_close(cts_ctx* ctx, void* dptr) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CUDA(ctx, cudaIpcCloseMemHandle(dptr));
+  return CTS_OK;
+}
+
+extern "C" int cts_ipc_free(cts_ctx* ctx, void* dptr) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CUDA(ctx, cudaFree(dptr));
+  return CTS_OK;
+}
+
+extern "C" int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const void* peer_partials, const void* peer_flags, int* state,
+                                                   int rank, int world, const void* resid_in, void* resid_out,
+                                                   const void* norm_w, float eps, void* norm_out, long long t, long long h,
+                                                   int dtype, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, peer_partials && peer_flags && state && resid_in && resid_out, "null pointer");
+  CTS_CHECK_ARG(ctx, world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "rank / world");
+  CTS_CHECK_ARG(ctx, (norm_w == nullptr) == (norm_out == nullptr), "norm_w / norm_out mismatch");
+  CTS_CHECK_ARG(ctx, h > 0 && h % 8 == 0 && h <= 8LL * kMaxVec * kThreads, "h must be a multiple of 8 and <= 16384");
+  CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
+  CTS_CHECK_ARG(ctx, t > 0 && t <= 2147483647LL, "t");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CTS_BF16)
+    peer_allreduce_residual_rmsnorm_kernel<__nv_bfloat16><<<(unsigned)t, kThreads, 0, st>>>(
+        (const float* const*)peer_partials, (int* const*)peer_flags, state, rank, world, (const __nv_bfloat16*)resid_in,
+        (__nv_bfloat16*)resid_out, (const __nv_bfloat16*)norm_w, eps, (__nv_bfloat16*)norm_out, (int)h);
+  else
+    peer_allreduce_residual_rmsnorm_kernel<__half><<<(unsigned)t, kThreads, 0, st>>>(
+        (const float* const*)peer_partials, (int* const*)peer_flags, state, rank, world, (const __half*)resid_in,
+        (__half*)resid_out, (const __half*)norm_w, eps, (__half*)norm_out, (int)h);
+  CTS_LAUNCH_CHECK(ctx);
+  return CTS_OK;
+}

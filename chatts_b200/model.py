@@ -63,7 +63,8 @@ class _Step:
 
 class ChatTSForCausalLM:
     def __init__(self, config, state_dict, device="cuda", dtype=torch.bfloat16, tp_rank=0, tp_size=1,
-                 max_batch=32, max_seq_len=2048, page_size=64, use_cuda_graph=True, comm=None):
+                 max_batch=32, max_seq_len=2048, page_size=64, use_cuda_graph=True, comm=None,
+                 use_peer_allreduce=True, graph_with_tp=False):
         if not torch.cuda.is_available():
             raise _cabi.CtsError("chatts_b200 needs a B200 (sm_100a) GPU; there is no CPU fallback")
         self.config, self.dtype = config, dtype
@@ -80,6 +81,7 @@ class ChatTSForCausalLM:
         self.page_size, self.max_batch, self.max_seq_len = page_size, max_batch, max_seq_len
         self.max_pages = (max_seq_len + page_size - 1) // page_size
         self.use_cuda_graph = use_cuda_graph
+        self.graph_with_tp = graph_with_tp
         self._load(state_dict)
         n_pos = min(cfg.max_position_embeddings, max(max_seq_len, 16))
         self.cos, self.sin = rope_tables(cfg, n_pos, dtype, self.device)
@@ -88,6 +90,11 @@ class ChatTSForCausalLM:
         self.kv = torch.zeros(self.L, 2, num_pages, self.nkv, page_size, self.d, device=self.device, dtype=dtype)
         self.pool = PagePool(num_pages)
         self._steps = {}
+        self.peer, self.peer_tokens = None, 0
+        if tp_size > 1 and use_peer_allreduce:
+            from .tp import PeerBuffers
+            self.peer_tokens = max(max_batch, 64)
+            self.peer = PeerBuffers(self.ctx, tp_rank, tp_size, self.peer_tokens, self.H, group=comm)
 
     # ------------------------------------------------------------------------------------------ loading
     def _load(self, sd):
@@ -169,7 +176,7 @@ class ChatTSForCausalLM:
             attend(l)
             # ---- o_proj + residual + post-attention RMSNorm
             if self.tp_size > 1:
-                self._tp_row_parallel(st, T, st.ao, self.wo[l], self.ln2[l])
+                self._tp_row_parallel(st, T, st.ao, self.wo[l], self.ln2[l], 0)
             elif sp["o"] > 1:
                 c.gemm(st.ao, self.wo[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["o"], t=T)
                 c.reduce_residual_rmsnorm(st.ws, sp["o"], st.h, st.h, self.ln2[l], eps, st.xn, t=T)
@@ -185,7 +192,7 @@ class ChatTSForCausalLM:
             # ---- down_proj + residual + next layer's input RMSNorm (or the final norm)
             nw = self.ln1[l + 1] if l + 1 < self.L else self.final_norm
             if self.tp_size > 1:
-                self._tp_row_parallel(st, T, st.act, self.wd[l], nw)
+                self._tp_row_parallel(st, T, st.act, self.wd[l], nw, 1)
             elif sp["d"] > 1:
                 c.gemm(st.act, self.wd[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["d"], t=T)
                 c.reduce_residual_rmsnorm(st.ws, sp["d"], st.h, st.h, nw, eps, st.xn, t=T)
@@ -193,11 +200,16 @@ class ChatTSForCausalLM:
                 c.gemm(st.act, self.wd[l], st.h, residual=st.h, epilogue=EPI_RESIDUAL, t=T)
                 c.reduce_residual_rmsnorm(None, 0, st.h, None, nw, eps, st.xn, t=T)
 
-    def _tp_row_parallel(self, st, T, x, w, norm_w):
-        """Row-parallel projection under tensor parallelism: local partial -> sum over ranks -> residual+norm.
-        Round 1: the cross-rank sum is NCCL (torch.distributed) on the fp32 partial; DESIGN.md lists the
-        peer-memory fused version as the next multi-GPU item."""
+    def _tp_row_parallel(self, st, T, x, w, norm_w, which):
+        """Row-parallel projection under tensor parallelism: local fp32 partial -> sum over ranks -> residual + norm.
+        Decode-sized T: ONE kernel over NVLink peer memory (cts_peer_allreduce_residual_rmsnorm; buffers alternate
+        between o_proj (0) and down_proj (1)).  Large prefill T: NCCL all-reduce of the fp32 partial (bandwidth-bound)."""
         c = self.ctx
+        if self.peer is not None and T <= self.peer_tokens:
+            c.gemm(x, w, self.peer.local_partial(which), epilogue=EPI_PARTIAL_F32, split_k=1, t=T)
+            c.peer_allreduce_residual_rmsnorm(self.peer.partials[which], self.peer.flags, self.peer.state, self.tp_rank,
+                                              self.tp_size, st.h, st.h, norm_w, self.eps, st.xn, T)
+            return
         c.gemm(x, w, st.ws, epilogue=EPI_PARTIAL_F32, split_k=1, t=T)
         part = st.ws[: T * self.H]
         torch.distributed.all_reduce(part, group=self.comm)
@@ -368,7 +380,7 @@ class ChatTSForCausalLM:
 
     def _decode_step(self, st, sample=True):
         """One decode step for the whole batch; replays the captured CUDA graph when enabled."""
-        if not self.use_cuda_graph or self.tp_size > 1:
+        if not self.use_cuda_graph or (self.tp_size > 1 and not self.graph_with_tp):
             self._decode_body(st, sample)
             return
         attr = "graph" if sample else "graph_nosample"

@@ -167,6 +167,25 @@ int cts_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab, int ba
                        int* step_ptr, int* cur_ids, int* positions, int* seq_lens, int* slot_map,
                        const int* page_table, int max_pages, int page_size, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tensor parallelism over NVLink peer memory (replaces RowParallelLinear's NCCL all-reduce +
+ * residual add + RMSNorm, vllm qwen2.py:100-116,168-174,299-311, for decode-sized messages).
+ * cts_ipc_*: symmetric buffers -- cudaMalloc + cudaIpc handle on the owner, cudaIpcOpenMemHandle on the peers
+ *   (handle = 64 opaque bytes the host exchanges through torch.distributed).
+ * cts_peer_allreduce_residual_rmsnorm: ONE kernel = cross-GPU flag barrier + peer pull of every rank's fp32
+ *   partial [t,h] (rank order, bit-identical on all ranks) + residual add + RMSNorm.
+ *   peer_partials: device array float*[world] (entry r = rank r's partial buffer mapped in this process)
+ *   peer_flags:    device array int*[world]   (entry r = rank r's flag array int[world], zero-initialised)
+ *   state:         local int[2] {epoch, done-counter}, zero-initialised, owned by the kernel
+ */
+int cts_ipc_alloc(cts_ctx* ctx, long long bytes, void** dptr, unsigned char* handle64);
+int cts_ipc_open(cts_ctx* ctx, const unsigned char* handle64, void** dptr);
+int cts_ipc_close(cts_ctx* ctx, void* dptr);
+int cts_ipc_free(cts_ctx* ctx, void* dptr);
+int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const void* peer_partials, const void* peer_flags, int* state, int rank,
+                                        int world, const void* resid_in, void* resid_out, const void* norm_w, float eps,
+                                        void* norm_out, long long t, long long h, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
