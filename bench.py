@@ -289,7 +289,7 @@ def run_b200(args):
                 t = torch.tensor([ms], device="cuda")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms = float(t)
-            ctx_end = int(lay.lens.max()) + int(st.step_ptr.item())
+            ctx_end = int(lay.lens.max()) + int(st.step_ptr[0].item())
         finally:
             model.pool.release(held)
         return ms, per_step_launches, ctx_end

@@ -73,7 +73,7 @@ def load_library():
     lib.cts_attn_prefill.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, f, vp, i, vp]
     lib.cts_attn_decode_workspace_floats.argtypes = [i, i, i, i]
     lib.cts_attn_decode_workspace_floats.restype = ll
-    lib.cts_attn_decode.argtypes = [vp, vp, vp, vp, vp, i, vp, i, i, i, i, i, f, i, vp, vp, i, vp]
+    lib.cts_attn_decode.argtypes = [vp, vp, vp, vp, i, vp, i, vp, i, i, i, i, i, f, i, vp, vp, i, vp]
     lib.cts_greedy_advance.argtypes = [vp, vp, ll, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cts_ipc_alloc.argtypes = [vp, ll, C.POINTER(vp), C.c_char_p]
     lib.cts_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
@@ -207,9 +207,9 @@ class Context:
 
     def attn_decode(self, q, k_cache, v_cache, page_table, seq_lens, batch, nh, nkv, head_dim, page_size, scale, num_splits,
                     workspace, out):
-        self._chk(self.lib.cts_attn_decode(self.h, _p(q), _p(k_cache), _p(v_cache), _p(page_table), page_table.shape[1],
-                                           _p(seq_lens), batch, nh, nkv, head_dim, page_size, float(scale), num_splits,
-                                           _p(workspace), _p(out), dtype_code(q.dtype), _stream()), 2)
+        self._chk(self.lib.cts_attn_decode(self.h, _p(q), _p(k_cache), _p(v_cache), k_cache.shape[0], _p(page_table),
+                                           page_table.shape[1], _p(seq_lens), batch, nh, nkv, head_dim, page_size, float(scale),
+                                           num_splits, _p(workspace), _p(out), dtype_code(q.dtype), _stream()))
 
     def greedy_advance(self, logits, batch, out_tokens, step_ptr, cur_ids, positions, seq_lens, slot_map, page_table,
                        page_size):
@@ -217,7 +217,7 @@ class Context:
                                               out_tokens.stride(0) if out_tokens is not None else 0, _p(step_ptr), _p(cur_ids),
                                               _p(positions), _p(seq_lens), _p(slot_map), _p(page_table),
                                               page_table.shape[1] if page_table is not None else 0, page_size,
-                                              dtype_code(logits.dtype), _stream()), 2 if step_ptr is not None else 1)
+                                              dtype_code(logits.dtype), _stream()))
 
 
     # ------------------------------------------------------------------ tensor parallel (peer memory)

@@ -37,6 +37,8 @@ peer_allreduce_residual_rmsnorm_kernel(const float* const* __restrict__ peer_par
                                        int* __restrict__ state, int rank, int world, const T* __restrict__ resid_in,
                                        T* __restrict__ resid_out, const T* __restrict__ norm_w, float eps,
                                        T* __restrict__ norm_out, int h) {
+  pdl_trigger();
+  pdl_wait();
   const long long t = blockIdx.x;
   __shared__ const float* src[kMaxRanks];
   __shared__ float red[kThreads / 32];
@@ -162,13 +164,13 @@ extern "C" int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const void* pee
   CTS_CHECK_ARG(ctx, t > 0 && t <= 2147483647LL, "t");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == CTS_BF16)
-    peer_allreduce_residual_rmsnorm_kernel<__nv_bfloat16><<<(unsigned)t, kThreads, 0, st>>>(
-        (const float* const*)peer_partials, (int* const*)peer_flags, state, rank, world, (const __nv_bfloat16*)resid_in,
-        (__nv_bfloat16*)resid_out, (const __nv_bfloat16*)norm_w, eps, (__nv_bfloat16*)norm_out, (int)h);
+    CTS_CUDA(ctx, launch_pdl(peer_allreduce_residual_rmsnorm_kernel<__nv_bfloat16>, dim3((unsigned)t), dim3(kThreads), 0, st, 1,
+                             (const float* const*)peer_partials, (int* const*)peer_flags, state, rank, world,
+                             (const __nv_bfloat16*)resid_in, (__nv_bfloat16*)resid_out, (const __nv_bfloat16*)norm_w, eps,
+                             (__nv_bfloat16*)norm_out, (int)h));
   else
-    peer_allreduce_residual_rmsnorm_kernel<__half><<<(unsigned)t, kThreads, 0, st>>>(
-        (const float* const*)peer_partials, (int* const*)peer_flags, state, rank, world, (const __half*)resid_in,
-        (__half*)resid_out, (const __half*)norm_w, eps, (__half*)norm_out, (int)h);
-  CTS_LAUNCH_CHECK(ctx);
+    CTS_CUDA(ctx, launch_pdl(peer_allreduce_residual_rmsnorm_kernel<__half>, dim3((unsigned)t), dim3(kThreads), 0, st, 1,
+                             (const float* const*)peer_partials, (int* const*)peer_flags, state, rank, world, (const __half*)resid_in,
+                             (__half*)resid_out, (const __half*)norm_w, eps, (__half*)norm_out, (int)h));
   return CTS_OK;
 }

@@ -13,6 +13,7 @@
 #include <mma.h>
 
 #include "common.cuh"
+#include "tensormap.cuh"
 
 namespace {
 
@@ -72,6 +73,8 @@ attn_prefill_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
   float* s_all = reinterpret_cast<float*>(pf_smem + SM::q_bytes + 4 * SM::kv_bytes);
   T* p_all = reinterpret_cast<T*>(pf_smem + SM::q_bytes + 4 * SM::kv_bytes + SM::s_bytes);
 
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
   const int seq0 = cu_seqlens[b], len = cu_seqlens[b + 1] - seq0;
   const int q0 = qt * kPfQ;
@@ -226,190 +229,260 @@ attn_prefill_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
 }
 
 // ================================================================================================
-// decode
+// decode: tensor-core flash-decoding over TMA-staged, 128B-swizzled KV pages
 // ================================================================================================
-constexpr int kDecThreads = 128;
-constexpr int kMaxGroup = 8;    // q heads per kv head
+// grid (num_splits, nkv, batch); 5 warps: warps 0..3 consume (each owns 16 of the 64 tokens of a tile and runs its
+// own online softmax, merged once at the end), warp 4 is the TMA producer.  A tile = 64 tokens = 64/page_size pages;
+// every page of the cache is [page_size rows x head_dim] contiguous, fetched as head_dim/64 boxes of
+// [page_size x 128 B] with the 128-byte swizzle so that ldmatrix reads are bank-conflict free.
+//   S[16 x 16] = Q[16(heads, G valid) x d] K^T   mma.sync m16n8k16, K via ldmatrix
+//   O[16 x d] += P[16 x 16] V                    V via ldmatrix.trans
+// The tensor cores are used to cut instruction count, not for FLOPs: the kernel is bound by the KV stream
+// (GQA intensity nh/nkv flop per byte).  The last CTA of a (sequence, kv head) to finish merges the split partials
+// (self-resetting counter), so there is no separate combine launch.
+constexpr int kDecConsumers = 128;
+constexpr int kDecThreads = 160;
+constexpr int kDecStages = 3;
+constexpr int kDecTile = 64;
+constexpr int kMaxGroup = 8;    // q heads per kv head (rows 8..15 of the MMA tile are padding)
 
-// workspace per (batch, head, split): [m, l, o[HD]]
 __host__ __device__ inline long long dec_ws_stride(int hd) { return hd + 2; }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <typename T> __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                               uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void mma16816<__nv_bfloat16>(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                                     uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void mma16816<__half>(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                              uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  T v[2] = {DT<T>::from_f(lo), DT<T>::from_f(hi)};
+  return *reinterpret_cast<uint32_t*>(v);
+}
 
 template <typename T, int HD>
 __global__ void __launch_bounds__(kDecThreads)
-attn_decode_kernel(const T* __restrict__ q, const T* __restrict__ k_cache, const T* __restrict__ v_cache,
+attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v, const T* __restrict__ q,
                    const int* __restrict__ page_table, int max_pages, const int* __restrict__ seq_lens, int nh, int nkv,
-                   int page_size, float scale, int num_splits, float* __restrict__ ws) {
-  extern __shared__ __align__(128) uint8_t dec_smem[];
-  __shared__ uint64_t bar[2];
-  __shared__ float q_s[kMaxGroup][HD];
-  __shared__ float m_s[kMaxGroup], l_s[kMaxGroup], alpha_s[kMaxGroup];
+                   int page_size, float scale, int num_splits, float* __restrict__ ws, int* __restrict__ counters,
+                   T* __restrict__ out) {
+  constexpr int NHALF = HD / 64;                 // 128-byte column blocks per row
+  constexpr int KSTEPS = HD / 16;
+  constexpr int HALF_BYTES = kDecTile * 128;     // one [64 rows x 128 B] swizzled block
+  constexpr int TILE_BYTES = NHALF * HALF_BYTES; // K (or V) tile
+  extern __shared__ uint8_t dec_raw[];
+  __shared__ uint64_t full_bar[kDecStages];
+  __shared__ uint64_t empty_bar[kDecStages];
+  __shared__ int is_last_s;
+  const uint32_t raw = smem_u32(dec_raw);
+  uint8_t* smem = dec_raw + (((raw + 1023u) & ~1023u) - raw);      // [stage][K tile | V tile]
 
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int G = nh / nkv;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int seq_len = seq_lens[b];
-  const int n_pages = (seq_len + page_size - 1) / page_size;
-  const int pps = (n_pages + num_splits - 1) / num_splits;
-  const int pg0 = split * pps, pg1 = min(n_pages, pg0 + pps);
 
-  const size_t tile_elems = (size_t)page_size * HD;
-  T* k_s = reinterpret_cast<T*>(dec_smem);                       // [2][page][HD]
-  T* v_s = k_s + 2 * tile_elems;                                  // [2][page][HD]
-  float* sc = reinterpret_cast<float*>(v_s + 2 * tile_elems);     // [page][kMaxGroup]
-
-  // out accumulators: thread owns dim pair dp and a token stripe ts of every page
-  constexpr int NP = HD / 2;                 // dim pairs
-  constexpr int NSTRIPE = kDecThreads / NP;  // 2 for HD=128, 4 for HD=64
-  const int dp = tid % NP, stripe = tid / NP;
-  float acc[kMaxGroup][2];
-#pragma unroll
-  for (int g = 0; g < kMaxGroup; ++g) acc[g][0] = acc[g][1] = 0.f;
-
+  pdl_trigger();
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    for (int s = 0; s < kDecStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kDecConsumers / 32);
+    }
     fence_mbar_init();
   }
-  for (int i = tid; i < G * HD; i += kDecThreads) {
-    const int g = i / HD, d = i % HD;
-    q_s[g][d] = DT<T>::to_f(q[((long long)b * nh + (long long)kvh * G + g) * HD + d]);
-  }
-  if (tid < kMaxGroup) { m_s[tid] = -INFINITY; l_s[tid] = 0.f; }
   __syncthreads();
+  pdl_wait();          // q, the freshly written KV row, seq_lens and the workspace all come from predecessors
 
-  const uint32_t tile_bytes = (uint32_t)(tile_elems * sizeof(T));
-  auto issue = [&](int pg, int st) {
-    const long long page = page_table[(long long)b * max_pages + pg];
-    const T* kg = k_cache + ((page * nkv + kvh) * (long long)page_size) * HD;
-    const T* vg = v_cache + ((page * nkv + kvh) * (long long)page_size) * HD;
-    mbar_expect_tx(&bar[st], 2 * tile_bytes);
-    bulk_load_1d(k_s + (size_t)st * tile_elems, kg, tile_bytes, &bar[st]);
-    bulk_load_1d(v_s + (size_t)st * tile_elems, vg, tile_bytes, &bar[st]);
-  };
-  if (tid == 0 && pg0 < pg1) issue(pg0, 0);
+  const int seq_len = seq_lens[b];
+  const int n_tiles = (seq_len + kDecTile - 1) / kDecTile;
+  const int tps = (n_tiles + num_splits - 1) / num_splits;
+  const int tl0 = split * tps, tl1 = min(n_tiles, tl0 + tps);
+  const int ntl = max(tl1 - tl0, 0);
+  const int npp = kDecTile / page_size;          // pages per tile
 
-  const int n_groups = kDecThreads / page_size;    // thread groups over tokens (page_size in {16,32,64,128})
-  const int tk = tid % page_size, hh = tid / page_size;
-  constexpr int NCH = HD / 8;
-
-  for (int pg = pg0; pg < pg1; ++pg) {
-    const int it = pg - pg0, st = it & 1;
-    if (tid == 0 && pg + 1 < pg1) {                           // the other buffer was released by the barrier below
-      fence_proxy_async_smem();
-      issue(pg + 1, st ^ 1);
-    }
-    mbar_wait(&bar[st], (uint32_t)(it >> 1) & 1u);
-    const T* kt = k_s + (size_t)st * tile_elems;
-    const T* vt = v_s + (size_t)st * tile_elems;
-    // ---- scores: thread (tk, hh) -> heads hh, hh + n_groups, ...
-    {
-      float dot[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint4* krow = reinterpret_cast<const uint4*>(kt + (size_t)tk * HD);
-#pragma unroll 4
-      for (int c = 0; c < NCH; ++c) {
-        const int ch = (c + tk) % NCH;                // rotate the chunk order: conflict-free 16 B reads
-        float kf[8];
-        unpack8<T>(krow[ch], kf);
+  // accumulators of this warp (rows g = lane/4 are real heads when g < G)
+  const int g = lane >> 2, tq = lane & 3;
+  float oacc[HD / 8][4];
 #pragma unroll
-        for (int slot = 0; slot < 4; ++slot) {
-          const int g = hh + slot * n_groups;
-          if (g < G) {
-            const float4 qa = *reinterpret_cast<const float4*>(&q_s[g][ch * 8]);
-            const float4 qb = *reinterpret_cast<const float4*>(&q_s[g][ch * 8 + 4]);
-            dot[slot] += kf[0] * qa.x + kf[1] * qa.y + kf[2] * qa.z + kf[3] * qa.w + kf[4] * qb.x + kf[5] * qb.y +
-                         kf[6] * qb.z + kf[7] * qb.w;
+  for (int i = 0; i < HD / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  if (warp == kDecConsumers / 32) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      for (int it = 0; it < ntl; ++it) {
+        const int s = it % kDecStages;
+        const uint32_t ph = (uint32_t)(it / kDecStages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], (uint32_t)(2 * TILE_BYTES));
+        uint8_t* ks = smem + (size_t)s * 2 * TILE_BYTES;
+        uint8_t* vs = ks + TILE_BYTES;
+        for (int j = 0; j < npp; ++j) {
+          int pg = (tl0 + it) * npp + j;
+          pg = pg < max_pages ? pg : max_pages - 1;          // pages past the sequence are masked; keep the read in bounds
+          const int page = page_table[(long long)b * max_pages + pg];
+          const int row0 = (page * nkv + kvh) * page_size;
+#pragma unroll
+          for (int h = 0; h < NHALF; ++h) {
+            tma_load_2d(ks + h * HALF_BYTES + j * page_size * 128, &tm_k, &full_bar[s], h * 64, row0, CTS_L2_EVICT_FIRST);
+            tma_load_2d(vs + h * HALF_BYTES + j * page_size * 128, &tm_v, &full_bar[s], h * 64, row0, CTS_L2_EVICT_FIRST);
           }
         }
       }
-      const bool valid = pg * page_size + tk < seq_len;
-#pragma unroll
-      for (int slot = 0; slot < 4; ++slot) {
-        const int g = hh + slot * n_groups;
-        if (g < G) sc[tk * kMaxGroup + g] = valid ? dot[slot] * scale : -INFINITY;
-      }
     }
-    __syncthreads();
-    // ---- online softmax: warp w handles heads w, w+4
-    for (int g = warp; g < G; g += kDecThreads / 32) {
-      float mx = -INFINITY;
-      for (int t = lane; t < page_size; t += 32) mx = fmaxf(mx, sc[t * kMaxGroup + g]);
-      mx = warp_max(mx);
-      const float m_old = m_s[g];
-      const float m_new = fmaxf(m_old, mx);
-      float sum = 0.f;
-      for (int t = lane; t < page_size; t += 32) {
-        const float s = sc[t * kMaxGroup + g];
-        const float p = (m_new > -INFINITY) ? __expf(s - m_new) : 0.f;
-        sc[t * kMaxGroup + g] = p;
-        sum += p;
-      }
-      sum = warp_sum(sum);
-      if (lane == 0) {
-        const float a = (m_old > -INFINITY) ? __expf(m_old - m_new) : 0.f;
-        alpha_s[g] = a;
-        l_s[g] = l_s[g] * a + sum;
-        m_s[g] = m_new;
-      }
-    }
-    __syncthreads();
-    // ---- O update: thread (dp, stripe)
+  } else {
+    // ------------------------------ consumers ------------------------------
+    // Q as the A operand: row g = head, the padding rows (g+8) are zero
+    uint32_t qa[KSTEPS][2];
     {
+      const T* qrow = q + ((long long)b * nh + (long long)kvh * G + (g < G ? g : 0)) * HD;
 #pragma unroll
-      for (int g = 0; g < kMaxGroup; ++g) {
-        if (g < G) { const float a = alpha_s[g]; acc[g][0] *= a; acc[g][1] *= a; }
-      }
-      for (int t = stripe; t < page_size; t += NSTRIPE) {
-        const uint32_t vraw = *reinterpret_cast<const uint32_t*>(vt + (size_t)t * HD + 2 * dp);
-        const T* vp = reinterpret_cast<const T*>(&vraw);
-        const float v0 = DT<T>::to_f(vp[0]), v1 = DT<T>::to_f(vp[1]);
-        const float4 pa = *reinterpret_cast<const float4*>(&sc[t * kMaxGroup]);
-        const float4 pb = *reinterpret_cast<const float4*>(&sc[t * kMaxGroup + 4]);
-        const float pr[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-#pragma unroll
-        for (int g = 0; g < kMaxGroup; ++g) {
-          if (g < G) { acc[g][0] += pr[g] * v0; acc[g][1] += pr[g] * v1; }
-        }
+      for (int kk = 0; kk < KSTEPS; ++kk) {
+        qa[kk][0] = g < G ? *reinterpret_cast<const uint32_t*>(qrow + kk * 16 + tq * 2) : 0u;
+        qa[kk][1] = g < G ? *reinterpret_cast<const uint32_t*>(qrow + kk * 16 + 8 + tq * 2) : 0u;
       }
     }
-    __syncthreads();    // everyone is done with buffer st and with sc before they are overwritten
+    const float sl2 = scale * 1.4426950408889634f;
+    const int lm = lane >> 3, lr = lane & 7;       // ldmatrix: this lane supplies row lr of matrix lm
+    for (int it = 0; it < ntl; ++it) {
+      const int s = it % kDecStages;
+      mbar_wait(&full_bar[s], (uint32_t)(it / kDecStages) & 1u);
+      const uint32_t kbase = smem_u32(smem + (size_t)s * 2 * TILE_BYTES);
+      const uint32_t vbase = kbase + TILE_BYTES;
+      // ---- S = Q K^T for this warp's 16 tokens (2 n-tiles of 8)
+      float sacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+      for (int kk = 0; kk < KSTEPS; ++kk) {
+        const int row = warp * 16 + (lm >> 1) * 8 + lr;          // matrices: (nt0,k0-7) (nt0,k8-15) (nt1,k0-7) (nt1,k8-15)
+        const int chunk = (kk & 3) * 2 + (lm & 1);
+        uint32_t bf[4];
+        ldsm_x4(kbase + (kk >> 2) * HALF_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4), bf);
+        mma16816<T>(sacc[0], qa[kk][0], 0u, qa[kk][1], 0u, bf[0], bf[1]);
+        mma16816<T>(sacc[1], qa[kk][0], 0u, qa[kk][1], 0u, bf[2], bf[3]);
+      }
+      // ---- online softmax on row g (values of a row live in the 4 lanes of a quad)
+      const int tok0 = (tl0 + it) * kDecTile + warp * 16 + tq * 2;
+      float sv[2][2];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const bool valid = tok0 + nt * 8 + j < seq_len;
+          sv[nt][j] = valid ? sacc[nt][j] * sl2 : -INFINITY;
+          mx = fmaxf(mx, sv[nt][j]);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_run, mx);
+      float alpha = 1.f, p[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+      if (m_new > -INFINITY) {
+        alpha = m_run > -INFINITY ? exp2f(m_run - m_new) : 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) p[nt][j] = exp2f(sv[nt][j] - m_new);      // exp2(-inf) = 0 for masked tokens
+      }
+      float ps = p[0][0] + p[0][1] + p[1][0] + p[1][1];
+      ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+      l_run = l_run * alpha + ps;
+      m_run = m_new;
+#pragma unroll
+      for (int i = 0; i < HD / 8; ++i) { oacc[i][0] *= alpha; oacc[i][1] *= alpha; }
+      // ---- O += P V ; P (row g x 16 tokens) is the A operand straight from the S accumulator layout
+      const uint32_t pa0 = pack2<T>(p[0][0], p[0][1]), pa2 = pack2<T>(p[1][0], p[1][1]);
+#pragma unroll
+      for (int dp = 0; dp < HD / 16; ++dp) {
+        const int row = warp * 16 + (lm & 1) * 8 + lr;           // matrices: (tok0-7,dn) (tok8-15,dn) (tok0-7,dn+1) (tok8-15,dn+1)
+        const int chunk = 2 * dp + (lm >> 1);
+        uint32_t bf[4];
+        ldsm_x4_trans(vbase + (chunk >> 3) * HALF_BYTES + row * 128 + (((chunk & 7) ^ (row & 7)) << 4), bf);
+        mma16816<T>(oacc[2 * dp], pa0, 0u, pa2, 0u, bf[0], bf[1]);
+        mma16816<T>(oacc[2 * dp + 1], pa0, 0u, pa2, 0u, bf[2], bf[3]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
   }
+  __syncthreads();     // every tile consumed: the ring can be reused as merge scratch
 
-  // ---- merge the token stripes and write this split's partial (m, l, o)
-  float* red = reinterpret_cast<float*>(dec_smem);      // reuse: [NSTRIPE][G][HD]
-  for (int g = 0; g < G; ++g) {
-    red[((size_t)stripe * kMaxGroup + g) * HD + 2 * dp] = acc[g][0];
-    red[((size_t)stripe * kMaxGroup + g) * HD + 2 * dp + 1] = acc[g][1];
+  // ---- merge the 4 consumer warps (disjoint token subsets) -> this split's (m, l, o)
+  float* m_sm = reinterpret_cast<float*>(smem);                 // [4][8]
+  float* l_sm = m_sm + 32;                                      // [4][8]
+  float* o_sm = l_sm + 32;                                      // [4][8][HD]
+  if (warp < kDecConsumers / 32 && g < G) {
+    if (tq == 0) { m_sm[warp * 8 + g] = m_run; l_sm[warp * 8 + g] = l_run; }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      o_sm[(warp * 8 + g) * HD + i * 8 + tq * 2] = oacc[i][0];
+      o_sm[(warp * 8 + g) * HD + i * 8 + tq * 2 + 1] = oacc[i][1];
+    }
   }
   __syncthreads();
   const long long wstride = dec_ws_stride(HD);
+  const long long head0 = (long long)b * nh + (long long)kvh * G;
   for (int i = tid; i < G * HD; i += kDecThreads) {
-    const int g = i / HD, d = i % HD;
-    float o = 0.f;
+    const int gg = i / HD, d = i % HD;
+    float M = -INFINITY;
 #pragma unroll
-    for (int s2 = 0; s2 < NSTRIPE; ++s2) o += red[((size_t)s2 * kMaxGroup + g) * HD + d];
-    float* w = ws + (((long long)b * nh + (long long)kvh * G + g) * num_splits + split) * wstride;
-    w[2 + d] = o;
-    if (d == 0) { w[0] = m_s[g]; w[1] = l_s[g]; }
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, m_sm[w * 8 + gg]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = m_sm[w * 8 + gg];
+      const float f = mw > -INFINITY ? exp2f(mw - M) : 0.f;
+      L += l_sm[w * 8 + gg] * f;
+      O += o_sm[(w * 8 + gg) * HD + d] * f;
+    }
+    if (num_splits == 1) {
+      out[(head0 + gg) * HD + d] = DT<T>::from_f(L > 0.f ? O / L : 0.f);
+    } else {
+      float* w = ws + ((head0 + gg) * num_splits + split) * wstride;
+      w[2 + d] = O;
+      if (d == 0) { w[0] = M; w[1] = L; }
+    }
   }
-}
-
-template <typename T, int HD>
-__global__ void attn_decode_combine_kernel(const float* __restrict__ ws, int num_splits, T* __restrict__ out) {
-  // grid (nh, batch); block HD threads
-  const long long bh = (long long)blockIdx.y * gridDim.x + blockIdx.x;
-  const int d = threadIdx.x;
-  const long long wstride = dec_ws_stride(HD);
-  const float* w = ws + bh * num_splits * wstride;
-  float m = -INFINITY;
-  for (int s = 0; s < num_splits; ++s) m = fmaxf(m, w[s * wstride]);
-  float l = 0.f, o = 0.f;
-  for (int s = 0; s < num_splits; ++s) {
-    const float ms = w[s * wstride];
-    const float sc = (ms > -INFINITY) ? __expf(ms - m) : 0.f;
-    l += w[s * wstride + 1] * sc;
-    o += w[s * wstride + 2 + d] * sc;
+  if (num_splits == 1) return;
+  // ---- the last split of this (sequence, kv head) to arrive merges all partials
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(&counters[b * nkv + kvh], 1);
+    is_last_s = prev == num_splits - 1;
   }
-  out[bh * HD + d] = DT<T>::from_f(l > 0.f ? o / l : 0.f);
+  __syncthreads();
+  if (!is_last_s) return;
+  __threadfence();
+  for (int i = tid; i < G * HD; i += kDecThreads) {
+    const int gg = i / HD, d = i % HD;
+    const float* w = ws + (head0 + gg) * num_splits * wstride;
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < num_splits; ++s2) M = fmaxf(M, __ldcg(w + s2 * wstride));
+    float L = 0.f, O = 0.f;
+    for (int s2 = 0; s2 < num_splits; ++s2) {
+      const float ms = __ldcg(w + s2 * wstride);
+      const float f = ms > -INFINITY ? exp2f(ms - M) : 0.f;
+      L += __ldcg(w + s2 * wstride + 1) * f;
+      O += __ldcg(w + s2 * wstride + 2 + d) * f;
+    }
+    out[(head0 + gg) * HD + d] = DT<T>::from_f(L > 0.f ? O / L : 0.f);
+  }
+  if (tid == 0) counters[b * nkv + kvh] = 0;       // self-resetting for the next launch
 }
 
 }  // namespace
@@ -431,7 +504,8 @@ extern "C" int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, cons
     auto kern = attn_prefill_kernel<TT, HDV>;                                                                \
     const size_t smem = PfSmem<HDV>::total;                                                                  \
     CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
-    kern<<<grid, kPfThreads, smem, st>>>((const TT*)q, (const TT*)k, (const TT*)v, cu_seqlens, nh, nkv, scale, (TT*)out); \
+    CTS_CUDA(ctx, launch_pdl(kern, grid, dim3(kPfThreads), smem, st, 1, (const TT*)q, (const TT*)k, (const TT*)v, cu_seqlens, nh, nkv, \
+                             scale, (TT*)out));                                                              \
   }
   if (dtype == CTS_BF16) {
     if (head_dim == 128) PF_LAUNCH(__nv_bfloat16, 128) else PF_LAUNCH(__nv_bfloat16, 64)
@@ -444,36 +518,41 @@ extern "C" int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, cons
 }
 
 extern "C" long long cts_attn_decode_workspace_floats(int batch, int nh, int head_dim, int num_splits) {
-  return (long long)batch * nh * num_splits * dec_ws_stride(head_dim);
+  // fp32 partials [batch, nh, splits, head_dim + 2] followed by int32 arrival counters [batch * nh] (upper bound on
+  // batch * nkv).  The caller zero-fills the buffer ONCE; the counters reset themselves after every launch.
+  return (long long)batch * nh * num_splits * dec_ws_stride(head_dim) + (long long)batch * nh;
 }
 
-extern "C" int cts_attn_decode(cts_ctx* ctx, const void* q, const void* k_cache, const void* v_cache, const int* page_table,
-                               int max_pages, const int* seq_lens, int batch, int nh, int nkv, int head_dim, int page_size,
-                               float scale, int num_splits, float* workspace, void* out, int dtype, void* stream) {
+extern "C" int cts_attn_decode(cts_ctx* ctx, const void* q, const void* k_cache, const void* v_cache, int num_pages,
+                               const int* page_table, int max_pages, const int* seq_lens, int batch, int nh, int nkv,
+                               int head_dim, int page_size, float scale, int num_splits, float* workspace, void* out, int dtype,
+                               void* stream) {
   if (!ctx) return CTS_ERR_BAD_ARG;
   CTS_CHECK_ARG(ctx, q && k_cache && v_cache && page_table && seq_lens && workspace && out, "null pointer");
   CTS_CHECK_ARG(ctx, nh > 0 && nkv > 0 && nh % nkv == 0 && nh / nkv <= kMaxGroup, "nh/nkv must be an integer <= 8");
-  CTS_CHECK_ARG(ctx, page_size == 16 || page_size == 32 || page_size == 64 || page_size == 128, "page_size must be 16, 32, 64 or 128");
+  CTS_CHECK_ARG(ctx, page_size == 16 || page_size == 32 || page_size == 64, "page_size must be 16, 32 or 64");
   CTS_CHECK_ARG(ctx, num_splits >= 1 && num_splits <= 65535, "num_splits");
+  CTS_CHECK_ARG(ctx, num_pages > 0 && max_pages > 0, "num_pages / max_pages");
+  CTS_CHECK_ARG(ctx, (long long)num_pages * nkv * page_size < 2147483647LL, "KV cache too large for 32-bit TMA row coordinates");
   CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
   if (head_dim != 64 && head_dim != 128) return cts_set_error(ctx, CTS_ERR_UNSUPPORTED, "cts_attn_decode: head_dim %d (64 or 128)", head_dim);
-  // 4 score slots per thread must cover all q heads of a kv head
-  CTS_CHECK_ARG(ctx, (nh / nkv) <= 4 * (kDecThreads / page_size), "page_size too large for this GQA group");
   if (batch == 0) return CTS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)num_pages * nkv * page_size;
+  CUtensorMap tm_k, tm_v;
+  int rc = cts_make_tmap_2d(ctx, &tm_k, k_cache, rows, head_dim, head_dim, page_size, dtype == CTS_BF16);
+  if (rc) return rc;
+  rc = cts_make_tmap_2d(ctx, &tm_v, v_cache, rows, head_dim, head_dim, page_size, dtype == CTS_BF16);
+  if (rc) return rc;
+  int* counters = reinterpret_cast<int*>(workspace + (long long)batch * nh * num_splits * dec_ws_stride(head_dim));
   dim3 grid((unsigned)num_splits, (unsigned)nkv, (unsigned)batch);
-  dim3 cgrid((unsigned)nh, (unsigned)batch);
-  size_t smem = (size_t)4 * page_size * head_dim * 2 + (size_t)page_size * kMaxGroup * 4;
-  const size_t red_bytes = (size_t)(kDecThreads / (head_dim / 2)) * kMaxGroup * head_dim * 4;
-  if (smem < red_bytes) smem = red_bytes;
+  const size_t smem = (size_t)kDecStages * 2 * (head_dim / 64) * kDecTile * 128 + 1024;
 #define DEC_LAUNCH(TT, HDV)                                                                                    \
   {                                                                                                            \
     auto kern = attn_decode_kernel<TT, HDV>;                                                                   \
     CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-    kern<<<grid, kDecThreads, smem, st>>>((const TT*)q, (const TT*)k_cache, (const TT*)v_cache, page_table, max_pages, \
-                                          seq_lens, nh, nkv, page_size, scale, num_splits, workspace);        \
-    CTS_LAUNCH_CHECK(ctx);                                                                                     \
-    attn_decode_combine_kernel<TT, HDV><<<cgrid, HDV, 0, st>>>(workspace, num_splits, (TT*)out);               \
+    CTS_CUDA(ctx, launch_pdl(kern, grid, dim3(kDecThreads), smem, st, 1, tm_k, tm_v, (const TT*)q, page_table, max_pages, seq_lens, \
+                             nh, nkv, page_size, scale, num_splits, workspace, counters, (TT*)out));           \
   }
   if (dtype == CTS_BF16) {
     if (head_dim == 128) DEC_LAUNCH(__nv_bfloat16, 128) else DEC_LAUNCH(__nv_bfloat16, 64)
@@ -481,6 +560,5 @@ extern "C" int cts_attn_decode(cts_ctx* ctx, const void* q, const void* k_cache,
     if (head_dim == 128) DEC_LAUNCH(__half, 128) else DEC_LAUNCH(__half, 64)
   }
 #undef DEC_LAUNCH
-  CTS_LAUNCH_CHECK(ctx);
   return CTS_OK;
 }

@@ -46,6 +46,42 @@ int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);
 static inline long long cdiv_ll(long long a, long long b) { return (a + b - 1) / b; }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched with the
+// programmatic-stream-serialization attribute, calls pdl_trigger() first thing (so its successor may be
+// scheduled as soon as all of this grid's CTAs are resident) and pdl_wait() before it touches anything a
+// predecessor produced.  Prologues (barrier init, TMEM alloc, tensor-map prefetch and -- in the GEMM -- the
+// TMA prefetch of the WEIGHT tiles, which no kernel ever writes) thereby overlap the predecessor's tail:
+// the decode step is ~480 short kernels, and this removes the launch/ramp bubble between them.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     unsigned cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[n].val.programmaticStreamSerializationAllowed = 1;
+  ++n;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ----------------------------------------------------------------------------------------------
 // dtype helpers: the model dtype is bf16 or fp16 (F5 in SURVEY.md: the reference runs fp16, the
 // baseline configs say bf16).  Every elementwise result is rounded to the model dtype exactly where
 // the HF/torch reference rounds it.

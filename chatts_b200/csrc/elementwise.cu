@@ -7,6 +7,8 @@
 //   cts_embed_gather             token embedding lookup (rows of <ts> patches are skipped: the encoder scatters them)
 //   cts_greedy_advance           argmax + device-side decode bookkeeping (graph-replayable decode loop)
 // Rounding points follow transformers' Qwen2 in the model dtype (modeling_qwen2.py line numbers in the header).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace {
@@ -16,6 +18,8 @@ template <typename T>
 __global__ void reduce_bias_act_kernel(const float* __restrict__ part, int S, long long t_total, long long n,
                                        const T* __restrict__ bias, int act, T* __restrict__ out, long long out_ld,
                                        const int* __restrict__ row_map) {
+  pdl_trigger();
+  pdl_wait();
   const long long t = blockIdx.y;
   long long row = t;
   if (row_map) {
@@ -60,6 +64,8 @@ __global__ void __launch_bounds__(kNormThreads)
 reduce_residual_rmsnorm_kernel(const float* __restrict__ part, int S, const T* __restrict__ resid_in,
                                T* __restrict__ resid_out, const T* __restrict__ norm_w, float eps,
                                T* __restrict__ norm_out, long long t_total, int h) {
+  pdl_trigger();
+  pdl_wait();
   const long long t = blockIdx.x;
   const int nvec = h / 8;
   float vals[kNormMaxVec][8];
@@ -117,10 +123,91 @@ reduce_residual_rmsnorm_kernel(const float* __restrict__ part, int S, const T* _
   }
 }
 
+// Cluster version: C CTAs (one thread-block cluster) share a token; each owns h/C columns, the sum of squares is
+// exchanged through distributed shared memory.  At decode (T <= 32 tokens) this turns a 32-CTA kernel into a
+// 256-CTA one, so the split-K partials are pulled from L2 by every SM instead of by 32 of them.
+constexpr int kClThreads = 128;
+constexpr int kClMaxVec = 4;     // h / C <= 8 * 4 * 128 = 4096 columns per CTA
+
+template <typename T>
+__global__ void __launch_bounds__(kClThreads)
+reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ part, int S, const T* __restrict__ resid_in,
+                                       T* __restrict__ resid_out, const T* __restrict__ norm_w, float eps,
+                                       T* __restrict__ norm_out, long long t_total, int h) {
+  pdl_trigger();
+  pdl_wait();
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const long long t = blockIdx.y;
+  const int hc = h / C, col0 = crank * hc, nvec = hc / 8;
+  float vals[kClMaxVec][8];
+  float ss = 0.f;
+  const long long stride = t_total * (long long)h;
+#pragma unroll
+  for (int it = 0; it < kClMaxVec; ++it) {
+    const int v = it * kClThreads + threadIdx.x;
+    if (v < nvec) {
+      const long long off = t * h + col0 + (long long)v * 8;
+      float r[8];
+      unpack8<T>(*reinterpret_cast<const uint4*>(resid_in + off), r);
+      if (S > 0) {
+        float a[8];
+        const float* p = part + off;
+        float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
+        a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+        for (int s = 1; s < S; ++s) {
+          lo = *reinterpret_cast<const float4*>(p + s * stride);
+          hi = *reinterpret_cast<const float4*>(p + s * stride + 4);
+          a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w; a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = rnd<T>(r[j] + rnd<T>(a[j]));
+        if (resid_out) *reinterpret_cast<uint4*>(resid_out + off) = pack8<T>(r);
+      } else if (resid_out && resid_out != resid_in) {
+        *reinterpret_cast<uint4*>(resid_out + off) = pack8<T>(r);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { vals[it][j] = r[j]; ss += r[j] * r[j]; }
+    }
+  }
+  __shared__ float red[kClThreads / 32];
+  __shared__ float ss_cta;
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kClThreads / 32; ++w) v += red[w];
+    ss_cta = v;
+  }
+  cluster.sync();
+  float tot = 0.f;
+  for (int r = 0; r < C; ++r) tot += *cluster.map_shared_rank(&ss_cta, r);     // fixed order: same value in all CTAs
+  cluster.sync();                                                              // nobody exits while peers still read
+  if (norm_out == nullptr) return;
+  const float inv = 1.0f / sqrtf(tot / (float)h + eps);
+#pragma unroll
+  for (int it = 0; it < kClMaxVec; ++it) {
+    const int v = it * kClThreads + threadIdx.x;
+    if (v < nvec) {
+      float w[8], o[8];
+      unpack8<T>(*reinterpret_cast<const uint4*>(norm_w + col0 + (long long)v * 8), w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = w[j] * rnd<T>(vals[it][j] * inv);
+      *reinterpret_cast<uint4*>(norm_out + t * h + col0 + (long long)v * 8) = pack8<T>(o);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void reduce_swiglu_kernel(const float* __restrict__ part, int S, long long t_total, long long inter,
                                      T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long t = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= inter) return;
@@ -145,6 +232,8 @@ __global__ void qkv_rope_cache_kernel(const void* __restrict__ src, int src_is_p
                                       T* __restrict__ q_out, T* __restrict__ k_cache, T* __restrict__ v_cache,
                                       T* __restrict__ k_out, T* __restrict__ v_out, long long t_total, int nh, int nkv,
                                       int d, int page_size) {
+  pdl_trigger();
+  pdl_wait();
   const int head = blockIdx.x;
   const long long t = blockIdx.y;
   const int half = d >> 1;
@@ -205,6 +294,8 @@ __global__ void qkv_rope_cache_kernel(const void* __restrict__ src, int src_is_p
 template <typename T>
 __global__ void embed_gather_kernel(const T* __restrict__ table, const int* __restrict__ ids, T* __restrict__ out,
                                     long long h, long long vocab) {
+  pdl_trigger();
+  pdl_wait();
   const long long t = blockIdx.x;
   const int id = ids[t];
   if (id < 0 || id >= vocab) return;
@@ -218,9 +309,11 @@ __global__ void embed_gather_kernel(const T* __restrict__ table, const int* __re
 template <typename T>
 __global__ void __launch_bounds__(1024)
 greedy_advance_kernel(const T* __restrict__ logits, long long vocab, int* __restrict__ out_tokens, int out_ld,
-                      const int* __restrict__ step_ptr, int* __restrict__ cur_ids, int* __restrict__ positions,
+                      int* __restrict__ step_ptr, int* __restrict__ cur_ids, int* __restrict__ positions,
                       int* __restrict__ seq_lens, int* __restrict__ slot_map, const int* __restrict__ page_table,
                       int max_pages, int page_size) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const T* row = logits + (long long)b * vocab;
   float best = -INFINITY;
@@ -266,7 +359,7 @@ greedy_advance_kernel(const T* __restrict__ logits, long long vocab, int* __rest
     }
     if (lane == 0) {
       const int tok = best_i < vocab ? (int)best_i : 0;
-      const int step = step_ptr ? step_ptr[0] : 0;
+      const int step = step_ptr ? step_ptr[0] : 0;      // step_ptr[0] only changes after every CTA has passed here
       if (out_tokens) out_tokens[(long long)b * out_ld + step] = tok;
       if (cur_ids) cur_ids[b] = tok;
       if (positions) {
@@ -278,11 +371,17 @@ greedy_advance_kernel(const T* __restrict__ logits, long long vocab, int* __rest
           slot_map[b] = pg < max_pages ? page_table[(long long)b * max_pages + pg] * page_size + np % page_size : -1;
         }
       }
+      if (step_ptr) {
+        __threadfence();
+        const int done = atomicAdd(&step_ptr[1], 1) + 1;     // step_ptr = {step, done-counter}
+        if (done == (int)gridDim.x) {
+          step_ptr[1] = 0;
+          step_ptr[0] = step + 1;
+        }
+      }
     }
   }
 }
-
-__global__ void step_increment_kernel(int* step_ptr) { step_ptr[0] += 1; }
 
 }  // namespace
 
@@ -307,9 +406,8 @@ extern "C" int cts_reduce_bias_act(cts_ctx* ctx, const float* partial, int split
   if (t == 0) return CTS_OK;
   const int threads = 128;
   dim3 grid((unsigned)cdiv_ll(cdiv_ll(n, 4), threads), (unsigned)t);
-  DISPATCH_T(dtype, reduce_bias_act_kernel<T><<<grid, threads, 0, (cudaStream_t)stream>>>(
-                        partial, split_k, t, n, (const T*)bias, act, (T*)out, out_ld, row_map));
-  CTS_LAUNCH_CHECK(ctx);
+  DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_bias_act_kernel<T>, grid, dim3(threads), 0, (cudaStream_t)stream, 1, partial, split_k, t,
+                                              n, (const T*)bias, act, (T*)out, out_ld, row_map)));
   return CTS_OK;
 }
 
@@ -324,9 +422,20 @@ extern "C" int cts_reduce_residual_rmsnorm(cts_ctx* ctx, const float* partial, i
   CTS_CHECK_ARG(ctx, split_k == 0 || resid_out != nullptr, "resid_out required when reducing partials");
   CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
   if (t == 0) return CTS_OK;
-  DISPATCH_T(dtype, reduce_residual_rmsnorm_kernel<T><<<(unsigned)t, kNormThreads, 0, (cudaStream_t)stream>>>(
-                        partial, split_k, (const T*)resid_in, (T*)resid_out, (const T*)norm_w, eps, (T*)norm_out, t, (int)h));
-  CTS_LAUNCH_CHECK(ctx);
+  // thread-block cluster over the hidden dimension when the row is wide enough (DSMEM exchange of the sum of squares)
+  unsigned C = 1;
+  for (unsigned c : {8u, 4u, 2u}) {
+    if (h % (8 * c) == 0 && h / (8 * c) >= 32 && h / c <= 8LL * kClMaxVec * kClThreads) { C = c; break; }
+  }
+  if (C > 1 && t <= 65535) {
+    DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_residual_rmsnorm_cluster_kernel<T>, dim3(C, (unsigned)t), dim3(kClThreads), 0,
+                                                (cudaStream_t)stream, C, partial, split_k, (const T*)resid_in, (T*)resid_out,
+                                                (const T*)norm_w, eps, (T*)norm_out, t, (int)h)));
+  } else {
+    DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_residual_rmsnorm_kernel<T>, dim3((unsigned)t), dim3(kNormThreads), 0,
+                                                (cudaStream_t)stream, 1, partial, split_k, (const T*)resid_in, (T*)resid_out,
+                                                (const T*)norm_w, eps, (T*)norm_out, t, (int)h)));
+  }
   return CTS_OK;
 }
 
@@ -338,8 +447,8 @@ extern "C" int cts_reduce_swiglu(cts_ctx* ctx, const float* partial, int split_k
   CTS_CHECK_ARG(ctx, t <= 65535, "t > 65535");
   if (t == 0) return CTS_OK;
   dim3 grid((unsigned)cdiv_ll(inter, 256), (unsigned)t);
-  DISPATCH_T(dtype, reduce_swiglu_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(partial, split_k, t, inter, (T*)out));
-  CTS_LAUNCH_CHECK(ctx);
+  DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_swiglu_kernel<T>, grid, dim3(256), 0, (cudaStream_t)stream, 1, partial, split_k, t,
+                                              inter, (T*)out)));
   return CTS_OK;
 }
 
@@ -366,13 +475,12 @@ extern "C" int cts_qkv_rope_cache(cts_ctx* ctx, const void* src, int src_is_part
     }
     const void* src_c = src_is_partial ? src : (const void*)((const char*)src + tb * width * 2);
     DISPATCH_T(dtype,
-               qkv_rope_cache_kernel<T><<<grid, threads, 0, (cudaStream_t)stream>>>(
-                   src_c, src_is_partial, split_k, (const T*)bias, positions + tb, (const T*)cos_tab, (const T*)sin_tab,
-                   slot_map ? slot_map + tb : nullptr, (T*)q_out + tb * (long long)nh * head_dim, (T*)k_cache, (T*)v_cache,
-                   k_out ? (T*)k_out + tb * (long long)nkv * head_dim : nullptr,
-                   v_out ? (T*)v_out + tb * (long long)nkv * head_dim : nullptr, src_is_partial ? t : tc, nh, nkv, head_dim,
-                   page_size));
-    CTS_LAUNCH_CHECK(ctx);
+               CTS_CUDA(ctx, launch_pdl(qkv_rope_cache_kernel<T>, grid, dim3(threads), 0, (cudaStream_t)stream, 1, src_c, src_is_partial,
+                                        split_k, (const T*)bias, positions + tb, (const T*)cos_tab, (const T*)sin_tab,
+                                        slot_map ? slot_map + tb : (const int*)nullptr, (T*)q_out + tb * (long long)nh * head_dim,
+                                        (T*)k_cache, (T*)v_cache, k_out ? (T*)k_out + tb * (long long)nkv * head_dim : (T*)nullptr,
+                                        v_out ? (T*)v_out + tb * (long long)nkv * head_dim : (T*)nullptr,
+                                        src_is_partial ? t : tc, nh, nkv, head_dim, page_size)));
   }
   return CTS_OK;
 }
@@ -384,8 +492,8 @@ extern "C" int cts_embed_gather(cts_ctx* ctx, const void* table, const int* ids,
   CTS_CHECK_ARG(ctx, h > 0 && h % 8 == 0, "h must be a multiple of 8");
   CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
   if (t == 0) return CTS_OK;
-  DISPATCH_T(dtype, embed_gather_kernel<T><<<(unsigned)t, 128, 0, (cudaStream_t)stream>>>((const T*)table, ids, (T*)out, h, vocab));
-  CTS_LAUNCH_CHECK(ctx);
+  DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(embed_gather_kernel<T>, dim3((unsigned)t), dim3(128), 0, (cudaStream_t)stream, 1,
+                                              (const T*)table, ids, (T*)out, h, vocab)));
   return CTS_OK;
 }
 
@@ -397,13 +505,8 @@ extern "C" int cts_greedy_advance(cts_ctx* ctx, const void* logits, long long vo
   CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
   CTS_CHECK_ARG(ctx, page_size > 0 || slot_map == nullptr, "page_size");
   if (batch == 0) return CTS_OK;
-  DISPATCH_T(dtype, greedy_advance_kernel<T><<<batch, 1024, 0, (cudaStream_t)stream>>>(
-                        (const T*)logits, vocab, out_tokens, out_ld, step_ptr, cur_ids, positions, seq_lens, slot_map,
-                        page_table, max_pages, page_size > 0 ? page_size : 1));
-  CTS_LAUNCH_CHECK(ctx);
-  if (step_ptr) {
-    step_increment_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr);
-    CTS_LAUNCH_CHECK(ctx);
-  }
+  DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(greedy_advance_kernel<T>, dim3(batch), dim3(1024), 0, (cudaStream_t)stream, 1,
+                                              (const T*)logits, vocab, out_tokens, out_ld, step_ptr, cur_ids, positions, seq_lens,
+                                              slot_map, page_table, max_pages, page_size > 0 ? page_size : 1)));
   return CTS_OK;
 }

@@ -78,6 +78,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   const int kb1 = (int)(((long long)p.kb_total * (split + 1)) / p.split_k);
   const int nkb = kb1 - kb0;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_x);
@@ -98,7 +99,22 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
+      // Phase 1 (before the dependency wait): the WEIGHT tiles of the first `stages` K blocks.  Nobody writes
+      // weights, so this stream may start while the predecessor kernel is still running (PDL).
+      const int npre = nkb < stages ? nkb : stages;
+      for (int i = 0; i < npre; ++i) {
+        mbar_expect_tx(&full_bar[i], (uint32_t)kStage);
+        uint8_t* st = smem + (size_t)i * kStage;
+        const int kc = (kb0 + i) * kBK;
+        tma_load_2d(st, &tm_w, &full_bar[i], kc, f0, CTS_L2_EVICT_FIRST);
+        if (DUAL) tma_load_2d(st + kABytes, &tm_w2, &full_bar[i], kc, f0, CTS_L2_EVICT_FIRST);
+      }
+      pdl_wait();   // activations are produced by the predecessor
+      for (int i = 0; i < npre; ++i) {
+        uint8_t* st = smem + (size_t)i * kStage;
+        tma_load_2d(st + kABytes * (DUAL ? 2 : 1), &tm_x, &full_bar[i], (kb0 + i) * kBK, t0, CTS_L2_EVICT_LAST);
+      }
+      for (int i = npre; i < nkb; ++i) {
         const int s = i % stages;
         const uint32_t ph = (uint32_t)(i / stages) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -137,6 +153,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     }
   } else {
     // ------------------------------ epilogue ------------------------------
+    pdl_wait();   // residual / row_map / the output buffers belong to predecessors until now
     mbar_wait(&acc_bar, 0);
     tc_fence_after();
     const int q = warp & 3;
@@ -227,8 +244,7 @@ int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   auto kern = gemm_tn_kernel<T, BN, DUAL>;
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)cdiv_ll(a->n, kBM), (unsigned)cdiv_ll(a->t, BN), (unsigned)a->split_k);
-  kern<<<grid, kThreads, smem, stream>>>(tm_w, tm_w2, tm_x, p);
-  CTS_LAUNCH_CHECK(ctx);
+  CTS_CUDA(ctx, launch_pdl(kern, grid, dim3(kThreads), smem, stream, 1, tm_w, tm_w2, tm_x, p));
   return CTS_OK;
 }
 

@@ -17,6 +17,8 @@ namespace {
 template <typename T>
 __global__ void ts_count_kernel(const T* __restrict__ x, int row_len, int nf, int patch, int* __restrict__ valid_len,
                                 int* __restrict__ patch_cnt) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.x;
   const T* row = x + (size_t)s * row_len;
   const int npts = row_len / nf;
@@ -53,6 +55,8 @@ __global__ void ts_count_kernel(const T* __restrict__ x, int row_len, int nf, in
 
 __global__ void ts_scan_kernel(const int* __restrict__ valid_len, const int* __restrict__ patch_cnt, int n,
                                int* __restrict__ row_offset, int* __restrict__ max_valid) {
+  pdl_trigger();
+  pdl_wait();
   // single CTA, chunked inclusive scan via warp shuffles
   __shared__ int warp_tot[32];
   __shared__ int carry_s;
@@ -98,6 +102,8 @@ __global__ void ts_patchify_kernel(const T* __restrict__ x, int row_len, int nf,
                                    const T* __restrict__ pos_table, int emb_dim, int max_seq_len,
                                    const int* __restrict__ valid_len, const int* __restrict__ row_offset,
                                    const int* __restrict__ max_valid, T* __restrict__ rows_out, int in0) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.y;
   const int pidx = blockIdx.x;
   const int vl = valid_len[s];
@@ -154,15 +160,14 @@ extern "C" int cts_ts_patch_count(cts_ctx* ctx, const void* x, int dtype, int n_
   if (n_series > 0) {
     CTS_CHECK_ARG(ctx, x != nullptr, "null x");
     if (dtype == CTS_BF16)
-      ts_count_kernel<__nv_bfloat16><<<n_series, 128, 0, st>>>((const __nv_bfloat16*)x, row_len, num_features, patch_size,
-                                                             valid_len, patch_cnt);
+      CTS_CUDA(ctx, launch_pdl(ts_count_kernel<__nv_bfloat16>, dim3(n_series), dim3(128), 0, st, 1, (const __nv_bfloat16*)x, row_len,
+                               num_features, patch_size, valid_len, patch_cnt));
     else
-      ts_count_kernel<__half><<<n_series, 128, 0, st>>>((const __half*)x, row_len, num_features, patch_size, valid_len,
-                                                      patch_cnt);
-    CTS_LAUNCH_CHECK(ctx);
+      CTS_CUDA(ctx, launch_pdl(ts_count_kernel<__half>, dim3(n_series), dim3(128), 0, st, 1, (const __half*)x, row_len, num_features,
+                               patch_size, valid_len, patch_cnt));
   }
-  ts_scan_kernel<<<1, 256, 0, st>>>(valid_len, patch_cnt, n_series, row_offset, max_valid);
-  CTS_LAUNCH_CHECK(ctx);
+  CTS_CUDA(ctx, launch_pdl(ts_scan_kernel, dim3(1), dim3(256), 0, st, 1, (const int*)valid_len, (const int*)patch_cnt, n_series,
+                           row_offset, max_valid));
   return CTS_OK;
 }
 
@@ -186,13 +191,12 @@ extern "C" int cts_ts_patchify(cts_ctx* ctx, const void* x, int dtype, int n_ser
   const int threads = in0 >= 256 ? 128 : 64;
   const size_t smem = (size_t)patch_size * 2;
   if (dtype == CTS_BF16)
-    ts_patchify_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(
-        (const __nv_bfloat16*)x, row_len, num_features, patch_size, mode, (const __nv_bfloat16*)pos_table, emb_dim,
-        max_seq_len, valid_len, row_offset, max_valid, (__nv_bfloat16*)rows_out, in0);
+    CTS_CUDA(ctx, launch_pdl(ts_patchify_kernel<__nv_bfloat16>, grid, dim3(threads), smem, st, 1, (const __nv_bfloat16*)x, row_len,
+                             num_features, patch_size, mode, (const __nv_bfloat16*)pos_table, emb_dim, max_seq_len, valid_len,
+                             row_offset, max_valid, (__nv_bfloat16*)rows_out, in0));
   else
-    ts_patchify_kernel<__half><<<grid, threads, smem, st>>>((const __half*)x, row_len, num_features, patch_size, mode,
-                                                          (const __half*)pos_table, emb_dim, max_seq_len, valid_len,
-                                                          row_offset, max_valid, (__half*)rows_out, in0);
-  CTS_LAUNCH_CHECK(ctx);
+    CTS_CUDA(ctx, launch_pdl(ts_patchify_kernel<__half>, grid, dim3(threads), smem, st, 1, (const __half*)x, row_len, num_features,
+                             patch_size, mode, (const __half*)pos_table, emb_dim, max_seq_len, valid_len, row_offset, max_valid,
+                             (__half*)rows_out, in0));
   return CTS_OK;
 }

@@ -351,13 +351,14 @@ class ChatTSForCausalLM:
         st.seq_lens = torch.zeros(B, device=dev, dtype=torch.int32)
         st.page_table = torch.zeros(B, self.max_pages, device=dev, dtype=torch.int32)
         st.out_tokens = torch.zeros(B, max(max_new, 256), device=dev, dtype=torch.int32)
-        st.step_ptr = torch.zeros(1, device=dev, dtype=torch.int32)
+        st.step_ptr = torch.zeros(2, device=dev, dtype=torch.int32)      # {step, arrival counter}
         st.logits = torch.empty(B, self.V, device=dev, dtype=self.dtype)
         # flash-decode split: fill the SMs with (split x kv head x batch) CTAs, at least 2 pages per split
-        per = max(1, (2 * 148) // max(1, B * self.nkv))
-        st.attn_splits = int(max(1, min(per, self.max_pages // 2 if self.max_pages >= 2 else 1, 32)))
-        st.attn_ws = torch.empty(self.ctx.attn_decode_workspace_floats(B, self.nh, self.d, st.attn_splits), device=dev,
-                                 dtype=torch.float32)
+        per = max(1, (3 * 148) // max(1, B * self.nkv))
+        max_tiles = max(1, (self.max_seq_len + 63) // 64)
+        st.attn_splits = int(max(1, min(per, max_tiles, 32)))
+        st.attn_ws = torch.zeros(self.ctx.attn_decode_workspace_floats(B, self.nh, self.d, st.attn_splits), device=dev,
+                                 dtype=torch.float32)      # zero-filled once: holds the self-resetting split counters
         st.graph = st.graph_nosample = None
         self._steps[key] = st
         return st
@@ -493,4 +494,4 @@ class ChatTSForCausalLM:
         pg = torch.div(st.positions, self.page_size, rounding_mode="floor").long().clamp_(max=self.max_pages - 1)
         st.slot_map.copy_((st.page_table.gather(1, pg[:, None]).reshape(-1) * self.page_size +
                            st.positions % self.page_size).to(torch.int32))
-        st.step_ptr.add_(1)
+        st.step_ptr[0] += 1

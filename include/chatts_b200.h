@@ -146,14 +146,17 @@ int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, const void* v, 
                      int max_seqlen, int nh, int nkv, int head_dim, float scale, void* out, int dtype,
                      void* stream);
 
-/* decode: one query token per sequence against the paged cache (flash-decoding split over KV pages).
- *   q [batch, nh, d]; page_table int32[batch, max_pages]; seq_lens int32[batch] (tokens incl. the current one)
- *   workspace: fp32, cts_attn_decode_workspace_floats(...) elements;  out [batch, nh*d]
+/* decode: one query token per sequence against the paged cache (flash-decoding split over KV tiles of 64 tokens;
+ * pages are staged by TMA with the 128-byte swizzle, QK^T and PV run on mma.sync, the last split to finish merges).
+ *   q [batch, nh, d]; k_cache/v_cache [num_pages, nkv, page_size, d]; page_table int32[batch, max_pages];
+ *   seq_lens int32[batch] (tokens incl. the current one); out [batch, nh*d]
+ *   workspace: fp32, cts_attn_decode_workspace_floats(...) elements, ZERO-FILLED ONCE by the caller (it holds the
+ *   self-resetting arrival counters after the partials)
  */
 long long cts_attn_decode_workspace_floats(int batch, int nh, int head_dim, int num_splits);
-int cts_attn_decode(cts_ctx* ctx, const void* q, const void* k_cache, const void* v_cache, const int* page_table,
-                    int max_pages, const int* seq_lens, int batch, int nh, int nkv, int head_dim, int page_size,
-                    float scale, int num_splits, float* workspace, void* out, int dtype, void* stream);
+int cts_attn_decode(cts_ctx* ctx, const void* q, const void* k_cache, const void* v_cache, int num_pages,
+                    const int* page_table, int max_pages, const int* seq_lens, int batch, int nh, int nkv, int head_dim,
+                    int page_size, float scale, int num_splits, float* workspace, void* out, int dtype, void* stream);
 
 /* K13 greedy sampling + device-side bookkeeping of the decode loop, so that a whole step
  * (embed -> 48 layers -> lm_head -> argmax -> advance) replays as one CUDA graph with no host round trip
@@ -161,7 +164,7 @@ int cts_attn_decode(cts_ctx* ctx, const void* q, const void* k_cache, const void
  *   logits [batch, vocab] model dtype -> next id (first max, like torch.argmax)
  *   out_tokens int32[batch, out_ld] column `*step_ptr` receives the id; cur_ids int32[batch] = id;
  *   positions[b] += 1; seq_lens[b] += 1; slot_map[b] = slot of the NEW position in the paged cache;
- *   *step_ptr += 1 (device counter).
+ *   step_ptr int32[2] = {step, arrival counter}: step += 1 once every sequence has been processed (device counter).
  */
 int cts_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab, int batch, int* out_tokens, int out_ld,
                        int* step_ptr, int* cur_ids, int* positions, int* seq_lens, int* slot_map,

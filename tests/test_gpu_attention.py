@@ -34,7 +34,8 @@ def test_prefill_varlen_causal_gqa(d, lens):
     assert e < 1.5e-2
 
 
-@pytest.mark.parametrize("d,nh,nkv,page", [(128, 40, 8, 64), (128, 10, 2, 64), (64, 4, 2, 16), (128, 8, 1, 32), (64, 8, 8, 64)])
+@pytest.mark.parametrize("d,nh,nkv,page", [(128, 40, 8, 64), (128, 10, 2, 64), (64, 4, 2, 16), (128, 8, 1, 32), (64, 8, 8, 64),
+                                            (128, 14, 2, 16), (128, 5, 1, 64)])
 @pytest.mark.parametrize("splits", [1, 3, 16])
 def test_decode_paged(d, nh, nkv, page, splits):
     c = ctx()
@@ -47,11 +48,13 @@ def test_decode_paged(d, nh, nkv, page, splits):
     vc = torch.randn(n_pages, nkv, page, d, generator=g).to(DT)
     perm = torch.randperm(n_pages, generator=g)[: B * max_pages].view(B, max_pages).to(torch.int32)   # scattered pages
     q = torch.randn(B, nh, d, generator=g).to(DT)
-    ws = torch.empty(c.attn_decode_workspace_floats(B, nh, d, splits), device="cuda", dtype=torch.float32)
+    ws = torch.zeros(c.attn_decode_workspace_floats(B, nh, d, splits), device="cuda", dtype=torch.float32)
     out = torch.full((B, nh * d), float("nan"), device="cuda", dtype=DT)
-    c.attn_decode(q.cuda(), kc.cuda(), vc.cuda(), perm.cuda(), torch.tensor(seq_lens, dtype=torch.int32).cuda(), B, nh, nkv, d, page,
-                  1.0 / math.sqrt(d), splits, ws, out)
-    torch.cuda.synchronize()
+    for _ in range(2):          # twice: the arrival counters must reset themselves
+        out.fill_(float("nan"))
+        c.attn_decode(q.cuda(), kc.cuda(), vc.cuda(), perm.cuda(), torch.tensor(seq_lens, dtype=torch.int32).cuda(), B, nh, nkv, d, page,
+                      1.0 / math.sqrt(d), splits, ws, out)
+        torch.cuda.synchronize()
     refs = []
     for b, sl in enumerate(seq_lens):
         pages = perm[b, : (sl + page - 1) // page].long()

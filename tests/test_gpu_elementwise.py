@@ -122,7 +122,7 @@ def test_greedy_advance(vocab):
     logits[1, 5] = logits[1, 400] = 50.0            # tie: the first index wins, like torch.argmax
     ld = logits.cuda()
     out_tokens = torch.zeros(b, 8, dtype=torch.int32, device="cuda")
-    step = torch.tensor([2], dtype=torch.int32, device="cuda")
+    step = torch.tensor([2, 0], dtype=torch.int32, device="cuda")
     cur = torch.zeros(b, dtype=torch.int32, device="cuda")
     pos = torch.tensor([14, 15, 31], dtype=torch.int32, device="cuda")
     sl = torch.tensor([15, 16, 32], dtype=torch.int32, device="cuda")
@@ -133,6 +133,6 @@ def test_greedy_advance(vocab):
     ref = torch.argmax(logits.float(), dim=-1)
     assert ref[1] == 5
     assert cur.cpu().tolist() == ref.tolist()
-    assert out_tokens.cpu()[:, 2].tolist() == ref.tolist() and int(step) == 3
+    assert out_tokens.cpu()[:, 2].tolist() == ref.tolist() and step.cpu().tolist() == [3, 0]
     assert pos.cpu().tolist() == [15, 16, 32] and sl.cpu().tolist() == [16, 17, 33]
     assert slot.cpu().tolist() == [3 * 16 + 15, 9 * 16 + 0, 6 * 16 + 0]
