@@ -90,3 +90,20 @@ int cts_make_tmap_2d(cts_ctx* ctx, CUtensorMap* tm, const void* base, long long 
   if (r != CUDA_SUCCESS) return cts_set_error(ctx, CTS_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
   return CTS_OK;
 }
+
+int cts_make_tmap_2d_dense(cts_ctx* ctx, CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld_elems,
+                           int box_rows, int box_cols, int is_bf16) {
+  if (((uintptr_t)base & 15) != 0) return cts_set_error(ctx, CTS_ERR_BAD_ARG, "tensor map: base not 16-byte aligned");
+  if ((ld_elems * 2) % 16 != 0) return cts_set_error(ctx, CTS_ERR_BAD_ARG, "tensor map: row pitch %lld B not a multiple of 16", ld_elems * 2);
+  if (box_rows < 1 || box_rows > 256 || box_cols < 8 || box_cols > 256 || (box_cols * 2) % 16 != 0)
+    return cts_set_error(ctx, CTS_ERR_BAD_ARG, "tensor map: box %d x %d", box_rows, box_cols);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld_elems * 2)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = ctx->encode_tiled(tm, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                                 const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cts_set_error(ctx, CTS_ERR_CUDA, "cuTensorMapEncodeTiled (dense) failed: CUresult %d", (int)r);
+  return CTS_OK;
+}

@@ -39,6 +39,8 @@ struct GemmParams {
   int split_k;
   int stages;
   int epilogue;
+  int l2_prefetch;   // K blocks of W this CTA prefetches into L2 beyond the shared-memory ring while it waits (decode)
+  int staged;        // 1: epilogue goes TMEM -> registers -> shared-memory tile -> TMA store (big tiles)
 };
 
 template <int BN, bool DUAL> __host__ __device__ constexpr int stage_bytes() { return kBM * kBK * 2 * (DUAL ? 2 : 1) + BN * kBK * 2; }
@@ -50,11 +52,13 @@ template <int BN, bool DUAL> __host__ __device__ constexpr int tmem_cols() {
 template <typename T, int BN, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w2,
-               const __grid_constant__ CUtensorMap tm_x, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_out,
+               const __grid_constant__ CUtensorMap tm_res, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
   __shared__ uint64_t acc_bar;
+  __shared__ uint64_t res_bar;
   __shared__ uint32_t tmem_slot;
 
   constexpr int kStage = stage_bytes<BN, DUAL>();
@@ -88,6 +92,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&acc_bar, 1);
+    mbar_init(&res_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kCols>(&tmem_slot);
@@ -108,6 +113,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         const int kc = (kb0 + i) * kBK;
         tma_load_2d(st, &tm_w, &full_bar[i], kc, f0, CTS_L2_EVICT_FIRST);
         if (DUAL) tma_load_2d(st + kABytes, &tm_w2, &full_bar[i], kc, f0, CTS_L2_EVICT_FIRST);
+      }
+      // ... and, for the skinny decode GEMMs, the next K blocks straight into L2, so the HBM stream of this GEMM's
+      // weights keeps running while the (tiny) predecessor kernel holds the dependency.
+      {
+        const int npf = (nkb - npre) < p.l2_prefetch ? (nkb - npre) : p.l2_prefetch;
+        for (int i = npre; i < npre + npf; ++i) {
+          tma_prefetch_l2_2d(&tm_w, (kb0 + i) * kBK, f0);
+          if (DUAL) tma_prefetch_l2_2d(&tm_w2, (kb0 + i) * kBK, f0);
+        }
       }
       pdl_wait();   // activations are produced by the predecessor
       for (int i = 0; i < npre; ++i) {
@@ -163,6 +177,49 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
     float bias = 0.f;
     if (p.bias != nullptr && f_ok) bias = DT<T>::to_f(reinterpret_cast<const T*>(p.bias)[f]);
     const int epi = p.epilogue;
+    if (p.staged) {
+      // ---- big tiles: stage the [BN tokens x 128 features] output tile in shared memory (the pipeline ring is idle
+      // once the accumulator is complete) and write it with ONE TMA store (coalesced, clipped at the tensor edge);
+      // the residual tile arrives the same way.  Keeps the epilogue a small fraction of the 128x256 mainloop.
+      T* out_s = reinterpret_cast<T*>(smem);                          // [BN][128]
+      T* res_s = reinterpret_cast<T*>(smem + (size_t)BN * kBM * 2);   // [BN][128]
+      const int ft = q * 32 + lane;
+      if (epi == CTS_EPI_RESIDUAL) {
+        if (threadIdx.x == 64) {
+          mbar_expect_tx(&res_bar, (uint32_t)(BN * kBM * 2));
+          tma_load_2d_nohint(res_s, &tm_res, &res_bar, f0, t0);
+        }
+        mbar_wait(&res_bar, 0);
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        if ((long long)t0 + c >= p.t) break;
+        uint32_t v[16], v2[16];
+        tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+        if (DUAL) tmem_ld_32x32b_x16(lane_addr + (uint32_t)(BN + c), v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float acc = __uint_as_float(v[j]);
+          float r;
+          if (epi == CTS_EPI_SWIGLU) {
+            r = rnd<T>(silu_f(rnd<T>(acc))) * rnd<T>(__uint_as_float(v2[j]));
+          } else {
+            r = acc + bias;
+            if (epi == CTS_EPI_GELU) r = gelu_erf(rnd<T>(r));
+            else if (epi == CTS_EPI_RESIDUAL) r = rnd<T>(r) + DT<T>::to_f(res_s[(c + j) * kBM + ft]);
+          }
+          out_s[(c + j) * kBM + ft] = DT<T>::from_f(r);
+        }
+      }
+      fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the TMA engine
+      named_bar_sync(1, 128);                   // the four epilogue warps
+      if (threadIdx.x == 64) {
+        tma_store_2d(&tm_out, out_s, f0, t0);
+        tma_store_commit();
+        tma_store_wait_read0();
+      }
+    } else {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
       if ((long long)t0 + c >= p.t) break;   // warp-uniform
@@ -204,6 +261,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         reinterpret_cast<T*>(p.out)[row * p.out_ld + f] = DT<T>::from_f(r);
       }
     }
+    }
   }
 
   tc_fence_before();
@@ -225,6 +283,18 @@ int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   }
   rc = cts_make_tmap_2d(ctx, &tm_x, a->x, a->t, a->k, a->x_ld, BN, is_bf16);
   if (rc) return rc;
+  // big tiles without a row scatter: output (and residual) tiles move by TMA through shared memory
+  const bool staged = BN >= 64 && a->row_map == nullptr && a->epilogue != CTS_EPI_PARTIAL_F32 && (a->out_ld * 2) % 16 == 0 &&
+                      ((uintptr_t)a->out & 15) == 0 && (a->epilogue != CTS_EPI_RESIDUAL || ((uintptr_t)a->residual & 15) == 0);
+  CUtensorMap tm_out = tm_x, tm_res = tm_x;
+  if (staged) {
+    rc = cts_make_tmap_2d_dense(ctx, &tm_out, a->out, a->t, a->n, a->out_ld, BN, kBM, is_bf16);
+    if (rc) return rc;
+    if (a->epilogue == CTS_EPI_RESIDUAL) {
+      rc = cts_make_tmap_2d_dense(ctx, &tm_res, a->residual, a->t, a->n, a->out_ld, BN, kBM, is_bf16);
+      if (rc) return rc;
+    }
+  }
 
   GemmParams p;
   p.n = a->n; p.k = a->k; p.t = a->t; p.out_ld = a->out_ld;
@@ -240,11 +310,19 @@ int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   p.stages = stages;
+  p.staged = staged ? 1 : 0;
+  // decode (BN <= 32): prefetch up to ~64 MB of this GEMM's weights into L2 across the whole grid while waiting
+  p.l2_prefetch = 0;
+  if (BN <= 32) {
+    const long long ctas = cdiv_ll(a->n, kBM) * cdiv_ll(a->t, BN) * a->split_k;
+    const long long per = (64LL << 20) / (ctas * kBM * kBK * 2 * (DUAL ? 2 : 1));
+    p.l2_prefetch = (int)(per > 64 ? 64 : per);
+  }
   const size_t smem = (size_t)stages * kStage + 1024;
   auto kern = gemm_tn_kernel<T, BN, DUAL>;
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)cdiv_ll(a->n, kBM), (unsigned)cdiv_ll(a->t, BN), (unsigned)a->split_k);
-  CTS_CUDA(ctx, launch_pdl(kern, grid, dim3(kThreads), smem, stream, 1, tm_w, tm_w2, tm_x, p));
+  CTS_CUDA(ctx, launch_pdl(kern, grid, dim3(kThreads), smem, stream, 1, tm_w, tm_w2, tm_x, tm_out, tm_res, p));
   return CTS_OK;
 }
 

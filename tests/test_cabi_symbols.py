@@ -41,7 +41,7 @@ def test_sass_is_blackwell_native():
         pytest.skip("cuobjdump not available")
     exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     sass = subprocess.run([exe, "-sass", _cabi.LIB_PATH], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UBLKCP"):
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "HMMA"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in subprocess.run([exe, "-lelf", _cabi.LIB_PATH], capture_output=True, text=True).stdout
 
