@@ -350,7 +350,7 @@ def run_b200(args):
 
     # ---- e2e through the public API with host tensors
     e2e = None
-    if world == 1:
+    if world == 1 and not args.sweep_only:
         enc = make_batch(cfg, args.batch, seed=1)
         enc = {k: v.pin_memory() for k, v in enc.items()}
         new = args.steps
@@ -397,6 +397,7 @@ def main():
     ap.add_argument("--only-batch", action="store_true", help="skip the b=1/8 side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run decode steps eagerly (for ncu launch lists)")
+    ap.add_argument("--sweep-only", action="store_true", help="decode timing only (skip e2e)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -20,6 +20,8 @@ struct cts_ctx {
   void* scratch;
   size_t scratch_bytes;
   PFN_cuTensorMapEncodeTiled_v12000 encode_tiled;
+  int l2_prefetch_mb;   // tuning knob (CTS_L2_PREFETCH_MB): weight bytes a decode GEMM prefetches into L2 while it waits
+  int decode_stages;    // tuning knob (CTS_DECODE_SMEM_KB): shared-memory budget per CTA of the decode GEMM
 };
 
 int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);

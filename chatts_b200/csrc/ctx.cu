@@ -62,6 +62,10 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
     return CTS_ERR_CUDA;
   }
   ctx->encode_tiled = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  const char* e1 = getenv("CTS_L2_PREFETCH_MB");
+  ctx->l2_prefetch_mb = e1 ? atoi(e1) : 0;
+  const char* e2 = getenv("CTS_DECODE_SMEM_KB");
+  ctx->decode_stages = e2 ? atoi(e2) : 100;
   *out = ctx;
   return CTS_OK;
 }

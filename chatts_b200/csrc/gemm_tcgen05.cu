@@ -305,7 +305,7 @@ int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   constexpr int kStage = stage_bytes<BN, DUAL>();
   // small-N (decode) tiles: leave room for two CTAs per SM so one CTA's prologue/epilogue overlaps the
   // other's stream; large-N (prefill) tiles take the whole SM.
-  const int budget = (BN <= 32) ? 100 * 1024 : 200 * 1024;
+  const int budget = (BN <= 32) ? ctx->decode_stages * 1024 : 200 * 1024;
   int stages = budget / kStage;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
@@ -313,9 +313,9 @@ int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   p.staged = staged ? 1 : 0;
   // decode (BN <= 32): prefetch up to ~64 MB of this GEMM's weights into L2 across the whole grid while waiting
   p.l2_prefetch = 0;
-  if (BN <= 32) {
+  if (BN <= 32 && ctx->l2_prefetch_mb > 0) {
     const long long ctas = cdiv_ll(a->n, kBM) * cdiv_ll(a->t, BN) * a->split_k;
-    const long long per = (64LL << 20) / (ctas * kBM * kBK * 2 * (DUAL ? 2 : 1));
+    const long long per = ((long long)ctx->l2_prefetch_mb << 20) / (ctas * kBM * kBK * 2 * (DUAL ? 2 : 1));
     p.l2_prefetch = (int)(per > 64 ? 64 : per);
   }
   const size_t smem = (size_t)stages * kStage + 1024;
