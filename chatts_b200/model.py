@@ -146,6 +146,11 @@ class ChatTSForCausalLM:
     # ------------------------------------------------------------------------------------------ layers
     def _splits(self, T):
         c = self.ctx
+        import os
+        ov = os.environ.get("CTS_SPLITS")          # tuning override "qkv,o,gu,d" (decode-sized T only)
+        if ov and T <= 32:
+            a = [int(v) for v in ov.split(",")]
+            return dict(qkv=a[0], o=a[1], gu=a[2], d=a[3])
         return dict(qkv=c.suggest_split(self.wqkv[0].shape[0], self.H, T), o=c.suggest_split(self.H, self.nh * self.d, T),
                     gu=c.suggest_split(self.I, self.H, T, True), d=c.suggest_split(self.H, self.I, T))
 
