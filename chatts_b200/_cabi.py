@@ -23,7 +23,7 @@ SYMBOLS = [
     "cts_reduce_bias_act", "cts_reduce_residual_rmsnorm", "cts_reduce_swiglu", "cts_qkv_rope_cache",
     "cts_embed_gather", "cts_attn_prefill", "cts_attn_decode_workspace_floats", "cts_attn_decode",
     "cts_greedy_advance", "cts_ipc_alloc", "cts_ipc_open", "cts_ipc_close", "cts_ipc_free",
-    "cts_peer_allreduce_residual_rmsnorm",
+    "cts_peer_allreduce_residual_rmsnorm", "cts_peer_greedy_advance",
 ]
 
 
@@ -80,6 +80,8 @@ def load_library():
     lib.cts_ipc_close.argtypes = [vp, vp]
     lib.cts_ipc_free.argtypes = [vp, vp]
     lib.cts_peer_allreduce_residual_rmsnorm.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
+    lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.cts_peer_greedy_advance.restype = i
     for name in ("cts_ipc_alloc", "cts_ipc_open", "cts_ipc_close", "cts_ipc_free", "cts_peer_allreduce_residual_rmsnorm"):
         getattr(lib, name).restype = i
     for name in ("cts_ts_patch_count", "cts_ts_patchify", "cts_gemm", "cts_gemm_suggest_split", "cts_reduce_bias_act",
@@ -237,6 +239,14 @@ class Context:
         self._chk(self.lib.cts_peer_allreduce_residual_rmsnorm(self.h, _p(peer_partials), _p(peer_flags), _p(state), rank, world,
                                                                _p(resid_in), _p(resid_out), _p(norm_w), float(eps), _p(norm_out), t,
                                                                resid_in.shape[-1], dtype_code(resid_in.dtype), _stream()))
+
+
+    def peer_greedy_advance(self, logits, batch, rank, world, peer_cand, peer_flags, state, max_batch, out_tokens, step_ptr, cur_ids,
+                            positions, seq_lens, slot_map, page_table, page_size):
+        self._chk(self.lib.cts_peer_greedy_advance(self.h, _p(logits), logits.shape[-1], batch, rank, world, _p(peer_cand), _p(peer_flags),
+                                                   _p(state), max_batch, _p(out_tokens), out_tokens.stride(0), _p(step_ptr), _p(cur_ids),
+                                                   _p(positions), _p(seq_lens), _p(slot_map), _p(page_table), page_table.shape[1],
+                                                   page_size, dtype_code(logits.dtype), _stream()))
 
 
 _ctx_cache = {}

@@ -116,6 +116,104 @@ peer_allreduce_residual_rmsnorm_kernel(const float* const* __restrict__ peer_par
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Vocab-parallel greedy sampling without a collective library call: every rank takes the argmax of ITS logits
+// shard, PUSHES (value, global index) into every peer's candidate table over NVLink (release store), waits until
+// all peers' candidates for this sequence have landed (acquire loads on its own flags), picks the global winner
+// (largest value, lowest index on ties -- identical on every rank) and advances the device-side decode state.
+// Replaces "ParallelLMHead logits all-gather + sampler" (chatts_vllm.py:607-610) for greedy decoding, which lets a
+// tensor-parallel decode step be captured in one CUDA graph.  One CTA per sequence.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+peer_greedy_advance_kernel(const T* __restrict__ logits, long long vshard, int rank, int world, float2* const* __restrict__ peer_cand,
+                           int* const* __restrict__ peer_flags, int* __restrict__ state, int max_b, int* __restrict__ out_tokens,
+                           int out_ld, int* __restrict__ step_ptr, int* __restrict__ cur_ids, int* __restrict__ positions,
+                           int* __restrict__ seq_lens, int* __restrict__ slot_map, const int* __restrict__ page_table, int max_pages,
+                           int page_size) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const int epoch = state[0] + 1;
+  const T* row = logits + (long long)b * vshard;
+  float best = -INFINITY;
+  long long best_i = vshard;
+  for (long long i = threadIdx.x; i < vshard; i += blockDim.x) {
+    const float f = DT<T>::to_f(row[i]);
+    if (f > best) { best = f; best_i = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  __shared__ float sb[32];
+  __shared__ long long si[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sb[warp] = best; si[warp] = best_i; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    best = lane < nw ? sb[lane] : -INFINITY;
+    best_i = lane < nw ? si[lane] : vshard;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    // push my candidate to every rank (slot [rank][b]) and then the flag
+    const float gidx = __int_as_float((int)(best_i + (long long)rank * vshard));
+    if (lane < world) {
+      float2* dst = peer_cand[lane] + (long long)rank * max_b + b;
+      asm volatile("st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(best), "f"(gidx) : "memory");
+      st_release_sys(peer_flags[lane] + rank * max_b + b, epoch);
+    }
+    // wait for every rank's candidate of this sequence
+    if (lane < world) {
+      const int* mine = peer_flags[rank] + lane * max_b + b;
+      unsigned spins = 0;
+      while (ld_acquire_sys(mine) < epoch) {
+        if (++spins > (1u << 26)) { printf("chatts_b200: peer argmax timed out (rank %d waits for %d)\n", rank, lane); __trap(); }
+      }
+    }
+    __syncwarp();
+    float v = -INFINITY;
+    int idx = 0x7fffffff;
+    if (lane < world) {
+      const float2* src = peer_cand[rank] + (long long)lane * max_b + b;
+      float a, c;
+      asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(c) : "l"(src) : "memory");
+      v = a;
+      idx = __float_as_int(c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    if (lane == 0) {
+      const int tok = idx == 0x7fffffff ? 0 : idx;
+      const int step = step_ptr[0];
+      out_tokens[(long long)b * out_ld + step] = tok;
+      cur_ids[b] = tok;
+      const int np = positions[b] + 1;
+      positions[b] = np;
+      seq_lens[b] = seq_lens[b] + 1;
+      const int pg = np / page_size;
+      slot_map[b] = pg < max_pages ? page_table[(long long)b * max_pages + pg] * page_size + np % page_size : -1;
+      __threadfence();
+      const int done = atomicAdd(&state[1], 1) + 1;
+      if (done == (int)gridDim.x) {
+        state[1] = 0;
+        state[0] = epoch;
+        step_ptr[0] = step + 1;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int cts_ipc_alloc(cts_ctx* ctx, long long bytes, void** dptr, unsigned char* handle64) {
@@ -172,5 +270,29 @@ extern "C" int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const void* pee
     CTS_CUDA(ctx, launch_pdl(peer_allreduce_residual_rmsnorm_kernel<__half>, dim3((unsigned)t), dim3(kThreads), 0, st, 1,
                              (const float* const*)peer_partials, (int* const*)peer_flags, state, rank, world, (const __half*)resid_in,
                              (__half*)resid_out, (const __half*)norm_w, eps, (__half*)norm_out, (int)h));
+  return CTS_OK;
+}
+
+extern "C" int cts_peer_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab_shard, int batch, int rank, int world,
+                                       const void* peer_cand, const void* peer_flags, int* state, int max_batch, int* out_tokens,
+                                       int out_ld, int* step_ptr, int* cur_ids, int* positions, int* seq_lens, int* slot_map,
+                                       const int* page_table, int max_pages, int page_size, int dtype, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, logits && peer_cand && peer_flags && state && out_tokens && step_ptr && cur_ids && positions && seq_lens &&
+                         slot_map && page_table, "null pointer");
+  CTS_CHECK_ARG(ctx, world >= 1 && world <= 32 && rank >= 0 && rank < world, "rank / world");
+  CTS_CHECK_ARG(ctx, batch >= 0 && batch <= max_batch && vocab_shard > 0 && vocab_shard * world < 2147483647LL, "sizes");
+  CTS_CHECK_ARG(ctx, page_size > 0 && max_pages > 0, "paging");
+  CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
+  if (batch == 0) return CTS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == CTS_BF16)
+    CTS_CUDA(ctx, launch_pdl(peer_greedy_advance_kernel<__nv_bfloat16>, dim3(batch), dim3(1024), 0, st, 1, (const __nv_bfloat16*)logits,
+                             vocab_shard, rank, world, (float2* const*)peer_cand, (int* const*)peer_flags, state, max_batch, out_tokens,
+                             out_ld, step_ptr, cur_ids, positions, seq_lens, slot_map, page_table, max_pages, page_size));
+  else
+    CTS_CUDA(ctx, launch_pdl(peer_greedy_advance_kernel<__half>, dim3(batch), dim3(1024), 0, st, 1, (const __half*)logits, vocab_shard,
+                             rank, world, (float2* const*)peer_cand, (int* const*)peer_flags, state, max_batch, out_tokens, out_ld,
+                             step_ptr, cur_ids, positions, seq_lens, slot_map, page_table, max_pages, page_size));
   return CTS_OK;
 }

@@ -64,7 +64,7 @@ class _Step:
 class ChatTSForCausalLM:
     def __init__(self, config, state_dict, device="cuda", dtype=torch.bfloat16, tp_rank=0, tp_size=1,
                  max_batch=32, max_seq_len=2048, page_size=64, use_cuda_graph=True, comm=None,
-                 use_peer_allreduce=True, graph_with_tp=False):
+                 use_peer_allreduce=True, graph_with_tp=True):
         if not torch.cuda.is_available():
             raise _cabi.CtsError("chatts_b200 needs a B200 (sm_100a) GPU; there is no CPU fallback")
         self.config, self.dtype = config, dtype
@@ -379,6 +379,12 @@ class ChatTSForCausalLM:
 
         self._layers(st, B, attend)
         c.gemm(st.xn, self.lm_head, st.logits, epilogue=EPI_NONE, t=B)
+        if sample and self.peer is not None:
+            # vocab-parallel greedy over peer memory: no collective call, graph-capturable
+            c.peer_greedy_advance(st.logits, B, self.tp_rank, self.tp_size, self.peer.cand, self.peer.cand_flags, self.peer.cand_state,
+                                  self.peer.max_batch, st.out_tokens, st.step_ptr, st.cur_ids, st.positions, st.seq_lens, st.slot_map,
+                                  st.page_table, self.page_size)
+            return
         st.full_logits = self._gather_vocab(st.logits)           # identity on one GPU; all-gather of vocab shards under TP
         if sample:
             c.greedy_advance(st.full_logits, B, st.out_tokens, st.step_ptr, st.cur_ids, st.positions, st.seq_lens, st.slot_map,
@@ -386,7 +392,7 @@ class ChatTSForCausalLM:
 
     def _decode_step(self, st, sample=True):
         """One decode step for the whole batch; replays the captured CUDA graph when enabled."""
-        if not self.use_cuda_graph or (self.tp_size > 1 and not self.graph_with_tp):
+        if not self.use_cuda_graph or (self.tp_size > 1 and not (self.graph_with_tp and self.peer is not None and sample)):
             self._decode_body(st, sample)
             return
         attr = "graph" if sample else "graph_nosample"

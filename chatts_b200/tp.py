@@ -26,7 +26,10 @@ class PeerBuffers:
         # one allocation per rank: n_buffers fp32 partial buffers, then the flag array int[world]
         self.part_bytes = self.floats * 4
         self.flag_off = n_buffers * self.part_bytes
-        total = self.flag_off + 256
+        self.max_batch = max_tokens
+        self.cand_off = self.flag_off + 256                                  # float2 [world][max_tokens]
+        self.cflag_off = self.cand_off + world * max_tokens * 8              # int32  [world][max_tokens]
+        total = self.cflag_off + world * max_tokens * 4 + 256
         self.local_ptr, handle = ctx.ipc_alloc(total)
         handles = [None] * world
         dist.all_gather_object(handles, handle, group=group)
@@ -38,6 +41,9 @@ class PeerBuffers:
             self.partials.append(arr)
         self.flags = torch.tensor([p + self.flag_off for p in self.peer_base], dtype=torch.int64, device=dev)
         self.state = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.cand = torch.tensor([p + self.cand_off for p in self.peer_base], dtype=torch.int64, device=dev)
+        self.cand_flags = torch.tensor([p + self.cflag_off for p in self.peer_base], dtype=torch.int64, device=dev)
+        self.cand_state = torch.zeros(2, dtype=torch.int32, device=dev)
         self.local = [_Raw(self.local_ptr + b * self.part_bytes) for b in range(n_buffers)]
 
     def local_partial(self, b):

@@ -189,6 +189,18 @@ int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const void* peer_partials,
                                         int world, const void* resid_in, void* resid_out, const void* norm_w, float eps,
                                         void* norm_out, long long t, long long h, int dtype, void* stream);
 
+/* vocab-parallel greedy sampling + decode-state advance over peer memory (no NCCL): local argmax of this rank's logits
+ * shard [batch, vocab_shard], candidates pushed to every peer, global winner chosen identically on all ranks
+ * (replaces ParallelLMHead's logits all-gather + sampler, chatts_vllm.py:607-610, for greedy decoding).
+ *   peer_cand:  device array float2*[world] (entry r = rank r's candidate table float2[world][max_batch])
+ *   peer_flags: device array int*[world]    (entry r = rank r's flag table int[world][max_batch], zero-initialised)
+ *   state:      local int[2], zero-initialised;  step_ptr int[2] as in cts_greedy_advance
+ */
+int cts_peer_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab_shard, int batch, int rank, int world,
+                            const void* peer_cand, const void* peer_flags, int* state, int max_batch, int* out_tokens, int out_ld,
+                            int* step_ptr, int* cur_ids, int* positions, int* seq_lens, int* slot_map, const int* page_table,
+                            int max_pages, int page_size, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
