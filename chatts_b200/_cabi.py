@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libchatts_b200.so")
 
 OK = 0
 BF16, F16 = 0, 1
-EPI_NONE, EPI_GELU, EPI_SWIGLU, EPI_PARTIAL_F32, EPI_RESIDUAL = 0, 1, 2, 3, 4
+EPI_NONE, EPI_GELU, EPI_SWIGLU, EPI_PARTIAL_F32, EPI_RESIDUAL, EPI_SPLITK_F32 = 0, 1, 2, 3, 4, 5
 
 # every symbol include/chatts_b200.h declares (tests/test_cabi_symbols.py checks the .so exports them all)
 SYMBOLS = [
@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("n", C.c_longlong), ("k", C.c_longlong), ("t", C.c_longlong),
         ("w_ld", C.c_longlong), ("x_ld", C.c_longlong), ("out_ld", C.c_longlong),
         ("dtype", C.c_int), ("epilogue", C.c_int), ("split_k", C.c_int), ("reserved", C.c_int),
+        ("splitk_ws", C.c_void_p), ("tile_counters", C.c_void_p),
     ]
 
 
@@ -159,7 +160,8 @@ class Context:
     def suggest_split(self, n, k, t, dual=False):
         return int(self.lib.cts_gemm_suggest_split(self.h, n, k, t, int(dual)))
 
-    def gemm(self, x, w, out, *, w2=None, bias=None, residual=None, row_map=None, epilogue=EPI_NONE, split_k=1, t=None):
+    def gemm(self, x, w, out, *, w2=None, bias=None, residual=None, row_map=None, epilogue=EPI_NONE, split_k=1, t=None,
+             splitk_ws=None, tile_counters=None):
         """out[T,N] (or fp32 partial [S,T,N]) = x[T,K] @ w[N,K]^T with the fused epilogue."""
         a = GemmArgs()
         a.w, a.w2, a.x = w.data_ptr(), (w2.data_ptr() if w2 is not None else None), x.data_ptr()
@@ -170,7 +172,9 @@ class Context:
         a.n, a.k = w.shape[0], w.shape[1]
         a.t = x.shape[0] if t is None else t
         a.w_ld, a.x_ld = w.stride(0), x.stride(0)
-        a.out_ld = out.stride(-2) if epilogue != EPI_PARTIAL_F32 else a.n
+        a.out_ld = out.stride(-2) if epilogue not in (EPI_PARTIAL_F32, EPI_SPLITK_F32) else a.n
+        a.splitk_ws = splitk_ws.data_ptr() if splitk_ws is not None else None
+        a.tile_counters = tile_counters.data_ptr() if tile_counters is not None else None
         a.dtype, a.epilogue, a.split_k = dtype_code(x.dtype), epilogue, split_k
         self._chk(self.lib.cts_gemm(self.h, C.byref(a), _stream()))
 

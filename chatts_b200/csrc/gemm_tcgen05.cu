@@ -39,6 +39,8 @@ struct GemmParams {
   int split_k;
   int stages;
   int epilogue;
+  float* splitk_ws;  // CTS_EPI_SPLITK_F32: fp32 [split_k, t, n] scratch
+  int* tile_cnt;     // CTS_EPI_SPLITK_F32: arrival counter per output tile (zero-initialised, self-resetting)
   int l2_prefetch;   // K blocks of W this CTA prefetches into L2 beyond the shared-memory ring while it waits (decode)
   int staged;        // 1: epilogue goes TMEM -> registers -> shared-memory tile -> TMA store (big tiles)
 };
@@ -60,6 +62,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   __shared__ uint64_t acc_bar;
   __shared__ uint64_t res_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ int last_flag;
 
   constexpr int kStage = stage_bytes<BN, DUAL>();
   constexpr int kABytes = kBM * kBK * 2;
@@ -219,6 +222,45 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         tma_store_commit();
         tma_store_wait_read0();
       }
+    } else if (epi == CTS_EPI_SPLITK_F32) {
+      // ---- split-K with in-kernel reduction: every split leaves its fp32 partial in the scratch; the LAST split of a
+      // tile to arrive (arrival counter, threadfence-reduction pattern) sums the partials in split order -- a fixed
+      // order, so the result is deterministic -- and writes the reduced fp32 tile.  Consumers then read ONE partial.
+      float* dst = p.split_k > 1 ? p.splitk_ws + (long long)split * p.t * p.n : reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        if ((long long)t0 + c >= p.t) break;
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const long long t = (long long)t0 + c + j;
+          if (t < p.t && f_ok) dst[t * p.n + f] = __uint_as_float(v[j]);
+        }
+      }
+      if (p.split_k > 1) {
+        __threadfence();
+        named_bar_sync(1, 128);
+        const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+        if (threadIdx.x == 64) last_flag = (atomicAdd(&p.tile_cnt[tile_id], 1) == p.split_k - 1);
+        named_bar_sync(1, 128);
+        if (last_flag) {
+          __threadfence();
+          const long long tmax = p.t - t0 < BN ? p.t - t0 : BN;
+          if (f_ok) {
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll 2
+            for (long long tt = 0; tt < tmax; ++tt) {
+              const long long off = (t0 + tt) * p.n + f;
+              float a = 0.f;
+              for (int s2 = 0; s2 < p.split_k; ++s2) a += __ldcg(p.splitk_ws + (long long)s2 * p.t * p.n + off);
+              o[off] = a;
+            }
+          }
+          if (threadIdx.x == 64) p.tile_cnt[tile_id] = 0;
+        }
+      }
     } else {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
@@ -284,7 +326,7 @@ int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   rc = cts_make_tmap_2d(ctx, &tm_x, a->x, a->t, a->k, a->x_ld, BN, is_bf16);
   if (rc) return rc;
   // big tiles without a row scatter: output (and residual) tiles move by TMA through shared memory
-  const bool staged = BN >= 64 && a->row_map == nullptr && a->epilogue != CTS_EPI_PARTIAL_F32 && (a->out_ld * 2) % 16 == 0 &&
+  const bool staged = BN >= 64 && a->row_map == nullptr && a->epilogue != CTS_EPI_PARTIAL_F32 && a->epilogue != CTS_EPI_SPLITK_F32 && (a->out_ld * 2) % 16 == 0 &&
                       ((uintptr_t)a->out & 15) == 0 && (a->epilogue != CTS_EPI_RESIDUAL || ((uintptr_t)a->residual & 15) == 0);
   CUtensorMap tm_out = tm_x, tm_res = tm_x;
   if (staged) {
@@ -299,6 +341,7 @@ int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   GemmParams p;
   p.n = a->n; p.k = a->k; p.t = a->t; p.out_ld = a->out_ld;
   p.bias = a->bias; p.residual = a->residual; p.out = a->out; p.row_map = a->row_map;
+  p.splitk_ws = (float*)a->splitk_ws; p.tile_cnt = a->tile_counters;
   p.kb_total = (int)cdiv_ll(a->k, kBK);
   p.split_k = a->split_k;
   p.epilogue = a->epilogue;
@@ -344,15 +387,18 @@ extern "C" int cts_gemm(cts_ctx* ctx, const cts_gemm_args* a, void* stream) {
   CTS_CHECK_ARG(ctx, a->w && a->x && a->out, "null w/x/out");
   CTS_CHECK_ARG(ctx, a->n > 0 && a->k > 0 && a->t > 0, "n, k, t must be positive");
   CTS_CHECK_ARG(ctx, a->dtype == CTS_BF16 || a->dtype == CTS_F16, "dtype must be CTS_BF16 or CTS_F16");
-  CTS_CHECK_ARG(ctx, a->epilogue >= CTS_EPI_NONE && a->epilogue <= CTS_EPI_RESIDUAL, "unknown epilogue");
+  CTS_CHECK_ARG(ctx, a->epilogue >= CTS_EPI_NONE && a->epilogue <= CTS_EPI_SPLITK_F32, "unknown epilogue");
   CTS_CHECK_ARG(ctx, a->split_k >= 1, "split_k must be >= 1");
-  CTS_CHECK_ARG(ctx, a->split_k == 1 || a->epilogue == CTS_EPI_PARTIAL_F32, "split_k > 1 needs CTS_EPI_PARTIAL_F32");
+  CTS_CHECK_ARG(ctx, a->split_k == 1 || a->epilogue == CTS_EPI_PARTIAL_F32 || a->epilogue == CTS_EPI_SPLITK_F32,
+                "split_k > 1 needs CTS_EPI_PARTIAL_F32 or CTS_EPI_SPLITK_F32");
+  CTS_CHECK_ARG(ctx, a->epilogue != CTS_EPI_SPLITK_F32 || a->split_k == 1 || (a->splitk_ws && a->tile_counters),
+                "CTS_EPI_SPLITK_F32 with split_k > 1 needs splitk_ws and tile_counters");
   CTS_CHECK_ARG(ctx, a->split_k <= cdiv_ll(a->k, kBK), "split_k exceeds the number of 64-wide K blocks");
   CTS_CHECK_ARG(ctx, a->split_k <= 65535 && cdiv_ll(a->t, 16) <= 65535 * 16LL, "grid too large");
   CTS_CHECK_ARG(ctx, (a->epilogue == CTS_EPI_SWIGLU) == (a->w2 != nullptr), "w2 is required by (and only by) CTS_EPI_SWIGLU");
   CTS_CHECK_ARG(ctx, a->epilogue != CTS_EPI_RESIDUAL || a->residual != nullptr, "CTS_EPI_RESIDUAL needs residual");
   CTS_CHECK_ARG(ctx, a->w_ld >= a->k && a->x_ld >= a->k, "leading dimension smaller than k");
-  CTS_CHECK_ARG(ctx, a->epilogue == CTS_EPI_PARTIAL_F32 || a->out_ld >= a->n, "out_ld smaller than n");
+  CTS_CHECK_ARG(ctx, a->epilogue == CTS_EPI_PARTIAL_F32 || a->epilogue == CTS_EPI_SPLITK_F32 || a->out_ld >= a->n, "out_ld smaller than n");
   cudaStream_t st = (cudaStream_t)stream;
   const bool dual = a->epilogue == CTS_EPI_SWIGLU;
   if (a->dtype == CTS_BF16)

@@ -78,6 +78,8 @@ int cts_ts_patchify(cts_ctx* ctx, const void* x, int dtype, int n_series, int ro
 #define CTS_EPI_SWIGLU 2      /* out = dtype(silu(dtype(acc_w)) * dtype(acc_w2))  modeling_qwen2.py:47 */
 #define CTS_EPI_PARTIAL_F32 3 /* out_f32[split][t][n] = acc   (split-K; reduced by a cts_reduce_* call) */
 #define CTS_EPI_RESIDUAL 4    /* out = dtype(residual + dtype(acc + bias))     modeling_qwen2.py:302,308 */
+#define CTS_EPI_SPLITK_F32 5  /* out_f32[t][n] = acc summed over the splits INSIDE the kernel: each split writes its partial to
+                                 splitk_ws, the last split of a tile to arrive (tile_counters) adds them in split order */
 
 typedef struct {
   const void* w;        /* [n, k] row-major, leading dimension w_ld elements */
@@ -92,8 +94,10 @@ typedef struct {
   long long w_ld, x_ld, out_ld;
   int dtype;
   int epilogue;
-  int split_k;          /* >=1; >1 only with CTS_EPI_PARTIAL_F32 */
+  int split_k;          /* >=1; >1 only with CTS_EPI_PARTIAL_F32 / CTS_EPI_SPLITK_F32 */
   int reserved;
+  void* splitk_ws;      /* CTS_EPI_SPLITK_F32, split_k > 1: fp32 [split_k, t, n] scratch */
+  int* tile_counters;   /* CTS_EPI_SPLITK_F32, split_k > 1: int32 [ceil(n/128) * ceil(t/BN)] zero-filled once (self-resetting) */
 } cts_gemm_args;
 
 int cts_gemm(cts_ctx* ctx, const cts_gemm_args* args, void* stream);

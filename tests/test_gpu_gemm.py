@@ -54,6 +54,26 @@ def test_gemm_split_k_partial_and_reduce(t, n, k, s):
     assert rel_err(out, ref2) < 8e-3
 
 
+@pytest.mark.parametrize("t,n,k,s", [(1, 384, 512, 4), (8, 256, 1024, 16), (32, 200, 2048, 5), (4, 130, 272, 3), (32, 5120, 640, 3)])
+def test_gemm_split_k_reduced_in_kernel(t, n, k, s):
+    """CTS_EPI_SPLITK_F32: the last split of each tile sums the partials; twice, to check the counters reset; bit-identical runs."""
+    c = ctx()
+    x, w, _ = _mk(t, n, k, torch.bfloat16, 5)
+    xd, wd = x.cuda(), w.cuda()
+    ws = torch.empty(s * t * n, device="cuda", dtype=torch.float32)
+    cnt = torch.zeros(1024, device="cuda", dtype=torch.int32)
+    ref = x.float() @ w.float().T
+    outs = []
+    for _ in range(3):
+        out = torch.full((t, n), float("nan"), device="cuda", dtype=torch.float32)
+        c.gemm(xd, wd, out, epilogue=5, split_k=s, splitk_ws=ws, tile_counters=cnt)
+        torch.cuda.synchronize()
+        outs.append(out.cpu())
+        assert (out.cpu() - ref).abs().max() / ref.abs().max() < 1e-5
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])       # deterministic summation order
+    assert int(cnt.abs().sum()) == 0
+
+
 @pytest.mark.parametrize("t", [1, 8, 40, 200])
 def test_gemm_gelu_swiglu_residual_rowmap(t):
     c = ctx()
