@@ -326,8 +326,7 @@ def run_b200(args):
         for _ in range(2):
             for l in range(L):
                 if sp > 1:
-                    ctx.gemm(st.xn, model.wgu[l], st.ws, epilogue=_cabi.EPI_SPLITK_F32, split_k=sp, t=B, splitk_ws=st.ws_part,
-                             tile_counters=st.tile_cnt)
+                    ctx.gemm(st.xn, model.wgu[l], st.ws, epilogue=_cabi.EPI_PARTIAL_F32, split_k=sp, t=B)
                 else:
                     ctx.gemm(st.xn, model.wgu[l][:I], st.act, w2=model.wgu[l][I:], epilogue=_cabi.EPI_SWIGLU, t=B)
         torch.cuda.synchronize()
@@ -336,8 +335,7 @@ def run_b200(args):
         for _ in range(n_rep):
             for l in range(L):
                 if sp > 1:
-                    ctx.gemm(st.xn, model.wgu[l], st.ws, epilogue=_cabi.EPI_SPLITK_F32, split_k=sp, t=B, splitk_ws=st.ws_part,
-                             tile_counters=st.tile_cnt)
+                    ctx.gemm(st.xn, model.wgu[l], st.ws, epilogue=_cabi.EPI_PARTIAL_F32, split_k=sp, t=B)
                 else:
                     ctx.gemm(st.xn, model.wgu[l][:I], st.act, w2=model.wgu[l][I:], epilogue=_cabi.EPI_SWIGLU, t=B)
         e1.record()

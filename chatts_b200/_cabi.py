@@ -80,7 +80,7 @@ def load_library():
     lib.cts_ipc_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     lib.cts_ipc_close.argtypes = [vp, vp]
     lib.cts_ipc_free.argtypes = [vp, vp]
-    lib.cts_peer_allreduce_residual_rmsnorm.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
+    lib.cts_peer_allreduce_residual_rmsnorm.argtypes = [vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
     lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cts_peer_greedy_advance.restype = i
     for name in ("cts_ipc_alloc", "cts_ipc_open", "cts_ipc_close", "cts_ipc_free", "cts_peer_allreduce_residual_rmsnorm"):
@@ -238,12 +238,12 @@ class Context:
         self._chk(self.lib.cts_ipc_open(self.h, handle, C.byref(ptr)), 0)
         return ptr.value
 
-    def peer_allreduce_residual_rmsnorm(self, peer_partials, peer_flags, state, rank, world, resid_in, resid_out, norm_w, eps,
-                                        norm_out, t):
-        self._chk(self.lib.cts_peer_allreduce_residual_rmsnorm(self.h, _p(peer_partials), _p(peer_flags), _p(state), rank, world,
-                                                               _p(resid_in), _p(resid_out), _p(norm_w), float(eps), _p(norm_out), t,
-                                                               resid_in.shape[-1], dtype_code(resid_in.dtype), _stream()))
-
+    def peer_allreduce_residual_rmsnorm(self, local_partial, split_k, peer_rows, peer_flags, state, rank, world, max_tokens, resid_in,
+                                        resid_out, norm_w, eps, norm_out, t):
+        self._chk(self.lib.cts_peer_allreduce_residual_rmsnorm(self.h, _p(local_partial), split_k, _p(peer_rows), _p(peer_flags), _p(state),
+                                                               rank, world, max_tokens, _p(resid_in), _p(resid_out), _p(norm_w),
+                                                               float(eps), _p(norm_out), t, resid_in.shape[-1],
+                                                               dtype_code(resid_in.dtype), _stream()))
 
     def peer_greedy_advance(self, logits, batch, rank, world, peer_cand, peer_flags, state, max_batch, out_tokens, step_ptr, cur_ids,
                             positions, seq_lens, slot_map, page_table, page_size):

@@ -33,21 +33,46 @@ constexpr int kMaxRanks = 16;
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-peer_allreduce_residual_rmsnorm_kernel(const float* const* __restrict__ peer_partials, int* const* __restrict__ peer_flags,
-                                       int* __restrict__ state, int rank, int world, const T* __restrict__ resid_in,
-                                       T* __restrict__ resid_out, const T* __restrict__ norm_w, float eps,
-                                       T* __restrict__ norm_out, int h) {
+peer_allreduce_residual_rmsnorm_kernel(const float* __restrict__ local_part, int S, long long t_total,
+                                       float* const* __restrict__ peer_rows, int* const* __restrict__ peer_flags,
+                                       int* __restrict__ state, int rank, int world, int max_tokens,
+                                       const T* __restrict__ resid_in, T* __restrict__ resid_out, const T* __restrict__ norm_w,
+                                       float eps, T* __restrict__ norm_out, int h) {
   pdl_trigger();
   pdl_wait();
   const long long t = blockIdx.x;
-  __shared__ const float* src[kMaxRanks];
+  __shared__ float* src[kMaxRanks];
   __shared__ float red[kThreads / 32];
   __shared__ float inv_s;
   const int epoch = state[0] + 1;      // state[0] is only advanced by the last CTA of this kernel to finish
+  if (threadIdx.x < world) src[threadIdx.x] = peer_rows[threadIdx.x];
+  __syncthreads();
+  const int nvec = h / 8;
+  // ---- phase A: reduce this rank's split-K partials of token t (fixed split order) into MY symmetric row
+  {
+    float* mine = src[rank] + t * h;
+    const long long stride = t_total * (long long)h;
+#pragma unroll
+    for (int it = 0; it < kMaxVec; ++it) {
+      const int v = it * kThreads + threadIdx.x;
+      if (v < nvec) {
+        const float* p = local_part + t * h + (long long)v * 8;
+        float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
+        for (int s = 1; s < S; ++s) {
+          const float4 l2 = *reinterpret_cast<const float4*>(p + s * stride), h2 = *reinterpret_cast<const float4*>(p + s * stride + 4);
+          lo.x += l2.x; lo.y += l2.y; lo.z += l2.z; lo.w += l2.w; hi.x += h2.x; hi.y += h2.y; hi.z += h2.z; hi.w += h2.w;
+        }
+        *reinterpret_cast<float4*>(mine + (long long)v * 8) = lo;
+        *reinterpret_cast<float4*>(mine + (long long)v * 8 + 4) = hi;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // ---- barrier for token t: tell every peer my row t is ready, wait for theirs
   if (threadIdx.x < world) {
-    src[threadIdx.x] = peer_partials[threadIdx.x];
-    if (blockIdx.x == 0) st_release_sys(peer_flags[threadIdx.x] + rank, epoch);     // tell peer: rank's partial is ready
-    const int* mine = peer_flags[rank] + threadIdx.x;                                // my own flag array, slot = peer
+    st_release_sys(peer_flags[threadIdx.x] + rank * max_tokens + t, epoch);
+    const int* mine = peer_flags[rank] + threadIdx.x * max_tokens + t;
     unsigned spins = 0;
     while (ld_acquire_sys(mine) < epoch) {
       if (++spins > (1u << 26)) {
@@ -57,8 +82,7 @@ peer_allreduce_residual_rmsnorm_kernel(const float* const* __restrict__ peer_par
     }
   }
   __syncthreads();
-
-  const int nvec = h / 8;
+  // ---- phase B: pull every rank's row (rank order: bit-identical sum on all ranks) + residual + RMSNorm
   float vals[kMaxVec][8];
   float ss = 0.f;
 #pragma unroll
@@ -66,7 +90,7 @@ peer_allreduce_residual_rmsnorm_kernel(const float* const* __restrict__ peer_par
     const int v = it * kThreads + threadIdx.x;
     if (v < nvec) {
       float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int r = 0; r < world; ++r) {          // fixed rank order: identical fp32 sum on every rank
+      for (int r = 0; r < world; ++r) {
         const float* p = src[r] + t * h + (long long)v * 8;
         const float4 lo = ld_peer_f4(p), hi = ld_peer_f4(p + 4);
         a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w; a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
@@ -249,27 +273,28 @@ extern "C" int cts_ipc_free(cts_ctx* ctx, void* dptr) {
   return CTS_OK;
 }
 
-extern "C" int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const void* peer_partials, const void* peer_flags, int* state,
-                                                   int rank, int world, const void* resid_in, void* resid_out,
-                                                   const void* norm_w, float eps, void* norm_out, long long t, long long h,
-                                                   int dtype, void* stream) {
+extern "C" int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const float* local_partial, int split_k, const void* peer_rows,
+                                                   const void* peer_flags, int* state, int rank, int world, int max_tokens,
+                                                   const void* resid_in, void* resid_out, const void* norm_w, float eps,
+                                                   void* norm_out, long long t, long long h, int dtype, void* stream) {
   if (!ctx) return CTS_ERR_BAD_ARG;
-  CTS_CHECK_ARG(ctx, peer_partials && peer_flags && state && resid_in && resid_out, "null pointer");
+  CTS_CHECK_ARG(ctx, local_partial && split_k >= 1 && peer_rows && peer_flags && state && resid_in && resid_out, "null pointer");
   CTS_CHECK_ARG(ctx, world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "rank / world");
   CTS_CHECK_ARG(ctx, (norm_w == nullptr) == (norm_out == nullptr), "norm_w / norm_out mismatch");
   CTS_CHECK_ARG(ctx, h > 0 && h % 8 == 0 && h <= 8LL * kMaxVec * kThreads, "h must be a multiple of 8 and <= 16384");
   CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
-  CTS_CHECK_ARG(ctx, t > 0 && t <= 2147483647LL, "t");
+  CTS_CHECK_ARG(ctx, t > 0 && t <= max_tokens, "t must be in 1..max_tokens");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == CTS_BF16)
     CTS_CUDA(ctx, launch_pdl(peer_allreduce_residual_rmsnorm_kernel<__nv_bfloat16>, dim3((unsigned)t), dim3(kThreads), 0, st, 1,
-                             (const float* const*)peer_partials, (int* const*)peer_flags, state, rank, world,
-                             (const __nv_bfloat16*)resid_in, (__nv_bfloat16*)resid_out, (const __nv_bfloat16*)norm_w, eps,
+                             local_partial, split_k, t, (float* const*)peer_rows, (int* const*)peer_flags, state, rank, world,
+                             max_tokens, (const __nv_bfloat16*)resid_in, (__nv_bfloat16*)resid_out, (const __nv_bfloat16*)norm_w, eps,
                              (__nv_bfloat16*)norm_out, (int)h));
   else
     CTS_CUDA(ctx, launch_pdl(peer_allreduce_residual_rmsnorm_kernel<__half>, dim3((unsigned)t), dim3(kThreads), 0, st, 1,
-                             (const float* const*)peer_partials, (int* const*)peer_flags, state, rank, world, (const __half*)resid_in,
-                             (__half*)resid_out, (const __half*)norm_w, eps, (__half*)norm_out, (int)h));
+                             local_partial, split_k, t, (float* const*)peer_rows, (int* const*)peer_flags, state, rank, world,
+                             max_tokens, (const __half*)resid_in, (__half*)resid_out, (const __half*)norm_w, eps, (__half*)norm_out,
+                             (int)h));
   return CTS_OK;
 }
 

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _cabi, layout
-from ._cabi import EPI_NONE, EPI_RESIDUAL, EPI_SPLITK_F32, EPI_SWIGLU
+from ._cabi import EPI_NONE, EPI_PARTIAL_F32, EPI_RESIDUAL, EPI_SWIGLU
 from .config import ChatTSConfig
 from .ts_encoder import TimeSeriesEmbedding
 from .weights import load_checkpoint, shard_tensor, synthetic_state_dict
@@ -167,13 +167,12 @@ class ChatTSForCausalLM:
         c, sp, eps = self.ctx, st.splits, self.eps
         I, H = self.I, self.H
         c.reduce_residual_rmsnorm(None, 0, st.h, None, self.ln1[0], eps, st.xn, t=T)
-        sk = dict(splitk_ws=st.ws_part, tile_counters=st.tile_cnt)     # in-kernel split-K reduction scratch
         for l in range(self.L):
             kc, vc = self.kv[l, 0], self.kv[l, 1]
             # ---- QKV projection + bias + RoPE + KV write
             if sp["qkv"] > 1:
-                c.gemm(st.xn, self.wqkv[l], st.ws, epilogue=EPI_SPLITK_F32, split_k=sp["qkv"], t=T, **sk)
-                c.qkv_rope_cache(st.ws, True, 1, self.bqkv[l], st.positions, self.cos, self.sin, st.slot_map, st.q, kc, vc,
+                c.gemm(st.xn, self.wqkv[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["qkv"], t=T)
+                c.qkv_rope_cache(st.ws, True, sp["qkv"], self.bqkv[l], st.positions, self.cos, self.sin, st.slot_map, st.q, kc, vc,
                                  st.k_lin, st.v_lin, T, self.nh, self.nkv, self.d, self.page_size)
             else:
                 c.gemm(st.xn, self.wqkv[l], st.qkv, bias=self.bqkv[l], epilogue=EPI_NONE, t=T)
@@ -184,15 +183,15 @@ class ChatTSForCausalLM:
             if self.tp_size > 1:
                 self._tp_row_parallel(st, T, st.ao, self.wo[l], self.ln2[l], 0, sp["o"])
             elif sp["o"] > 1:
-                c.gemm(st.ao, self.wo[l], st.ws, epilogue=EPI_SPLITK_F32, split_k=sp["o"], t=T, **sk)
-                c.reduce_residual_rmsnorm(st.ws, 1, st.h, st.h, self.ln2[l], eps, st.xn, t=T)
+                c.gemm(st.ao, self.wo[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["o"], t=T)
+                c.reduce_residual_rmsnorm(st.ws, sp["o"], st.h, st.h, self.ln2[l], eps, st.xn, t=T)
             else:
                 c.gemm(st.ao, self.wo[l], st.h, residual=st.h, epilogue=EPI_RESIDUAL, t=T)
                 c.reduce_residual_rmsnorm(None, 0, st.h, None, self.ln2[l], eps, st.xn, t=T)
             # ---- gate/up + SwiGLU
             if sp["gu"] > 1:
-                c.gemm(st.xn, self.wgu[l], st.ws, epilogue=EPI_SPLITK_F32, split_k=sp["gu"], t=T, **sk)
-                c.reduce_swiglu(st.ws, 1, T, I, st.act)
+                c.gemm(st.xn, self.wgu[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["gu"], t=T)
+                c.reduce_swiglu(st.ws, sp["gu"], T, I, st.act)
             else:
                 c.gemm(st.xn, self.wgu[l][:I], st.act, w2=self.wgu[l][I:], epilogue=EPI_SWIGLU, t=T)
             # ---- down_proj + residual + next layer's input RMSNorm (or the final norm)
@@ -200,28 +199,27 @@ class ChatTSForCausalLM:
             if self.tp_size > 1:
                 self._tp_row_parallel(st, T, st.act, self.wd[l], nw, 1, sp["d"])
             elif sp["d"] > 1:
-                c.gemm(st.act, self.wd[l], st.ws, epilogue=EPI_SPLITK_F32, split_k=sp["d"], t=T, **sk)
-                c.reduce_residual_rmsnorm(st.ws, 1, st.h, st.h, nw, eps, st.xn, t=T)
+                c.gemm(st.act, self.wd[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["d"], t=T)
+                c.reduce_residual_rmsnorm(st.ws, sp["d"], st.h, st.h, nw, eps, st.xn, t=T)
             else:
                 c.gemm(st.act, self.wd[l], st.h, residual=st.h, epilogue=EPI_RESIDUAL, t=T)
                 c.reduce_residual_rmsnorm(None, 0, st.h, None, nw, eps, st.xn, t=T)
 
     def _tp_row_parallel(self, st, T, x, w, norm_w, which, split):
-        """Row-parallel projection under tensor parallelism: local fp32 partial (split-K reduced inside the GEMM) -> sum
-        over ranks -> residual + norm.  Decode-sized T: ONE kernel over NVLink peer memory
-        (cts_peer_allreduce_residual_rmsnorm; buffers alternate between o_proj (0) and down_proj (1)).  Large prefill T:
-        NCCL all-reduce of the fp32 partial (bandwidth-bound)."""
+        """Row-parallel projection under tensor parallelism: local split-K partials -> sum over splits and ranks ->
+        residual + norm.  Decode-sized T: ONE kernel over NVLink peer memory (cts_peer_allreduce_residual_rmsnorm: each
+        CTA reduces its token's local split-K partials into the symmetric buffer, signals, pulls the peers' rows; the
+        buffers alternate between o_proj (0) and down_proj (1)).  Large prefill T: NCCL all-reduce (bandwidth-bound)."""
         c = self.ctx
-        sk = dict(splitk_ws=st.ws_part, tile_counters=st.tile_cnt)
+        c.gemm(x, w, st.ws, epilogue=EPI_PARTIAL_F32, split_k=split, t=T)
         if self.peer is not None and T <= self.peer_tokens:
-            c.gemm(x, w, self.peer.local_partial(which), epilogue=EPI_SPLITK_F32, split_k=split, t=T, **sk)
-            c.peer_allreduce_residual_rmsnorm(self.peer.partials[which], self.peer.flags, self.peer.state, self.tp_rank,
-                                              self.tp_size, st.h, st.h, norm_w, self.eps, st.xn, T)
+            c.peer_allreduce_residual_rmsnorm(st.ws, split, self.peer.partials[which], self.peer.flags[which], self.peer.state,
+                                              self.tp_rank, self.tp_size, self.peer.max_batch, st.h, st.h, norm_w, self.eps,
+                                              st.xn, T)
             return
-        c.gemm(x, w, st.ws, epilogue=EPI_SPLITK_F32, split_k=split, t=T, **sk)
-        part = st.ws[: T * self.H]
+        part = st.ws[: T * self.H] if split == 1 else st.ws.view(-1)[: split * T * self.H].view(split, T * self.H).sum(0)
         torch.distributed.all_reduce(part, group=self.comm)
-        c.reduce_residual_rmsnorm(st.ws, 1, st.h, st.h, norm_w, self.eps, st.xn, t=T)
+        c.reduce_residual_rmsnorm(part, 1, st.h, st.h, norm_w, self.eps, st.xn, t=T)
 
     def _alloc_step(self, T, decode):
         st = _Step()
@@ -233,10 +231,8 @@ class ChatTSForCausalLM:
         st.ao = torch.empty(T, self.nh * self.d, device=dev, dtype=dt)
         st.act = torch.empty(T, self.I, device=dev, dtype=dt)
         st.qkv = torch.empty(T, self.wqkv[0].shape[0], device=dev, dtype=dt) if st.splits["qkv"] == 1 else None
-        n_max = max(self.wqkv[0].shape[0], 2 * self.I, self.H)
-        st.ws = torch.empty(T * n_max, device=dev, dtype=torch.float32)                      # reduced fp32 [T, N]
-        st.ws_part = torch.empty(self._ws_floats(T, st.splits), device=dev, dtype=torch.float32)   # [S, T, N] scratch
-        st.tile_cnt = torch.zeros(4096, device=dev, dtype=torch.int32)                       # self-resetting tile counters
+        ws_n = max(self._ws_floats(T, st.splits), T * self.H)
+        st.ws = torch.empty(ws_n, device=dev, dtype=torch.float32)                           # split-K partials [S, T, N]
         st.positions = torch.zeros(T, device=dev, dtype=torch.int32)
         st.slot_map = torch.zeros(T, device=dev, dtype=torch.int32)
         if decode:

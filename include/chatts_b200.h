@@ -179,19 +179,23 @@ int cts_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab, int ba
  * residual add + RMSNorm, vllm qwen2.py:100-116,168-174,299-311, for decode-sized messages).
  * cts_ipc_*: symmetric buffers -- cudaMalloc + cudaIpc handle on the owner, cudaIpcOpenMemHandle on the peers
  *   (handle = 64 opaque bytes the host exchanges through torch.distributed).
- * cts_peer_allreduce_residual_rmsnorm: ONE kernel = cross-GPU flag barrier + peer pull of every rank's fp32
- *   partial [t,h] (rank order, bit-identical on all ranks) + residual add + RMSNorm.
- *   peer_partials: device array float*[world] (entry r = rank r's partial buffer mapped in this process)
- *   peer_flags:    device array int*[world]   (entry r = rank r's flag array int[world], zero-initialised)
- *   state:         local int[2] {epoch, done-counter}, zero-initialised, owned by the kernel
+ * cts_peer_allreduce_residual_rmsnorm: ONE kernel = reduction of this rank's split-K partials + per-token cross-GPU flag
+ *   barrier + peer pull of every rank's reduced fp32 row (rank order, bit-identical on all ranks) + residual add + RMSNorm.
+ *   local_partial: fp32 [split_k, t, h] in local memory (output of cts_gemm with CTS_EPI_PARTIAL_F32)
+ *   peer_rows:  device array float*[world] (entry r = rank r's symmetric row buffer fp32 [max_tokens, h])
+ *   peer_flags: device array int*[world]   (entry r = rank r's flag table int[world][max_tokens], zero-initialised)
+ *   state:      local int[2] {epoch, done-counter}, zero-initialised, owned by the kernel
+ *   Consecutive calls must alternate between two (rows, flags) sets: the barrier of call n+1 is what licenses
+ *   overwriting the rows of call n.
  */
 int cts_ipc_alloc(cts_ctx* ctx, long long bytes, void** dptr, unsigned char* handle64);
 int cts_ipc_open(cts_ctx* ctx, const unsigned char* handle64, void** dptr);
 int cts_ipc_close(cts_ctx* ctx, void* dptr);
 int cts_ipc_free(cts_ctx* ctx, void* dptr);
-int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const void* peer_partials, const void* peer_flags, int* state, int rank,
-                                        int world, const void* resid_in, void* resid_out, const void* norm_w, float eps,
-                                        void* norm_out, long long t, long long h, int dtype, void* stream);
+int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const float* local_partial, int split_k, const void* peer_rows,
+                                        const void* peer_flags, int* state, int rank, int world, int max_tokens,
+                                        const void* resid_in, void* resid_out, const void* norm_w, float eps, void* norm_out,
+                                        long long t, long long h, int dtype, void* stream);
 
 /* vocab-parallel greedy sampling + decode-state advance over peer memory (no NCCL): local argmax of this rank's logits
  * shard [batch, vocab_shard], candidates pushed to every peer, global winner chosen identically on all ranks
