@@ -9,6 +9,8 @@
 // every rank, so all ranks hold bit-identical h without a broadcast -- fused with the residual add and the next
 // RMSNorm.  No NCCL call, no extra launch, no copy.  The two partial buffers (o_proj / down_proj) alternate, so
 // the barrier of call n+1 is what licenses overwriting the buffer of call n.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace {
@@ -27,10 +29,12 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
   return v;
 }
 
-constexpr int kThreads = 256;
-constexpr int kMaxVec = 8;
+constexpr int kThreads = 128;
+constexpr int kMaxVec = 4;       // h / C <= 8 * 4 * 128 columns per CTA
 constexpr int kMaxRanks = 16;
+constexpr int kMaxCluster = 8;   // CTAs (one cluster) per token
 
+// grid (C, T), cluster (C,1,1): CTA (c, t) owns columns [c*h/C, (c+1)*h/C) of token t.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 peer_allreduce_residual_rmsnorm_kernel(const float* __restrict__ local_part, int S, long long t_total,
@@ -40,23 +44,27 @@ peer_allreduce_residual_rmsnorm_kernel(const float* __restrict__ local_part, int
                                        float eps, T* __restrict__ norm_out, int h) {
   pdl_trigger();
   pdl_wait();
-  const long long t = blockIdx.x;
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks();
+  const int crank = (int)cluster.block_rank();
+  const long long t = blockIdx.y;
+  const int hc = h / C, col0 = crank * hc, nvec = hc / 8;
   __shared__ float* src[kMaxRanks];
   __shared__ float red[kThreads / 32];
-  __shared__ float inv_s;
+  __shared__ float ss_cta;
   const int epoch = state[0] + 1;      // state[0] is only advanced by the last CTA of this kernel to finish
   if (threadIdx.x < world) src[threadIdx.x] = peer_rows[threadIdx.x];
   __syncthreads();
-  const int nvec = h / 8;
-  // ---- phase A: reduce this rank's split-K partials of token t (fixed split order) into MY symmetric row
+  // ---- phase A: reduce this rank's split-K partials of my column chunk (fixed split order) into MY symmetric row
   {
-    float* mine = src[rank] + t * h;
+    float* mine = src[rank] + t * h + col0;
     const long long stride = t_total * (long long)h;
 #pragma unroll
     for (int it = 0; it < kMaxVec; ++it) {
       const int v = it * kThreads + threadIdx.x;
       if (v < nvec) {
-        const float* p = local_part + t * h + (long long)v * 8;
+        const float* p = local_part + t * h + col0 + (long long)v * 8;
         float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
         for (int s = 1; s < S; ++s) {
           const float4 l2 = *reinterpret_cast<const float4*>(p + s * stride), h2 = *reinterpret_cast<const float4*>(p + s * stride + 4);
@@ -69,10 +77,11 @@ peer_allreduce_residual_rmsnorm_kernel(const float* __restrict__ local_part, int
   }
   __threadfence_system();
   __syncthreads();
-  // ---- barrier for token t: tell every peer my row t is ready, wait for theirs
+  // ---- barrier for (token t, chunk crank): tell every peer my chunk is ready, wait for theirs
+  const long long slot = (t * kMaxCluster + crank);
   if (threadIdx.x < world) {
-    st_release_sys(peer_flags[threadIdx.x] + rank * max_tokens + t, epoch);
-    const int* mine = peer_flags[rank] + threadIdx.x * max_tokens + t;
+    st_release_sys(peer_flags[threadIdx.x] + (long long)rank * max_tokens * kMaxCluster + slot, epoch);
+    const int* mine = peer_flags[rank] + (long long)threadIdx.x * max_tokens * kMaxCluster + slot;
     unsigned spins = 0;
     while (ld_acquire_sys(mine) < epoch) {
       if (++spins > (1u << 26)) {
@@ -82,57 +91,77 @@ peer_allreduce_residual_rmsnorm_kernel(const float* __restrict__ local_part, int
     }
   }
   __syncthreads();
-  // ---- phase B: pull every rank's row (rank order: bit-identical sum on all ranks) + residual + RMSNorm
+  // ---- phase B: pull every rank's chunk (rank order: bit-identical sum on all ranks) + residual; the loads are plain
+  // (batched by the compiler; L1 holds no stale copy: it is invalidated at kernel start and these lines were never read)
   float vals[kMaxVec][8];
   float ss = 0.f;
 #pragma unroll
   for (int it = 0; it < kMaxVec; ++it) {
     const int v = it * kThreads + threadIdx.x;
     if (v < nvec) {
+      float4 lo[kMaxRanks / 2], hi[kMaxRanks / 2];
       float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int r = 0; r < world; ++r) {
-        const float* p = src[r] + t * h + (long long)v * 8;
-        const float4 lo = ld_peer_f4(p), hi = ld_peer_f4(p + 4);
-        a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w; a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
+      for (int r0 = 0; r0 < world; r0 += kMaxRanks / 2) {
+#pragma unroll
+        for (int j = 0; j < kMaxRanks / 2; ++j) {
+          if (r0 + j < world) {
+            const float* p = src[r0 + j] + t * h + col0 + (long long)v * 8;
+            lo[j] = __ldcv(reinterpret_cast<const float4*>(p));
+            hi[j] = __ldcv(reinterpret_cast<const float4*>(p + 4));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxRanks / 2; ++j) {
+          if (r0 + j < world) {
+            a[0] += lo[j].x; a[1] += lo[j].y; a[2] += lo[j].z; a[3] += lo[j].w;
+            a[4] += hi[j].x; a[5] += hi[j].y; a[6] += hi[j].z; a[7] += hi[j].w;
+          }
+        }
       }
+      const long long off = t * h + col0 + (long long)v * 8;
       float rr[8];
-      unpack8<T>(*reinterpret_cast<const uint4*>(resid_in + t * h + (long long)v * 8), rr);
+      unpack8<T>(*reinterpret_cast<const uint4*>(resid_in + off), rr);
 #pragma unroll
       for (int j = 0; j < 8; ++j) rr[j] = rnd<T>(rr[j] + rnd<T>(a[j]));
-      *reinterpret_cast<uint4*>(resid_out + t * h + (long long)v * 8) = pack8<T>(rr);
+      *reinterpret_cast<uint4*>(resid_out + off) = pack8<T>(rr);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { vals[it][j] = rr[j]; ss += rr[j] * rr[j]; }
     }
   }
+  // ---- RMSNorm statistic across the cluster (DSMEM)
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) v += red[w];
+    ss_cta = v;
+  }
+  cluster.sync();
+  float tot = 0.f;
+  for (int r = 0; r < C; ++r) tot += *cluster.map_shared_rank(&ss_cta, r);
+  cluster.sync();
   if (norm_out != nullptr) {
-    ss = warp_sum(ss);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float v = threadIdx.x < kThreads / 32 ? red[threadIdx.x] : 0.f;
-      v = warp_sum(v);
-      if (threadIdx.x == 0) inv_s = 1.0f / sqrtf(v / (float)h + eps);
-    }
-    __syncthreads();
-    const float inv = inv_s;
+    const float inv = 1.0f / sqrtf(tot / (float)h + eps);
 #pragma unroll
     for (int it = 0; it < kMaxVec; ++it) {
       const int v = it * kThreads + threadIdx.x;
       if (v < nvec) {
         float w[8], o[8];
-        unpack8<T>(*reinterpret_cast<const uint4*>(norm_w + (long long)v * 8), w);
+        unpack8<T>(*reinterpret_cast<const uint4*>(norm_w + col0 + (long long)v * 8), w);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = w[j] * rnd<T>(vals[it][j] * inv);
-        *reinterpret_cast<uint4*>(norm_out + t * h + (long long)v * 8) = pack8<T>(o);
+        *reinterpret_cast<uint4*>(norm_out + t * h + col0 + (long long)v * 8) = pack8<T>(o);
       }
     }
   }
-  // last CTA to finish publishes the new epoch for the next call (stream-ordered, so no race with its readers)
+  // last CTA of the grid to finish publishes the new epoch for the next call
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     const int done = atomicAdd(&state[1], 1) + 1;
-    if (done == (int)gridDim.x) {
+    if (done == (int)(gridDim.x * gridDim.y)) {
       state[1] = 0;
       state[0] = epoch;
       __threadfence();
@@ -281,17 +310,22 @@ extern "C" int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const float* lo
   CTS_CHECK_ARG(ctx, local_partial && split_k >= 1 && peer_rows && peer_flags && state && resid_in && resid_out, "null pointer");
   CTS_CHECK_ARG(ctx, world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "rank / world");
   CTS_CHECK_ARG(ctx, (norm_w == nullptr) == (norm_out == nullptr), "norm_w / norm_out mismatch");
-  CTS_CHECK_ARG(ctx, h > 0 && h % 8 == 0 && h <= 8LL * kMaxVec * kThreads, "h must be a multiple of 8 and <= 16384");
+  CTS_CHECK_ARG(ctx, h > 0 && h % 8 == 0, "h must be a multiple of 8");
   CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
-  CTS_CHECK_ARG(ctx, t > 0 && t <= max_tokens, "t must be in 1..max_tokens");
+  CTS_CHECK_ARG(ctx, t > 0 && t <= max_tokens && t <= 65535, "t must be in 1..max_tokens");
+  unsigned C = 1;
+  for (unsigned c : {8u, 4u, 2u}) {
+    if (h % (8 * c) == 0 && h / (8 * c) >= 32) { C = c; break; }
+  }
+  CTS_CHECK_ARG(ctx, h / C <= 8LL * kMaxVec * kThreads, "h too large");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == CTS_BF16)
-    CTS_CUDA(ctx, launch_pdl(peer_allreduce_residual_rmsnorm_kernel<__nv_bfloat16>, dim3((unsigned)t), dim3(kThreads), 0, st, 1,
+    CTS_CUDA(ctx, launch_pdl(peer_allreduce_residual_rmsnorm_kernel<__nv_bfloat16>, dim3(C, (unsigned)t), dim3(kThreads), 0, st, C,
                              local_partial, split_k, t, (float* const*)peer_rows, (int* const*)peer_flags, state, rank, world,
                              max_tokens, (const __nv_bfloat16*)resid_in, (__nv_bfloat16*)resid_out, (const __nv_bfloat16*)norm_w, eps,
                              (__nv_bfloat16*)norm_out, (int)h));
   else
-    CTS_CUDA(ctx, launch_pdl(peer_allreduce_residual_rmsnorm_kernel<__half>, dim3((unsigned)t), dim3(kThreads), 0, st, 1,
+    CTS_CUDA(ctx, launch_pdl(peer_allreduce_residual_rmsnorm_kernel<__half>, dim3(C, (unsigned)t), dim3(kThreads), 0, st, C,
                              local_partial, split_k, t, (float* const*)peer_rows, (int* const*)peer_flags, state, rank, world,
                              max_tokens, (const __half*)resid_in, (__half*)resid_out, (const __half*)norm_w, eps, (__half*)norm_out,
                              (int)h));

@@ -25,9 +25,9 @@ class PeerBuffers:
         dev = torch.device(f"cuda:{torch.cuda.current_device()}")
         # one allocation per rank: n_buffers fp32 partial buffers, then the flag array int[world]
         self.part_bytes = self.floats * 4
-        self.flag_off = n_buffers * self.part_bytes                          # int32 [n_buffers][world][max_tokens]
+        self.flag_off = n_buffers * self.part_bytes                          # int32 [n_buffers][world][max_tokens][8 chunks]
         self.max_batch = max_tokens
-        self.cand_off = self.flag_off + n_buffers * world * max_tokens * 4 + 256   # float2 [world][max_tokens]
+        self.cand_off = self.flag_off + n_buffers * world * max_tokens * 8 * 4 + 256   # float2 [world][max_tokens]
         self.cflag_off = self.cand_off + world * max_tokens * 8              # int32  [world][max_tokens]
         total = self.cflag_off + world * max_tokens * 4 + 256
         self.local_ptr, handle = ctx.ipc_alloc(total)
@@ -39,7 +39,7 @@ class PeerBuffers:
         for b in range(n_buffers):
             arr = torch.tensor([p + b * self.part_bytes for p in self.peer_base], dtype=torch.int64, device=dev)
             self.partials.append(arr)
-        self.flags = [torch.tensor([p + self.flag_off + b * world * max_tokens * 4 for p in self.peer_base], dtype=torch.int64,
+        self.flags = [torch.tensor([p + self.flag_off + b * world * max_tokens * 8 * 4 for p in self.peer_base], dtype=torch.int64,
                                    device=dev) for b in range(n_buffers)]
         self.state = torch.zeros(2, dtype=torch.int32, device=dev)
         self.cand = torch.tensor([p + self.cand_off for p in self.peer_base], dtype=torch.int64, device=dev)

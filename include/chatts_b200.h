@@ -183,7 +183,8 @@ int cts_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab, int ba
  *   barrier + peer pull of every rank's reduced fp32 row (rank order, bit-identical on all ranks) + residual add + RMSNorm.
  *   local_partial: fp32 [split_k, t, h] in local memory (output of cts_gemm with CTS_EPI_PARTIAL_F32)
  *   peer_rows:  device array float*[world] (entry r = rank r's symmetric row buffer fp32 [max_tokens, h])
- *   peer_flags: device array int*[world]   (entry r = rank r's flag table int[world][max_tokens], zero-initialised)
+ *   peer_flags: device array int*[world]   (entry r = rank r's flag table int[world][max_tokens][8], zero-initialised;
+ *               one flag per (token, column chunk): the kernel runs a cluster of up to 8 CTAs per token)
  *   state:      local int[2] {epoch, done-counter}, zero-initialised, owned by the kernel
  *   Consecutive calls must alternate between two (rows, flags) sets: the barrier of call n+1 is what licenses
  *   overwriting the rows of call n.
