@@ -56,10 +56,11 @@ peer_allreduce_residual_rmsnorm_kernel(const float* __restrict__ local_part, int
   const int epoch = state[0] + 1;      // state[0] is only advanced by the last CTA of this kernel to finish
   if (threadIdx.x < world) src[threadIdx.x] = peer_rows[threadIdx.x];
   __syncthreads();
-  // ---- phase A: reduce this rank's split-K partials of my column chunk (fixed split order) into MY symmetric row
+  // ---- phase A: reduce this rank's split-K partials of my column chunk (fixed split order) and PUSH the result into
+  // slot [rank] of EVERY rank's row buffer (posted NVLink writes; the release store below orders them before the flag)
   {
-    float* mine = src[rank] + t * h + col0;
     const long long stride = t_total * (long long)h;
+    const long long slot_off = ((long long)rank * max_tokens + t) * h + col0;
 #pragma unroll
     for (int it = 0; it < kMaxVec; ++it) {
       const int v = it * kThreads + threadIdx.x;
@@ -70,16 +71,19 @@ peer_allreduce_residual_rmsnorm_kernel(const float* __restrict__ local_part, int
           const float4 l2 = *reinterpret_cast<const float4*>(p + s * stride), h2 = *reinterpret_cast<const float4*>(p + s * stride + 4);
           lo.x += l2.x; lo.y += l2.y; lo.z += l2.z; lo.w += l2.w; hi.x += h2.x; hi.y += h2.y; hi.z += h2.z; hi.w += h2.w;
         }
-        *reinterpret_cast<float4*>(mine + (long long)v * 8) = lo;
-        *reinterpret_cast<float4*>(mine + (long long)v * 8 + 4) = hi;
+        for (int r = 0; r < world; ++r) {
+          float* dst = src[r] + slot_off + (long long)v * 8;
+          *reinterpret_cast<float4*>(dst) = lo;
+          *reinterpret_cast<float4*>(dst + 4) = hi;
+        }
       }
     }
   }
-  __threadfence_system();
   __syncthreads();
   // ---- barrier for (token t, chunk crank): tell every peer my chunk is ready, wait for theirs
   const long long slot = (t * kMaxCluster + crank);
   if (threadIdx.x < world) {
+    __threadfence_system();      // cumulative: the CTA's pushes (ordered before this thread by the barrier) precede the flag
     st_release_sys(peer_flags[threadIdx.x] + (long long)rank * max_tokens * kMaxCluster + slot, epoch);
     const int* mine = peer_flags[rank] + (long long)threadIdx.x * max_tokens * kMaxCluster + slot;
     unsigned spins = 0;
@@ -91,8 +95,7 @@ peer_allreduce_residual_rmsnorm_kernel(const float* __restrict__ local_part, int
     }
   }
   __syncthreads();
-  // ---- phase B: pull every rank's chunk (rank order: bit-identical sum on all ranks) + residual; the loads are plain
-  // (batched by the compiler; L1 holds no stale copy: it is invalidated at kernel start and these lines were never read)
+  // ---- phase B: every rank's chunk is now in MY buffer (slot r = rank r): sum in rank order (bit-identical on all ranks)
   float vals[kMaxVec][8];
   float ss = 0.f;
 #pragma unroll
@@ -105,7 +108,7 @@ peer_allreduce_residual_rmsnorm_kernel(const float* __restrict__ local_part, int
 #pragma unroll
         for (int j = 0; j < kMaxRanks / 2; ++j) {
           if (r0 + j < world) {
-            const float* p = src[r0 + j] + t * h + col0 + (long long)v * 8;
+            const float* p = src[rank] + ((long long)(r0 + j) * max_tokens + t) * h + col0 + (long long)v * 8;   // local slot of rank r
             lo[j] = __ldcv(reinterpret_cast<const float4*>(p));
             hi[j] = __ldcv(reinterpret_cast<const float4*>(p + 4));
           }

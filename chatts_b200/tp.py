@@ -21,7 +21,7 @@ class _Raw:
 class PeerBuffers:
     def __init__(self, ctx, rank, world, max_tokens, hidden, group=None, n_buffers=2):
         self.ctx, self.rank, self.world = ctx, rank, world
-        self.floats = max_tokens * hidden
+        self.floats = world * max_tokens * hidden          # per buffer: one [max_tokens, hidden] slot per source rank
         dev = torch.device(f"cuda:{torch.cuda.current_device()}")
         # one allocation per rank: n_buffers fp32 partial buffers, then the flag array int[world]
         self.part_bytes = self.floats * 4

@@ -182,7 +182,8 @@ int cts_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab, int ba
  * cts_peer_allreduce_residual_rmsnorm: ONE kernel = reduction of this rank's split-K partials + per-token cross-GPU flag
  *   barrier + peer pull of every rank's reduced fp32 row (rank order, bit-identical on all ranks) + residual add + RMSNorm.
  *   local_partial: fp32 [split_k, t, h] in local memory (output of cts_gemm with CTS_EPI_PARTIAL_F32)
- *   peer_rows:  device array float*[world] (entry r = rank r's symmetric row buffer fp32 [max_tokens, h])
+ *   peer_rows:  device array float*[world] (entry r = rank r's symmetric buffer fp32 [world, max_tokens, h]: every rank
+ *               PUSHES its reduced rows into slot [its rank] of every peer, then each rank sums its local slots)
  *   peer_flags: device array int*[world]   (entry r = rank r's flag table int[world][max_tokens][8], zero-initialised;
  *               one flag per (token, column chunk): the kernel runs a cluster of up to 8 CTAs per token)
  *   state:      local int[2] {epoch, done-counter}, zero-initialised, owned by the kernel
