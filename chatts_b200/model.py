@@ -308,10 +308,11 @@ class ChatTSForCausalLM:
         torch.distributed.all_gather(parts, logits, group=self.comm)
         return torch.cat(parts, dim=-1)
 
-    def forward(self, input_ids, attention_mask=None, timeseries=None, logits_to_keep=1, **_):
-        """HF-style forward on the HF merge layout.  logits_to_keep=1 -> [B,1,V] (next-token logits);
-        0 -> list of per-sample [T_b, V] tensors for every merged position."""
-        _, _, counts, lay = self._prepare_inputs(input_ids, attention_mask, timeseries)
+    def forward(self, input_ids, attention_mask=None, timeseries=None, logits_to_keep=1, layout_kind="hf", **_):
+        """HF-style forward.  layout_kind="hf": input_ids hold the un-expanded <ts><ts/> pairs, patch rows are inserted
+        (HF surface); "vllm": one flat prompt whose <ts> copies are overwritten in order (chatts_vllm.py:405-415,569-573).
+        logits_to_keep=1 -> [B,1,V] (next-token logits); 0 -> list of per-sample [T_b, V] tensors for every position."""
+        _, _, counts, lay = self._prepare_inputs(input_ids, attention_mask, timeseries, layout_kind)
         B = lay.cu_seqlens.shape[0] - 1
         pts, held = self._alloc_pages(lay.lens, 0)
         try:

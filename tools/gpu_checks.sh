@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 rm -f gpurun_out/parity_metrics.jsonl
 nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 STATUS=0
-for f in gemm elementwise attention ts_encoder model; do
+for f in gemm elementwise attention ts_encoder model configs; do
   echo "=== tests/test_gpu_$f.py"
   timeout ${TEST_TIMEOUT:-420} python -m pytest tests/test_gpu_$f.py -q -m gpu -x --no-header -p no:cacheprovider > gpurun_out/test_$f.log 2>&1
   rc=$?
