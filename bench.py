@@ -343,8 +343,14 @@ def run_b200(args):
         us = e0.elapsed_time(e1) * 1e3 / (n_rep * L)
         alg = 2 * I * cfg.hidden_size * 2 + B * cfg.hidden_size * 2 + B * I * 2
         ach = alg / (us * 1e-6) / 1e9
-        roof = {"bound": "hbm", "kernel": "gemm_tn_kernel (gate_up+SwiGLU, tcgen05/TMA, swap-AB)", "achieved": ach, "peak": hbm_peak,
-                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "us_per_launch": us, "algorithmic_bytes": alg,
+        traffic = None
+        try:       # dram__bytes_read+write per launch of this kernel from the committed ncu --set full capture (b=32)
+            if B == 32:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))["gate_up_decode_traffic_bytes_per_launch"]
+        except Exception:
+            traffic = None
+        roof = {"bound": "hbm", "kernel": "gemm_tn_kernel (gate_up projection, tcgen05/TMA, swap-AB, split-K 2)", "achieved": ach, "peak": hbm_peak,
+                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "us_per_launch": us, "algorithmic_bytes": alg,
                 "peak_source": peak_src, "split_k": sp,
                 "whole_step": {"bytes": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / hbm_peak}}
 

@@ -41,7 +41,7 @@ def _oracle_last_logits(cfg, sd, enc, samples):
 
 def test_config2_batch32_variable_length_series_prefill():
     """configs[2]: batch-32 prefill, 8 variable-length series (64-1024) per sample, sp-mask path."""
-    cfg, sd, model, proc = _mk()
+    cfg, sd, model, proc = _mk(max_seq_len=2048)
     rng = np.random.default_rng(2)
     prompts, series = [], []
     for b in range(32):
