@@ -69,7 +69,7 @@ def load_library():
     lib.cts_reduce_bias_act.argtypes = [vp, vp, i, ll, ll, vp, i, vp, ll, vp, i, vp]
     lib.cts_reduce_residual_rmsnorm.argtypes = [vp, vp, i, vp, vp, vp, f, vp, ll, ll, i, vp]
     lib.cts_reduce_swiglu.argtypes = [vp, vp, i, ll, ll, vp, i, vp]
-    lib.cts_qkv_rope_cache.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, i, i, i, i, vp]
+    lib.cts_qkv_rope_cache.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, i, i, i, vp, vp, f, i, vp]
     lib.cts_embed_gather.argtypes = [vp, vp, vp, vp, ll, ll, ll, i, vp]
     lib.cts_attn_prefill.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, f, vp, i, vp]
     lib.cts_attn_decode_workspace_floats.argtypes = [i, i, i, i]
@@ -193,10 +193,11 @@ class Context:
         self._chk(self.lib.cts_reduce_swiglu(self.h, _p(partial), split_k, t, inter, _p(out), dtype_code(out.dtype), _stream()))
 
     def qkv_rope_cache(self, src, src_is_partial, split_k, bias, positions, cos, sin, slot_map, q_out, k_cache, v_cache,
-                       k_out, v_out, t, nh, nkv, head_dim, page_size):
+                       k_out, v_out, t, nh, nkv, head_dim, page_size, q_norm_w=None, k_norm_w=None, norm_eps=1e-6):
         self._chk(self.lib.cts_qkv_rope_cache(self.h, _p(src), int(src_is_partial), split_k, _p(bias), _p(positions), _p(cos),
                                               _p(sin), _p(slot_map), _p(q_out), _p(k_cache), _p(v_cache), _p(k_out), _p(v_out),
-                                              t, nh, nkv, head_dim, page_size, dtype_code(q_out.dtype), _stream()))
+                                              t, nh, nkv, head_dim, page_size, _p(q_norm_w), _p(k_norm_w), float(norm_eps),
+                                              dtype_code(q_out.dtype), _stream()))
 
     def embed_gather(self, table, ids, out, t=None):
         t = ids.shape[0] if t is None else t

@@ -25,6 +25,8 @@ class ChatTSConfig:
     rope_theta: float = 1e6
     max_position_embeddings: int = 32768
     tie_word_embeddings: bool = False
+    attention_bias: bool = True                 # Qwen2: q/k/v bias; Qwen3 (ChatTS-8B): none
+    qk_norm: bool = False                       # Qwen3 (ChatTS-8B): per-head RMSNorm of q and k before RoPE
     ts: dict = field(default_factory=_default_ts)
     ts_token_start_index: int = 151665          # <ts>; <ts/> = +1 (chatts_vllm.py:441)
     eos_token_id: int = 151645                  # stop ids 151643/151645 (chatts/utils/llm_utils.py:153)
@@ -41,6 +43,16 @@ class ChatTSConfig:
         """Public Qwen2.5-14B shape + the TS encoder of the released ChatTS-14B (UNVERIFIED offline; a real
         checkpoint's config.json overrides every field through from_json)."""
         return cls()
+
+    @classmethod
+    def chatts_8b(cls):
+        """ChatTS-8B = Qwen3-8B decoder (Qwen3TSForCausalLM, chatts_vllm.py:633-668) + the TS encoder at hidden 4096
+        (public Qwen3-8B shape; UNVERIFIED offline, config.json overrides)."""
+        ts = _default_ts()
+        ts["hidden_size"] = 4096
+        return cls(hidden_size=4096, intermediate_size=12288, num_hidden_layers=36, num_attention_heads=32,
+                   num_key_value_heads=8, head_dim=128, vocab_size=151936, rms_norm_eps=1e-6, rope_theta=1e6,
+                   max_position_embeddings=40960, attention_bias=False, qk_norm=True, ts=ts, ts_token_start_index=151669)
 
     @classmethod
     def tiny(cls, **kw):
@@ -61,6 +73,10 @@ class ChatTSConfig:
             cfg.head_dim = cfg.hidden_size // cfg.num_attention_heads
         if "rope_parameters" in d and isinstance(d["rope_parameters"], dict):
             cfg.rope_theta = d["rope_parameters"].get("rope_theta", cfg.rope_theta)
+        arch = " ".join(d.get("architectures", []) or [])
+        if "Qwen3" in arch or d.get("model_type") in ("qwen3", "chatts_qwen3"):
+            cfg.qk_norm = d.get("qk_norm", True)
+            cfg.attention_bias = bool(d.get("attention_bias", False))
         if isinstance(cfg.eos_token_id, (list, tuple)):
             cfg.eos_token_id = int(cfg.eos_token_id[0])
         return cfg

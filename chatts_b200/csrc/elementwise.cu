@@ -223,7 +223,8 @@ __global__ void reduce_swiglu_kernel(const float* __restrict__ part, int S, long
 }
 
 // ------------------------------------------------------------------------------------------------
-// grid (heads_total = nh + 2*nkv, T); block = head_dim/2 threads: thread i owns dims i and i + d/2 (the
+constexpr int kRopeHeadsPerBlock = 4;
+// grid (ceil((nh + 2*nkv) / 4), T); block = 4 x head_dim/2 threads: thread i of a head owns dims i and i + d/2 (the
 // rotate_half pair, modeling_qwen2.py:116-120,141-145).
 template <typename T>
 __global__ void qkv_rope_cache_kernel(const void* __restrict__ src, int src_is_partial, int S, const T* __restrict__ bias,
@@ -231,16 +232,18 @@ __global__ void qkv_rope_cache_kernel(const void* __restrict__ src, int src_is_p
                                       const T* __restrict__ sin_tab, const int* __restrict__ slot_map,
                                       T* __restrict__ q_out, T* __restrict__ k_cache, T* __restrict__ v_cache,
                                       T* __restrict__ k_out, T* __restrict__ v_out, long long t_total, int nh, int nkv,
-                                      int d, int page_size) {
+                                      int d, int page_size, const T* __restrict__ q_norm_w, const T* __restrict__ k_norm_w,
+                                      float norm_eps) {
   pdl_trigger();
   pdl_wait();
-  const int head = blockIdx.x;
-  const long long t = blockIdx.y;
   const int half = d >> 1;
-  const int i = threadIdx.x;
-  if (i >= half) return;
+  const int hl = threadIdx.x / half;                    // head slot inside the block (kRopeHeadsPerBlock heads per CTA)
+  const int head = blockIdx.x * kRopeHeadsPerBlock + hl;
+  const long long t = blockIdx.y;
+  const int i = threadIdx.x % half;
+  const bool active = head < nh + 2 * nkv;
   const long long width = (long long)(nh + 2 * nkv) * d;
-  const long long c0 = (long long)head * d + i, c1 = c0 + half;
+  const long long c0 = (long long)(active ? head : 0) * d + i, c1 = c0 + half;
   float x0, x1;
   if (src_is_partial) {
     const float* p = reinterpret_cast<const float*>(src) + t * width;
@@ -255,6 +258,25 @@ __global__ void qkv_rope_cache_kernel(const void* __restrict__ src, int src_is_p
   }
   const bool is_q = head < nh;
   const bool is_k = !is_q && head < nh + nkv;
+  if (q_norm_w != nullptr || k_norm_w != nullptr) {          // block-uniform (a CTA may hold q, k and v heads)
+    // Qwen3 per-head RMSNorm of q / k over head_dim before RoPE (transformers qwen3/modeling_qwen3.py q_norm/k_norm;
+    // vllm qwen3.py) -- same fp32-statistic / dtype rounding points as Qwen2RMSNorm
+    __shared__ float red[32];
+    float ss = active ? x0 * x0 + x1 * x1 : 0.f;
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    const int wph = half >= 32 ? half / 32 : 1;        // warps per head (head_dim/2 is a multiple of 32 here)
+    for (int w = 0; w < wph; ++w) tot += red[hl * wph + w];
+    const float inv = 1.0f / sqrtf(tot / (float)d + norm_eps);
+    const T* nw = is_q ? q_norm_w : (is_k ? k_norm_w : nullptr);
+    if (active && nw != nullptr) {
+      x0 = rnd<T>(DT<T>::to_f(nw[i]) * rnd<T>(x0 * inv));
+      x1 = rnd<T>(DT<T>::to_f(nw[i + half]) * rnd<T>(x1 * inv));
+    }
+  }
+  if (!active) return;
   if (is_q || is_k) {
     const int pos = positions[t];
     // cos/sin are [max_pos, d/2]: emb = cat(freqs, freqs) (:110) makes both halves share the same angle
@@ -427,7 +449,7 @@ extern "C" int cts_reduce_residual_rmsnorm(cts_ctx* ctx, const float* partial, i
   for (unsigned c : {8u, 4u, 2u}) {
     if (h % (8 * c) == 0 && h / (8 * c) >= 32 && h / c <= 8LL * kClMaxVec * kClThreads) { C = c; break; }
   }
-  if (C > 1 && t <= 65535) {
+  if (C > 1 && t <= 256) {      // decode-sized T: spread each token over a cluster; big T already fills the GPU
     DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_residual_rmsnorm_cluster_kernel<T>, dim3(C, (unsigned)t), dim3(kClThreads), 0,
                                                 (cudaStream_t)stream, C, partial, split_k, (const T*)resid_in, (T*)resid_out,
                                                 (const T*)norm_w, eps, (T*)norm_out, t, (int)h)));
@@ -455,7 +477,8 @@ extern "C" int cts_reduce_swiglu(cts_ctx* ctx, const float* partial, int split_k
 extern "C" int cts_qkv_rope_cache(cts_ctx* ctx, const void* src, int src_is_partial, int split_k, const void* bias,
                                   const int* positions, const void* cos_tab, const void* sin_tab, const int* slot_map,
                                   void* q_out, void* k_cache, void* v_cache, void* k_out, void* v_out, long long t, int nh,
-                                  int nkv, int head_dim, int page_size, int dtype, void* stream) {
+                                  int nkv, int head_dim, int page_size, const void* q_norm_w, const void* k_norm_w, float norm_eps,
+                                  int dtype, void* stream) {
   if (!ctx) return CTS_ERR_BAD_ARG;
   CTS_CHECK_ARG(ctx, src && positions && cos_tab && sin_tab && q_out, "null pointer");
   CTS_CHECK_ARG(ctx, nh > 0 && nkv > 0 && head_dim > 0 && head_dim % 2 == 0 && head_dim <= 512, "head config");
@@ -466,10 +489,11 @@ extern "C" int cts_qkv_rope_cache(cts_ctx* ctx, const void* src, int src_is_part
   if (t == 0) return CTS_OK;
   // t can exceed 65535 in a big prefill: fold into chunks of the y grid dimension
   const long long width = (long long)(nh + 2 * nkv) * head_dim;
-  const int threads = ((head_dim / 2 + 31) / 32) * 32;
+  CTS_CHECK_ARG(ctx, (head_dim / 2) % 32 == 0 || (q_norm_w == nullptr && k_norm_w == nullptr), "q/k norm needs head_dim % 64 == 0");
+  const int threads = kRopeHeadsPerBlock * (head_dim / 2);
   for (long long tb = 0; tb < t; tb += 65535) {
     const long long tc = (t - tb) < 65535 ? (t - tb) : 65535;
-    dim3 grid((unsigned)(nh + 2 * nkv), (unsigned)tc);
+    dim3 grid((unsigned)((nh + 2 * nkv + kRopeHeadsPerBlock - 1) / kRopeHeadsPerBlock), (unsigned)tc);
     if (src_is_partial) {
       CTS_CHECK_ARG(ctx, t <= 65535, "partial input with t > 65535");
     }
@@ -480,7 +504,8 @@ extern "C" int cts_qkv_rope_cache(cts_ctx* ctx, const void* src, int src_is_part
                                         slot_map ? slot_map + tb : (const int*)nullptr, (T*)q_out + tb * (long long)nh * head_dim,
                                         (T*)k_cache, (T*)v_cache, k_out ? (T*)k_out + tb * (long long)nkv * head_dim : (T*)nullptr,
                                         v_out ? (T*)v_out + tb * (long long)nkv * head_dim : (T*)nullptr,
-                                        src_is_partial ? t : tc, nh, nkv, head_dim, page_size)));
+                                        src_is_partial ? t : tc, nh, nkv, head_dim, page_size, (const T*)q_norm_w, (const T*)k_norm_w,
+                                        norm_eps)));
   }
   return CTS_OK;
 }

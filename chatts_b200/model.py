@@ -110,6 +110,7 @@ class ChatTSForCausalLM:
         self.lm_head = take("lm_head.weight") if "lm_head.weight" in sd else (
             shard_tensor("lm_head.weight", sd["model.embed_tokens.weight"], cfg, self.tp_rank, self.tp_size).to(dev, dt).contiguous())
         self.ln1, self.ln2, self.wqkv, self.bqkv, self.wo, self.wgu, self.wd = [], [], [], [], [], [], []
+        self.qn, self.kn = [], []
         for l in range(self.L):
             p = f"model.layers.{l}."
             self.ln1.append(take(p + "input_layernorm.weight"))
@@ -119,6 +120,9 @@ class ChatTSForCausalLM:
                 self.bqkv.append(torch.cat([take(p + f"self_attn.{n}_proj.bias") for n in "qkv"], 0).contiguous())
             else:
                 self.bqkv.append(None)
+            has_qkn = (p + "self_attn.q_norm.weight") in sd          # Qwen3 / ChatTS-8B
+            self.qn.append(take(p + "self_attn.q_norm.weight") if has_qkn else None)
+            self.kn.append(take(p + "self_attn.k_norm.weight") if has_qkn else None)
             self.wo.append(take(p + "self_attn.o_proj.weight"))
             self.wgu.append(torch.cat([take(p + "mlp.gate_proj.weight"), take(p + "mlp.up_proj.weight")], 0).contiguous())
             self.wd.append(take(p + "mlp.down_proj.weight"))
@@ -173,11 +177,11 @@ class ChatTSForCausalLM:
             if sp["qkv"] > 1:
                 c.gemm(st.xn, self.wqkv[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["qkv"], t=T)
                 c.qkv_rope_cache(st.ws, True, sp["qkv"], self.bqkv[l], st.positions, self.cos, self.sin, st.slot_map, st.q, kc, vc,
-                                 st.k_lin, st.v_lin, T, self.nh, self.nkv, self.d, self.page_size)
+                                 st.k_lin, st.v_lin, T, self.nh, self.nkv, self.d, self.page_size, self.qn[l], self.kn[l], eps)
             else:
                 c.gemm(st.xn, self.wqkv[l], st.qkv, bias=self.bqkv[l], epilogue=EPI_NONE, t=T)
                 c.qkv_rope_cache(st.qkv, False, 1, None, st.positions, self.cos, self.sin, st.slot_map, st.q, kc, vc,
-                                 st.k_lin, st.v_lin, T, self.nh, self.nkv, self.d, self.page_size)
+                                 st.k_lin, st.v_lin, T, self.nh, self.nkv, self.d, self.page_size, self.qn[l], self.kn[l], eps)
             attend(l)
             # ---- o_proj + residual + post-attention RMSNorm
             if self.tp_size > 1:

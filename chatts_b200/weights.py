@@ -36,11 +36,15 @@ def decoder_shapes(cfg, layers=None):
     for l in range(cfg.num_hidden_layers if layers is None else layers):
         p = f"model.layers.{l}."
         shapes[p + "self_attn.q_proj.weight"] = (nh * d, H)
-        shapes[p + "self_attn.q_proj.bias"] = (nh * d,)
         shapes[p + "self_attn.k_proj.weight"] = (nkv * d, H)
-        shapes[p + "self_attn.k_proj.bias"] = (nkv * d,)
         shapes[p + "self_attn.v_proj.weight"] = (nkv * d, H)
-        shapes[p + "self_attn.v_proj.bias"] = (nkv * d,)
+        if getattr(cfg, "attention_bias", True):
+            shapes[p + "self_attn.q_proj.bias"] = (nh * d,)
+            shapes[p + "self_attn.k_proj.bias"] = (nkv * d,)
+            shapes[p + "self_attn.v_proj.bias"] = (nkv * d,)
+        if getattr(cfg, "qk_norm", False):
+            shapes[p + "self_attn.q_norm.weight"] = (d,)
+            shapes[p + "self_attn.k_norm.weight"] = (d,)
         shapes[p + "self_attn.o_proj.weight"] = (H, nh * d)
         shapes[p + "mlp.gate_proj.weight"] = (I, H)
         shapes[p + "mlp.up_proj.weight"] = (I, H)
@@ -67,7 +71,7 @@ def synthetic_state_dict(cfg, seed=1234, device="cpu", dtype=torch.bfloat16, std
         if names is not None and name not in names:
             # still advance the generator identically? No: names-filtered dicts are only used for benchmarks.
             continue
-        if name.endswith("layernorm.weight") or name == "model.norm.weight":
+        if name.endswith(("layernorm.weight", "q_norm.weight", "k_norm.weight")) or name == "model.norm.weight":
             t = torch.rand(shape, generator=g, device=device, dtype=torch.float32) + 0.5
         else:
             t = torch.randn(shape, generator=g, device=device, dtype=torch.float32) * std

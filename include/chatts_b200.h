@@ -130,11 +130,14 @@ int cts_reduce_swiglu(cts_ctx* ctx, const float* partial, int split_k, long long
  *   src: fp32 [split_k, t, (nh+2nkv)*d] when src_is_partial, else model-dtype [t, (nh+2nkv)*d] (bias already in)
  *   cos/sin: [max_pos, d/2] model dtype;  positions int32[t];  slot_map int32[t] (<0: no cache write)
  *   cache layout: [num_pages, nkv, page_size, d]
+ *   q_norm_w / k_norm_w [d] (or NULL): Qwen3 / ChatTS-8B per-head RMSNorm of q and k before RoPE
+ *   (chatts_vllm.py:633-668 selects Qwen3ForCausalLM; transformers qwen3/modeling_qwen3.py), eps = norm_eps
  */
 int cts_qkv_rope_cache(cts_ctx* ctx, const void* src, int src_is_partial, int split_k, const void* bias,
                        const int* positions, const void* cos_tab, const void* sin_tab, const int* slot_map,
                        void* q_out, void* k_cache, void* v_cache, void* k_out, void* v_out, long long t, int nh,
-                       int nkv, int head_dim, int page_size, int dtype, void* stream);
+                       int nkv, int head_dim, int page_size, const void* q_norm_w, const void* k_norm_w, float norm_eps,
+                       int dtype, void* stream);
 
 /* K4  embedding lookup: out[i] = table[ids[i]] for ids[i] >= 0 (rows with id < 0 are left untouched:
  * they are the patch rows the TS encoder scatters)            chatts_vllm.py:569 */

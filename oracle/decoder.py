@@ -90,6 +90,11 @@ def forward_hidden(x, w, cfg, state):
         q = F.linear(a, w[pre + "self_attn.q_proj.weight"], w.get(pre + "self_attn.q_proj.bias")).view(T, nh, d)
         k = F.linear(a, w[pre + "self_attn.k_proj.weight"], w.get(pre + "self_attn.k_proj.bias")).view(T, nkv, d)
         v = F.linear(a, w[pre + "self_attn.v_proj.weight"], w.get(pre + "self_attn.v_proj.bias")).view(T, nkv, d)
+        if (pre + "self_attn.q_norm.weight") in w:
+            # Qwen3 (ChatTS-8B, chatts_vllm.py:633-668): per-head RMSNorm of q and k over head_dim before RoPE
+            # (transformers models/qwen3/modeling_qwen3.py Qwen3Attention.forward)
+            q = rms_norm(q, w[pre + "self_attn.q_norm.weight"], eps)
+            k = rms_norm(k, w[pre + "self_attn.k_norm.weight"], eps)
         q, k = apply_rope(q, k, cos, sin)
         state.k[l] = k if state.k[l] is None else torch.cat([state.k[l], k], 0)
         state.v[l] = v if state.v[l] is None else torch.cat([state.v[l], v], 0)

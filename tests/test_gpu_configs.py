@@ -193,3 +193,17 @@ def test_full_size_decoder_layer_vs_oracle():
         lgf = od.logits(od.forward_hidden(sd["model.embed_tokens.weight"][tok][None], sd, cfg.to_dict(), st), sd)[0].float()
     record("full_size_decoder_layer", err=err, worst_gap_rel=worst)
     assert err < 2e-2 and worst < 2e-2
+
+
+def test_chatts_8b_qwen3_variant_matches_oracle():
+    """ChatTS-8B decoder family (Qwen3: per-head q/k RMSNorm before RoPE, no qkv bias; chatts_vllm.py:633-668)."""
+    cfg, sd, model, proc = _mk(seed=6, max_batch=2, max_seq_len=512, qk_norm=True, attention_bias=False)
+    assert "model.layers.0.self_attn.q_norm.weight" in sd and "model.layers.0.self_attn.q_proj.bias" not in sd
+    x = np.arange(200)
+    enc = proc(text=["Q3 <ts><ts/> end", "no ts"], timeseries=[np.cos(x / 7) * 3], padding=True, return_tensors="pt")
+    lg = model.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"]).logits[:, 0]
+    ref, _ = _oracle_last_logits(cfg, sd, enc, samples=[0, 1])
+    worst = max(rel_err(lg[b], r) for b, (r, _) in ref.items())
+    ids = model.generate(**enc, max_new_tokens=10, ignore_eos=True)
+    record("chatts_8b_qwen3_variant", err=worst)
+    assert worst < 2e-2 and ids.shape[1] == enc["input_ids"].shape[1] + 10

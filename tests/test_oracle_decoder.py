@@ -65,3 +65,31 @@ def test_greedy_generate_matches_transformers_fp32():
     with torch.no_grad():
         ids = m.generate(inputs_embeds=x[None], max_new_tokens=6, do_sample=False)
     assert ids[0].tolist() == toks
+
+
+def test_qwen3_variant_matches_transformers():
+    """ChatTS-8B uses the Qwen3 decoder (chatts_vllm.py:633-668): per-head q/k RMSNorm, no qkv bias."""
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    torch.manual_seed(0)
+    c = Qwen3Config(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+                    head_dim=64, vocab_size=320, rms_norm_eps=1e-6, rope_theta=1e6, max_position_embeddings=512,
+                    tie_word_embeddings=False, attention_bias=False, attn_implementation="eager")
+    m = Qwen3ForCausalLM(c).eval()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "norm" in n:
+                p.uniform_(0.5, 1.5)
+    w = {k: v.detach() for k, v in m.state_dict().items()}
+    cfg = dict(CFG)
+    x = torch.randn(23, 256) * 0.5
+    st = od.State(2)
+    lg = od.logits(od.forward_hidden(x, w, cfg, st), w)
+    with torch.no_grad():
+        out = m(inputs_embeds=x[None], use_cache=True)
+    scale = out.logits.abs().max()
+    assert (lg - out.logits[0]).abs().max() / scale < 2e-5
+    e = torch.randn(1, 256) * 0.5
+    lg = od.logits(od.forward_hidden(e, w, cfg, st), w)
+    with torch.no_grad():
+        o2 = m(inputs_embeds=e[None], past_key_values=out.past_key_values, use_cache=True)
+    assert (lg - o2.logits[0]).abs().max() / scale < 2e-5
