@@ -60,7 +60,7 @@ def test_config2_batch32_variable_length_series_prefill():
 
 def test_config3_batch8_30_series_len512_decode():
     """configs[3] workload on one GPU: batch-8 decode, 30 series x len-512 per sample (960 patch rows each)."""
-    cfg, sd, model, proc = _mk(seed=1, max_batch=8, max_seq_len=2048)
+    cfg, sd, model, proc = _mk(seed=1, max_batch=8, max_seq_len=4608, max_position_embeddings=8192)
     rng = np.random.default_rng(3)
     prompts = [" ".join(f"m{k}: <ts><ts/>" for k in range(30)) + " summarize." for _ in range(8)]
     series = [np.cumsum(rng.normal(size=512)) for _ in range(8 * 30)]
