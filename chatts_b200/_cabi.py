@@ -71,7 +71,7 @@ def load_library():
     lib.cts_reduce_swiglu.argtypes = [vp, vp, i, ll, ll, vp, i, vp]
     lib.cts_qkv_rope_cache.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, i, i, i, vp, vp, f, i, vp]
     lib.cts_embed_gather.argtypes = [vp, vp, vp, vp, ll, ll, ll, i, vp]
-    lib.cts_attn_prefill.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, f, vp, i, vp]
+    lib.cts_attn_prefill.argtypes = [vp, vp, vp, vp, vp, i, i, ll, i, i, i, f, vp, i, vp]
     lib.cts_attn_decode_workspace_floats.argtypes = [i, i, i, i]
     lib.cts_attn_decode_workspace_floats.restype = ll
     lib.cts_attn_decode.argtypes = [vp, vp, vp, vp, i, vp, i, vp, i, i, i, i, i, f, i, vp, vp, i, vp]
@@ -206,8 +206,8 @@ class Context:
 
     # ------------------------------------------------------------------ attention
     def attn_prefill(self, q, k, v, cu_seqlens, batch, max_seqlen, nh, nkv, head_dim, scale, out):
-        self._chk(self.lib.cts_attn_prefill(self.h, _p(q), _p(k), _p(v), _p(cu_seqlens), batch, max_seqlen, nh, nkv, head_dim,
-                                            float(scale), _p(out), dtype_code(q.dtype), _stream()))
+        self._chk(self.lib.cts_attn_prefill(self.h, _p(q), _p(k), _p(v), _p(cu_seqlens), batch, max_seqlen, q.shape[0], nh, nkv,
+                                            head_dim, float(scale), _p(out), dtype_code(q.dtype), _stream()))
 
     def attn_decode_workspace_floats(self, batch, nh, head_dim, num_splits):
         return int(self.lib.cts_attn_decode_workspace_floats(batch, nh, head_dim, num_splits))

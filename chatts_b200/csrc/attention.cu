@@ -12,6 +12,8 @@
 //                     each page; partial (m, l, o) per split are merged by a second tiny kernel.
 #include <mma.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tensormap.cuh"
 
@@ -226,6 +228,219 @@ attn_prefill_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
       *reinterpret_cast<uint4*>(o_g + col) = pack8<T>(f);
     }
   }
+}
+
+// ================================================================================================
+// prefill on tcgen05 (head_dim 128): S = Q K^T and O += P V on the 5th-gen tensor cores, accumulators in TMEM
+// ================================================================================================
+// One CTA = 128 query rows of one (sequence, head).  Q, K, V tiles arrive by TMA (128-byte swizzle); the MMA warp
+// issues tcgen05.mma (M=128, N=128, K=16) for S[128 x 128] = Q K^T into TMEM columns 0..127; the four softmax warps
+// (thread = query row, lane-aligned with TMEM) read S with tcgen05.ld, and
+//   pass 1: keep the running row maximum                                 (K tiles only)
+//   pass 2: write P = exp2((s - m) * scale*log2e) as bf16/fp16 into a swizzled K-major shared tile, accumulate the row
+//           sum, and the MMA warp issues O[128 x 128] += P V into TMEM columns 128..255 (V is the MN-major B operand).
+// Two passes mean the O accumulator never needs a rescale (QK^T costs 2x, the softmax/PV path 1x).  Causal masking only
+// touches the diagonal tile (query and KV tiles are both 128 and aligned).  Epilogue: O / l from TMEM to global.
+constexpr int kTcQ = 128, kTcKV = 128, kTcThreads = 192;
+constexpr int kTcTile = kTcKV * 128 * 2;        // bytes of one [128 rows x 128 d] bf16 tile = two 16 KiB swizzled halves
+constexpr int kTcHalf = kTcKV * 128;            // one [128 rows x 128 B] half
+
+// MN-major (N contiguous) B operand, 128B swizzle: atoms of [8 K-rows x 64 N-elements]; LBO = stride between the
+// two 64-element N atoms (the two halves of the tile), SBO = stride between consecutive 8-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTcThreads, 1)
+attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const __grid_constant__ CUtensorMap tm_v, const int* __restrict__ cu_seqlens, int nh, int nkv,
+                        float scale, T* __restrict__ out) {
+  constexpr int HD = 128;
+  extern __shared__ uint8_t tc_raw[];
+  __shared__ uint64_t q_bar, kv_full[2], kv_empty[2], s_full, s_free, p_full, o_done;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t raw = smem_u32(tc_raw);
+  uint8_t* smem = tc_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* q_s = smem;                       // 32 KiB
+  uint8_t* p_s = smem + kTcTile;             // 32 KiB
+  uint8_t* kv_s = smem + 2 * kTcTile;        // 2 stages x (K 32 KiB + V 32 KiB)
+
+  const int b = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
+    mbar_init(&q_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(&s_full, 1);
+    mbar_init(&s_free, 4);
+    mbar_init(&p_full, 4);
+    mbar_init(&o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  pdl_wait();
+
+  const int seq0 = cu_seqlens[b], len = cu_seqlens[b + 1] - seq0;
+  const int q0 = qt * kTcQ;
+  const bool live = q0 < len;                   // CTA-uniform
+  const int kvh = head / (nh / nkv);
+  const int ntiles = live ? qt + 1 : 0;         // causal: KV tiles 0..qt
+  const int total = 2 * ntiles;                 // pass 1 then pass 2
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0 && live) {
+      mbar_expect_tx(&q_bar, (uint32_t)kTcTile);
+      tma_load_2d(q_s, &tm_q, &q_bar, head * HD, seq0 + q0, CTS_L2_EVICT_FIRST);
+      tma_load_2d(q_s + kTcHalf, &tm_q, &q_bar, head * HD + 64, seq0 + q0, CTS_L2_EVICT_FIRST);
+      for (int i = 0; i < total; ++i) {
+        const int s = i & 1;
+        const int j = i < ntiles ? i : i - ntiles;
+        const bool with_v = i >= ntiles;
+        mbar_wait(&kv_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&kv_full[s], (uint32_t)(with_v ? 2 * kTcTile : kTcTile));
+        uint8_t* ks = kv_s + (size_t)s * 2 * kTcTile;
+        const int row = seq0 + j * kTcKV;
+        tma_load_2d(ks, &tm_k, &kv_full[s], kvh * HD, row, CTS_L2_EVICT_LAST);
+        tma_load_2d(ks + kTcHalf, &tm_k, &kv_full[s], kvh * HD + 64, row, CTS_L2_EVICT_LAST);
+        if (with_v) {
+          tma_load_2d(ks + kTcTile, &tm_v, &kv_full[s], kvh * HD, row, CTS_L2_EVICT_LAST);
+          tma_load_2d(ks + kTcTile + kTcHalf, &tm_v, &kv_full[s], kvh * HD + 64, row, CTS_L2_EVICT_LAST);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0 && live) {
+      constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+      const uint32_t idesc_qk = umma_idesc_f16(kBf16 ? 1 : 0, 128, 128);
+      const uint32_t idesc_pv = idesc_qk | (1u << 16);                  // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(q_s), p_addr = smem_u32(p_s);
+      mbar_wait(&q_bar, 0);
+      for (int i = 0; i < total; ++i) {
+        const int s = i & 1;
+        const bool pass2 = i >= ntiles;
+        const uint32_t k_addr = smem_u32(kv_s + (size_t)s * 2 * kTcTile), v_addr = k_addr + kTcTile;
+        mbar_wait(&kv_full[s], (uint32_t)(i >> 1) & 1u);
+        if (i > 0) mbar_wait(&s_free, (uint32_t)(i - 1) & 1u);          // softmax warps are done with S of tile i-1
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (uint32_t)(kk >> 2) * kTcHalf + (uint32_t)(kk & 3) * 32;
+          umma_f16(tmem_base, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off), idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full);
+        if (!pass2) {
+          umma_commit(&kv_empty[s]);                                    // K consumed
+        } else {
+          mbar_wait(&p_full, (uint32_t)(i - ntiles) & 1u);              // P tile written (and S free again)
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < kTcKV / 16; ++kk) {
+            const uint32_t aoff = (uint32_t)(kk >> 2) * kTcHalf + (uint32_t)(kk & 3) * 32;
+            const uint64_t bdesc = umma_desc_mn_sw128(v_addr + (uint32_t)kk * 16 * 128, kTcHalf, 1024);
+            umma_f16(tmem_base + 128, umma_desc_k_sw128(p_addr + aoff), bdesc, idesc_pv, (i > ntiles || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[s]);                                    // K, V and P consumed
+        }
+      }
+      umma_commit(&o_done);
+    }
+  } else if (live) {
+    // ------------------------------ softmax / epilogue warps (thread = query row) ------------------------------
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                          // row inside the tile == TMEM lane
+    const int qi = q0 + r;                                // query index inside the sequence
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float sl2 = scale * 1.4426950408889634f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int i = 0; i < total; ++i) {
+      const bool pass2 = i >= ntiles;
+      const int j = pass2 ? i - ntiles : i;
+      const int kv0 = j * kTcKV;
+      const bool diag = j == qt;
+      mbar_wait(&s_full, (uint32_t)i & 1u);
+      tc_fence_after();
+      if (!pass2) {
+        float mx = m_run;
+#pragma unroll 1
+        for (int c = 0; c < kTcKV; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float sv = __uint_as_float(v[e]);
+            if (!diag || kv0 + c + e <= qi) mx = fmaxf(mx, sv);
+          }
+        }
+        m_run = mx;
+      } else {
+        const float mneg = m_run > -INFINITY ? m_run * sl2 : 0.f;
+#pragma unroll 1
+        for (int c = 0; c < kTcKV; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+          tmem_ld_wait();
+          float pv[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const bool ok = !diag || kv0 + c + e <= qi;
+            pv[e] = ok ? exp2f(__uint_as_float(v[e]) * sl2 - mneg) : 0.f;
+            l_run += pv[e];
+          }
+          // P[r][c..c+15] -> K-major swizzled tile: 16-byte chunk index (c/8 .. +1) inside the 64-wide half c/64
+          const uint32_t hb = (uint32_t)(c >> 6) * kTcHalf + (uint32_t)r * 128;
+          const int ch = (c & 63) >> 3;
+          *reinterpret_cast<uint4*>(p_s + hb + (((ch) ^ (r & 7)) << 4)) = pack8<T>(pv);
+          *reinterpret_cast<uint4*>(p_s + hb + (((ch + 1) ^ (r & 7)) << 4)) = pack8<T>(pv + 8);
+        }
+        fence_proxy_async_smem();                       // P must be visible to the tensor core (async proxy)
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_free);
+        if (pass2) mbar_arrive(&p_full);
+      }
+    }
+    // ---- epilogue: O / l
+    mbar_wait(&o_done, 0);
+    tc_fence_after();
+    {
+      // tcgen05.ld is warp-collective: every lane loads its row; only rows inside the sequence are stored
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      T* o_g = out + ((long long)seq0 + (qi < len ? qi : 0)) * nh * HD + (long long)head * HD;
+#pragma unroll 1
+      for (int c = 0; c < HD; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(lane_addr + 128u + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (qi < len) {
+          float f[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) * inv;
+          *reinterpret_cast<uint4*>(o_g + c) = pack8<T>(f);
+          *reinterpret_cast<uint4*>(o_g + c + 8) = pack8<T>(f + 8);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
 // ================================================================================================
@@ -488,8 +703,8 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
 }  // namespace
 
 extern "C" int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, const void* v, const int* cu_seqlens, int batch,
-                                int max_seqlen, int nh, int nkv, int head_dim, float scale, void* out, int dtype,
-                                void* stream) {
+                                int max_seqlen, long long total_tokens_hint, int nh, int nkv, int head_dim, float scale, void* out,
+                                int dtype, void* stream) {
   if (!ctx) return CTS_ERR_BAD_ARG;
   CTS_CHECK_ARG(ctx, q && k && v && cu_seqlens && out, "null pointer");
   CTS_CHECK_ARG(ctx, nh > 0 && nkv > 0 && nh % nkv == 0, "nh must be a positive multiple of nkv");
@@ -497,8 +712,31 @@ extern "C" int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, cons
   if (head_dim != 64 && head_dim != 128) return cts_set_error(ctx, CTS_ERR_UNSUPPORTED, "cts_attn_prefill: head_dim %d (64 or 128)", head_dim);
   if (batch == 0 || max_seqlen == 0) return CTS_OK;
   CTS_CHECK_ARG(ctx, batch <= 65535 && nh <= 65535, "grid");
-  dim3 grid((unsigned)((max_seqlen + kPfQ - 1) / kPfQ), (unsigned)nh, (unsigned)batch);
   cudaStream_t st = (cudaStream_t)stream;
+  if (head_dim == 128 && !ctx->force_wmma_attention) {
+    // tcgen05 path: Q/K/V through TMA tensor maps over the packed [tokens, heads*128] activations
+    const long long total_tokens = total_tokens_hint > 0 ? total_tokens_hint : (long long)batch * max_seqlen;
+    CUtensorMap tm_q, tm_k, tm_v;
+    int rc = cts_make_tmap_2d(ctx, &tm_q, q, total_tokens, (long long)nh * 128, (long long)nh * 128, kTcQ, dtype == CTS_BF16);
+    if (rc) return rc;
+    rc = cts_make_tmap_2d(ctx, &tm_k, k, total_tokens, (long long)nkv * 128, (long long)nkv * 128, kTcKV, dtype == CTS_BF16);
+    if (rc) return rc;
+    rc = cts_make_tmap_2d(ctx, &tm_v, v, total_tokens, (long long)nkv * 128, (long long)nkv * 128, kTcKV, dtype == CTS_BF16);
+    if (rc) return rc;
+    dim3 g5((unsigned)((max_seqlen + kTcQ - 1) / kTcQ), (unsigned)nh, (unsigned)batch);
+    const size_t smem5 = (size_t)6 * kTcTile + 1024;
+    if (dtype == CTS_BF16) {
+      auto kern = attn_prefill_tc5_kernel<__nv_bfloat16>;
+      CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+      CTS_CUDA(ctx, launch_pdl(kern, g5, dim3(kTcThreads), smem5, st, 1, tm_q, tm_k, tm_v, cu_seqlens, nh, nkv, scale, (__nv_bfloat16*)out));
+    } else {
+      auto kern = attn_prefill_tc5_kernel<__half>;
+      CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+      CTS_CUDA(ctx, launch_pdl(kern, g5, dim3(kTcThreads), smem5, st, 1, tm_q, tm_k, tm_v, cu_seqlens, nh, nkv, scale, (__half*)out));
+    }
+    return CTS_OK;
+  }
+  dim3 grid((unsigned)((max_seqlen + kPfQ - 1) / kPfQ), (unsigned)nh, (unsigned)batch);
 #define PF_LAUNCH(TT, HDV)                                                                                   \
   {                                                                                                          \
     auto kern = attn_prefill_kernel<TT, HDV>;                                                                \

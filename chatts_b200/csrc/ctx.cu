@@ -64,6 +64,8 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
   ctx->encode_tiled = (PFN_cuTensorMapEncodeTiled_v12000)fn;
   const char* e1 = getenv("CTS_L2_PREFETCH_MB");
   ctx->l2_prefetch_mb = e1 ? atoi(e1) : 0;
+  const char* e3 = getenv("CTS_ATTN_WMMA");
+  ctx->force_wmma_attention = e3 ? atoi(e3) : 0;
   const char* e2 = getenv("CTS_DECODE_SMEM_KB");
   ctx->decode_stages = e2 ? atoi(e2) : 75;   // 3 CTAs/SM x 3-4 stages measured best on B200 (profiles/r1_sweep_decode_gemm.txt)
   *out = ctx;

@@ -147,11 +147,12 @@ int cts_embed_gather(cts_ctx* ctx, const void* table, const int* ids, void* out,
 /* ------------------------------------------------------------------------------------------------
  * K8 attention                       modeling_qwen2.py:161-184 ; vllm qwen2.py:188-197,234
  * prefill: causal GQA over the tokens of this call, variable length, cu_seqlens int32[batch+1]
- *   q [t, nh, d], k/v [t, nkv, d] (RoPE applied), out [t, nh*d]
+ *   q [t, nh, d], k/v [t, nkv, d] (RoPE applied), out [t, nh*d]; total_tokens = t (rows of q/k/v; bounds the TMA maps)
+ *   head_dim 128: tcgen05 kernel (TMA-staged Q/K/V, S and O accumulators in TMEM); head_dim 64: HMMA (wmma) kernel
  */
 int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, const void* v, const int* cu_seqlens, int batch,
-                     int max_seqlen, int nh, int nkv, int head_dim, float scale, void* out, int dtype,
-                     void* stream);
+                     int max_seqlen, long long total_tokens, int nh, int nkv, int head_dim, float scale, void* out,
+                     int dtype, void* stream);
 
 /* decode: one query token per sequence against the paged cache (flash-decoding split over KV tiles of 64 tokens;
  * pages are staged by TMA with the 128-byte swizzle, QK^T and PV run on mma.sync, the last split to finish merges).
