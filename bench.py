@@ -325,19 +325,13 @@ def run_b200(args):
         n_rep = max(1, args.steps // 4)
         for _ in range(2):
             for l in range(L):
-                if sp > 1:
-                    ctx.gemm(st.xn, model.wgu[l], st.ws, epilogue=_cabi.EPI_PARTIAL_F32, split_k=sp, t=B)
-                else:
-                    ctx.gemm(st.xn, model.wgu[l][:I], st.act, w2=model.wgu[l][I:], epilogue=_cabi.EPI_SWIGLU, t=B)
+                ctx.gemm(st.xn, model.wgu[l], st.ws, epilogue=_cabi.EPI_PARTIAL_F32, split_k=sp, t=B)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n_rep):
             for l in range(L):
-                if sp > 1:
-                    ctx.gemm(st.xn, model.wgu[l], st.ws, epilogue=_cabi.EPI_PARTIAL_F32, split_k=sp, t=B)
-                else:
-                    ctx.gemm(st.xn, model.wgu[l][:I], st.act, w2=model.wgu[l][I:], epilogue=_cabi.EPI_SWIGLU, t=B)
+                ctx.gemm(st.xn, model.wgu[l], st.ws, epilogue=_cabi.EPI_PARTIAL_F32, split_k=sp, t=B)
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (n_rep * L)

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libchatts_b200.so")
 
 OK = 0
 BF16, F16 = 0, 1
-EPI_NONE, EPI_GELU, EPI_SWIGLU, EPI_PARTIAL_F32, EPI_RESIDUAL, EPI_SPLITK_F32 = 0, 1, 2, 3, 4, 5
+EPI_NONE, EPI_GELU, EPI_SWIGLU, EPI_PARTIAL_F32, EPI_RESIDUAL, EPI_SPLITK_F32, EPI_SWIGLU_IL = 0, 1, 2, 3, 4, 5, 6
 
 # every symbol include/chatts_b200.h declares (tests/test_cabi_symbols.py checks the .so exports them all)
 SYMBOLS = [
@@ -68,7 +68,7 @@ def load_library():
     lib.cts_gemm_suggest_split.argtypes = [vp, ll, ll, ll, i]
     lib.cts_reduce_bias_act.argtypes = [vp, vp, i, ll, ll, vp, i, vp, ll, vp, i, vp]
     lib.cts_reduce_residual_rmsnorm.argtypes = [vp, vp, i, vp, vp, vp, f, vp, ll, ll, i, vp]
-    lib.cts_reduce_swiglu.argtypes = [vp, vp, i, ll, ll, vp, i, vp]
+    lib.cts_reduce_swiglu.argtypes = [vp, vp, i, ll, ll, vp, i, i, vp]
     lib.cts_qkv_rope_cache.argtypes = [vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, i, i, i, vp, vp, f, i, vp]
     lib.cts_embed_gather.argtypes = [vp, vp, vp, vp, ll, ll, ll, i, vp]
     lib.cts_attn_prefill.argtypes = [vp, vp, vp, vp, vp, i, i, ll, i, i, i, f, vp, i, vp]
@@ -189,8 +189,9 @@ class Context:
                                                        float(eps), _p(norm_out), t, resid_in.shape[-1],
                                                        dtype_code(resid_in.dtype), _stream()))
 
-    def reduce_swiglu(self, partial, split_k, t, inter, out):
-        self._chk(self.lib.cts_reduce_swiglu(self.h, _p(partial), split_k, t, inter, _p(out), dtype_code(out.dtype), _stream()))
+    def reduce_swiglu(self, partial, split_k, t, inter, out, interleaved=False):
+        self._chk(self.lib.cts_reduce_swiglu(self.h, _p(partial), split_k, t, inter, _p(out), int(interleaved),
+                                             dtype_code(out.dtype), _stream()))
 
     def qkv_rope_cache(self, src, src_is_partial, split_k, bias, positions, cos, sin, slot_map, q_out, k_cache, v_cache,
                        k_out, v_out, t, nh, nkv, head_dim, page_size, q_norm_w=None, k_norm_w=None, norm_eps=1e-6):

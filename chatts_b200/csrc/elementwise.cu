@@ -59,7 +59,7 @@ __global__ void reduce_bias_act_kernel(const float* __restrict__ part, int S, lo
 constexpr int kNormThreads = 256;
 constexpr int kNormMaxVec = 8;   // up to 8 x 8 elements per thread -> H <= 16384
 
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(kNormThreads)
 reduce_residual_rmsnorm_kernel(const float* __restrict__ part, int S, const T* __restrict__ resid_in,
                                T* __restrict__ resid_out, const T* __restrict__ norm_w, float eps,
@@ -68,11 +68,11 @@ reduce_residual_rmsnorm_kernel(const float* __restrict__ part, int S, const T* _
   pdl_wait();
   const long long t = blockIdx.x;
   const int nvec = h / 8;
-  float vals[kNormMaxVec][8];
+  float vals[NV][8];
   float ss = 0.f;
   const long long stride = t_total * (long long)h;
 #pragma unroll
-  for (int it = 0; it < kNormMaxVec; ++it) {
+  for (int it = 0; it < NV; ++it) {
     const int v = it * kNormThreads + threadIdx.x;
     if (v < nvec) {
       float r[8];
@@ -111,7 +111,7 @@ reduce_residual_rmsnorm_kernel(const float* __restrict__ part, int S, const T* _
   __syncthreads();
   const float inv = inv_s;
 #pragma unroll
-  for (int it = 0; it < kNormMaxVec; ++it) {
+  for (int it = 0; it < NV; ++it) {
     const int v = it * kNormThreads + threadIdx.x;
     if (v < nvec) {
       float w[8], o[8];
@@ -205,109 +205,135 @@ reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ part, int S, co
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void reduce_swiglu_kernel(const float* __restrict__ part, int S, long long t_total, long long inter,
-                                     T* __restrict__ out) {
+                                     T* __restrict__ out, int interleaved) {
   pdl_trigger();
   pdl_wait();
   const long long t = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= inter) return;
   const long long n = 2 * inter;
+  // column of gate_i / up_i in the projection output: stacked [gate | up], or interleaved per 128-wide tile
+  // (64 gate columns then the 64 matching up columns -- the layout CTS_EPI_SWIGLU_IL uses)
+  const long long gi = interleaved ? (i >> 6) * 128 + (i & 63) : i;
+  const long long ui = interleaved ? gi + 64 : inter + i;
   float g = 0.f, u = 0.f;
   for (int s = 0; s < S; ++s) {
     const float* p = part + ((long long)s * t_total + t) * n;
-    g += p[i];
-    u += p[inter + i];
+    g += p[gi];
+    u += p[ui];
   }
   const float r = rnd<T>(silu_f(rnd<T>(g))) * rnd<T>(u);
   out[t * inter + i] = DT<T>::from_f(r);
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int kRopeHeadsPerBlock = 4;
-// grid (ceil((nh + 2*nkv) / 4), T); block = 4 x head_dim/2 threads: thread i of a head owns dims i and i + d/2 (the
-// rotate_half pair, modeling_qwen2.py:116-120,141-145).
+// grid (ceil(heads * (d/16) / 256), T); thread = (head, chunk of 8 rotary pairs): it owns dims [8j, 8j+8) and the
+// matching dims of the upper half (the rotate_half pair, modeling_qwen2.py:116-120,141-145) -> every global access is a
+// 16-byte vector.  The d/16 threads of a head sit in one warp, so the Qwen3 per-head RMSNorm is a sub-warp shuffle.
+constexpr int kRopeThreads = 256;
+
 template <typename T>
-__global__ void qkv_rope_cache_kernel(const void* __restrict__ src, int src_is_partial, int S, const T* __restrict__ bias,
-                                      const int* __restrict__ positions, const T* __restrict__ cos_tab,
-                                      const T* __restrict__ sin_tab, const int* __restrict__ slot_map,
-                                      T* __restrict__ q_out, T* __restrict__ k_cache, T* __restrict__ v_cache,
-                                      T* __restrict__ k_out, T* __restrict__ v_out, long long t_total, int nh, int nkv,
-                                      int d, int page_size, const T* __restrict__ q_norm_w, const T* __restrict__ k_norm_w,
-                                      float norm_eps) {
+__global__ void __launch_bounds__(kRopeThreads)
+qkv_rope_cache_kernel(const void* __restrict__ src, int src_is_partial, int S, const T* __restrict__ bias,
+                      const int* __restrict__ positions, const T* __restrict__ cos_tab, const T* __restrict__ sin_tab,
+                      const int* __restrict__ slot_map, T* __restrict__ q_out, T* __restrict__ k_cache, T* __restrict__ v_cache,
+                      T* __restrict__ k_out, T* __restrict__ v_out, long long t_total, int nh, int nkv, int d, int page_size,
+                      const T* __restrict__ q_norm_w, const T* __restrict__ k_norm_w, float norm_eps) {
   pdl_trigger();
   pdl_wait();
   const int half = d >> 1;
-  const int hl = threadIdx.x / half;                    // head slot inside the block (kRopeHeadsPerBlock heads per CTA)
-  const int head = blockIdx.x * kRopeHeadsPerBlock + hl;
+  const int cph = half >> 3;                          // 8-pair chunks per head (8 for d = 128): power of two <= 32
+  const int item = blockIdx.x * kRopeThreads + threadIdx.x;
+  const int head = item / cph, j = item % cph;
   const long long t = blockIdx.y;
-  const int i = threadIdx.x % half;
-  const bool active = head < nh + 2 * nkv;
-  const long long width = (long long)(nh + 2 * nkv) * d;
-  const long long c0 = (long long)(active ? head : 0) * d + i, c1 = c0 + half;
-  float x0, x1;
+  const int heads = nh + 2 * nkv;
+  const bool active = head < heads;
+  const long long width = (long long)heads * d;
+  const long long c0 = (long long)(active ? head : 0) * d + j * 8, c1 = c0 + half;
+  float x0[8], x1[8];
   if (src_is_partial) {
     const float* p = reinterpret_cast<const float*>(src) + t * width;
     const long long stride = t_total * width;
-    x0 = p[c0]; x1 = p[c1];
-    for (int s = 1; s < S; ++s) { x0 += p[c0 + s * stride]; x1 += p[c1 + s * stride]; }
-    if (bias) { x0 += DT<T>::to_f(bias[c0]); x1 += DT<T>::to_f(bias[c1]); }
-    x0 = rnd<T>(x0); x1 = rnd<T>(x1);                 // nn.Linear output in the model dtype
+    float4 a = *reinterpret_cast<const float4*>(p + c0), b = *reinterpret_cast<const float4*>(p + c0 + 4);
+    float4 c = *reinterpret_cast<const float4*>(p + c1), e = *reinterpret_cast<const float4*>(p + c1 + 4);
+    for (int s = 1; s < S; ++s) {
+      const float* ps = p + s * stride;
+      const float4 a2 = *reinterpret_cast<const float4*>(ps + c0), b2 = *reinterpret_cast<const float4*>(ps + c0 + 4);
+      const float4 c2 = *reinterpret_cast<const float4*>(ps + c1), e2 = *reinterpret_cast<const float4*>(ps + c1 + 4);
+      a.x += a2.x; a.y += a2.y; a.z += a2.z; a.w += a2.w; b.x += b2.x; b.y += b2.y; b.z += b2.z; b.w += b2.w;
+      c.x += c2.x; c.y += c2.y; c.z += c2.z; c.w += c2.w; e.x += e2.x; e.y += e2.y; e.z += e2.z; e.w += e2.w;
+    }
+    x0[0] = a.x; x0[1] = a.y; x0[2] = a.z; x0[3] = a.w; x0[4] = b.x; x0[5] = b.y; x0[6] = b.z; x0[7] = b.w;
+    x1[0] = c.x; x1[1] = c.y; x1[2] = c.z; x1[3] = c.w; x1[4] = e.x; x1[5] = e.y; x1[6] = e.z; x1[7] = e.w;
+    if (bias) {
+      float b0[8], b1[8];
+      unpack8<T>(*reinterpret_cast<const uint4*>(bias + c0), b0);
+      unpack8<T>(*reinterpret_cast<const uint4*>(bias + c1), b1);
+#pragma unroll
+      for (int e2 = 0; e2 < 8; ++e2) { x0[e2] += b0[e2]; x1[e2] += b1[e2]; }
+    }
+#pragma unroll
+    for (int e2 = 0; e2 < 8; ++e2) { x0[e2] = rnd<T>(x0[e2]); x1[e2] = rnd<T>(x1[e2]); }   // nn.Linear output in the model dtype
   } else {
     const T* p = reinterpret_cast<const T*>(src) + t * width;
-    x0 = DT<T>::to_f(p[c0]); x1 = DT<T>::to_f(p[c1]);
+    unpack8<T>(*reinterpret_cast<const uint4*>(p + c0), x0);
+    unpack8<T>(*reinterpret_cast<const uint4*>(p + c1), x1);
   }
   const bool is_q = head < nh;
   const bool is_k = !is_q && head < nh + nkv;
-  if (q_norm_w != nullptr || k_norm_w != nullptr) {          // block-uniform (a CTA may hold q, k and v heads)
-    // Qwen3 per-head RMSNorm of q / k over head_dim before RoPE (transformers qwen3/modeling_qwen3.py q_norm/k_norm;
-    // vllm qwen3.py) -- same fp32-statistic / dtype rounding points as Qwen2RMSNorm
-    __shared__ float red[32];
-    float ss = active ? x0 * x0 + x1 * x1 : 0.f;
-    ss = warp_sum(ss);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-    __syncthreads();
-    float tot = 0.f;
-    const int wph = half >= 32 ? half / 32 : 1;        // warps per head (head_dim/2 is a multiple of 32 here)
-    for (int w = 0; w < wph; ++w) tot += red[hl * wph + w];
-    const float inv = 1.0f / sqrtf(tot / (float)d + norm_eps);
+  if (q_norm_w != nullptr || k_norm_w != nullptr) {
+    // Qwen3 per-head RMSNorm of q / k over head_dim before RoPE (transformers qwen3/modeling_qwen3.py q_norm/k_norm)
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ss += x0[e] * x0[e] + x1[e] * x1[e];
+    for (int o = cph >> 1; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);     // the cph lanes of this head
+    const float inv = 1.0f / sqrtf(ss / (float)d + norm_eps);
     const T* nw = is_q ? q_norm_w : (is_k ? k_norm_w : nullptr);
     if (active && nw != nullptr) {
-      x0 = rnd<T>(DT<T>::to_f(nw[i]) * rnd<T>(x0 * inv));
-      x1 = rnd<T>(DT<T>::to_f(nw[i + half]) * rnd<T>(x1 * inv));
+      float w0[8], w1[8];
+      unpack8<T>(*reinterpret_cast<const uint4*>(nw + j * 8), w0);
+      unpack8<T>(*reinterpret_cast<const uint4*>(nw + half + j * 8), w1);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { x0[e] = rnd<T>(w0[e] * rnd<T>(x0[e] * inv)); x1[e] = rnd<T>(w1[e] * rnd<T>(x1[e] * inv)); }
     }
   }
   if (!active) return;
   if (is_q || is_k) {
     const int pos = positions[t];
     // cos/sin are [max_pos, d/2]: emb = cat(freqs, freqs) (:110) makes both halves share the same angle
-    const float c = DT<T>::to_f(cos_tab[(long long)pos * half + i]);
-    const float s = DT<T>::to_f(sin_tab[(long long)pos * half + i]);
-    // q_embed = (q * cos) + (rotate_half(q) * sin), every product and the sum rounded to dtype (:144)
-    const float r0 = rnd<T>(rnd<T>(x0 * c) + rnd<T>(-x1 * s));
-    const float r1 = rnd<T>(rnd<T>(x1 * c) + rnd<T>(x0 * s));
-    x0 = r0; x1 = r1;
+    float cs[8], sn[8];
+    unpack8<T>(*reinterpret_cast<const uint4*>(cos_tab + (long long)pos * half + j * 8), cs);
+    unpack8<T>(*reinterpret_cast<const uint4*>(sin_tab + (long long)pos * half + j * 8), sn);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      // q_embed = (q * cos) + (rotate_half(q) * sin), every product and the sum rounded to dtype (:144)
+      const float r0 = rnd<T>(rnd<T>(x0[e] * cs[e]) + rnd<T>(-x1[e] * sn[e]));
+      const float r1 = rnd<T>(rnd<T>(x1[e] * cs[e]) + rnd<T>(x0[e] * sn[e]));
+      x0[e] = r0; x1[e] = r1;
+    }
   }
+  const uint4 lo = pack8<T>(x0), hi = pack8<T>(x1);
   if (is_q) {
-    T* o = q_out + t * (long long)nh * d + (long long)head * d;
-    o[i] = DT<T>::from_f(x0);
-    o[i + half] = DT<T>::from_f(x1);
+    T* o = q_out + t * (long long)nh * d + (long long)head * d + j * 8;
+    *reinterpret_cast<uint4*>(o) = lo;
+    *reinterpret_cast<uint4*>(o + half) = hi;
     return;
   }
   const int kvh = is_k ? head - nh : head - nh - nkv;
   T* lin = is_k ? k_out : v_out;
   if (lin) {
-    T* o = lin + t * (long long)nkv * d + (long long)kvh * d;
-    o[i] = DT<T>::from_f(x0);
-    o[i + half] = DT<T>::from_f(x1);
+    T* o = lin + t * (long long)nkv * d + (long long)kvh * d + j * 8;
+    *reinterpret_cast<uint4*>(o) = lo;
+    *reinterpret_cast<uint4*>(o + half) = hi;
   }
   T* cache = is_k ? k_cache : v_cache;
   if (cache && slot_map) {
     const int slot = slot_map[t];
     if (slot >= 0) {
       const long long page = slot / page_size, off = slot % page_size;
-      T* o = cache + ((page * nkv + kvh) * page_size + off) * d;     // [num_pages, nkv, page_size, d]
-      o[i] = DT<T>::from_f(x0);
-      o[i + half] = DT<T>::from_f(x1);
+      T* o = cache + ((page * nkv + kvh) * page_size + off) * d + j * 8;     // [num_pages, nkv, page_size, d]
+      *reinterpret_cast<uint4*>(o) = lo;
+      *reinterpret_cast<uint4*>(o + half) = hi;
     }
   }
 }
@@ -454,23 +480,29 @@ extern "C" int cts_reduce_residual_rmsnorm(cts_ctx* ctx, const float* partial, i
                                                 (cudaStream_t)stream, C, partial, split_k, (const T*)resid_in, (T*)resid_out,
                                                 (const T*)norm_w, eps, (T*)norm_out, t, (int)h)));
   } else {
-    DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_residual_rmsnorm_kernel<T>, dim3((unsigned)t), dim3(kNormThreads), 0,
-                                                (cudaStream_t)stream, 1, partial, split_k, (const T*)resid_in, (T*)resid_out,
-                                                (const T*)norm_w, eps, (T*)norm_out, t, (int)h)));
+    const int nv = (int)cdiv_ll(h / 8, kNormThreads);
+#define NORM_LAUNCH(NVV)                                                                                                      \
+    DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_residual_rmsnorm_kernel<T, NVV>, dim3((unsigned)t), dim3(kNormThreads), 0, \
+                                                (cudaStream_t)stream, 1, partial, split_k, (const T*)resid_in, (T*)resid_out,  \
+                                                (const T*)norm_w, eps, (T*)norm_out, t, (int)h)))
+    if (nv <= 1) { NORM_LAUNCH(1); } else if (nv <= 2) { NORM_LAUNCH(2); } else if (nv <= 3) { NORM_LAUNCH(3); }
+    else if (nv <= 4) { NORM_LAUNCH(4); } else { NORM_LAUNCH(8); }
+#undef NORM_LAUNCH
   }
   return CTS_OK;
 }
 
 extern "C" int cts_reduce_swiglu(cts_ctx* ctx, const float* partial, int split_k, long long t, long long inter, void* out,
-                                 int dtype, void* stream) {
+                                 int interleaved, int dtype, void* stream) {
   if (!ctx) return CTS_ERR_BAD_ARG;
   CTS_CHECK_ARG(ctx, partial && out && split_k >= 1 && inter > 0, "args");
+  CTS_CHECK_ARG(ctx, !interleaved || inter % 64 == 0, "interleaved gate/up layout needs inter % 64 == 0");
   CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
   CTS_CHECK_ARG(ctx, t <= 65535, "t > 65535");
   if (t == 0) return CTS_OK;
   dim3 grid((unsigned)cdiv_ll(inter, 256), (unsigned)t);
   DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_swiglu_kernel<T>, grid, dim3(256), 0, (cudaStream_t)stream, 1, partial, split_k, t,
-                                              inter, (T*)out)));
+                                              inter, (T*)out, interleaved)));
   return CTS_OK;
 }
 
@@ -489,11 +521,12 @@ extern "C" int cts_qkv_rope_cache(cts_ctx* ctx, const void* src, int src_is_part
   if (t == 0) return CTS_OK;
   // t can exceed 65535 in a big prefill: fold into chunks of the y grid dimension
   const long long width = (long long)(nh + 2 * nkv) * head_dim;
-  CTS_CHECK_ARG(ctx, (head_dim / 2) % 32 == 0 || (q_norm_w == nullptr && k_norm_w == nullptr), "q/k norm needs head_dim % 64 == 0");
-  const int threads = kRopeHeadsPerBlock * (head_dim / 2);
+  CTS_CHECK_ARG(ctx, head_dim % 16 == 0 && ((head_dim / 16) & (head_dim / 16 - 1)) == 0 && head_dim / 16 <= 32,
+                "head_dim must be 16 * 2^n (<= 512)");
+  const int threads = kRopeThreads;
   for (long long tb = 0; tb < t; tb += 65535) {
     const long long tc = (t - tb) < 65535 ? (t - tb) : 65535;
-    dim3 grid((unsigned)((nh + 2 * nkv + kRopeHeadsPerBlock - 1) / kRopeHeadsPerBlock), (unsigned)tc);
+    dim3 grid((unsigned)cdiv_ll((long long)(nh + 2 * nkv) * (head_dim / 16), kRopeThreads), (unsigned)tc);
     if (src_is_partial) {
       CTS_CHECK_ARG(ctx, t <= 65535, "partial input with t > 65535");
     }

@@ -311,6 +311,211 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   if (warp == 1) tmem_dealloc<kCols>(tmem_base);
 }
 
+// =================================================================================================================
+// Persistent variant for big token counts (prefill): one CTA per SM walks the output tiles (128 features x 256 tokens),
+// the TMA/MMA ring runs continuously across tiles and the accumulator is DOUBLE-BUFFERED in TMEM (2 x 256 columns), so
+// the epilogue of tile i (TMEM -> registers -> shared -> TMA store, residual tile by TMA load) overlaps the mainloop of
+// tile i+1.  Epilogues: NONE / GELU / RESIDUAL, and SWIGLU_IL for gate_up weights stored INTERLEAVED (each 128-row weight
+// tile = 64 gate rows then the 64 matching up rows), which makes SwiGLU tile-local: the "up" warps hand their values to
+// the "gate" warps through shared memory and the tile emits 64 output features.
+// =================================================================================================================
+constexpr int kPBN = 256;
+constexpr int kPStages = 3;
+constexpr int kPStageBytes = kBM * kBK * 2 + kPBN * kBK * 2;     // 48 KiB
+constexpr int kPChunk = 128;                                      // tokens per epilogue chunk
+constexpr int kPOutBytes = kPChunk * kBM * 2;                     // 32 KiB staging tile
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                          const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
+                          const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kPStages], empty_bar[kPStages], tmem_full[2], tmem_empty[2], res_bar;
+  __shared__ uint32_t tmem_slot;
+  constexpr bool kIsBf16 = std::is_same<T, __nv_bfloat16>::value;
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* out_s = smem + kPStages * kPStageBytes;
+  uint8_t* res_s = out_s + kPOutBytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (int)((p.n + kBM - 1) / kBM), tiles_n = (int)((p.t + kPBN - 1) / kPBN);
+  const int total_tiles = tiles_m * tiles_n;
+  const int nkb = p.kb_total;
+  const int epi = p.epilogue;
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_out);
+    for (int s = 0; s < kPStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+    mbar_init(&res_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      pdl_wait();
+      uint32_t it = 0;                                   // global K-block counter across this CTA's tiles
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int f0 = (tile % tiles_m) * kBM, t0 = (tile / tiles_m) * kPBN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kPStages;
+          mbar_wait(&empty_bar[s], ((it / kPStages) & 1u) ^ 1u);
+          mbar_expect_tx(&full_bar[s], (uint32_t)kPStageBytes);
+          uint8_t* st = smem + (size_t)s * kPStageBytes;
+          tma_load_2d(st, &tm_w, &full_bar[s], kb * kBK, f0, CTS_L2_EVICT_NORMAL);
+          tma_load_2d(st + kBM * kBK * 2, &tm_x, &full_bar[s], kb * kBK, t0, CTS_L2_EVICT_NORMAL);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kIsBf16 ? 1 : 0, kPBN, kBM);
+      uint32_t it = 0, lt = 0;                           // K-block counter, local tile counter
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1u;
+        mbar_wait(&tmem_empty[buf], ((lt >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % kPStages;
+          mbar_wait(&full_bar[s], (it / kPStages) & 1u);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)s * kPStageBytes);
+          const uint64_t a_desc = umma_desc_k_sw128(a_addr), b_desc = umma_desc_k_sw128(a_addr + kBM * kBK * 2);
+#pragma unroll
+          for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * ((kUmmaK * 2) >> 4));
+            umma_f16(tmem_base + buf * kPBN, a_desc + adv, b_desc + adv, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue warps ------------------------------
+    pdl_wait();
+    const int q = warp & 3;
+    const int ft = q * 32 + lane;                         // row of the weight tile == TMEM lane
+    uint32_t lt = 0, res_uses = 0;
+    T* outp = reinterpret_cast<T*>(out_s);
+    T* resp = reinterpret_cast<T*>(res_s);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const int f0 = (tile % tiles_m) * kBM, t0 = (tile / tiles_m) * kPBN;
+      const uint32_t buf = lt & 1u;
+      const long long f = (long long)f0 + ft;
+      float bias = 0.f;
+      if (p.bias != nullptr && f < p.n) bias = DT<T>::to_f(reinterpret_cast<const T*>(p.bias)[f]);
+      mbar_wait(&tmem_full[buf], (lt >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t lane_addr = tmem_base + buf * kPBN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < kPBN / kPChunk; ++ch) {
+        const int tc0 = t0 + ch * kPChunk;
+        const bool chunk_live = tc0 < p.t;                // CTA-uniform
+        if (epi == CTS_EPI_RESIDUAL && chunk_live) {
+          if (threadIdx.x == 64) {
+            mbar_expect_tx(&res_bar, (uint32_t)kPOutBytes);
+            tma_load_2d_nohint(res_s, &tm_res, &res_bar, f0, tc0);
+          }
+          mbar_wait(&res_bar, res_uses & 1u);
+          ++res_uses;
+        }
+#pragma unroll 1
+        for (int c = 0; c < kPChunk; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(lane_addr + (uint32_t)(ch * kPChunk + c), v);
+          tmem_ld_wait();
+          if (!chunk_live) continue;
+          if (epi == CTS_EPI_SWIGLU_IL) {
+            if (ft >= 64) {                               // "up" rows: publish dtype(u) for the gate warps
+#pragma unroll
+              for (int j = 0; j < 16; ++j) resp[(c + j) * 64 + (ft - 64)] = DT<T>::from_f(__uint_as_float(v[j]));
+            }
+            named_bar_sync(2, 128);
+            if (ft < 64) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float g = rnd<T>(__uint_as_float(v[j]));
+                const float u = DT<T>::to_f(resp[(c + j) * 64 + ft]);
+                outp[(c + j) * 64 + ft] = DT<T>::from_f(rnd<T>(silu_f(g)) * u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float r = __uint_as_float(v[j]) + bias;
+              if (epi == CTS_EPI_GELU) r = gelu_erf(rnd<T>(r));
+              else if (epi == CTS_EPI_RESIDUAL) r = rnd<T>(r) + DT<T>::to_f(resp[(c + j) * kBM + ft]);
+              outp[(c + j) * kBM + ft] = DT<T>::from_f(r);
+            }
+          }
+        }
+        if (ch == kPBN / kPChunk - 1) {                   // last TMEM read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+        if (chunk_live) {
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (threadIdx.x == 64) {
+            if (epi == CTS_EPI_SWIGLU_IL) tma_store_2d(&tm_out, out_s, f0 / 2, tc0);
+            else tma_store_2d(&tm_out, out_s, f0, tc0);
+            tma_store_commit();
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // staging tile may be rewritten
+          }
+          named_bar_sync(1, 128);
+        }
+      }
+    }
+    if (threadIdx.x == 64) tma_store_wait_read0();        // all stores fully performed before the CTA retires
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+template <typename T>
+int launch_persistent(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
+  const bool is_bf16 = a->dtype == CTS_BF16;
+  const bool il = a->epilogue == CTS_EPI_SWIGLU_IL;
+  CUtensorMap tm_w, tm_x, tm_out, tm_res;
+  int rc = cts_make_tmap_2d(ctx, &tm_w, a->w, a->n, a->k, a->w_ld, kBM, is_bf16);
+  if (rc) return rc;
+  rc = cts_make_tmap_2d(ctx, &tm_x, a->x, a->t, a->k, a->x_ld, kPBN, is_bf16);
+  if (rc) return rc;
+  rc = cts_make_tmap_2d_dense(ctx, &tm_out, a->out, a->t, il ? a->n / 2 : a->n, a->out_ld, kPChunk, il ? 64 : kBM, is_bf16);
+  if (rc) return rc;
+  tm_res = tm_out;
+  if (a->epilogue == CTS_EPI_RESIDUAL) {
+    rc = cts_make_tmap_2d_dense(ctx, &tm_res, a->residual, a->t, a->n, a->out_ld, kPChunk, kBM, is_bf16);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = a->n; p.k = a->k; p.t = a->t; p.out_ld = a->out_ld;
+  p.bias = a->bias; p.residual = a->residual; p.out = a->out;
+  p.kb_total = (int)cdiv_ll(a->k, kBK);
+  p.split_k = 1; p.epilogue = a->epilogue; p.stages = kPStages;
+  const size_t smem = (size_t)kPStages * kPStageBytes + 2 * kPOutBytes + 1024;
+  auto kern = gemm_tn_persistent_kernel<T>;
+  CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long tiles = cdiv_ll(a->n, kBM) * cdiv_ll(a->t, kPBN);
+  const unsigned grid = (unsigned)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  CTS_CUDA(ctx, launch_pdl(kern, dim3(grid), dim3(kThreads), smem, stream, 1, tm_w, tm_x, tm_out, tm_res, p));
+  return CTS_OK;
+}
+
 template <typename T, int BN, bool DUAL>
 int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   const bool is_bf16 = a->dtype == CTS_BF16;
@@ -387,7 +592,7 @@ extern "C" int cts_gemm(cts_ctx* ctx, const cts_gemm_args* a, void* stream) {
   CTS_CHECK_ARG(ctx, a->w && a->x && a->out, "null w/x/out");
   CTS_CHECK_ARG(ctx, a->n > 0 && a->k > 0 && a->t > 0, "n, k, t must be positive");
   CTS_CHECK_ARG(ctx, a->dtype == CTS_BF16 || a->dtype == CTS_F16, "dtype must be CTS_BF16 or CTS_F16");
-  CTS_CHECK_ARG(ctx, a->epilogue >= CTS_EPI_NONE && a->epilogue <= CTS_EPI_SPLITK_F32, "unknown epilogue");
+  CTS_CHECK_ARG(ctx, a->epilogue >= CTS_EPI_NONE && a->epilogue <= CTS_EPI_SWIGLU_IL, "unknown epilogue");
   CTS_CHECK_ARG(ctx, a->split_k >= 1, "split_k must be >= 1");
   CTS_CHECK_ARG(ctx, a->split_k == 1 || a->epilogue == CTS_EPI_PARTIAL_F32 || a->epilogue == CTS_EPI_SPLITK_F32,
                 "split_k > 1 needs CTS_EPI_PARTIAL_F32 or CTS_EPI_SPLITK_F32");
@@ -398,8 +603,19 @@ extern "C" int cts_gemm(cts_ctx* ctx, const cts_gemm_args* a, void* stream) {
   CTS_CHECK_ARG(ctx, (a->epilogue == CTS_EPI_SWIGLU) == (a->w2 != nullptr), "w2 is required by (and only by) CTS_EPI_SWIGLU");
   CTS_CHECK_ARG(ctx, a->epilogue != CTS_EPI_RESIDUAL || a->residual != nullptr, "CTS_EPI_RESIDUAL needs residual");
   CTS_CHECK_ARG(ctx, a->w_ld >= a->k && a->x_ld >= a->k, "leading dimension smaller than k");
-  CTS_CHECK_ARG(ctx, a->epilogue == CTS_EPI_PARTIAL_F32 || a->epilogue == CTS_EPI_SPLITK_F32 || a->out_ld >= a->n, "out_ld smaller than n");
+  CTS_CHECK_ARG(ctx, a->epilogue == CTS_EPI_PARTIAL_F32 || a->epilogue == CTS_EPI_SPLITK_F32 ||
+                         a->out_ld >= (a->epilogue == CTS_EPI_SWIGLU_IL ? a->n / 2 : a->n), "out_ld smaller than n");
   cudaStream_t st = (cudaStream_t)stream;
+  CTS_CHECK_ARG(ctx, a->epilogue != CTS_EPI_SWIGLU_IL || (a->n % 128 == 0 && a->t > 128 && a->row_map == nullptr),
+                "CTS_EPI_SWIGLU_IL needs n % 128 == 0, t > 128 and no row_map (small t: CTS_EPI_PARTIAL_F32 + cts_reduce_swiglu)");
+  const bool pers_epi = a->epilogue == CTS_EPI_NONE || a->epilogue == CTS_EPI_GELU || a->epilogue == CTS_EPI_RESIDUAL ||
+                        a->epilogue == CTS_EPI_SWIGLU_IL;
+  if (a->t > 128 && pers_epi && a->row_map == nullptr && a->split_k == 1 && (a->out_ld * 2) % 16 == 0 &&
+      ((uintptr_t)a->out & 15) == 0 && (a->epilogue != CTS_EPI_RESIDUAL || ((uintptr_t)a->residual & 15) == 0) &&
+      !ctx->no_persistent_gemm) {
+    return a->dtype == CTS_BF16 ? launch_persistent<__nv_bfloat16>(ctx, a, st) : launch_persistent<__half>(ctx, a, st);
+  }
+  CTS_CHECK_ARG(ctx, a->epilogue != CTS_EPI_SWIGLU_IL, "CTS_EPI_SWIGLU_IL is only implemented by the persistent kernel");
   const bool dual = a->epilogue == CTS_EPI_SWIGLU;
   if (a->dtype == CTS_BF16)
     return dual ? dispatch_bn<__nv_bfloat16, true>(ctx, a, st) : dispatch_bn<__nv_bfloat16, false>(ctx, a, st);

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _cabi, layout
-from ._cabi import EPI_NONE, EPI_PARTIAL_F32, EPI_RESIDUAL, EPI_SWIGLU
+from ._cabi import EPI_NONE, EPI_PARTIAL_F32, EPI_RESIDUAL, EPI_SWIGLU_IL
 from .config import ChatTSConfig
 from .ts_encoder import TimeSeriesEmbedding
 from .weights import load_checkpoint, shard_tensor, synthetic_state_dict
@@ -124,7 +124,12 @@ class ChatTSForCausalLM:
             self.qn.append(take(p + "self_attn.q_norm.weight") if has_qkn else None)
             self.kn.append(take(p + "self_attn.k_norm.weight") if has_qkn else None)
             self.wo.append(take(p + "self_attn.o_proj.weight"))
-            self.wgu.append(torch.cat([take(p + "mlp.gate_proj.weight"), take(p + "mlp.up_proj.weight")], 0).contiguous())
+            # gate/up INTERLEAVED per 128-row tile (64 gate rows, then the 64 matching up rows): SwiGLU becomes local to
+            # one MMA tile (CTS_EPI_SWIGLU_IL in the persistent prefill GEMM; cts_reduce_swiglu(interleaved) at decode)
+            g, u = take(p + "mlp.gate_proj.weight"), take(p + "mlp.up_proj.weight")
+            assert g.shape[0] % 64 == 0, "intermediate_size (per rank) must be a multiple of 64"
+            self.wgu.append(torch.stack([g.view(-1, 64, g.shape[1]), u.view(-1, 64, u.shape[1])], 1).reshape(2 * g.shape[0], g.shape[1]).contiguous())
+            del g, u
             self.wd.append(take(p + "mlp.down_proj.weight"))
         ts_w = {k: v for k, v in sd.items() if k.startswith("ts_encoder.")}
         self.ts_encoder = TimeSeriesEmbedding(cfg.ts, ts_w, device=dev, dtype=dt) if ts_w else None
@@ -160,7 +165,7 @@ class ChatTSForCausalLM:
 
     def _ws_floats(self, T, sp):
         return max(sp["qkv"] * T * self.wqkv[0].shape[0] if sp["qkv"] > 1 else 0, sp["o"] * T * self.H if sp["o"] > 1 else 0,
-                   sp["gu"] * T * 2 * self.I if sp["gu"] > 1 else 0, sp["d"] * T * self.H if sp["d"] > 1 else 0, 1)
+                   sp["gu"] * T * 2 * self.I if T <= 128 else 0, sp["d"] * T * self.H if sp["d"] > 1 else 0, 1)
 
     def _all_reduce_hidden(self, st, T):
         """Row-parallel outputs (o_proj, down_proj) need the sum over tensor-parallel ranks before the residual add."""
@@ -193,11 +198,11 @@ class ChatTSForCausalLM:
                 c.gemm(st.ao, self.wo[l], st.h, residual=st.h, epilogue=EPI_RESIDUAL, t=T)
                 c.reduce_residual_rmsnorm(None, 0, st.h, None, self.ln2[l], eps, st.xn, t=T)
             # ---- gate/up + SwiGLU
-            if sp["gu"] > 1:
-                c.gemm(st.xn, self.wgu[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["gu"], t=T)
-                c.reduce_swiglu(st.ws, sp["gu"], T, I, st.act)
+            if T > 128:
+                c.gemm(st.xn, self.wgu[l], st.act, epilogue=EPI_SWIGLU_IL, t=T)          # persistent, SwiGLU fused in the tile
             else:
-                c.gemm(st.xn, self.wgu[l][:I], st.act, w2=self.wgu[l][I:], epilogue=EPI_SWIGLU, t=T)
+                c.gemm(st.xn, self.wgu[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["gu"], t=T)
+                c.reduce_swiglu(st.ws, sp["gu"], T, I, st.act, interleaved=True)
             # ---- down_proj + residual + next layer's input RMSNorm (or the final norm)
             nw = self.ln1[l + 1] if l + 1 < self.L else self.final_norm
             if self.tp_size > 1:

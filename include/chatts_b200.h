@@ -78,6 +78,8 @@ int cts_ts_patchify(cts_ctx* ctx, const void* x, int dtype, int n_series, int ro
 #define CTS_EPI_SWIGLU 2      /* out = dtype(silu(dtype(acc_w)) * dtype(acc_w2))  modeling_qwen2.py:47 */
 #define CTS_EPI_PARTIAL_F32 3 /* out_f32[split][t][n] = acc   (split-K; reduced by a cts_reduce_* call) */
 #define CTS_EPI_RESIDUAL 4    /* out = dtype(residual + dtype(acc + bias))     modeling_qwen2.py:302,308 */
+#define CTS_EPI_SWIGLU_IL 6   /* gate_up weights INTERLEAVED per 128-row tile (64 gate rows, then the 64 matching up rows):
+                                 out[t][i] = dtype(silu(dtype(gate_i)) * dtype(up_i)), out has n/2 columns; t > 128 only */
 #define CTS_EPI_SPLITK_F32 5  /* out_f32[t][n] = acc summed over the splits INSIDE the kernel: each split writes its partial to
                                  splitk_ws, the last split of a tile to arrive (tile_counters) adds them in split order */
 
@@ -119,9 +121,10 @@ int cts_reduce_residual_rmsnorm(cts_ctx* ctx, const float* partial, int split_k,
                                 void* resid_out, const void* norm_w, float eps, void* norm_out, long long t,
                                 long long h, int dtype, void* stream);
 
-/* out[t][i] = dtype(silu(dtype(sum_s p[s][t][i])) * dtype(sum_s p[s][t][inter+i]))   (modeling_qwen2.py:47) */
+/* out[t][i] = dtype(silu(dtype(sum_s p[s][t][g(i)])) * dtype(sum_s p[s][t][u(i)]))   (modeling_qwen2.py:47)
+ * stacked layout: g(i) = i, u(i) = inter + i;  interleaved (CTS_EPI_SWIGLU_IL weights): g(i) = (i/64)*128 + i%64, u = g + 64 */
 int cts_reduce_swiglu(cts_ctx* ctx, const float* partial, int split_k, long long t, long long inter, void* out,
-                      int dtype, void* stream);
+                      int interleaved, int dtype, void* stream);
 
 /* q/k/v = dtype(sum_s partial + bias); RoPE(q,k) with the fp32-computed cos/sin tables cast to dtype
  * (modeling_qwen2.py:107-146,217-222); q -> q_out [t, nh*d]; k,v -> paged KV cache slot slot_map[t]

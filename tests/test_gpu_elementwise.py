@@ -39,7 +39,7 @@ def test_reduce_swiglu():
     t, inter, s = 6, 200, 3
     part = torch.randn(s, t, 2 * inter)
     out = torch.empty(t, inter, device="cuda", dtype=DT)
-    c.reduce_swiglu(part.cuda(), s, t, inter, out)
+    c.reduce_swiglu(part.cuda(), s, t, inter, out, interleaved=False)
     tot = part.sum(0)
     g, u = tot[:, :inter].to(DT), tot[:, inter:].to(DT)
     ref = (torch.nn.functional.silu(g.float()).to(DT).float() * u.float()).to(DT)

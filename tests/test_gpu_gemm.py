@@ -129,3 +129,52 @@ def test_gemm_bad_args_report_errors():
     with pytest.raises(CtsError):
         c.gemm(torch.zeros(4, 64, device="cuda", dtype=torch.bfloat16), torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16),
                out, split_k=2)            # split-K without the partial epilogue
+
+
+@pytest.mark.parametrize("t,inter,k", [(129, 128, 128), (300, 704, 256), (1000, 1408, 512), (2048, 256, 1024)])
+def test_persistent_swiglu_interleaved(t, inter, k):
+    """Persistent double-buffered kernel + tile-local SwiGLU on interleaved gate/up weights (CTS_EPI_SWIGLU_IL), and the
+    decode-side cts_reduce_swiglu(interleaved) on the same weights."""
+    c = ctx()
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(t + inter)
+    x = (torch.randn(t, k, generator=g) * 0.5).to(dtype)
+    wg = (torch.randn(inter, k, generator=g) * 0.1).to(dtype)
+    wu = (torch.randn(inter, k, generator=g) * 0.1).to(dtype)
+    wil = torch.stack([wg.view(-1, 64, k), wu.view(-1, 64, k)], 1).reshape(2 * inter, k).contiguous()
+    gg = (x.float() @ wg.float().T).to(dtype)
+    uu = (x.float() @ wu.float().T).to(dtype)
+    ref = (torch.nn.functional.silu(gg.float()).to(dtype).float() * uu.float()).to(dtype)
+    out = torch.full((t, inter), float("nan"), device="cuda", dtype=dtype)
+    c.gemm(x.cuda(), wil.cuda(), out, epilogue=6)
+    torch.cuda.synchronize()
+    e = rel_err(out, ref)
+    record("gemm_persistent_swiglu_il", t=t, inter=inter, k=k, err=e)
+    assert torch.isfinite(out.float()).all() and e < 8e-3
+    # decode-style: split-K partials + interleaved reduce on a few rows
+    tt, s = min(t, 8), 2
+    part = torch.empty(s, tt, 2 * inter, device="cuda", dtype=torch.float32)
+    c.gemm(x[:tt].cuda().contiguous(), wil.cuda(), part, epilogue=EPI_PARTIAL, split_k=s)
+    out2 = torch.empty(tt, inter, device="cuda", dtype=dtype)
+    c.reduce_swiglu(part, s, tt, inter, out2, interleaved=True)
+    torch.cuda.synchronize()
+    assert rel_err(out2, ref[:tt]) < 8e-3
+
+
+@pytest.mark.parametrize("t,n,k", [(257, 384, 640), (1024, 5120, 512), (700, 200, 136)])
+def test_persistent_bias_gelu_residual(t, n, k):
+    c = ctx()
+    dtype = torch.bfloat16
+    x, w, b = _mk(t, n, k, dtype, 7)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    lin = x.float() @ w.float().T + b.float()
+    out = torch.full((t, n), float("nan"), device="cuda", dtype=dtype)
+    c.gemm(xd, wd, out, bias=bd, epilogue=EPI_GELU)
+    assert rel_err(out, torch.nn.functional.gelu(lin.to(dtype).float()).to(dtype)) < 8e-3
+    res = (torch.randn(t, n) * 0.3).to(dtype)
+    h = res.cuda().clone()
+    c.gemm(xd, wd, h, bias=bd, residual=h, epilogue=EPI_RESIDUAL)          # in place
+    torch.cuda.synchronize()
+    e = rel_err(h, (res.float() + lin.to(dtype).float()).to(dtype))
+    record("gemm_persistent_residual", t=t, n=n, k=k, err=e)
+    assert e < 8e-3
