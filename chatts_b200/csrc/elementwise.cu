@@ -243,7 +243,7 @@ qkv_rope_cache_kernel(const void* __restrict__ src, int src_is_partial, int S, c
   pdl_wait();
   const int half = d >> 1;
   const int cph = half >> 3;                          // 8-pair chunks per head (8 for d = 128): power of two <= 32
-  const int item = blockIdx.x * kRopeThreads + threadIdx.x;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
   const int head = item / cph, j = item % cph;
   const long long t = blockIdx.y;
   const int heads = nh + 2 * nkv;
@@ -523,10 +523,10 @@ extern "C" int cts_qkv_rope_cache(cts_ctx* ctx, const void* src, int src_is_part
   const long long width = (long long)(nh + 2 * nkv) * head_dim;
   CTS_CHECK_ARG(ctx, head_dim % 16 == 0 && ((head_dim / 16) & (head_dim / 16 - 1)) == 0 && head_dim / 16 <= 32,
                 "head_dim must be 16 * 2^n (<= 512)");
-  const int threads = kRopeThreads;
+  const int threads = t <= 64 ? 64 : kRopeThreads;      // decode: more, smaller CTAs pull the split-K partials from L2
   for (long long tb = 0; tb < t; tb += 65535) {
     const long long tc = (t - tb) < 65535 ? (t - tb) : 65535;
-    dim3 grid((unsigned)cdiv_ll((long long)(nh + 2 * nkv) * (head_dim / 16), kRopeThreads), (unsigned)tc);
+    dim3 grid((unsigned)cdiv_ll((long long)(nh + 2 * nkv) * (head_dim / 16), threads), (unsigned)tc);
     if (src_is_partial) {
       CTS_CHECK_ARG(ctx, t <= 65535, "partial input with t > 65535");
     }
