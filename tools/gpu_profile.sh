@@ -6,7 +6,7 @@ KREG='regex:gemm_tn|attn_|reduce_|qkv_rope|embed_gather|greedy|ts_|peer_'
 B=${PROFILE_BATCH:-32}
 BENCH="python bench.py --steps 2 --warmup 3 --batch $B --only-batch --no-cpu-baseline --no-graph --sweep-only"
 echo "=== launch list (one eager decode step)"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s ${LIST_SKIP:-560} -c ${LIST_COUNT:-450} --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s ${LIST_SKIP:-440} -c ${LIST_COUNT:-450} --csv \
    --log-file gpurun_out/launches_b$B.csv $BENCH > gpurun_out/ncu_launch_b$B.log 2>&1
 echo "rc=$?"; wc -l gpurun_out/launches_b$B.csv
 echo "=== full set: decode GEMMs"
@@ -20,5 +20,9 @@ echo "rc=$?"
 echo "=== full set: decode attention"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_decode_kernel -s 10 -c 2 \
    -o gpurun_out/prof_attn_b$B -f $BENCH > gpurun_out/ncu_attn_b$B.log 2>&1
+echo "rc=$?"
+echo "=== full set: prefill attention (tcgen05)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_prefill -s 4 -c 2 \
+   -o gpurun_out/prof_attn_prefill_b$B -f $BENCH > gpurun_out/ncu_attn_prefill_b$B.log 2>&1
 echo "rc=$?"
 ls -la gpurun_out/ | grep -E "ncu-rep|csv"
