@@ -344,6 +344,18 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid
   const int total_tiles = tiles_m * tiles_n;
   const int nkb = p.kb_total;
   const int epi = p.epilogue;
+  // L2-aware rasterisation: the feature tiles are walked in groups of `gm` whose weights (gm x 128 x K) fit in L2; inside
+  // a group the token tiles advance slowly and the gm feature tiles fast, so the ~148 tiles in flight share a few token
+  // tiles and the group's weights stay L2-resident across all token tiles.  DRAM then sees the weights once and the
+  // activations once per group (instead of the weights once per token tile: 20 GB per gate_up launch before).
+  const int gm = p.l2_prefetch > 0 ? p.l2_prefetch : tiles_m;
+  auto tile_coords = [&](int id, int& m_blk, int& n_blk) {
+    const int per_group = gm * tiles_n;
+    const int g = id / per_group, r = id - g * per_group;
+    const int gm_here = min(gm, tiles_m - g * gm);
+    n_blk = r / gm_here;
+    m_blk = g * gm + (r - n_blk * gm_here);
+  };
 
   pdl_trigger();
   if (threadIdx.x == 0) {
@@ -365,7 +377,9 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid
       pdl_wait();
       uint32_t it = 0;                                   // global K-block counter across this CTA's tiles
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int f0 = (tile % tiles_m) * kBM, t0 = (tile / tiles_m) * kPBN;
+        int mb, nb;
+        tile_coords(tile, mb, nb);
+        const int f0 = mb * kBM, t0 = nb * kPBN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % kPStages;
           mbar_wait(&empty_bar[s], ((it / kPStages) & 1u) ^ 1u);
@@ -410,7 +424,9 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid
     T* outp = reinterpret_cast<T*>(out_s);
     T* resp = reinterpret_cast<T*>(res_s);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-      const int f0 = (tile % tiles_m) * kBM, t0 = (tile / tiles_m) * kPBN;
+      int mb, nb;
+      tile_coords(tile, mb, nb);
+      const int f0 = mb * kBM, t0 = nb * kPBN;
       const uint32_t buf = lt & 1u;
       const long long f = (long long)f0 + ft;
       float bias = 0.f;
@@ -507,6 +523,15 @@ int launch_persistent(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream)
   p.bias = a->bias; p.residual = a->residual; p.out = a->out;
   p.kb_total = (int)cdiv_ll(a->k, kBK);
   p.split_k = 1; p.epilogue = a->epilogue; p.stages = kPStages;
+  {
+    // feature tiles per L2 group: keep the group's weights within ~48 MB, balanced over the groups
+    const long long tiles_m = cdiv_ll(a->n, kBM);
+    long long gmax = (48LL << 20) / ((long long)kBM * a->k * 2);
+    if (gmax < 1) gmax = 1;
+    const long long groups = cdiv_ll(tiles_m, gmax);
+    p.l2_prefetch = (int)cdiv_ll(tiles_m, groups);       // field reused as "group_m" by the persistent kernel
+    if (ctx->l2_prefetch_mb < 0) p.l2_prefetch = 0;      // CTS_L2_PREFETCH_MB=-1: plain feature-fastest order (A/B testing)
+  }
   const size_t smem = (size_t)kPStages * kPStageBytes + 2 * kPOutBytes + 1024;
   auto kern = gemm_tn_persistent_kernel<T>;
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
