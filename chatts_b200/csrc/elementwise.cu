@@ -227,6 +227,96 @@ __global__ void reduce_swiglu_kernel(const float* __restrict__ part, int S, long
 }
 
 // ------------------------------------------------------------------------------------------------
+constexpr int kRopeHeadsPerBlock = 4;
+// Scalar variant, used for split-K partial input (decode): many small CTAs pull the fp32 partials from L2 in parallel.
+// grid (ceil((nh + 2*nkv) / 4), T); block = 4 x head_dim/2 threads: thread i of a head owns dims i and i + d/2 (the
+// rotate_half pair, modeling_qwen2.py:116-120,141-145).
+template <typename T>
+__global__ void qkv_rope_cache_scalar_kernel(const void* __restrict__ src, int src_is_partial, int S, const T* __restrict__ bias,
+                                      const int* __restrict__ positions, const T* __restrict__ cos_tab,
+                                      const T* __restrict__ sin_tab, const int* __restrict__ slot_map,
+                                      T* __restrict__ q_out, T* __restrict__ k_cache, T* __restrict__ v_cache,
+                                      T* __restrict__ k_out, T* __restrict__ v_out, long long t_total, int nh, int nkv,
+                                      int d, int page_size, const T* __restrict__ q_norm_w, const T* __restrict__ k_norm_w,
+                                      float norm_eps) {
+  pdl_trigger();
+  pdl_wait();
+  const int half = d >> 1;
+  const int hl = threadIdx.x / half;                    // head slot inside the block (kRopeHeadsPerBlock heads per CTA)
+  const int head = blockIdx.x * kRopeHeadsPerBlock + hl;
+  const long long t = blockIdx.y;
+  const int i = threadIdx.x % half;
+  const bool active = head < nh + 2 * nkv;
+  const long long width = (long long)(nh + 2 * nkv) * d;
+  const long long c0 = (long long)(active ? head : 0) * d + i, c1 = c0 + half;
+  float x0, x1;
+  if (src_is_partial) {
+    const float* p = reinterpret_cast<const float*>(src) + t * width;
+    const long long stride = t_total * width;
+    x0 = p[c0]; x1 = p[c1];
+    for (int s = 1; s < S; ++s) { x0 += p[c0 + s * stride]; x1 += p[c1 + s * stride]; }
+    if (bias) { x0 += DT<T>::to_f(bias[c0]); x1 += DT<T>::to_f(bias[c1]); }
+    x0 = rnd<T>(x0); x1 = rnd<T>(x1);                 // nn.Linear output in the model dtype
+  } else {
+    const T* p = reinterpret_cast<const T*>(src) + t * width;
+    x0 = DT<T>::to_f(p[c0]); x1 = DT<T>::to_f(p[c1]);
+  }
+  const bool is_q = head < nh;
+  const bool is_k = !is_q && head < nh + nkv;
+  if (q_norm_w != nullptr || k_norm_w != nullptr) {          // block-uniform (a CTA may hold q, k and v heads)
+    // Qwen3 per-head RMSNorm of q / k over head_dim before RoPE (transformers qwen3/modeling_qwen3.py q_norm/k_norm;
+    // vllm qwen3.py) -- same fp32-statistic / dtype rounding points as Qwen2RMSNorm
+    __shared__ float red[32];
+    float ss = active ? x0 * x0 + x1 * x1 : 0.f;
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    const int wph = half >= 32 ? half / 32 : 1;        // warps per head (head_dim/2 is a multiple of 32 here)
+    for (int w = 0; w < wph; ++w) tot += red[hl * wph + w];
+    const float inv = 1.0f / sqrtf(tot / (float)d + norm_eps);
+    const T* nw = is_q ? q_norm_w : (is_k ? k_norm_w : nullptr);
+    if (active && nw != nullptr) {
+      x0 = rnd<T>(DT<T>::to_f(nw[i]) * rnd<T>(x0 * inv));
+      x1 = rnd<T>(DT<T>::to_f(nw[i + half]) * rnd<T>(x1 * inv));
+    }
+  }
+  if (!active) return;
+  if (is_q || is_k) {
+    const int pos = positions[t];
+    // cos/sin are [max_pos, d/2]: emb = cat(freqs, freqs) (:110) makes both halves share the same angle
+    const float c = DT<T>::to_f(cos_tab[(long long)pos * half + i]);
+    const float s = DT<T>::to_f(sin_tab[(long long)pos * half + i]);
+    // q_embed = (q * cos) + (rotate_half(q) * sin), every product and the sum rounded to dtype (:144)
+    const float r0 = rnd<T>(rnd<T>(x0 * c) + rnd<T>(-x1 * s));
+    const float r1 = rnd<T>(rnd<T>(x1 * c) + rnd<T>(x0 * s));
+    x0 = r0; x1 = r1;
+  }
+  if (is_q) {
+    T* o = q_out + t * (long long)nh * d + (long long)head * d;
+    o[i] = DT<T>::from_f(x0);
+    o[i + half] = DT<T>::from_f(x1);
+    return;
+  }
+  const int kvh = is_k ? head - nh : head - nh - nkv;
+  T* lin = is_k ? k_out : v_out;
+  if (lin) {
+    T* o = lin + t * (long long)nkv * d + (long long)kvh * d;
+    o[i] = DT<T>::from_f(x0);
+    o[i + half] = DT<T>::from_f(x1);
+  }
+  T* cache = is_k ? k_cache : v_cache;
+  if (cache && slot_map) {
+    const int slot = slot_map[t];
+    if (slot >= 0) {
+      const long long page = slot / page_size, off = slot % page_size;
+      T* o = cache + ((page * nkv + kvh) * page_size + off) * d;     // [num_pages, nkv, page_size, d]
+      o[i] = DT<T>::from_f(x0);
+      o[i + half] = DT<T>::from_f(x1);
+    }
+  }
+}
+
 // grid (ceil(heads * (d/16) / 256), T); thread = (head, chunk of 8 rotary pairs): it owns dims [8j, 8j+8) and the
 // matching dims of the upper half (the rotate_half pair, modeling_qwen2.py:116-120,141-145) -> every global access is a
 // 16-byte vector.  The d/16 threads of a head sit in one warp, so the Qwen3 per-head RMSNorm is a sub-warp shuffle.
@@ -531,6 +621,18 @@ extern "C" int cts_qkv_rope_cache(cts_ctx* ctx, const void* src, int src_is_part
       CTS_CHECK_ARG(ctx, t <= 65535, "partial input with t > 65535");
     }
     const void* src_c = src_is_partial ? src : (const void*)((const char*)src + tb * width * 2);
+    if (src_is_partial && (head_dim / 2) % 32 == 0) {
+      dim3 sgrid((unsigned)((nh + 2 * nkv + kRopeHeadsPerBlock - 1) / kRopeHeadsPerBlock), (unsigned)tc);
+      DISPATCH_T(dtype,
+                 CTS_CUDA(ctx, launch_pdl(qkv_rope_cache_scalar_kernel<T>, sgrid, dim3(kRopeHeadsPerBlock * (head_dim / 2)), 0,
+                                          (cudaStream_t)stream, 1, src_c, src_is_partial, split_k, (const T*)bias, positions + tb,
+                                          (const T*)cos_tab, (const T*)sin_tab, slot_map ? slot_map + tb : (const int*)nullptr,
+                                          (T*)q_out + tb * (long long)nh * head_dim, (T*)k_cache, (T*)v_cache,
+                                          k_out ? (T*)k_out + tb * (long long)nkv * head_dim : (T*)nullptr,
+                                          v_out ? (T*)v_out + tb * (long long)nkv * head_dim : (T*)nullptr, t, nh, nkv, head_dim,
+                                          page_size, (const T*)q_norm_w, (const T*)k_norm_w, norm_eps)));
+      continue;
+    }
     DISPATCH_T(dtype,
                CTS_CUDA(ctx, launch_pdl(qkv_rope_cache_kernel<T>, grid, dim3(threads), 0, (cudaStream_t)stream, 1, src_c, src_is_partial,
                                         split_k, (const T*)bias, positions + tb, (const T*)cos_tab, (const T*)sin_tab,
