@@ -167,10 +167,6 @@ class ChatTSForCausalLM:
         return max(sp["qkv"] * T * self.wqkv[0].shape[0] if sp["qkv"] > 1 else 0, sp["o"] * T * self.H if sp["o"] > 1 else 0,
                    sp["gu"] * T * 2 * self.I if T <= 128 else 0, sp["d"] * T * self.H if sp["d"] > 1 else 0, 1)
 
-    def _all_reduce_hidden(self, st, T):
-        """Row-parallel outputs (o_proj, down_proj) need the sum over tensor-parallel ranks before the residual add."""
-        raise NotImplementedError
-
     def _layers(self, st, T, attend):
         """Runs every decoder layer on st.h [T,H] in place; leaves RMSNorm_final(h) in st.xn."""
         c, sp, eps = self.ctx, st.splits, self.eps
