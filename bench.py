@@ -348,6 +348,36 @@ def run_b200(args):
                 "peak_source": peak_src, "split_k": sp,
                 "whole_step": {"bytes": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / hbm_peak}}
 
+    # ---- TS encoder alone (north_star: reported against the HBM roofline): N = 8*B series x 256 points -> 128*B patch rows,
+    # L2 flushed (256 MB write) before every timed call, CUDA events around the encode (patchify + 5 tcgen05 GEMM layers)
+    ts_roof = None
+    if world == 1:
+        from chatts_b200._cabi import CtsError  # noqa: F401
+        enc_b = make_batch(cfg, args.batch, seed=2)
+        x_ts = enc_b["timeseries"].to("cuda", torch.bfloat16)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        tse = model.ts_encoder
+        reps, tot_ms, rows = 8, 0.0, 0
+        for it in range(reps + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            feats, pc = tse.encode(x_ts)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                tot_ms += e0.elapsed_time(e1)
+                rows = int(feats.shape[0])
+        us = tot_ms * 1e3 / reps
+        H, in0, nl = tse.hidden_size, tse.input_size, tse.num_layers
+        w_bytes = 2 * (in0 * H + (nl - 1) * H * H + nl * H)
+        alg = w_bytes + x_ts.numel() * 2 + rows * in0 * 2 * 2 + rows * H * 2 * (2 * nl - 1)
+        flops = 2.0 * rows * (in0 * H + (nl - 1) * H * H)
+        ach = alg / (us * 1e-6) / 1e9
+        ts_roof = {"series": int(x_ts.shape[0]), "points": SERIES_LEN, "patch_rows": rows, "us": us, "algorithmic_bytes": alg,
+                   "achieved_gbs": ach, "hbm_frac": ach / hbm_peak, "tflops": flops / (us * 1e-6) / 1e12,
+                   "bound": "hbm (weight stream)" if rows <= 280 else "tensor", "launches": 1 + 2 + 2 * nl}
+
     # ---- e2e through the public API with host tensors
     e2e = None
     if world == 1 and not args.sweep_only:
@@ -379,7 +409,7 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.batch, world),
                 "by_batch": {str(b): {"tokens_per_s": r["tokens_per_s"], "ms_per_step": r["ms_per_step"]} for b, r in results.items()},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(main["launches"] * args.steps), "launches_per_step": main["launches"],
-                "roofline": roof, "cpu_baseline": cpu, "arch": ctx.arch, "lib": os.path.relpath(_cabi.LIB_PATH, ROOT)}
+                "roofline": roof, "ts_encoder": ts_roof, "cpu_baseline": cpu, "arch": ctx.arch, "lib": os.path.relpath(_cabi.LIB_PATH, ROOT)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
