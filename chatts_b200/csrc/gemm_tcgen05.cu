@@ -576,9 +576,9 @@ int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   p.split_k = a->split_k;
   p.epilogue = a->epilogue;
   constexpr int kStage = stage_bytes<BN, DUAL>();
-  // small-N (decode) tiles: leave room for two CTAs per SM so one CTA's prologue/epilogue overlaps the
+  // small-N (decode / short-prompt / TS-encoder) tiles: leave room for two or three CTAs per SM so one CTA's prologue/epilogue overlaps the
   // other's stream; large-N (prefill) tiles take the whole SM.
-  const int budget = (BN <= 32) ? ctx->decode_stages * 1024 : 200 * 1024;
+  const int budget = (BN <= 32) ? ctx->decode_stages * 1024 : (BN <= 128 ? 100 * 1024 : 200 * 1024);
   int stages = budget / kStage;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
@@ -652,7 +652,7 @@ extern "C" int cts_gemm_suggest_split(cts_ctx* ctx, long long n, long long k, lo
   const int bn = t <= 16 ? 16 : t <= 32 ? 32 : t <= 64 ? 64 : t <= 128 ? 128 : 256;
   const long long tiles = cdiv_ll(n, kBM) * cdiv_ll(t, bn);
   const long long kb = cdiv_ll(k, kBK);
-  const long long slots = (long long)ctx->sm_count * (bn <= 32 ? 2 : 1);
+  const long long slots = (long long)ctx->sm_count * (bn <= 128 ? 2 : 1);
   if (tiles >= slots) return 1;
   long long s = slots / tiles;
   const long long max_by_k = kb / 8 > 0 ? kb / 8 : 1;   // keep >= 8 K blocks (1 KiB of each weight row) per split

@@ -262,7 +262,9 @@ class ChatTSForCausalLM:
             if not isinstance(timeseries, torch.Tensor):
                 raise ValueError(f"Incorrect type of ts input features. Got type: {type(timeseries)}")   # chatts_vllm.py:533-535
             counts = self.ts_encoder.patch_counts(timeseries)            # H2D (if needed) + count kernels, async
-            cnt_h = counts[2].cpu().numpy().astype(np.int64)             # the one host sync
+            host = torch.stack([counts[1], counts[2]]).cpu()             # the one host sync: (valid_len, patch_cnt)
+            self._host_counts = (host[0], host[1])
+            cnt_h = host[1].numpy().astype(np.int64)
         if layout_kind == "hf":
             lay = layout.hf_layout(ids_cpu, am_cpu, cnt_h, cfg.ts_token_start_index)
         else:
@@ -289,7 +291,7 @@ class ChatTSForCausalLM:
         c.embed_gather(self.embed, ids_d, st.h, t=T)
         if counts is not None and lay.row_map.shape[0] > 0:
             rmap = torch.from_numpy(lay.row_map).to(dev, non_blocking=True)
-            self.ts_encoder.encode(timeseries, out=st.h, row_map=rmap, counts=counts)
+            self.ts_encoder.encode(timeseries, out=st.h, row_map=rmap, counts=counts, host_counts=self._host_counts)
         max_len = int(lens.max())
         scale = 1.0 / math.sqrt(self.d)
 

@@ -55,15 +55,19 @@ class TimeSeriesEmbedding:
         return x.reshape(n, -1).contiguous()
 
     # -- A4..A7 -------------------------------------------------------------------------------------
-    def encode(self, x, out=None, row_map=None, counts=None):
+    def encode(self, x, out=None, row_map=None, counts=None, host_counts=None):
         """Encode all series of ``x`` [N, 2L, 1].  Rows are written to ``out[row_map[r]]`` when given (the
-        merged embedding sequence), else to a fresh [sum P, H] tensor.  Returns (feats_or_None, patch_cnt_cpu)."""
+        merged embedding sequence), else to a fresh [sum P, H] tensor.  Returns (feats_or_None, patch_cnt_cpu).
+        ``host_counts`` = (valid_len, patch_cnt) CPU tensors from an earlier copy: skips the device->host sync."""
         if counts is None:
             counts = self.patch_counts(x)
         x, valid, cnt, off, mx = counts
         n = x.shape[0]
-        host = torch.stack([valid, cnt]).cpu()                 # the one sync of the call
-        valid_h, cnt_h = host[0], host[1]
+        if host_counts is None:
+            host = torch.stack([valid, cnt]).cpu()             # the one sync of the call
+            valid_h, cnt_h = host[0], host[1]
+        else:
+            valid_h, cnt_h = host_counts
         total = int(cnt_h.sum())
         if self.mode != 1 and bool(((valid_h % self.patch_size) != 0).any()):
             # reference behaviour: self.padding_idx is read at :128 but defined only under
