@@ -97,14 +97,14 @@ def test_gemm_gelu_swiglu_residual_rowmap(t):
     record("gemm_swiglu", t=t, err=e)
     assert e < 8e-3
     # residual, in place
-    res = (torch.randn(t, n) * 0.3).to(dtype)
+    res = (torch.randn(t, n, generator=torch.Generator().manual_seed(12)) * 0.3).to(dtype)
     h = res.cuda().clone()
     c.gemm(xd, wd, h, bias=bd, residual=h, epilogue=EPI_RESIDUAL)
     ref = (res.float() + (x.float() @ w.float().T + b.float()).to(dtype).float()).to(dtype)
-    assert rel_err(h, ref) < 8e-3
+    assert rel_err(h, ref) <= 2 ** -7 + 1e-6
     # row scatter: token i -> row perm[i] of a bigger buffer, -1 dropped
     big = torch.zeros(2 * t + 3, n, device="cuda", dtype=dtype)
-    perm = torch.randperm(2 * t + 3)[:t].to(torch.int32)
+    perm = torch.randperm(2 * t + 3, generator=torch.Generator().manual_seed(13))[:t].to(torch.int32)
     if t > 2:
         perm[1] = -1
     c.gemm(xd, wd, big, bias=bd, row_map=perm.cuda(), epilogue=EPI_NONE)
@@ -170,11 +170,39 @@ def test_persistent_bias_gelu_residual(t, n, k):
     lin = x.float() @ w.float().T + b.float()
     out = torch.full((t, n), float("nan"), device="cuda", dtype=dtype)
     c.gemm(xd, wd, out, bias=bd, epilogue=EPI_GELU)
-    assert rel_err(out, torch.nn.functional.gelu(lin.to(dtype).float()).to(dtype)) < 8e-3
-    res = (torch.randn(t, n) * 0.3).to(dtype)
+    eg = rel_err(out, torch.nn.functional.gelu(lin.to(dtype).float()).to(dtype))
+    assert eg <= 2 ** -7 + 1e-6, eg
+    res = (torch.randn(t, n, generator=torch.Generator().manual_seed(11)) * 0.3).to(dtype)
     h = res.cuda().clone()
     c.gemm(xd, wd, h, bias=bd, residual=h, epilogue=EPI_RESIDUAL)          # in place
     torch.cuda.synchronize()
-    e = rel_err(h, (res.float() + lin.to(dtype).float()).to(dtype))
-    record("gemm_persistent_residual", t=t, n=n, k=k, err=e)
-    assert e < 8e-3
+    ref = (res.float() + lin.to(dtype).float()).to(dtype)
+    e = rel_err(h, ref)
+    # at most one bf16 ulp (2^-7 of the largest magnitude) anywhere: accumulation order only
+    n_off = int(((h.float().cpu() - ref.float()).abs() > 0).sum())
+    record("gemm_persistent_residual", t=t, n=n, k=k, err=e, elements_differing=n_off)
+    assert e <= 2 ** -7 + 1e-6, (e, n_off)
+
+
+def test_persistent_kernel_is_deterministic_under_repetition():
+    """Race detector: the persistent double-buffered kernel must give bit-identical results on 12 repetitions
+    (RESIDUAL with a separate residual buffer, and interleaved SwiGLU)."""
+    c = ctx()
+    dtype = torch.bfloat16
+    t, n, k = 1536, 5120, 1024
+    x, w, b = _mk(t, n, k, dtype, 21)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    res = (torch.randn(t, n, generator=torch.Generator().manual_seed(3)) * 0.3).to(dtype).cuda()
+    first = None
+    for _ in range(12):
+        out = torch.empty(t, n, device="cuda", dtype=dtype)
+        c.gemm(xd, wd, out, bias=bd, residual=res, epilogue=EPI_RESIDUAL)
+        out2 = torch.empty(t, n // 2, device="cuda", dtype=dtype)
+        c.gemm(xd, wd, out2, epilogue=6)
+        torch.cuda.synchronize()
+        if first is None:
+            first = (out.clone(), out2.clone())
+            ref = (res.float().cpu() + (x.float() @ w.float().T + b.float()).to(dtype).float()).to(dtype)
+            assert rel_err(out, ref) <= 2 ** -7 + 1e-6
+        else:
+            assert torch.equal(out, first[0]) and torch.equal(out2, first[1])
