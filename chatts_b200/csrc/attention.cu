@@ -241,12 +241,13 @@ attn_prefill_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
 //           sum, and the MMA warp issues O[128 x 128] += P V into TMEM columns 128..255 (V is the MN-major B operand).
 // Two passes mean the O accumulator never needs a rescale (QK^T costs 2x, the softmax/PV path 1x).  Causal masking only
 // touches the diagonal tile (query and KV tiles are both 128 and aligned).  Epilogue: O / l from TMEM to global.
-constexpr int kTcQ = 128, kTcKV = 128, kTcThreads = 192;
-constexpr int kTcTile = kTcKV * 128 * 2;        // bytes of one [128 rows x 128 d] bf16 tile = two 16 KiB swizzled halves
-constexpr int kTcHalf = kTcKV * 128;            // one [128 rows x 128 B] half
+constexpr int kTcQ = 128, kTcKV = 64, kTcThreads = 192;
+constexpr int kTcQHalf = kTcQ * 128;            // one [128 q rows x 128 B] swizzled half of the Q tile (16 KiB)
+constexpr int kTcKHalf = kTcKV * 128;           // one [64 kv rows x 128 B] half of a K or V tile (8 KiB)
+constexpr int kTcSmem = 2 * kTcQHalf + kTcQ * 128 + 2 * 2 * kTcKHalf;   // Q 32 + P 16 + K 16 + V 16 = 80 KiB -> 2 CTAs / SM
 
 // MN-major (N contiguous) B operand, 128B swizzle: atoms of [8 K-rows x 64 N-elements]; LBO = stride between the
-// two 64-element N atoms (the two halves of the tile), SBO = stride between consecutive 8-row K groups.
+// 64-element N atoms (the two d-halves of the V tile), SBO = stride between consecutive 8-row K groups.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
@@ -257,20 +258,24 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
+// Pipeline (per CTA; two CTAs share an SM): K and V are single-buffered with independent full/empty barriers, S is
+// double-buffered in TMEM (2 x 64 columns) and the MMA warp issues QK^T of tile i BEFORE P.V of tile i-1, so the softmax
+// warps work on tile i while the tensor core runs P.V(i-1); P is single-buffered behind a p_free barrier.
 template <typename T>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)
 attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const int* __restrict__ cu_seqlens, int nh, int nkv,
                         float scale, T* __restrict__ out) {
   constexpr int HD = 128;
   extern __shared__ uint8_t tc_raw[];
-  __shared__ uint64_t q_bar, kv_full[2], kv_empty[2], s_full, s_free, p_full, o_done;
+  __shared__ uint64_t q_bar, k_full, k_empty, v_full, v_empty, s_full[2], s_free[2], p_full, p_free, o_done;
   __shared__ uint32_t tmem_slot;
   const uint32_t raw = smem_u32(tc_raw);
   uint8_t* smem = tc_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint8_t* q_s = smem;                       // 32 KiB
-  uint8_t* p_s = smem + kTcTile;             // 32 KiB
-  uint8_t* kv_s = smem + 2 * kTcTile;        // 2 stages x (K 32 KiB + V 32 KiB)
+  uint8_t* q_s = smem;                               // 32 KiB: 2 d-halves x [128 x 128 B]
+  uint8_t* p_s = q_s + 2 * kTcQHalf;                 // 16 KiB: [128 x 128 B] (64 kv columns)
+  uint8_t* k_s = p_s + kTcQ * 128;                   // 16 KiB: 2 d-halves x [64 x 128 B]
+  uint8_t* v_s = k_s + 2 * kTcKHalf;                 // 16 KiB
 
   const int b = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -278,10 +283,10 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(&q_bar, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(&s_full, 1);
-    mbar_init(&s_free, 4);
+    mbar_init(&k_full, 1); mbar_init(&k_empty, 1); mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 4); }
     mbar_init(&p_full, 4);
+    mbar_init(&p_free, 1);
     mbar_init(&o_done, 1);
     fence_mbar_init();
   }
@@ -289,35 +294,35 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_base = tmem_slot;               // S0: cols 0..63, S1: 64..127, O: 128..255
   pdl_wait();
 
   const int seq0 = cu_seqlens[b], len = cu_seqlens[b + 1] - seq0;
   const int q0 = qt * kTcQ;
-  const bool live = q0 < len;                   // CTA-uniform
+  const bool live = q0 < len;                         // CTA-uniform
   const int kvh = head / (nh / nkv);
-  const int ntiles = live ? qt + 1 : 0;         // causal: KV tiles 0..qt
-  const int total = 2 * ntiles;                 // pass 1 then pass 2
+  const int kv_end = min(len, q0 + kTcQ);             // causal: keys 0 .. kv_end-1
+  const int nt = live ? (kv_end + kTcKV - 1) / kTcKV : 0;
+  const int total = 2 * nt;                           // pass 1 (row max) then pass 2 (P, O)
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0 && live) {
-      mbar_expect_tx(&q_bar, (uint32_t)kTcTile);
+      mbar_expect_tx(&q_bar, (uint32_t)(2 * kTcQHalf));
       tma_load_2d(q_s, &tm_q, &q_bar, head * HD, seq0 + q0, CTS_L2_EVICT_FIRST);
-      tma_load_2d(q_s + kTcHalf, &tm_q, &q_bar, head * HD + 64, seq0 + q0, CTS_L2_EVICT_FIRST);
+      tma_load_2d(q_s + kTcQHalf, &tm_q, &q_bar, head * HD + 64, seq0 + q0, CTS_L2_EVICT_FIRST);
       for (int i = 0; i < total; ++i) {
-        const int s = i & 1;
-        const int j = i < ntiles ? i : i - ntiles;
-        const bool with_v = i >= ntiles;
-        mbar_wait(&kv_empty[s], ((uint32_t)(i >> 1) & 1u) ^ 1u);
-        mbar_expect_tx(&kv_full[s], (uint32_t)(with_v ? 2 * kTcTile : kTcTile));
-        uint8_t* ks = kv_s + (size_t)s * 2 * kTcTile;
+        const int j = i < nt ? i : i - nt;
         const int row = seq0 + j * kTcKV;
-        tma_load_2d(ks, &tm_k, &kv_full[s], kvh * HD, row, CTS_L2_EVICT_LAST);
-        tma_load_2d(ks + kTcHalf, &tm_k, &kv_full[s], kvh * HD + 64, row, CTS_L2_EVICT_LAST);
-        if (with_v) {
-          tma_load_2d(ks + kTcTile, &tm_v, &kv_full[s], kvh * HD, row, CTS_L2_EVICT_LAST);
-          tma_load_2d(ks + kTcTile + kTcHalf, &tm_v, &kv_full[s], kvh * HD + 64, row, CTS_L2_EVICT_LAST);
+        mbar_wait(&k_empty, ((uint32_t)i & 1u) ^ 1u);
+        mbar_expect_tx(&k_full, (uint32_t)(2 * kTcKHalf));
+        tma_load_2d(k_s, &tm_k, &k_full, kvh * HD, row, CTS_L2_EVICT_LAST);
+        tma_load_2d(k_s + kTcKHalf, &tm_k, &k_full, kvh * HD + 64, row, CTS_L2_EVICT_LAST);
+        if (i >= nt) {
+          mbar_wait(&v_empty, ((uint32_t)j & 1u) ^ 1u);
+          mbar_expect_tx(&v_full, (uint32_t)(2 * kTcKHalf));
+          tma_load_2d(v_s, &tm_v, &v_full, kvh * HD, row, CTS_L2_EVICT_LAST);
+          tma_load_2d(v_s + kTcKHalf, &tm_v, &v_full, kvh * HD + 64, row, CTS_L2_EVICT_LAST);
         }
       }
     }
@@ -325,37 +330,39 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     // ------------------------------ MMA issuer ------------------------------
     if (lane == 0 && live) {
       constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
-      const uint32_t idesc_qk = umma_idesc_f16(kBf16 ? 1 : 0, 128, 128);
-      const uint32_t idesc_pv = idesc_qk | (1u << 16);                  // B (= V) is MN-major
-      const uint32_t q_addr = smem_u32(q_s), p_addr = smem_u32(p_s);
+      const uint32_t idesc_qk = umma_idesc_f16(kBf16 ? 1 : 0, kTcKV, 128);
+      const uint32_t idesc_pv = umma_idesc_f16(kBf16 ? 1 : 0, 128, 128) | (1u << 16);   // B (= V) is MN-major
+      const uint32_t q_addr = smem_u32(q_s), p_addr = smem_u32(p_s), k_addr = smem_u32(k_s), v_addr = smem_u32(v_s);
+      auto issue_pv = [&](int j) {                        // O += P(j) V(j)
+        mbar_wait(&p_full, (uint32_t)j & 1u);
+        mbar_wait(&v_full, (uint32_t)j & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kTcKV / 16; ++kk) {
+          const uint64_t bdesc = umma_desc_mn_sw128(v_addr + (uint32_t)kk * 16 * 128, 2 * kTcKHalf / 2, 1024);
+          umma_f16(tmem_base + 128, umma_desc_k_sw128(p_addr + (uint32_t)kk * 32), bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty);
+        umma_commit(&p_free);
+      };
       mbar_wait(&q_bar, 0);
       for (int i = 0; i < total; ++i) {
-        const int s = i & 1;
-        const bool pass2 = i >= ntiles;
-        const uint32_t k_addr = smem_u32(kv_s + (size_t)s * 2 * kTcTile), v_addr = k_addr + kTcTile;
-        mbar_wait(&kv_full[s], (uint32_t)(i >> 1) & 1u);
-        if (i > 0) mbar_wait(&s_free, (uint32_t)(i - 1) & 1u);          // softmax warps are done with S of tile i-1
+        const uint32_t sb = (uint32_t)i & 1u;
+        mbar_wait(&k_full, (uint32_t)i & 1u);
+        if (i >= 2) mbar_wait(&s_free[sb], (uint32_t)((i - 2) >> 1) & 1u);     // softmax warps finished reading S[sb]
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t off = (uint32_t)(kk >> 2) * kTcHalf + (uint32_t)(kk & 3) * 32;
-          umma_f16(tmem_base, umma_desc_k_sw128(q_addr + off), umma_desc_k_sw128(k_addr + off), idesc_qk, kk > 0 ? 1u : 0u);
+          const uint32_t qoff = (uint32_t)(kk >> 2) * kTcQHalf + (uint32_t)(kk & 3) * 32;
+          const uint32_t koff = (uint32_t)(kk >> 2) * kTcKHalf + (uint32_t)(kk & 3) * 32;
+          umma_f16(tmem_base + sb * kTcKV, umma_desc_k_sw128(q_addr + qoff), umma_desc_k_sw128(k_addr + koff), idesc_qk,
+                   kk > 0 ? 1u : 0u);
         }
-        umma_commit(&s_full);
-        if (!pass2) {
-          umma_commit(&kv_empty[s]);                                    // K consumed
-        } else {
-          mbar_wait(&p_full, (uint32_t)(i - ntiles) & 1u);              // P tile written (and S free again)
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < kTcKV / 16; ++kk) {
-            const uint32_t aoff = (uint32_t)(kk >> 2) * kTcHalf + (uint32_t)(kk & 3) * 32;
-            const uint64_t bdesc = umma_desc_mn_sw128(v_addr + (uint32_t)kk * 16 * 128, kTcHalf, 1024);
-            umma_f16(tmem_base + 128, umma_desc_k_sw128(p_addr + aoff), bdesc, idesc_pv, (i > ntiles || kk > 0) ? 1u : 0u);
-          }
-          umma_commit(&kv_empty[s]);                                    // K, V and P consumed
-        }
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty);
+        if (i > nt) issue_pv(i - 1 - nt);                 // P.V of the previous pass-2 tile, behind this tile's QK^T
       }
+      if (nt > 0) issue_pv(nt - 1);
       umma_commit(&o_done);
     }
   } else if (live) {
@@ -363,70 +370,74 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const int q = warp & 3;
     const int r = q * 32 + lane;                          // row inside the tile == TMEM lane
     const int qi = q0 + r;                                // query index inside the sequence
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = scale * 1.4426950408889634f;
     float m_run = -INFINITY, l_run = 0.f;
     for (int i = 0; i < total; ++i) {
-      const bool pass2 = i >= ntiles;
-      const int j = pass2 ? i - ntiles : i;
+      const bool pass2 = i >= nt;
+      const int j = pass2 ? i - nt : i;
       const int kv0 = j * kTcKV;
-      const bool diag = j == qt;
-      mbar_wait(&s_full, (uint32_t)i & 1u);
+      const bool need_mask = kv0 + kTcKV - 1 > q0;        // CTA-uniform: the tile reaches past the first query row
+      const uint32_t sb = (uint32_t)i & 1u;
+      const uint32_t s_addr = lane_base + sb * kTcKV;
+      mbar_wait(&s_full[sb], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       if (!pass2) {
         float mx = m_run;
 #pragma unroll 1
         for (int c = 0; c < kTcKV; c += 16) {
           uint32_t v[16];
-          tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+          tmem_ld_32x32b_x16(s_addr + (uint32_t)c, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float sv = __uint_as_float(v[e]);
-            if (!diag || kv0 + c + e <= qi) mx = fmaxf(mx, sv);
-          }
+          for (int e = 0; e < 16; ++e)
+            if (!need_mask || kv0 + c + e <= qi) mx = fmaxf(mx, __uint_as_float(v[e]));
         }
         m_run = mx;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[sb]);
       } else {
         const float mneg = m_run > -INFINITY ? m_run * sl2 : 0.f;
-#pragma unroll 1
+        uint4 pk[kTcKV / 8];
+#pragma unroll
         for (int c = 0; c < kTcKV; c += 16) {
           uint32_t v[16];
-          tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+          tmem_ld_32x32b_x16(s_addr + (uint32_t)c, v);
           tmem_ld_wait();
           float pv[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const bool ok = !diag || kv0 + c + e <= qi;
+            const bool ok = !need_mask || kv0 + c + e <= qi;
             pv[e] = ok ? exp2f(__uint_as_float(v[e]) * sl2 - mneg) : 0.f;
             l_run += pv[e];
           }
-          // P[r][c..c+15] -> K-major swizzled tile: 16-byte chunk index (c/8 .. +1) inside the 64-wide half c/64
-          const uint32_t hb = (uint32_t)(c >> 6) * kTcHalf + (uint32_t)r * 128;
-          const int ch = (c & 63) >> 3;
-          *reinterpret_cast<uint4*>(p_s + hb + (((ch) ^ (r & 7)) << 4)) = pack8<T>(pv);
-          *reinterpret_cast<uint4*>(p_s + hb + (((ch + 1) ^ (r & 7)) << 4)) = pack8<T>(pv + 8);
+          pk[c / 8] = pack8<T>(pv);
+          pk[c / 8 + 1] = pack8<T>(pv + 8);
         }
-        fence_proxy_async_smem();                       // P must be visible to the tensor core (async proxy)
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_free);
-        if (pass2) mbar_arrive(&p_full);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[sb]);          // S[sb] is free for QK^T of tile i+2
+        if (j > 0) mbar_wait(&p_free, (uint32_t)(j - 1) & 1u);   // P.V(j-1) has consumed the previous P tile
+        // P[r][0..63] -> K-major swizzled tile (row r, 16-byte chunk ch at ch ^ (r & 7))
+#pragma unroll
+        for (int ch = 0; ch < kTcKV / 8; ++ch)
+          *reinterpret_cast<uint4*>(p_s + (uint32_t)r * 128 + ((ch ^ (r & 7)) << 4)) = pk[ch];
+        fence_proxy_async_smem();                         // P must be visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full);
       }
     }
-    // ---- epilogue: O / l
+    // ---- epilogue: O / l   (tcgen05.ld is warp-collective: every lane loads, rows inside the sequence are stored)
     mbar_wait(&o_done, 0);
     tc_fence_after();
     {
-      // tcgen05.ld is warp-collective: every lane loads its row; only rows inside the sequence are stored
       const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
       T* o_g = out + ((long long)seq0 + (qi < len ? qi : 0)) * nh * HD + (long long)head * HD;
 #pragma unroll 1
       for (int c = 0; c < HD; c += 16) {
         uint32_t v[16];
-        tmem_ld_32x32b_x16(lane_addr + 128u + (uint32_t)c, v);
+        tmem_ld_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
         tmem_ld_wait();
         if (qi < len) {
           float f[16];
@@ -724,7 +735,7 @@ extern "C" int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, cons
     rc = cts_make_tmap_2d(ctx, &tm_v, v, total_tokens, (long long)nkv * 128, (long long)nkv * 128, kTcKV, dtype == CTS_BF16);
     if (rc) return rc;
     dim3 g5((unsigned)((max_seqlen + kTcQ - 1) / kTcQ), (unsigned)nh, (unsigned)batch);
-    const size_t smem5 = (size_t)6 * kTcTile + 1024;
+    const size_t smem5 = (size_t)kTcSmem + 1024;
     if (dtype == CTS_BF16) {
       auto kern = attn_prefill_tc5_kernel<__nv_bfloat16>;
       CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
