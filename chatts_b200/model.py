@@ -367,6 +367,9 @@ class ChatTSForCausalLM:
         per = max(1, (3 * 148) // max(1, B * self.nkv))
         max_tiles = max(1, (self.max_seq_len + 63) // 64)
         st.attn_splits = int(max(1, min(per, max_tiles, 32)))
+        import os
+        if os.environ.get("CTS_ATTN_SPLITS"):                      # tuning override
+            st.attn_splits = int(os.environ["CTS_ATTN_SPLITS"])
         st.attn_ws = torch.zeros(self.ctx.attn_decode_workspace_floats(B, self.nh, self.d, st.attn_splits), device=dev,
                                  dtype=torch.float32)      # zero-filled once: holds the self-resetting split counters
         st.graph = st.graph_nosample = None
