@@ -267,13 +267,9 @@ def run_b200(args):
             st.step_ptr.zero_()
             ctx.greedy_advance(logits, batch, st.out_tokens, st.step_ptr, st.cur_ids, st.positions, st.seq_lens, st.slot_map,
                                st.page_table, model.page_size)
-            l0 = ctx.launches
-            model._decode_step(st)                      # first call captures the graph (and runs one real step)
-            per_step_launches = None
-            for _ in range(max(args.warmup - 1, 2)):
-                l0 = ctx.launches
+            for _ in range(max(args.warmup, 3)):        # untimed warm-up steps; the first one also captures the CUDA graph
                 model._decode_step(st)
-            # launches per step: count them by running the body eagerly once outside the graph bookkeeping
+            # kernels per step, counted by running the same step body eagerly once (one more untimed step)
             l0 = ctx.launches
             model._decode_body(st, True)
             per_step_launches = ctx.launches - l0
