@@ -23,6 +23,7 @@ struct cts_ctx {
   int l2_prefetch_mb;   // tuning knob (CTS_L2_PREFETCH_MB): weight bytes a decode GEMM prefetches into L2 while it waits
   int force_wmma_attention;   // CTS_ATTN_WMMA=1: use the round-1 HMMA prefill attention even for head_dim 128 (A/B testing)
   int no_persistent_gemm;     // CTS_NO_PERSISTENT_GEMM=1: A/B switch back to the one-tile-per-CTA kernel for big T
+  int norm_cluster;           // CTS_NORM_CLUSTER: max thread-block-cluster size of the decode RMSNorm kernel (default 8)
   int decode_stages;    // tuning knob (CTS_DECODE_SMEM_KB): shared-memory budget per CTA of the decode GEMM
 };
 

@@ -68,6 +68,8 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
   ctx->force_wmma_attention = e3 ? atoi(e3) : 0;
   const char* e4 = getenv("CTS_NO_PERSISTENT_GEMM");
   ctx->no_persistent_gemm = e4 ? atoi(e4) : 0;
+  const char* e5 = getenv("CTS_NORM_CLUSTER");
+  ctx->norm_cluster = e5 ? atoi(e5) : 8;
   const char* e2 = getenv("CTS_DECODE_SMEM_KB");
   ctx->decode_stages = e2 ? atoi(e2) : 75;   // 3 CTAs/SM x 3-4 stages measured best on B200 (profiles/r1_sweep_decode_gemm.txt)
   *out = ctx;

@@ -563,6 +563,7 @@ extern "C" int cts_reduce_residual_rmsnorm(cts_ctx* ctx, const float* partial, i
   // thread-block cluster over the hidden dimension when the row is wide enough (DSMEM exchange of the sum of squares)
   unsigned C = 1;
   for (unsigned c : {8u, 4u, 2u}) {
+    if (c > (unsigned)ctx->norm_cluster) continue;
     if (h % (8 * c) == 0 && h / (8 * c) >= 32 && h / c <= 8LL * kClMaxVec * kClThreads) { C = c; break; }
   }
   if (C > 1 && t <= 256) {      // decode-sized T: spread each token over a cluster; big T already fills the GPU
