@@ -152,6 +152,67 @@ class ChatTSForCausalLM:
         sd = load_checkpoint(path, device="cpu")
         return cls(cfg, sd, device=dev, dtype=dt, **kw)
 
+    # ------------------------------------------------------------------------------------------ LoRA
+    def merge_lora(self, adapter, lora_alpha=None, r=None):
+        """PeftModel.from_pretrained(model, adapter).merge_and_unload() (demo/demo_lora.ipynb cells 3-4): fold LoRA adapters
+        into the resident weights, W += (alpha / r) * B @ A, for q/k/v/o/gate/up/down_proj.  ``adapter`` is a directory with
+        adapter_model.safetensors + adapter_config.json, or a name->tensor dict (PEFT names:
+        ``...layers.{i}.self_attn.q_proj.lora_A.weight`` [r, in], ``...lora_B.weight`` [out, r]).  Load-time host logic:
+        the merged weights then run through the same kernels."""
+        import json
+        import os
+        import re
+        if isinstance(adapter, str):
+            cfg_path = os.path.join(adapter, "adapter_config.json")
+            if os.path.exists(cfg_path):
+                ac = json.load(open(cfg_path))
+                lora_alpha = ac.get("lora_alpha", lora_alpha) if lora_alpha is None else lora_alpha
+                r = ac.get("r", r) if r is None else r
+            from safetensors.torch import load_file
+            sd = load_file(os.path.join(adapter, "adapter_model.safetensors"))
+        else:
+            sd = dict(adapter)
+        pairs = {}
+        for name, t in sd.items():
+            m = re.search(r"layers\.(\d+)\.(?:self_attn|mlp)\.(\w+_proj)\.lora_([AB])(?:\.\w+)?\.weight$", name)
+            if m:
+                pairs.setdefault((int(m.group(1)), m.group(2)), {})[m.group(3)] = t
+        if not pairs:
+            raise ValueError("no LoRA tensors (…{q,k,v,o,gate,up,down}_proj.lora_{A,B}.weight) found in the adapter")
+        cfg, d = self.config, self.d
+        nh_t, nkv_t = cfg.num_attention_heads, cfg.num_key_value_heads
+        merged = 0
+        for (l, proj), ab in sorted(pairs.items()):
+            A, B = ab["A"].to(self.device, torch.float32), ab["B"].to(self.device, torch.float32)
+            rank = A.shape[0]
+            scale = float(lora_alpha if lora_alpha is not None else rank) / float(r if r is not None else rank)
+            delta = (B @ A) * scale                                   # [out, in] in the unsharded HF shape
+            delta = shard_tensor(f"model.layers.{l}.{'self_attn' if proj[0] in 'qkvo' else 'mlp'}.{proj}.weight", delta, cfg,
+                                 self.tp_rank, self.tp_size)
+
+            def add(w_rows, dlt):
+                w_rows.copy_((w_rows.float() + dlt).to(self.dtype))
+
+            if proj == "q_proj":
+                add(self.wqkv[l][: self.nh * d], delta)
+            elif proj == "k_proj":
+                add(self.wqkv[l][self.nh * d:(self.nh + self.nkv) * d], delta)
+            elif proj == "v_proj":
+                add(self.wqkv[l][(self.nh + self.nkv) * d:], delta)
+            elif proj == "o_proj":
+                add(self.wo[l], delta)
+            elif proj == "down_proj":
+                add(self.wd[l], delta)
+            elif proj in ("gate_proj", "up_proj"):
+                # interleaved layout: tile k holds gate rows [64k, 64k+64) then up rows [64k, 64k+64)
+                v = self.wgu[l].view(-1, 2, 64, self.H)
+                sel = v[:, 0 if proj == "gate_proj" else 1]
+                sel.copy_((sel.float() + delta.view(-1, 64, self.H)).to(self.dtype))
+            else:
+                continue
+            merged += 1
+        return merged          # in-place update: captured decode graphs keep reading the same (now merged) buffers
+
     # ------------------------------------------------------------------------------------------ layers
     def _splits(self, T):
         c = self.ctx

@@ -207,3 +207,35 @@ def test_chatts_8b_qwen3_variant_matches_oracle():
     ids = model.generate(**enc, max_new_tokens=10, ignore_eos=True)
     record("chatts_8b_qwen3_variant", err=worst)
     assert worst < 2e-2 and ids.shape[1] == enc["input_ids"].shape[1] + 10
+
+
+def test_lora_merge_and_unload_matches_oracle(tmp_path):
+    """demo/demo_lora.ipynb cells 3-4: PeftModel.from_pretrained(...).merge_and_unload() -> adapters folded into the weights."""
+    import json
+    from safetensors.torch import save_file
+    cfg, sd, model, proc = _mk(seed=8, max_batch=2, max_seq_len=512)
+    g = torch.Generator().manual_seed(4)
+    r, alpha = 8, 16
+    ad, sd2 = {}, {k: v.clone() for k, v in sd.items()}
+    for l in range(cfg.num_hidden_layers):
+        for blk, proj in (("self_attn", "q_proj"), ("self_attn", "k_proj"), ("self_attn", "v_proj"), ("self_attn", "o_proj"),
+                          ("mlp", "gate_proj"), ("mlp", "up_proj"), ("mlp", "down_proj")):
+            w = sd[f"model.layers.{l}.{blk}.{proj}.weight"]
+            A = torch.randn(r, w.shape[1], generator=g) * 0.05
+            B = torch.randn(w.shape[0], r, generator=g) * 0.05
+            ad[f"base_model.model.model.layers.{l}.{blk}.{proj}.lora_A.weight"] = A
+            ad[f"base_model.model.model.layers.{l}.{blk}.{proj}.lora_B.weight"] = B
+            sd2[f"model.layers.{l}.{blk}.{proj}.weight"] = (w.float() + (alpha / r) * (B @ A)).to(DT)
+    d = tmp_path / "adapter"
+    d.mkdir()
+    save_file(ad, str(d / "adapter_model.safetensors"))
+    json.dump({"r": r, "lora_alpha": alpha, "target_modules": ["q_proj"]}, open(d / "adapter_config.json", "w"))
+    x = np.arange(128)
+    enc = proc(text=["lora <ts><ts/> ?"], timeseries=[np.sin(x / 9.0)], return_tensors="pt")
+    before = model.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"]).logits[:, 0].clone()
+    assert model.merge_lora(str(d)) == 7 * cfg.num_hidden_layers
+    lg = model.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"]).logits[:, 0]
+    ref, _ = _oracle_last_logits(cfg, sd2, enc, samples=[0])
+    e = rel_err(lg[0], ref[0][0])
+    record("lora_merge", err=e, moved=rel_err(lg[0], before[0]))
+    assert e < 2e-2 and rel_err(lg[0], before[0]) > 5e-2          # matches the merged oracle, and really changed
