@@ -14,6 +14,15 @@ DT = torch.bfloat16
 @pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("lens", [[1], [5, 64, 65], [130, 17, 200, 1], [577]])
 def test_prefill_varlen_causal_gqa(d, lens):
+    _prefill_case(d, lens, torch.bfloat16)
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_prefill_fp16(d):
+    _prefill_case(d, [129, 64, 300], torch.float16)
+
+
+def _prefill_case(d, lens, DT):
     c = ctx()
     nh, nkv = 4, 2
     T = sum(lens)
@@ -29,7 +38,7 @@ def test_prefill_varlen_causal_gqa(d, lens):
     ref = torch.cat([od.attention(q[a:b].float(), k[a:b].float(), v[a:b].float(), nh // nkv, 0)
                      for a, b in zip(cu[:-1].tolist(), cu[1:].tolist())])
     e = rel_err(out, ref)
-    record("attn_prefill", d=d, lens=str(lens), err=e)
+    record("attn_prefill", d=d, lens=str(lens), err=e, dtype=str(DT))
     assert torch.isfinite(out.float()).all()
     assert e < 1.5e-2
 
@@ -38,6 +47,15 @@ def test_prefill_varlen_causal_gqa(d, lens):
                                             (128, 14, 2, 16), (128, 5, 1, 64)])
 @pytest.mark.parametrize("splits", [1, 3, 16])
 def test_decode_paged(d, nh, nkv, page, splits):
+    _decode_case(d, nh, nkv, page, splits, torch.bfloat16)
+
+
+@pytest.mark.parametrize("d,nh,nkv,page", [(128, 40, 8, 64), (64, 4, 2, 16)])
+def test_decode_paged_fp16(d, nh, nkv, page):
+    _decode_case(d, nh, nkv, page, 3, torch.float16)
+
+
+def _decode_case(d, nh, nkv, page, splits, DT):
     c = ctx()
     seq_lens = [1, page, page + 1, 5 * page - 3, 333][: 4 if nh == 40 else 5]
     B = len(seq_lens)

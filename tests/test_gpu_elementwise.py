@@ -136,3 +136,50 @@ def test_greedy_advance(vocab):
     assert out_tokens.cpu()[:, 2].tolist() == ref.tolist() and step.cpu().tolist() == [3, 0]
     assert pos.cpu().tolist() == [15, 16, 32] and sl.cpu().tolist() == [16, 17, 33]
     assert slot.cpu().tolist() == [3 * 16 + 15, 9 * 16 + 0, 6 * 16 + 0]
+
+
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("partial", [True, False])
+def test_qkv_rope_cache_qwen3_qk_norm(d, partial):
+    """Qwen3 / ChatTS-8B: per-head RMSNorm of q and k before RoPE (scalar kernel on split-K partials, vector kernel otherwise)."""
+    c = ctx()
+    from chatts_b200.config import ChatTSConfig
+    from chatts_b200.model import rope_tables
+    t, nh, nkv, page = 9, 8, 2, 16
+    cfg = ChatTSConfig.tiny(head_dim=d, num_attention_heads=nh, num_key_value_heads=nkv)
+    width = (nh + 2 * nkv) * d
+    g = torch.Generator().manual_seed(31 + d)
+    qn = (torch.rand(d, generator=g) + 0.5).to(DT)
+    kn = (torch.rand(d, generator=g) + 0.5).to(DT)
+    positions = torch.arange(t, dtype=torch.int32) * 3
+    if partial:
+        s = 2
+        part = torch.randn(s, t, width, generator=g)
+        qkv = part.sum(0).to(DT)
+        src = part.cuda()
+    else:
+        s = 1
+        qkv = torch.randn(t, width, generator=g).to(DT)
+        src = qkv.cuda()
+    cos, sin = rope_tables(cfg, 64, DT, "cuda")
+    kc = torch.zeros(4, nkv, page, d, device="cuda", dtype=DT)
+    vc = torch.zeros_like(kc)
+    slot = torch.arange(t, dtype=torch.int32) + 5
+    q_out = torch.empty(t, nh * d, device="cuda", dtype=DT)
+    k_lin = torch.empty(t, nkv * d, device="cuda", dtype=DT)
+    v_lin = torch.empty(t, nkv * d, device="cuda", dtype=DT)
+    c.qkv_rope_cache(src, partial, s, None, positions.cuda(), cos, sin, slot.cuda(), q_out, kc, vc, k_lin, v_lin, t, nh, nkv, d, page,
+                     qn.cuda(), kn.cuda(), 1e-6)
+    torch.cuda.synchronize()
+    oc, osn = od.rope_tables(dict(head_dim=d, rope_theta=cfg.rope_theta, hidden_size=0, num_attention_heads=1), 64, DT)
+    q = od.rms_norm(qkv[:, : nh * d].view(t, nh, d), qn, 1e-6)
+    k = od.rms_norm(qkv[:, nh * d:(nh + nkv) * d].view(t, nkv, d), kn, 1e-6)
+    v = qkv[:, (nh + nkv) * d:].view(t, nkv, d)
+    qe, ke = od.apply_rope(q, k, oc[positions.long()], osn[positions.long()])
+    # the norm's fp32 sum order differs (shuffle tree vs torch), so allow one dtype ulp after the exact RoPE rounding chain
+    assert rel_err(q_out.view(t, nh, d), qe) <= 2 ** -7 and rel_err(k_lin.view(t, nkv, d), ke) <= 2 ** -7
+    assert torch.equal(v_lin.cpu().view(t, nkv, d), v)
+    kcc = kc.cpu()
+    for i in range(t):
+        sl = int(slot[i])
+        assert torch.equal(kcc[sl // page, :, sl % page], k_lin.cpu().view(t, nkv, d)[i])
