@@ -23,7 +23,7 @@ SYMBOLS = [
     "cts_reduce_bias_act", "cts_reduce_residual_rmsnorm", "cts_reduce_swiglu", "cts_qkv_rope_cache",
     "cts_embed_gather", "cts_attn_prefill", "cts_attn_decode_workspace_floats", "cts_attn_decode",
     "cts_greedy_advance", "cts_ipc_alloc", "cts_ipc_open", "cts_ipc_close", "cts_ipc_free",
-    "cts_peer_allreduce_residual_rmsnorm", "cts_peer_greedy_advance",
+    "cts_peer_allreduce_residual_rmsnorm", "cts_peer_greedy_advance", "cts_decode_chain",
 ]
 
 
@@ -40,6 +40,15 @@ class GemmArgs(C.Structure):
         ("dtype", C.c_int), ("epilogue", C.c_int), ("split_k", C.c_int), ("reserved", C.c_int),
         ("splitk_ws", C.c_void_p), ("tile_counters", C.c_void_p),
     ]
+
+
+class ChainArgs(C.Structure):
+    _fields_ = (
+        [(k, C.c_int) for k in ("t", "hidden", "inter", "nh", "nkv", "head_dim", "phase_begin", "phase_end", "norm5_has_partial",
+                                "dtype")] + [("split", C.c_int * 4)] +
+        [(k, C.c_void_p) for k in ("wo", "wgu", "wd", "wqkv", "ao", "h", "xn", "act", "ln_post", "ln_next")] + [("eps", C.c_float)] +
+        [(k, C.c_void_p) for k in ("bqkv", "q_norm_w", "k_norm_w", "positions", "cos_tab", "sin_tab", "slot_map", "q_out", "k_cache",
+                                   "v_cache")] + [("page_size", C.c_int)] + [(k, C.c_void_p) for k in ("ws", "ssq", "sync")])
 
 
 _lib = None
@@ -81,6 +90,8 @@ def load_library():
     lib.cts_ipc_close.argtypes = [vp, vp]
     lib.cts_ipc_free.argtypes = [vp, vp]
     lib.cts_peer_allreduce_residual_rmsnorm.argtypes = [vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
+    lib.cts_decode_chain.argtypes = [vp, C.POINTER(ChainArgs), vp]
+    lib.cts_decode_chain.restype = i
     lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cts_peer_greedy_advance.restype = i
     for name in ("cts_ipc_alloc", "cts_ipc_open", "cts_ipc_close", "cts_ipc_free", "cts_peer_allreduce_residual_rmsnorm"):
@@ -246,6 +257,25 @@ class Context:
                                                                rank, world, max_tokens, _p(resid_in), _p(resid_out), _p(norm_w),
                                                                float(eps), _p(norm_out), t, resid_in.shape[-1],
                                                                dtype_code(resid_in.dtype), _stream()))
+
+    def decode_chain(self, *, t, hidden, inter, nh, nkv, head_dim, phases, splits, h, xn, act, ws, ssq, sync, eps, dtype,
+                     norm5_has_partial=1, wo=None, wgu=None, wd=None, wqkv=None, ao=None, ln_post=None, ln_next=None, bqkv=None,
+                     q_norm_w=None, k_norm_w=None, positions=None, cos=None, sin=None, slot_map=None, q_out=None, k_cache=None,
+                     v_cache=None, page_size=0):
+        """One persistent kernel for the phases [phases[0], phases[1]) of a decode layer chain (include/chatts_b200.h)."""
+        a = ChainArgs()
+        a.t, a.hidden, a.inter, a.nh, a.nkv, a.head_dim = t, hidden, inter, nh, nkv, head_dim
+        a.phase_begin, a.phase_end, a.norm5_has_partial, a.dtype = phases[0], phases[1], int(norm5_has_partial), dtype_code(dtype)
+        for i2, v in enumerate(splits):
+            a.split[i2] = int(v)
+        dp = lambda x: None if x is None else x.data_ptr()
+        a.wo, a.wgu, a.wd, a.wqkv, a.ao = dp(wo), dp(wgu), dp(wd), dp(wqkv), dp(ao)
+        a.h, a.xn, a.act, a.ln_post, a.ln_next, a.eps = dp(h), dp(xn), dp(act), dp(ln_post), dp(ln_next), float(eps)
+        a.bqkv, a.q_norm_w, a.k_norm_w = dp(bqkv), dp(q_norm_w), dp(k_norm_w)
+        a.positions, a.cos_tab, a.sin_tab, a.slot_map = dp(positions), dp(cos), dp(sin), dp(slot_map)
+        a.q_out, a.k_cache, a.v_cache, a.page_size = dp(q_out), dp(k_cache), dp(v_cache), int(page_size)
+        a.ws, a.ssq, a.sync = dp(ws), dp(ssq), dp(sync)
+        self._chk(self.lib.cts_decode_chain(self.h, C.byref(a), _stream()))
 
     def peer_greedy_advance(self, logits, batch, rank, world, peer_cand, peer_flags, state, max_batch, out_tokens, step_ptr, cur_ids,
                             positions, seq_lens, slot_map, page_table, page_size):

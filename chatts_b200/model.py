@@ -64,7 +64,7 @@ class _Step:
 class ChatTSForCausalLM:
     def __init__(self, config, state_dict, device="cuda", dtype=torch.bfloat16, tp_rank=0, tp_size=1,
                  max_batch=32, max_seq_len=2048, page_size=64, use_cuda_graph=True, comm=None,
-                 use_peer_allreduce=True, graph_with_tp=True):
+                 use_peer_allreduce=True, graph_with_tp=True, use_chain=None):
         if not torch.cuda.is_available():
             raise _cabi.CtsError("chatts_b200 needs a B200 (sm_100a) GPU; there is no CPU fallback")
         self.config, self.dtype = config, dtype
@@ -82,6 +82,8 @@ class ChatTSForCausalLM:
         self.max_pages = (max_seq_len + page_size - 1) // page_size
         self.use_cuda_graph = use_cuda_graph
         self.graph_with_tp = graph_with_tp
+        import os as _os
+        self.use_chain = bool(int(_os.environ.get("CTS_DECODE_CHAIN", "0"))) if use_chain is None else bool(use_chain)
         self._load(state_dict)
         n_pos = min(cfg.max_position_embeddings, max(max_seq_len, 16))
         self.cos, self.sin = rope_tables(cfg, n_pos, dtype, self.device)
@@ -433,9 +435,33 @@ class ChatTSForCausalLM:
             st.attn_splits = int(os.environ["CTS_ATTN_SPLITS"])
         st.attn_ws = torch.zeros(self.ctx.attn_decode_workspace_floats(B, self.nh, self.d, st.attn_splits), device=dev,
                                  dtype=torch.float32)      # zero-filled once: holds the self-resetting split counters
+        st.ssq = torch.zeros(B * 8, device=dev, dtype=torch.float32)
+        st.chain_sync = torch.zeros(2, device=dev, dtype=torch.int32)       # grid-barrier counters of the chain kernel
         st.graph = st.graph_nosample = None
         self._steps[key] = st
         return st
+
+    def _chain_ok(self, B):
+        return (self.use_chain and self.tp_size == 1 and B <= 32 and self.H % 64 == 0 and self.H // 64 <= 192 and self.I % 64 == 0)
+
+    def _decode_layers_chain(self, st, attend):
+        """Decode layers with the persistent chain kernel: per layer ONE attention launch + ONE chain launch
+        (o_proj -> +resid/norm -> gate_up -> SwiGLU -> down -> +resid/norm -> next QKV -> RoPE/KV write)."""
+        c, B, sp = self.ctx, st.B, st.splits
+        common = dict(t=B, hidden=self.H, inter=self.I, nh=self.nh, nkv=self.nkv, head_dim=self.d,
+                      splits=(sp["o"], sp["gu"], sp["d"], sp["qkv"]), h=st.h, xn=st.xn, act=st.act, ws=st.ws, ssq=st.ssq,
+                      sync=st.chain_sync, eps=self.eps, dtype=self.dtype, positions=st.positions, cos=self.cos, sin=self.sin,
+                      slot_map=st.slot_map, q_out=st.q, page_size=self.page_size)
+        # head: RMSNorm(ln1[0]) -> QKV(0) -> RoPE / KV write(0)
+        c.decode_chain(phases=(5, 8), norm5_has_partial=0, ln_next=self.ln1[0], wqkv=self.wqkv[0], bqkv=self.bqkv[0],
+                       q_norm_w=self.qn[0], k_norm_w=self.kn[0], k_cache=self.kv[0, 0], v_cache=self.kv[0, 1], **common)
+        for l in range(self.L):
+            attend(l)
+            last = l == self.L - 1
+            nxt = {} if last else dict(wqkv=self.wqkv[l + 1], bqkv=self.bqkv[l + 1], q_norm_w=self.qn[l + 1], k_norm_w=self.kn[l + 1],
+                                       k_cache=self.kv[l + 1, 0], v_cache=self.kv[l + 1, 1])
+            c.decode_chain(phases=(0, 6 if last else 8), wo=self.wo[l], ao=st.ao, ln_post=self.ln2[l], wgu=self.wgu[l], wd=self.wd[l],
+                           ln_next=self.final_norm if last else self.ln1[l + 1], **nxt, **common)
 
     def _decode_body(self, st, sample):
         c, B = self.ctx, st.B
@@ -446,7 +472,10 @@ class ChatTSForCausalLM:
             c.attn_decode(st.q, self.kv[l, 0], self.kv[l, 1], st.page_table, st.seq_lens, B, self.nh, self.nkv, self.d,
                           self.page_size, scale, st.attn_splits, st.attn_ws, st.ao)
 
-        self._layers(st, B, attend)
+        if self._chain_ok(B):
+            self._decode_layers_chain(st, attend)
+        else:
+            self._layers(st, B, attend)
         c.gemm(st.xn, self.lm_head, st.logits, epilogue=EPI_NONE, t=B)
         if sample and self.peer is not None:
             # vocab-parallel greedy over peer memory: no collective call, graph-capturable

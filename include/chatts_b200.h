@@ -218,6 +218,35 @@ int cts_peer_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab_sh
                             int* step_ptr, int* cur_ids, int* positions, int* seq_lens, int* slot_map, const int* page_table,
                             int max_pages, int page_size, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Decode "chain": everything between two attention calls of a decode step (t <= 32 tokens) in ONE persistent,
+ * cooperatively launched kernel (modeling_qwen2.py:269-310 minus the attention):
+ *   phase 0 o_proj GEMM | 1 residual+RMSNorm(ln_post) | 2 gate_up GEMM | 3 SwiGLU | 4 down GEMM |
+ *   phase 5 residual+RMSNorm(ln_next) | 6 QKV GEMM of the next layer | 7 bias+(q/k norm)+RoPE+paged KV write
+ * Phases [phase_begin, phase_end) run, separated by grid barriers; the TMA producer pre-loads the weight tiles of the
+ * next GEMM phase before each barrier so the HBM stream never stops.  Same arithmetic / rounding points as cts_gemm +
+ * the cts_reduce_* / cts_qkv_rope_cache kernels it replaces on the decode path.
+ *   split[4]: split-K factors of {o_proj, gate_up, down, qkv}; tiles*split of every phase must fit one co-resident wave.
+ *   ws: fp32 >= max(split*t*n) floats; ssq: fp32 [t*8]; sync: int32[2], zero-filled once (self-resetting).
+ *   wgu is the INTERLEAVED gate/up weight (see CTS_EPI_SWIGLU_IL).  norm5_has_partial = 0: phase 5 is a plain RMSNorm of h
+ *   (the "head" chain embed -> norm -> QKV -> RoPE of layer 0).
+ */
+typedef struct {
+  int t, hidden, inter, nh, nkv, head_dim;
+  int phase_begin, phase_end, norm5_has_partial, dtype;
+  int split[4];
+  const void* wo; const void* wgu; const void* wd; const void* wqkv;     /* weights of the phases that run (else NULL) */
+  const void* ao;                                                         /* [t, nh*head_dim] attention output      */
+  void* h; void* xn; void* act;                                           /* [t,hidden] residual, [t,hidden], [t,inter] */
+  const void* ln_post; const void* ln_next; float eps;
+  const void* bqkv; const void* q_norm_w; const void* k_norm_w;
+  const int* positions; const void* cos_tab; const void* sin_tab; const int* slot_map;
+  void* q_out; void* k_cache; void* v_cache; int page_size;
+  float* ws; float* ssq; int* sync;
+} cts_chain_args;
+
+int cts_decode_chain(cts_ctx* ctx, const cts_chain_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
