@@ -482,11 +482,23 @@ int launch_chain(cts_ctx* ctx, const cts_chain_args* a, cudaStream_t st) {
 
   auto kern = decode_chain_kernel<T, BN>;
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  CTS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  // co-resident capacity: the occupancy API, cross-checked against the plain resource arithmetic (227 KB of shared memory
+  // and 64 K registers per SM).  All CTAs must be resident at once: the phases are separated by grid barriers.
+  int per_sm_api = 0;
+  CTS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_api, kern, kThreads, smem));
+  cudaFuncAttributes fa;
+  CTS_CUDA(ctx, cudaFuncGetAttributes(&fa, kern));
+  const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * kThreads;
+  int per_sm_res = (int)((227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+  if (regs_per_cta > 0 && 65536 / regs_per_cta < per_sm_res) per_sm_res = 65536 / regs_per_cta;
+  if (per_sm_res > 32) per_sm_res = 32;
+  const bool cooperative = per_sm_api >= per_sm_res;            // otherwise: plain launch on the resource arithmetic
+  const int per_sm = per_sm_api > per_sm_res ? per_sm_api : per_sm_res;
   const int capacity = per_sm * ctx->sm_count;
   if (max_units > capacity)
-    return cts_set_error(ctx, CTS_ERR_UNSUPPORTED, "cts_decode_chain: %d work units exceed the co-resident capacity %d", max_units, capacity);
+    return cts_set_error(ctx, CTS_ERR_UNSUPPORTED, "cts_decode_chain: %d work units exceed the co-resident capacity %d (api %d, resources %d per SM)",
+                         max_units, capacity, per_sm_api, per_sm_res);
   const int grid = max_units;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -497,7 +509,7 @@ int launch_chain(cts_ctx* ctx, const cts_chain_args* a, cudaStream_t st) {
   attr[0].id = cudaLaunchAttributeCooperative;
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = cooperative ? 1 : 0;
   CTS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, tm_wo, tm_wgu, tm_wd, tm_wqkv, tm_ao, tm_xn, tm_act, p));
   return CTS_OK;
 }
