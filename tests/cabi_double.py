@@ -1,0 +1,137 @@
+"""TEST INFRASTRUCTURE ONLY: a torch/CPU test double of the C-ABI binding (`chatts_b200._cabi.Context`).
+
+It lets the `-m "not gpu"` suite drive the HOST logic of the package (prefill / decode orchestration, paged-KV
+bookkeeping, generate(), the vLLM-shaped front end) on a machine without a GPU: every entry point of the binding is
+restated with plain torch ops in the same rounding discipline (fp32 accumulate, result rounded to the model dtype).
+It is injected by the `cabi_double` fixture (monkeypatch of `_cabi.get_context`); the package never imports it and has
+no CPU fallback of its own -- without the fixture `get_context()` raises when the CUDA library or the GPU is missing.
+"""
+import torch
+import torch.nn.functional as F
+
+
+class TorchDouble:
+    arch = "test-double"
+    launches = 0
+
+    def __init__(self, split=1):
+        self.split = split
+
+    def ts_patch_count(self, x, nf, p):
+        n = x.shape[0]; xr = x.reshape(n, -1, nf)
+        valid = xr[:, :, -1].long().sum(1).int(); cnt = (valid + p - 1) // p
+        off = torch.cat([torch.zeros(1, dtype=torch.int32), cnt.cumsum(0).int()]); mx = valid.max().reshape(1).int() if n else torch.zeros(1, dtype=torch.int32)
+        return valid, cnt.int(), off, mx
+    def ts_patchify(self, x, nf, p, mode, pos_table, emb, maxseq, valid, off, mx, max_patches, rows):
+        n = x.shape[0]; xr = x.reshape(n, -1, nf)
+        for s in range(n):
+            vl = int(valid[s]); cnt = (vl + p - 1) // p
+            for pi in range(cnt):
+                r = int(off[s]) + pi
+                for j in range(p):
+                    pt = pi * p + j; src = pt if pt < vl else vl - 1
+                    rows[r, j] = xr[s, src, 0]
+                    if mode == 1:
+                        idx = pt if pt < vl else maxseq
+                        rows[r, p + j * emb: p + (j + 1) * emb] = pos_table[idx]
+    def suggest_split(self, n, k, t, dual=False): return self.split if k >= 64 * self.split else 1
+    def gemm(self, x, w, out, *, w2=None, bias=None, residual=None, row_map=None, epilogue=0, split_k=1, t=None, splitk_ws=None, tile_counters=None):
+        t = x.shape[0] if t is None else t
+        xx = x[:t].float(); acc = xx @ w.float().T
+        dt = x.dtype
+        if epilogue == 6:
+            a2 = acc.view(t, -1, 2, 64); g = a2[:, :, 0].reshape(t, -1).to(dt); u = a2[:, :, 1].reshape(t, -1).to(dt)
+            out[:t] = (F.silu(g.float()).to(dt).float() * u.float()).to(dt); return
+        if epilogue == 5:
+            out.view(-1)[: t * w.shape[0]].view(t, w.shape[0]).copy_(acc); return
+        if epilogue == 3:
+            K = w.shape[1]; kb = (K + 63) // 64
+            o = out.view(-1)[: split_k * t * w.shape[0]].view(split_k, t, w.shape[0])
+            for s in range(split_k):
+                a, b = kb * s // split_k * 64, kb * (s + 1) // split_k * 64
+                o[s] = xx[:, a:b] @ w.float()[:, a:b].T
+            return
+        if epilogue == 2:
+            g = acc.to(dt); u = (xx @ w2.float().T).to(dt)
+            r = (F.silu(g.float()).to(dt).float() * u.float()).to(dt)
+        else:
+            r = acc + (bias.float() if bias is not None else 0)
+            if epilogue == 1: r = F.gelu(r.to(dt).float())
+            if epilogue == 4: r = r.to(dt).float() + residual[:t].float()
+            r = r.to(dt)
+        if row_map is not None:
+            for i in range(t):
+                if row_map[i] >= 0: out[int(row_map[i])] = r[i]
+        else:
+            out[:t] = r
+    def reduce_bias_act(self, part, s, t, n, bias, act, out, row_map=None):
+        r = part.view(-1)[: s * t * n].view(s, t, n).sum(0) + (bias.float() if bias is not None else 0)
+        dt = out.dtype
+        if act == 1: r = F.gelu(r.to(dt).float())
+        r = r.to(dt)
+        if row_map is not None:
+            for i in range(t):
+                if row_map[i] >= 0: out[int(row_map[i])] = r[i]
+        else: out[:t] = r
+    def reduce_residual_rmsnorm(self, part, s, rin, rout, w, eps, nout, t=None):
+        t = rin.shape[0] if t is None else t; h = rin.shape[-1]; dt = rin.dtype
+        x = rin[:t]
+        if s:
+            p = part.view(-1)[: s * t * h].view(s, t, h).sum(0).to(dt)
+            x = (x.float() + p.float()).to(dt); rout[:t] = x
+        if nout is not None:
+            xf = x.float(); xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+            nout[:t] = w * xf.to(dt)
+    def reduce_swiglu(self, part, s, t, inter, out, interleaved=False):
+        p = part.view(-1)[: s * t * 2 * inter].view(s, t, 2 * inter).sum(0); dt = out.dtype
+        if interleaved:
+            pp = p.view(t, -1, 2, 64); g, u = pp[:, :, 0].reshape(t, inter), pp[:, :, 1].reshape(t, inter)
+        else:
+            g, u = p[:, :inter], p[:, inter:]
+        out[:t] = (F.silu(g.to(dt).float()).to(dt).float() * u.to(dt).float()).to(dt)
+    def qkv_rope_cache(self, src, partial, s, bias, pos, cos, sin, slot, q_out, kc, vc, k_lin, v_lin, t, nh, nkv, d, page, q_norm_w=None, k_norm_w=None, norm_eps=1e-6):
+        W = (nh + 2 * nkv) * d; dt = q_out.dtype
+        if partial:
+            x = src.view(-1)[: s * t * W].view(s, t, W).sum(0) + (bias.float() if bias is not None else 0); x = x.to(dt)
+        else: x = src[:t]
+        q = x[:, : nh * d].view(t, nh, d); k = x[:, nh * d:(nh + nkv) * d].view(t, nkv, d); v = x[:, (nh + nkv) * d:].view(t, nkv, d)
+        if q_norm_w is not None:
+            def hn(a, w):
+                af = a.float()
+                return w * (af * torch.rsqrt(af.pow(2).mean(-1, keepdim=True) + norm_eps)).to(dt)
+            q, k = hn(q, q_norm_w), hn(k, k_norm_w)
+        c = torch.cat([cos[pos[:t].long()]] * 2, -1)[:, None]; sn = torch.cat([sin[pos[:t].long()]] * 2, -1)[:, None]
+        rot = lambda a: torch.cat((-a[..., d // 2:], a[..., : d // 2]), -1)
+        q = q * c + rot(q) * sn; k = k * c + rot(k) * sn
+        q_out[:t] = q.reshape(t, -1)
+        if k_lin is not None: k_lin[:t] = k.reshape(t, -1); v_lin[:t] = v.reshape(t, -1)
+        for i in range(t):
+            sl = int(slot[i])
+            if sl >= 0: kc[sl // page, :, sl % page] = k[i]; vc[sl // page, :, sl % page] = v[i]
+    def embed_gather(self, table, ids, out, t=None):
+        t = ids.shape[0] if t is None else t
+        for i in range(t):
+            if ids[i] >= 0: out[i] = table[int(ids[i])]
+    def _attn(self, q, k, v, nrep, p0):
+        T, nh, d = q.shape; S = k.shape[0]
+        kk = k.repeat_interleave(nrep, 1).float(); vv = v.repeat_interleave(nrep, 1).float()
+        w = torch.einsum("thd,shd->hts", q.float(), kk) * d ** -0.5
+        m = torch.arange(S)[None] > (torch.arange(T)[:, None] + p0)
+        w = w.masked_fill(m[None], -1e30).softmax(-1)
+        return torch.einsum("hts,shd->thd", w, vv).reshape(T, nh * d)
+    def attn_prefill(self, q, k, v, cu, B, maxlen, nh, nkv, d, scale, out):
+        for b in range(B):
+            a, e = int(cu[b]), int(cu[b + 1])
+            out[a:e] = self._attn(q[a:e].view(-1, nh, d), k[a:e].view(-1, nkv, d), v[a:e].view(-1, nkv, d), nh // nkv, 0).to(out.dtype)
+    def attn_decode_workspace_floats(self, *a): return 8
+    def attn_decode(self, q, kc, vc, pt, sl, B, nh, nkv, d, page, scale, splits, ws, out):
+        for b in range(B):
+            n = int(sl[b]); pages = pt[b, : (n + page - 1) // page].long()
+            kk = kc[pages].permute(0, 2, 1, 3).reshape(-1, nkv, d)[:n]; vv = vc[pages].permute(0, 2, 1, 3).reshape(-1, nkv, d)[:n]
+            out[b] = self._attn(q[b:b + 1].view(1, nh, d), kk, vv, nh // nkv, n - 1).to(out.dtype)[0]
+    def greedy_advance(self, logits, B, out_tokens, step_ptr, cur, pos, sl, slot, pt, page):
+        tok = logits[:B].float().argmax(-1).int(); st = int(step_ptr[0])
+        out_tokens[:B, st] = tok; cur[:B] = tok; pos[:B] += 1; sl[:B] += 1
+        for b in range(B):
+            slot[b] = pt[b, int(pos[b]) // page] * page + int(pos[b]) % page
+        step_ptr += 1

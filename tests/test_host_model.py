@@ -1,0 +1,128 @@
+"""Host logic of the drop-in surfaces on CPU: the package driven through the torch test double of the C-ABI
+(tests/cabi_double.py), checked against the oracle.  Covers what the GPU tests cannot see without a device: prompt
+expansion / merge order (chatts_vllm.py:538-574), left padding, paged-KV bookkeeping across generate() calls, split-K
+workspace plumbing, sampling arguments and the vLLM request shape (demo/demo_vllm.py:18-63).
+"""
+import numpy as np
+import pytest
+import torch
+
+from chatts_b200 import ChatTSConfig, ChatTSProcessor, SimpleTokenizer
+from chatts_b200.weights import synthetic_state_dict
+from oracle import decoder as od
+from oracle import merge as om
+from oracle import ts_encoder as ote
+
+DT = torch.bfloat16
+
+
+def _series():
+    x = np.arange(256)
+    a = np.sin(x / 10) * 5.0
+    a[100:] -= 10.0
+    return a, (x * 0.05)[:100]
+
+
+def _build(cabi_double, split=1, qwen3=False, **kw):
+    from chatts_b200.model import ChatTSForCausalLM
+
+    cabi_double.split = split
+    cfg = ChatTSConfig.tiny()
+    if qwen3:
+        cfg.qk_norm, cfg.attention_bias = True, False
+    sd = synthetic_state_dict(cfg, seed=1234, device="cpu", dtype=DT, std=0.05)
+    model = ChatTSForCausalLM(cfg, sd, device="cpu", dtype=DT, max_batch=8, max_seq_len=512, page_size=16,
+                              use_cuda_graph=False, **kw)
+    proc = ChatTSProcessor(SimpleTokenizer(cfg.ts_token_start_index, cfg.pad_token_id, cfg.eos_token_id), cfg)
+    return cfg, sd, model, proc
+
+
+def _oracle_embeds(cfg, sd, enc):
+    ts_w = {k[len("ts_encoder."):]: v for k, v in sd.items() if k.startswith("ts_encoder.")}
+    feats, pc = ote.forward(enc["timeseries"].to(DT), cfg.ts, ts_w)
+    return om.hf_merge(enc["input_ids"], enc["attention_mask"], sd["model.embed_tokens.weight"], feats, pc.tolist(),
+                       cfg.ts_token_start_index)
+
+
+PROMPTS = ["A <ts><ts/> and B <ts><ts/> ?", "Only text, no series, but a longer prompt to left-pad the other one"]
+
+
+@pytest.mark.parametrize("split,qwen3", [(1, False), (3, False), (2, True)])
+def test_forward_matches_oracle_through_double(cabi_double, split, qwen3):
+    cfg, sd, model, proc = _build(cabi_double, split, qwen3)
+    enc = proc(text=PROMPTS, timeseries=list(_series()), padding=True, return_tensors="pt")
+    out = model.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"], logits_to_keep=0).logits
+    for b, e in enumerate(_oracle_embeds(cfg, sd, enc)):
+        ref = od.logits(od.forward_hidden(e, sd, cfg.to_dict(), od.State(cfg.num_hidden_layers)), sd).float()
+        assert out[b].shape == ref.shape                      # expanded length = text + patch rows of this sample
+        err = float((out[b].float() - ref).abs().max() / ref.abs().max())
+        assert err < 2.5e-2, err                               # two bf16 evaluations with different accumulation order
+
+
+def test_generate_bookkeeping_and_teacher_forced_tokens(cabi_double):
+    cfg, sd, model, proc = _build(cabi_double, split=2)
+    enc = proc(text=PROMPTS, timeseries=list(_series()), padding=True, return_tensors="pt")
+    S = enc["input_ids"].shape[1]
+    new = 12
+    ids = model.generate(**enc, max_new_tokens=new, ignore_eos=True)
+    assert ids.shape == (2, S + new) and torch.equal(ids[:, :S], enc["input_ids"])
+    assert len(model.pool.free) == model.pool.num_pages        # every KV page returned
+    # teacher-forced: feed OUR tokens to the oracle; wherever we differ from its argmax the two logits must be a near tie
+    for b, e in enumerate(_oracle_embeds(cfg, sd, enc)):
+        st = od.State(cfg.num_hidden_layers)
+        lg = od.logits(od.forward_hidden(e, sd, cfg.to_dict(), st)[-1:], sd)[0].float()
+        exact = 0
+        for t in range(new):
+            tok = int(ids[b, S + t])
+            top = float(lg.max())
+            assert top - float(lg[tok]) <= 3e-2 * max(1.0, abs(top)), (b, t)
+            exact += int(int(lg.argmax()) == tok)
+            nxt = sd["model.embed_tokens.weight"][tok][None, :]
+            lg = od.logits(od.forward_hidden(nxt, sd, cfg.to_dict(), st), sd)[0].float()
+        assert exact >= new - 2
+    # a second call reuses the pool and gives the same answer (no state leaks between calls)
+    again = model.generate(**enc, max_new_tokens=new, ignore_eos=True)
+    assert torch.equal(again, ids)
+
+
+def test_generate_arguments(cabi_double):
+    cfg, sd, model, proc = _build(cabi_double)
+    enc = proc(text=PROMPTS, timeseries=list(_series()), padding=True, return_tensors="pt")
+    S = enc["input_ids"].shape[1]
+    greedy = model.generate(**enc, max_new_tokens=6, ignore_eos=True)
+    # max_length counts the prompt (inference_tsmllm_deepspeed.py:101); synced_gpus is accepted and ignored
+    ml = model.generate(**enc, max_length=S + 6, ignore_eos=True, synced_gpus=False)
+    assert torch.equal(ml, greedy)
+    # EOS stop: declare the 3rd generated token of sample 0 to be EOS -> that row is padded after it
+    eos = int(greedy[0, S + 2])
+    stopped = model.generate(**enc, max_new_tokens=6, eos_token_id=eos)
+    row = stopped[0, S:].tolist()
+    first = row.index(eos)
+    assert first <= 2 and all(t == cfg.pad_token_id or t == eos for t in row[first + 1:])
+    # sampling: seeded -> reproducible; temperature/top_p accepted (inference_tsmllm_deepspeed.py:103-105)
+    s1 = model.generate(**enc, max_new_tokens=5, do_sample=True, temperature=0.7, top_p=0.9, ignore_eos=True, seed=7)
+    s2 = model.generate(**enc, max_new_tokens=5, do_sample=True, temperature=0.7, top_p=0.9, ignore_eos=True, seed=7)
+    assert s1.shape == (2, S + 5) and torch.equal(s1, s2)
+    assert len(model.pool.free) == model.pool.num_pages
+
+
+def test_placeholder_mismatch_raises(cabi_double):
+    cfg, sd, model, proc = _build(cabi_double)
+    with pytest.raises(AssertionError):                        # encoding_utils.py:58,68
+        proc(text=["one <ts><ts/> only"], timeseries=list(_series()), padding=True, return_tensors="pt")
+
+
+def test_vllm_request_shape(cabi_double):
+    from chatts_b200.vllm_compat import LLM, SamplingParams
+
+    cfg, sd, model, proc = _build(cabi_double)
+    a, b = _series()
+    llm = LLM(model=model)
+    reqs = [{"prompt": "two: <ts><ts/> <ts><ts/>", "multi_modal_data": {"timeseries": [a, b.tolist()]}},
+            {"prompt": "none"}]
+    outs = llm.generate(reqs, SamplingParams(max_tokens=6, ignore_eos=True))
+    assert [len(o.outputs[0].token_ids) for o in outs] == [6, 6]
+    assert all(isinstance(o.outputs[0].text, str) for o in outs)
+    with pytest.raises(TypeError):                             # chatts_vllm.py:277-279
+        llm.generate([{"prompt": "x <ts><ts/>", "multi_modal_data": {"timeseries": ["not a series"]}}],
+                     SamplingParams(max_tokens=2))
