@@ -24,7 +24,12 @@ SYMBOLS = [
     "cts_embed_gather", "cts_attn_prefill", "cts_attn_decode_workspace_floats", "cts_attn_decode",
     "cts_greedy_advance", "cts_ipc_alloc", "cts_ipc_open", "cts_ipc_close", "cts_ipc_free",
     "cts_peer_allreduce_residual_rmsnorm", "cts_peer_greedy_advance", "cts_decode_chain",
+    # A9: LoRA fine-tune step
+    "cts_attn_prefill_lse", "cts_attn_bwd", "cts_swiglu", "cts_swiglu_bwd", "cts_rmsnorm_bwd", "cts_qkv_rope_bwd",
+    "cts_ce_loss_grad", "cts_gather_rows", "cts_lora_wgrad", "cts_adamw", "cts_grad_norm_ws_floats", "cts_grad_norm_clip",
+    "cts_lora_pack",
 ]
+PACK_DESC_LONGS = 12
 
 
 class CtsError(RuntimeError):
@@ -94,6 +99,24 @@ def load_library():
     lib.cts_decode_chain.restype = i
     lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cts_peer_greedy_advance.restype = i
+    # ---- A9: LoRA fine-tune step
+    lib.cts_attn_prefill_lse.argtypes = [vp, vp, vp, vp, vp, i, i, ll, i, i, i, f, vp, vp, i, vp]
+    lib.cts_attn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, ll, i, i, i, f, vp, vp, vp, vp, i, vp]
+    lib.cts_swiglu.argtypes = [vp, vp, ll, ll, i, vp, i, vp]
+    lib.cts_swiglu_bwd.argtypes = [vp, vp, vp, ll, ll, i, vp, i, vp]
+    lib.cts_rmsnorm_bwd.argtypes = [vp, vp, vp, vp, f, vp, vp, ll, ll, i, vp]
+    lib.cts_qkv_rope_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f, vp, ll, i, i, i, i, vp]
+    lib.cts_ce_loss_grad.argtypes = [vp, vp, ll, vp, ll, ll, f, vp, vp, i, i, vp]
+    lib.cts_gather_rows.argtypes = [vp, vp, vp, ll, ll, vp, i, vp]
+    lib.cts_lora_wgrad.argtypes = [vp, vp, ll, ll, i, ll, vp, ll, ll, i, ll, f, vp, ll, ll, i, vp]
+    lib.cts_adamw.argtypes = [vp, vp, vp, vp, vp, ll, f, f, f, f, f, i, vp, vp]
+    lib.cts_grad_norm_ws_floats.argtypes = []
+    lib.cts_grad_norm_ws_floats.restype = ll
+    lib.cts_grad_norm_clip.argtypes = [vp, vp, ll, f, vp, vp, vp]
+    lib.cts_lora_pack.argtypes = [vp, vp, vp, i, ll, vp, i, vp]
+    for name in ("cts_attn_prefill_lse", "cts_attn_bwd", "cts_swiglu", "cts_swiglu_bwd", "cts_rmsnorm_bwd", "cts_qkv_rope_bwd",
+                 "cts_ce_loss_grad", "cts_gather_rows", "cts_lora_wgrad", "cts_adamw", "cts_grad_norm_clip", "cts_lora_pack"):
+        getattr(lib, name).restype = i
     for name in ("cts_ipc_alloc", "cts_ipc_open", "cts_ipc_close", "cts_ipc_free", "cts_peer_allreduce_residual_rmsnorm"):
         getattr(lib, name).restype = i
     for name in ("cts_ts_patch_count", "cts_ts_patchify", "cts_gemm", "cts_gemm_suggest_split", "cts_reduce_bias_act",
@@ -238,6 +261,58 @@ class Context:
                                               page_table.shape[1] if page_table is not None else 0, page_size,
                                               dtype_code(logits.dtype), _stream()))
 
+    # ------------------------------------------------------------------ A9: LoRA fine-tune step
+    def attn_prefill_lse(self, q, k, v, cu_seqlens, batch, max_seqlen, nh, nkv, head_dim, scale, out, lse):
+        self._chk(self.lib.cts_attn_prefill_lse(self.h, _p(q), _p(k), _p(v), _p(cu_seqlens), batch, max_seqlen, q.shape[0], nh, nkv,
+                                                head_dim, float(scale), _p(out), _p(lse), dtype_code(q.dtype), _stream()))
+
+    def attn_bwd(self, q, k, v, out, dout, lse, cu_seqlens, batch, max_seqlen, nh, nkv, head_dim, scale, delta_ws, dq, dk, dv):
+        self._chk(self.lib.cts_attn_bwd(self.h, _p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), _p(cu_seqlens), batch, max_seqlen,
+                                        q.shape[0], nh, nkv, head_dim, float(scale), _p(delta_ws), _p(dq), _p(dk), _p(dv),
+                                        dtype_code(q.dtype), _stream()), 3)
+
+    def swiglu(self, gu, t, inter, out, interleaved=True):
+        self._chk(self.lib.cts_swiglu(self.h, _p(gu), t, inter, int(interleaved), _p(out), dtype_code(gu.dtype), _stream()))
+
+    def swiglu_bwd(self, gu, dact, t, inter, dgu, interleaved=True):
+        self._chk(self.lib.cts_swiglu_bwd(self.h, _p(gu), _p(dact), t, inter, int(interleaved), _p(dgu), dtype_code(gu.dtype),
+                                          _stream()))
+
+    def rmsnorm_bwd(self, dy, x, w, eps, dres_in, dx_out, t=None):
+        t = x.shape[0] if t is None else t
+        self._chk(self.lib.cts_rmsnorm_bwd(self.h, _p(dy), _p(x), _p(w), float(eps), _p(dres_in), _p(dx_out), t, x.shape[-1],
+                                           dtype_code(x.dtype), _stream()))
+
+    def qkv_rope_bwd(self, dq, dk, dv, qkv, positions, cos, sin, q_norm_w, k_norm_w, norm_eps, dqkv, t, nh, nkv, head_dim):
+        self._chk(self.lib.cts_qkv_rope_bwd(self.h, _p(dq), _p(dk), _p(dv), _p(qkv), _p(positions), _p(cos), _p(sin), _p(q_norm_w),
+                                            _p(k_norm_w), float(norm_eps), _p(dqkv), t, nh, nkv, head_dim, dtype_code(dq.dtype),
+                                            _stream()))
+
+    def ce_loss_grad(self, logits, targets, n_rows, grad_scale, row_loss, loss_out, accumulate=False):
+        self._chk(self.lib.cts_ce_loss_grad(self.h, _p(logits), logits.stride(0), _p(targets), n_rows, logits.shape[1],
+                                            float(grad_scale), _p(row_loss), _p(loss_out), int(accumulate),
+                                            dtype_code(logits.dtype), _stream()), 2)
+
+    def gather_rows(self, src, idx, n_out, dst):
+        self._chk(self.lib.cts_gather_rows(self.h, _p(src), _p(idx), n_out, src.shape[-1], _p(dst), dtype_code(src.dtype), _stream()))
+
+    def lora_wgrad(self, p, p_col0, p_il, m, q, q_col0, r, t, scale, out, so_m, so_r):
+        """out[i*so_m + j*so_r] += scale * sum_t p[t, col(i)] * q[t, q_col0 + j]   (out: fp32 view into the gradient arena)"""
+        self._chk(self.lib.cts_lora_wgrad(self.h, _p(p), p.stride(0), p_col0, int(p_il), m, _p(q), q.stride(0), q_col0, r, t,
+                                          float(scale), _p(out), so_m, so_r, dtype_code(p.dtype), _stream()))
+
+    def adamw(self, p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None):
+        self._chk(self.lib.cts_adamw(self.h, _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+                                     float(weight_decay), int(step), _p(grad_scale), _stream()))
+
+    def grad_norm_ws_floats(self):
+        return int(self.lib.cts_grad_norm_ws_floats())
+
+    def grad_norm_clip(self, g, max_norm, ws, out):
+        self._chk(self.lib.cts_grad_norm_clip(self.h, _p(g), g.numel(), float(max_norm), _p(ws), _p(out), _stream()), 2)
+
+    def lora_pack(self, master, desc, n_desc, max_elems, work):
+        self._chk(self.lib.cts_lora_pack(self.h, _p(master), _p(desc), n_desc, max_elems, _p(work), dtype_code(work.dtype), _stream()))
 
     # ------------------------------------------------------------------ tensor parallel (peer memory)
     def ipc_alloc(self, nbytes):

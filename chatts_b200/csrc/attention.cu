@@ -63,10 +63,11 @@ __device__ __forceinline__ void pf_load_tile(T* dst, const T* __restrict__ src, 
   }
 }
 
-template <typename T, int HD>
+// LSE = true (the training forward, cts_attn_prefill_lse) adds one store per query row: lse[token][head] = log sum_j exp(scale s_j).
+template <typename T, int HD, bool LSE>
 __global__ void __launch_bounds__(kPfThreads)
 attn_prefill_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
-                    const int* __restrict__ cu_seqlens, int nh, int nkv, float scale, T* __restrict__ out) {
+                    const int* __restrict__ cu_seqlens, int nh, int nkv, float scale, T* __restrict__ out, float* __restrict__ lse) {
   using SM = PfSmem<HD>;
   constexpr int LD = SM::LD, SLD = SM::SLD;
   extern __shared__ __align__(128) uint8_t pf_smem[];
@@ -227,6 +228,9 @@ attn_prefill_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
       for (int e = 0; e < 8; ++e) f[e] = o_w[r_loc * (HD + 8) + col + e] * inv;
       *reinterpret_cast<uint4*>(o_g + col) = pack8<T>(f);
     }
+    if constexpr (LSE) {
+      if (c_half == 0) lse[((long long)seq0 + row_g) * nh + head] = l_run > 0.f ? m_run * scale + logf(l_run) : -INFINITY;
+    }
   }
 }
 
@@ -261,11 +265,11 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 // Pipeline (per CTA; two CTAs share an SM): K and V are single-buffered with independent full/empty barriers, S is
 // double-buffered in TMEM (2 x 64 columns) and the MMA warp issues QK^T of tile i BEFORE P.V of tile i-1, so the softmax
 // warps work on tile i while the tensor core runs P.V(i-1); P is single-buffered behind a p_free barrier.
-template <typename T>
+template <typename T, bool LSE>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                         const __grid_constant__ CUtensorMap tm_v, const int* __restrict__ cu_seqlens, int nh, int nkv,
-                        float scale, T* __restrict__ out) {
+                        float scale, T* __restrict__ out, float* __restrict__ lse) {
   constexpr int HD = 128;
   extern __shared__ uint8_t tc_raw[];
   __shared__ uint64_t q_bar, k_full, k_empty, v_full, v_empty, s_full[2], s_free[2], p_full, p_free, o_done;
@@ -446,6 +450,9 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           *reinterpret_cast<uint4*>(o_g + c) = pack8<T>(f);
           *reinterpret_cast<uint4*>(o_g + c + 8) = pack8<T>(f + 8);
         }
+      }
+      if constexpr (LSE) {
+        if (qi < len) lse[((long long)seq0 + qi) * nh + head] = l_run > 0.f ? m_run * scale + logf(l_run) : -INFINITY;
       }
     }
   }
@@ -713,9 +720,9 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
 
 }  // namespace
 
-extern "C" int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, const void* v, const int* cu_seqlens, int batch,
-                                int max_seqlen, long long total_tokens_hint, int nh, int nkv, int head_dim, float scale, void* out,
-                                int dtype, void* stream) {
+static int attn_prefill_impl(cts_ctx* ctx, const void* q, const void* k, const void* v, const int* cu_seqlens, int batch,
+                             int max_seqlen, long long total_tokens_hint, int nh, int nkv, int head_dim, float scale, void* out,
+                             float* lse, int dtype, void* stream) {
   if (!ctx) return CTS_ERR_BAD_ARG;
   CTS_CHECK_ARG(ctx, q && k && v && cu_seqlens && out, "null pointer");
   CTS_CHECK_ARG(ctx, nh > 0 && nkv > 0 && nh % nkv == 0, "nh must be a positive multiple of nkv");
@@ -736,34 +743,56 @@ extern "C" int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, cons
     if (rc) return rc;
     dim3 g5((unsigned)((max_seqlen + kTcQ - 1) / kTcQ), (unsigned)nh, (unsigned)batch);
     const size_t smem5 = (size_t)kTcSmem + 1024;
+#define TC5_LAUNCH(TT, LSEV)                                                                                 \
+  {                                                                                                          \
+    auto kern = attn_prefill_tc5_kernel<TT, LSEV>;                                                           \
+    CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));      \
+    CTS_CUDA(ctx, launch_pdl(kern, g5, dim3(kTcThreads), smem5, st, 1, tm_q, tm_k, tm_v, cu_seqlens, nh, nkv, scale, (TT*)out, lse)); \
+  }
     if (dtype == CTS_BF16) {
-      auto kern = attn_prefill_tc5_kernel<__nv_bfloat16>;
-      CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-      CTS_CUDA(ctx, launch_pdl(kern, g5, dim3(kTcThreads), smem5, st, 1, tm_q, tm_k, tm_v, cu_seqlens, nh, nkv, scale, (__nv_bfloat16*)out));
+      if (lse) TC5_LAUNCH(__nv_bfloat16, true) else TC5_LAUNCH(__nv_bfloat16, false)
     } else {
-      auto kern = attn_prefill_tc5_kernel<__half>;
-      CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-      CTS_CUDA(ctx, launch_pdl(kern, g5, dim3(kTcThreads), smem5, st, 1, tm_q, tm_k, tm_v, cu_seqlens, nh, nkv, scale, (__half*)out));
+      if (lse) TC5_LAUNCH(__half, true) else TC5_LAUNCH(__half, false)
     }
+#undef TC5_LAUNCH
     return CTS_OK;
   }
   dim3 grid((unsigned)((max_seqlen + kPfQ - 1) / kPfQ), (unsigned)nh, (unsigned)batch);
-#define PF_LAUNCH(TT, HDV)                                                                                   \
+#define PF_LAUNCH2(TT, HDV, LSEV)                                                                            \
   {                                                                                                          \
-    auto kern = attn_prefill_kernel<TT, HDV>;                                                                \
+    auto kern = attn_prefill_kernel<TT, HDV, LSEV>;                                                          \
     const size_t smem = PfSmem<HDV>::total;                                                                  \
     CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
     CTS_CUDA(ctx, launch_pdl(kern, grid, dim3(kPfThreads), smem, st, 1, (const TT*)q, (const TT*)k, (const TT*)v, cu_seqlens, nh, nkv, \
-                             scale, (TT*)out));                                                              \
+                             scale, (TT*)out, lse));                                                         \
   }
+#define PF_LAUNCH(TT, HDV) { if (lse) PF_LAUNCH2(TT, HDV, true) else PF_LAUNCH2(TT, HDV, false) }
   if (dtype == CTS_BF16) {
     if (head_dim == 128) PF_LAUNCH(__nv_bfloat16, 128) else PF_LAUNCH(__nv_bfloat16, 64)
   } else {
     if (head_dim == 128) PF_LAUNCH(__half, 128) else PF_LAUNCH(__half, 64)
   }
 #undef PF_LAUNCH
+#undef PF_LAUNCH2
   CTS_LAUNCH_CHECK(ctx);
   return CTS_OK;
+}
+
+extern "C" int cts_attn_prefill(cts_ctx* ctx, const void* q, const void* k, const void* v, const int* cu_seqlens, int batch,
+                                int max_seqlen, long long total_tokens_hint, int nh, int nkv, int head_dim, float scale, void* out,
+                                int dtype, void* stream) {
+  return attn_prefill_impl(ctx, q, k, v, cu_seqlens, batch, max_seqlen, total_tokens_hint, nh, nkv, head_dim, scale, out, nullptr,
+                           dtype, stream);
+}
+
+// training forward: same kernels + the softmax statistics the backward needs (csrc/attention_bwd.cu)
+extern "C" int cts_attn_prefill_lse(cts_ctx* ctx, const void* q, const void* k, const void* v, const int* cu_seqlens, int batch,
+                                    int max_seqlen, long long total_tokens_hint, int nh, int nkv, int head_dim, float scale,
+                                    void* out, float* lse, int dtype, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, lse != nullptr, "null lse");
+  return attn_prefill_impl(ctx, q, k, v, cu_seqlens, batch, max_seqlen, total_tokens_hint, nh, nkv, head_dim, scale, out, lse, dtype,
+                           stream);
 }
 
 extern "C" long long cts_attn_decode_workspace_floats(int batch, int nh, int head_dim, int num_splits) {

@@ -96,6 +96,26 @@ class ChatTSProcessor:
             prefixes.append(render_prefix(ts, meta))
         return encs, prefixes
 
+    @staticmethod
+    def render_text(text, prefixes):
+        """Replace the i-th ``<ts><ts/>`` of ``text`` by the i-th rendered prefix (which ends in ``<ts><ts/>`` itself)."""
+        parts = text.split(TS_PLACEHOLDER)
+        assert len(parts) - 1 == len(prefixes), "time series / <ts><ts/> placeholder count mismatch"
+        s = parts[0]
+        for j, pre in enumerate(prefixes):
+            s += pre + parts[j + 1]
+        return s
+
+    def pad_series(self, encs):
+        """encoding_utils.py:78-84: zero-padded [N, 2 Lmax, 1] tensor of the encoded series."""
+        if not encs:
+            return torch.zeros(0, 0, 1, dtype=self.dtype)
+        max_len = max(e.shape[0] for e in encs)
+        arr = np.zeros((len(encs), max_len, 1), dtype=np.float64)
+        for i, e in enumerate(encs):
+            arr[i, : e.shape[0]] = e
+        return torch.from_numpy(arr).to(self.dtype)
+
     def __call__(self, text, timeseries=None, padding=True, return_tensors="pt", vllm_flag=False, **kw):
         if isinstance(text, str):
             text = [text]
@@ -103,26 +123,15 @@ class ChatTSProcessor:
         encs, prefixes = self.encode_series(timeseries)
         k, rendered = 0, []
         for t in text:
-            parts = t.split(TS_PLACEHOLDER)
-            n = len(parts) - 1
+            n = t.count(TS_PLACEHOLDER)
             assert k + n <= len(prefixes), "more <ts><ts/> placeholders than time series"    # encoding_utils.py:58,68
-            s = parts[0]
-            for j in range(n):
-                s += prefixes[k + j] + parts[j + 1]
+            rendered.append(self.render_text(t, prefixes[k: k + n]))
             k += n
-            rendered.append(s)
         assert k == len(prefixes), "time series / <ts><ts/> placeholder count mismatch"
         if vllm_flag:
             # chatts_vllm.py:319-348,392: per series (ts_tokens, encoded [1, 2L, 1])
             toks = [self.tokenizer.encode(p) if hasattr(self.tokenizer, "encode") else None for p in prefixes]
             return {"timeseries": [(tk, e[None]) for tk, e in zip(toks, encs)], "text": rendered}
         out = dict(self.tokenizer(rendered, padding=padding, return_tensors=return_tensors))
-        if encs:
-            max_len = max(e.shape[0] for e in encs)
-            arr = np.zeros((len(encs), max_len, 1), dtype=np.float64)               # encoding_utils.py:78-84
-            for i, e in enumerate(encs):
-                arr[i, : e.shape[0]] = e
-            out["timeseries"] = torch.from_numpy(arr).to(self.dtype)
-        else:
-            out["timeseries"] = torch.zeros(0, 0, 1, dtype=self.dtype)
+        out["timeseries"] = self.pad_series(encs)                                   # encoding_utils.py:78-84
         return out

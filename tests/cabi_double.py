@@ -105,7 +105,7 @@ class TorchDouble:
         q = q * c + rot(q) * sn; k = k * c + rot(k) * sn
         q_out[:t] = q.reshape(t, -1)
         if k_lin is not None: k_lin[:t] = k.reshape(t, -1); v_lin[:t] = v.reshape(t, -1)
-        for i in range(t):
+        for i in range(t if (slot is not None and kc is not None) else 0):
             sl = int(slot[i])
             if sl >= 0: kc[sl // page, :, sl % page] = k[i]; vc[sl // page, :, sl % page] = v[i]
     def embed_gather(self, table, ids, out, t=None):
@@ -135,3 +135,98 @@ class TorchDouble:
         for b in range(B):
             slot[b] = pt[b, int(pos[b]) // page] * page + int(pos[b]) % page
         step_ptr += 1
+
+    # ------------------------------------------------------------------ A9: LoRA fine-tune step (include/chatts_b200.h "A9")
+    def _attn_lse(self, q, k, v, nrep):
+        T, nh, d = q.shape
+        kk = k.repeat_interleave(nrep, 1); vv = v.repeat_interleave(nrep, 1)
+        w = torch.einsum("thd,shd->hts", q, kk) * d ** -0.5
+        m = torch.arange(T)[None] > torch.arange(T)[:, None]
+        w = w.masked_fill(m[None], float("-inf"))
+        return torch.einsum("hts,shd->thd", w.softmax(-1), vv).reshape(T, nh * d), torch.logsumexp(w, -1).T      # [T, nh]
+    def attn_prefill_lse(self, q, k, v, cu, B, maxlen, nh, nkv, d, scale, out, lse):
+        for b in range(B):
+            a, e = int(cu[b]), int(cu[b + 1])
+            o, l = self._attn_lse(q[a:e].view(-1, nh, d).float(), k[a:e].view(-1, nkv, d).float(), v[a:e].view(-1, nkv, d).float(), nh // nkv)
+            out[a:e] = o.to(out.dtype); lse[a:e] = l
+    def attn_bwd(self, q, k, v, out, dout, lse, cu, B, maxlen, nh, nkv, d, scale, delta_ws, dq, dk, dv):
+        for b in range(B):
+            a, e = int(cu[b]), int(cu[b + 1])
+            with torch.enable_grad():
+                qq = q[a:e].view(-1, nh, d).float().requires_grad_(True); kk = k[a:e].view(-1, nkv, d).float().requires_grad_(True)
+                vv = v[a:e].view(-1, nkv, d).float().requires_grad_(True)
+                o, _ = self._attn_lse(qq, kk, vv, nh // nkv)
+                gq, gk, gv = torch.autograd.grad(o, [qq, kk, vv], dout[a:e].float())
+            dq[a:e] = gq.reshape(e - a, -1).to(dq.dtype); dk[a:e] = gk.reshape(e - a, -1).to(dk.dtype); dv[a:e] = gv.reshape(e - a, -1).to(dv.dtype)
+    @staticmethod
+    def _gu_split(gu, t, inter, interleaved):
+        x = gu[:t]
+        if interleaved:
+            xx = x.view(t, -1, 2, 64); return xx[:, :, 0].reshape(t, inter), xx[:, :, 1].reshape(t, inter)
+        return x[:, :inter], x[:, inter:]
+    def swiglu(self, gu, t, inter, out, interleaved=True):
+        g, u = self._gu_split(gu, t, inter, interleaved); dt = out.dtype
+        out[:t] = (F.silu(g.float()).to(dt).float() * u.float()).to(dt)
+    def swiglu_bwd(self, gu, dact, t, inter, dgu, interleaved=True):
+        g, u = self._gu_split(gu, t, inter, interleaved); g, u, d = g.float(), u.float(), dact[:t].float(); dt = dgu.dtype
+        sg = torch.sigmoid(g)
+        dg = (d * u * sg * (1 + g * (1 - sg))).to(dt); du = (d * F.silu(g).to(dt).float()).to(dt)
+        if interleaved:
+            o = dgu[:t].view(t, -1, 2, 64); o[:, :, 0] = dg.view(t, -1, 64); o[:, :, 1] = du.view(t, -1, 64)
+        else:
+            dgu[:t, :inter] = dg; dgu[:t, inter:] = du
+    def rmsnorm_bwd(self, dy, x, w, eps, dres_in, dx_out, t=None):
+        t = x.shape[0] if t is None else t
+        with torch.enable_grad():
+            xx = x[:t].float().requires_grad_(True)
+            y = w.float() * (xx * torch.rsqrt(xx.pow(2).mean(-1, keepdim=True) + eps))
+            (gx,) = torch.autograd.grad(y, [xx], dy[:t].float())
+        r = gx + (dres_in[:t].float() if dres_in is not None else 0)
+        dx_out[:t] = r.to(dx_out.dtype)
+    def qkv_rope_bwd(self, dq, dk, dv, qkv, pos, cos, sin, q_norm_w, k_norm_w, norm_eps, dqkv, t, nh, nkv, d):
+        c = torch.cat([cos[pos[:t].long()]] * 2, -1)[:, None].float(); sn = torch.cat([sin[pos[:t].long()]] * 2, -1)[:, None].float()
+        rot = lambda a: torch.cat((-a[..., d // 2:], a[..., : d // 2]), -1)
+        with torch.enable_grad():
+            x = qkv[:t].float().requires_grad_(True)
+            q = x[:, : nh * d].view(t, nh, d); k = x[:, nh * d:(nh + nkv) * d].view(t, nkv, d); v = x[:, (nh + nkv) * d:]
+            if q_norm_w is not None:
+                hn = lambda a, w: w.float() * (a * torch.rsqrt(a.pow(2).mean(-1, keepdim=True) + norm_eps))
+                q, k = hn(q, q_norm_w), hn(k, k_norm_w)
+            q = q * c + rot(q) * sn; k = k * c + rot(k) * sn
+            tot = (q.reshape(t, -1) * dq[:t].float()).sum() + (k.reshape(t, -1) * dk[:t].float()).sum() + (v * dv[:t].float()).sum()
+            (gx,) = torch.autograd.grad(tot, [x])
+        dqkv[:t] = gx.to(dqkv.dtype)
+    def ce_loss_grad(self, logits, targets, n, grad_scale, row_loss, loss_out, accumulate=False):
+        lg = logits[:n].float(); tg = targets[:n].long()
+        lse = torch.logsumexp(lg, -1)
+        row_loss[:n] = lse - lg.gather(1, tg[:, None])[:, 0]
+        p = torch.softmax(lg, -1); p[torch.arange(n), tg] -= 1
+        logits[:n] = (p * grad_scale).to(logits.dtype)
+        loss_out[0] = (loss_out[0] if accumulate else 0) + grad_scale * row_loss[:n].sum()
+    def gather_rows(self, src, idx, n, dst):
+        ii = idx[:n].long()
+        dst[:n] = torch.where((ii >= 0)[:, None], src[ii.clamp(min=0)], torch.zeros((), dtype=src.dtype))
+    def lora_wgrad(self, p, p_col0, p_il, m, q, q_col0, r, t, scale, out, so_m, so_r):
+        i = torch.arange(m)
+        cols = p_col0 + i if p_il == 0 else (i // 64) * 128 + i % 64 + (64 if p_il == 2 else 0)
+        g = scale * (p[:t][:, cols].float().T @ q[:t, q_col0:q_col0 + r].float())                # [m, r]
+        torch.as_strided(out, (m, r), (so_m, so_r)).add_(g)
+    def adamw(self, p, g, m, v, lr, b1, b2, eps, wd, step, grad_scale=None):
+        gg = g * (float(grad_scale[0]) if grad_scale is not None else 1.0)
+        p.mul_(1 - lr * wd); m.mul_(b1).add_(gg, alpha=1 - b1); v.mul_(b2).addcmul_(gg, gg, value=1 - b2)
+        p.sub_((lr / (1 - b1 ** step)) * m / (v.sqrt() / (1 - b2 ** step) ** 0.5 + eps))
+    def grad_norm_ws_floats(self): return 8
+    def grad_norm_clip(self, g, max_norm, ws, out):
+        n = g.norm(); out[0] = n; out[1] = min(1.0, max_norm / (float(n) + 1e-6)) if max_norm > 0 else 1.0
+    def lora_pack(self, master, desc, n_desc, max_elems, work):
+        import numpy as np
+        D = desc.view(n_desc, -1).tolist()
+        for src_off, rows, cols, dst_off, dst_ld, row0, il, col0, dstT_off, dstT_ld, sbits, _ in D:
+            scale = float(np.uint32(sbits).view(np.float32))
+            src = (master[src_off: src_off + rows * cols].view(rows, cols) * scale).to(work.dtype)
+            i = torch.arange(rows)
+            rm = row0 + i if il == 0 else (i // 64) * 128 + i % 64 + (64 if il == 2 else 0)
+            for a in range(rows):
+                r0 = int(rm[a])
+                work[dst_off + r0 * dst_ld + col0: dst_off + r0 * dst_ld + col0 + cols] = src[a]
+                work[dstT_off + col0 * dstT_ld + r0: dstT_off + (col0 + cols) * dstT_ld + r0: dstT_ld] = src[a]
