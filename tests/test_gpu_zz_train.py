@@ -1,0 +1,352 @@
+"""sm_100a kernels of the LoRA fine-tune step (row A9) through the C-ABI, against the torch restatement of every entry
+point (tests/cabi_double.py, fp32 on the CPU, itself checked against oracle/lora.py by tests/test_host_train.py) and, for
+the whole step, against oracle/lora.py directly.
+
+STATUS: these kernels were written after the round-1 GPU budget was spent; they have been compiled for sm_100a and
+their host orchestration is parity-checked on CPU through the double, but they had not yet executed on a B200 when this
+file was committed.  Until a GPU run confirms them the tests are marked xfail(strict=False): an XPASS in the report means
+"validated on hardware", an XFAIL names a kernel to fix -- either way the rest of the `-m gpu` suite stays meaningful.
+The file sorts last on purpose (a sticky CUDA error here cannot poison earlier tests); none of the new kernels spins on
+a flag, so a defect cannot hang the box.  Remove the marker once green.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from tests.cabi_double import TorchDouble
+from tests.gpu_util import ctx, record, rel_err
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="A9 training kernels: first B200 execution pending (round-1 GPU budget exhausted)")]
+DT = torch.bfloat16
+DBL = TorchDouble()
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _rn(g, *shape, std=1.0, dtype=DT):
+    return (torch.randn(*shape, generator=g) * std).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------ small-N / small-K GEMMs
+@pytest.mark.parametrize("t,n,k", [(300, 24, 256), (300, 256, 24), (64, 8, 704), (513, 16, 136), (40, 48, 512), (1000, 704, 8),
+                                   (129, 1408, 16), (7, 24, 256)])
+def test_gemm_lora_shapes(t, n, k):
+    """The LoRA down/up products: N = fused rank (8..48) and K = fused rank -- box larger than the tensor on one side."""
+    c = ctx()
+    g = _g(t + n + k)
+    x, w = _rn(g, t, k, std=0.5), _rn(g, n, k, std=0.1)
+    res = _rn(g, t, n, std=0.3)
+    out = torch.full((t, n), float("nan"), device="cuda", dtype=DT)
+    c.gemm(x.cuda(), w.cuda(), out)
+    ref = (x.float() @ w.float().T).to(DT)
+    e0 = rel_err(out, ref)
+    h = res.cuda().clone()
+    c.gemm(x.cuda(), w.cuda(), h, residual=h, epilogue=4)
+    torch.cuda.synchronize()
+    ref2 = (res.float() + ref.float()).to(DT)
+    e1 = rel_err(h, ref2)
+    record("gemm_lora_shape", t=t, n=n, k=k, err=e0, err_residual=e1)
+    assert torch.isfinite(out.float()).all() and e0 < 8e-3 and e1 <= 2 ** -7 + 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ elementwise backward
+@pytest.mark.parametrize("t,inter,il", [(5, 704, True), (300, 128, True), (33, 704, False), (2, 8, False)])
+def test_swiglu_fwd_bwd(t, inter, il):
+    c = ctx()
+    g = _g(t + inter)
+    gu, dact = _rn(g, t, 2 * inter), _rn(g, t, inter)
+    out, dgu = torch.empty(t, inter, device="cuda", dtype=DT), torch.empty(t, 2 * inter, device="cuda", dtype=DT)
+    c.swiglu(gu.cuda(), t, inter, out, interleaved=il)
+    c.swiglu_bwd(gu.cuda(), dact.cuda(), t, inter, dgu, interleaved=il)
+    torch.cuda.synchronize()
+    ro, rd = torch.empty(t, inter, dtype=DT), torch.empty(t, 2 * inter, dtype=DT)
+    DBL.swiglu(gu, t, inter, ro, interleaved=il)
+    DBL.swiglu_bwd(gu, dact, t, inter, rd, interleaved=il)
+    assert rel_err(out, ro) <= 2 ** -7 + 1e-6 and rel_err(dgu, rd) < 1e-2
+
+
+@pytest.mark.parametrize("t,h", [(3, 256), (70, 4096), (5, 5120)])
+def test_rmsnorm_bwd(t, h):
+    c = ctx()
+    g = _g(t + h)
+    dy, x, w, dres = _rn(g, t, h), _rn(g, t, h, std=2.0), (torch.rand(h, generator=g) + 0.5).to(DT), _rn(g, t, h)
+    ref = torch.empty(t, h, dtype=DT)
+    DBL.rmsnorm_bwd(dy, x, w, 1e-6, dres, ref)
+    out = torch.empty(t, h, device="cuda", dtype=DT)
+    c.rmsnorm_bwd(dy.cuda(), x.cuda(), w.cuda(), 1e-6, dres.cuda(), out)
+    e = rel_err(out, ref)
+    ref0 = torch.empty(t, h, dtype=DT)
+    DBL.rmsnorm_bwd(dy, x, w, 1e-6, None, ref0)
+    inpl = dy.cuda().clone()
+    c.rmsnorm_bwd(inpl, x.cuda(), w.cuda(), 1e-6, None, inpl)            # dx_out aliases dy
+    acc = dres.cuda().clone()
+    c.rmsnorm_bwd(dy.cuda(), x.cuda(), w.cuda(), 1e-6, acc, acc)          # dx_out aliases dres_in (the trainer's use)
+    torch.cuda.synchronize()
+    record("rmsnorm_bwd", t=t, h=h, err=e)
+    assert e < 1e-2 and rel_err(inpl, ref0) < 1e-2 and torch.equal(acc, out)
+
+
+@pytest.mark.parametrize("d,nh,nkv,qk", [(64, 4, 2, False), (64, 4, 2, True), (128, 8, 2, True), (128, 5, 1, False)])
+def test_qkv_rope_bwd(d, nh, nkv, qk):
+    c = ctx()
+    t = 37
+    g = _g(d + nh)
+    W = (nh + 2 * nkv) * d
+    qkv, dq, dk, dv = _rn(g, t, W), _rn(g, t, nh * d), _rn(g, t, nkv * d), _rn(g, t, nkv * d)
+    pos = torch.randint(0, 200, (t,), generator=g).to(torch.int32)
+    ang = torch.rand(256, d // 2, generator=g) * 6.28
+    cos, sin = ang.cos().to(DT), ang.sin().to(DT)
+    qn = (torch.rand(d, generator=g) + 0.5).to(DT) if qk else None
+    kn = (torch.rand(d, generator=g) + 0.5).to(DT) if qk else None
+    ref = torch.empty(t, W, dtype=DT)
+    DBL.qkv_rope_bwd(dq, dk, dv, qkv, pos, cos, sin, qn, kn, 1e-6, ref, t, nh, nkv, d)
+    out = torch.full((t, W), float("nan"), device="cuda", dtype=DT)
+    cu = lambda a: None if a is None else a.cuda()
+    c.qkv_rope_bwd(dq.cuda(), dk.cuda(), dv.cuda(), qkv.cuda(), pos.cuda(), cos.cuda(), sin.cuda(), cu(qn), cu(kn), 1e-6, out, t, nh, nkv, d)
+    torch.cuda.synchronize()
+    e = rel_err(out, ref)
+    record("qkv_rope_bwd", d=d, qk=qk, err=e)
+    assert torch.isfinite(out.float()).all() and e < 1e-2
+
+
+@pytest.mark.parametrize("n,vocab", [(1, 1000), (9, 1000), (3, 151936)])
+def test_cross_entropy_fwd_bwd(n, vocab):
+    c = ctx()
+    g = _g(n + vocab)
+    logits = _rn(g, n, vocab, std=3.0)
+    tgt = torch.randint(0, vocab, (n,), generator=g).to(torch.int32)
+    ref_l, ref_rows, ref_out = logits.clone(), torch.zeros(n), torch.full((1,), 0.25)
+    DBL.ce_loss_grad(ref_l, tgt, n, 1.0 / 7, ref_rows, ref_out, accumulate=True)
+    lg = logits.clone().cuda()
+    rows, out = torch.zeros(n, device="cuda"), torch.full((1,), 0.25, device="cuda")
+    c.ce_loss_grad(lg, tgt.cuda(), n, 1.0 / 7, rows, out, accumulate=True)
+    torch.cuda.synchronize()
+    e = rel_err(lg, ref_l)
+    record("ce_loss_grad", n=n, vocab=vocab, err=e, loss=float(out[0]))
+    assert torch.allclose(rows.cpu(), ref_rows, atol=1e-4, rtol=1e-5) and abs(float(out[0]) - float(ref_out[0])) < 1e-4 * abs(float(ref_out[0]))
+    assert e < 1e-2
+    out2 = torch.full((1,), 5.0, device="cuda")
+    c.ce_loss_grad(logits.clone().cuda(), tgt.cuda(), n, 1.0 / 7, rows, out2, accumulate=False)
+    assert abs(float(out2[0]) - (float(ref_out[0]) - 0.25)) < 1e-4 * abs(float(ref_out[0]))
+
+
+def test_gather_rows_and_zero_fill():
+    c = ctx()
+    g = _g(0)
+    src = _rn(g, 50, 256)
+    idx = torch.tensor([3, -1, 49, 0, -1, 7], dtype=torch.int32)
+    out = torch.full((6, 256), float("nan"), device="cuda", dtype=DT)
+    c.gather_rows(src.cuda(), idx.cuda(), 6, out)
+    ref = torch.empty(6, 256, dtype=DT)
+    DBL.gather_rows(src, idx, 6, ref)
+    assert torch.equal(out.cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ LoRA weight gradient
+@pytest.mark.parametrize("t,m,r,il", [(37, 256, 8, 0), (5000, 704, 16, 0), (300, 128, 4, 1), (300, 128, 16, 2), (9000, 64, 16, 0),
+                                      (100, 4096, 16, 0)])
+def test_lora_wgrad(t, m, r, il):
+    c = ctx()
+    g = _g(t + m + r)
+    ld = 2 * m if il else m + 64
+    col0 = 0 if il else 32
+    p, q = _rn(g, t, ld, std=0.5), _rn(g, t, 3 * r + 8, std=0.5)
+    # dB layout [m, r] and dA layout [r, m], each accumulated on top of existing content
+    for so_m, so_r, name in ((r, 1, "dB"), (1, m, "dA")):
+        base = torch.randn(m * r, generator=g)
+        ref = base.clone()
+        DBL.lora_wgrad(p, col0, il, m, q, r, r, t, 0.5, ref, so_m, so_r)
+        out = base.cuda()
+        c.lora_wgrad(p.cuda(), col0, il, m, q.cuda(), r, r, t, 0.5, out, so_m, so_r)
+        torch.cuda.synchronize()
+        e = rel_err(out, ref)
+        record("lora_wgrad", t=t, m=m, r=r, il=il, layout=name, err=e)
+        assert e < 2e-4, (name, e)                  # fp32 accumulation of exact bf16 products: only the summation order differs
+
+
+# ------------------------------------------------------------------------------------------------ optimiser + packing
+def test_adamw_and_clip_match_torch():
+    c = ctx()
+    g = _g(1)
+    n = 100003
+    p0 = torch.randn(n, generator=g)
+    par = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([par], lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1)
+    p, m, v = p0.cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    ws, out = torch.zeros(c.grad_norm_ws_floats(), device="cuda"), torch.zeros(2, device="cuda")
+    for step in range(1, 4):
+        gr = torch.randn(n, generator=g) * 0.01
+        par.grad = gr.clone()
+        tn = torch.nn.utils.clip_grad_norm_([par], 1.0)
+        opt.step()
+        gd = gr.cuda()
+        c.grad_norm_clip(gd, 1.0, ws, out)
+        c.adamw(p, gd, m, v, 3e-3, 0.9, 0.95, 1e-8, 0.1, step, grad_scale=out[1:2])
+        torch.cuda.synchronize()
+        assert abs(float(out[0]) - float(tn)) < 1e-5 * float(tn)
+        assert torch.allclose(p.cpu(), par.detach(), atol=2e-6, rtol=1e-5), step
+    c.grad_norm_clip(gd, 0.0, ws, out)
+    assert float(out[1]) == 1.0
+
+
+def test_lora_pack_matches_double():
+    from chatts_b200._cabi import PACK_DESC_LONGS
+    c = ctx()
+    g = _g(2)
+    r, K, N, R = 8, 256, 384, 24
+    master = torch.randn(3 * r * K + 128 * r * 3, generator=g)
+    one, sb = int(np.float32(1.0).view(np.uint32)), int(np.float32(2.0).view(np.uint32))
+    offA, offAt, offB, offBt = 0, R * K, 2 * R * K, 2 * R * K + N * R
+    desc = [[0, r, K, offA, K, 8, 0, 0, offAt, R, one, 0],                        # A of member 1 -> rows 8..15
+            [3 * r * K, 128, r, offB, R, 128, 0, 8, offBt, N, sb, 0],              # B of member 1 -> rows 128..255, cols 8..15
+            [3 * r * K + 128 * r, 128, r, offB, R, 0, 1, 16, offBt, N, sb, 0]]     # interleaved "gate" rows, cols 16..23
+    assert all(len(d) == PACK_DESC_LONGS for d in desc)
+    dt = torch.tensor(desc, dtype=torch.int64).reshape(-1)
+    ref = torch.zeros(2 * R * K + 2 * N * R, dtype=DT)
+    DBL.lora_pack(master, dt, 3, 128 * r * 8, ref)
+    work = torch.zeros_like(ref).cuda()
+    c.lora_pack(master.cuda(), dt.cuda(), 3, max(r * K, 128 * r), work)
+    torch.cuda.synchronize()
+    assert torch.equal(work.cpu(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ attention: LSE + backward
+def _attn_inputs(d, lens, nh=4, nkv=2, dtype=DT):
+    T = sum(lens)
+    g = _g(T + d)
+    q, k, v, do = _rn(g, T, nh * d, dtype=dtype), _rn(g, T, nkv * d, dtype=dtype), _rn(g, T, nkv * d, dtype=dtype), _rn(g, T, nh * d, dtype=dtype)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    return T, q, k, v, do, cu
+
+
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("lens", [[1], [5, 64, 65], [130, 17, 200, 1], [577]])
+def test_prefill_lse_matches_prefill_and_logsumexp(d, lens):
+    c = ctx()
+    nh, nkv = 4, 2
+    T, q, k, v, _, cu = _attn_inputs(d, lens)
+    sc = 1.0 / math.sqrt(d)
+    a, b = torch.empty(T, nh * d, device="cuda", dtype=DT), torch.empty(T, nh * d, device="cuda", dtype=DT)
+    lse = torch.full((T, nh), float("nan"), device="cuda")
+    c.attn_prefill(q.cuda(), k.cuda(), v.cuda(), cu.cuda(), len(lens), max(lens), nh, nkv, d, sc, a)
+    c.attn_prefill_lse(q.cuda(), k.cuda(), v.cuda(), cu.cuda(), len(lens), max(lens), nh, nkv, d, sc, b, lse)
+    torch.cuda.synchronize()
+    ro, rl = torch.empty(T, nh * d, dtype=DT), torch.empty(T, nh)
+    DBL.attn_prefill_lse(q, k, v, cu, len(lens), max(lens), nh, nkv, d, sc, ro, rl)
+    e = float((lse.cpu() - rl).abs().max())
+    record("attn_prefill_lse", d=d, lens=str(lens), lse_abs_err=e)
+    assert torch.equal(a, b)                                   # same kernel, one extra store
+    assert e < 2e-3
+
+
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("lens", [[1], [5, 64, 65], [130, 17, 200, 1], [577], [64, 128]])
+def test_attention_backward(d, lens):
+    c = ctx()
+    nh, nkv = 4, 2
+    T, q, k, v, do, cu = _attn_inputs(d, lens)
+    sc = 1.0 / math.sqrt(d)
+    qd, kd, vd, dod, cud = q.cuda(), k.cuda(), v.cuda(), do.cuda(), cu.cuda()
+    o, lse = torch.empty(T, nh * d, device="cuda", dtype=DT), torch.empty(T, nh, device="cuda")
+    c.attn_prefill_lse(qd, kd, vd, cud, len(lens), max(lens), nh, nkv, d, sc, o, lse)
+    dq, dk, dv = (torch.full((T, n_ * d), float("nan"), device="cuda", dtype=DT) for n_ in (nh, nkv, nkv))
+    ws = torch.empty(T, nh, device="cuda")
+    c.attn_bwd(qd, kd, vd, o, dod, lse, cud, len(lens), max(lens), nh, nkv, d, sc, ws, dq, dk, dv)
+    torch.cuda.synchronize()
+    rq, rk, rv = torch.empty(T, nh * d, dtype=DT), torch.empty(T, nkv * d, dtype=DT), torch.empty(T, nkv * d, dtype=DT)
+    DBL.attn_bwd(q, k, v, None, do, None, cu, len(lens), max(lens), nh, nkv, d, sc, None, rq, rk, rv)
+    eq, ek, ev = rel_err(dq, rq), rel_err(dk, rk), rel_err(dv, rv)
+    record("attn_bwd", d=d, lens=str(lens), dq=eq, dk=ek, dv=ev)
+    for t_ in (dq, dk, dv):
+        assert torch.isfinite(t_.float()).all()
+    assert eq < 2e-2 and ek < 2e-2 and ev < 2e-2, (eq, ek, ev)
+    # deterministic: no atomics in the attention backward
+    dq2, dk2, dv2 = (torch.empty_like(t_) for t_ in (dq, dk, dv))
+    c.attn_bwd(qd, kd, vd, o, dod, lse, cud, len(lens), max(lens), nh, nkv, d, sc, ws, dq2, dk2, dv2)
+    torch.cuda.synchronize()
+    assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)
+
+
+def test_attention_backward_gqa_group_of_8_fp16():
+    c = ctx()
+    d, nh, nkv, lens = 128, 8, 1, [100, 260]
+    T, q, k, v, do, cu = _attn_inputs(d, lens, nh, nkv, torch.float16)
+    sc = 1.0 / math.sqrt(d)
+    qd, kd, vd, dod, cud = q.cuda(), k.cuda(), v.cuda(), do.cuda(), cu.cuda()
+    o, lse = torch.empty(T, nh * d, device="cuda", dtype=torch.float16), torch.empty(T, nh, device="cuda")
+    c.attn_prefill_lse(qd, kd, vd, cud, 2, max(lens), nh, nkv, d, sc, o, lse)
+    dq, dk, dv = (torch.empty(T, n_ * d, device="cuda", dtype=torch.float16) for n_ in (nh, nkv, nkv))
+    c.attn_bwd(qd, kd, vd, o, dod, lse, cud, 2, max(lens), nh, nkv, d, sc, torch.empty(T, nh, device="cuda"), dq, dk, dv)
+    torch.cuda.synchronize()
+    rq, rk, rv = (torch.empty(T, n_ * d, dtype=torch.float16) for n_ in (nh, nkv, nkv))
+    DBL.attn_bwd(q, k, v, None, do, None, cu, 2, max(lens), nh, nkv, d, sc, None, rq, rk, rv)
+    assert rel_err(dq, rq) < 1e-2 and rel_err(dk, rk) < 1e-2 and rel_err(dv, rv) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ the whole step
+def _trainer_case(qwen3, head_dim=64):
+    from chatts_b200 import ChatTSConfig, ChatTSProcessor, SimpleTokenizer
+    from chatts_b200.model import ChatTSForCausalLM
+    from chatts_b200.weights import synthetic_state_dict
+    from tests.test_host_train import RECORDS
+
+    kw = {} if head_dim == 64 else dict(head_dim=128, hidden_size=512, num_attention_heads=4, num_key_value_heads=2,
+                                        ts=dict(patch_size=16, num_layers=3, hidden_size=512, num_features=2, max_sequence_length=512,
+                                                use_position_embedding=True, use_position_idx=False, embedding_dim=16))
+    cfg = ChatTSConfig.tiny(**kw)
+    if qwen3:
+        cfg.qk_norm, cfg.attention_bias = True, False
+    sd = synthetic_state_dict(cfg, seed=1234, device="cpu", dtype=DT, std=0.05)
+    model = ChatTSForCausalLM(cfg, sd, dtype=DT, max_batch=8, max_seq_len=512, page_size=16)
+    proc = ChatTSProcessor(SimpleTokenizer(cfg.ts_token_start_index, cfg.pad_token_id, cfg.eos_token_id), cfg)
+    return cfg, sd, model, proc, RECORDS
+
+
+@pytest.mark.parametrize("qwen3,head_dim", [(False, 64), (True, 64), (True, 128)])
+def test_train_step_matches_oracle(qwen3, head_dim):
+    from chatts_b200.train import LoraTrainer, encode_records
+    from oracle import lora as ol
+    from tests.test_host_train import _oracle_inputs
+
+    cfg, sd, model, proc, records = _trainer_case(qwen3, head_dim)
+    r, alpha = 8, 16
+    tr = LoraTrainer(model, r=r, lora_alpha=alpha, seed=3, init_b_std=0.05, max_grad_norm=0.0)
+    ad = ol.init_adapters(cfg.to_dict(), r, seed=3, b_std=0.05)
+    batch = encode_records(proc, records, eos_token_id=cfg.eos_token_id)
+    tr.zero_grad()
+    bt = tr.forward_backward(**batch)
+    torch.cuda.synchronize()
+    embeds, labels = _oracle_inputs(cfg, sd, batch)
+    w = {k: v for k, v in sd.items() if not k.startswith("ts_encoder.")}
+    loss, g = ol.grads(embeds, labels, w, ad, alpha / r, cfg.to_dict())
+    got_loss = float(tr.loss_out[0])
+    got = tr.grads()
+    worst = max(rel_err(got[n], ref) for n, ref in g.items())
+    flat_ref = torch.cat([g[n].reshape(-1) for n in tr.index])
+    cos = float(torch.nn.functional.cosine_similarity(tr.g.cpu(), flat_ref, dim=0))
+    record("train_step_vs_oracle", qwen3=qwen3, head_dim=head_dim, loss=got_loss, loss_ref=loss, worst_grad_rel=worst, cosine=cos,
+           tokens=bt.T, labels=bt.n_counted)
+    assert abs(got_loss - loss) < 2e-2 * abs(loss), (got_loss, loss)
+    assert worst < 8e-2 and cos > 0.998, (worst, cos)
+
+
+def test_training_reduces_loss_and_merge_roundtrip(tmp_path):
+    from chatts_b200.train import LoraTrainer, encode_records
+
+    cfg, sd, model, proc, records = _trainer_case(True)
+    batch = encode_records(proc, records, eos_token_id=cfg.eos_token_id)
+    tr = LoraTrainer(model, r=16, lora_alpha=32, seed=0, lr=5e-3, max_grad_norm=1.0)
+    l0 = float(tr.eval_loss(batch)[0])
+    losses = [float(tr.train_step(batch)[0]) for _ in range(4)]
+    record("train_loss_curve", l0=l0, losses=str(losses), grad_norm=float(tr.norm_out[0]))
+    assert abs(losses[0] - l0) < 1e-3 * l0 and losses[-1] < losses[0] - 0.05, losses
+    lt = float(tr.eval_loss(batch)[0])
+    tr.save_adapter(str(tmp_path / "ad"))
+    assert model.merge_lora(str(tmp_path / "ad")) == cfg.num_hidden_layers * 7
+    lm = float(LoraTrainer(model, r=16, lora_alpha=32, seed=0).eval_loss(batch)[0])
+    assert abs(lm - lt) < 3e-2 * lt, (lm, lt)

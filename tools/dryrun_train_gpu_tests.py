@@ -1,0 +1,41 @@
+"""Dry-run of tests/test_gpu_zz_train.py on a machine WITHOUT a GPU: `ctx()` returns the torch test double, `.cuda()` is the
+identity and `device="cuda"` is dropped, so the TEST LOGIC (shapes, arguments, reference arithmetic, tolerances) is
+exercised end to end.  A failure on the B200 then points at a kernel, not at the test.  TEST INFRASTRUCTURE ONLY.
+
+    python tools/dryrun_train_gpu_tests.py [pytest args]
+"""
+import sys, functools
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch, pytest
+for name in ("empty", "full", "zeros", "ones", "randn", "tensor", "empty_like", "zeros_like"):
+    orig = getattr(torch, name)
+    def mk(orig):
+        @functools.wraps(orig)
+        def f(*a, **k):
+            if k.get("device") in ("cuda",) or str(k.get("device", "")).startswith("cuda"):
+                k.pop("device")
+            return orig(*a, **k)
+        return f
+    setattr(torch, name, mk(orig))
+torch.Tensor.cuda = lambda self, *a, **k: self
+torch.cuda.synchronize = lambda *a, **k: None
+torch.cuda.is_available = lambda: True
+torch.cuda.current_device = lambda: 0
+torch.cuda.is_current_stream_capturing = lambda: False
+torch.Tensor.pin_memory = lambda self: self
+from tests.cabi_double import TorchDouble
+from chatts_b200 import _cabi
+dbl = TorchDouble()
+_cabi.get_context = lambda device=None: dbl
+import tests.gpu_util as gu
+gu.ctx = lambda: dbl
+gu.record = lambda *a, **k: None
+import chatts_b200.model as mm
+_orig_init = mm.ChatTSForCausalLM.__init__
+def _init(self, config, state_dict, device="cpu", **kw):
+    kw.setdefault("use_cuda_graph", False)
+    _orig_init(self, config, state_dict, device="cpu", **kw)
+mm.ChatTSForCausalLM.__init__ = _init
+sys.exit(pytest.main([os.path.join(ROOT, "tests", "test_gpu_zz_train.py"), "-q", "-p", "no:cacheprovider", "--runxfail", "-m", "gpu"] + sys.argv[1:]))
