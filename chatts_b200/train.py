@@ -13,7 +13,7 @@ checked against ``oracle/lora.py`` (torch.autograd over the decoder oracle, itse
   * ``clip_grad_norm_`` + ``torch.optim.AdamW`` on fp32 master adapters; gradients are summed across the data-parallel
     ranks with ONE all-reduce of the flat gradient arena (NCCL on the GPUs, gloo in the CPU tests).
 
-B200-first layout (DESIGN.md section 8):
+B200-first layout (DESIGN.md section 7):
   * every matrix product is ``cts_gemm`` (tcgen05): the frozen projections, their input gradients dX = dY W through
     TRANSPOSED copies of the frozen weights that stay resident in HBM (8B: +15 GB of the 180 GB), and the LoRA products,
     which are fused per projection GROUP -- qkv / o / gate_up / down -- into two small GEMMs: U = X A_f^T with the member
