@@ -36,6 +36,72 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json, cuBLAS bf16 burst)"
+    return 1700.0, "fallback (B200_PROFILING.md)"
+
+
+def _event_timer(fn, reps):
+    """us per call of fn(i), i = 0..reps-1, between CUDA events on the current stream (after one untimed pass)."""
+    fn(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+
+
+def measure_attention(model, st, batch, ctx_len, prompt_len, hbm_peak, timer=_event_timer):
+    """north_star: "attention tensor-pipe util reported as achieved fraction of roofline".  Both attention kernels timed
+    ALONE on the launching stream:
+      * paged flash-decode at the benchmark batch / context, one launch per LAYER's cache (48 x 84 MB at b=32 >> L2, so every
+        launch streams its K/V from HBM) -> GB/s against the HBM peak (GQA intensity nh/nkv flop/B: HBM-bound);
+      * tcgen05 prefill attention over batch x prompt_len positions (Q/K/V/O 0.28 GB > L2) -> causal-useful TFLOP/s
+        (4 * S^2/2 * d * nh per sequence) against the measured bf16 tensor peak."""
+    import math
+    c, L = model.ctx, model.L
+    nh, nkv, d = model.nh, model.nkv, model.d
+    scale = 1.0 / math.sqrt(d)
+    dev, dt = model.device, model.dtype
+    out = {}
+    # ---- decode: st.page_table / st.seq_lens still describe the benchmark batch (pages keep their contents after release)
+    us = timer(lambda i: c.attn_decode(st.q, model.kv[i % L, 0], model.kv[i % L, 1], st.page_table, st.seq_lens, batch, nh, nkv, d,
+                                       model.page_size, scale, st.attn_splits, st.attn_ws, st.ao), 2 * L)
+    alg = batch * ctx_len * 2 * nkv * d * 2 + 2 * batch * nh * d * 2
+    out["decode"] = {"kernel": "attn_decode_kernel (TMA paged flash-decode, mma.sync, fused split merge)", "bound": "hbm", "us_per_launch": us,
+                     "algorithmic_bytes": alg, "achieved_gbs": alg / (us * 1e-6) / 1e9, "frac": alg / (us * 1e-6) / 1e9 / hbm_peak,
+                     "batch": batch, "context": ctx_len, "splits": st.attn_splits}
+    # ---- prefill
+    T = batch * prompt_len
+    g = torch.Generator(device=dev).manual_seed(7) if str(dev) != "cpu" else torch.Generator().manual_seed(7)
+    q = (torch.randn(T, nh * d, device=dev, generator=g) * 0.5).to(dt)
+    k = (torch.randn(T, nkv * d, device=dev, generator=g) * 0.5).to(dt)
+    v = (torch.randn(T, nkv * d, device=dev, generator=g) * 0.5).to(dt)
+    o = torch.empty(T, nh * d, device=dev, dtype=dt)
+    cu = torch.arange(0, T + 1, prompt_len, dtype=torch.int32, device=dev)
+    us = timer(lambda i: c.attn_prefill(q, k, v, cu, batch, prompt_len, nh, nkv, d, scale, o), 8)
+    flops = batch * 4.0 * (prompt_len * prompt_len / 2.0) * d * nh
+    peak, src = tensor_peak()
+    out["prefill"] = {"kernel": "attn_prefill_tc5_kernel (tcgen05, S/O in TMEM)" if d == 128 else "attn_prefill_kernel (HMMA)",
+                      "bound": "tensor", "us_per_launch": us, "causal_flops": flops, "achieved_tflops": flops / (us * 1e-6) / 1e12,
+                      "frac": flops / (us * 1e-6) / 1e12 / peak, "peak_tflops": peak, "peak_source": src, "tokens": T,
+                      "tensor_pipe_active_pct_ncu": None}
+    try:       # tensor-pipe utilisation of the same kernel from the committed `ncu --set full` capture (a profiler number, never a timing)
+        cap = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
+        out["prefill"]["tensor_pipe_active_pct_ncu"] = float(cap["prefill_attention_tcgen05_b32x576"][0]["tensor_pipe_active_pct"])
+        out["decode"]["dram_pct_of_peak_ncu"] = float(cap["decode_attention_b32_ctx576"][0]["dram_pct_of_peak"])
+        out["ncu_source"] = "profiles/r1_ncu_summary.json"
+    except Exception:
+        pass
+    return out
+
+
 def make_series(i, k, length=SERIES_LEN):
     """SURVEY.md §8d synthetic series: sine + trend + noise + one level shift, seeded per (sample, series)."""
     rng = np.random.default_rng(1000 * i + k)
@@ -381,6 +447,14 @@ def run_b200(args):
                    "achieved_gbs": ach, "hbm_frac": ach / hbm_peak, "tflops": flops / (us * 1e-6) / 1e12,
                    "bound": "hbm (weight stream)" if rows <= 280 else "tensor", "launches": 1 + 2 * nl, "timed": "CUDA-graph replay of patchify + MLP, L2 flushed before each replay"}
 
+    # ---- attention kernels alone (north_star: attention reported as achieved fraction of its roofline)
+    attn_roof = None
+    if world == 1:
+        try:
+            attn_roof = measure_attention(model, model._decode_state(args.batch, max_new), args.batch, int(main["ctx_end"]), 576, hbm_peak)
+        except Exception as e:  # pragma: no cover  (a side measurement must never cost the headline line)
+            attn_roof = {"error": repr(e)}
+
     # ---- e2e through the public API with host tensors
     e2e = None
     if world == 1 and not args.sweep_only:
@@ -412,7 +486,7 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.batch, world),
                 "by_batch": {str(b): {"tokens_per_s": r["tokens_per_s"], "ms_per_step": r["ms_per_step"]} for b, r in results.items()},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(main["launches"] * args.steps), "launches_per_step": main["launches"],
-                "roofline": roof, "ts_encoder": ts_roof, "cpu_baseline": cpu, "arch": ctx.arch, "lib": os.path.relpath(_cabi.LIB_PATH, ROOT)}
+                "roofline": roof, "ts_encoder": ts_roof, "attention": attn_roof, "cpu_baseline": cpu, "arch": ctx.arch, "lib": os.path.relpath(_cabi.LIB_PATH, ROOT)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
