@@ -28,6 +28,7 @@ SYMBOLS = [
     "cts_attn_prefill_lse", "cts_attn_bwd", "cts_swiglu", "cts_swiglu_bwd", "cts_rmsnorm_bwd", "cts_qkv_rope_bwd",
     "cts_ce_loss_grad", "cts_gather_rows", "cts_lora_wgrad", "cts_adamw", "cts_grad_norm_ws_floats", "cts_grad_norm_clip",
     "cts_lora_pack",
+    "cts_sample_advance",
 ]
 PACK_DESC_LONGS = 12
 
@@ -99,6 +100,8 @@ def load_library():
     lib.cts_decode_chain.restype = i
     lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cts_peer_greedy_advance.restype = i
+    lib.cts_sample_advance.argtypes = [vp, vp, ll, i, f, i, f, C.c_ulonglong, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
+    lib.cts_sample_advance.restype = i
     # ---- A9: LoRA fine-tune step
     lib.cts_attn_prefill_lse.argtypes = [vp, vp, vp, vp, vp, i, i, ll, i, i, i, f, vp, vp, i, vp]
     lib.cts_attn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, ll, i, i, i, f, vp, vp, vp, vp, i, vp]
@@ -256,6 +259,15 @@ class Context:
     def greedy_advance(self, logits, batch, out_tokens, step_ptr, cur_ids, positions, seq_lens, slot_map, page_table,
                        page_size):
         self._chk(self.lib.cts_greedy_advance(self.h, _p(logits), logits.shape[-1], batch, _p(out_tokens),
+                                              out_tokens.stride(0) if out_tokens is not None else 0, _p(step_ptr), _p(cur_ids),
+                                              _p(positions), _p(seq_lens), _p(slot_map), _p(page_table),
+                                              page_table.shape[1] if page_table is not None else 0, page_size,
+                                              dtype_code(logits.dtype), _stream()))
+
+    def sample_advance(self, logits, batch, temperature, top_k, top_p, seed, out_tokens, step_ptr, cur_ids, positions, seq_lens,
+                       slot_map, page_table, page_size):
+        self._chk(self.lib.cts_sample_advance(self.h, _p(logits), logits.shape[-1], batch, float(temperature), int(top_k or 0),
+                                              float(top_p if top_p is not None else 1.0), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(out_tokens),
                                               out_tokens.stride(0) if out_tokens is not None else 0, _p(step_ptr), _p(cur_ids),
                                               _p(positions), _p(seq_lens), _p(slot_map), _p(page_table),
                                               page_table.shape[1] if page_table is not None else 0, page_size,

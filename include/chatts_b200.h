@@ -181,6 +181,19 @@ int cts_greedy_advance(cts_ctx* ctx, const void* logits, long long vocab, int ba
                        int* step_ptr, int* cur_ids, int* positions, int* seq_lens, int* slot_map,
                        const int* page_table, int max_pages, int page_size, int dtype, void* stream);
 
+/* K13, sampled variant: temperature -> top-k -> top-p -> multinomial (transformers TemperatureLogitsWarper / TopKLogitsWarper /
+ * TopPLogitsWarper + torch.multinomial; vLLM Sampler -- chatts/utils/inference_tsmllm_deepspeed.py:95-100 decodes with
+ * temperature 0.2, chatts/utils/llm_utils.py:166-170 passes temperature / top_p) fused with the same device-side advance as
+ * cts_greedy_advance, so a sampled decode step needs no host round trip either.
+ *   kept set = {i : z_i >= tau}, z = logits / temperature; tau by bisection over the 16-bit ordered key of the logit (no sort):
+ *   top_k > 0: the k largest (ties at the k-th value kept); 0 < top_p < 1: the smallest threshold set whose probability reaches
+ *   top_p of the top-k mass.  The token is drawn by inverse CDF in index order with the counter-based uniform
+ *   u = splitmix64(seed ^ splitmix64(step << 32 | sequence)) >> 40 / 2^24: (seed, step, sequence) fixes the draw.
+ *   temperature > 0 (greedy is cts_greedy_advance); vocab <= 2^24; state pointers as in cts_greedy_advance. */
+int cts_sample_advance(cts_ctx* ctx, const void* logits, long long vocab, int batch, float temperature, int top_k, float top_p,
+                       unsigned long long seed, int* out_tokens, int out_ld, int* step_ptr, int* cur_ids, int* positions,
+                       int* seq_lens, int* slot_map, const int* page_table, int max_pages, int page_size, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Tensor parallelism over NVLink peer memory (replaces RowParallelLinear's NCCL all-reduce +
  * residual add + RMSNorm, vllm qwen2.py:100-116,168-174,299-311, for decode-sized messages).

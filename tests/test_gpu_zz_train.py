@@ -2,12 +2,15 @@
 point (tests/cabi_double.py, fp32 on the CPU, itself checked against oracle/lora.py by tests/test_host_train.py) and, for
 the whole step, against oracle/lora.py directly.
 
-STATUS: these kernels were written after the round-1 GPU budget was spent; they have been compiled for sm_100a and
-their host orchestration is parity-checked on CPU through the double, but they had not yet executed on a B200 when this
-file was committed.  Until a GPU run confirms them the tests are marked xfail(strict=False): an XPASS in the report means
-"validated on hardware", an XFAIL names a kernel to fix -- either way the rest of the `-m gpu` suite stays meaningful.
-The file sorts last on purpose (a sticky CUDA error here cannot poison earlier tests); none of the new kernels spins on
-a flag, so a defect cannot hang the box.  Remove the marker once green.
+STATUS (end of round 1).  Validated on a B200 in the last seconds of the round-1 GPU budget
+(profiles/r1_train_kernels_first_b200_run.log, 29 passed): the small-N / small-K LoRA GEMM shapes, SwiGLU forward/backward,
+RMSNorm backward, RoPE(+q/k-norm) backward, fused cross entropy, row gather and the LoRA weight-gradient kernel -- these
+run as plain tests.  NOT yet executed on a B200 (the budget ran out): the attention LSE flag, the attention backward, AdamW +
+clip, adapter packing and the whole-step tests -- compiled for sm_100a, orchestration parity-checked on CPU through the
+double, marked PENDING = xfail(strict=False): an XPASS in the report means "validated on hardware", an XFAIL names a kernel
+to fix.  The file sorts last on purpose (a sticky CUDA error here cannot poison earlier tests); none of the new kernels
+spins on a flag, so a defect cannot hang the box.  Remove the markers once green (tools/gpu_train_checks.sh runs them with
+--runxfail).
 """
 import math
 
@@ -18,8 +21,8 @@ import torch
 from tests.cabi_double import TorchDouble
 from tests.gpu_util import ctx, record, rel_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="A9 training kernels: first B200 execution pending (round-1 GPU budget exhausted)")]
+pytestmark = pytest.mark.gpu
+PENDING = pytest.mark.xfail(strict=False, reason="first B200 execution pending (round-1 GPU budget exhausted before this kernel could run)")
 DT = torch.bfloat16
 DBL = TorchDouble()
 
@@ -170,6 +173,7 @@ def test_lora_wgrad(t, m, r, il):
 
 
 # ------------------------------------------------------------------------------------------------ optimiser + packing
+@PENDING
 def test_adamw_and_clip_match_torch():
     c = ctx()
     g = _g(1)
@@ -194,6 +198,7 @@ def test_adamw_and_clip_match_torch():
     assert float(out[1]) == 1.0
 
 
+@PENDING
 def test_lora_pack_matches_double():
     from chatts_b200._cabi import PACK_DESC_LONGS
     c = ctx()
@@ -224,6 +229,7 @@ def _attn_inputs(d, lens, nh=4, nkv=2, dtype=DT):
     return T, q, k, v, do, cu
 
 
+@PENDING
 @pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("lens", [[1], [5, 64, 65], [130, 17, 200, 1], [577]])
 def test_prefill_lse_matches_prefill_and_logsumexp(d, lens):
@@ -244,6 +250,7 @@ def test_prefill_lse_matches_prefill_and_logsumexp(d, lens):
     assert e < 2e-3
 
 
+@PENDING
 @pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("lens", [[1], [5, 64, 65], [130, 17, 200, 1], [577], [64, 128]])
 def test_attention_backward(d, lens):
@@ -272,6 +279,7 @@ def test_attention_backward(d, lens):
     assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)
 
 
+@PENDING
 def test_attention_backward_gqa_group_of_8_fp16():
     c = ctx()
     d, nh, nkv, lens = 128, 8, 1, [100, 260]
@@ -307,6 +315,7 @@ def _trainer_case(qwen3, head_dim=64):
     return cfg, sd, model, proc, RECORDS
 
 
+@PENDING
 @pytest.mark.parametrize("qwen3,head_dim", [(False, 64), (True, 64), (True, 128)])
 def test_train_step_matches_oracle(qwen3, head_dim):
     from chatts_b200.train import LoraTrainer, encode_records
@@ -335,6 +344,7 @@ def test_train_step_matches_oracle(qwen3, head_dim):
     assert worst < 8e-2 and cos > 0.998, (worst, cos)
 
 
+@PENDING
 def test_training_reduces_loss_and_merge_roundtrip(tmp_path):
     from chatts_b200.train import LoraTrainer, encode_records
 
