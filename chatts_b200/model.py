@@ -64,7 +64,7 @@ class _Step:
 class ChatTSForCausalLM:
     def __init__(self, config, state_dict, device="cuda", dtype=torch.bfloat16, tp_rank=0, tp_size=1,
                  max_batch=32, max_seq_len=2048, page_size=64, use_cuda_graph=True, comm=None,
-                 use_peer_allreduce=True, graph_with_tp=True, use_chain=None):
+                 use_peer_allreduce=True, graph_with_tp=True, use_chain=None, use_sample_kernel=None):
         if not torch.cuda.is_available():
             raise _cabi.CtsError("chatts_b200 needs a B200 (sm_100a) GPU; there is no CPU fallback")
         self.config, self.dtype = config, dtype
@@ -84,6 +84,9 @@ class ChatTSForCausalLM:
         self.graph_with_tp = graph_with_tp
         import os as _os
         self.use_chain = bool(int(_os.environ.get("CTS_DECODE_CHAIN", "0"))) if use_chain is None else bool(use_chain)
+        # sampled decoding through cts_sample_advance (csrc/sampling.cu) instead of torch ops: off by default until the kernel has
+        # run on a B200 (written after the round-1 GPU budget was spent); CTS_SAMPLE_KERNEL=1 / use_sample_kernel=True turns it on
+        self.use_sample_kernel = bool(int(_os.environ.get("CTS_SAMPLE_KERNEL", "0"))) if use_sample_kernel is None else bool(use_sample_kernel)
         self._load(state_dict)
         n_pos = min(cfg.max_position_embeddings, max(max_seq_len, 16))
         self.cos, self.sin = rope_tables(cfg, n_pos, dtype, self.device)
@@ -517,7 +520,7 @@ class ChatTSForCausalLM:
     # ------------------------------------------------------------------------------------------ generate
     @torch.no_grad()
     def generate(self, input_ids=None, attention_mask=None, timeseries=None, max_new_tokens=None, max_length=None,
-                 do_sample=False, temperature=None, top_p=None, streamer=None, eos_token_id=None, pad_token_id=None,
+                 do_sample=False, temperature=None, top_p=None, top_k=None, streamer=None, eos_token_id=None, pad_token_id=None,
                  synced_gpus=False, sync_every=16, ignore_eos=False, seed=None, **_):
         """model.generate(**processor_out, max_new_tokens=...) -> LongTensor [B, S + new] whose first S columns are
         the ORIGINAL (un-expanded) input ids (README.md:102-103)."""
@@ -545,11 +548,22 @@ class ChatTSForCausalLM:
             gen = torch.Generator(device=dev)
             if seed is not None:
                 gen.manual_seed(seed)
+            kseed = int(seed) if seed is not None else int.from_bytes(__import__("os").urandom(8), "little")
+
+            def sample(lg, step):
+                if self.use_sample_kernel:
+                    # temperature / top-k / top-p + multinomial + advance in one launch; the draw is a function of (seed, step, row)
+                    self.ctx.sample_advance(lg, B, temperature, top_k or 0, 1.0 if top_p is None else top_p, kseed, st.out_tokens,
+                                            st.step_ptr, st.cur_ids, st.positions, st.seq_lens, st.slot_map, st.page_table,
+                                            self.page_size)
+                else:
+                    self._sample_advance(st, lg, step, temperature, top_p, gen, top_k)
+
             if greedy:
                 self.ctx.greedy_advance(logits, B, st.out_tokens, st.step_ptr, st.cur_ids, st.positions, st.seq_lens, st.slot_map,
                                         st.page_table, self.page_size)
             else:
-                self._sample_advance(st, logits, 0, temperature, top_p, gen)
+                sample(logits, 0)
             done = np.zeros(B, dtype=bool)
             out = np.full((B, max_new_tokens), pad, dtype=np.int64)
             emitted = 0
@@ -573,7 +587,7 @@ class ChatTSForCausalLM:
                     self._decode_step(st, sample=True)
                 else:
                     self._decode_step(st, sample=False)
-                    self._sample_advance(st, st.full_logits, produced, temperature, top_p, gen)
+                    sample(st.full_logits, produced)
                 produced += 1
             if streamer is not None:
                 streamer.end()
@@ -584,10 +598,13 @@ class ChatTSForCausalLM:
         n_out = int(min(max(first.max(), 1), max_new_tokens))
         return torch.cat([torch.as_tensor(ids_cpu, dtype=torch.long), torch.as_tensor(out[:, :n_out])], dim=1)
 
-    def _sample_advance(self, st, logits, step, temperature, top_p, gen):
+    def _sample_advance(self, st, logits, step, temperature, top_p, gen, top_k=None):
         """Stochastic sampling (temperature / top-p, chatts/utils/inference_tsmllm_deepspeed.py:95-100).  Round 1: the
         distribution arithmetic is torch on the device logits (not graph-captured); greedy is the fused kernel."""
         lg = logits[: st.B].float() / float(temperature)
+        if top_k is not None and 0 < top_k < lg.shape[-1]:
+            kth = torch.topk(lg, int(top_k), dim=-1).values[:, -1:]
+            lg = lg.masked_fill(lg < kth, float("-inf"))
         probs = torch.softmax(lg, dim=-1)
         if top_p is not None and top_p < 1.0:
             sp, si = torch.sort(probs, dim=-1, descending=True)

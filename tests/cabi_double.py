@@ -230,3 +230,56 @@ class TorchDouble:
                 r0 = int(rm[a])
                 work[dst_off + r0 * dst_ld + col0: dst_off + r0 * dst_ld + col0 + cols] = src[a]
                 work[dstT_off + col0 * dstT_ld + r0: dstT_off + (col0 + cols) * dstT_ld + r0: dstT_ld] = src[a]
+
+    # ------------------------------------------------------------------ K13 sampled variant (csrc/sampling.cu)
+    @staticmethod
+    def _splitmix64(x):
+        M = (1 << 64) - 1
+        x = (x + 0x9E3779B97F4A7C15) & M
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M
+        return x ^ (x >> 31)
+    @classmethod
+    def sample_reference(cls, row, temperature, top_k, top_p, seed, step, b):
+        """(token, cdf float64 over the kept set in index order, target, kept mask) -- the statement cts_sample_advance follows."""
+        import numpy as np
+        x = row.float().numpy(); V = x.shape[0]
+        bits = row.contiguous().view(torch.int16).numpy().astype(np.uint16).astype(np.uint32)
+        key = np.where(bits & 0x8000, (~bits) & 0xFFFF, bits | 0x8000)
+        ok = ~np.isnan(x)
+        m = x[ok].max()
+        p = np.where(ok, np.exp((x - m) * np.float32(1.0 / temperature), dtype=np.float32), np.float32(0))
+        kmax = int(key[ok].max()); tau = 0
+        if top_k and 0 < top_k < V:
+            lo, hi = 0, kmax + 1
+            while hi - lo > 1:
+                mid = lo + ((hi - lo) >> 1)
+                lo, hi = (mid, hi) if int((ok & (key >= mid)).sum()) >= top_k else (lo, mid)
+            tau = lo
+        mass = float(p[ok & (key >= tau)].sum(dtype=np.float64))
+        if top_p is not None and 0.0 < top_p < 1.0:
+            lo, hi, target = tau, kmax + 1, top_p * mass
+            while hi - lo > 1:
+                mid = lo + ((hi - lo) >> 1)
+                lo, hi = (mid, hi) if float(p[ok & (key >= mid)].sum(dtype=np.float64)) >= target else (lo, mid)
+            tau = lo
+        kept = ok & (key >= tau)
+        cdf = np.cumsum(np.where(kept, p, 0), dtype=np.float64)
+        M = (1 << 64) - 1
+        h = cls._splitmix64((int(seed) & M) ^ cls._splitmix64(((int(step) & 0xFFFFFFFF) << 32) | (int(b) & 0xFFFFFFFF)))
+        u = float(h >> 40) / 16777216.0
+        target = u * cdf[-1]
+        tok = int(np.searchsorted(cdf, target, side="right"))
+        tok = min(tok, int(np.nonzero(kept)[0][-1]))
+        return tok, cdf, target, kept
+    def sample_advance(self, logits, B, temperature, top_k, top_p, seed, out_tokens, step_ptr, cur, pos, sl, slot, pt, page):
+        st = int(step_ptr[0])
+        for b in range(B):
+            tok = self.sample_reference(logits[b], temperature, top_k, top_p, seed, st, b)[0]
+            out_tokens[b, st] = tok
+            if cur is not None: cur[b] = tok
+            if pos is not None:
+                pos[b] += 1
+                if sl is not None: sl[b] += 1
+                if slot is not None and pt is not None: slot[b] = pt[b, int(pos[b]) // page] * page + int(pos[b]) % page
+        step_ptr[0] += 1

@@ -1,4 +1,4 @@
-"""Dry-run of tests/test_gpu_zz_train.py on a machine WITHOUT a GPU: `ctx()` returns the torch test double, `.cuda()` is the
+"""Dry-run of tests/test_gpu_zz_train.py and tests/test_gpu_zz_sampling.py on a machine WITHOUT a GPU: `ctx()` returns the torch test double, `.cuda()` is the
 identity and `device="cuda"` is dropped, so the TEST LOGIC (shapes, arguments, reference arithmetic, tolerances) is
 exercised end to end.  A failure on the B200 then points at a kernel, not at the test.  TEST INFRASTRUCTURE ONLY.
 
@@ -38,4 +38,4 @@ def _init(self, config, state_dict, device="cpu", **kw):
     kw.setdefault("use_cuda_graph", False)
     _orig_init(self, config, state_dict, device="cpu", **kw)
 mm.ChatTSForCausalLM.__init__ = _init
-sys.exit(pytest.main([os.path.join(ROOT, "tests", "test_gpu_zz_train.py"), "-q", "-p", "no:cacheprovider", "--runxfail", "-m", "gpu"] + sys.argv[1:]))
+sys.exit(pytest.main([os.path.join(ROOT, "tests", "test_gpu_zz_train.py"), os.path.join(ROOT, "tests", "test_gpu_zz_sampling.py"), "-q", "-p", "no:cacheprovider", "--runxfail", "-m", "gpu"] + sys.argv[1:]))
