@@ -471,10 +471,89 @@ class LoraTrainer:
         self.optimizer_step()
         return self.loss_out.clone()
 
+    # ------------------------------------------------------------------------------------------ schedule, resume, epochs
+    def set_lr(self, lr):
+        self.lr = float(lr)
+
+    def state_dict(self):
+        """Everything a resumed run needs: master adapters, Adam moments, step counter, hyper-parameters (host tensors)."""
+        return {"p": self.p.detach().cpu().clone(), "m": self.m.detach().cpu().clone(), "v": self.v.detach().cpu().clone(),
+                "step": self.step_count, "r": self.r, "lora_alpha": self.alpha, "targets": list(self.targets), "n_params": self.n_params,
+                "lr": self.lr, "betas": list(self.betas), "eps": self.eps, "weight_decay": self.weight_decay,
+                "max_grad_norm": self.max_grad_norm}
+
+    def load_state_dict(self, sd):
+        if (sd["r"], list(sd["targets"]), sd["n_params"]) != (self.r, list(self.targets), self.n_params):
+            raise ValueError("checkpoint was written for a different LoRA configuration (rank / target modules / model shape)")
+        for name in ("p", "m", "v"):
+            getattr(self, name).copy_(sd[name])
+        self.step_count = int(sd["step"])
+        self.lr = float(sd.get("lr", self.lr))
+        self.pack()
+
+    def save_checkpoint(self, path):
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        tmp = path + ".tmp"
+        torch.save(self.state_dict(), tmp)
+        os.replace(tmp, path)                                   # atomic: a killed run never leaves a torn checkpoint
+
+    def load_checkpoint(self, path):
+        self.load_state_dict(torch.load(path, map_location="cpu", weights_only=False))
+
+    def fit(self, processor, records, epochs=1, samples_per_step=8, micro_batch=None, lr_schedule="cosine", warmup_steps=0,
+            min_lr_ratio=0.0, eos_token_id=None, max_length=None, shuffle_seed=0, on_step=None, checkpoint=None, checkpoint_every=0):
+        """The loop of the external recipe around train_step: every rank walks ITS shard of ``records`` (rank::world) in the
+        same seeded order, ``samples_per_step`` records per rank and optimisation step in micro-batches of ``micro_batch``
+        (gradient accumulation), learning rate warmed up linearly then decayed (cosine | linear | constant).
+        ``checkpoint``: file to resume from if present and to write every ``checkpoint_every`` steps (rank 0 writes)."""
+        import torch.distributed as dist
+        world = self._world()
+        rank = dist.get_rank(self.group) if world > 1 else 0
+        mine = shard_records(list(records), rank, world)
+        per = max(1, int(samples_per_step))
+        steps_per_epoch = len(shard_records(list(records), world - 1, world)) // per        # the shortest shard sets the pace
+        if steps_per_epoch == 0:
+            raise ValueError(f"{len(records)} records are too few for {world} ranks x {per} samples per step")
+        total_steps = steps_per_epoch * int(epochs)
+        base_lr = self.lr
+        start = 0
+        if checkpoint and os.path.exists(checkpoint):
+            self.load_checkpoint(checkpoint)
+            start = self.step_count
+        mb = int(micro_batch or per)
+        losses = []
+        for step in range(start, total_steps):
+            ep, k = divmod(step, steps_per_epoch)
+            order = np.random.default_rng(shuffle_seed + ep).permutation(len(mine))
+            chunk = [mine[i] for i in order[k * per:(k + 1) * per]]
+            self.lr = base_lr * lr_factor(step, total_steps, warmup_steps, lr_schedule, min_lr_ratio)
+            batches = [encode_records(processor, chunk[i: i + mb], eos_token_id=eos_token_id, max_length=max_length)
+                       for i in range(0, len(chunk), mb)]
+            loss = self.train_step(batches)
+            losses.append(loss)
+            if on_step is not None:
+                on_step(step, loss, self)
+            if checkpoint and checkpoint_every and (step + 1) % checkpoint_every == 0 and rank == 0:
+                self.save_checkpoint(checkpoint)
+        self.lr = base_lr
+        return [float(l[0]) for l in losses]                                             # one host read at the end
+
     @torch.no_grad()
     def eval_loss(self, batch):
         self.forward_backward(batch["input_ids"], batch.get("attention_mask"), batch.get("timeseries"), batch["labels"], backward=False)
         return self.loss_out.clone()
+
+
+def lr_factor(step, total_steps, warmup_steps=0, schedule="cosine", min_ratio=0.0):
+    """transformers get_{cosine,linear,constant}_schedule_with_warmup as a pure function of the step."""
+    if warmup_steps and step < warmup_steps:
+        return (step + 1) / float(warmup_steps + 1) if schedule == "constant" else step / float(max(1, warmup_steps))
+    if schedule == "constant":
+        return 1.0
+    prog = (step - warmup_steps) / float(max(1, total_steps - warmup_steps))
+    prog = min(max(prog, 0.0), 1.0)
+    dec = 0.5 * (1.0 + math.cos(math.pi * prog)) if schedule == "cosine" else 1.0 - prog
+    return min_ratio + (1.0 - min_ratio) * dec
 
 
 # ---------------------------------------------------------------------------------------------- data

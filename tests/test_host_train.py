@@ -187,3 +187,46 @@ def test_label_rows_skip_patch_rows_and_sample_boundaries(cabi_double):
         assert lay.src_col[row + 1] >= 0 and tgt >= 0
     with pytest.raises(ValueError):
         tr.forward_backward(batch["input_ids"], batch["attention_mask"], batch["timeseries"], batch["labels"][:, :-1])
+
+
+def test_fit_schedule_accumulation_and_resume(cabi_double, tmp_path):
+    """fit(): seeded epochs over the shard, micro-batch accumulation, LR schedule identical to transformers', checkpoint +
+    resume reproduces the uninterrupted run bit for bit."""
+    from transformers.optimization import get_cosine_schedule_with_warmup, get_linear_schedule_with_warmup
+    from chatts_b200.train import LoraTrainer, lr_factor
+
+    for name, mk in (("cosine", get_cosine_schedule_with_warmup), ("linear", get_linear_schedule_with_warmup)):
+        opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+        sch = mk(opt, num_warmup_steps=3, num_training_steps=20)
+        for step in range(20):
+            assert abs(sch.get_last_lr()[0] - lr_factor(step, 20, 3, name)) < 1e-9, (name, step)
+            opt.step(); sch.step()
+    cfg, sd, model, proc = _build(cabi_double, False)
+    recs = RECORDS * 2                                              # 6 records: 3 steps of 2 samples per epoch
+    kw = dict(r=8, lora_alpha=16, seed=1, init_b_std=0.02, lr=5e-3, max_grad_norm=1.0)
+    seen = []
+    tr = LoraTrainer(model, **kw)
+    full = tr.fit(proc, recs, epochs=2, samples_per_step=2, micro_batch=1, warmup_steps=2, eos_token_id=cfg.eos_token_id,
+                  on_step=lambda s, l, t: seen.append((s, t.lr)))
+    assert len(full) == 6 and tr.step_count == 6 and [s for s, _ in seen] == list(range(6))
+    assert seen[0][1] == 0.0 and abs(seen[2][1] - 5e-3) < 1e-12 and seen[5][1] < seen[3][1] and tr.lr == 5e-3
+    # interrupted after 4 steps, resumed from the checkpoint: same parameters as the uninterrupted run
+    ck = str(tmp_path / "ck" / "trainer.pt")
+    a = LoraTrainer(model, **kw)
+
+    class Stop(Exception):
+        pass
+
+    def bail(s, l, t):
+        if s == 3:
+            t.save_checkpoint(ck)
+            raise Stop
+
+    with pytest.raises(Stop):
+        a.fit(proc, recs, epochs=2, samples_per_step=2, micro_batch=1, warmup_steps=2, eos_token_id=cfg.eos_token_id, on_step=bail)
+    b = LoraTrainer(model, **kw)
+    rest = b.fit(proc, recs, epochs=2, samples_per_step=2, micro_batch=1, warmup_steps=2, eos_token_id=cfg.eos_token_id, checkpoint=ck)
+    assert len(rest) == 2 and b.step_count == 6
+    assert torch.equal(b.p, tr.p) and torch.equal(b.m, tr.m) and rest == full[4:]
+    with pytest.raises(ValueError):
+        LoraTrainer(model, r=4, seed=1).load_checkpoint(ck)
