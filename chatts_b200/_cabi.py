@@ -28,7 +28,7 @@ SYMBOLS = [
     "cts_attn_prefill_lse", "cts_attn_bwd", "cts_swiglu", "cts_swiglu_bwd", "cts_rmsnorm_bwd", "cts_qkv_rope_bwd",
     "cts_ce_loss_grad", "cts_gather_rows", "cts_lora_wgrad", "cts_adamw", "cts_grad_norm_ws_floats", "cts_grad_norm_clip",
     "cts_lora_pack",
-    "cts_sample_advance",
+    "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step",
 ]
 PACK_DESC_LONGS = 12
 
@@ -55,6 +55,22 @@ class ChainArgs(C.Structure):
         [(k, C.c_void_p) for k in ("wo", "wgu", "wd", "wqkv", "ao", "h", "xn", "act", "ln_post", "ln_next")] + [("eps", C.c_float)] +
         [(k, C.c_void_p) for k in ("bqkv", "q_norm_w", "k_norm_w", "positions", "cos_tab", "sin_tab", "slot_map", "q_out", "k_cache",
                                    "v_cache")] + [("page_size", C.c_int)] + [(k, C.c_void_p) for k in ("ws", "ssq", "sync")])
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("wqkv", "bqkv", "q_norm", "k_norm", "wo", "wgu", "wd", "ln1", "ln2", "k_cache", "v_cache")]
+
+
+class DecoderStepArgs(C.Structure):
+    _fields_ = (
+        [(k, C.c_int) for k in ("n_layers", "hidden", "inter", "nh", "nkv", "head_dim", "vocab", "vocab_rows", "page_size", "num_pages",
+                                "max_pages", "dtype", "batch", "sample")] + [("eps", C.c_float)] +
+        [(k, C.c_int) for k in ("split_qkv", "split_o", "split_gu", "split_d", "attn_splits")] +
+        [("layers", C.POINTER(LayerWeights))] +
+        [(k, C.c_void_p) for k in ("embed", "final_norm", "lm_head", "cos_tab", "sin_tab", "cur_ids", "positions", "seq_lens", "slot_map",
+                                   "page_table", "out_tokens")] + [("out_ld", C.c_int)] +
+        [(k, C.c_void_p) for k in ("step_ptr", "h", "xn", "q", "ao", "act", "logits", "ws")] + [("ws_floats", C.c_longlong)] +
+        [("attn_ws", C.c_void_p)])
 
 
 _lib = None
@@ -100,6 +116,13 @@ def load_library():
     lib.cts_decode_chain.restype = i
     lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cts_peer_greedy_advance.restype = i
+    lib.cts_rmsnorm.argtypes = [vp, vp, vp, f, vp, ll, ll, i, vp]
+    lib.cts_lm_head.argtypes = [vp, vp, vp, vp, ll, ll, ll, i, vp]
+    lib.cts_decoder_step_ws_floats.argtypes = [C.POINTER(DecoderStepArgs)]
+    lib.cts_decoder_step_ws_floats.restype = ll
+    lib.cts_decoder_step.argtypes = [vp, C.POINTER(DecoderStepArgs), vp]
+    for name in ("cts_rmsnorm", "cts_lm_head", "cts_decoder_step"):
+        getattr(lib, name).restype = i
     lib.cts_sample_advance.argtypes = [vp, vp, ll, i, f, i, f, C.c_ulonglong, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cts_sample_advance.restype = i
     # ---- A9: LoRA fine-tune step
@@ -263,6 +286,49 @@ class Context:
                                               _p(positions), _p(seq_lens), _p(slot_map), _p(page_table),
                                               page_table.shape[1] if page_table is not None else 0, page_size,
                                               dtype_code(logits.dtype), _stream()))
+
+    def rmsnorm(self, x, w, eps, out, t=None):
+        t = x.shape[0] if t is None else t
+        self._chk(self.lib.cts_rmsnorm(self.h, _p(x), _p(w), float(eps), _p(out), t, x.shape[-1], dtype_code(x.dtype), _stream()))
+
+    def lm_head(self, hidden, w, logits, t=None):
+        t = hidden.shape[0] if t is None else t
+        self._chk(self.lib.cts_lm_head(self.h, _p(hidden), _p(w), _p(logits), t, w.shape[1], w.shape[0], dtype_code(hidden.dtype), _stream()))
+
+    def decoder_step(self, *, layers, embed, final_norm, lm_head, cos, sin, hidden, inter, nh, nkv, head_dim, eps, page_size, batch,
+                     splits, attn_splits, cur_ids, positions, seq_lens, slot_map, page_table, out_tokens, step_ptr, h, xn, q, ao, act,
+                     logits, ws, attn_ws, sample=True):
+        """One whole decode step enqueued by ONE C call (cts_decoder_step).  ``layers``: list of dicts of tensors (wqkv, bqkv,
+        q_norm, k_norm, wo, wgu, wd, ln1, ln2, k_cache, v_cache); ``splits`` = (qkv, o, gu, d).  The ctypes layer table is
+        cached per list object."""
+        key = id(layers)
+        cache = self.__dict__.setdefault("_layer_tables", {})
+        if key not in cache:
+            arr = (LayerWeights * len(layers))()
+            for i2, lw in enumerate(layers):
+                for f2, _ in LayerWeights._fields_:
+                    t2 = lw.get(f2)
+                    setattr(arr[i2], f2, None if t2 is None else t2.data_ptr())
+            cache[key] = (arr, layers)                       # keep the list alive: the table holds raw pointers into it
+        arr = cache[key][0]
+        a = DecoderStepArgs()
+        a.n_layers, a.hidden, a.inter, a.nh, a.nkv, a.head_dim = len(layers), hidden, inter, nh, nkv, head_dim
+        a.vocab, a.vocab_rows = lm_head.shape[0], embed.shape[0]
+        a.page_size, a.num_pages, a.max_pages = page_size, layers[0]["k_cache"].shape[0], page_table.shape[1]
+        a.dtype, a.batch, a.sample, a.eps = dtype_code(h.dtype), batch, int(bool(sample)), float(eps)
+        a.split_qkv, a.split_o, a.split_gu, a.split_d = (int(v) for v in splits)
+        a.attn_splits = int(attn_splits)
+        a.layers = arr
+        dp = lambda x: None if x is None else x.data_ptr()
+        a.embed, a.final_norm, a.lm_head, a.cos_tab, a.sin_tab = dp(embed), dp(final_norm), dp(lm_head), dp(cos), dp(sin)
+        a.cur_ids, a.positions, a.seq_lens, a.slot_map, a.page_table = dp(cur_ids), dp(positions), dp(seq_lens), dp(slot_map), dp(page_table)
+        a.out_tokens, a.out_ld, a.step_ptr = dp(out_tokens), (out_tokens.stride(0) if out_tokens is not None else 0), dp(step_ptr)
+        a.h, a.xn, a.q, a.ao, a.act, a.logits = dp(h), dp(xn), dp(q), dp(ao), dp(act), dp(logits)
+        a.ws, a.ws_floats, a.attn_ws = dp(ws), ws.numel(), dp(attn_ws)
+        need = int(self.lib.cts_decoder_step_ws_floats(C.byref(a)))
+        if ws.numel() < need:
+            raise CtsError(f"decoder_step: split-K workspace holds {ws.numel()} floats, {need} needed")
+        self._chk(self.lib.cts_decoder_step(self.h, C.byref(a), _stream()), 3 + 9 * len(layers) + int(bool(sample)))
 
     def sample_advance(self, logits, batch, temperature, top_k, top_p, seed, out_tokens, step_ptr, cur_ids, positions, seq_lens,
                        slot_map, page_table, page_size):

@@ -64,7 +64,7 @@ class _Step:
 class ChatTSForCausalLM:
     def __init__(self, config, state_dict, device="cuda", dtype=torch.bfloat16, tp_rank=0, tp_size=1,
                  max_batch=32, max_seq_len=2048, page_size=64, use_cuda_graph=True, comm=None,
-                 use_peer_allreduce=True, graph_with_tp=True, use_chain=None, use_sample_kernel=None):
+                 use_peer_allreduce=True, graph_with_tp=True, use_chain=None, use_sample_kernel=None, use_native_step=None):
         if not torch.cuda.is_available():
             raise _cabi.CtsError("chatts_b200 needs a B200 (sm_100a) GPU; there is no CPU fallback")
         self.config, self.dtype = config, dtype
@@ -86,6 +86,9 @@ class ChatTSForCausalLM:
         self.use_chain = bool(int(_os.environ.get("CTS_DECODE_CHAIN", "0"))) if use_chain is None else bool(use_chain)
         # sampled decoding through cts_sample_advance (csrc/sampling.cu) instead of torch ops: off by default until the kernel has
         # run on a B200 (written after the round-1 GPU budget was spent); CTS_SAMPLE_KERNEL=1 / use_sample_kernel=True turns it on
+        # the whole decode step enqueued by one C call (cts_decoder_step) instead of ~440 ctypes calls: identical launches; off by
+        # default until compared with the Python orchestration on a B200 (CTS_NATIVE_STEP=1 / use_native_step=True)
+        self.use_native_step = bool(int(_os.environ.get("CTS_NATIVE_STEP", "0"))) if use_native_step is None else bool(use_native_step)
         self.use_sample_kernel = bool(int(_os.environ.get("CTS_SAMPLE_KERNEL", "0"))) if use_sample_kernel is None else bool(use_sample_kernel)
         self._load(state_dict)
         n_pos = min(cfg.max_position_embeddings, max(max_seq_len, 16))
@@ -303,6 +306,9 @@ class ChatTSForCausalLM:
         st.act = torch.empty(T, self.I, device=dev, dtype=dt)
         st.qkv = torch.empty(T, self.wqkv[0].shape[0], device=dev, dtype=dt) if st.splits["qkv"] == 1 else None
         ws_n = max(self._ws_floats(T, st.splits), T * self.H)
+        if decode and self.use_native_step:          # cts_decoder_step always takes the split-K partial path (also at factor 1)
+            sp = st.splits
+            ws_n = max(ws_n, sp["qkv"] * T * self.wqkv[0].shape[0], sp["o"] * T * self.H, sp["gu"] * T * 2 * self.I, sp["d"] * T * self.H)
         st.ws = torch.empty(ws_n, device=dev, dtype=torch.float32)                           # split-K partials [S, T, N]
         st.positions = torch.zeros(T, device=dev, dtype=torch.int32)
         st.slot_map = torch.zeros(T, device=dev, dtype=torch.int32)
@@ -444,6 +450,9 @@ class ChatTSForCausalLM:
         self._steps[key] = st
         return st
 
+    def _native_ok(self, B):
+        return self.use_native_step and self.tp_size == 1 and B <= 128 and not self._chain_ok(B)
+
     def _chain_ok(self, B):
         return (self.use_chain and self.tp_size == 1 and B <= 32 and self.H % 64 == 0 and self.H // 64 <= 192 and self.I % 64 == 0)
 
@@ -469,6 +478,20 @@ class ChatTSForCausalLM:
     def _decode_body(self, st, sample):
         c, B = self.ctx, st.B
         scale = 1.0 / math.sqrt(self.d)
+        if self._native_ok(B):
+            if not hasattr(self, "_layer_list"):
+                self._layer_list = [dict(wqkv=self.wqkv[l], bqkv=self.bqkv[l], q_norm=self.qn[l], k_norm=self.kn[l], wo=self.wo[l],
+                                         wgu=self.wgu[l], wd=self.wd[l], ln1=self.ln1[l], ln2=self.ln2[l], k_cache=self.kv[l, 0],
+                                         v_cache=self.kv[l, 1]) for l in range(self.L)]
+            sp = st.splits
+            c.decoder_step(layers=self._layer_list, embed=self.embed, final_norm=self.final_norm, lm_head=self.lm_head, cos=self.cos,
+                           sin=self.sin, hidden=self.H, inter=self.I, nh=self.nh, nkv=self.nkv, head_dim=self.d, eps=self.eps,
+                           page_size=self.page_size, batch=B, splits=(sp["qkv"], sp["o"], sp["gu"], sp["d"]), attn_splits=st.attn_splits,
+                           cur_ids=st.cur_ids, positions=st.positions, seq_lens=st.seq_lens, slot_map=st.slot_map, page_table=st.page_table,
+                           out_tokens=st.out_tokens, step_ptr=st.step_ptr, h=st.h, xn=st.xn, q=st.q, ao=st.ao, act=st.act,
+                           logits=st.logits, ws=st.ws, attn_ws=st.attn_ws, sample=sample)
+            st.full_logits = st.logits
+            return
         c.embed_gather(self.embed, st.cur_ids, st.h, t=B)
 
         def attend(l):

@@ -261,6 +261,51 @@ typedef struct {
 int cts_decode_chain(cts_ctx* ctx, const cts_chain_args* args, void* stream);
 
 
+/* ------------------------------------------------------------------------------------------------
+ * Whole decode step from C, and the two aliases of SURVEY.md 8(b)'s symbol list.  Host-side executors only: they enqueue the
+ * kernels above on `stream` (capturable into a CUDA graph), nothing new runs on the device.
+ *   cts_rmsnorm : out = w * dtype(x * rsqrt(mean(x^2) + eps))                      modeling_qwen2.py:258-263
+ *   cts_lm_head : logits[t, vocab] = hidden[t, h] @ w[vocab, h]^T                  chatts_vllm.py:607-610
+ *   cts_decoder_step : one decode step of the whole batch (modeling_qwen2.py:269-310 x n_layers; chatts_vllm.py:595-610):
+ *     embed(cur_ids) -> layers -> final norm -> lm_head -> (sample != 0) greedy advance of the device-side loop state.
+ *     Same launches and rounding points as the Python orchestration (chatts_b200/model.py:_decode_body, tp = 1).
+ */
+int cts_rmsnorm(cts_ctx* ctx, const void* x, const void* w, float eps, void* out, long long t, long long h, int dtype, void* stream);
+int cts_lm_head(cts_ctx* ctx, const void* hidden, const void* w, void* logits, long long t, long long h, long long vocab, int dtype,
+                void* stream);
+
+typedef struct {
+  const void* wqkv;   /* [(nh+2nkv)*d, hidden]                                       */
+  const void* bqkv;   /* [(nh+2nkv)*d] or NULL (Qwen3)                               */
+  const void* q_norm; /* [d] or NULL                                                 */
+  const void* k_norm; /* [d] or NULL                                                 */
+  const void* wo;     /* [hidden, nh*d]                                              */
+  const void* wgu;    /* [2*inter, hidden], gate/up INTERLEAVED (CTS_EPI_SWIGLU_IL)  */
+  const void* wd;     /* [hidden, inter]                                             */
+  const void* ln1;    /* input_layernorm [hidden]                                    */
+  const void* ln2;    /* post_attention_layernorm [hidden]                           */
+  void* k_cache;      /* [num_pages, nkv, page_size, d] of THIS layer                */
+  void* v_cache;
+} cts_layer_weights;
+
+typedef struct {
+  int n_layers, hidden, inter, nh, nkv, head_dim, vocab, vocab_rows;   /* vocab_rows: rows of the embedding table (0 = vocab) */
+  int page_size, num_pages, max_pages, dtype, batch, sample;
+  float eps;
+  int split_qkv, split_o, split_gu, split_d;   /* split-K factors (>= 1; cts_gemm_suggest_split gives the library's choice) */
+  int attn_splits;
+  const cts_layer_weights* layers;              /* HOST array [n_layers] */
+  const void* embed; const void* final_norm; const void* lm_head; const void* cos_tab; const void* sin_tab;
+  int* cur_ids; int* positions; int* seq_lens; int* slot_map; const int* page_table;     /* decode state, as cts_greedy_advance */
+  int* out_tokens; int out_ld; int* step_ptr;
+  void* h; void* xn; void* q; void* ao; void* act; void* logits;                         /* [batch, ...] activations */
+  float* ws; long long ws_floats;               /* split-K partials, >= cts_decoder_step_ws_floats(args) */
+  float* attn_ws;                               /* cts_attn_decode workspace (zero-filled once) */
+} cts_decoder_step_args;
+
+long long cts_decoder_step_ws_floats(const cts_decoder_step_args* args);
+int cts_decoder_step(cts_ctx* ctx, const cts_decoder_step_args* args, void* stream);
+
 /* ================================================================================================
  * A9  LoRA fine-tune step (BASELINE config 5: ChatTS-8B, forward + backward, data parallel).
  * The reference repo holds no training code (README.md:216-218 -> external ChatTS-Training; demo/demo_lora.ipynb cells

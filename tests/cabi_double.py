@@ -283,3 +283,28 @@ class TorchDouble:
                 if sl is not None: sl[b] += 1
                 if slot is not None and pt is not None: slot[b] = pt[b, int(pos[b]) // page] * page + int(pos[b]) % page
         step_ptr[0] += 1
+
+    # ------------------------------------------------------------------ host executors (csrc/decoder_step.cu)
+    def rmsnorm(self, x, w, eps, out, t=None): self.reduce_residual_rmsnorm(None, 0, x, None, w, eps, out, t=t)
+    def lm_head(self, hidden, w, logits, t=None): self.gemm(hidden, w, logits, t=t)
+    def decoder_step(self, *, layers, embed, final_norm, lm_head, cos, sin, hidden, inter, nh, nkv, head_dim, eps, page_size, batch, splits,
+                     attn_splits, cur_ids, positions, seq_lens, slot_map, page_table, out_tokens, step_ptr, h, xn, q, ao, act, logits, ws,
+                     attn_ws, sample=True):
+        """Same call sequence as cts_decoder_step: every projection through the split-K partial path."""
+        T, H, I, d = batch, hidden, inter, head_dim; sq, so, sg, sd_ = splits
+        self.embed_gather(embed, cur_ids, h, t=T)
+        self.reduce_residual_rmsnorm(None, 0, h, None, layers[0]["ln1"], eps, xn, t=T)
+        for l, w in enumerate(layers):
+            self.gemm(xn, w["wqkv"], ws, epilogue=3, split_k=sq, t=T)
+            self.qkv_rope_cache(ws, True, sq, w["bqkv"], positions, cos, sin, slot_map, q, w["k_cache"], w["v_cache"], None, None, T, nh, nkv, d,
+                                page_size, w["q_norm"], w["k_norm"], eps)
+            self.attn_decode(q, w["k_cache"], w["v_cache"], page_table, seq_lens, T, nh, nkv, d, page_size, d ** -0.5, attn_splits, attn_ws, ao)
+            self.gemm(ao, w["wo"], ws, epilogue=3, split_k=so, t=T)
+            self.reduce_residual_rmsnorm(ws, so, h, h, w["ln2"], eps, xn, t=T)
+            self.gemm(xn, w["wgu"], ws, epilogue=3, split_k=sg, t=T)
+            self.reduce_swiglu(ws, sg, T, I, act, interleaved=True)
+            self.gemm(act, w["wd"], ws, epilogue=3, split_k=sd_, t=T)
+            self.reduce_residual_rmsnorm(ws, sd_, h, h, layers[l + 1]["ln1"] if l + 1 < len(layers) else final_norm, eps, xn, t=T)
+        self.gemm(xn, lm_head, logits, t=T)
+        if sample:
+            self.greedy_advance(logits, T, out_tokens, step_ptr, cur_ids, positions, seq_lens, slot_map, page_table, page_size)

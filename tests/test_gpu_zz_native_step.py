@@ -1,0 +1,51 @@
+"""cts_decoder_step / cts_rmsnorm / cts_lm_head (csrc/decoder_step.cu: host-side executors over the validated kernels) against
+the per-kernel Python orchestration: the same launches in the same order must give bit-identical tokens and logits.
+PENDING: written after the round-1 GPU budget was spent -- xfail(strict=False) until it has run on a B200."""
+import numpy as np
+import pytest
+import torch
+
+from tests.gpu_util import ctx
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first B200 execution pending (round-1 GPU budget exhausted before this code could run)")]
+DT = torch.bfloat16
+
+
+def _models(qwen3, graph):
+    from chatts_b200 import ChatTSConfig, ChatTSProcessor, SimpleTokenizer
+    from chatts_b200.model import ChatTSForCausalLM
+    from chatts_b200.weights import synthetic_state_dict
+    cfg = ChatTSConfig.tiny()
+    if qwen3:
+        cfg.qk_norm, cfg.attention_bias = True, False
+    sd = synthetic_state_dict(cfg, seed=1234, device="cpu", dtype=DT, std=0.05)
+    kw = dict(dtype=DT, max_batch=4, max_seq_len=256, page_size=16, use_cuda_graph=graph)
+    proc = ChatTSProcessor(SimpleTokenizer(cfg.ts_token_start_index, cfg.pad_token_id, cfg.eos_token_id), cfg)
+    return ChatTSForCausalLM(cfg, sd, **kw), ChatTSForCausalLM(cfg, sd, use_native_step=True, **kw), proc
+
+
+@pytest.mark.parametrize("qwen3,graph", [(False, False), (True, True)])
+def test_native_step_is_bit_identical(qwen3, graph):
+    ref, native, proc = _models(qwen3, graph)
+    x = np.arange(256)
+    enc = proc(text=["A <ts><ts/> ?", "text only, longer prompt to pad the first"], timeseries=[np.sin(x / 9) * 4], return_tensors="pt")
+    a = ref.generate(**enc, max_new_tokens=24, ignore_eos=True)
+    b = native.generate(**enc, max_new_tokens=24, ignore_eos=True)
+    assert torch.equal(a, b)
+
+
+def test_rmsnorm_and_lm_head_aliases():
+    c = ctx()
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(9, 256, generator=g)).to(DT).cuda()
+    w = (torch.rand(256, generator=g) + 0.5).to(DT).cuda()
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    c.rmsnorm(x, w, 1e-6, a)
+    c.reduce_residual_rmsnorm(None, 0, x, None, w, 1e-6, b)
+    wl = (torch.randn(1000, 256, generator=g) * 0.05).to(DT).cuda()
+    la, lb = torch.empty(9, 1000, device="cuda", dtype=DT), torch.empty(9, 1000, device="cuda", dtype=DT)
+    c.lm_head(x, wl, la)
+    c.gemm(x, wl, lb)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(la, lb)

@@ -126,3 +126,15 @@ def test_vllm_request_shape(cabi_double):
     with pytest.raises(TypeError):                             # chatts_vllm.py:277-279
         llm.generate([{"prompt": "x <ts><ts/>", "multi_modal_data": {"timeseries": ["not a series"]}}],
                      SamplingParams(max_tokens=2))
+
+
+@pytest.mark.parametrize("split,qwen3", [(1, False), (3, True)])
+def test_native_step_executor_generates_the_same_tokens(cabi_double, split, qwen3):
+    """use_native_step=True routes the decode step through ctx.decoder_step (cts_decoder_step: one C call per step): same
+    tokens as the per-kernel orchestration, same paged-KV bookkeeping."""
+    cfg, sd, model, proc = _build(cabi_double, split, qwen3)
+    enc = proc(text=PROMPTS, timeseries=list(_series()), padding=True, return_tensors="pt")
+    ref = model.generate(**enc, max_new_tokens=9, ignore_eos=True)
+    cfg2, sd2, native, _ = _build(cabi_double, split, qwen3, use_native_step=True)
+    out = native.generate(**enc, max_new_tokens=9, ignore_eos=True)
+    assert torch.equal(out, ref) and len(native.pool.free) == native.pool.num_pages

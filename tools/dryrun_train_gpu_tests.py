@@ -38,4 +38,4 @@ def _init(self, config, state_dict, device="cpu", **kw):
     kw.setdefault("use_cuda_graph", False)
     _orig_init(self, config, state_dict, device="cpu", **kw)
 mm.ChatTSForCausalLM.__init__ = _init
-sys.exit(pytest.main([os.path.join(ROOT, "tests", "test_gpu_zz_train.py"), os.path.join(ROOT, "tests", "test_gpu_zz_sampling.py"), "-q", "-p", "no:cacheprovider", "--runxfail", "-m", "gpu"] + sys.argv[1:]))
+sys.exit(pytest.main([os.path.join(ROOT, "tests", "test_gpu_zz_train.py"), os.path.join(ROOT, "tests", "test_gpu_zz_sampling.py"), os.path.join(ROOT, "tests", "test_gpu_zz_native_step.py"), "-q", "-p", "no:cacheprovider", "--runxfail", "-m", "gpu"] + sys.argv[1:]))
