@@ -35,7 +35,7 @@ gu.record = lambda *a, **k: None
 import chatts_b200.model as mm
 _orig_init = mm.ChatTSForCausalLM.__init__
 def _init(self, config, state_dict, device="cpu", **kw):
-    kw.setdefault("use_cuda_graph", False)
+    kw["use_cuda_graph"] = False          # no CUDA streams / graphs on the CPU
     _orig_init(self, config, state_dict, device="cpu", **kw)
 mm.ChatTSForCausalLM.__init__ = _init
 sys.exit(pytest.main([os.path.join(ROOT, "tests", "test_gpu_zz_train.py"), os.path.join(ROOT, "tests", "test_gpu_zz_sampling.py"), os.path.join(ROOT, "tests", "test_gpu_zz_native_step.py"), "-q", "-p", "no:cacheprovider", "--runxfail", "-m", "gpu"] + sys.argv[1:]))
