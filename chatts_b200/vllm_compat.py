@@ -18,10 +18,15 @@ MAX_TS_PER_PROMPT = 50      # chatts_vllm.py:219-220
 
 @dataclass
 class SamplingParams:
+    """The fields the reference's callers set (llm_utils.py:153: temperature, top_p, max_tokens, stop_token_ids, stop, n;
+    demo/demo_vllm.py:24)."""
     max_tokens: int = 16
     temperature: float = 0.0
     top_p: float = 1.0
+    top_k: int = 0
     stop_token_ids: list = field(default_factory=list)
+    stop: list = field(default_factory=list)          # stop STRINGS: the text is cut before the first occurrence
+    n: int = 1                                        # completions per request (temperature > 0: independent seeds)
     ignore_eos: bool = False
     seed: int = None
 
@@ -62,8 +67,18 @@ class LLM:
         sp = sampling_params or SamplingParams()
         if isinstance(inputs, dict):
             inputs = [inputs]
+        n = max(1, int(sp.n))
+        if n > 1:
+            # n completions per request = n copies of the request in the batch, each row with its own draw
+            # (llm_utils.py:127-130 reads outputs[i].outputs[j].text for j < n)
+            flat = self._generate([r for r in inputs for _ in range(n)], sp)
+            return [RequestOutput(inputs[i]["prompt"], [flat[i * n + j].outputs[0] for j in range(n)]) for i in range(len(inputs))]
+        return self._generate(inputs, sp)
+
+    def _generate(self, inputs, sp):
         outs = []
         bs = self.model.max_batch
+        stops = [sp.stop] if isinstance(sp.stop, str) else list(sp.stop or [])
         for i0 in range(0, len(inputs), bs):
             chunk = inputs[i0:i0 + bs]
             prompts, series = [], []
@@ -79,9 +94,14 @@ class LLM:
             enc = self.processor(text=prompts, timeseries=series, padding=True, return_tensors="pt")
             S = enc["input_ids"].shape[1]
             ids = self.model.generate(**enc, max_new_tokens=sp.max_tokens, do_sample=sp.temperature > 0,
-                                      temperature=sp.temperature, top_p=sp.top_p, ignore_eos=sp.ignore_eos, seed=sp.seed,
+                                      temperature=sp.temperature, top_p=sp.top_p, top_k=(sp.top_k if sp.top_k and sp.top_k > 0 else None),
+                                      ignore_eos=sp.ignore_eos, seed=(None if sp.seed is None else sp.seed + i0),
                                       eos_token_id=(list(sp.stop_token_ids) or None))
             for b, req in enumerate(chunk):
                 toks = ids[b, S:].tolist()
-                outs.append(RequestOutput(req["prompt"], [CompletionOutput(self.tokenizer.decode(toks), toks)]))
+                text = self.tokenizer.decode(toks)
+                cut = min([text.find(st) for st in stops if st and st in text], default=-1)
+                if cut >= 0:
+                    text = text[:cut]
+                outs.append(RequestOutput(req["prompt"], [CompletionOutput(text, toks)]))
         return outs

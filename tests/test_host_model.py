@@ -128,6 +128,28 @@ def test_vllm_request_shape(cabi_double):
                      SamplingParams(max_tokens=2))
 
 
+def test_vllm_sampling_params_n_stop_topk(cabi_double):
+    """The SamplingParams fields the reference's workers set (llm_utils.py:153): n completions per request, stop strings,
+    stop_token_ids, top_k / top_p / temperature."""
+    from chatts_b200.vllm_compat import LLM, SamplingParams
+
+    cfg, sd, model, proc = _build(cabi_double)
+    a, _ = _series()
+    llm = LLM(model=model)
+    reqs = [{"prompt": "s: <ts><ts/>", "multi_modal_data": {"timeseries": [a]}}, {"prompt": "plain"}]
+    outs = llm.generate(reqs, SamplingParams(max_tokens=5, temperature=0.7, top_p=0.9, top_k=50, n=3, seed=4, ignore_eos=True))
+    assert len(outs) == 2 and all(len(o.outputs) == 3 for o in outs)
+    assert all(len(c.token_ids) == 5 for o in outs for c in o.outputs)
+    assert len({tuple(c.token_ids) for c in outs[0].outputs}) > 1           # independent draws per completion
+    again = llm.generate(reqs, SamplingParams(max_tokens=5, temperature=0.7, top_p=0.9, top_k=50, n=3, seed=4, ignore_eos=True))
+    assert [[c.token_ids for c in o.outputs] for o in again] == [[c.token_ids for c in o.outputs] for o in outs]
+    g = llm.generate(reqs[1:], SamplingParams(max_tokens=8, ignore_eos=True))[0].outputs[0]
+    if len(g.text) >= 3:                                                       # cut BEFORE the first stop string
+        stop = g.text[2:3]
+        cut = llm.generate(reqs[1:], SamplingParams(max_tokens=8, ignore_eos=True, stop=[stop]))[0].outputs[0]
+        assert cut.text == g.text[: g.text.find(stop)] and stop not in cut.text
+
+
 @pytest.mark.parametrize("split,qwen3", [(1, False), (3, True)])
 def test_native_step_executor_generates_the_same_tokens(cabi_double, split, qwen3):
     """use_native_step=True routes the decode step through ctx.decoder_step (cts_decoder_step: one C call per step): same
