@@ -360,3 +360,89 @@ def test_training_reduces_loss_and_merge_roundtrip(tmp_path):
     assert model.merge_lora(str(tmp_path / "ad")) == cfg.num_hidden_layers * 7
     lm = float(LoraTrainer(model, r=16, lora_alpha=32, seed=0).eval_loss(batch)[0])
     assert abs(lm - lt) < 3e-2 * lt, (lm, lt)
+
+
+def _id_batch(cfg, samples, seed, n_series=2, series_len=256, prefix=20, prompt=24, answer=40):
+    """Token-id level records (BASELINE cfg5 shape, scaled down in length): prefix ids + <ts><ts/> per series, prompt, answer."""
+    from chatts_b200.processor import sp_encoding
+    rng = np.random.default_rng(seed)
+    hi = min(cfg.vocab_size, cfg.ts_token_start_index) - 10          # stay clear of <ts>, <ts/>, eos, pad
+    ids, lab, series = [], [], []
+    for b in range(samples):
+        row = []
+        for k in range(n_series):
+            row += rng.integers(0, hi, prefix).tolist() + [cfg.ts_token_start_index, cfg.ts_token_start_index + 1]
+            t = np.arange(series_len - 16 * ((b + k) % 3))                      # ragged lengths: 256 / 240 / 224 points
+            series.append(sp_encoding(np.sin(t / (5.0 + k)) * (1 + b) + 0.01 * t)[0])
+        row += rng.integers(0, hi, prompt).tolist()
+        ans = rng.integers(0, hi, answer).tolist()
+        ids.append(row + ans)
+        lab.append([-100] * len(row) + ans)
+    L = max(e.shape[0] for e in series)
+    ts = np.zeros((len(series), L, 1))
+    for i, e in enumerate(series):
+        ts[i, : e.shape[0]] = e
+    ids = torch.tensor(ids, dtype=torch.long)
+    return {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": torch.tensor(lab, dtype=torch.long),
+            "timeseries": torch.from_numpy(ts).to(torch.float32)}
+
+
+@PENDING
+@pytest.mark.parametrize("full_dims", [False, True])
+def test_gradient_is_the_directional_derivative_of_the_loss(full_dims):
+    """Size-independent property of the whole backward (no oracle needed, so it also runs at the ChatTS-8B layer shape of
+    BASELINE config 5): along D = grad/|grad| in adapter space, (L(p + eD) - L(p - eD)) / 2e == <grad L, D> = |grad|.  Also: the
+    gradient of a batch is the sum of its micro-batches' gradients (token-mean over the union), and every adapter tensor
+    receives a finite, non-zero gradient."""
+    from chatts_b200 import ChatTSConfig
+    from chatts_b200.model import ChatTSForCausalLM
+    from chatts_b200.train import LoraTrainer
+
+    if full_dims:
+        cfg = ChatTSConfig.chatts_8b()
+        cfg.num_hidden_layers = 2                                  # 8B layer shapes (H 4096, I 12288, 32/8 heads x 128, V 151936), 2 layers
+        model = ChatTSForCausalLM.from_synthetic(cfg, seed=7, max_batch=1, max_seq_len=512, page_size=64, use_cuda_graph=False)
+        samples = 6
+    else:
+        cfg = ChatTSConfig.tiny(qk_norm=True, attention_bias=False)
+        from chatts_b200.weights import synthetic_state_dict
+        sd = synthetic_state_dict(cfg, seed=7, device="cpu", dtype=DT, std=0.05)
+        model = ChatTSForCausalLM(cfg, sd, dtype=DT, max_batch=1, max_seq_len=512, page_size=16, use_cuda_graph=False)
+        samples = 4
+    tr = LoraTrainer(model, r=16, lora_alpha=32, seed=2, init_b_std=0.02, max_grad_norm=0.0)
+    batch = _id_batch(cfg, samples, seed=5)
+    tr.zero_grad()
+    tr.forward_backward(**batch)
+    g = tr.g.clone()
+    assert torch.isfinite(g).all()
+    for name in tr.index:
+        assert float(tr.grad(name).abs().max()) > 0, name
+    # micro-batches: same gradient as the whole batch when normalised by the same label count
+    total = LoraTrainer.count_labels(batch)
+    half = samples // 2
+    n_ser = 2
+    parts = [{k: (v[:half] if k != "timeseries" else v[: half * n_ser]) for k, v in batch.items()},
+             {k: (v[half:] if k != "timeseries" else v[half * n_ser:]) for k, v in batch.items()}]
+    tr.zero_grad()
+    for p in parts:
+        tr.forward_backward(**p, denominator=total, accumulate_loss=True)
+    e_acc = rel_err(tr.g, g)
+    # directional derivative along a random unit direction, step sized for a loss change well above bf16 noise
+    # along the gradient itself (a random direction in a 10^5..10^7-dimensional space has a slope too small to see through
+    # the bf16 noise of the loss): slope = ||g||, step sized for a predicted loss change of 0.03 per side
+    D = g / g.norm()
+    slope = float((g * D).sum())
+    p0 = tr.p.clone()
+    eps = 0.03 / max(abs(slope), 1e-6)
+    losses = []
+    for sgn in (+1.0, -1.0):
+        tr.p.copy_(p0 + sgn * eps * D)
+        tr.pack()
+        losses.append(float(tr.eval_loss(batch)[0]))
+    tr.p.copy_(p0)
+    tr.pack()
+    fd = (losses[0] - losses[1]) / (2 * eps)
+    record("train_directional_derivative", full_dims=full_dims, slope=slope, finite_difference=fd, eps=eps, accumulation_rel_err=e_acc,
+           loss_plus=losses[0], loss_minus=losses[1])
+    assert e_acc < 3e-2, e_acc
+    assert abs(fd - slope) < 0.15 * abs(slope) + 1e-4, (fd, slope)

@@ -230,3 +230,26 @@ def test_fit_schedule_accumulation_and_resume(cabi_double, tmp_path):
     assert torch.equal(b.p, tr.p) and torch.equal(b.m, tr.m) and rest == full[4:]
     with pytest.raises(ValueError):
         LoraTrainer(model, r=4, seed=1).load_checkpoint(ck)
+
+
+def test_gradient_is_the_directional_derivative(cabi_double):
+    """No oracle involved: along D = g/|g|, (L(p + eD) - L(p - eD)) / 2e must equal |g| (the whole backward is the derivative
+    of the loss the forward computes).  The same property is the GPU test at the ChatTS-8B layer shape."""
+    from chatts_b200.train import LoraTrainer, encode_records
+
+    cfg, sd, model, proc = _build(cabi_double, True)
+    tr = LoraTrainer(model, r=8, lora_alpha=16, seed=2, init_b_std=0.02, max_grad_norm=0.0)
+    batch = encode_records(proc, RECORDS, eos_token_id=cfg.eos_token_id)
+    tr.zero_grad()
+    tr.forward_backward(**batch)
+    g, p0 = tr.g.clone(), tr.p.clone()
+    D = g / g.norm()
+    slope = float(g.norm())
+    eps = 0.03 / slope
+    vals = []
+    for sgn in (1.0, -1.0):
+        tr.p.copy_(p0 + sgn * eps * D)
+        tr.pack()
+        vals.append(float(tr.eval_loss(batch)[0]))
+    fd = (vals[0] - vals[1]) / (2 * eps)
+    assert abs(fd - slope) < 0.05 * slope, (fd, slope)
