@@ -13,6 +13,7 @@
 // building blocks as the validated round-0 prefill kernel (attention.cu).  The tcgen05/TMEM version is a round-2 item
 // (DESIGN.md); no mbarrier / flag spin anywhere in this file.
 #include <mma.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -384,6 +385,16 @@ attn_bwd_dkv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
 
 }  // namespace
 
+// tcgen05 / TMEM version for head_dim 128 (attention_bwd_tc5.cu); opt-in until it has been validated on a B200
+int cts_attn_bwd_tc5_launch(cts_ctx* ctx, const void* q, const void* k, const void* v, const void* dout, const float* lse,
+                            const float* delta, const int* cu_seqlens, int batch, int max_seqlen, long long total_tokens, int nh,
+                            int nkv, float scale, void* dq, void* dk, void* dv, int dtype, cudaStream_t st);
+
+static bool attn_bwd_use_tc5() {          // read per call (host side, once per launch): tests flip it inside one process
+  const char* e = getenv("CTS_ATTN_BWD_TC5");
+  return e && e[0] == '1';
+}
+
 extern "C" int cts_attn_bwd(cts_ctx* ctx, const void* q, const void* k, const void* v, const void* out, const void* dout,
                             const float* lse, const int* cu_seqlens, int batch, int max_seqlen, long long total_tokens, int nh,
                             int nkv, int head_dim, float scale, float* delta_ws, void* dq, void* dk, void* dv, int dtype,
@@ -399,6 +410,17 @@ extern "C" int cts_attn_bwd(cts_ctx* ctx, const void* q, const void* k, const vo
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows = total_tokens * nh;
   const unsigned tiles = (unsigned)((max_seqlen + kBwTile - 1) / kBwTile);
+  if (head_dim == 128 && attn_bwd_use_tc5()) {
+    if (dtype == CTS_BF16) {
+      CTS_CUDA(ctx, launch_pdl(attn_bwd_delta_kernel<__nv_bfloat16>, dim3((unsigned)cdiv_ll(rows, 8)), dim3(256), 0, st, 1,
+                               (const __nv_bfloat16*)out, (const __nv_bfloat16*)dout, delta_ws, rows, 128));
+    } else {
+      CTS_CUDA(ctx, launch_pdl(attn_bwd_delta_kernel<__half>, dim3((unsigned)cdiv_ll(rows, 8)), dim3(256), 0, st, 1, (const __half*)out,
+                               (const __half*)dout, delta_ws, rows, 128));
+    }
+    return cts_attn_bwd_tc5_launch(ctx, q, k, v, dout, lse, delta_ws, cu_seqlens, batch, max_seqlen, total_tokens, nh, nkv, scale, dq, dk,
+                                   dv, dtype, st);
+  }
 #define BW_LAUNCH(TT, HDV)                                                                                                  \
   {                                                                                                                         \
     CTS_CUDA(ctx, launch_pdl(attn_bwd_delta_kernel<TT>, dim3((unsigned)cdiv_ll(rows, 8)), dim3(256), 0, st, 1, (const TT*)out,  \
