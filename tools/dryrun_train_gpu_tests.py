@@ -1,4 +1,4 @@
-"""Dry-run of tests/test_gpu_zz_train.py and tests/test_gpu_zz_sampling.py on a machine WITHOUT a GPU: `ctx()` returns the torch test double, `.cuda()` is the
+"""Dry-run of the training / sampling / native-step GPU test files on a machine WITHOUT a GPU: `ctx()` returns the torch test double, `.cuda()` is the
 identity and `device="cuda"` is dropped, so the TEST LOGIC (shapes, arguments, reference arithmetic, tolerances) is
 exercised end to end.  A failure on the B200 then points at a kernel, not at the test.  TEST INFRASTRUCTURE ONLY.
 
@@ -41,5 +41,6 @@ mm.ChatTSForCausalLM.__init__ = _init
 extra = sys.argv[1:]
 if "-k" not in extra:          # the ChatTS-8B-shaped case generates its weights on the device: GPU only
     extra += ["-k", "not (directional and True)"]
-sys.exit(pytest.main([os.path.join(ROOT, "tests", f) for f in ("test_gpu_zz_train.py", "test_gpu_zz_sampling.py", "test_gpu_zz_native_step.py")] +
+sys.exit(pytest.main([os.path.join(ROOT, "tests", f) for f in ("test_gpu_train_kernels.py", "test_gpu_zz_train.py", "test_gpu_zzz_sampling.py", "test_gpu_zzz_native_step.py",
+                                                         "test_gpu_zzzz_attn_bwd_tc5.py")] +
                      ["-q", "-p", "no:cacheprovider", "--runxfail", "-m", "gpu"] + extra))
