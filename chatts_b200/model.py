@@ -158,6 +158,13 @@ class ChatTSForCausalLM:
               torch.bfloat16: torch.bfloat16, None: getattr(torch, cfg.torch_dtype, torch.bfloat16)}[torch_dtype]
         dev = device if device is not None else (f"cuda:{device_map}" if isinstance(device_map, int) else (device_map or "cuda"))
         sd = load_checkpoint(path, device="cpu")
+        if any(k.endswith(".qweight") for k in sd):                # GPTQ-Int4 checkpoint: dequantise at load time (weights.py)
+            import json as _json
+            import os as _os
+            from .weights import dequantize_gptq
+            cj = _os.path.join(path, "config.json") if _os.path.isdir(path) else path
+            qc = _json.load(open(cj)).get("quantization_config", {})
+            sd = dequantize_gptq(sd, qc, dtype=dt)
         return cls(cfg, sd, device=dev, dtype=dt, **kw)
 
     # ------------------------------------------------------------------------------------------ LoRA

@@ -98,6 +98,76 @@ def load_checkpoint(path, device="cpu", dtype=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# GPTQ-Int4 checkpoints (README.md:52,262-263 advertise ChatTS-{8B,14B}-GPTQ-Int4).
+# Load-time dequantisation to the model dtype: the quantised checkpoints then run on the same bf16/fp16 kernels (same speed
+# and memory as the full-precision model -- a W4A16 decode GEMM is not built).  Packing per AutoGPTQ / optimum's published
+# `QuantLinear` (UNVERIFIED offline against a real checkpoint -- none is available; the CPU test is a pack/unpack round trip):
+#   qweight int32 [in/8, out]   : 8 consecutive INPUT indices per word, low nibble first
+#   qzeros  int32 [groups, out/8]: 8 consecutive OUTPUT indices per word; checkpoint_format "gptq" stores zero - 1
+#   scales  fp16  [groups, out];  g_idx int32 [in] (group of every input row; absent = i // group_size)
+#   W[out, in] = scales[g, out] * (q[in, out] - zero[g, out])
+# --------------------------------------------------------------------------------------------------
+def _unpack_nibbles(t, axis):
+    """int32 words -> 8 four-bit values each, expanded along ``axis``."""
+    sh = torch.arange(0, 32, 4, dtype=torch.int32, device=t.device)
+    if axis == 0:
+        v = (t[:, None, :] >> sh[None, :, None]) & 0xF
+        return v.reshape(t.shape[0] * 8, t.shape[1])
+    v = (t[:, :, None] >> sh[None, None, :]) & 0xF
+    return v.reshape(t.shape[0], t.shape[1] * 8)
+
+
+def dequantize_gptq_linear(qweight, qzeros, scales, g_idx=None, group_size=128, zero_offset=1, dtype=torch.bfloat16):
+    q = _unpack_nibbles(qweight.to(torch.int32), 0)                       # [in, out]
+    z = _unpack_nibbles(qzeros.to(torch.int32), 1)[:, : scales.shape[1]] + int(zero_offset)   # [groups, out]
+    n_in = q.shape[0]
+    g = (torch.arange(n_in, device=q.device) // int(group_size)) if g_idx is None else g_idx.to(torch.long)
+    w = scales.to(torch.float32)[g] * (q - z[g]).to(torch.float32)        # [in, out]
+    return w.t().contiguous().to(dtype)
+
+
+def dequantize_gptq(sd, quant_cfg=None, dtype=torch.bfloat16):
+    """Replace every ``<name>.{qweight,qzeros,scales[,g_idx]}`` group of a GPTQ checkpoint by ``<name>.weight``."""
+    quant_cfg = quant_cfg or {}
+    bits = int(quant_cfg.get("bits", 4))
+    if bits != 4:
+        raise ValueError(f"GPTQ checkpoints with {bits}-bit weights are not supported (4-bit only)")
+    gs = int(quant_cfg.get("group_size", 128))
+    zo = 0 if str(quant_cfg.get("checkpoint_format", "gptq")) == "gptq_v2" else 1
+    out = {}
+    for k, t in sd.items():
+        if k.endswith(".qweight"):
+            base = k[: -len(".qweight")]
+            n_in = t.shape[0] * 8
+            group = gs if gs > 0 else n_in                              # group_size -1: one group per column
+            out[base + ".weight"] = dequantize_gptq_linear(t, sd[base + ".qzeros"], sd[base + ".scales"], sd.get(base + ".g_idx"),
+                                                            group, zo, dtype)
+        elif k.endswith((".qzeros", ".scales", ".g_idx")) and (k.rsplit(".", 1)[0] + ".qweight") in sd:
+            continue
+        else:
+            out[k] = t
+    return out
+
+
+def pack_gptq_linear(w, group_size=128, zero_offset=1):
+    """Inverse of dequantize_gptq_linear for tests: asymmetric 4-bit round-to-nearest per (group, out) -> packed tensors."""
+    wt = w.to(torch.float32).t().contiguous()                             # [in, out]
+    n_in, n_out = wt.shape
+    G = n_in // group_size
+    wg = wt.view(G, group_size, n_out)
+    lo, hi = wg.min(1).values, wg.max(1).values
+    scale = ((hi - lo) / 15.0).clamp_min(1e-8)
+    zero = torch.round(-lo / scale).clamp(0, 15)
+    q = torch.clamp(torch.round(wg / scale[:, None]) + zero[:, None], 0, 15).to(torch.int32).view(n_in, n_out)
+    sh = torch.arange(0, 32, 4, dtype=torch.int64)
+    qweight = ((q.view(n_in // 8, 8, n_out).to(torch.int64) << sh[None, :, None]).sum(1) & 0xFFFFFFFF)
+    zs = (zero.to(torch.int64) - zero_offset) & 0xF
+    qzeros = ((zs.view(G, n_out // 8, 8) << sh[None, None, :]).sum(2) & 0xFFFFFFFF)
+    to_i32 = lambda x: torch.where(x >= 2 ** 31, x - 2 ** 32, x).to(torch.int32)
+    return to_i32(qweight), to_i32(qzeros), scale.to(torch.float16), (torch.arange(n_in) // group_size).to(torch.int32)
+
+
+# --------------------------------------------------------------------------------------------------
 # tensor parallel shard plan (Megatron style; SURVEY.md §8e): column split of QKV / gate / up / lm_head,
 # row split of o_proj / down_proj, kv heads divided across ranks (nkv % tp == 0), everything else replicated.
 # --------------------------------------------------------------------------------------------------

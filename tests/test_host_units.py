@@ -69,3 +69,31 @@ def test_page_pool():
         pool.alloc(1)
     pool.release(a)
     assert sorted(pool.alloc(3)) == sorted(a)
+
+
+def test_gptq_int4_dequantisation_roundtrip(tmp_path):
+    """GPTQ-Int4 checkpoints (README.md:262-263) are dequantised at load time: pack -> unpack reproduces the 4-bit grid, for
+    both zero conventions, with and without g_idx, and a packed checkpoint loads through load_checkpoint + dequantize_gptq."""
+    import torch
+    from safetensors.torch import save_file
+    from chatts_b200.weights import dequantize_gptq, dequantize_gptq_linear, load_checkpoint, pack_gptq_linear
+
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(48, 256, generator=g) * 0.05                       # [out, in]
+    for zo in (1, 0):
+        qw, qz, sc, gi = pack_gptq_linear(w, group_size=128, zero_offset=zo)
+        assert qw.shape == (32, 48) and qz.shape == (2, 6) and sc.shape == (2, 48) and qw.dtype == torch.int32
+        d1 = dequantize_gptq_linear(qw, qz, sc, gi, 128, zo, torch.float32)
+        d2 = dequantize_gptq_linear(qw, qz, sc, None, 128, zo, torch.float32)
+        assert torch.equal(d1, d2) and d1.shape == w.shape
+        step = sc.float().t().repeat_interleave(128, 1)                  # quantisation step of every element
+        assert float(((d1 - w).abs() / step).max()) <= 0.5 + 2e-2       # round-to-nearest on the 4-bit grid (fp16 scales)
+    qw, qz, sc, gi = pack_gptq_linear(w, 128, 1)
+    save_file({"model.layers.0.mlp.up_proj.qweight": qw, "model.layers.0.mlp.up_proj.qzeros": qz, "model.layers.0.mlp.up_proj.scales": sc,
+               "model.layers.0.mlp.up_proj.g_idx": gi, "model.norm.weight": torch.ones(4)}, str(tmp_path / "model.safetensors"))
+    sd = dequantize_gptq(load_checkpoint(str(tmp_path)), {"bits": 4, "group_size": 128}, dtype=torch.bfloat16)
+    assert set(sd) == {"model.layers.0.mlp.up_proj.weight", "model.norm.weight"}
+    assert sd["model.layers.0.mlp.up_proj.weight"].dtype == torch.bfloat16 and sd["model.layers.0.mlp.up_proj.weight"].shape == (48, 256)
+    import pytest
+    with pytest.raises(ValueError):
+        dequantize_gptq({"a.qweight": qw, "a.qzeros": qz, "a.scales": sc}, {"bits": 8})
