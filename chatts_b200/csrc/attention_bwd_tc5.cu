@@ -13,7 +13,7 @@
 // Round-1 pipeline: one tile in flight (TMA of tile j+1 overlaps the MMAs of tile j through the full/empty barriers; the
 // tensor core idles while the softmax warps work).  Every mbarrier wait is bounded (common.cuh: a protocol bug traps, it
 // cannot hang the box).  OPT-IN (CTS_ATTN_BWD_TC5=1): written after the round-1 GPU budget was spent, not yet executed on a
-// B200; the HMMA kernels of attention_bwd.cu stay the default until this one has passed tests/test_gpu_zzzz_attn_bwd_tc5.py.
+// B200; the HMMA kernels of attention_bwd.cu stay the default until this one has passed tests/test_gpu_zz_d_attn_bwd_tc5.py.
 #include <type_traits>
 
 #include "common.cuh"

@@ -3,7 +3,7 @@
 RoPE(+q/k-norm) backward, fused cross entropy, row gather and the LoRA weight-gradient kernel -- through the C-ABI against
 the torch restatement of every entry point (tests/cabi_double.py, fp32 on the CPU, itself checked against oracle/lora.py by
 tests/test_host_train.py).  The parts of the training path still waiting for their first GPU run live in
-tests/test_gpu_zz_train.py."""
+tests/test_gpu_zz_c_train.py."""
 import math
 
 import numpy as np

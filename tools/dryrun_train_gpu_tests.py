@@ -41,6 +41,6 @@ mm.ChatTSForCausalLM.__init__ = _init
 extra = sys.argv[1:]
 if "-k" not in extra:          # the ChatTS-8B-shaped case generates its weights on the device: GPU only
     extra += ["-k", "not (directional and True)"]
-sys.exit(pytest.main([os.path.join(ROOT, "tests", f) for f in ("test_gpu_train_kernels.py", "test_gpu_zz_train.py", "test_gpu_zzz_sampling.py", "test_gpu_zzz_native_step.py",
-                                                         "test_gpu_zzzz_attn_bwd_tc5.py")] +
+sys.exit(pytest.main([os.path.join(ROOT, "tests", f) for f in ("test_gpu_train_kernels.py", "test_gpu_zz_c_train.py", "test_gpu_zz_b_sampling.py", "test_gpu_zz_a_native_step.py",
+                                                         "test_gpu_zz_d_attn_bwd_tc5.py")] +
                      ["-q", "-p", "no:cacheprovider", "--runxfail", "-m", "gpu"] + extra))

@@ -8,13 +8,13 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_metrics.jsonl
 STATUS=0
-for f in train_kernels zzz_sampling zzz_native_step zzzz_attn_bwd_tc5; do          # each file in its own process: a trapped kernel cannot take the rest down
+for f in train_kernels zz_a_native_step zz_b_sampling zz_d_attn_bwd_tc5; do          # each file in its own process: a trapped kernel cannot take the rest down
   echo "=== tests/test_gpu_$f.py (--runxfail)"
   timeout 300 python -m pytest tests/test_gpu_$f.py -q -m gpu --runxfail --no-header -p no:cacheprovider -rfE > gpurun_out/test_$f.log 2>&1
   echo "rc=$?"; tail -n 12 gpurun_out/test_$f.log
 done
-echo "=== tests/test_gpu_zz_train.py (--runxfail)"
-timeout ${TEST_TIMEOUT:-600} python -m pytest tests/test_gpu_zz_train.py -q -m gpu --runxfail --no-header -p no:cacheprovider -rfE \
+echo "=== tests/test_gpu_zz_c_train.py (--runxfail)"
+timeout ${TEST_TIMEOUT:-600} python -m pytest tests/test_gpu_zz_c_train.py -q -m gpu --runxfail --no-header -p no:cacheprovider -rfE \
    > gpurun_out/test_train.log 2>&1
 rc=$?
 tail -n 40 gpurun_out/test_train.log
