@@ -575,6 +575,14 @@ extern "C" int cts_gather_rows(cts_ctx* ctx, const void* src, const int* idx, lo
   return CTS_OK;
 }
 
+// tensor-core variant (lora_wgrad_mma.cu), opt-in through CTS_WGRAD_MMA=1 until it has run on a B200
+bool cts_lora_wgrad_mma_enabled();
+bool cts_lora_wgrad_mma_ok(const void* p, long long p_ld, long long p_col0, int p_il, long long m, const void* q, long long q_ld,
+                           long long q_col0, int r);
+int cts_lora_wgrad_mma_launch(cts_ctx* ctx, const void* p, long long p_ld, long long p_col0, int p_il, long long m, const void* q,
+                              long long q_ld, long long q_col0, int r, long long t, float scale, float* out, long long so_m,
+                              long long so_r, int dtype, cudaStream_t st);
+
 extern "C" int cts_lora_wgrad(cts_ctx* ctx, const void* p, long long p_ld, long long p_col0, int p_il, long long m, const void* q,
                               long long q_ld, long long q_col0, int r, long long t, float scale, float* out, long long so_m,
                               long long so_r, int dtype, void* stream) {
@@ -586,6 +594,9 @@ extern "C" int cts_lora_wgrad(cts_ctx* ctx, const void* p, long long p_ld, long 
   CTS_CHECK_ARG(ctx, r > 0 && r <= 64 && t >= 0, "1 <= r <= 64");
   CTS_CHECK_DTYPE(ctx, dtype);
   if (t == 0) return CTS_OK;
+  if (cts_lora_wgrad_mma_enabled() && cts_lora_wgrad_mma_ok(p, p_ld, p_col0, p_il, m, q, q_ld, q_col0, r))
+    return cts_lora_wgrad_mma_launch(ctx, p, p_ld, p_col0, p_il, m, q, q_ld, q_col0, r, t, scale, out, so_m, so_r, dtype,
+                                     (cudaStream_t)stream);
   const long long tiles = cdiv_ll(m, kWgM) * cdiv_ll(r, kWgR);
   long long splits = (4LL * ctx->sm_count) / tiles;                  // ~4 CTAs per SM over the whole grid
   const long long max_splits = cdiv_ll(t, 256);                      // at least 256 tokens (32 per warp) per CTA

@@ -304,3 +304,30 @@ def test_gradient_is_the_directional_derivative_of_the_loss(full_dims):
            loss_plus=losses[0], loss_minus=losses[1])
     assert e_acc < 3e-2, e_acc
     assert abs(fd - slope) < 0.15 * abs(slope) + 1e-4, (fd, slope)
+
+
+@PENDING
+@pytest.mark.parametrize("t,m,r,il", [(37, 256, 8, 0), (5000, 704, 16, 0), (300, 128, 16, 1), (300, 128, 16, 2), (9000, 64, 16, 0),
+                                      (100, 4096, 16, 0), (513, 200, 24, 0)])
+def test_lora_wgrad_tensor_core_variant(t, m, r, il, monkeypatch):
+    """lora_wgrad_mma.cu (CTS_WGRAD_MMA=1): ldmatrix.trans + mma.sync version of the weight gradient against the restatement
+    and against the validated FMA kernel."""
+    c = ctx()
+    g = _g(t + m + r)
+    ld = 2 * m if il else m + 64
+    col0 = 0 if il else 32
+    p, q = _rn(g, t, ld, std=0.5), _rn(g, t, 3 * r + 8, std=0.5)
+    for so_m, so_r, name in ((r, 1, "dB"), (1, m, "dA")):
+        base = torch.randn(m * r, generator=g)
+        ref = base.clone()
+        DBL.lora_wgrad(p, col0, il, m, q, r, r, t, 0.5, ref, so_m, so_r)
+        got = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("CTS_WGRAD_MMA", flag)
+            out = base.clone().cuda()
+            c.lora_wgrad(p.cuda(), col0, il, m, q.cuda(), r, r, t, 0.5, out, so_m, so_r)
+            torch.cuda.synchronize()
+            got[flag] = out
+        e, cross = rel_err(got["1"], ref), rel_err(got["1"], got["0"])
+        record("lora_wgrad_mma", t=t, m=m, r=r, il=il, layout=name, err=e, vs_fma=cross)
+        assert e < 2e-4 and cross < 2e-4, (name, e, cross)
