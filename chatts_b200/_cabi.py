@@ -28,7 +28,7 @@ SYMBOLS = [
     "cts_attn_prefill_lse", "cts_attn_bwd", "cts_swiglu", "cts_swiglu_bwd", "cts_rmsnorm_bwd", "cts_qkv_rope_bwd",
     "cts_ce_loss_grad", "cts_gather_rows", "cts_lora_wgrad", "cts_adamw", "cts_grad_norm_ws_floats", "cts_grad_norm_clip",
     "cts_lora_pack",
-    "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step",
+    "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step", "cts_ts_encode",
 ]
 PACK_DESC_LONGS = 12
 
@@ -71,6 +71,15 @@ class DecoderStepArgs(C.Structure):
                                    "page_table", "out_tokens")] + [("out_ld", C.c_int)] +
         [(k, C.c_void_p) for k in ("step_ptr", "h", "xn", "q", "ao", "act", "logits", "ws")] + [("ws_floats", C.c_longlong)] +
         [("attn_ws", C.c_void_p)])
+
+
+class TsEncodeArgs(C.Structure):
+    _fields_ = ([("x", C.c_void_p)] + [(k, C.c_int) for k in ("dtype", "n_series", "row_len", "num_features", "patch_size", "mode")] +
+                [("pos_table", C.c_void_p)] + [(k, C.c_int) for k in ("emb_dim", "max_seq_len", "num_layers", "hidden", "in0")] +
+                [("weights", C.POINTER(C.c_void_p)), ("biases", C.POINTER(C.c_void_p))] +
+                [(k, C.c_void_p) for k in ("valid_len", "patch_cnt", "row_offset", "max_valid")] + [("total_rows", C.c_longlong)] +
+                [("rows_ws", C.c_void_p), ("act_ws", C.c_void_p * 2), ("splitk_ws", C.c_void_p), ("splitk_floats", C.c_longlong),
+                 ("out", C.c_void_p), ("out_ld", C.c_longlong), ("row_map", C.c_void_p)])
 
 
 _lib = None
@@ -116,6 +125,8 @@ def load_library():
     lib.cts_decode_chain.restype = i
     lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cts_peer_greedy_advance.restype = i
+    lib.cts_ts_encode.argtypes = [vp, C.POINTER(TsEncodeArgs), vp]
+    lib.cts_ts_encode.restype = i
     lib.cts_rmsnorm.argtypes = [vp, vp, vp, f, vp, ll, ll, i, vp]
     lib.cts_lm_head.argtypes = [vp, vp, vp, vp, ll, ll, ll, i, vp]
     lib.cts_decoder_step_ws_floats.argtypes = [C.POINTER(DecoderStepArgs)]
@@ -286,6 +297,37 @@ class Context:
                                               _p(positions), _p(seq_lens), _p(slot_map), _p(page_table),
                                               page_table.shape[1] if page_table is not None else 0, page_size,
                                               dtype_code(logits.dtype), _stream()))
+
+    def ts_encode(self, x, num_features, patch_size, mode, pos_table, emb_dim, max_seq_len, weights, biases, total_rows, out, row_map=None):
+        """cts_ts_encode: counts + patchify + the whole MLP from one C call.  ``total_rows`` is the host-known sum of the patch
+        counts.  Returns (valid_len, patch_cnt, row_offset) device tensors."""
+        n = x.shape[0]
+        xx = x.reshape(n, -1).contiguous()
+        dev, dt = xx.device, xx.dtype
+        hidden, in0 = weights[0].shape[0], weights[0].shape[1]
+        valid = torch.empty(n, dtype=torch.int32, device=dev)
+        cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        off = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        mx = torch.empty(1, dtype=torch.int32, device=dev)
+        rows = torch.empty(max(total_rows, 1), in0, device=dev, dtype=dt)
+        act = [torch.empty(max(total_rows, 1), hidden, device=dev, dtype=dt) for _ in range(2)]
+        ws = torch.empty(16 * max(total_rows, 1) * hidden, device=dev, dtype=torch.float32)
+        a = TsEncodeArgs()
+        a.x, a.dtype, a.n_series, a.row_len = xx.data_ptr(), dtype_code(dt), n, xx.shape[1]
+        a.num_features, a.patch_size, a.mode = num_features, patch_size, mode
+        a.pos_table = pos_table.data_ptr() if pos_table is not None else None
+        a.emb_dim, a.max_seq_len, a.num_layers, a.hidden, a.in0 = emb_dim, max_seq_len, len(weights), hidden, in0
+        wt = (C.c_void_p * len(weights))(*[w.data_ptr() for w in weights])
+        bt = (C.c_void_p * len(biases))(*[b.data_ptr() for b in biases])
+        a.weights, a.biases = wt, bt
+        a.valid_len, a.patch_cnt, a.row_offset, a.max_valid = valid.data_ptr(), cnt.data_ptr(), off.data_ptr(), mx.data_ptr()
+        a.total_rows = total_rows
+        a.rows_ws, a.splitk_ws, a.splitk_floats = rows.data_ptr(), ws.data_ptr(), ws.numel()
+        a.act_ws[0], a.act_ws[1] = act[0].data_ptr(), act[1].data_ptr()
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+        a.row_map = row_map.data_ptr() if row_map is not None else None
+        self._chk(self.lib.cts_ts_encode(self.h, C.byref(a), _stream()), 3 + 2 * len(weights))
+        return valid, cnt, off
 
     def rmsnorm(self, x, w, eps, out, t=None):
         t = x.shape[0] if t is None else t

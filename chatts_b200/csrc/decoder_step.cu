@@ -97,3 +97,52 @@ extern "C" int cts_decoder_step(cts_ctx* ctx, const cts_decoder_step_args* a, vo
 #undef STEP
   return CTS_OK;
 }
+
+// cts_ts_encode: A3..A7 of the TS encoder from one C call (chatts_vllm.py:93-193 + the row scatter of :569-573): patch counts ->
+// patchify -> num_layers x [tcgen05 GEMM (+ split-K tail) with bias / exact-erf GELU], the last layer scattering its rows
+// through row_map into the embedding sequence.  `total_rows` (= sum of patch counts) is a HOST number: the caller sizes the
+// merged sequence with it anyway (it comes from its own mask arithmetic or from a copy of cts_ts_patch_count's output).
+// Same launches as chatts_b200/ts_encoder.py:TimeSeriesEmbedding.encode.
+extern "C" int cts_ts_encode(cts_ctx* ctx, const cts_ts_encode_args* a, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, a != nullptr && a->weights && a->biases, "null args / weight tables");
+  CTS_CHECK_ARG(ctx, a->num_layers >= 1 && a->hidden > 0 && a->in0 > 0 && a->n_series >= 0 && a->total_rows >= 0, "shape");
+  CTS_CHECK_ARG(ctx, a->valid_len && a->patch_cnt && a->row_offset && a->max_valid, "null metadata buffers");
+  int rc;
+#define STEP(call) do { rc = (call); if (rc != CTS_OK) return rc; } while (0)
+  STEP(cts_ts_patch_count(ctx, a->x, a->dtype, a->n_series, a->row_len, a->num_features, a->patch_size, a->valid_len, a->patch_cnt,
+                          a->row_offset, a->max_valid, stream));
+  if (a->total_rows == 0 || a->n_series == 0) return CTS_OK;
+  CTS_CHECK_ARG(ctx, a->rows_ws && a->act_ws[0] && a->act_ws[1] && a->out, "null workspace / out");
+  const int max_patches = (a->row_len / a->num_features + a->patch_size - 1) / a->patch_size;
+  STEP(cts_ts_patchify(ctx, a->x, a->dtype, a->n_series, a->row_len, a->num_features, a->patch_size, a->mode, a->pos_table, a->emb_dim,
+                       a->max_seq_len, a->valid_len, a->row_offset, a->max_valid, max_patches, a->rows_ws, a->in0, stream));
+  const void* hcur = a->rows_ws;
+  long long k = a->in0;
+  for (int li = 0; li < a->num_layers; ++li) {
+    const bool last = li == a->num_layers - 1;
+    void* dst = last ? a->out : a->act_ws[li & 1];
+    const long long dst_ld = last ? a->out_ld : a->hidden;
+    const int* rmap = last ? a->row_map : nullptr;
+    const int act = last ? CTS_EPI_NONE : CTS_EPI_GELU;
+    const int split = cts_gemm_suggest_split(ctx, a->hidden, k, a->total_rows, 0);
+    cts_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.w = a->weights[li]; g.x = hcur;
+    g.n = a->hidden; g.k = k; g.t = a->total_rows;
+    g.w_ld = k; g.x_ld = k; g.dtype = a->dtype;
+    if (split > 1) {
+      CTS_CHECK_ARG(ctx, a->splitk_ws && a->splitk_floats >= (long long)split * a->total_rows * a->hidden, "split-K workspace too small");
+      g.out = a->splitk_ws; g.out_ld = a->hidden; g.epilogue = CTS_EPI_PARTIAL_F32; g.split_k = split;
+      STEP(cts_gemm(ctx, &g, stream));
+      STEP(cts_reduce_bias_act(ctx, a->splitk_ws, split, a->total_rows, a->hidden, a->biases[li], act, dst, dst_ld, rmap, a->dtype, stream));
+    } else {
+      g.bias = a->biases[li]; g.out = dst; g.out_ld = dst_ld; g.row_map = rmap; g.epilogue = act; g.split_k = 1;
+      STEP(cts_gemm(ctx, &g, stream));
+    }
+    hcur = dst;
+    k = a->hidden;
+  }
+#undef STEP
+  return CTS_OK;
+}

@@ -274,6 +274,24 @@ int cts_rmsnorm(cts_ctx* ctx, const void* x, const void* w, float eps, void* out
 int cts_lm_head(cts_ctx* ctx, const void* hidden, const void* w, void* logits, long long t, long long h, long long vocab, int dtype,
                 void* stream);
 
+/* A3..A7 of the TS encoder from one C call (SURVEY.md 8(b) `cts_ts_encode`): cts_ts_patch_count -> cts_ts_patchify ->
+ * num_layers x cts_gemm (+ cts_reduce_bias_act when the library splits K), bias + exact-erf GELU between layers, the last layer
+ * scattering row i to out[row_map[i]] (chatts_vllm.py:93-193, :569-573).  total_rows = sum of the patch counts, known to the
+ * HOST (it sizes the merged sequence); act_ws: two [total_rows, hidden] ping-pong buffers; rows_ws [total_rows, in0];
+ * splitk_ws: fp32, >= 16 * total_rows * hidden floats covers every split the library may choose. */
+typedef struct {
+  const void* x; int dtype, n_series, row_len, num_features, patch_size, mode;
+  const void* pos_table; int emb_dim, max_seq_len;
+  int num_layers, hidden, in0;
+  const void* const* weights;        /* HOST array [num_layers] of device pointers: W_0 [hidden, in0], W_i [hidden, hidden] */
+  const void* const* biases;         /* HOST array [num_layers] of device pointers: [hidden] */
+  int* valid_len; int* patch_cnt; int* row_offset; int* max_valid;      /* device outputs of the count stage (n_series [+1]) */
+  long long total_rows;
+  void* rows_ws; void* act_ws[2]; float* splitk_ws; long long splitk_floats;
+  void* out; long long out_ld; const int* row_map;                     /* row_map NULL: rows land at out[0..total_rows) */
+} cts_ts_encode_args;
+int cts_ts_encode(cts_ctx* ctx, const cts_ts_encode_args* args, void* stream);
+
 typedef struct {
   const void* wqkv;   /* [(nh+2nkv)*d, hidden]                                       */
   const void* bqkv;   /* [(nh+2nkv)*d] or NULL (Qwen3)                               */

@@ -308,3 +308,18 @@ class TorchDouble:
         self.gemm(xn, lm_head, logits, t=T)
         if sample:
             self.greedy_advance(logits, T, out_tokens, step_ptr, cur_ids, positions, seq_lens, slot_map, page_table, page_size)
+    def ts_encode(self, x, nf, p, mode, pos_table, emb, maxseq, weights, biases, total_rows, out, row_map=None):
+        """Same call sequence as cts_ts_encode."""
+        n = x.shape[0]; xx = x.reshape(n, -1).contiguous()
+        valid, cnt, off, mx = self.ts_patch_count(xx, nf, p)
+        if total_rows == 0: return valid, cnt, off
+        in0 = weights[0].shape[1]; H = weights[0].shape[0]
+        rows = torch.zeros(total_rows, in0, dtype=xx.dtype)
+        self.ts_patchify(xx, nf, p, mode, pos_table, emb, maxseq, valid, off, mx, (xx.shape[1] // nf + p - 1) // p, rows)
+        h = rows
+        for li, (w, b) in enumerate(zip(weights, biases)):
+            last = li == len(weights) - 1
+            dst = out if last else torch.empty(total_rows, H, dtype=xx.dtype)
+            self.gemm(h, w, dst, bias=b, row_map=row_map if last else None, epilogue=0 if last else 1)
+            h = dst
+        return valid, cnt, off

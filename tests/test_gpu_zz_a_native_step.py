@@ -49,3 +49,37 @@ def test_rmsnorm_and_lm_head_aliases():
     c.gemm(x, wl, lb)
     torch.cuda.synchronize()
     assert torch.equal(a, b) and torch.equal(la, lb)
+
+
+@pytest.mark.parametrize("n_series,lens", [(3, [256, 100, 37]), (16, [256] * 16)])
+def test_ts_encode_executor_matches_python_orchestration(n_series, lens):
+    """cts_ts_encode (counts + patchify + MLP from one C call) == TimeSeriesEmbedding.encode (the same launches from Python)."""
+    from chatts_b200 import ChatTSConfig
+    from chatts_b200.processor import sp_encoding
+    from chatts_b200.ts_encoder import TimeSeriesEmbedding
+    from chatts_b200.weights import synthetic_state_dict
+    c = ctx()
+    cfg = ChatTSConfig.tiny()
+    sd = synthetic_state_dict(cfg, seed=4, device="cpu", dtype=DT, std=0.05)
+    ts_w = {k: v for k, v in sd.items() if k.startswith("ts_encoder.")}
+    enc = TimeSeriesEmbedding(cfg.ts, ts_w, dtype=DT)
+    series = [sp_encoding(np.sin(np.arange(L) / 7.0) * (i + 1))[0] for i, L in enumerate(lens)]
+    Lmax = max(e.shape[0] for e in series)
+    x = np.zeros((n_series, Lmax, 1))
+    for i, e in enumerate(series):
+        x[i, : e.shape[0]] = e
+    xt = torch.from_numpy(x).to(torch.float32)
+    feats, cnt = enc.encode(xt)
+    total = int(cnt.sum())
+    out = torch.full((total, enc.hidden_size), float("nan"), device="cuda", dtype=DT)
+    valid, pc, off = c.ts_encode(xt.cuda().to(DT), enc.num_features, enc.patch_size, enc.mode, enc.pos_table, enc.embedding_dim,
+                                 enc.max_sequence_length, enc.w, enc.b, total, out)
+    torch.cuda.synchronize()
+    assert pc.cpu().tolist() == cnt.tolist() and torch.equal(out, feats)
+    # scattered variant: rows land at row_map positions of a bigger buffer
+    perm = torch.randperm(total + 5, generator=torch.Generator().manual_seed(1))[:total].to(torch.int32)
+    big = torch.zeros(total + 5, enc.hidden_size, device="cuda", dtype=DT)
+    c.ts_encode(xt.cuda().to(DT), enc.num_features, enc.patch_size, enc.mode, enc.pos_table, enc.embedding_dim, enc.max_sequence_length,
+                enc.w, enc.b, total, big, row_map=perm.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(big[perm.long().cuda()], feats)

@@ -38,6 +38,11 @@ def _init(self, config, state_dict, device="cpu", **kw):
     kw["use_cuda_graph"] = False          # no CUDA streams / graphs on the CPU
     _orig_init(self, config, state_dict, device="cpu", **kw)
 mm.ChatTSForCausalLM.__init__ = _init
+import chatts_b200.ts_encoder as te
+_orig_te = te.TimeSeriesEmbedding.__init__
+def _te_init(self, config, weights, device="cpu", **kw):
+    _orig_te(self, config, weights, device="cpu", **kw)
+te.TimeSeriesEmbedding.__init__ = _te_init
 extra = sys.argv[1:]
 if "-k" not in extra:          # the ChatTS-8B-shaped case generates its weights on the device: GPU only
     extra += ["-k", "not (directional and True)"]
