@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _cabi, layout
+from .trace import span
 from ._cabi import EPI_NONE, EPI_PARTIAL_F32, EPI_RESIDUAL, EPI_SWIGLU_IL
 from .config import ChatTSConfig
 from .ts_encoder import TimeSeriesEmbedding
@@ -568,7 +569,8 @@ class ChatTSForCausalLM:
         greedy = not (do_sample and temperature is not None and temperature > 0)
         page_tables, held = self._alloc_pages(lay.lens, max_new_tokens)
         try:
-            logits = self._prefill(lay, counts, timeseries, page_tables)
+            with span("cts.prefill"):
+                logits = self._prefill(lay, counts, timeseries, page_tables)
             st = self._decode_state(B, max_new_tokens)
             lens32 = torch.from_numpy(lay.lens.astype(np.int32))
             st.page_table.copy_(torch.from_numpy(page_tables), non_blocking=True)
@@ -613,11 +615,12 @@ class ChatTSForCausalLM:
                     emitted = produced
                     if produced >= max_new_tokens or done.all():
                         break
-                if greedy:
-                    self._decode_step(st, sample=True)
-                else:
-                    self._decode_step(st, sample=False)
-                    sample(st.full_logits, produced)
+                with span("cts.decode_step"):
+                    if greedy:
+                        self._decode_step(st, sample=True)
+                    else:
+                        self._decode_step(st, sample=False)
+                        sample(st.full_logits, produced)
                 produced += 1
             if streamer is not None:
                 streamer.end()

@@ -36,6 +36,7 @@ import numpy as np
 import torch
 
 from . import _cabi, layout
+from .trace import span
 from ._cabi import EPI_NONE, EPI_RESIDUAL, PACK_DESC_LONGS
 
 TARGETS = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
@@ -463,12 +464,15 @@ class LoraTrainer:
         self.loss_out.zero_()
         if total > 0:
             for b in batches:
-                self.forward_backward(b["input_ids"], b.get("attention_mask"), b.get("timeseries"), b["labels"], denominator=total,
-                                      accumulate_loss=True)
+                with span("cts.train.forward_backward"):
+                    self.forward_backward(b["input_ids"], b.get("attention_mask"), b.get("timeseries"), b["labels"], denominator=total,
+                                          accumulate_loss=True)
         if world > 1:
-            dist.all_reduce(self.g, group=self.group)                    # ONE bucket: the whole gradient arena
-            dist.all_reduce(self.loss_out, group=self.group)
-        self.optimizer_step()
+            with span("cts.train.allreduce"):
+                dist.all_reduce(self.g, group=self.group)                # ONE bucket: the whole gradient arena
+                dist.all_reduce(self.loss_out, group=self.group)
+        with span("cts.train.optimizer"):
+            self.optimizer_step()
         return self.loss_out.clone()
 
     # ------------------------------------------------------------------------------------------ schedule, resume, epochs
