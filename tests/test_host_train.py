@@ -253,3 +253,32 @@ def test_gradient_is_the_directional_derivative(cabi_double):
         vals.append(float(tr.eval_loss(batch)[0]))
     fd = (vals[0] - vals[1]) / (2 * eps)
     assert abs(fd - slope) < 0.05 * slope, (fd, slope)
+
+
+def test_label_rows_against_brute_force_on_random_batches(cabi_double):
+    """_prepare (vectorised index arithmetic) vs a position-by-position statement of ForCausalLMLoss's shift on the merged
+    sequence, over random batches: random texts with 0..3 series of ragged lengths, random output lengths, left padding."""
+    from chatts_b200.train import LoraTrainer, encode_records
+
+    cfg, sd, model, proc = _build(cabi_double, False)
+    tr = LoraTrainer(model, r=8, seed=0)
+    rng = np.random.default_rng(7)
+    for trial in range(12):
+        recs = []
+        for _ in range(int(rng.integers(1, 5))):
+            n_ts = int(rng.integers(0, 4))
+            text = "".join(f"w{int(rng.integers(0, 99))} <ts><ts/> " for _ in range(n_ts)) + "q" * int(rng.integers(1, 30))
+            series = [np.sin(np.arange(int(rng.integers(5, 200))) / 3.0) * float(rng.uniform(0.5, 9)) for _ in range(n_ts)]
+            recs.append({"input": text, "output": "a" * int(rng.integers(1, 20)), "timeseries": series})
+        batch = encode_records(proc, recs, eos_token_id=cfg.eos_token_id)
+        bt = tr._prepare(batch["input_ids"], batch["attention_mask"], batch["timeseries"], batch["labels"])
+        _, labels = _oracle_inputs(cfg, sd, batch)
+        sel, tgt, base = [], [], 0
+        for y in labels:                                   # position i of a sample predicts label i + 1 of the same sample
+            for i in range(len(y) - 1):
+                if int(y[i + 1]) != -100:
+                    sel.append(base + i)
+                    tgt.append(int(y[i + 1]))
+            base += len(y)
+        assert bt.sel.tolist() == sel and bt.targets.tolist() == tgt, trial
+        assert bt.T == base and bt.n_counted == LoraTrainer.count_labels(batch) == len(sel)
