@@ -1,0 +1,265 @@
+"""OpenAI-style HTTP front end for the B200 engine: what ``scripts/start_vllm_server.sh`` +
+``demo/vllm_api.py`` give a ChatTS user -- ``POST /v1/chat/completions`` whose user message carries text parts and
+``{"timeseries": [...]}`` parts, consumed in ``<ts><ts/>`` order (demo/vllm_api.py:45-55) -- plus ``/v1/completions`` with the
+vLLM request shape (``prompt`` + ``multi_modal_data.timeseries``, demo/demo_vllm.py:47-52), ``/v1/models`` and ``/health``.
+
+    python -m chatts_b200.server --model /path/to/ChatTS-14B --port 12345
+    client = openai.OpenAI(base_url="http://127.0.0.1:12345/v1", api_key="test")        # demo/vllm_api.py works unchanged
+
+Scheduling: ONE worker thread owns the model (one host thread per C-ABI context).  Requests that arrive within
+``batch_window_ms`` of each other and share their sampling parameters are decoded as one batch (up to ``max_num_seqs``) --
+static micro-batching; a batch runs to completion before the next one starts (iteration-level / continuous batching is
+not built).  ``stream=true`` sends one SSE chunk per generated token through the engine's streamer hook.
+Host-side plumbing only: every number comes from ``vllm_compat.LLM`` -> ``ChatTSForCausalLM`` -> libchatts_b200.so.
+"""
+import argparse
+import json
+import queue
+import threading
+import time
+import uuid
+from concurrent.futures import Future
+from dataclasses import dataclass, field
+
+MAX_TS_DEFAULT = 15          # scripts/start_vllm_server.sh:9  (--limit-mm-per-prompt timeseries=15)
+
+
+@dataclass
+class _Job:
+    prompt: str
+    series: list
+    params: dict
+    future: Future = field(default_factory=Future)
+    stream_q: "queue.Queue | None" = None
+
+
+def messages_to_prompt(messages, tokenizer=None, chat_template=True):
+    """OpenAI chat messages -> (prompt text, series list).  Text parts are concatenated in order, ``{"timeseries": [...]}``
+    parts are collected in order (they pair with the ``<ts><ts/>`` placeholders of the text, demo/vllm_api.py:36,52).  With a
+    tokenizer that has a chat template and ``chat_template=True`` the roles are rendered by it; otherwise the ChatML layout
+    the reference's demos write by hand (demo/vllm_api.py:37) is used unless the text already contains ``<|im_start|>``."""
+    series, turns = [], []
+    for m in messages:
+        content = m.get("content", "")
+        if isinstance(content, str):
+            text = content
+        else:
+            text = ""
+            for part in content:
+                if "timeseries" in part:
+                    series.append(part["timeseries"])
+                elif part.get("type") == "text" or "text" in part:
+                    text += part.get("text", "")
+                else:
+                    raise ValueError(f"unsupported content part: {sorted(part)}")
+        turns.append({"role": m.get("role", "user"), "content": text})
+    if len(turns) == 1 and "<|im_start|>" in turns[0]["content"]:
+        return turns[0]["content"], series                      # the caller templated the prompt itself (demo/vllm_api.py:37)
+    if chat_template and tokenizer is not None and getattr(tokenizer, "chat_template", None):
+        return tokenizer.apply_chat_template(turns, add_generation_prompt=True, tokenize=False), series
+    out = "".join(f"<|im_start|>{t['role']}\n{t['content']}<|im_end|>" for t in turns) + "<|im_start|>assistant\n"
+    return out, series
+
+
+class Engine:
+    """Worker thread + request queue around a ``vllm_compat.LLM``."""
+
+    def __init__(self, llm, batch_window_ms=5.0, max_ts_per_prompt=MAX_TS_DEFAULT):
+        self.llm, self.window, self.max_ts = llm, batch_window_ms / 1e3, max_ts_per_prompt
+        self.q = queue.Queue()
+        self.stop = False
+        self.batches = []                                 # sizes of the batches run so far (observability / tests)
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+
+    def submit(self, prompt, series, params, stream=False):
+        if len(series) > self.max_ts:
+            raise ValueError(f"at most {self.max_ts} time series per prompt")
+        job = _Job(prompt, list(series), dict(params), stream_q=queue.Queue() if stream else None)
+        self.q.put(job)
+        return job
+
+    def close(self):
+        self.stop = True
+        self.q.put(None)
+        self.thread.join(timeout=10)
+
+    # -------------------------------------------------------------------------------------------- worker
+    def _loop(self):
+        from .vllm_compat import SamplingParams
+        while not self.stop:
+            job = self.q.get()
+            if job is None:
+                break
+            batch = [job]
+            deadline = time.monotonic() + self.window
+            cap = self.llm.model.max_batch
+            while len(batch) < cap and job.stream_q is None:
+                try:
+                    nxt = self.q.get(timeout=max(0.0, deadline - time.monotonic()))
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    self.stop = True
+                    break
+                if nxt.params == job.params and nxt.stream_q is None:
+                    batch.append(nxt)
+                else:
+                    self.q.put(nxt)                       # different sampling parameters / streaming: its own batch, next round
+                    break
+            self.batches.append(len(batch))
+            try:
+                sp = SamplingParams(**job.params)
+                reqs = [{"prompt": j.prompt, "multi_modal_data": {"timeseries": j.series}} if j.series else {"prompt": j.prompt} for j in batch]
+                if job.stream_q is not None:
+                    outs = self.llm.generate(reqs, sp, streamer=_QueueStreamer(job.stream_q, self.llm.tokenizer))
+                else:
+                    outs = self.llm.generate(reqs, sp)
+                for j, o in zip(batch, outs):
+                    j.future.set_result(o)
+            except Exception as e:      # surfaced to every caller of the batch; the worker keeps serving
+                for j in batch:
+                    if not j.future.done():
+                        j.future.set_exception(e)
+            finally:
+                if job.stream_q is not None:
+                    job.stream_q.put(None)
+
+
+class _QueueStreamer:
+    """HF-streamer protocol (put / end) -> per-token text pieces on a queue (single-request batches)."""
+
+    def __init__(self, q, tokenizer):
+        self.q, self.tok = q, tokenizer
+
+    def put(self, ids):
+        t = int(ids.reshape(-1)[0])
+        self.q.put(self.tok.decode([t]))
+
+    def end(self):
+        pass
+
+
+def _sampling_from_body(body):
+    p = {"max_tokens": int(body.get("max_tokens") or body.get("max_completion_tokens") or 256),
+         "temperature": float(body.get("temperature", 0.0) or 0.0), "top_p": float(body.get("top_p", 1.0) or 1.0),
+         "top_k": int(body.get("top_k", 0) or 0), "n": int(body.get("n", 1) or 1)}
+    stop = body.get("stop")
+    if stop:
+        p["stop"] = [stop] if isinstance(stop, str) else list(stop)
+    if body.get("stop_token_ids"):
+        p["stop_token_ids"] = list(body["stop_token_ids"])
+    if body.get("seed") is not None:
+        p["seed"] = int(body["seed"])
+    if body.get("ignore_eos"):
+        p["ignore_eos"] = True
+    return p
+
+
+def create_app(llm, served_model_name="chatts", batch_window_ms=5.0, max_ts_per_prompt=MAX_TS_DEFAULT):
+    from fastapi import FastAPI, HTTPException, Request
+    from fastapi.responses import JSONResponse, StreamingResponse
+
+    app = FastAPI(title="chatts_b200")
+    engine = Engine(llm, batch_window_ms, max_ts_per_prompt)
+    app.state.engine = engine
+
+    @app.get("/health")
+    def health():
+        return {"status": "ok"}
+
+    @app.get("/v1/models")
+    def models():
+        return {"object": "list", "data": [{"id": served_model_name, "object": "model", "owned_by": "chatts_b200"}]}
+
+    def usage(prompt, outs):
+        n_out = sum(len(c.token_ids) for c in outs)
+        n_in = len(llm.tokenizer.encode(prompt)) if hasattr(llm.tokenizer, "encode") else 0
+        return {"prompt_tokens": n_in, "completion_tokens": n_out, "total_tokens": n_in + n_out}
+
+    async def run(prompt, series, body, chat):
+        import asyncio
+        params = _sampling_from_body(body)
+        rid = ("chatcmpl-" if chat else "cmpl-") + uuid.uuid4().hex[:24]
+        created = int(time.time())
+        n_ph = prompt.count("<ts><ts/>")
+        if n_ph != len(series):                                      # the reference asserts the same (encoding_utils.py:58,68)
+            raise HTTPException(400, f"{n_ph} <ts><ts/> placeholders but {len(series)} time series")
+        try:
+            job = engine.submit(prompt, series, params, stream=bool(body.get("stream")))
+        except ValueError as e:
+            raise HTTPException(400, str(e))
+        if body.get("stream"):
+            def gen():
+                first = True
+                while True:
+                    piece = job.stream_q.get()
+                    if piece is None:
+                        break
+                    delta = {"role": "assistant", "content": piece} if (chat and first) else ({"content": piece} if chat else None)
+                    first = False
+                    ch = {"index": 0, "delta": delta, "finish_reason": None} if chat else {"index": 0, "text": piece, "finish_reason": None}
+                    yield "data: " + json.dumps({"id": rid, "object": "chat.completion.chunk" if chat else "text_completion", "created": created,
+                                                 "model": served_model_name, "choices": [ch]}) + "\n\n"
+                ch = {"index": 0, "delta": {}, "finish_reason": "stop"} if chat else {"index": 0, "text": "", "finish_reason": "stop"}
+                yield "data: " + json.dumps({"id": rid, "object": "chat.completion.chunk" if chat else "text_completion", "created": created,
+                                             "model": served_model_name, "choices": [ch]}) + "\n\n"
+                yield "data: [DONE]\n\n"
+            return StreamingResponse(gen(), media_type="text/event-stream")
+        try:
+            out = await asyncio.wrap_future(job.future)
+        except (AssertionError, TypeError, ValueError) as e:         # the reference's own input errors (encoding_utils.py:58,68; chatts_vllm.py:277)
+            raise HTTPException(400, str(e))
+        choices = []
+        for i, c in enumerate(out.outputs):
+            fin = "length" if len(c.token_ids) >= params["max_tokens"] else "stop"
+            choices.append({"index": i, "message": {"role": "assistant", "content": c.text}, "finish_reason": fin} if chat else
+                           {"index": i, "text": c.text, "finish_reason": fin})
+        return JSONResponse({"id": rid, "object": "chat.completion" if chat else "text_completion", "created": created,
+                             "model": served_model_name, "choices": choices, "usage": usage(prompt, out.outputs)})
+
+    @app.post("/v1/chat/completions")
+    async def chat_completions(request: Request):
+        body = await request.json()
+        try:
+            prompt, series = messages_to_prompt(body.get("messages", []), llm.tokenizer)
+        except ValueError as e:
+            raise HTTPException(400, str(e))
+        return await run(prompt, series, body, chat=True)
+
+    @app.post("/v1/completions")
+    async def completions(request: Request):
+        body = await request.json()
+        prompt = body.get("prompt", "")
+        series = (body.get("multi_modal_data") or {}).get("timeseries", [])
+        return await run(prompt, series, body, chat=False)
+
+    return app
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default=None, help="checkpoint directory; default: synthetic ChatTS-14B weights + byte tokenizer")
+    ap.add_argument("--served-model-name", default="chatts")
+    ap.add_argument("--host", default="0.0.0.0")
+    ap.add_argument("--port", type=int, default=12345)
+    ap.add_argument("--max-model-len", type=int, default=6000)
+    ap.add_argument("--max-num-seqs", type=int, default=32)
+    ap.add_argument("--limit-mm-per-prompt", default="timeseries=15")
+    ap.add_argument("--dtype", default="bfloat16")
+    ap.add_argument("--batch-window-ms", type=float, default=5.0)
+    args = ap.parse_args()
+    import uvicorn
+    from .vllm_compat import LLM
+    limit = int(dict(kv.split("=") for kv in args.limit_mm_per_prompt.split(",")).get("timeseries", MAX_TS_DEFAULT))
+    tok = None
+    if args.model:
+        from transformers import AutoTokenizer
+        tok = AutoTokenizer.from_pretrained(args.model, trust_remote_code=True)
+    llm = LLM(model=args.model, tokenizer=tok, dtype=args.dtype, max_model_len=args.max_model_len, max_num_seqs=args.max_num_seqs,
+              limit_mm_per_prompt={"timeseries": limit})
+    uvicorn.run(create_app(llm, args.served_model_name, args.batch_window_ms, limit), host=args.host, port=args.port)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,7 +63,7 @@ class LLM:
         self.processor = ChatTSProcessor(self.tokenizer, cfg, dtype=torch.float32)
         self.limit = (limit_mm_per_prompt or {}).get("timeseries", MAX_TS_PER_PROMPT)
 
-    def generate(self, inputs, sampling_params=None, use_tqdm=False):
+    def generate(self, inputs, sampling_params=None, use_tqdm=False, streamer=None):
         sp = sampling_params or SamplingParams()
         if isinstance(inputs, dict):
             inputs = [inputs]
@@ -73,9 +73,9 @@ class LLM:
             # (llm_utils.py:127-130 reads outputs[i].outputs[j].text for j < n)
             flat = self._generate([r for r in inputs for _ in range(n)], sp)
             return [RequestOutput(inputs[i]["prompt"], [flat[i * n + j].outputs[0] for j in range(n)]) for i in range(len(inputs))]
-        return self._generate(inputs, sp)
+        return self._generate(inputs, sp, streamer)
 
-    def _generate(self, inputs, sp):
+    def _generate(self, inputs, sp, streamer=None):
         outs = []
         bs = self.model.max_batch
         stops = [sp.stop] if isinstance(sp.stop, str) else list(sp.stop or [])
@@ -96,7 +96,7 @@ class LLM:
             ids = self.model.generate(**enc, max_new_tokens=sp.max_tokens, do_sample=sp.temperature > 0,
                                       temperature=sp.temperature, top_p=sp.top_p, top_k=(sp.top_k if sp.top_k and sp.top_k > 0 else None),
                                       ignore_eos=sp.ignore_eos, seed=(None if sp.seed is None else sp.seed + i0),
-                                      eos_token_id=(list(sp.stop_token_ids) or None))
+                                      eos_token_id=(list(sp.stop_token_ids) or None), streamer=streamer)
             for b, req in enumerate(chunk):
                 toks = ids[b, S:].tolist()
                 text = self.tokenizer.decode(toks)
