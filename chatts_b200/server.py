@@ -8,8 +8,9 @@ vLLM request shape (``prompt`` + ``multi_modal_data.timeseries``, demo/demo_vllm
 
 Scheduling: ONE worker thread owns the model (one host thread per C-ABI context).  Requests that arrive within
 ``batch_window_ms`` of each other and share their sampling parameters are decoded as one batch (up to ``max_num_seqs``) --
-static micro-batching; a batch runs to completion before the next one starts (iteration-level / continuous batching is
-not built).  ``stream=true`` sends one SSE chunk per generated token through the engine's streamer hook.
+static micro-batching, a batch runs to completion before the next one starts (``--scheduler batch``, sampling supported); or
+iteration-level batching over the static decode slots (``--scheduler continuous``, engine.ContinuousEngine: requests join and
+leave between graph replays; greedy).  ``stream=true`` sends one SSE chunk per generated token through the engine's streamer hook.
 Host-side plumbing only: every number comes from ``vllm_compat.LLM`` -> ``ChatTSForCausalLM`` -> libchatts_b200.so.
 """
 import argparse
@@ -64,17 +65,21 @@ def messages_to_prompt(messages, tokenizer=None, chat_template=True):
 class Engine:
     """Worker thread + request queue around a ``vllm_compat.LLM``."""
 
-    def __init__(self, llm, batch_window_ms=5.0, max_ts_per_prompt=MAX_TS_DEFAULT):
+    def __init__(self, llm, batch_window_ms=5.0, max_ts_per_prompt=MAX_TS_DEFAULT, scheduler="batch", steps_per_round=4):
         self.llm, self.window, self.max_ts = llm, batch_window_ms / 1e3, max_ts_per_prompt
         self.q = queue.Queue()
         self.stop = False
         self.batches = []                                 # sizes of the batches run so far (observability / tests)
-        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.scheduler, self.steps_per_round = scheduler, steps_per_round
+        self.occupancy = []                               # continuous scheduler: active slots per round
+        self.thread = threading.Thread(target=self._loop_continuous if scheduler == "continuous" else self._loop, daemon=True)
         self.thread.start()
 
     def submit(self, prompt, series, params, stream=False):
         if len(series) > self.max_ts:
             raise ValueError(f"at most {self.max_ts} time series per prompt")
+        if self.scheduler == "continuous" and params.get("temperature", 0.0) > 0:
+            raise ValueError("the continuous scheduler decodes greedily; start the server with --scheduler batch for sampling")
         job = _Job(prompt, list(series), dict(params), stream_q=queue.Queue() if stream else None)
         self.q.put(job)
         return job
@@ -126,6 +131,81 @@ class Engine:
                     job.stream_q.put(None)
 
 
+    # -------------------------------------------------------------------------------------------- continuous scheduler
+    def _loop_continuous(self):
+        """Iteration-level batching (engine.ContinuousEngine): requests join the static decode slots between graph replays and
+        leave them at EOS / max_tokens; streaming requests get their new tokens after every round."""
+        from .engine import ContinuousEngine
+        from .vllm_compat import CompletionOutput, RequestOutput
+        llm = self.llm
+        eng = ContinuousEngine(llm.model, steps_per_round=self.steps_per_round)
+        jobs, sent = {}, {}
+
+        def admit(job):
+            try:
+                enc = llm.processor(text=[job.prompt], timeseries=job.series, padding=True, return_tensors="pt")
+                p = job.params
+                rid = eng.add_request(enc["input_ids"][0], enc["timeseries"], max_new_tokens=p.get("max_tokens", 16),
+                                      eos_token_id=(list(p["stop_token_ids"]) if p.get("stop_token_ids") else None),
+                                      ignore_eos=p.get("ignore_eos", False))
+                jobs[rid], sent[rid] = job, 0
+            except Exception as e:
+                job.future.set_exception(e)
+                if job.stream_q is not None:
+                    job.stream_q.put(None)
+
+        def text_of(job, toks):
+            text = llm.tokenizer.decode(toks)
+            stops = job.params.get("stop") or []
+            cut = min([text.find(st) for st in stops if st and st in text], default=-1)
+            return text[:cut] if cut >= 0 else text
+
+        while not self.stop:
+            if not eng.has_work():
+                job = self.q.get()
+                if job is None:
+                    break
+                admit(job)
+            while True:
+                try:
+                    job = self.q.get_nowait()
+                except queue.Empty:
+                    break
+                if job is None:
+                    self.stop = True
+                    break
+                admit(job)
+            try:
+                finished = eng.step()
+            except Exception as e:      # an engine failure ends every request in flight; the loop keeps serving new ones
+                for rid, job in list(jobs.items()):
+                    if not job.future.done():
+                        job.future.set_exception(e)
+                    if job.stream_q is not None:
+                        job.stream_q.put(None)
+                jobs.clear(); sent.clear()
+                continue
+            if eng.occupancy:
+                self.occupancy.append(eng.occupancy[-1])
+            for r in list(eng.active.values()) + list(finished):       # streaming: hand over what the round produced
+                job = jobs.get(r.rid)
+                if job is not None and job.stream_q is not None:
+                    for t in r.tokens[sent[r.rid]:]:
+                        job.stream_q.put(llm.tokenizer.decode([t]))
+                    sent[r.rid] = len(r.tokens)
+            for r in finished:
+                job = jobs.pop(r.rid, None)
+                sent.pop(r.rid, None)
+                if job is None:
+                    continue
+                n = max(1, int(job.params.get("n", 1)))
+                out = CompletionOutput(text_of(job, r.tokens), list(r.tokens))
+                job.future.set_result(RequestOutput(job.prompt, [out] * n))
+                if job.stream_q is not None:
+                    job.stream_q.put(None)
+        eng.close()
+
+
 class _QueueStreamer:
     """HF-streamer protocol (put / end) -> per-token text pieces on a queue (single-request batches)."""
 
@@ -156,12 +236,13 @@ def _sampling_from_body(body):
     return p
 
 
-def create_app(llm, served_model_name="chatts", batch_window_ms=5.0, max_ts_per_prompt=MAX_TS_DEFAULT):
+def create_app(llm, served_model_name="chatts", batch_window_ms=5.0, max_ts_per_prompt=MAX_TS_DEFAULT, scheduler="batch",
+               steps_per_round=4):
     from fastapi import FastAPI, HTTPException, Request
     from fastapi.responses import JSONResponse, StreamingResponse
 
     app = FastAPI(title="chatts_b200")
-    engine = Engine(llm, batch_window_ms, max_ts_per_prompt)
+    engine = Engine(llm, batch_window_ms, max_ts_per_prompt, scheduler, steps_per_round)
     app.state.engine = engine
 
     @app.get("/health")
@@ -248,6 +329,9 @@ def main():
     ap.add_argument("--limit-mm-per-prompt", default="timeseries=15")
     ap.add_argument("--dtype", default="bfloat16")
     ap.add_argument("--batch-window-ms", type=float, default=5.0)
+    ap.add_argument("--scheduler", default="batch", choices=["batch", "continuous"],
+                    help="batch: micro-batches run to completion (sampling supported); continuous: iteration-level batching, greedy")
+    ap.add_argument("--steps-per-round", type=int, default=4, help="continuous scheduler: decode steps between two host reads")
     args = ap.parse_args()
     import uvicorn
     from .vllm_compat import LLM
@@ -258,7 +342,8 @@ def main():
         tok = AutoTokenizer.from_pretrained(args.model, trust_remote_code=True)
     llm = LLM(model=args.model, tokenizer=tok, dtype=args.dtype, max_model_len=args.max_model_len, max_num_seqs=args.max_num_seqs,
               limit_mm_per_prompt={"timeseries": limit})
-    uvicorn.run(create_app(llm, args.served_model_name, args.batch_window_ms, limit), host=args.host, port=args.port)
+    uvicorn.run(create_app(llm, args.served_model_name, args.batch_window_ms, limit, args.scheduler, args.steps_per_round),
+                host=args.host, port=args.port)
 
 
 if __name__ == "__main__":

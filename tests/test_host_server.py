@@ -87,3 +87,39 @@ def test_messages_to_prompt_chatml_and_parts():
     assert p == "<|im_start|>system\nS<|im_end|><|im_start|>user\na <ts><ts/><|im_end|><|im_start|>assistant\n" and s == [[1, 2, 3]]
     raw = "<|im_start|>user\nhi<|im_end|><|im_start|>assistant\n"
     assert messages_to_prompt([{"role": "user", "content": raw}])[0] == raw
+
+
+def test_continuous_scheduler_serves_concurrent_requests(cabi_double):
+    """--scheduler continuous: more concurrent requests than slots, different lengths; each answer equals the stand-alone
+    greedy generation; a streamed request receives the same text piecewise; sampling is refused with 400."""
+    from starlette.testclient import TestClient
+    from chatts_b200.server import create_app
+    from chatts_b200.vllm_compat import LLM, SamplingParams
+    cfg, sd, model, proc = _build(cabi_double)
+    llm = LLM(model=model)
+    a, _ = _series()
+    bodies = [{"prompt": "x <ts><ts/> y", "multi_modal_data": {"timeseries": [a.tolist()]}, "max_tokens": 6, "ignore_eos": True}] + \
+             [{"prompt": f"plain text number {i}", "max_tokens": 3 + i, "ignore_eos": True} for i in range(9)]
+    want = []
+    for b in bodies:
+        req = {"prompt": b["prompt"], "multi_modal_data": b.get("multi_modal_data", {})}
+        want.append(llm.generate([req], SamplingParams(max_tokens=b["max_tokens"], ignore_eos=True))[0].outputs[0].text)
+    app = create_app(llm, scheduler="continuous", steps_per_round=2)
+    with TestClient(app) as http:
+        res = [None] * len(bodies)
+        def call(i):
+            res[i] = http.post("/v1/completions", json=bodies[i]).json()
+        ths = [threading.Thread(target=call, args=(i,)) for i in range(len(bodies))]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        assert [r["choices"][0]["text"] for r in res] == want
+        assert max(app.state.engine.occupancy) <= model.max_batch and max(app.state.engine.occupancy) >= 2
+        pieces = []
+        with http.stream("POST", "/v1/completions", json={**bodies[3], "stream": True}) as r:
+            for line in r.iter_lines():
+                if line.startswith("data: ") and line != "data: [DONE]":
+                    pieces.append(json.loads(line[6:])["choices"][0]["text"])
+        assert "".join(pieces) == want[3]
+        assert http.post("/v1/completions", json={"prompt": "x", "temperature": 0.7}).status_code == 400
+    app.state.engine.close()
+    assert len(model.pool.free) == model.pool.num_pages
