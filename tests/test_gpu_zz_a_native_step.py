@@ -83,3 +83,39 @@ def test_ts_encode_executor_matches_python_orchestration(n_series, lens):
                 enc.w, enc.b, total, big, row_map=perm.cuda())
     torch.cuda.synchronize()
     assert torch.equal(big[perm.long().cuda()], feats)
+
+
+def test_continuous_engine_on_the_captured_decode_graph():
+    """engine.ContinuousEngine on the GPU: requests join / leave the static slots between CUDA-graph replays; every request
+    reproduces the tokens it gets when it is served alone at the same decode width (same kernels, same split factors, rows
+    independent), and its first token is generate()'s."""
+    from chatts_b200 import ChatTSConfig, ChatTSProcessor, SimpleTokenizer
+    from chatts_b200.engine import ContinuousEngine
+    from chatts_b200.model import ChatTSForCausalLM
+    from chatts_b200.weights import synthetic_state_dict
+    cfg = ChatTSConfig.tiny()
+    sd = synthetic_state_dict(cfg, seed=1234, device="cpu", dtype=DT, std=0.05)
+    model = ChatTSForCausalLM(cfg, sd, dtype=DT, max_batch=4, max_seq_len=256, page_size=16, use_cuda_graph=True)
+    proc = ChatTSProcessor(SimpleTokenizer(cfg.ts_token_start_index, cfg.pad_token_id, cfg.eos_token_id), cfg)
+    x = np.arange(200)
+    specs = [("A <ts><ts/> ?", [np.sin(x / 9) * 4], 9), ("plain text", [], 5), ("B <ts><ts/> and <ts><ts/>", [x * 0.05, np.cos(x / 5)[:77]], 12),
+             ("short", [], 2), ("one more plain prompt", [], 7), ("C <ts><ts/>", [np.sin(x / 3)], 6)]
+    encs = [(proc(text=[t], timeseries=s, return_tensors="pt"), n) for t, s, n in specs]
+    # reference: the same engine serving ONE request at a time (prefill alone, decode width 4 with three dummy slots) -- identical
+    # kernel shapes and split factors, so row independence makes the crowded run reproduce it exactly
+    ref = []
+    for enc, n in encs:
+        solo = ContinuousEngine(model, slots=4, steps_per_round=3, max_prefill_batch=1)
+        solo.add_request(enc["input_ids"][0], enc["timeseries"], max_new_tokens=n, ignore_eos=True)
+        ref.append(solo.run()[0].tokens)
+        solo.close()
+    one = model.generate(**encs[0][0], max_new_tokens=1, ignore_eos=True)[0, -1].item()
+    assert ref[0][0] == one                                                   # same first token as generate() (same prefill shape)
+    pages0 = len(model.pool.free)
+    eng = ContinuousEngine(model, slots=4, steps_per_round=3, max_prefill_batch=1)
+    for enc, n in encs:
+        eng.add_request(enc["input_ids"][0], enc["timeseries"], max_new_tokens=n, ignore_eos=True)
+    done = eng.run()
+    eng.close()
+    assert [r.tokens for r in done] == ref
+    assert len(model.pool.free) == pages0 and max(eng.occupancy) <= 4
