@@ -53,7 +53,6 @@ class ContinuousEngine:
         self.st = model._decode_state(self.B, max(self.k, 1))
         self.scratch = model.pool.alloc(1)[0]              # dummy sequences of the free slots live here
         dev = model.device
-        self._all = torch.arange(self.B, device=dev)
         self.st.page_table.fill_(self.scratch)
         self.st.cur_ids.fill_(int(model.config.pad_token_id) % model.embed.shape[0])
         self._reset_free(list(range(self.B)))
@@ -148,7 +147,6 @@ class ContinuousEngine:
             st = self.st
             st.cur_ids[slots], st.positions[slots], st.seq_lens[slots], st.slot_map[slots] = t_cur, t_pos, t_seq, t_slot
             st.page_table[slots] = t_pt
-            per = pts.shape[1]
             for i, r in enumerate(group):
                 need = (int(lay.lens[i]) + max(q.max_new_tokens for q in group) + self.k + m.page_size - 1) // m.page_size
                 r.pages = [int(x) for x in pts[i, :need]]

@@ -35,7 +35,6 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from . import _cabi, layout
 from .trace import span
 from ._cabi import EPI_NONE, EPI_RESIDUAL, PACK_DESC_LONGS
 
