@@ -66,6 +66,7 @@ class _Group:
     def __init__(self, key, K, N, members):
         self.key, self.K, self.N, self.members = key, K, N, members
         self.R = 0          # padded fused rank (multiple of 8: 16-byte rows for TMA)
+        self.a_off = 0      # arena offset of the members' stacked A matrices
         self.A = self.At = self.B = self.Bt = None      # views into the work arena
 
 
@@ -109,13 +110,6 @@ class LoraTrainer:
             "d": (self.I, self.H, [("down_proj", 0, 0, self.I, self.H)]),
         }
         for l in range(self.L):
-            for p in self.targets:                                   # oracle/lora.py order: layer, then TARGETS order; A then B
-                fin, fout = next((mm[3], mm[4]) for g in spec.values() for mm in g[2] if mm[0] == p)
-                base = f"model.layers.{l}.{_module_of(p)}.{p}"
-                self.index[base + ".lora_A.weight"] = (off, (self.r, fin))
-                off += self.r * fin
-                self.index[base + ".lora_B.weight"] = (off, (fout, self.r))
-                off += fout * self.r
             gl = {}
             for key, (K, N, mem) in spec.items():
                 present = [mm for mm in mem if mm[0] in self.targets]
@@ -124,6 +118,15 @@ class LoraTrainer:
                 members = [_Member(mm[0], j * self.r, mm[1], mm[2], mm[3], mm[4]) for j, mm in enumerate(present)]
                 g = _Group(key, K, N, members)
                 g.R = _ceil8(self.r * len(members))
+                # arena layout of a group: the members' A matrices STACKED ([r x members, in], contiguous -> their weight gradient
+                # is one cts_lora_wgrad launch over the shared input X), then the members' B matrices
+                g.a_off = off
+                for mm in members:
+                    self.index[f"model.layers.{l}.{_module_of(mm.proj)}.{mm.proj}.lora_A.weight"] = (off, (self.r, mm.fin))
+                    off += self.r * mm.fin
+                for mm in members:
+                    self.index[f"model.layers.{l}.{_module_of(mm.proj)}.{mm.proj}.lora_B.weight"] = (off, (mm.fout, self.r))
+                    off += mm.fout * self.r
                 gl[key] = g
             self.groups.append(gl)
         self.n_params = off
@@ -295,10 +298,16 @@ class LoraTrainer:
         du = torch.empty(T, g.R, device=dy.device, dtype=dy.dtype)
         c.gemm(dy, g.Bt, du, epilogue=EPI_NONE, t=T)
         for mm in g.members:
-            base = f"model.layers.{l}.{_module_of(mm.proj)}.{mm.proj}"
-            gA, gB = self.grad(base + ".lora_A.weight"), self.grad(base + ".lora_B.weight")
+            gB = self.grad(f"model.layers.{l}.{_module_of(mm.proj)}.{mm.proj}.lora_B.weight")
             c.lora_wgrad(dy, mm.n0, mm.il, mm.fout, u, mm.j0, self.r, T, self.scaling, gB, self.r, 1)        # dB = s dY^T U
-            c.lora_wgrad(x, 0, 0, mm.fin, du, mm.j0, self.r, T, 1.0, gA, 1, mm.fin)                            # dA = dU^T X
+        # dA of ALL members in one launch: they share X, their A's are stacked in the arena exactly like dU's columns
+        rt, fin = self.r * len(g.members), g.members[0].fin
+        if rt <= 64:
+            c.lora_wgrad(x, 0, 0, fin, du, 0, rt, T, 1.0, self.g[g.a_off: g.a_off + rt * fin], 1, fin)       # dA = dU^T X
+        else:                                                     # cts_lora_wgrad takes at most 64 rank columns per launch
+            for mm in g.members:
+                gA = self.grad(f"model.layers.{l}.{_module_of(mm.proj)}.{mm.proj}.lora_A.weight")
+                c.lora_wgrad(x, 0, 0, mm.fin, du, mm.j0, self.r, T, 1.0, gA, 1, mm.fin)
         if dx is not None:
             c.gemm(du, g.At, dx, residual=dx, epilogue=EPI_RESIDUAL, t=T)
 
