@@ -85,11 +85,11 @@ class ChatTSForCausalLM:
         self.graph_with_tp = graph_with_tp
         import os as _os
         self.use_chain = bool(int(_os.environ.get("CTS_DECODE_CHAIN", "0"))) if use_chain is None else bool(use_chain)
-        # sampled decoding through cts_sample_advance (csrc/sampling.cu) instead of torch ops: off by default until the kernel has
-        # run on a B200 (written after the round-1 GPU budget was spent); CTS_SAMPLE_KERNEL=1 / use_sample_kernel=True turns it on
         # the whole decode step enqueued by one C call (cts_decoder_step) instead of ~440 ctypes calls: identical launches; off by
         # default until compared with the Python orchestration on a B200 (CTS_NATIVE_STEP=1 / use_native_step=True)
         self.use_native_step = bool(int(_os.environ.get("CTS_NATIVE_STEP", "0"))) if use_native_step is None else bool(use_native_step)
+        # sampled decoding through cts_sample_advance (csrc/sampling.cu) instead of torch ops: off by default until the kernel has
+        # run on a B200 (written after the round-1 GPU budget was spent); CTS_SAMPLE_KERNEL=1 / use_sample_kernel=True turns it on
         self.use_sample_kernel = bool(int(_os.environ.get("CTS_SAMPLE_KERNEL", "0"))) if use_sample_kernel is None else bool(use_sample_kernel)
         self._load(state_dict)
         n_pos = min(cfg.max_position_embeddings, max(max_seq_len, 16))
