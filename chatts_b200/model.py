@@ -166,7 +166,16 @@ class ChatTSForCausalLM:
             cj = _os.path.join(path, "config.json") if _os.path.isdir(path) else path
             qc = _json.load(open(cj)).get("quantization_config", {})
             sd = dequantize_gptq(sd, qc, dtype=dt)
-        return cls(cfg, sd, device=dev, dtype=dt, **kw)
+        model = cls(cfg, sd, device=dev, dtype=dt, **kw)
+        # generation_config.json: the defaults HF's generate() applies when the caller passes none (README.md:102 calls
+        # model.generate(**inputs, max_new_tokens=300) with no sampling arguments)
+        import json as _json2
+        import os as _os2
+        gc = _os2.path.join(path, "generation_config.json") if _os2.path.isdir(path) else ""
+        if gc and _os2.path.exists(gc):
+            model.generation_defaults = {k: v for k, v in _json2.load(open(gc)).items()
+                                         if k in ("do_sample", "temperature", "top_p", "top_k", "eos_token_id", "pad_token_id", "max_new_tokens")}
+        return model
 
     # ------------------------------------------------------------------------------------------ LoRA
     def merge_lora(self, adapter, lora_alpha=None, r=None):
@@ -551,11 +560,24 @@ class ChatTSForCausalLM:
     # ------------------------------------------------------------------------------------------ generate
     @torch.no_grad()
     def generate(self, input_ids=None, attention_mask=None, timeseries=None, max_new_tokens=None, max_length=None,
-                 do_sample=False, temperature=None, top_p=None, top_k=None, streamer=None, eos_token_id=None, pad_token_id=None,
+                 do_sample=None, temperature=None, top_p=None, top_k=None, streamer=None, eos_token_id=None, pad_token_id=None,
                  synced_gpus=False, sync_every=16, ignore_eos=False, seed=None, **_):
         """model.generate(**processor_out, max_new_tokens=...) -> LongTensor [B, S + new] whose first S columns are
         the ORIGINAL (un-expanded) input ids (README.md:102-103)."""
         cfg, dev = self.config, self.device
+        gd = getattr(self, "generation_defaults", None)
+        if gd:                                          # checkpoint defaults apply only where the caller said nothing
+            if do_sample is None and gd.get("do_sample"):
+                do_sample = True
+                temperature = gd.get("temperature", 1.0) if temperature is None else temperature
+                top_p = gd.get("top_p") if top_p is None else top_p
+                top_k = gd.get("top_k") if top_k is None else top_k
+            if eos_token_id is None and gd.get("eos_token_id") is not None:
+                eos_token_id = gd["eos_token_id"]
+            if pad_token_id is None and gd.get("pad_token_id") is not None:
+                pad_token_id = gd["pad_token_id"]
+            if max_new_tokens is None and max_length is None and gd.get("max_new_tokens"):
+                max_new_tokens = gd["max_new_tokens"]
         ids_cpu, am_cpu, counts, lay = self._prepare_inputs(input_ids, attention_mask, timeseries)
         B, S = ids_cpu.shape
         if max_new_tokens is None:

@@ -160,3 +160,27 @@ def test_native_step_executor_generates_the_same_tokens(cabi_double, split, qwen
     cfg2, sd2, native, _ = _build(cabi_double, split, qwen3, use_native_step=True)
     out = native.generate(**enc, max_new_tokens=9, ignore_eos=True)
     assert torch.equal(out, ref) and len(native.pool.free) == native.pool.num_pages
+
+
+def test_from_pretrained_reads_generation_config_defaults(cabi_double, tmp_path):
+    """HF's generate() falls back to the checkpoint's generation_config.json when the caller passes no sampling arguments
+    (README.md:102): from_pretrained picks those defaults up; explicit arguments still win."""
+    import json
+    from safetensors.torch import save_file
+    from chatts_b200.model import ChatTSForCausalLM
+
+    cfg, sd, model, proc = _build(cabi_double)
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    json.dump({**cfg.to_dict(), "architectures": ["Qwen2TSForCausalLM"]}, open(d / "config.json", "w"))
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(d / "model.safetensors"))
+    json.dump({"do_sample": True, "temperature": 0.7, "top_p": 0.8, "top_k": 20, "eos_token_id": [998, 997]}, open(d / "generation_config.json", "w"))
+    m = ChatTSForCausalLM.from_pretrained(str(d), device="cpu", torch_dtype=DT, max_batch=4, max_seq_len=256, page_size=16, use_cuda_graph=False)
+    assert m.generation_defaults["temperature"] == 0.7 and m.generation_defaults["top_k"] == 20
+    enc = proc(text=["hello"], timeseries=[], return_tensors="pt")
+    a = m.generate(**enc, max_new_tokens=8, seed=1, ignore_eos=True)
+    b = m.generate(**enc, max_new_tokens=8, seed=2, ignore_eos=True)
+    g1 = m.generate(**enc, max_new_tokens=8, do_sample=False, ignore_eos=True)
+    g2 = model.generate(**enc, max_new_tokens=8, ignore_eos=True)
+    assert not torch.equal(a, b)                       # the checkpoint's sampling defaults are in force
+    assert torch.equal(g1, g2)                         # explicit greedy request == the model without a generation config
