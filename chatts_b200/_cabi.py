@@ -28,8 +28,9 @@ SYMBOLS = [
     "cts_attn_prefill_lse", "cts_attn_bwd", "cts_swiglu", "cts_swiglu_bwd", "cts_rmsnorm_bwd", "cts_qkv_rope_bwd",
     "cts_ce_loss_grad", "cts_gather_rows", "cts_lora_wgrad", "cts_adamw", "cts_grad_norm_ws_floats", "cts_grad_norm_clip",
     "cts_lora_pack",
-    "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step", "cts_ts_encode",
+    "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step", "cts_ts_encode", "cts_gemm_decode_fused",
 ]
+FUSED_RESIDUAL, FUSED_SWIGLU, FUSED_QKV_ROPE = 0, 1, 2
 PACK_DESC_LONGS = 12
 
 
@@ -71,6 +72,14 @@ class DecoderStepArgs(C.Structure):
                                    "page_table", "out_tokens")] + [("out_ld", C.c_int)] +
         [(k, C.c_void_p) for k in ("step_ptr", "h", "xn", "q", "ao", "act", "logits", "ws")] + [("ws_floats", C.c_longlong)] +
         [("attn_ws", C.c_void_p)])
+
+
+class FusedGemmArgs(C.Structure):
+    _fields_ = ([("w", C.c_void_p), ("x", C.c_void_p), ("n", C.c_longlong), ("k", C.c_longlong), ("t", C.c_longlong)] +
+                [(k, C.c_int) for k in ("dtype", "mode", "split_k", "reserved")] +
+                [(k, C.c_void_p) for k in ("bias", "h", "act", "positions", "cos_tab", "sin_tab", "slot_map", "q_out", "k_cache", "v_cache",
+                                           "q_norm", "k_norm")] + [("eps", C.c_float)] +
+                [(k, C.c_int) for k in ("nh", "nkv", "head_dim", "page_size")])
 
 
 class TsEncodeArgs(C.Structure):
@@ -125,6 +134,8 @@ def load_library():
     lib.cts_decode_chain.restype = i
     lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
     lib.cts_peer_greedy_advance.restype = i
+    lib.cts_gemm_decode_fused.argtypes = [vp, C.POINTER(FusedGemmArgs), vp]
+    lib.cts_gemm_decode_fused.restype = i
     lib.cts_ts_encode.argtypes = [vp, C.POINTER(TsEncodeArgs), vp]
     lib.cts_ts_encode.restype = i
     lib.cts_rmsnorm.argtypes = [vp, vp, vp, f, vp, ll, ll, i, vp]
@@ -297,6 +308,20 @@ class Context:
                                               _p(positions), _p(seq_lens), _p(slot_map), _p(page_table),
                                               page_table.shape[1] if page_table is not None else 0, page_size,
                                               dtype_code(logits.dtype), _stream()))
+
+    def gemm_decode_fused(self, x, w, mode, split_k, t, *, bias=None, h=None, act=None, positions=None, cos=None, sin=None, slot_map=None,
+                          q_out=None, k_cache=None, v_cache=None, q_norm=None, k_norm=None, eps=1e-6, nh=0, nkv=0, head_dim=0,
+                          page_size=0):
+        """Cluster-reduced decode GEMM with the projection's tail fused in (cts_gemm_decode_fused); t <= 32, split_k <= 8."""
+        a = FusedGemmArgs()
+        dp = lambda v: None if v is None else v.data_ptr()
+        a.w, a.x, a.n, a.k, a.t = w.data_ptr(), x.data_ptr(), w.shape[0], w.shape[1], t
+        a.dtype, a.mode, a.split_k = dtype_code(x.dtype), int(mode), int(split_k)
+        a.bias, a.h, a.act = dp(bias), dp(h), dp(act)
+        a.positions, a.cos_tab, a.sin_tab, a.slot_map = dp(positions), dp(cos), dp(sin), dp(slot_map)
+        a.q_out, a.k_cache, a.v_cache, a.q_norm, a.k_norm = dp(q_out), dp(k_cache), dp(v_cache), dp(q_norm), dp(k_norm)
+        a.eps, a.nh, a.nkv, a.head_dim, a.page_size = float(eps), nh, nkv, head_dim, page_size
+        self._chk(self.lib.cts_gemm_decode_fused(self.h, C.byref(a), _stream()))
 
     def ts_encode(self, x, num_features, patch_size, mode, pos_table, emb_dim, max_seq_len, weights, biases, total_rows, out, row_map=None):
         """cts_ts_encode: counts + patchify + the whole MLP from one C call.  ``total_rows`` is the host-known sum of the patch

@@ -1,0 +1,307 @@
+// chatts_b200 -- decode GEMM with the split-K reduction AND the projection's tail fused in, through a thread-block cluster.
+//
+// The decode step is nine dependent stages per layer (84 us of weight stream + 19 us of attention +
+// ~35 us of small kernels and ramps).  Four of the nine exist only because the skinny decode GEMMs split K over CTAs and a
+// second kernel has to add the fp32 partials before it can apply bias / RoPE / SwiGLU / the residual.  Here the K splits of
+// one 128-feature tile form ONE CLUSTER (grid.z = split <= 8 = cluster.z): every CTA runs the same TMA -> tcgen05 -> TMEM
+// mainloop as gemm_tn_kernel, parks its fp32 accumulator tile in its own shared memory, and after a cluster barrier the
+// CTAs reduce disjoint TOKENS of the tile over distributed shared memory (split order: the same summation order as the
+// stand-alone reduce kernels, so results are bit-identical to the multi-kernel path) and apply the tail in place:
+//
+//   CTS_FUSED_RESIDUAL  h[t][f] = dtype(h[t][f] + dtype(sum))                                o_proj / down_proj (modeling_qwen2.py:302,308)
+//   CTS_FUSED_SWIGLU    act[t][i] = dtype(silu(dtype(gate_i)) * dtype(up_i))   (interleaved gate/up weight)   (:47)
+//   CTS_FUSED_QKV_ROPE  dtype(sum + bias) -> Qwen3 q/k RMSNorm -> RoPE -> q_out / paged KV write                (:116-146,217-222)
+//
+// A 128-row tile of the QKV weight is exactly one head (head_dim 128; two heads at head_dim 64), and a tile of the
+// interleaved gate_up weight holds 64 (gate, up) pairs, so every tail is tile-local.  Per layer this removes the
+// RoPE/KV-write and the SwiGLU launches, turns the two reduce+residual+RMSNorm launches into plain RMSNorms and removes the
+// fp32 partial round trip through L2 (9 -> 7 stages; folding the RMSNorm weight into the next projection would make it 5).
+//
+// OPT-IN (CTS_DECODE_FUSED=1 / use_fused_decode=True): written after the round-1 GPU budget was spent, never executed.  T <= 32
+// tokens, split <= 8.  Every mbarrier wait is bounded (trap, not hang); the cluster barriers are reached by all threads of all
+// CTAs unconditionally.
+#include <cooperative_groups.h>
+
+#include <type_traits>
+
+#include "common.cuh"
+#include "tensormap.cuh"
+
+namespace {
+
+namespace cg = cooperative_groups;
+
+constexpr int kBM = 128, kBK = 64, kUmmaK = 16, kThreads = 192, kMaxStages = 12;
+
+struct FusedParams {
+  long long n, k, t;
+  int kb_total, split, stages, mode;
+  const void* bias;
+  void* h;                // RESIDUAL: [t, n] residual stream, updated in place
+  void* act;              // SWIGLU: [t, n/2]
+  // QKV_ROPE
+  const int* positions; const void* cos_tab; const void* sin_tab; const int* slot_map;
+  void* q_out; void* k_cache; void* v_cache;
+  const void* q_norm; const void* k_norm; float eps;
+  int nh, nkv, d, page_size;
+};
+
+template <typename T, int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t acc_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float xch[kBM];            // tile-local exchange (SwiGLU up values / RoPE partners)
+  __shared__ float red[4];              // per-warp partial sums of the q/k RMSNorm statistic
+
+  constexpr int kABytes = kBM * kBK * 2;
+  constexpr int kStage = kABytes + BN * kBK * 2;
+  constexpr int kCols = 32;
+  constexpr bool kIsBf16 = std::is_same<T, __nv_bfloat16>::value;
+  static_assert(BN <= 32, "decode-sized token tile");
+
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  float* part_s = reinterpret_cast<float*>(smem);          // [BN][128] fp32, reuses the pipeline ring once the accumulator is complete
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f0 = blockIdx.x * kBM;
+  const int split = blockIdx.z;                            // == rank inside the (1, 1, split) cluster
+  const int S = p.split;
+  const int stages = p.stages;
+  const int kb0 = (int)(((long long)p.kb_total * split) / S);
+  const int kb1 = (int)(((long long)p.kb_total * (split + 1)) / S);
+  const int nkb = kb1 - kb0;
+  const int T_ = (int)p.t;
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_x);
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kCols>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (as gemm_tn_kernel: weights before the dependency wait) ------------------------------
+    if (lane == 0) {
+      const int npre = nkb < stages ? nkb : stages;
+      for (int i = 0; i < npre; ++i) {
+        mbar_expect_tx(&full_bar[i], (uint32_t)kStage);
+        tma_load_2d(smem + (size_t)i * kStage, &tm_w, &full_bar[i], (kb0 + i) * kBK, f0, CTS_L2_EVICT_FIRST);
+      }
+      pdl_wait();
+      for (int i = 0; i < npre; ++i)
+        tma_load_2d(smem + (size_t)i * kStage + kABytes, &tm_x, &full_bar[i], (kb0 + i) * kBK, 0, CTS_L2_EVICT_LAST);
+      for (int i = npre; i < nkb; ++i) {
+        const int s = i % stages;
+        mbar_wait(&empty_bar[s], (((uint32_t)(i / stages)) & 1u) ^ 1u);
+        mbar_expect_tx(&full_bar[s], (uint32_t)kStage);
+        uint8_t* st = smem + (size_t)s * kStage;
+        tma_load_2d(st, &tm_w, &full_bar[s], (kb0 + i) * kBK, f0, CTS_L2_EVICT_FIRST);
+        tma_load_2d(st + kABytes, &tm_x, &full_bar[s], (kb0 + i) * kBK, 0, CTS_L2_EVICT_LAST);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(kIsBf16 ? 1 : 0, BN, kBM);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % stages;
+        mbar_wait(&full_bar[s], ((uint32_t)(i / stages)) & 1u);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * kStage);
+        const uint64_t a_desc = umma_desc_k_sw128(a_addr), b_desc = umma_desc_k_sw128(a_addr + kABytes);
+#pragma unroll
+        for (int kk = 0; kk < kBK / kUmmaK; ++kk) {
+          const uint64_t adv = (uint64_t)(kk * ((kUmmaK * 2) >> 4));
+          umma_f16(tmem_base, a_desc + adv, b_desc + adv, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&acc_bar);
+    }
+  } else {
+    // ------------------------------ epilogue, part A: park this split's fp32 tile in shared memory ------------------------------
+    pdl_wait();
+    if (nkb > 0) {
+      mbar_wait(&acc_bar, 0);
+      tc_fence_after();
+    }
+    const int q = warp & 3;
+    const int ft = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      if (c >= T_) break;                                    // warp-uniform
+      uint32_t v[16];
+      if (nkb > 0) {
+        tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) part_s[(c + j) * kBM + ft] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster.sync();                                            // every split's tile is in its CTA's shared memory
+
+  if (warp >= 2) {
+    // ------------------------------ epilogue, part B: this CTA reduces tokens t = split, split + S, ... and applies the tail ------------------------------
+    const int ft = (warp & 3) * 32 + lane;                   // feature inside the tile (note: warp & 3 is a permutation of 0..3)
+    const long long f = (long long)f0 + ft;
+    const bool f_ok = f < p.n;
+    const int mode = p.mode;
+    for (int t = split; t < T_; t += S) {
+      float acc = 0.f;
+      for (int s2 = 0; s2 < S; ++s2) acc += *cluster.map_shared_rank(&part_s[t * kBM + ft], s2);      // split order, DSMEM
+      if (mode == CTS_FUSED_RESIDUAL) {
+        if (f_ok) {
+          T* hp = reinterpret_cast<T*>(p.h) + (long long)t * p.n + f;
+          *hp = DT<T>::from_f(rnd<T>(DT<T>::to_f(*hp) + rnd<T>(acc)));
+        }
+      } else if (mode == CTS_FUSED_SWIGLU) {
+        // tile = 64 gate rows then the 64 matching up rows: the up half publishes dtype(u), the gate half finishes
+        if (ft >= 64) xch[ft - 64] = rnd<T>(acc);
+        named_bar_sync(1, 128);
+        if (ft < 64 && f_ok) {
+          const long long i = (long long)(f0 >> 1) + ft;     // output feature: tile * 64 + ft
+          reinterpret_cast<T*>(p.act)[(long long)t * (p.n >> 1) + i] = DT<T>::from_f(rnd<T>(silu_f(rnd<T>(acc))) * xch[ft]);
+        }
+        named_bar_sync(1, 128);                              // xch is rewritten by the next token
+      } else {
+        // QKV: bias, per-head RMSNorm (Qwen3), RoPE, q_out / paged KV write -- head = f / d, all inside this tile
+        const int d = p.d, half = d >> 1;
+        const int head = (int)(f / d), i = (int)(f % d);
+        const bool is_q = head < p.nh, is_k = !is_q && head < p.nh + p.nkv;
+        float x = acc;
+        if (p.bias != nullptr && f_ok) x += DT<T>::to_f(reinterpret_cast<const T*>(p.bias)[f]);
+        x = rnd<T>(x);
+        if (p.q_norm != nullptr || p.k_norm != nullptr) {    // kernel-uniform
+          // statistic over the d features of the head: d = 128 -> the four warps, d = 64 -> warps {0,1} and {2,3} of the tile
+          float ss = warp_sum(f_ok ? x * x : 0.f);
+          if (lane == 0) red[ft >> 5] = ss;
+          named_bar_sync(1, 128);
+          float tot;
+          if (d == 128) tot = red[0] + red[1] + red[2] + red[3];
+          else tot = (ft < 64) ? red[0] + red[1] : red[2] + red[3];
+          named_bar_sync(1, 128);
+          const T* nw = reinterpret_cast<const T*>(is_q ? p.q_norm : (is_k ? p.k_norm : nullptr));
+          if (nw != nullptr && f_ok) {
+            const float inv = 1.0f / sqrtf(tot / (float)d + p.eps);
+            x = rnd<T>(DT<T>::to_f(nw[i]) * rnd<T>(x * inv));
+          }
+        }
+        xch[ft] = x;
+        named_bar_sync(1, 128);
+        if (f_ok) {
+          if (is_q || is_k) {
+            const int pos = p.positions[t];
+            const int ii = i < half ? i : i - half;
+            const float c = DT<T>::to_f(reinterpret_cast<const T*>(p.cos_tab)[(long long)pos * half + ii]);
+            const float sn = DT<T>::to_f(reinterpret_cast<const T*>(p.sin_tab)[(long long)pos * half + ii]);
+            const float xp = xch[i < half ? ft + half : ft - half];                      // rotate_half partner
+            x = i < half ? rnd<T>(rnd<T>(x * c) + rnd<T>(-xp * sn)) : rnd<T>(rnd<T>(x * c) + rnd<T>(xp * sn));
+          }
+          if (is_q) {
+            reinterpret_cast<T*>(p.q_out)[(long long)t * p.nh * d + (long long)head * d + i] = DT<T>::from_f(x);
+          } else {
+            const int kvh = is_k ? head - p.nh : head - p.nh - p.nkv;
+            T* cache = reinterpret_cast<T*>(is_k ? p.k_cache : p.v_cache);
+            const int slot = p.slot_map ? p.slot_map[t] : -1;
+            if (cache != nullptr && slot >= 0) {
+              const long long page = slot / p.page_size, off = slot % p.page_size;
+              cache[((page * p.nkv + kvh) * p.page_size + off) * d + i] = DT<T>::from_f(x);
+            }
+          }
+        }
+        named_bar_sync(1, 128);                              // xch / red are rewritten by the next token
+      }
+    }
+  }
+  cluster.sync();                                            // nobody leaves while a peer still reads its tile
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kCols>(tmem_base);
+}
+
+template <typename T, int BN>
+int launch_fused(cts_ctx* ctx, const cts_fused_gemm_args* a, cudaStream_t stream) {
+  const bool is_bf16 = a->dtype == CTS_BF16;
+  CUtensorMap tm_w, tm_x;
+  int rc = cts_make_tmap_2d(ctx, &tm_w, a->w, a->n, a->k, a->k, kBM, is_bf16);
+  if (rc) return rc;
+  rc = cts_make_tmap_2d(ctx, &tm_x, a->x, a->t, a->k, a->k, BN, is_bf16);
+  if (rc) return rc;
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = a->n; p.k = a->k; p.t = a->t;
+  p.kb_total = (int)cdiv_ll(a->k, kBK);
+  p.split = a->split_k; p.mode = a->mode;
+  p.bias = a->bias; p.h = a->h; p.act = a->act;
+  p.positions = a->positions; p.cos_tab = a->cos_tab; p.sin_tab = a->sin_tab; p.slot_map = a->slot_map;
+  p.q_out = a->q_out; p.k_cache = a->k_cache; p.v_cache = a->v_cache; p.q_norm = a->q_norm; p.k_norm = a->k_norm; p.eps = a->eps;
+  p.nh = a->nh; p.nkv = a->nkv; p.d = a->head_dim; p.page_size = a->page_size;
+  constexpr int kStage = kBM * kBK * 2 + BN * kBK * 2;
+  int stages = ctx->decode_stages * 1024 / kStage;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) stages = 2;
+  while ((size_t)stages * kStage < (size_t)BN * kBM * 4) ++stages;       // the parked fp32 tile reuses the ring
+  p.stages = stages;
+  const size_t smem = (size_t)stages * kStage + 1024;
+  auto kern = gemm_decode_fused_kernel<T, BN>;
+  CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cdiv_ll(a->n, kBM), 1, (unsigned)a->split_k);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 1;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = (unsigned)a->split_k;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  CTS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, tm_w, tm_x, p));
+  return CTS_OK;
+}
+
+}  // namespace
+
+extern "C" int cts_gemm_decode_fused(cts_ctx* ctx, const cts_fused_gemm_args* a, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, a != nullptr && a->w && a->x, "null args / w / x");
+  CTS_CHECK_ARG(ctx, a->n > 0 && a->k > 0 && a->t > 0 && a->t <= 32, "n, k > 0 and 1 <= t <= 32 (decode-sized step)");
+  CTS_CHECK_ARG(ctx, a->dtype == CTS_BF16 || a->dtype == CTS_F16, "dtype");
+  CTS_CHECK_ARG(ctx, a->split_k >= 1 && a->split_k <= 8, "1 <= split_k <= 8 (portable cluster size)");
+  CTS_CHECK_ARG(ctx, a->split_k <= cdiv_ll(a->k, kBK), "split_k exceeds the number of 64-wide K blocks");
+  CTS_CHECK_ARG(ctx, a->mode >= CTS_FUSED_RESIDUAL && a->mode <= CTS_FUSED_QKV_ROPE, "mode");
+  if (a->mode == CTS_FUSED_RESIDUAL) CTS_CHECK_ARG(ctx, a->h != nullptr, "CTS_FUSED_RESIDUAL needs h");
+  if (a->mode == CTS_FUSED_SWIGLU) CTS_CHECK_ARG(ctx, a->act != nullptr && a->n % 128 == 0, "CTS_FUSED_SWIGLU needs act and n % 128 == 0");
+  if (a->mode == CTS_FUSED_QKV_ROPE) {
+    CTS_CHECK_ARG(ctx, a->positions && a->cos_tab && a->sin_tab && a->q_out, "CTS_FUSED_QKV_ROPE needs positions, cos/sin tables, q_out");
+    CTS_CHECK_ARG(ctx, (a->head_dim == 64 || a->head_dim == 128) && a->nh > 0 && a->nkv > 0 &&
+                           a->n == (long long)(a->nh + 2 * a->nkv) * a->head_dim, "head_dim 64 or 128, n = (nh + 2 nkv) * head_dim");
+    CTS_CHECK_ARG(ctx, a->page_size > 0 || a->k_cache == nullptr, "page_size");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->dtype == CTS_BF16) return a->t <= 16 ? launch_fused<__nv_bfloat16, 16>(ctx, a, st) : launch_fused<__nv_bfloat16, 32>(ctx, a, st);
+  return a->t <= 16 ? launch_fused<__half, 16>(ctx, a, st) : launch_fused<__half, 32>(ctx, a, st);
+}

@@ -65,7 +65,7 @@ class _Step:
 class ChatTSForCausalLM:
     def __init__(self, config, state_dict, device="cuda", dtype=torch.bfloat16, tp_rank=0, tp_size=1,
                  max_batch=32, max_seq_len=2048, page_size=64, use_cuda_graph=True, comm=None,
-                 use_peer_allreduce=True, graph_with_tp=True, use_chain=None, use_sample_kernel=None, use_native_step=None):
+                 use_peer_allreduce=True, graph_with_tp=True, use_chain=None, use_sample_kernel=None, use_native_step=None, use_fused_decode=None):
         if not torch.cuda.is_available():
             raise _cabi.CtsError("chatts_b200 needs a B200 (sm_100a) GPU; there is no CPU fallback")
         self.config, self.dtype = config, dtype
@@ -88,6 +88,9 @@ class ChatTSForCausalLM:
         # the whole decode step enqueued by one C call (cts_decoder_step) instead of ~440 ctypes calls: identical launches; off by
         # default until compared with the Python orchestration on a B200 (CTS_NATIVE_STEP=1 / use_native_step=True)
         self.use_native_step = bool(int(_os.environ.get("CTS_NATIVE_STEP", "0"))) if use_native_step is None else bool(use_native_step)
+        # decode GEMMs with the split-K reduction and the projection tail fused in through a thread-block cluster
+        # (csrc/gemm_decode_fused.cu: 9 -> 7 dependent stages per layer); off by default until it has run on a B200
+        self.use_fused_decode = bool(int(_os.environ.get("CTS_DECODE_FUSED", "0"))) if use_fused_decode is None else bool(use_fused_decode)
         # sampled decoding through cts_sample_advance (csrc/sampling.cu) instead of torch ops: off by default until the kernel has
         # run on a B200 (written after the round-1 GPU budget was spent); CTS_SAMPLE_KERNEL=1 / use_sample_kernel=True turns it on
         self.use_sample_kernel = bool(int(_os.environ.get("CTS_SAMPLE_KERNEL", "0"))) if use_sample_kernel is None else bool(use_sample_kernel)
@@ -258,8 +261,22 @@ class ChatTSForCausalLM:
         c, sp, eps = self.ctx, st.splits, self.eps
         I, H = self.I, self.H
         c.reduce_residual_rmsnorm(None, 0, st.h, None, self.ln1[0], eps, st.xn, t=T)
+        fused = self.use_fused_decode and self.tp_size == 1 and T <= 32 and st.k_lin is None      # decode states only
         for l in range(self.L):
             kc, vc = self.kv[l, 0], self.kv[l, 1]
+            if fused:
+                # 7 stages per layer: every projection reduces its K splits inside a cluster and applies its tail in the epilogue
+                nw = self.ln1[l + 1] if l + 1 < self.L else self.final_norm
+                c.gemm_decode_fused(st.xn, self.wqkv[l], _cabi.FUSED_QKV_ROPE, min(sp["qkv"], 8), T, bias=self.bqkv[l], positions=st.positions,
+                                    cos=self.cos, sin=self.sin, slot_map=st.slot_map, q_out=st.q, k_cache=kc, v_cache=vc, q_norm=self.qn[l],
+                                    k_norm=self.kn[l], eps=eps, nh=self.nh, nkv=self.nkv, head_dim=self.d, page_size=self.page_size)
+                attend(l)
+                c.gemm_decode_fused(st.ao, self.wo[l], _cabi.FUSED_RESIDUAL, min(sp["o"], 8), T, h=st.h)
+                c.reduce_residual_rmsnorm(None, 0, st.h, None, self.ln2[l], eps, st.xn, t=T)
+                c.gemm_decode_fused(st.xn, self.wgu[l], _cabi.FUSED_SWIGLU, min(sp["gu"], 8), T, act=st.act)
+                c.gemm_decode_fused(st.act, self.wd[l], _cabi.FUSED_RESIDUAL, min(sp["d"], 8), T, h=st.h)
+                c.reduce_residual_rmsnorm(None, 0, st.h, None, nw, eps, st.xn, t=T)
+                continue
             # ---- QKV projection + bias + RoPE + KV write
             if sp["qkv"] > 1:
                 c.gemm(st.xn, self.wqkv[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["qkv"], t=T)

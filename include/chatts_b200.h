@@ -262,6 +262,32 @@ int cts_decode_chain(cts_ctx* ctx, const cts_chain_args* args, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------
+ * Decode GEMM with the split-K reduction and the projection's tail fused in (csrc/gemm_decode_fused.cu): the K splits of one
+ * 128-feature tile form one thread-block cluster (grid.z = cluster.z = split_k <= 8), park their fp32 accumulator tiles in
+ * shared memory and reduce disjoint tokens over distributed shared memory in split order -- bit-identical to
+ * cts_gemm(CTS_EPI_PARTIAL_F32) + the matching cts_reduce_* / cts_qkv_rope_cache call, without the second launch and without
+ * the fp32 round trip through L2.  t <= 32 tokens.
+ *   CTS_FUSED_RESIDUAL : h[t][f] = dtype(h[t][f] + dtype(acc))                     o_proj / down_proj  (modeling_qwen2.py:302,308)
+ *   CTS_FUSED_SWIGLU   : act[t][i] = dtype(silu(dtype(gate_i)) * dtype(up_i)), interleaved gate/up weight, act [t, n/2]      (:47)
+ *   CTS_FUSED_QKV_ROPE : bias + Qwen3 q/k norm + RoPE + q_out / paged KV write, arguments as cts_qkv_rope_cache  (:116-146,217-222)
+ */
+#define CTS_FUSED_RESIDUAL 0
+#define CTS_FUSED_SWIGLU 1
+#define CTS_FUSED_QKV_ROPE 2
+typedef struct {
+  const void* w; const void* x;          /* w [n, k] row-major (ld = k), x [t, k] (ld = k) */
+  long long n, k, t;
+  int dtype, mode, split_k, reserved;
+  const void* bias;                      /* [n] or NULL (QKV_ROPE) */
+  void* h;                               /* RESIDUAL: [t, n], updated in place */
+  void* act;                             /* SWIGLU: [t, n/2] */
+  const int* positions; const void* cos_tab; const void* sin_tab; const int* slot_map;
+  void* q_out; void* k_cache; void* v_cache; const void* q_norm; const void* k_norm;
+  float eps; int nh, nkv, head_dim, page_size;
+} cts_fused_gemm_args;
+int cts_gemm_decode_fused(cts_ctx* ctx, const cts_fused_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Whole decode step from C, and the two aliases of SURVEY.md 8(b)'s symbol list.  Host-side executors only: they enqueue the
  * kernels above on `stream` (capturable into a CUDA graph), nothing new runs on the device.
  *   cts_rmsnorm : out = w * dtype(x * rsqrt(mean(x^2) + eps))                      modeling_qwen2.py:258-263

@@ -323,3 +323,15 @@ class TorchDouble:
             self.gemm(h, w, dst, bias=b, row_map=row_map if last else None, epilogue=0 if last else 1)
             h = dst
         return valid, cnt, off
+
+    # ------------------------------------------------------------------ csrc/gemm_decode_fused.cu
+    def gemm_decode_fused(self, x, w, mode, split_k, t, *, bias=None, h=None, act=None, positions=None, cos=None, sin=None, slot_map=None,
+                          q_out=None, k_cache=None, v_cache=None, q_norm=None, k_norm=None, eps=1e-6, nh=0, nkv=0, head_dim=0, page_size=0):
+        """cts_gemm(CTS_EPI_PARTIAL_F32) + the matching reduce, i.e. what the cluster kernel fuses (same split order)."""
+        n = w.shape[0]
+        ws = torch.empty(split_k * t * n, dtype=torch.float32)
+        self.gemm(x, w, ws, epilogue=3, split_k=split_k, t=t)
+        if mode == 0: self.reduce_residual_rmsnorm(ws, split_k, h, h, None, eps, None, t=t)
+        elif mode == 1: self.reduce_swiglu(ws, split_k, t, n // 2, act, interleaved=True)
+        else: self.qkv_rope_cache(ws, True, split_k, bias, positions, cos, sin, slot_map, q_out, k_cache, v_cache, None, None, t, nh, nkv, head_dim,
+                                  page_size, q_norm, k_norm, eps)

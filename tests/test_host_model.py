@@ -184,3 +184,16 @@ def test_from_pretrained_reads_generation_config_defaults(cabi_double, tmp_path)
     g2 = model.generate(**enc, max_new_tokens=8, ignore_eos=True)
     assert not torch.equal(a, b)                       # the checkpoint's sampling defaults are in force
     assert torch.equal(g1, g2)                         # explicit greedy request == the model without a generation config
+
+
+@pytest.mark.parametrize("split,qwen3", [(1, False), (3, True)])
+def test_fused_decode_gemms_generate_the_same_tokens(cabi_double, split, qwen3):
+    """use_fused_decode=True: QKV / o_proj / gate_up / down_proj through ctx.gemm_decode_fused (cluster-reduced split-K + fused
+    tail) and plain RMSNorms between them -- same tokens, same KV cache contents as the nine-stage layer."""
+    cfg, sd, model, proc = _build(cabi_double, split, qwen3)
+    enc = proc(text=PROMPTS, timeseries=list(_series()), padding=True, return_tensors="pt")
+    ref = model.generate(**enc, max_new_tokens=9, ignore_eos=True)
+    cfg2, sd2, fused, _ = _build(cabi_double, split, qwen3, use_fused_decode=True)
+    out = fused.generate(**enc, max_new_tokens=9, ignore_eos=True)
+    assert torch.equal(out, ref) and len(fused.pool.free) == fused.pool.num_pages
+    assert torch.equal(fused.kv, model.kv)

@@ -47,5 +47,5 @@ extra = sys.argv[1:]
 if "-k" not in extra:          # the ChatTS-8B-shaped case generates its weights on the device: GPU only
     extra += ["-k", "not (directional and True)"]
 sys.exit(pytest.main([os.path.join(ROOT, "tests", f) for f in ("test_gpu_train_kernels.py", "test_gpu_zz_c_train.py", "test_gpu_zz_b_sampling.py", "test_gpu_zz_a_native_step.py",
-                                                         "test_gpu_zz_d_attn_bwd_tc5.py")] +
+                                                         "test_gpu_zz_d_attn_bwd_tc5.py", "test_gpu_zz_e_fused_decode.py")] +
                      ["-q", "-p", "no:cacheprovider", "--runxfail", "-m", "gpu"] + extra))

@@ -24,12 +24,12 @@ ab CTS_ATTN_BWD_TC5=1
 ab CTS_WGRAD_MMA=1
 ab CTS_ATTN_BWD_TC5=1 CTS_WGRAD_MMA=1
 echo "## decode: native step executor / sampling kernel (tokens/s, b=32)"
-for v in "CTS_BASE=1" "CTS_NATIVE_STEP=1"; do
-  echo "## $v"; env $v timeout 400 python bench.py --steps 32 --warmup 3 --only-batch --no-cpu-baseline --sweep-only 2>>gpurun_out/ab.err | python -c "
+for v in "CTS_BASE=1" "CTS_NATIVE_STEP=1" "CTS_DECODE_FUSED=1"; do
+  echo "## $v"; env $v timeout 400 python bench.py --steps 32 --warmup 3 --no-cpu-baseline --sweep-only 2>>gpurun_out/ab.err | python -c "
 import sys,json
 for l in sys.stdin:
     l=l.strip()
     if l.startswith('{'):
-        d=json.loads(l); print({'ms_per_step': round(d['ms_per_step'],3), 'launches_per_step': d.get('launches_per_step')})
+        d=json.loads(l); print({'ms_per_step': round(d['ms_per_step'],3), 'launches_per_step': d.get('launches_per_step'), 'by_batch': {b: round(v['ms_per_step'],3) for b, v in d['by_batch'].items()}})
 "; done
 ls -la gpurun_out | tail -n 40
