@@ -261,21 +261,29 @@ class ChatTSForCausalLM:
         c, sp, eps = self.ctx, st.splits, self.eps
         I, H = self.I, self.H
         c.reduce_residual_rmsnorm(None, 0, st.h, None, self.ln1[0], eps, st.xn, t=T)
-        fused = self.use_fused_decode and self.tp_size == 1 and T <= 32 and st.k_lin is None      # decode states only
+        fused = self.use_fused_decode and T <= 32 and st.k_lin is None                            # decode states only
         for l in range(self.L):
             kc, vc = self.kv[l, 0], self.kv[l, 1]
             if fused:
                 # 7 stages per layer: every projection reduces its K splits inside a cluster and applies its tail in the epilogue
+                # (under tensor parallelism the row-parallel o_proj / down_proj keep the peer-memory all-reduce kernel, which sums
+                # the local splits itself; the column-parallel QKV and gate_up projections are fused all the same)
                 nw = self.ln1[l + 1] if l + 1 < self.L else self.final_norm
                 c.gemm_decode_fused(st.xn, self.wqkv[l], _cabi.FUSED_QKV_ROPE, min(sp["qkv"], 8), T, bias=self.bqkv[l], positions=st.positions,
                                     cos=self.cos, sin=self.sin, slot_map=st.slot_map, q_out=st.q, k_cache=kc, v_cache=vc, q_norm=self.qn[l],
                                     k_norm=self.kn[l], eps=eps, nh=self.nh, nkv=self.nkv, head_dim=self.d, page_size=self.page_size)
                 attend(l)
-                c.gemm_decode_fused(st.ao, self.wo[l], _cabi.FUSED_RESIDUAL, min(sp["o"], 8), T, h=st.h)
-                c.reduce_residual_rmsnorm(None, 0, st.h, None, self.ln2[l], eps, st.xn, t=T)
+                if self.tp_size > 1:
+                    self._tp_row_parallel(st, T, st.ao, self.wo[l], self.ln2[l], 0, sp["o"])
+                else:
+                    c.gemm_decode_fused(st.ao, self.wo[l], _cabi.FUSED_RESIDUAL, min(sp["o"], 8), T, h=st.h)
+                    c.reduce_residual_rmsnorm(None, 0, st.h, None, self.ln2[l], eps, st.xn, t=T)
                 c.gemm_decode_fused(st.xn, self.wgu[l], _cabi.FUSED_SWIGLU, min(sp["gu"], 8), T, act=st.act)
-                c.gemm_decode_fused(st.act, self.wd[l], _cabi.FUSED_RESIDUAL, min(sp["d"], 8), T, h=st.h)
-                c.reduce_residual_rmsnorm(None, 0, st.h, None, nw, eps, st.xn, t=T)
+                if self.tp_size > 1:
+                    self._tp_row_parallel(st, T, st.act, self.wd[l], nw, 1, sp["d"])
+                else:
+                    c.gemm_decode_fused(st.act, self.wd[l], _cabi.FUSED_RESIDUAL, min(sp["d"], 8), T, h=st.h)
+                    c.reduce_residual_rmsnorm(None, 0, st.h, None, nw, eps, st.xn, t=T)
                 continue
             # ---- QKV projection + bias + RoPE + KV write
             if sp["qkv"] > 1:
