@@ -16,6 +16,7 @@ for l in sys.stdin:
 " >> $OUT
 }
 run CTS_BASELINE=1
+run CTS_DECODE_FUSED=1
 for s in "1,1,1,1" "2,1,2,1" "3,2,3,2" "5,3,4,3"; do run CTS_SPLITS=$s; done          # qkv,o,gu,d (decode-sized T only)
 for a in 1 2 4; do run CTS_ATTN_SPLITS=$a; done
 for k in 50 75 100; do run CTS_DECODE_SMEM_KB=$k; done
