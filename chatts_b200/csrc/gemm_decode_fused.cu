@@ -166,9 +166,25 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
     const long long f = (long long)f0 + ft;
     const bool f_ok = f < p.n;
     const int mode = p.mode;
-    for (int t = split; t < T_; t += S) {
-      float acc = 0.f;
-      for (int s2 = 0; s2 < S; ++s2) acc += *cluster.map_shared_rank(&part_s[t * kBM + ft], s2);      // split order, DSMEM
+    // tokens in groups of 4: the 4 x S distributed-shared-memory loads of a group are independent and issued back to back, so
+    // the DSMEM latency is paid once per group instead of once per token; the sum of a token still runs in split order
+    constexpr int kGroup = 4;
+    float accs[kGroup];
+    for (int tb = split; tb < T_; tb += kGroup * S)
+    for (int u = 0; u < kGroup; ++u) {
+      if (u == 0) {
+#pragma unroll
+        for (int u2 = 0; u2 < kGroup; ++u2) {
+          const int t2 = tb + u2 * S;
+          float a2 = 0.f;
+          if (t2 < T_)
+            for (int s2 = 0; s2 < S; ++s2) a2 += *cluster.map_shared_rank(&part_s[t2 * kBM + ft], s2);      // split order, DSMEM
+          accs[u2] = a2;
+        }
+      }
+      const int t = tb + u * S;
+      if (t >= T_) break;                                    // CTA-uniform
+      const float acc = accs[u];
       if (mode == CTS_FUSED_RESIDUAL) {
         if (f_ok) {
           T* hp = reinterpret_cast<T*>(p.h) + (long long)t * p.n + f;
