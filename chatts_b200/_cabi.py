@@ -79,7 +79,9 @@ class FusedGemmArgs(C.Structure):
                 [(k, C.c_int) for k in ("dtype", "mode", "split_k", "reserved")] +
                 [(k, C.c_void_p) for k in ("bias", "h", "act", "positions", "cos_tab", "sin_tab", "slot_map", "q_out", "k_cache", "v_cache",
                                            "q_norm", "k_norm")] + [("eps", C.c_float)] +
-                [(k, C.c_int) for k in ("nh", "nkv", "head_dim", "page_size")])
+                [(k, C.c_int) for k in ("nh", "nkv", "head_dim", "page_size")] +
+                [("norm_h", C.c_void_p), ("norm_w", C.c_void_p), ("ssq_in", C.c_void_p), ("ssq_tiles", C.c_int), ("norm_eps", C.c_float),
+                 ("ssq_out", C.c_void_p)])
 
 
 class TsEncodeArgs(C.Structure):
@@ -311,12 +313,16 @@ class Context:
 
     def gemm_decode_fused(self, x, w, mode, split_k, t, *, bias=None, h=None, act=None, positions=None, cos=None, sin=None, slot_map=None,
                           q_out=None, k_cache=None, v_cache=None, q_norm=None, k_norm=None, eps=1e-6, nh=0, nkv=0, head_dim=0,
-                          page_size=0):
-        """Cluster-reduced decode GEMM with the projection's tail fused in (cts_gemm_decode_fused); t <= 32, split_k <= 8."""
+                          page_size=0, norm_h=None, norm_w=None, ssq_in=None, norm_eps=1e-6, ssq_out=None):
+        """Cluster-reduced decode GEMM with the projection's tail fused in (cts_gemm_decode_fused); t <= 32, split_k <= 8.
+        norm_h / norm_w / ssq_in: the token operand is RMSNorm(norm_h) produced inside the kernel (x may be None);
+        ssq_out (RESIDUAL): per-tile sums of squares of the updated h for the next projection's fused RMSNorm."""
         a = FusedGemmArgs()
         dp = lambda v: None if v is None else v.data_ptr()
-        a.w, a.x, a.n, a.k, a.t = w.data_ptr(), x.data_ptr(), w.shape[0], w.shape[1], t
-        a.dtype, a.mode, a.split_k = dtype_code(x.dtype), int(mode), int(split_k)
+        a.w, a.x, a.n, a.k, a.t = w.data_ptr(), dp(x), w.shape[0], w.shape[1], t
+        a.norm_h, a.norm_w, a.ssq_in, a.ssq_out = dp(norm_h), dp(norm_w), dp(ssq_in), dp(ssq_out)
+        a.ssq_tiles, a.norm_eps = (ssq_in.shape[-1] if ssq_in is not None else 0), float(norm_eps)
+        a.dtype, a.mode, a.split_k = dtype_code(w.dtype), int(mode), int(split_k)
         a.bias, a.h, a.act = dp(bias), dp(h), dp(act)
         a.positions, a.cos_tab, a.sin_tab, a.slot_map = dp(positions), dp(cos), dp(sin), dp(slot_map)
         a.q_out, a.k_cache, a.v_cache, a.q_norm, a.k_norm = dp(q_out), dp(k_cache), dp(v_cache), dp(q_norm), dp(k_norm)

@@ -44,9 +44,12 @@ struct FusedParams {
   void* q_out; void* k_cache; void* v_cache;
   const void* q_norm; const void* k_norm; float eps;
   int nh, nkv, d, page_size;
+  // NORM_IN: the token operand is RMSNorm(norm_h) * norm_w, produced by the epilogue warps straight into the swizzled B tiles
+  const void* norm_h; const void* norm_w; const float* ssq_in; int ssq_tiles; float norm_eps;
+  float* ssq_out;         // RESIDUAL: [t][tiles of n] sum of squares of the updated h per 128-feature tile (or NULL)
 };
 
-template <typename T, int BN>
+template <typename T, int BN, bool NORM_IN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -56,6 +59,7 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
   __shared__ uint32_t tmem_slot;
   __shared__ float xch[kBM];            // tile-local exchange (SwiGLU up values / RoPE partners)
   __shared__ float red[4];              // per-warp partial sums of the q/k RMSNorm statistic
+  __shared__ float rstd_s[32];          // NORM_IN: rsqrt(mean(h^2) + eps) of every token
 
   constexpr int kABytes = kBM * kBK * 2;
   constexpr int kStage = kABytes + BN * kBK * 2;
@@ -82,7 +86,8 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_x);
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    // NORM_IN: a stage is full when the weight tile has landed (TMA, expect_tx) AND the four epilogue warps have written B
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], NORM_IN ? 5 : 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
     fence_mbar_init();
   }
@@ -96,20 +101,22 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
     // ------------------------------ TMA producer (as gemm_tn_kernel: weights before the dependency wait) ------------------------------
     if (lane == 0) {
       const int npre = nkb < stages ? nkb : stages;
+      constexpr uint32_t kTx = NORM_IN ? (uint32_t)kABytes : (uint32_t)kStage;
       for (int i = 0; i < npre; ++i) {
-        mbar_expect_tx(&full_bar[i], (uint32_t)kStage);
+        mbar_expect_tx(&full_bar[i], kTx);
         tma_load_2d(smem + (size_t)i * kStage, &tm_w, &full_bar[i], (kb0 + i) * kBK, f0, CTS_L2_EVICT_FIRST);
       }
       pdl_wait();
-      for (int i = 0; i < npre; ++i)
-        tma_load_2d(smem + (size_t)i * kStage + kABytes, &tm_x, &full_bar[i], (kb0 + i) * kBK, 0, CTS_L2_EVICT_LAST);
+      if (!NORM_IN)
+        for (int i = 0; i < npre; ++i)
+          tma_load_2d(smem + (size_t)i * kStage + kABytes, &tm_x, &full_bar[i], (kb0 + i) * kBK, 0, CTS_L2_EVICT_LAST);
       for (int i = npre; i < nkb; ++i) {
         const int s = i % stages;
         mbar_wait(&empty_bar[s], (((uint32_t)(i / stages)) & 1u) ^ 1u);
-        mbar_expect_tx(&full_bar[s], (uint32_t)kStage);
+        mbar_expect_tx(&full_bar[s], kTx);
         uint8_t* st = smem + (size_t)s * kStage;
         tma_load_2d(st, &tm_w, &full_bar[s], (kb0 + i) * kBK, f0, CTS_L2_EVICT_FIRST);
-        tma_load_2d(st + kABytes, &tm_x, &full_bar[s], (kb0 + i) * kBK, 0, CTS_L2_EVICT_LAST);
+        if (!NORM_IN) tma_load_2d(st + kABytes, &tm_x, &full_bar[s], (kb0 + i) * kBK, 0, CTS_L2_EVICT_LAST);
       }
     }
   } else if (warp == 1) {
@@ -132,8 +139,46 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
       umma_commit(&acc_bar);
     }
   } else {
-    // ------------------------------ epilogue, part A: park this split's fp32 tile in shared memory ------------------------------
     pdl_wait();
+    if (NORM_IN) {
+      // ------------------------------ B-operand producers: xn = norm_w * dtype(h * rstd) written as the swizzled K-major token tile ------------------------------
+      // (modeling_qwen2.py:258-263 -- the same values the stand-alone RMSNorm kernel stores, without the launch and the round trip;
+      //  the row statistic comes from the per-tile sums of squares the previous fused RESIDUAL projection left in ssq_in)
+      const int et = (int)threadIdx.x - 64;                   // 0..127 inside the epilogue group
+      if (et < BN) {
+        float tot = 0.f;
+        if (et < T_)
+          for (int j = 0; j < p.ssq_tiles; ++j) tot += p.ssq_in[(long long)et * p.ssq_tiles + j];       // fixed order
+        rstd_s[et] = 1.0f / sqrtf(tot / (float)p.k + p.norm_eps);
+      }
+      named_bar_sync(1, 128);
+      const T* hsrc = reinterpret_cast<const T*>(p.norm_h);
+      const T* nw = reinterpret_cast<const T*>(p.norm_w);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % stages;
+        mbar_wait(&empty_bar[s], (((uint32_t)(i / stages)) & 1u) ^ 1u);       // the MMAs that read this slot have completed
+        uint8_t* bt = smem + (size_t)s * kStage + kABytes;                      // [BN rows x 128 B], 128B swizzle
+        for (int it = et; it < BN * 8; it += 128) {
+          const int t = it >> 3, ch = it & 7;
+          const long long k0 = (long long)(kb0 + i) * kBK + ch * 8;
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (t < T_ && k0 < p.k) {                                             // k is a multiple of 8 (16-byte rows)
+            float hv[8], wv[8], xv[8];
+            unpack8<T>(*reinterpret_cast<const uint4*>(hsrc + (long long)t * p.k + k0), hv);
+            unpack8<T>(*reinterpret_cast<const uint4*>(nw + k0), wv);
+            const float r = rstd_s[t];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xv[e] = wv[e] * rnd<T>(hv[e] * r);
+            o = pack8<T>(xv);
+          }
+          *reinterpret_cast<uint4*>(bt + (uint32_t)t * 128 + ((ch ^ (t & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();                                               // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+      }
+    }
+    // ------------------------------ epilogue, part A: park this split's fp32 tile in shared memory ------------------------------
     if (nkb > 0) {
       mbar_wait(&acc_bar, 0);
       tc_fence_after();
@@ -186,9 +231,18 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
       if (t >= T_) break;                                    // CTA-uniform
       const float acc = accs[u];
       if (mode == CTS_FUSED_RESIDUAL) {
+        float r = 0.f;
         if (f_ok) {
           T* hp = reinterpret_cast<T*>(p.h) + (long long)t * p.n + f;
-          *hp = DT<T>::from_f(rnd<T>(DT<T>::to_f(*hp) + rnd<T>(acc)));
+          r = rnd<T>(DT<T>::to_f(*hp) + rnd<T>(acc));
+          *hp = DT<T>::from_f(r);
+        }
+        if (p.ssq_out != nullptr) {                           // kernel-uniform: this tile's share of sum(h^2) for the next RMSNorm
+          const float ss = warp_sum(r * r);
+          if (lane == 0) red[ft >> 5] = ss;
+          named_bar_sync(1, 128);
+          if (ft == 0) p.ssq_out[(long long)t * gridDim.x + blockIdx.x] = red[0] + red[1] + red[2] + red[3];
+          named_bar_sync(1, 128);
         }
       } else if (mode == CTS_FUSED_SWIGLU) {
         // tile = 64 gate rows then the 64 matching up rows: the up half publishes dtype(u), the gate half finishes
@@ -255,14 +309,18 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
   if (warp == 1) tmem_dealloc<kCols>(tmem_base);
 }
 
-template <typename T, int BN>
+template <typename T, int BN, bool NORM_IN>
 int launch_fused(cts_ctx* ctx, const cts_fused_gemm_args* a, cudaStream_t stream) {
   const bool is_bf16 = a->dtype == CTS_BF16;
   CUtensorMap tm_w, tm_x;
   int rc = cts_make_tmap_2d(ctx, &tm_w, a->w, a->n, a->k, a->k, kBM, is_bf16);
   if (rc) return rc;
-  rc = cts_make_tmap_2d(ctx, &tm_x, a->x, a->t, a->k, a->k, BN, is_bf16);
-  if (rc) return rc;
+  if (NORM_IN) {
+    tm_x = tm_w;                                            // unused: the token operand is produced in the kernel
+  } else {
+    rc = cts_make_tmap_2d(ctx, &tm_x, a->x, a->t, a->k, a->k, BN, is_bf16);
+    if (rc) return rc;
+  }
   FusedParams p;
   memset(&p, 0, sizeof(p));
   p.n = a->n; p.k = a->k; p.t = a->t;
@@ -272,6 +330,8 @@ int launch_fused(cts_ctx* ctx, const cts_fused_gemm_args* a, cudaStream_t stream
   p.positions = a->positions; p.cos_tab = a->cos_tab; p.sin_tab = a->sin_tab; p.slot_map = a->slot_map;
   p.q_out = a->q_out; p.k_cache = a->k_cache; p.v_cache = a->v_cache; p.q_norm = a->q_norm; p.k_norm = a->k_norm; p.eps = a->eps;
   p.nh = a->nh; p.nkv = a->nkv; p.d = a->head_dim; p.page_size = a->page_size;
+  p.norm_h = a->norm_h; p.norm_w = a->norm_w; p.ssq_in = a->ssq_in; p.ssq_tiles = a->ssq_tiles; p.norm_eps = a->norm_eps;
+  p.ssq_out = a->ssq_out;
   constexpr int kStage = kBM * kBK * 2 + BN * kBK * 2;
   int stages = ctx->decode_stages * 1024 / kStage;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -279,7 +339,7 @@ int launch_fused(cts_ctx* ctx, const cts_fused_gemm_args* a, cudaStream_t stream
   while ((size_t)stages * kStage < (size_t)BN * kBM * 4) ++stages;       // the parked fp32 tile reuses the ring
   p.stages = stages;
   const size_t smem = (size_t)stages * kStage + 1024;
-  auto kern = gemm_decode_fused_kernel<T, BN>;
+  auto kern = gemm_decode_fused_kernel<T, BN, NORM_IN>;
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)cdiv_ll(a->n, kBM), 1, (unsigned)a->split_k);
@@ -303,7 +363,7 @@ int launch_fused(cts_ctx* ctx, const cts_fused_gemm_args* a, cudaStream_t stream
 
 extern "C" int cts_gemm_decode_fused(cts_ctx* ctx, const cts_fused_gemm_args* a, void* stream) {
   if (!ctx) return CTS_ERR_BAD_ARG;
-  CTS_CHECK_ARG(ctx, a != nullptr && a->w && a->x, "null args / w / x");
+  CTS_CHECK_ARG(ctx, a != nullptr && a->w, "null args / w");
   CTS_CHECK_ARG(ctx, a->n > 0 && a->k > 0 && a->t > 0 && a->t <= 32, "n, k > 0 and 1 <= t <= 32 (decode-sized step)");
   CTS_CHECK_ARG(ctx, a->dtype == CTS_BF16 || a->dtype == CTS_F16, "dtype");
   CTS_CHECK_ARG(ctx, a->split_k >= 1 && a->split_k <= 8, "1 <= split_k <= 8 (portable cluster size)");
@@ -317,7 +377,17 @@ extern "C" int cts_gemm_decode_fused(cts_ctx* ctx, const cts_fused_gemm_args* a,
                            a->n == (long long)(a->nh + 2 * a->nkv) * a->head_dim, "head_dim 64 or 128, n = (nh + 2 nkv) * head_dim");
     CTS_CHECK_ARG(ctx, a->page_size > 0 || a->k_cache == nullptr, "page_size");
   }
+  const bool norm_in = a->norm_h != nullptr;
+  if (norm_in) {
+    CTS_CHECK_ARG(ctx, a->norm_w && a->ssq_in && a->ssq_tiles > 0 && a->k % 8 == 0, "NORM_IN needs norm_w, ssq_in, ssq_tiles > 0 and k % 8 == 0");
+  } else {
+    CTS_CHECK_ARG(ctx, a->x != nullptr, "x is required unless norm_h is given");
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->dtype == CTS_BF16) return a->t <= 16 ? launch_fused<__nv_bfloat16, 16>(ctx, a, st) : launch_fused<__nv_bfloat16, 32>(ctx, a, st);
-  return a->t <= 16 ? launch_fused<__half, 16>(ctx, a, st) : launch_fused<__half, 32>(ctx, a, st);
+#define FUSED_GO(TT)                                                                                              \
+  if (norm_in) return a->t <= 16 ? launch_fused<TT, 16, true>(ctx, a, st) : launch_fused<TT, 32, true>(ctx, a, st); \
+  return a->t <= 16 ? launch_fused<TT, 16, false>(ctx, a, st) : launch_fused<TT, 32, false>(ctx, a, st);
+  if (a->dtype == CTS_BF16) { FUSED_GO(__nv_bfloat16) }
+  FUSED_GO(__half)
+#undef FUSED_GO
 }

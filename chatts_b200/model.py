@@ -90,7 +90,10 @@ class ChatTSForCausalLM:
         self.use_native_step = bool(int(_os.environ.get("CTS_NATIVE_STEP", "0"))) if use_native_step is None else bool(use_native_step)
         # decode GEMMs with the split-K reduction and the projection tail fused in through a thread-block cluster
         # (csrc/gemm_decode_fused.cu: 9 -> 7 dependent stages per layer); off by default until it has run on a B200
-        self.use_fused_decode = bool(int(_os.environ.get("CTS_DECODE_FUSED", "0"))) if use_fused_decode is None else bool(use_fused_decode)
+        #   1: projections fused with their tails, plain RMSNorm launches between them (7 stages, bit-identical to the default path)
+        #   2: the RMSNorms too -- the residual projections emit per-tile sums of squares, the next projection builds its normalised
+        #      token operand itself (5 stages; single GPU only)
+        self.use_fused_decode = int(_os.environ.get("CTS_DECODE_FUSED", "0")) if use_fused_decode is None else int(use_fused_decode)
         # sampled decoding through cts_sample_advance (csrc/sampling.cu) instead of torch ops: off by default until the kernel has
         # run on a B200 (written after the round-1 GPU budget was spent); CTS_SAMPLE_KERNEL=1 / use_sample_kernel=True turns it on
         self.use_sample_kernel = bool(int(_os.environ.get("CTS_SAMPLE_KERNEL", "0"))) if use_sample_kernel is None else bool(use_sample_kernel)
@@ -269,9 +272,27 @@ class ChatTSForCausalLM:
                 # (under tensor parallelism the row-parallel o_proj / down_proj keep the peer-memory all-reduce kernel, which sums
                 # the local splits itself; the column-parallel QKV and gate_up projections are fused all the same)
                 nw = self.ln1[l + 1] if l + 1 < self.L else self.final_norm
-                c.gemm_decode_fused(st.xn, self.wqkv[l], _cabi.FUSED_QKV_ROPE, min(sp["qkv"], 8), T, bias=self.bqkv[l], positions=st.positions,
-                                    cos=self.cos, sin=self.sin, slot_map=st.slot_map, q_out=st.q, k_cache=kc, v_cache=vc, q_norm=self.qn[l],
-                                    k_norm=self.kn[l], eps=eps, nh=self.nh, nkv=self.nkv, head_dim=self.d, page_size=self.page_size)
+                deep = self.use_fused_decode >= 2 and self.tp_size == 1
+                rope = dict(bias=self.bqkv[l], positions=st.positions, cos=self.cos, sin=self.sin, slot_map=st.slot_map, q_out=st.q, k_cache=kc,
+                            v_cache=vc, q_norm=self.qn[l], k_norm=self.kn[l], eps=eps, nh=self.nh, nkv=self.nkv, head_dim=self.d,
+                            page_size=self.page_size)
+                if deep:
+                    # 5 stages: QKV(norm in, RoPE out) -> attention -> o_proj(+residual, sum of squares out) -> gate_up(norm in, SwiGLU out)
+                    # -> down(+residual, sum of squares out); layer 0 takes the xn of the plain RMSNorm above
+                    if l == 0:
+                        c.gemm_decode_fused(st.xn, self.wqkv[l], _cabi.FUSED_QKV_ROPE, min(sp["qkv"], 8), T, **rope)
+                    else:
+                        c.gemm_decode_fused(None, self.wqkv[l], _cabi.FUSED_QKV_ROPE, min(sp["qkv"], 8), T, norm_h=st.h, norm_w=self.ln1[l],
+                                            ssq_in=st.ssq_b, norm_eps=eps, **rope)
+                    attend(l)
+                    c.gemm_decode_fused(st.ao, self.wo[l], _cabi.FUSED_RESIDUAL, min(sp["o"], 8), T, h=st.h, ssq_out=st.ssq_a)
+                    c.gemm_decode_fused(None, self.wgu[l], _cabi.FUSED_SWIGLU, min(sp["gu"], 8), T, act=st.act, norm_h=st.h, norm_w=self.ln2[l],
+                                        ssq_in=st.ssq_a, norm_eps=eps)
+                    c.gemm_decode_fused(st.act, self.wd[l], _cabi.FUSED_RESIDUAL, min(sp["d"], 8), T, h=st.h, ssq_out=st.ssq_b)
+                    if l + 1 == self.L:
+                        c.reduce_residual_rmsnorm(None, 0, st.h, None, self.final_norm, eps, st.xn, t=T)
+                    continue
+                c.gemm_decode_fused(st.xn, self.wqkv[l], _cabi.FUSED_QKV_ROPE, min(sp["qkv"], 8), T, **rope)
                 attend(l)
                 if self.tp_size > 1:
                     self._tp_row_parallel(st, T, st.ao, self.wo[l], self.ln2[l], 0, sp["o"])
@@ -487,6 +508,9 @@ class ChatTSForCausalLM:
         st.attn_ws = torch.zeros(self.ctx.attn_decode_workspace_floats(B, self.nh, self.d, st.attn_splits), device=dev,
                                  dtype=torch.float32)      # zero-filled once: holds the self-resetting split counters
         st.ssq = torch.zeros(B * 8, device=dev, dtype=torch.float32)
+        tiles_h = (self.H + 127) // 128                             # per-tile sums of squares of h (fused decode level 2)
+        st.ssq_a = torch.zeros(B, tiles_h, device=dev, dtype=torch.float32)
+        st.ssq_b = torch.zeros(B, tiles_h, device=dev, dtype=torch.float32)
         st.chain_sync = torch.zeros(2, device=dev, dtype=torch.int32)       # grid-barrier counters of the chain kernel
         st.graph = st.graph_nosample = None
         self._steps[key] = st

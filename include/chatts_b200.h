@@ -284,6 +284,12 @@ typedef struct {
   const int* positions; const void* cos_tab; const void* sin_tab; const int* slot_map;
   void* q_out; void* k_cache; void* v_cache; const void* q_norm; const void* k_norm;
   float eps; int nh, nkv, head_dim, page_size;
+  /* optional RMSNorm fusion on both sides (5 stages per layer instead of 7):
+   *   norm_h != NULL: the token operand is norm_w * dtype(norm_h * rsqrt(sum_j ssq_in[t][j] / k + norm_eps)) (modeling_qwen2.py:258-263),
+   *     written by the kernel straight into its B tiles -- x is ignored; ssq_in fp32 [t][ssq_tiles] = per-tile sums of squares of norm_h
+   *   ssq_out != NULL (CTS_FUSED_RESIDUAL): fp32 [t][ceil(n/128)] = sum of squares of the updated h over each 128-feature tile */
+  const void* norm_h; const void* norm_w; const float* ssq_in; int ssq_tiles; float norm_eps;
+  float* ssq_out;
 } cts_fused_gemm_args;
 int cts_gemm_decode_fused(cts_ctx* ctx, const cts_fused_gemm_args* args, void* stream);
 

@@ -326,12 +326,20 @@ class TorchDouble:
 
     # ------------------------------------------------------------------ csrc/gemm_decode_fused.cu
     def gemm_decode_fused(self, x, w, mode, split_k, t, *, bias=None, h=None, act=None, positions=None, cos=None, sin=None, slot_map=None,
-                          q_out=None, k_cache=None, v_cache=None, q_norm=None, k_norm=None, eps=1e-6, nh=0, nkv=0, head_dim=0, page_size=0):
+                          q_out=None, k_cache=None, v_cache=None, q_norm=None, k_norm=None, eps=1e-6, nh=0, nkv=0, head_dim=0, page_size=0,
+                          norm_h=None, norm_w=None, ssq_in=None, norm_eps=1e-6, ssq_out=None):
         """cts_gemm(CTS_EPI_PARTIAL_F32) + the matching reduce, i.e. what the cluster kernel fuses (same split order)."""
         n = w.shape[0]
+        if norm_h is not None:            # token operand = RMSNorm(norm_h) from the per-tile sums of squares
+            hh = norm_h[:t].float(); rstd = torch.rsqrt(ssq_in[:t].sum(-1, keepdim=True) / hh.shape[-1] + norm_eps)
+            x = norm_w * (hh * rstd).to(norm_h.dtype)
         ws = torch.empty(split_k * t * n, dtype=torch.float32)
         self.gemm(x, w, ws, epilogue=3, split_k=split_k, t=t)
-        if mode == 0: self.reduce_residual_rmsnorm(ws, split_k, h, h, None, eps, None, t=t)
+        if mode == 0:
+            self.reduce_residual_rmsnorm(ws, split_k, h, h, None, eps, None, t=t)
+            if ssq_out is not None:
+                hf = h[:t].float(); pad = (-hf.shape[1]) % 128
+                ssq_out[:t] = torch.nn.functional.pad(hf, (0, pad)).view(t, -1, 128).pow(2).sum(-1)
         elif mode == 1: self.reduce_swiglu(ws, split_k, t, n // 2, act, interleaved=True)
         else: self.qkv_rope_cache(ws, True, split_k, bias, positions, cos, sin, slot_map, q_out, k_cache, v_cache, None, None, t, nh, nkv, head_dim,
                                   page_size, q_norm, k_norm, eps)

@@ -112,3 +112,80 @@ def test_generate_with_fused_decode_gemms(qwen3, graph):
         assert torch.equal(a, b)
     else:       # q/k-norm statistic order differs by an ulp: identical prefix expected, full equality not guaranteed
         assert torch.equal(a[:, : enc["input_ids"].shape[1] + 4], b[:, : enc["input_ids"].shape[1] + 4])
+
+
+@pytest.mark.parametrize("t,n,k,s", [(8, 5120, 5120, 7), (32, 640, 1024, 3)])
+def test_residual_emits_per_tile_sums_of_squares(t, n, k, s):
+    c = ctx()
+    g = _g(t + n)
+    x, w, h0 = _rn(g, t, k, std=0.5), _rn(g, n, k, std=0.05), _rn(g, t, n, std=0.5)
+    tiles = (n + 127) // 128
+    out, ssq = h0.clone(), torch.full((t, tiles), float("nan"), device="cuda")
+    c.gemm_decode_fused(x, w, 0, s, t, h=out, ssq_out=ssq)
+    ref = h0.clone()
+    c.gemm_decode_fused(x, w, 0, s, t, h=ref)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    want = torch.nn.functional.pad(out.float(), (0, tiles * 128 - n)).view(t, tiles, 128).pow(2).sum(-1)
+    assert torch.allclose(ssq, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode,t,s", [(1, 8, 2), (2, 32, 5), (1, 32, 3)])
+def test_rmsnorm_fused_into_the_token_operand(mode, t, s):
+    """norm_h / norm_w / ssq_in: the kernel builds xn = w * dtype(h * rstd) itself -- against the RMSNorm launch + the same fused GEMM."""
+    c = ctx()
+    g = _g(mode * 100 + t)
+    H, inter, d, nh, nkv, page = 1024, 704, 128, 4, 2, 16
+    h = _rn(g, t, H, std=1.5)
+    nw = (torch.rand(H, generator=g) + 0.5).to(DT).cuda()
+    tiles = H // 128
+    ssq = h.float().view(t, tiles, 128).pow(2).sum(-1).contiguous()
+    xn = torch.empty_like(h)
+    c.reduce_residual_rmsnorm(None, 0, h, None, nw, 1e-6, xn, t=t)
+    if mode == 1:
+        w = _rn(g, 2 * inter, H, std=0.05)
+        a, b = torch.empty(t, inter, device="cuda", dtype=DT), torch.empty(t, inter, device="cuda", dtype=DT)
+        c.gemm_decode_fused(xn, w, 1, s, t, act=a)
+        c.gemm_decode_fused(None, w, 1, s, t, act=b, norm_h=h, norm_w=nw, ssq_in=ssq, norm_eps=1e-6)
+        pairs = [(a, b)]
+    else:
+        N = (nh + 2 * nkv) * d
+        w, bias = _rn(g, N, H, std=0.05), _rn(g, N, std=0.2)
+        pos = torch.arange(t, dtype=torch.int32).cuda()
+        ang = torch.rand(64, d // 2, generator=g) * 6.28
+        cos, sin = ang.cos().to(DT).cuda(), ang.sin().to(DT).cuda()
+        slot = torch.arange(t, dtype=torch.int32).cuda()
+        outs = []
+        for fused_norm in (False, True):
+            q = torch.empty(t, nh * d, device="cuda", dtype=DT)
+            kc, vc = torch.zeros(4, nkv, page, d, device="cuda", dtype=DT), torch.zeros(4, nkv, page, d, device="cuda", dtype=DT)
+            kw = dict(bias=bias, positions=pos, cos=cos, sin=sin, slot_map=slot, q_out=q, k_cache=kc, v_cache=vc, eps=1e-6, nh=nh, nkv=nkv,
+                      head_dim=d, page_size=page)
+            if fused_norm:
+                c.gemm_decode_fused(None, w, 2, s, t, norm_h=h, norm_w=nw, ssq_in=ssq, norm_eps=1e-6, **kw)
+            else:
+                c.gemm_decode_fused(xn, w, 2, s, t, **kw)
+            outs.append((q, kc, vc))
+        pairs = list(zip(outs[0], outs[1]))
+    torch.cuda.synchronize()
+    for a, b in pairs:      # the row statistic is summed tile by tile: rstd may move by an fp32 ulp -> at most one bf16 ulp in the output
+        assert torch.isfinite(b.float()).all()
+        assert float((a.float() - b.float()).abs().max()) <= 2 ** -7 * float(a.float().abs().max()) + 1e-6
+
+
+def test_generate_with_five_stage_layers():
+    from chatts_b200 import ChatTSConfig, ChatTSProcessor, SimpleTokenizer
+    from chatts_b200.model import ChatTSForCausalLM
+    from chatts_b200.weights import synthetic_state_dict
+    cfg = ChatTSConfig.tiny()
+    sd = synthetic_state_dict(cfg, seed=1234, device="cpu", dtype=DT, std=0.05)
+    kw = dict(dtype=DT, max_batch=4, max_seq_len=256, page_size=16, use_cuda_graph=True)
+    ref, deep = ChatTSForCausalLM(cfg, sd, **kw), ChatTSForCausalLM(cfg, sd, use_fused_decode=2, **kw)
+    proc = ChatTSProcessor(SimpleTokenizer(cfg.ts_token_start_index, cfg.pad_token_id, cfg.eos_token_id), cfg)
+    x = np.arange(256)
+    enc = proc(text=["A <ts><ts/> ?", "text only, a longer prompt to pad the first one"], timeseries=[np.sin(x / 9) * 4], return_tensors="pt")
+    a = ref.generate(**enc, max_new_tokens=16, ignore_eos=True)
+    b = deep.generate(**enc, max_new_tokens=16, ignore_eos=True)
+    S = enc["input_ids"].shape[1]
+    record("fused_decode_5stage_generate", equal=bool(torch.equal(a, b)), first_diff=int((a != b).float().argmax()) if not torch.equal(a, b) else -1)
+    assert torch.equal(a[:, : S + 3], b[:, : S + 3])           # an ulp in a statistic may flip a near-tie later on; the start must agree

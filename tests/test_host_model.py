@@ -193,7 +193,11 @@ def test_fused_decode_gemms_generate_the_same_tokens(cabi_double, split, qwen3):
     cfg, sd, model, proc = _build(cabi_double, split, qwen3)
     enc = proc(text=PROMPTS, timeseries=list(_series()), padding=True, return_tensors="pt")
     ref = model.generate(**enc, max_new_tokens=9, ignore_eos=True)
-    cfg2, sd2, fused, _ = _build(cabi_double, split, qwen3, use_fused_decode=True)
-    out = fused.generate(**enc, max_new_tokens=9, ignore_eos=True)
-    assert torch.equal(out, ref) and len(fused.pool.free) == fused.pool.num_pages
-    assert torch.equal(fused.kv, model.kv)
+    for level in (1, 2):                       # 7 stages (plain RMSNorm launches kept) and 5 stages (RMSNorm inside the projections)
+        cfg2, sd2, fused, _ = _build(cabi_double, split, qwen3, use_fused_decode=level)
+        out = fused.generate(**enc, max_new_tokens=9, ignore_eos=True)
+        assert torch.equal(out, ref) and len(fused.pool.free) == fused.pool.num_pages, level
+        if level == 1:
+            assert torch.equal(fused.kv, model.kv)
+        else:                                  # the row statistic is summed tile by tile: at most an ulp of bf16 in the cache
+            assert float((fused.kv.float() - model.kv.float()).abs().max()) <= 2 ** -6 * float(model.kv.float().abs().max())
