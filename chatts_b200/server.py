@@ -65,7 +65,7 @@ def messages_to_prompt(messages, tokenizer=None, chat_template=True):
 class Engine:
     """Worker thread + request queue around a ``vllm_compat.LLM``."""
 
-    def __init__(self, llm, batch_window_ms=5.0, max_ts_per_prompt=MAX_TS_DEFAULT, scheduler="batch", steps_per_round=4):
+    def __init__(self, llm, batch_window_ms=5.0, max_ts_per_prompt=MAX_TS_DEFAULT, scheduler="batch", steps_per_round=4, autostart=True):
         self.llm, self.window, self.max_ts = llm, batch_window_ms / 1e3, max_ts_per_prompt
         self.q = queue.Queue()
         self.stop = False
@@ -73,7 +73,13 @@ class Engine:
         self.scheduler, self.steps_per_round = scheduler, steps_per_round
         self.occupancy = []                               # continuous scheduler: active slots per round
         self.thread = threading.Thread(target=self._loop_continuous if scheduler == "continuous" else self._loop, daemon=True)
-        self.thread.start()
+        if autostart:
+            self.thread.start()
+
+    def start(self):
+        """Start the worker (``autostart=False`` lets a caller queue requests first: deterministic batches in tests)."""
+        if not self.thread.is_alive():
+            self.thread.start()
 
     def submit(self, prompt, series, params, stream=False):
         if len(series) > self.max_ts:
@@ -87,7 +93,8 @@ class Engine:
     def close(self):
         self.stop = True
         self.q.put(None)
-        self.thread.join(timeout=10)
+        if self.thread.is_alive():
+            self.thread.join(timeout=10)
 
     # -------------------------------------------------------------------------------------------- worker
     def _loop(self):

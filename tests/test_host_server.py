@@ -53,7 +53,7 @@ def test_completions_body_batching_and_errors(served):
     [t.start() for t in ths]
     [t.join() for t in ths]
     assert all(r["usage"]["completion_tokens"] == 5 for r in res)
-    assert max(app.state.engine.batches[n0:]) >= 2 and sum(app.state.engine.batches[n0:]) == 4
+    assert sum(app.state.engine.batches[n0:]) == 4              # (how they were grouped depends on arrival times: see the engine test)
     assert res[0]["choices"][0]["text"] == ref["choices"][0]["text"] == res[2]["choices"][0]["text"]    # greedy: batch-invariant here
     # the reference's input errors -> 400
     assert http.post("/v1/completions", json={"prompt": "two <ts><ts/> <ts><ts/>", "multi_modal_data": {"timeseries": [a.tolist()]}}).status_code == 400
@@ -113,7 +113,7 @@ def test_continuous_scheduler_serves_concurrent_requests(cabi_double):
         [t.start() for t in ths]
         [t.join() for t in ths]
         assert [r["choices"][0]["text"] for r in res] == want
-        assert max(app.state.engine.occupancy) <= model.max_batch and max(app.state.engine.occupancy) >= 2
+        assert max(app.state.engine.occupancy) <= model.max_batch
         pieces = []
         with http.stream("POST", "/v1/completions", json={**bodies[3], "stream": True}) as r:
             for line in r.iter_lines():
@@ -123,3 +123,23 @@ def test_continuous_scheduler_serves_concurrent_requests(cabi_double):
         assert http.post("/v1/completions", json={"prompt": "x", "temperature": 0.7}).status_code == 400
     app.state.engine.close()
     assert len(model.pool.free) == model.pool.num_pages
+
+
+@pytest.mark.parametrize("scheduler", ["batch", "continuous"])
+def test_engine_groups_queued_requests_deterministically(cabi_double, scheduler):
+    """Requests queued before the worker starts: the batch scheduler decodes equal-parameter requests as ONE batch (and a
+    request with other parameters on its own), the continuous scheduler fills its slots -- independent of thread timing."""
+    from chatts_b200.server import Engine
+    from chatts_b200.vllm_compat import LLM
+    cfg, sd, model, proc = _build(cabi_double)
+    eng = Engine(LLM(model=model), batch_window_ms=50.0, scheduler=scheduler, steps_per_round=2, autostart=False)
+    p5 = {"max_tokens": 5, "temperature": 0.0, "top_p": 1.0, "top_k": 0, "n": 1, "ignore_eos": True}
+    jobs = [eng.submit(f"prompt {i}", [], p5) for i in range(3)] + [eng.submit("other", [], {**p5, "max_tokens": 3})]
+    eng.start()
+    outs = [j.future.result(timeout=120) for j in jobs]
+    assert [len(o.outputs[0].token_ids) for o in outs] == [5, 5, 5, 3]
+    if scheduler == "batch":
+        assert eng.batches == [3, 1]
+    else:
+        assert max(eng.occupancy) == 4
+    eng.close()
