@@ -24,7 +24,7 @@ ab CTS_ATTN_BWD_TC5=1
 ab CTS_WGRAD_MMA=1
 ab CTS_ATTN_BWD_TC5=1 CTS_WGRAD_MMA=1
 echo "## decode: native step executor / sampling kernel (tokens/s, b=32)"
-for v in "CTS_BASE=1" "CTS_NATIVE_STEP=1" "CTS_DECODE_FUSED=1"; do
+for v in "CTS_BASE=1" "CTS_NATIVE_STEP=1" "CTS_DECODE_FUSED=1" "CTS_DECODE_FUSED=2"; do
   echo "## $v"; env $v timeout 400 python bench.py --steps 32 --warmup 3 --no-cpu-baseline --sweep-only 2>>gpurun_out/ab.err | python -c "
 import sys,json
 for l in sys.stdin:
