@@ -10,8 +10,9 @@
 //                            diagonal):  S^T = K Q^T, dP^T = V dO^T -> softmax warps (thread = key row) form P^T and dS^T ->
 //                            dV += P^T dO (cols 128..255), dK += dS^T Q (cols 256..383): summed over the GQA group in TMEM,
 //                            no atomics, fixed order.
-// Round-1 pipeline: one tile in flight (TMA of tile j+1 overlaps the MMAs of tile j through the full/empty barriers; the
-// tensor core idles while the softmax warps work).  Every mbarrier wait is bounded (common.cuh: a protocol bug traps, it
+// Round-1 pipeline: the streamed operand tiles (K/V in the dQ kernel, Q/dO in the dK/dV kernel) are double-buffered, so the TMA
+// of tile j+1 is in flight while tile j is consumed; S / dP and the P-like tiles are single-buffered (the tensor core idles
+// while the softmax warps work -- the next tuning step).  Every mbarrier wait is bounded (common.cuh: a protocol bug traps, it
 // cannot hang the box).  OPT-IN (CTS_ATTN_BWD_TC5=1): written after the round-1 GPU budget was spent, not yet executed on a
 // B200; the HMMA kernels of attention_bwd.cu stay the default until this one has passed tests/test_gpu_zz_d_attn_bwd_tc5.py.
 #include <type_traits>
@@ -71,15 +72,15 @@ attn_bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                        const float* __restrict__ lse, const float* __restrict__ delta, const int* __restrict__ cu_seqlens, int nh,
                        int nkv, float scale, T* __restrict__ dq) {
   extern __shared__ uint8_t dq_raw[];
-  __shared__ uint64_t qdo_bar, kv_full, kv_empty, s_full, s_free, ds_full, ds_free, o_done;
+  __shared__ uint64_t qdo_bar, kv_full[2], kv_empty[2], s_full, s_free, ds_full, ds_free, o_done;
   __shared__ uint32_t tmem_slot;
   const uint32_t raw = smem_u32(dq_raw);
   uint8_t* smem = dq_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* q_s = smem;                       // 32 KiB
   uint8_t* do_s = q_s + 2 * kBigHalf;        // 32 KiB
   uint8_t* ds_s = do_s + 2 * kBigHalf;       // 16 KiB
-  uint8_t* k_s = ds_s + kPTile;              // 16 KiB
-  uint8_t* v_s = k_s + 2 * kSmallHalf;       // 16 KiB
+  uint8_t* kv_s = ds_s + kPTile;             // 2 stages x (K 16 KiB | V 16 KiB): tile j+1 lands while tile j is being consumed
+  constexpr int kKvStage = 4 * kSmallHalf;
 
   const int b = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,7 +88,7 @@ attn_bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(&qdo_bar, 1);
-    mbar_init(&kv_full, 1); mbar_init(&kv_empty, 1);
+    for (int st = 0; st < 2; ++st) { mbar_init(&kv_full[st], 1); mbar_init(&kv_empty[st], 1); }
     mbar_init(&s_full, 1); mbar_init(&s_free, 4);
     mbar_init(&ds_full, 4); mbar_init(&ds_free, 1);
     mbar_init(&o_done, 1);
@@ -117,12 +118,15 @@ attn_bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       tma_load_2d(do_s + kBigHalf, &tm_do, &qdo_bar, head * kHD + 64, seq0 + q0, CTS_L2_EVICT_FIRST);
       for (int j = 0; j < nt; ++j) {
         const int row = seq0 + j * kSmallRows;
-        mbar_wait(&kv_empty, ((uint32_t)j & 1u) ^ 1u);
-        mbar_expect_tx(&kv_full, (uint32_t)(4 * kSmallHalf));
-        tma_load_2d(k_s, &tm_k, &kv_full, kvh * kHD, row, CTS_L2_EVICT_LAST);
-        tma_load_2d(k_s + kSmallHalf, &tm_k, &kv_full, kvh * kHD + 64, row, CTS_L2_EVICT_LAST);
-        tma_load_2d(v_s, &tm_v, &kv_full, kvh * kHD, row, CTS_L2_EVICT_LAST);
-        tma_load_2d(v_s + kSmallHalf, &tm_v, &kv_full, kvh * kHD + 64, row, CTS_L2_EVICT_LAST);
+        const int st = j & 1;
+        uint8_t* k_s = kv_s + st * kKvStage;
+        uint8_t* v_s = k_s + 2 * kSmallHalf;
+        mbar_wait(&kv_empty[st], (((uint32_t)j >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&kv_full[st], (uint32_t)kKvStage);
+        tma_load_2d(k_s, &tm_k, &kv_full[st], kvh * kHD, row, CTS_L2_EVICT_LAST);
+        tma_load_2d(k_s + kSmallHalf, &tm_k, &kv_full[st], kvh * kHD + 64, row, CTS_L2_EVICT_LAST);
+        tma_load_2d(v_s, &tm_v, &kv_full[st], kvh * kHD, row, CTS_L2_EVICT_LAST);
+        tma_load_2d(v_s + kSmallHalf, &tm_v, &kv_full[st], kvh * kHD + 64, row, CTS_L2_EVICT_LAST);
       }
     }
   } else if (warp == 1) {
@@ -131,11 +135,12 @@ attn_bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
       const uint32_t idesc_s = umma_idesc_f16(kBf16 ? 1 : 0, kSmallRows, 128);
       const uint32_t idesc_o = umma_idesc_f16(kBf16 ? 1 : 0, 128, 128) | (1u << 16);      // B is MN-major
-      const uint32_t q_addr = smem_u32(q_s), do_addr = smem_u32(do_s), ds_addr = smem_u32(ds_s), k_addr = smem_u32(k_s),
-                     v_addr = smem_u32(v_s);
+      const uint32_t q_addr = smem_u32(q_s), do_addr = smem_u32(do_s), ds_addr = smem_u32(ds_s);
       mbar_wait(&qdo_bar, 0);
       for (int j = 0; j < nt; ++j) {
-        mbar_wait(&kv_full, (uint32_t)j & 1u);
+        const int st = j & 1;
+        const uint32_t k_addr = smem_u32(kv_s + st * kKvStage), v_addr = k_addr + 2 * kSmallHalf;
+        mbar_wait(&kv_full[st], ((uint32_t)j >> 1) & 1u);
         if (j > 0) mbar_wait(&s_free, (uint32_t)(j - 1) & 1u);      // softmax warps finished reading S / dP of tile j-1
         tc_fence_after();
         mma_rows_x_rowsT(tmem_base, q_addr, k_addr, idesc_s);        // S  = Q  K^T
@@ -144,7 +149,7 @@ attn_bwd_dq_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         mbar_wait(&ds_full, (uint32_t)j & 1u);                       // dS(j) is in shared memory
         tc_fence_after();
         mma_p_x_tile(tmem_base + 128, ds_addr, k_addr, idesc_o, j > 0);   // dQ += dS K
-        umma_commit(&kv_empty);                                      // K, V may be reloaded
+        umma_commit(&kv_empty[st]);                                  // this K/V stage may be reloaded
         umma_commit(&ds_free);                                       // dS tile may be rewritten
       }
       umma_commit(&o_done);
@@ -220,16 +225,16 @@ attn_bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                         const float* __restrict__ lse, const float* __restrict__ delta, const int* __restrict__ cu_seqlens, int nh,
                         int nkv, float scale, T* __restrict__ dk, T* __restrict__ dv) {
   extern __shared__ uint8_t dkv_raw[];
-  __shared__ uint64_t kv_bar, qd_full, qd_empty, s_full, s_free, pd_full, pd_free, done_bar;
+  __shared__ uint64_t kv_bar, qd_full[2], qd_empty[2], s_full, s_free, pd_full, pd_free, done_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ float stat_s[2][2][kSmallRows];          // [iteration parity][lse * log2e | delta][query of the tile]
   const uint32_t raw = smem_u32(dkv_raw);
   uint8_t* smem = dkv_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* k_s = smem;                        // 32 KiB
   uint8_t* v_s = k_s + 2 * kBigHalf;          // 32 KiB
-  uint8_t* q_s = v_s + 2 * kBigHalf;          // 16 KiB
-  uint8_t* do_s = q_s + 2 * kSmallHalf;       // 16 KiB
-  uint8_t* pt_s = do_s + 2 * kSmallHalf;      // 16 KiB  P^T
+  uint8_t* qd_s = v_s + 2 * kBigHalf;         // 2 stages x (Q 16 KiB | dO 16 KiB)
+  constexpr int kQdStage = 4 * kSmallHalf;
+  uint8_t* pt_s = qd_s + 2 * kQdStage;        // 16 KiB  P^T
   uint8_t* dst_s = pt_s + kPTile;             // 16 KiB  dS^T
 
   const int b = blockIdx.z, kvh = blockIdx.y, kt = blockIdx.x;
@@ -238,7 +243,7 @@ attn_bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(&kv_bar, 1);
-    mbar_init(&qd_full, 1); mbar_init(&qd_empty, 1);
+    for (int st = 0; st < 2; ++st) { mbar_init(&qd_full[st], 1); mbar_init(&qd_empty[st], 1); }
     mbar_init(&s_full, 1); mbar_init(&s_free, 4);
     mbar_init(&pd_full, 4); mbar_init(&pd_free, 1);
     mbar_init(&done_bar, 1);
@@ -271,12 +276,15 @@ attn_bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       for (int n = 0; n < n_iter; ++n) {
         const int head = kvh * G + n / nI;
         const int row = seq0 + (it0 + n % nI) * kSmallRows;
-        mbar_wait(&qd_empty, ((uint32_t)n & 1u) ^ 1u);
-        mbar_expect_tx(&qd_full, (uint32_t)(4 * kSmallHalf));
-        tma_load_2d(q_s, &tm_q, &qd_full, head * kHD, row, CTS_L2_EVICT_LAST);
-        tma_load_2d(q_s + kSmallHalf, &tm_q, &qd_full, head * kHD + 64, row, CTS_L2_EVICT_LAST);
-        tma_load_2d(do_s, &tm_do, &qd_full, head * kHD, row, CTS_L2_EVICT_LAST);
-        tma_load_2d(do_s + kSmallHalf, &tm_do, &qd_full, head * kHD + 64, row, CTS_L2_EVICT_LAST);
+        const int st = n & 1;
+        uint8_t* q_s = qd_s + st * kQdStage;
+        uint8_t* do_s = q_s + 2 * kSmallHalf;
+        mbar_wait(&qd_empty[st], (((uint32_t)n >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(&qd_full[st], (uint32_t)kQdStage);
+        tma_load_2d(q_s, &tm_q, &qd_full[st], head * kHD, row, CTS_L2_EVICT_LAST);
+        tma_load_2d(q_s + kSmallHalf, &tm_q, &qd_full[st], head * kHD + 64, row, CTS_L2_EVICT_LAST);
+        tma_load_2d(do_s, &tm_do, &qd_full[st], head * kHD, row, CTS_L2_EVICT_LAST);
+        tma_load_2d(do_s + kSmallHalf, &tm_do, &qd_full[st], head * kHD + 64, row, CTS_L2_EVICT_LAST);
       }
     }
   } else if (warp == 1) {
@@ -285,11 +293,12 @@ attn_bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
       const uint32_t idesc_s = umma_idesc_f16(kBf16 ? 1 : 0, kSmallRows, 128);
       const uint32_t idesc_o = umma_idesc_f16(kBf16 ? 1 : 0, 128, 128) | (1u << 16);      // B is MN-major
-      const uint32_t k_addr = smem_u32(k_s), v_addr = smem_u32(v_s), q_addr = smem_u32(q_s), do_addr = smem_u32(do_s),
-                     pt_addr = smem_u32(pt_s), dst_addr = smem_u32(dst_s);
+      const uint32_t k_addr = smem_u32(k_s), v_addr = smem_u32(v_s), pt_addr = smem_u32(pt_s), dst_addr = smem_u32(dst_s);
       mbar_wait(&kv_bar, 0);
       for (int n = 0; n < n_iter; ++n) {
-        mbar_wait(&qd_full, (uint32_t)n & 1u);
+        const int st = n & 1;
+        const uint32_t q_addr = smem_u32(qd_s + st * kQdStage), do_addr = q_addr + 2 * kSmallHalf;
+        mbar_wait(&qd_full[st], ((uint32_t)n >> 1) & 1u);
         if (n > 0) mbar_wait(&s_free, (uint32_t)(n - 1) & 1u);
         tc_fence_after();
         mma_rows_x_rowsT(tmem_base, k_addr, q_addr, idesc_s);         // S^T  = K Q^T
@@ -299,7 +308,7 @@ attn_bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tc_fence_after();
         mma_p_x_tile(tmem_base + 128, pt_addr, do_addr, idesc_o, n > 0);    // dV += P^T  dO
         mma_p_x_tile(tmem_base + 256, dst_addr, q_addr, idesc_o, n > 0);    // dK += dS^T Q
-        umma_commit(&qd_empty);                                       // Q, dO may be reloaded
+        umma_commit(&qd_empty[st]);                                   // this Q/dO stage may be reloaded
         umma_commit(&pd_free);                                        // P^T, dS^T may be rewritten
       }
       umma_commit(&done_bar);
@@ -386,8 +395,8 @@ attn_bwd_dkv_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-constexpr int kDqSmem = 4 * kBigHalf + kPTile + 4 * kSmallHalf;          // Q 32 + dO 32 + dS 16 + K 16 + V 16 = 112 KiB
-constexpr int kDkvSmem = 4 * kBigHalf + 4 * kSmallHalf + 2 * kPTile;     // K 32 + V 32 + Q 16 + dO 16 + P^T 16 + dS^T 16 = 128 KiB
+constexpr int kDqSmem = 4 * kBigHalf + kPTile + 8 * kSmallHalf;          // Q 32 + dO 32 + dS 16 + 2 x (K 16 + V 16) = 144 KiB
+constexpr int kDkvSmem = 4 * kBigHalf + 8 * kSmallHalf + 2 * kPTile;     // K 32 + V 32 + 2 x (Q 16 + dO 16) + P^T 16 + dS^T 16 = 160 KiB
 
 }  // namespace
 

@@ -118,33 +118,36 @@ def wait(bar, parity):
 # ====================================================================================================================== dQ kernel
 def sim_dq(nt, seed):
     s = Sim(seed)
-    qdo, kv_full, kv_empty = MBar(1), MBar(1), MBar(1)
+    qdo, kv_full, kv_empty = MBar(1), [MBar(1), MBar(1)], [MBar(1), MBar(1)]            # K/V ring of two stages
     s_full, s_free, ds_full, ds_free, o_done = MBar(1), MBar(4), MBar(4), MBar(1), MBar(1)
-    s.mem.update({"Q": None, "dO": None, "K": None, "V": None, "dS": None, "S": None, "dP": None, "dQ": ("dQ", -1)})
+    s.mem.update({"Q": None, "dO": None, "K0": None, "V0": None, "K1": None, "V1": None, "dS": None, "S": None, "dP": None,
+                  "dQ": ("dQ", -1)})
 
     def producer():
         qdo.expect_tx(4)
         for b in ("Q", "Q", "dO", "dO"):
             s.tma(b, b, qdo, 1)
         for j in range(nt):
-            yield wait(kv_empty, (j & 1) ^ 1)
-            kv_full.expect_tx(4)
-            s.tma("K", ("K", j), kv_full, 2)
-            s.tma("V", ("V", j), kv_full, 2)
+            st = j & 1
+            yield wait(kv_empty[st], ((j >> 1) & 1) ^ 1)
+            kv_full[st].expect_tx(4)
+            s.tma(f"K{st}", ("K", j), kv_full[st], 2)
+            s.tma(f"V{st}", ("V", j), kv_full[st], 2)
             yield None
 
     def mma():
         yield wait(qdo, 0)
         for j in range(nt):
-            yield wait(kv_full, j & 1)
+            st = j & 1
+            yield wait(kv_full[st], (j >> 1) & 1)
             if j > 0:
                 yield wait(s_free, (j - 1) & 1)
-            s.mma([("Q", "Q"), ("K", ("K", j))], ("S", ("S", j)))
-            s.mma([("dO", "dO"), ("V", ("V", j))], ("dP", ("dP", j)))
+            s.mma([("Q", "Q"), (f"K{st}", ("K", j))], ("S", ("S", j)))
+            s.mma([("dO", "dO"), (f"V{st}", ("V", j))], ("dP", ("dP", j)))
             s.commit(s_full)
             yield wait(ds_full, j & 1)
-            s.mma([("dS", ("dS", j)), ("K", ("K", j))], ("dQ", ("dQ", j)), chain=[("dQ", ("dQ", j - 1))])
-            s.commit(kv_empty)
+            s.mma([("dS", ("dS", j)), (f"K{st}", ("K", j))], ("dQ", ("dQ", j)), chain=[("dQ", ("dQ", j - 1))])
+            s.commit(kv_empty[st])
             s.commit(ds_free)
             yield None
         s.commit(o_done)
@@ -175,9 +178,9 @@ def sim_dq(nt, seed):
 # ====================================================================================================================== dK/dV kernel
 def sim_dkv(n_iter, seed):
     s = Sim(seed)
-    kv_bar, qd_full, qd_empty = MBar(1), MBar(1), MBar(1)
+    kv_bar, qd_full, qd_empty = MBar(1), [MBar(1), MBar(1)], [MBar(1), MBar(1)]          # Q/dO ring of two stages
     s_full, s_free, pd_full, pd_free, done = MBar(1), MBar(4), MBar(4), MBar(1), MBar(1)
-    s.mem.update({"K": None, "V": None, "Q": None, "dO": None, "PT": None, "dST": None, "ST": None, "dPT": None,
+    s.mem.update({"K": None, "V": None, "Q0": None, "dO0": None, "Q1": None, "dO1": None, "PT": None, "dST": None, "ST": None, "dPT": None,
                   "dV": ("dV", -1), "dK": ("dK", -1)})
 
     def producer():
@@ -185,25 +188,27 @@ def sim_dkv(n_iter, seed):
         s.tma("K", "K", kv_bar, 1)
         s.tma("V", "V", kv_bar, 1)
         for n in range(n_iter):
-            yield wait(qd_empty, (n & 1) ^ 1)
-            qd_full.expect_tx(2)
-            s.tma("Q", ("Q", n), qd_full, 1)
-            s.tma("dO", ("dO", n), qd_full, 1)
+            st = n & 1
+            yield wait(qd_empty[st], ((n >> 1) & 1) ^ 1)
+            qd_full[st].expect_tx(2)
+            s.tma(f"Q{st}", ("Q", n), qd_full[st], 1)
+            s.tma(f"dO{st}", ("dO", n), qd_full[st], 1)
             yield None
 
     def mma():
         yield wait(kv_bar, 0)
         for n in range(n_iter):
-            yield wait(qd_full, n & 1)
+            st = n & 1
+            yield wait(qd_full[st], (n >> 1) & 1)
             if n > 0:
                 yield wait(s_free, (n - 1) & 1)
-            s.mma([("K", "K"), ("Q", ("Q", n))], ("ST", ("ST", n)))
-            s.mma([("V", "V"), ("dO", ("dO", n))], ("dPT", ("dPT", n)))
+            s.mma([("K", "K"), (f"Q{st}", ("Q", n))], ("ST", ("ST", n)))
+            s.mma([("V", "V"), (f"dO{st}", ("dO", n))], ("dPT", ("dPT", n)))
             s.commit(s_full)
             yield wait(pd_full, n & 1)
-            s.mma([("PT", ("PT", n)), ("dO", ("dO", n))], ("dV", ("dV", n)), chain=[("dV", ("dV", n - 1))])
-            s.mma([("dST", ("dST", n)), ("Q", ("Q", n))], ("dK", ("dK", n)), chain=[("dK", ("dK", n - 1))])
-            s.commit(qd_empty)
+            s.mma([("PT", ("PT", n)), (f"dO{st}", ("dO", n))], ("dV", ("dV", n)), chain=[("dV", ("dV", n - 1))])
+            s.mma([("dST", ("dST", n)), (f"Q{st}", ("Q", n))], ("dK", ("dK", n)), chain=[("dK", ("dK", n - 1))])
+            s.commit(qd_empty[st])
             s.commit(pd_free)
             yield None
         s.commit(done)
