@@ -154,14 +154,104 @@ def run(args):
         dist.destroy_process_group()
 
 
+def run_reference(args):
+    """CPU arm for config 5: what the external recipe executes on a host -- stock transformers Qwen3ForCausalLM at the ChatTS-8B
+    layer shape with peft-style LoRA modules around its seven projections (peft itself is not installed: the same
+    `base(x) + B(A(x)) * alpha/r` wrapper the oracle tests use), forward + backward + AdamW on ONE synthetic sample of 448
+    positions.  Bounded sample: `layers_sample` decoder layers are instantiated and timed, the per-layer time is scaled to 36
+    layers (embedding / lm_head / loss timed with 0 layers and added once)."""
+    import torch.nn as nn
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    S = N_SERIES * (PREFIX_IDS + 2 + SERIES_LEN // 16) + PROMPT_IDS + ANSWER_IDS
+    full_layers, layers_sample = 36, 2
+
+    class LoRALinear(nn.Module):
+        def __init__(self, base, r=16, alpha=32):
+            super().__init__()
+            self.base, self.scaling = base, alpha / r
+            self.lora_A = nn.Parameter(torch.randn(r, base.in_features, dtype=base.weight.dtype) * 0.01)
+            self.lora_B = nn.Parameter(torch.zeros(base.out_features, r, dtype=base.weight.dtype))
+
+        def forward(self, x):
+            return self.base(x) + nn.functional.linear(nn.functional.linear(x, self.lora_A), self.lora_B) * self.scaling
+
+    def step_time(nl):
+        cfg = Qwen3Config(hidden_size=4096, intermediate_size=12288, num_hidden_layers=nl, num_attention_heads=32, num_key_value_heads=8,
+                          head_dim=128, vocab_size=151936, rms_norm_eps=1e-6, rope_theta=1e6, max_position_embeddings=40960,
+                          tie_word_embeddings=False, attention_bias=False)
+        with torch.device("meta"):
+            m = Qwen3ForCausalLM(cfg)
+        m = m.to_empty(device="cpu").to(torch.bfloat16)
+        g = torch.Generator().manual_seed(0)
+        with torch.no_grad():
+            for p_ in m.parameters():
+                if p_.dim() == 1:
+                    p_.fill_(1.0)
+                else:
+                    blk = (torch.randn(4096, generator=g) * 0.02).to(torch.bfloat16)
+                    p_.view(-1)[: (p_.numel() // 4096) * 4096].view(-1, 4096).copy_(blk)
+        for mod in m.modules():
+            if hasattr(mod, "inv_freq") and hasattr(mod, "compute_default_rope_parameters"):
+                inv, _ = mod.compute_default_rope_parameters(cfg, "cpu")
+                mod.inv_freq = inv
+                mod.original_inv_freq = inv.clone()
+        for p_ in m.parameters():
+            p_.requires_grad_(False)
+        train = []
+        for layer in m.model.layers:
+            for mod, names in ((layer.self_attn, ("q_proj", "k_proj", "v_proj", "o_proj")), (layer.mlp, ("gate_proj", "up_proj", "down_proj"))):
+                for nm in names:
+                    w = LoRALinear(getattr(mod, nm))
+                    setattr(mod, nm, w)
+                    train += [w.lora_A, w.lora_B]
+        opt = torch.optim.AdamW(train, lr=1e-4) if train else None
+        ids = torch.randint(0, 150000, (1, S))
+        labels = ids.clone()
+        labels[:, : S - ANSWER_IDS] = -100
+        ts = []
+        for it in range(3):
+            t0 = time.perf_counter()
+            out = m(input_ids=ids, labels=labels)
+            if train:
+                out.loss.backward()
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+            ts.append(time.perf_counter() - t0)
+        del m
+        return float(np.median(ts[1:]))
+
+    t_s, t_0 = step_time(layers_sample), step_time(0)
+    per_layer = max(t_s - t_0, 0.0) / layers_sample
+    step = t_0 + per_layer * full_layers
+    v = S / step
+    base = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "reference",
+            "sample": (f"stock transformers Qwen3ForCausalLM + LoRA wrappers (r=16 on q,k,v,o,gate,up,down), bf16, {threads} threads, ChatTS-8B layer "
+                       f"shape, ONE sample of {S} positions ({ANSWER_IDS} labels): forward+backward+AdamW; timed {layers_sample} of 36 decoder layers "
+                       f"(median of 2 steps), per-layer time scaled x36 (head {t_0 * 1e3:.0f} ms, layer {per_layer * 1e3:.0f} ms)")}
+    line = {"impl": "reference", "metric": "lora_finetune_positions_per_s", "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": {"workload": f"ChatTS-8B LoRA r=16 fine-tune step, 1 sample x {S} merged positions (CPU arm)"},
+            "cpu_baseline": base, "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--samples", type=int, default=16, help="samples per GPU and step (448 merged positions each)")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer decoder layers (INVALID as a benchmark)")
-    run(ap.parse_args())
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run(args)
 
 
 if __name__ == "__main__":
