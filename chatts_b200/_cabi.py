@@ -29,6 +29,7 @@ SYMBOLS = [
     "cts_ce_loss_grad", "cts_gather_rows", "cts_lora_wgrad", "cts_adamw", "cts_grad_norm_ws_floats", "cts_grad_norm_clip",
     "cts_lora_pack",
     "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step", "cts_ts_encode", "cts_gemm_decode_fused",
+    "cts_peer_ll_region_bytes", "cts_peer_allreduce_ll",
 ]
 FUSED_RESIDUAL, FUSED_SWIGLU, FUSED_QKV_ROPE = 0, 1, 2
 PACK_DESC_LONGS = 12
@@ -132,6 +133,10 @@ def load_library():
     lib.cts_ipc_close.argtypes = [vp, vp]
     lib.cts_ipc_free.argtypes = [vp, vp]
     lib.cts_peer_allreduce_residual_rmsnorm.argtypes = [vp, vp, i, vp, vp, vp, i, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
+    lib.cts_peer_ll_region_bytes.argtypes = [i, i, ll]
+    lib.cts_peer_ll_region_bytes.restype = ll
+    lib.cts_peer_allreduce_ll.argtypes = [vp, vp, i, vp, ll, vp, i, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
+    lib.cts_peer_allreduce_ll.restype = i
     lib.cts_decode_chain.argtypes = [vp, C.POINTER(ChainArgs), vp]
     lib.cts_decode_chain.restype = i
     lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
@@ -483,6 +488,15 @@ class Context:
                                                                rank, world, max_tokens, _p(resid_in), _p(resid_out), _p(norm_w),
                                                                float(eps), _p(norm_out), t, resid_in.shape[-1],
                                                                dtype_code(resid_in.dtype), _stream()))
+
+    def peer_ll_region_bytes(self, world, max_tokens, h):
+        return int(self.lib.cts_peer_ll_region_bytes(world, max_tokens, h))
+
+    def peer_allreduce_ll(self, local_partial, split_k, peer_regions, region_bytes, state, rank, world, max_tokens, resid_in, resid_out,
+                          norm_w, eps, norm_out, t):
+        self._chk(self.lib.cts_peer_allreduce_ll(self.h, _p(local_partial), split_k, _p(peer_regions), region_bytes, _p(state), rank, world,
+                                                 max_tokens, _p(resid_in), _p(resid_out), _p(norm_w), float(eps), _p(norm_out), t,
+                                                 resid_in.shape[-1], dtype_code(resid_in.dtype), _stream()))
 
     def decode_chain(self, *, t, hidden, inter, nh, nkv, head_dim, phases, splits, h, xn, act, ws, ssq, sync, eps, dtype,
                      norm5_has_partial=1, wo=None, wgu=None, wd=None, wqkv=None, ao=None, ln_post=None, ln_next=None, bqkv=None,

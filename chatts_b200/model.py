@@ -65,7 +65,7 @@ class _Step:
 class ChatTSForCausalLM:
     def __init__(self, config, state_dict, device="cuda", dtype=torch.bfloat16, tp_rank=0, tp_size=1,
                  max_batch=32, max_seq_len=2048, page_size=64, use_cuda_graph=True, comm=None,
-                 use_peer_allreduce=True, graph_with_tp=True, use_chain=None, use_sample_kernel=None, use_native_step=None, use_fused_decode=None):
+                 use_peer_allreduce=True, graph_with_tp=True, use_chain=None, use_sample_kernel=None, use_native_step=None, use_fused_decode=None, use_peer_ll=None):
         if not torch.cuda.is_available():
             raise _cabi.CtsError("chatts_b200 needs a B200 (sm_100a) GPU; there is no CPU fallback")
         self.config, self.dtype = config, dtype
@@ -94,6 +94,8 @@ class ChatTSForCausalLM:
         #   2: the RMSNorms too -- the residual projections emit per-tile sums of squares, the next projection builds its normalised
         #      token operand itself (5 stages; single GPU only)
         self.use_fused_decode = int(_os.environ.get("CTS_DECODE_FUSED", "0")) if use_fused_decode is None else int(use_fused_decode)
+        # tensor parallelism: low-latency two-shot all-reduce (cts_peer_allreduce_ll) instead of the one-shot push kernel
+        self.use_peer_ll = (_os.environ.get("CTS_PEER_LL", "0") == "1") if use_peer_ll is None else bool(use_peer_ll)
         # sampled decoding through cts_sample_advance (csrc/sampling.cu) instead of torch ops: off by default until the kernel has
         # run on a B200 (written after the round-1 GPU budget was spent); CTS_SAMPLE_KERNEL=1 / use_sample_kernel=True turns it on
         self.use_sample_kernel = bool(int(_os.environ.get("CTS_SAMPLE_KERNEL", "0"))) if use_sample_kernel is None else bool(use_sample_kernel)
@@ -349,6 +351,10 @@ class ChatTSForCausalLM:
         buffers alternate between o_proj (0) and down_proj (1)).  Large prefill T: NCCL all-reduce (bandwidth-bound)."""
         c = self.ctx
         c.gemm(x, w, st.ws, epilogue=EPI_PARTIAL_F32, split_k=split, t=T)
+        if self.peer is not None and T <= self.peer_tokens and self.use_peer_ll:
+            c.peer_allreduce_ll(st.ws, split, self.peer.partials[which], self.peer.part_bytes, self.peer.state, self.tp_rank, self.tp_size,
+                                self.peer.max_batch, st.h, st.h, norm_w, self.eps, st.xn, T)
+            return
         if self.peer is not None and T <= self.peer_tokens:
             c.peer_allreduce_residual_rmsnorm(st.ws, split, self.peer.partials[which], self.peer.flags[which], self.peer.state,
                                               self.tp_rank, self.tp_size, self.peer.max_batch, st.h, st.h, norm_w, self.eps,

@@ -21,7 +21,11 @@ class _Raw:
 class PeerBuffers:
     def __init__(self, ctx, rank, world, max_tokens, hidden, group=None, n_buffers=2):
         self.ctx, self.rank, self.world = ctx, rank, world
-        self.floats = world * max_tokens * hidden          # per buffer: one [max_tokens, hidden] slot per source rank
+        # per buffer: one [max_tokens, hidden] fp32 slot per source rank (one-shot kernel); never less than 4 slots, which is what the
+        # low-latency layout (cts_peer_allreduce_ll: 12 bytes per element + statistics) needs at 2 ranks
+        self.floats = max(world, 4) * max_tokens * hidden
+        ll_bytes = ctx.peer_ll_region_bytes(world, max_tokens, hidden)
+        self.floats = max(self.floats, (ll_bytes + 255) // 256 * 64)
         dev = torch.device(f"cuda:{torch.cuda.current_device()}")
         # one allocation per rank: n_buffers fp32 partial buffers, then the flag array int[world]
         self.part_bytes = self.floats * 4

@@ -219,6 +219,21 @@ int cts_peer_allreduce_residual_rmsnorm(cts_ctx* ctx, const float* local_partial
                                         const void* resid_in, void* resid_out, const void* norm_w, float eps, void* norm_out,
                                         long long t, long long h, int dtype, void* stream);
 
+/* Low-latency variant of cts_peer_allreduce_residual_rmsnorm (same result contract: h = resid + dtype(sum over ranks, rank order),
+ * norm_out = RMSNorm(h) * w, bit-identical on every rank; replaces the same RowParallelLinear -> all-reduce -> add -> RMSNorm,
+ * vllm qwen2.py:100-116,168-174): a two-shot all-reduce -- reduce-scatter of the fp32 partials to per-column-chunk owners, then
+ * an all-gather of the owners' rounded h chunks and sums of squares -- whose validity flags travel inside the data (16-byte units
+ * {d0, epoch, d1, epoch}), so there is no fence, no flag store and no round trip: two one-way NVLink hops per call and
+ * T*h*12 bytes of egress instead of (world-1)*T*h*4.  world in {2, 4, 8}; h % (4*world) == 0.
+ *   peer_regions: device array void*[world]; entry r = rank r's region of THIS buffer set (zero-initialised, >= region_bytes,
+ *                 cts_peer_ll_region_bytes(world, max_tokens, h)); two sets must alternate between consecutive calls
+ *   state:        local int[2], zero-initialised (epoch, arrivals)
+ */
+long long cts_peer_ll_region_bytes(int world, int max_tokens, long long h);
+int cts_peer_allreduce_ll(cts_ctx* ctx, const float* local_partial, int split_k, const void* peer_regions, long long region_bytes,
+                          int* state, int rank, int world, int max_tokens, const void* resid_in, void* resid_out, const void* norm_w,
+                          float eps, void* norm_out, long long t, long long h, int dtype, void* stream);
+
 /* vocab-parallel greedy sampling + decode-state advance over peer memory (no NCCL): local argmax of this rank's logits
  * shard [batch, vocab_shard], candidates pushed to every peer, global winner chosen identically on all ranks
  * (replaces ParallelLMHead's logits all-gather + sampler, chatts_vllm.py:607-610, for greedy decoding).

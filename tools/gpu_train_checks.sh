@@ -8,7 +8,7 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_metrics.jsonl
 STATUS=0
-for f in train_kernels zz_a_native_step zz_b_sampling zz_d_attn_bwd_tc5 zz_e_fused_decode; do          # each file in its own process: a trapped kernel cannot take the rest down
+for f in train_kernels zz_a_native_step zz_b_sampling zz_d_attn_bwd_tc5 zz_e_fused_decode zz_f_peer_ll; do          # each file in its own process: a trapped kernel cannot take the rest down
   echo "=== tests/test_gpu_$f.py (--runxfail)"
   timeout 300 python -m pytest tests/test_gpu_$f.py -q -m gpu --runxfail --no-header -p no:cacheprovider -rfE > gpurun_out/test_$f.log 2>&1
   echo "rc=$?"; tail -n 12 gpurun_out/test_$f.log
