@@ -2,7 +2,6 @@
 
 torch.distributed carries only the 64-byte IPC handles (and NCCL the large prefill all-reduces); the decode
 all-reduce itself is cts_peer_allreduce_residual_rmsnorm over the mapped peer pointers."""
-import ctypes as C
 
 import torch
 import torch.distributed as dist

@@ -8,7 +8,6 @@ Names follow the checkpoint / the reference's mapper (chatts/vllm/chatts_vllm.py
   ts_encoder.mlp.{0,2,..}.{weight,bias}, ts_encoder.position_embedding.weight.
 """
 import glob
-import json
 import os
 
 import torch

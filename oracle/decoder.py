@@ -11,7 +11,6 @@ pinned against the installed transformers Qwen2ForCausalLM in tests/test_oracle_
 Weights: plain dict with HF names (``model.layers.{i}.self_attn.q_proj.weight`` ...).
 One sample at a time (no padding): x [T, H].
 """
-import math
 
 import torch
 import torch.nn.functional as F

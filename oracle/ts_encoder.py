@@ -9,7 +9,6 @@ Weights are passed as a plain dict with the checkpoint's names:
   ``mlp.{2*i}.weight`` [out,in], ``mlp.{2*i}.bias`` [out]   (nn.Sequential of Linear,GELU,...  :83-91)
   ``position_embedding.weight`` [max_sequence_length+1, embedding_dim]                     (:75)
 """
-import math
 
 import torch
 
