@@ -82,7 +82,8 @@ class FusedGemmArgs(C.Structure):
                                            "q_norm", "k_norm")] + [("eps", C.c_float)] +
                 [(k, C.c_int) for k in ("nh", "nkv", "head_dim", "page_size")] +
                 [("norm_h", C.c_void_p), ("norm_w", C.c_void_p), ("ssq_in", C.c_void_p), ("ssq_tiles", C.c_int), ("norm_eps", C.c_float),
-                 ("ssq_out", C.c_void_p)])
+                 ("ssq_out", C.c_void_p), ("peer_regions", C.c_void_p), ("peer_state", C.c_void_p)] +
+                [(k, C.c_int) for k in ("peer_rank", "peer_world", "peer_max_tokens", "peer_reserved")] + [("peer_region_bytes", C.c_longlong)])
 
 
 class TsEncodeArgs(C.Structure):
@@ -318,10 +319,11 @@ class Context:
 
     def gemm_decode_fused(self, x, w, mode, split_k, t, *, bias=None, h=None, act=None, positions=None, cos=None, sin=None, slot_map=None,
                           q_out=None, k_cache=None, v_cache=None, q_norm=None, k_norm=None, eps=1e-6, nh=0, nkv=0, head_dim=0,
-                          page_size=0, norm_h=None, norm_w=None, ssq_in=None, norm_eps=1e-6, ssq_out=None):
+                          page_size=0, norm_h=None, norm_w=None, ssq_in=None, norm_eps=1e-6, ssq_out=None, peer=None):
         """Cluster-reduced decode GEMM with the projection's tail fused in (cts_gemm_decode_fused); t <= 32, split_k <= 8.
         norm_h / norm_w / ssq_in: the token operand is RMSNorm(norm_h) produced inside the kernel (x may be None);
-        ssq_out (RESIDUAL): per-tile sums of squares of the updated h for the next projection's fused RMSNorm."""
+        ssq_out (RESIDUAL): per-tile sums of squares of the updated h for the next projection's fused RMSNorm;
+        peer (RESIDUAL, row-parallel under TP): the all-reduce over peer memory happens inside the kernel."""
         a = FusedGemmArgs()
         dp = lambda v: None if v is None else v.data_ptr()
         a.w, a.x, a.n, a.k, a.t = w.data_ptr(), dp(x), w.shape[0], w.shape[1], t
@@ -332,6 +334,9 @@ class Context:
         a.positions, a.cos_tab, a.sin_tab, a.slot_map = dp(positions), dp(cos), dp(sin), dp(slot_map)
         a.q_out, a.k_cache, a.v_cache, a.q_norm, a.k_norm = dp(q_out), dp(k_cache), dp(v_cache), dp(q_norm), dp(k_norm)
         a.eps, a.nh, a.nkv, a.head_dim, a.page_size = float(eps), nh, nkv, head_dim, page_size
+        if peer is not None:            # (regions, region_bytes, state, rank, world, max_tokens): row-parallel projection under TP
+            a.peer_regions, a.peer_region_bytes, a.peer_state = peer[0].data_ptr(), int(peer[1]), peer[2].data_ptr()
+            a.peer_rank, a.peer_world, a.peer_max_tokens = int(peer[3]), int(peer[4]), int(peer[5])
         self._chk(self.lib.cts_gemm_decode_fused(self.h, C.byref(a), _stream()))
 
     def ts_encode(self, x, num_features, patch_size, mode, pos_table, emb_dim, max_seq_len, weights, biases, total_rows, out, row_map=None):

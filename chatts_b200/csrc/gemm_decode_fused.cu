@@ -47,7 +47,37 @@ struct FusedParams {
   // NORM_IN: the token operand is RMSNorm(norm_h) * norm_w, produced by the epilogue warps straight into the swizzled B tiles
   const void* norm_h; const void* norm_w; const float* ssq_in; int ssq_tiles; float norm_eps;
   float* ssq_out;         // RESIDUAL: [t][tiles of n] sum of squares of the updated h per 128-feature tile (or NULL)
+  // RESIDUAL of a row-parallel projection under tensor parallelism: all-reduce over peer memory inside the kernel (see tp_tail)
+  uint8_t* const* peer_region; int* peer_state; int peer_rank, peer_world, peer_max_tokens;
 };
+
+// ---- wire format of the in-kernel all-reduce (shared with allreduce_ll.cu): the epoch travels inside every 8-byte word
+constexpr unsigned kPeerSpinLimit = 1u << 24;
+__device__ __forceinline__ void st_ll16(void* p, uint32_t d0, uint32_t d1, uint32_t epoch) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(d0), "r"(epoch), "r"(d1), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll16(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_ll8(void* p, uint32_t d, uint32_t epoch) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(d), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll8(const void* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ void peer_timeout(const char* what, int rank) {
+  printf("chatts_b200: fused GEMM + all-reduce timed out in %s on rank %d (block %d,%d thread %d)\n", what, rank, blockIdx.x, blockIdx.z,
+         threadIdx.x);
+  __trap();
+}
+template <typename T> __device__ __forceinline__ uint32_t pack_pair(float a, float b) {
+  T v[2] = {DT<T>::from_f(a), DT<T>::from_f(b)};
+  return *reinterpret_cast<uint32_t*>(v);
+}
 
 template <typename T, int BN, bool NORM_IN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -215,6 +245,106 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
     // the DSMEM latency is paid once per group instead of once per token; the sum of a token still runs in split order
     constexpr int kGroup = 4;
     float accs[kGroup];
+    if (mode == CTS_FUSED_RESIDUAL && p.peer_region != nullptr) {
+      // ------------------------------ tensor-parallel tail: GEMM + all-reduce + residual in this launch ------------------------------
+      // Two-shot all-reduce at (tile, token) granularity, flags inside the data (the protocol of allreduce_ll.cu, model-checked in
+      // tests/test_peer_ll_protocol.py).  The three passes run over ALL of this CTA's tokens each, so the two NVLink hops are paid
+      // once per CTA, not once per token.  h is identical on every rank before and after (the owner alone reads its residual).
+      const int W = p.peer_world, me = p.peer_rank, Tmax = p.peer_max_tokens;
+      const int hw = (int)(p.n / W);                          // columns per owner; hw % 128 == 0 (host-checked): a tile has ONE owner
+      const int owner = f0 / hw;
+      const int col = f0 - owner * hw + ft;                   // column inside the owner's chunk
+      const uint32_t epoch = (uint32_t)(p.peer_state[0] + 1); // advanced by the last CTA of every call (end of this kernel)
+      const long long ag_off = (long long)Tmax * p.n * 8, sq_off = (long long)Tmax * p.n * 12;
+      uint8_t* mine = p.peer_region[me];
+      uint8_t* own_reg = p.peer_region[owner];
+      const bool even = (ft & 1) == 0;                        // one lane per PAIR of features does the wire work
+      T* hrow = reinterpret_cast<T*>(p.h);
+      // pass A: this rank's full-K partial of (tile, token) -> the owner's region, slot [me]
+      for (int tb = split; tb < T_; tb += kGroup * S) {
+#pragma unroll
+        for (int u2 = 0; u2 < kGroup; ++u2) {
+          const int t2 = tb + u2 * S;
+          float a2 = 0.f;
+          if (t2 < T_)
+            for (int s2 = 0; s2 < S; ++s2) a2 += *cluster.map_shared_rank(&part_s[t2 * kBM + ft], s2);      // split order, DSMEM
+          accs[u2] = a2;
+        }
+#pragma unroll
+        for (int u = 0; u < kGroup; ++u) {
+          const int t = tb + u * S;
+          const float nb = __shfl_down_sync(0xffffffffu, accs[u], 1);
+          if (t < T_ && even)
+            st_ll16(own_reg + ((((long long)me * Tmax + t) * hw + col) >> 1) * 16, __float_as_uint(accs[u]), __float_as_uint(nb), epoch);
+        }
+      }
+      // pass B (owner of this tile's columns): contributions in RANK ORDER + residual, rounded; broadcast h and the tile's sum of squares
+      if (owner == me) {
+        for (int t = split; t < T_; t += S) {
+          float h0 = 0.f, h1 = 0.f;
+          if (even) {
+            uint4 uu[8];
+            unsigned spins = 0;
+            for (;;) {
+              bool ok = true;
+#pragma unroll
+              for (int r = 0; r < 8; ++r)
+                if (r < W) {
+                  uu[r] = ld_ll16(mine + ((((long long)r * Tmax + t) * hw + col) >> 1) * 16);
+                  ok = ok && uu[r].y == epoch && uu[r].w == epoch;
+                }
+              if (ok) break;
+              if (++spins > kPeerSpinLimit) peer_timeout("reduce-scatter", me);
+            }
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              if (r < W) {
+                a0 += __uint_as_float(uu[r].x);
+                a1 += __uint_as_float(uu[r].z);
+              }
+            const uint32_t rv = *reinterpret_cast<const uint32_t*>(hrow + (long long)t * p.n + f);
+            const T* rp = reinterpret_cast<const T*>(&rv);
+            h0 = rnd<T>(DT<T>::to_f(rp[0]) + rnd<T>(a0));
+            h1 = rnd<T>(DT<T>::to_f(rp[1]) + rnd<T>(a1));
+            const uint32_t wv = pack_pair<T>(h0, h1);
+            const long long unit = ((long long)me * Tmax + t) * hw + col;
+            const long long addr = ag_off + (unit >> 2) * 16 + ((unit >> 1) & 1) * 8;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              if (r < W) st_ll8(p.peer_region[r] + addr, wv, epoch);
+          }
+          if (p.ssq_out != nullptr) {                         // kernel-uniform
+            const float ss = warp_sum(h0 * h0 + h1 * h1);
+            if (lane == 0) red[ft >> 5] = ss;
+            named_bar_sync(1, 128);
+            if (ft < W)
+              st_ll8(p.peer_region[ft] + sq_off + ((long long)t * gridDim.x + blockIdx.x) * 8, __float_as_uint(red[0] + red[1] + red[2] + red[3]),
+                     epoch);
+            named_bar_sync(1, 128);                          // red is rewritten by the next token
+          }
+        }
+      }
+      // pass C (every rank, the owner included): h and the statistic from the broadcast -- the same numbers everywhere
+      for (int t = split; t < T_; t += S) {
+        if (even) {
+          const long long unit = ((long long)owner * Tmax + t) * hw + col;
+          const uint8_t* src = mine + ag_off + (unit >> 2) * 16 + ((unit >> 1) & 1) * 8;
+          uint2 v;
+          unsigned spins = 0;
+          while ((v = ld_ll8(src)).y != epoch)
+            if (++spins > kPeerSpinLimit) peer_timeout("all-gather", me);
+          *reinterpret_cast<uint32_t*>(hrow + (long long)t * p.n + f) = v.x;
+        } else if (ft == 1 && p.ssq_out != nullptr) {
+          const uint8_t* src = mine + sq_off + ((long long)t * gridDim.x + blockIdx.x) * 8;
+          uint2 v;
+          unsigned spins = 0;
+          while ((v = ld_ll8(src)).y != epoch)
+            if (++spins > kPeerSpinLimit) peer_timeout("statistics gather", me);
+          p.ssq_out[(long long)t * gridDim.x + blockIdx.x] = __uint_as_float(v.x);
+        }
+      }
+    } else
     for (int tb = split; tb < T_; tb += kGroup * S)
     for (int u = 0; u < kGroup; ++u) {
       if (u == 0) {
@@ -307,6 +437,15 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<kCols>(tmem_base);
+  if (p.peer_region != nullptr && threadIdx.x == 0) {        // the last CTA of the grid to finish publishes the next epoch
+    __threadfence();
+    const int done = atomicAdd(&p.peer_state[1], 1) + 1;
+    if (done == (int)(gridDim.x * gridDim.z)) {
+      p.peer_state[1] = 0;
+      p.peer_state[0] = p.peer_state[0] + 1;
+      __threadfence();
+    }
+  }
 }
 
 template <typename T, int BN, bool NORM_IN>
@@ -332,6 +471,8 @@ int launch_fused(cts_ctx* ctx, const cts_fused_gemm_args* a, cudaStream_t stream
   p.nh = a->nh; p.nkv = a->nkv; p.d = a->head_dim; p.page_size = a->page_size;
   p.norm_h = a->norm_h; p.norm_w = a->norm_w; p.ssq_in = a->ssq_in; p.ssq_tiles = a->ssq_tiles; p.norm_eps = a->norm_eps;
   p.ssq_out = a->ssq_out;
+  p.peer_region = (uint8_t* const*)a->peer_regions; p.peer_state = a->peer_state;
+  p.peer_rank = a->peer_rank; p.peer_world = a->peer_world; p.peer_max_tokens = a->peer_max_tokens;
   constexpr int kStage = kBM * kBK * 2 + BN * kBK * 2;
   int stages = ctx->decode_stages * 1024 / kStage;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -376,6 +517,14 @@ extern "C" int cts_gemm_decode_fused(cts_ctx* ctx, const cts_fused_gemm_args* a,
     CTS_CHECK_ARG(ctx, (a->head_dim == 64 || a->head_dim == 128) && a->nh > 0 && a->nkv > 0 &&
                            a->n == (long long)(a->nh + 2 * a->nkv) * a->head_dim, "head_dim 64 or 128, n = (nh + 2 nkv) * head_dim");
     CTS_CHECK_ARG(ctx, a->page_size > 0 || a->k_cache == nullptr, "page_size");
+  }
+  if (a->peer_regions != nullptr) {
+    CTS_CHECK_ARG(ctx, a->mode == CTS_FUSED_RESIDUAL && a->peer_state != nullptr, "the in-kernel all-reduce belongs to CTS_FUSED_RESIDUAL and needs peer_state");
+    CTS_CHECK_ARG(ctx, a->peer_world >= 2 && a->peer_world <= 8 && a->peer_rank >= 0 && a->peer_rank < a->peer_world, "peer_world in 2..8, peer_rank");
+    CTS_CHECK_ARG(ctx, a->n % (128LL * a->peer_world) == 0, "n must be a multiple of 128 * peer_world (a tile has one owner)");
+    CTS_CHECK_ARG(ctx, a->t <= a->peer_max_tokens, "t exceeds peer_max_tokens");
+    CTS_CHECK_ARG(ctx, a->peer_region_bytes >= (long long)a->peer_max_tokens * a->n * 12 + (long long)a->peer_max_tokens * (a->n / 128) * 8,
+                  "symmetric region too small");
   }
   const bool norm_in = a->norm_h != nullptr;
   if (norm_in) {

@@ -327,8 +327,9 @@ class TorchDouble:
     # ------------------------------------------------------------------ csrc/gemm_decode_fused.cu
     def gemm_decode_fused(self, x, w, mode, split_k, t, *, bias=None, h=None, act=None, positions=None, cos=None, sin=None, slot_map=None,
                           q_out=None, k_cache=None, v_cache=None, q_norm=None, k_norm=None, eps=1e-6, nh=0, nkv=0, head_dim=0, page_size=0,
-                          norm_h=None, norm_w=None, ssq_in=None, norm_eps=1e-6, ssq_out=None):
+                          norm_h=None, norm_w=None, ssq_in=None, norm_eps=1e-6, ssq_out=None, peer=None):
         """cts_gemm(CTS_EPI_PARTIAL_F32) + the matching reduce, i.e. what the cluster kernel fuses (same split order)."""
+        assert peer is None, "the in-kernel all-reduce needs peer memory: not part of the single-process double"
         n = w.shape[0]
         if norm_h is not None:            # token operand = RMSNorm(norm_h) from the per-tile sums of squares
             hh = norm_h[:t].float(); rstd = torch.rsqrt(ssq_in[:t].sum(-1, keepdim=True) / hh.shape[-1] + norm_eps)

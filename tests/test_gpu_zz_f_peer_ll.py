@@ -104,3 +104,45 @@ def test_ll_rejects_bad_arguments():
         c.peer_allreduce_ll(torch.zeros(1, 17, 256, device="cuda"), 1, R.ptrs[0], R.bytes, R.state[0], 0, 2, 16,
                             torch.zeros(17, 256, dtype=torch.bfloat16, device="cuda"), torch.zeros(17, 256, dtype=torch.bfloat16, device="cuda"),
                             None, 1e-6, None, 17)
+
+
+@pytest.mark.parametrize("W,T,N,Kr,S", [(2, 1, 256, 128, 1), (2, 7, 512, 320, 2), (4, 16, 512, 256, 3), (8, 32, 1024, 640, 2), (4, 32, 1024, 1728, 4)])
+def test_fused_gemm_allreduce_tail(W, T, N, Kr, S):
+    """gemm_decode_fused(CTS_FUSED_RESIDUAL, peer=...): row-parallel projection + all-reduce + residual (+ per-tile sums of squares) in
+    ONE launch per rank, W ranks as W streams.  Expected h: each rank's partial from the validated split-K GEMM (splits added in
+    order), ranks added in order, rounded, added to the residual -- bit for bit; ssq_out = per-tile sums of squares of that h."""
+    c = ctx()
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(W * 100 + T + N)
+    tmax = 32
+    R = _Ranks(c, W, tmax, N)
+    need = tmax * N * 12 + tmax * (N // 128) * 8
+    assert R.bytes >= need
+    h0 = (torch.randn(T, N, generator=g) * 0.5).to(dt).cuda()
+    hs = [h0.clone() for _ in range(W)]
+    ssq = [torch.full((T, N // 128), float("nan"), device="cuda") for _ in range(W)]
+    cur = h0.clone()
+    for n, which in enumerate([0, 1, 0]):
+        xs = [(torch.randn(T, Kr, generator=g) * 0.5).to(dt).cuda() for _ in range(W)]
+        ws_ = [(torch.randn(N, Kr, generator=g) * 0.05).to(dt).cuda() for _ in range(W)]
+        acc = torch.zeros(T, N, device="cuda")
+        for r in range(W):
+            buf = torch.empty(S * T * N, device="cuda", dtype=torch.float32)
+            c.gemm(xs[r], ws_[r], buf, epilogue=3, split_k=S, t=T)
+            part = buf.view(S, T, N)
+            loc = part[0].clone()
+            for s in range(1, S):
+                loc = loc + part[s]
+            acc = acc + loc
+        torch.cuda.synchronize()
+        for r in range(W):
+            with torch.cuda.stream(R.streams[r]):
+                c.gemm_decode_fused(xs[r], ws_[r], 0, S, T, h=hs[r], ssq_out=ssq[r], peer=(R.ptrs[which], R.bytes, R.state[r], r, W, tmax))
+        torch.cuda.synchronize()
+        cur = (cur.float() + acc.to(dt).float()).to(dt)
+        want_ssq = cur.float().pow(2).view(T, N // 128, 128).sum(-1)
+        for r in range(W):
+            assert torch.equal(hs[r], cur), f"call {n}: h differs from the rank-ordered sum on rank {r}"
+            assert torch.equal(ssq[r], ssq[0]), f"call {n}: statistic differs between ranks 0 and {r}"
+        assert torch.allclose(ssq[0], want_ssq, rtol=1e-4), f"call {n}: per-tile sums of squares"
+    record("fused_gemm_allreduce_tail", W=W, T=T, N=N, K_per_rank=Kr, split=S, bit_exact_h=True)

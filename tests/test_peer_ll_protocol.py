@@ -249,3 +249,142 @@ def test_simulation_detects_a_one_word_epoch_check():
         verdict, _ = simulate(2, 2, 2, 32, 1, calls=4, seed=seed, both=False)
         bad += verdict != "ok"
     assert bad > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The same protocol at (tile, token) granularity inside the decode GEMM (gemm_decode_fused.cu, tensor-parallel tail): the owner of
+# a 128-column tile is one rank, all-gather units are 8-byte halves of the 16-byte layout, the statistic is one 8-byte unit per
+# (token, tile).  Calls of the stand-alone kernel and of the fused tail alternate on the SAME regions and epoch counter.
+# ---------------------------------------------------------------------------------------------------------------------------
+TILE = 8            # stands for the kernel's 128 (the index arithmetic only needs hw % TILE == 0 and TILE % 4 == 0)
+
+
+def cta_fused(ranks, me, which, tile, split, S, W, Tmax, n, local_part, resid, out_h, out_ssq, ssq_cells):
+    """One CTA of the cluster of `tile` on rank `me`: tokens split, split+S, ...; pair lanes as in the kernel."""
+    hw, R = n // W, ranks[me]
+    f0 = tile * TILE
+    owner = f0 // hw
+    epoch = R.epoch_state + 1
+    T = local_part.shape[0]
+    toks = range(split, T, S)
+    for t in toks:                                                       # pass A
+        for ft in range(0, TILE, 2):
+            col = f0 - owner * hw + ft
+            unit = ((me * Tmax + t) * hw + col) >> 1
+            yield from st_ll(ranks[owner].rs[which], unit, np.float32(local_part[t, f0 + ft]), np.float32(local_part[t, f0 + ft + 1]), epoch)
+    if owner == me:                                                      # pass B
+        for t in toks:
+            ss = np.float32(0)
+            for ft in range(0, TILE, 2):
+                col = f0 - owner * hw + ft
+                while True:
+                    us = [R.rs[which][((r * Tmax + t) * hw + col) >> 1].copy() for r in range(W)]
+                    if all(ll_ok(u, epoch) for u in us):
+                        break
+                    yield "poll"
+                a0 = a1 = np.float32(0)
+                for u in us:
+                    a0, a1 = np.float32(a0 + np.float32(u[0])), np.float32(a1 + np.float32(u[2]))
+                h0 = rnd(np.float32(resid[t, f0 + ft]) + rnd(a0))
+                h1 = rnd(np.float32(resid[t, f0 + ft + 1]) + rnd(a1))
+                ss = np.float32(ss + np.float32(h0 * h0 + h1 * h1))
+                unit = (me * Tmax + t) * hw + col
+                for j in range(W):                                       # 8-byte half of the 16-byte all-gather unit
+                    cell = ranks[j].ag[which][unit >> 2]
+                    half = (unit >> 1) & 1
+                    cell[2 * half], cell[2 * half + 1] = _pack(h0, h1), epoch
+                    yield
+            for j in range(W):
+                ssq_cells[j][which][t, tile] = (float(ss), epoch)
+                yield
+    for t in toks:                                                       # pass C
+        for ft in range(0, TILE, 2):
+            col = f0 - owner * hw + ft
+            unit = (owner * Tmax + t) * hw + col
+            half = (unit >> 1) & 1
+            while True:
+                cell = R.ag[which][unit >> 2]
+                if cell[2 * half + 1] == epoch:
+                    w = cell[2 * half]
+                    break
+                yield "poll"
+            out_h[t, f0 + ft], out_h[t, f0 + ft + 1] = _unpack(w)
+        while ssq_cells[me][which][t, tile][1] != epoch:
+            yield "poll"
+        out_ssq[t, tile] = ssq_cells[me][which][t, tile][0]
+    yield "done"
+
+
+def simulate_mixed(W, T, n, S, kinds, seed):
+    """kinds: sequence of 'll' (stand-alone kernel, C = 1) and 'fused' calls over the same regions / epochs."""
+    rng = np.random.default_rng(seed)
+    Tmax, tiles = T + 1, n // TILE
+    ranks = [Rank(W, Tmax, n) for _ in range(W)]
+    ssq_cells = [[np.zeros((Tmax, tiles), dtype=object) for _ in range(2)] for _ in range(W)]
+    for r in range(W):
+        for b in range(2):
+            for i in range(Tmax):
+                for j in range(tiles):
+                    ssq_cells[r][b][i, j] = (0.0, 0)
+    r0 = rng.standard_normal((T, n)).astype(np.float16).astype(np.float32)
+    resid = [r0.copy() for _ in range(W)]
+    norm_w = np.ones(n, np.float32)
+    parts = [rng.standard_normal((W, 1, T, n)).astype(np.float32) for _ in kinds]
+    call_of, live, outs = [0] * W, {}, {}
+
+    def start(r):
+        i = call_of[r]
+        which = i % 2
+        oh, aux = np.zeros((T, n), np.float32), np.zeros((T, max(n, tiles)), np.float32)
+        outs[(r, i)] = (oh, aux)
+        if kinds[i] == "ll":
+            live[r] = [cta(ranks, r, which, 0, t, 1, W, Tmax, n, 1, parts[i][r], resid[r], norm_w, 1e-6, oh, aux) for t in range(T)]
+        else:
+            live[r] = [cta_fused(ranks, r, which, tile, sp, S, W, Tmax, n, parts[i][r, 0], resid[r], oh, aux, ssq_cells)
+                       for tile in range(tiles) for sp in range(S)]
+
+    for r in range(W):
+        start(r)
+    idle = 0
+    while any(live[r] is not None for r in range(W)):
+        r = int(rng.integers(W))
+        if live[r] is None:
+            continue
+        g = live[r][int(rng.integers(len(live[r])))]
+        try:
+            ev = next(g)
+        except StopIteration:
+            ev = "done"
+        idle = idle + 1 if ev == "poll" else 0
+        if idle > 300_000:
+            return "deadlock", None
+        if ev == "done":
+            live[r].remove(g)
+            if not live[r]:
+                ranks[r].epoch_state += 1
+                resid[r] = outs[(r, call_of[r])][0].copy()
+                call_of[r] += 1
+                if call_of[r] < len(kinds):
+                    start(r)
+                else:
+                    live[r] = None
+    cur = r0
+    for i, kind in enumerate(kinds):
+        cur = expected(parts[i], cur, norm_w, 1e-6)
+        for r in range(W):
+            if not np.array_equal(outs[(r, i)][0], cur):
+                return "wrong sum", (i, r)
+            if not np.array_equal(outs[(r, i)][1], outs[(0, i)][1]):
+                return "ranks differ", (i, r)
+        if kind == "fused":                                             # per-tile statistic = sum of squares of the tile's h
+            want = (cur.reshape(T, tiles, TILE).astype(np.float64) ** 2).sum(-1)
+            if not np.allclose(outs[(0, i)][1][:, :tiles], want, rtol=1e-5):
+                return "wrong statistic", i
+    return "ok", None
+
+
+@pytest.mark.parametrize("W,T,n,S", [(2, 3, 32, 2), (4, 2, 64, 1), (2, 5, 48, 3)])
+def test_fused_gemm_tail_and_stand_alone_kernel_share_regions(W, T, n, S):
+    for seed in range(3):
+        verdict, info = simulate_mixed(W, T, n, S, ["fused", "fused", "ll", "fused", "ll", "ll", "fused"], seed)
+        assert verdict == "ok", (verdict, info, seed)

@@ -15,7 +15,7 @@ for l in sys.stdin:
         d=json.loads(l); print({b:round(v['ms_per_step'],3) for b,v in d['by_batch'].items()})
 " >> $OUT
 }
-for v in "CTS_BASELINE=1" "CTS_PEER_LL=1" "CTS_PEER_LL=1 CTS_DECODE_FUSED=1"; do          # correctness first: TP vs the 1-GPU path on the same weights
+for v in "CTS_BASELINE=1" "CTS_PEER_LL=1" "CTS_PEER_LL=1 CTS_DECODE_FUSED=1" "CTS_PEER_LL=1 CTS_DECODE_FUSED=2"; do          # correctness first: TP vs the 1-GPU path on the same weights
   echo "## tp_check $v" >> $OUT
   env $v timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29400 + RANDOM % 200)) \
       tools/tp_check.py 2>>gpurun_out/tp_sweep.err | tail -n 6 >> $OUT
@@ -24,6 +24,7 @@ run CTS_BASELINE=1
 run CTS_DECODE_FUSED=1
 run CTS_PEER_LL=1                                   # two-shot all-reduce with in-band flags (csrc/allreduce_ll.cu)
 run CTS_PEER_LL=1 CTS_DECODE_FUSED=1
+run CTS_PEER_LL=1 CTS_DECODE_FUSED=2                  # GEMM + all-reduce in one kernel, norms folded into the next projection
 for s in "1,1,1,1" "2,1,2,1" "3,2,3,2" "5,3,4,3"; do run CTS_SPLITS=$s; done          # qkv,o,gu,d (decode-sized T only)
 for a in 1 2 4; do run CTS_ATTN_SPLITS=$a; done
 for k in 50 75 100; do run CTS_DECODE_SMEM_KB=$k; done
