@@ -10,11 +10,11 @@ rm -f gpurun_out/parity_metrics.jsonl
 STATUS=0
 for f in train_kernels zz_a_native_step zz_b_sampling zz_d_attn_bwd_tc5 zz_e_fused_decode zz_f_peer_ll; do          # each file in its own process: a trapped kernel cannot take the rest down
   echo "=== tests/test_gpu_$f.py (--runxfail)"
-  timeout 300 python -m pytest tests/test_gpu_$f.py -q -m gpu --runxfail --no-header -p no:cacheprovider -rfE > gpurun_out/test_$f.log 2>&1
+  timeout 300 python -m pytest tests/test_gpu_$f.py -q -m gpu --runxfail --no-header -p no:cacheprovider -rfE --junitxml gpurun_out/junit_$f.xml > gpurun_out/test_$f.log 2>&1
   echo "rc=$?"; tail -n 12 gpurun_out/test_$f.log
 done
 echo "=== tests/test_gpu_zz_c_train.py (--runxfail)"
-timeout ${TEST_TIMEOUT:-600} python -m pytest tests/test_gpu_zz_c_train.py -q -m gpu --runxfail --no-header -p no:cacheprovider -rfE \
+timeout ${TEST_TIMEOUT:-600} python -m pytest tests/test_gpu_zz_c_train.py -q -m gpu --runxfail --no-header -p no:cacheprovider -rfE --junitxml gpurun_out/junit_zz_c_train.xml \
    > gpurun_out/test_train.log 2>&1
 rc=$?
 tail -n 40 gpurun_out/test_train.log
