@@ -279,7 +279,12 @@ class ChatTSForCausalLM:
                 tp_deep = self.tp_size > 1 and self.use_peer_ll and self.peer is not None and H % (128 * self.tp_size) == 0
                 deep = self.use_fused_decode >= 2 and (self.tp_size == 1 or tp_deep)
                 pr = [None, None]
+                so, sd = min(sp["o"], 8), min(sp["d"], 8)
                 if deep and self.tp_size > 1:
+                    # a (tile, token) of the in-kernel all-reduce waits for the same tile's CTAs on the other ranks: keep every rank's
+                    # whole grid resident (one CTA per SM suffices) instead of relying on the order CTAs are scheduled in
+                    cap = max(1, 148 // max(1, H // 128))
+                    so, sd = min(so, cap), min(sd, cap)
                     pr = [(self.peer.partials[w], self.peer.part_bytes, self.peer.state, self.tp_rank, self.tp_size, self.peer.max_batch) for w in (0, 1)]
                 rope = dict(bias=self.bqkv[l], positions=st.positions, cos=self.cos, sin=self.sin, slot_map=st.slot_map, q_out=st.q, k_cache=kc,
                             v_cache=vc, q_norm=self.qn[l], k_norm=self.kn[l], eps=eps, nh=self.nh, nkv=self.nkv, head_dim=self.d,
@@ -293,10 +298,10 @@ class ChatTSForCausalLM:
                         c.gemm_decode_fused(None, self.wqkv[l], _cabi.FUSED_QKV_ROPE, min(sp["qkv"], 8), T, norm_h=st.h, norm_w=self.ln1[l],
                                             ssq_in=st.ssq_b, norm_eps=eps, **rope)
                     attend(l)
-                    c.gemm_decode_fused(st.ao, self.wo[l], _cabi.FUSED_RESIDUAL, min(sp["o"], 8), T, h=st.h, ssq_out=st.ssq_a, peer=pr[0])
+                    c.gemm_decode_fused(st.ao, self.wo[l], _cabi.FUSED_RESIDUAL, so, T, h=st.h, ssq_out=st.ssq_a, peer=pr[0])
                     c.gemm_decode_fused(None, self.wgu[l], _cabi.FUSED_SWIGLU, min(sp["gu"], 8), T, act=st.act, norm_h=st.h, norm_w=self.ln2[l],
                                         ssq_in=st.ssq_a, norm_eps=eps)
-                    c.gemm_decode_fused(st.act, self.wd[l], _cabi.FUSED_RESIDUAL, min(sp["d"], 8), T, h=st.h, ssq_out=st.ssq_b, peer=pr[1])
+                    c.gemm_decode_fused(st.act, self.wd[l], _cabi.FUSED_RESIDUAL, sd, T, h=st.h, ssq_out=st.ssq_b, peer=pr[1])
                     if l + 1 == self.L:
                         c.reduce_residual_rmsnorm(None, 0, st.h, None, self.final_norm, eps, st.xn, t=T)
                     continue
