@@ -487,6 +487,9 @@ def run_b200(args):
                 "by_batch": {str(b): {"tokens_per_s": r["tokens_per_s"], "ms_per_step": r["ms_per_step"]} for b, r in results.items()},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(main["launches"] * args.steps), "launches_per_step": main["launches"],
                 "roofline": roof, "ts_encoder": ts_roof, "attention": attn_roof, "cpu_baseline": cpu, "arch": ctx.arch, "lib": os.path.relpath(_cabi.LIB_PATH, ROOT)}
+        # which opt-in variants of the decode path this line was measured with (all off = the validated default path)
+        line["config"]["variants"] = {k: int(getattr(model, a, 0) or 0) for k, a in (("decode_fused", "use_fused_decode"), ("peer_ll", "use_peer_ll"),
+                                                                                   ("native_step", "use_native_step"), ("decode_chain", "use_chain"))}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
