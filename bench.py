@@ -358,7 +358,7 @@ def run_b200(args):
 
     results = {}
     with ClockSampler(local) as clk:
-        batches = [args.batch] if args.only_batch else sorted(set([1, 8, args.batch]))
+        batches = [args.batch] if args.only_batch else sorted(set(b for b in (1, 8, args.batch) if b <= args.batch))
         for b in batches:
             ms, launches, ctx_end = measure_decode(b)
             results[b] = dict(ms_total=ms, ms_per_step=ms / args.steps, tokens_per_s=b * args.steps / (ms / 1e3), launches=launches,
