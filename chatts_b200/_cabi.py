@@ -214,6 +214,9 @@ class Context:
         self.h = h
         self.arch = self.lib.cts_arch().decode()
         self.launches = 0          # kernels launched through this ctx (bench.py's gpu_launches evidence)
+        # CTS_DEBUG_SYNC=1: synchronise after every entry point and name the one whose kernel faulted (asynchronous CUDA errors
+        # otherwise surface at some later, unrelated call).  Debugging aid only -- never on in a measurement.
+        self._debug_sync = os.environ.get("CTS_DEBUG_SYNC", "0") == "1"
 
     def close(self):
         if getattr(self, "h", None):
@@ -224,6 +227,12 @@ class Context:
         self.launches += n_kernels
         if rc != OK:
             raise CtsError(f"chatts_b200 error {rc}: {self.lib.cts_last_error(self.h).decode()}")
+        if self._debug_sync and not torch.cuda.is_current_stream_capturing():
+            try:
+                torch.cuda.synchronize()
+            except Exception as e:
+                import sys
+                raise CtsError(f"kernel fault inside Context.{sys._getframe(1).f_code.co_name}: {e}") from e
 
     # ------------------------------------------------------------------ TS front end
     def ts_patch_count(self, x, num_features, patch_size):

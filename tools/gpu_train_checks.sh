@@ -13,6 +13,15 @@ for f in train_kernels zz_a_native_step zz_b_sampling zz_d_attn_bwd_tc5 zz_e_fus
   timeout 300 python -m pytest tests/test_gpu_$f.py -q -m gpu --runxfail --no-header -p no:cacheprovider -rfE --junitxml gpurun_out/junit_$f.xml > gpurun_out/test_$f.log 2>&1
   echo "rc=$?"; tail -n 12 gpurun_out/test_$f.log
 done
+# a file that failed above: rerun its first failing case alone with CTS_DEBUG_SYNC=1 so the log names the faulting entry point
+for f in zz_a_native_step zz_b_sampling zz_d_attn_bwd_tc5 zz_e_fused_decode zz_f_peer_ll; do
+  if grep -q "^FAILED\|^ERROR" gpurun_out/test_$f.log 2>/dev/null; then
+    first=$(grep -m1 "^FAILED\|^ERROR" gpurun_out/test_$f.log | awk '{print $2}')
+    echo "=== debug rerun of $first"
+    CTS_DEBUG_SYNC=1 timeout 200 python -m pytest "$first" -q -m gpu --runxfail --no-header -p no:cacheprovider -x 2>&1 | tail -n 25 > gpurun_out/debug_$f.log
+    tail -n 12 gpurun_out/debug_$f.log
+  fi
+done
 echo "=== tests/test_gpu_zz_c_train.py (--runxfail)"
 timeout ${TEST_TIMEOUT:-600} python -m pytest tests/test_gpu_zz_c_train.py -q -m gpu --runxfail --no-header -p no:cacheprovider -rfE --junitxml gpurun_out/junit_zz_c_train.xml \
    > gpurun_out/test_train.log 2>&1
