@@ -3,11 +3,12 @@
 // replaces "RowParallelLinear -> NCCL all-reduce -> residual add -> RMSNorm" (vllm qwen2.py:100-116,168-174,
 // 299-311) for the decode-sized messages (b*5120 fp32 = 20..640 KiB) where the
 // collective is latency-bound: every rank's o_proj / down_proj GEMM leaves its fp32 partial in a symmetric
-// (cudaIpc-mapped) buffer; this kernel (1) signals "my partial is complete" into every peer's flag array with a
-// system-scope release store, (2) waits with acquire loads until all peers have signalled this epoch, (3) PULLS
-// the peers' rows over NVLink (plain vectorised peer loads) and reduces them in rank order -- the same order on
-// every rank, so all ranks hold bit-identical h without a broadcast -- fused with the residual add and the next
-// RMSNorm.  No NCCL call, no extra launch, no copy.  The two partial buffers (o_proj / down_proj) alternate, so
+// (cudaIpc-mapped) buffer; this kernel (1) reduces the rank's split-K partials and PUSHES its chunk into slot [rank] of
+// every peer's buffer (posted NVLink writes), (2) signals "my chunk has landed" into every peer's flag array with a
+// system-scope release store and waits with acquire loads until all peers have signalled this epoch, (3) sums the
+// local slots in rank order -- the same order on every rank, so all ranks hold bit-identical h without a broadcast --
+// fused with the residual add and the next RMSNorm.  No NCCL call, no extra launch, no copy.  (allreduce_ll.cu is the
+// two-shot variant with the flags inside the data.)  The two partial buffers (o_proj / down_proj) alternate, so
 // the barrier of call n+1 is what licenses overwriting the buffer of call n.
 #include <cooperative_groups.h>
 
