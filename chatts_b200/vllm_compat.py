@@ -65,8 +65,10 @@ class LLM:
 
     def generate(self, inputs, sampling_params=None, use_tqdm=False, streamer=None):
         sp = sampling_params or SamplingParams()
-        if isinstance(inputs, dict):
+        if isinstance(inputs, (dict, str)):
             inputs = [inputs]
+        # plain strings are text-only prompts (llm_utils.py:127 passes a list of str to the same call)
+        inputs = [{"prompt": r} if isinstance(r, str) else r for r in inputs]
         n = max(1, int(sp.n))
         if n > 1:
             # n completions per request = n copies of the request in the batch, each row with its own draw

@@ -126,6 +126,10 @@ def test_vllm_request_shape(cabi_double):
     with pytest.raises(TypeError):                             # chatts_vllm.py:277-279
         llm.generate([{"prompt": "x <ts><ts/>", "multi_modal_data": {"timeseries": ["not a series"]}}],
                      SamplingParams(max_tokens=2))
+    # plain strings = text-only prompts through the same call (llm_utils.py:127), keyword form of demo_vllm.py:59
+    plain = llm.generate(["none", "another"], sampling_params=SamplingParams(max_tokens=6, ignore_eos=True), use_tqdm=False)
+    assert plain[0].prompt == "none" and plain[0].outputs[0].token_ids == outs[1].outputs[0].token_ids
+    assert len(llm.generate("none", SamplingParams(max_tokens=3, ignore_eos=True))) == 1
 
 
 def test_vllm_sampling_params_n_stop_topk(cabi_double):
