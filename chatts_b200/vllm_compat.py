@@ -107,3 +107,84 @@ class LLM:
                     text = text[:cut]
                 outs.append(RequestOutput(req["prompt"], [CompletionOutput(text, toks)]))
         return outs
+
+
+# --------------------------------------------------------------------------------------------------
+# Streaming surface of the reference's interactive script (chatts/utils/vllm_stream_qa.py:26-59):
+#     model = AsyncLLMEngine.from_engine_args(AsyncEngineArgs(model=..., max_model_len=..., limit_mm_per_prompt={"timeseries": 15}))
+#     async for request_output in model.generate(prompt, SamplingParams(max_tokens=...), request_id=...):
+#         request_output.outputs[0].text            # CUMULATIVE text so far
+# One request at a time per engine (the script is a chat loop); tokens come from the decode loop through the HF-streamer
+# protocol of ChatTSForCausalLM.generate (put / end), one device->host read per token.
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class AsyncEngineArgs:
+    model: object = None
+    enforce_eager: bool = True                        # accepted and ignored: the decode step is always one CUDA graph
+    gpu_memory_utilization: float = 0.9               # accepted and ignored: the KV pool is sized by max_model_len x max_num_seqs
+    max_model_len: int = 2048
+    tensor_parallel_size: int = 1
+    limit_mm_per_prompt: dict = None
+    trust_remote_code: bool = True
+    dtype: str = "bfloat16"
+    max_num_seqs: int = 1
+
+
+class _AsyncStreamer:
+    def __init__(self, loop, queue):
+        self.loop, self.queue = loop, queue
+
+    def put(self, ids):
+        self.loop.call_soon_threadsafe(self.queue.put_nowait, [int(x) for x in ids.reshape(-1)[:1]])
+
+    def end(self):
+        pass
+
+
+class AsyncLLMEngine:
+    def __init__(self, llm):
+        import threading
+        self.llm = llm
+        self._busy = threading.Lock()
+
+    @classmethod
+    def from_engine_args(cls, args, llm=None):
+        if llm is None:
+            llm = LLM(model=args.model, tensor_parallel_size=args.tensor_parallel_size, dtype=args.dtype, max_model_len=args.max_model_len,
+                      max_num_seqs=args.max_num_seqs, limit_mm_per_prompt=args.limit_mm_per_prompt, trust_remote_code=args.trust_remote_code)
+        return cls(llm)
+
+    async def generate(self, prompt, sampling_params=None, request_id=None):
+        """Async generator of RequestOutput with the cumulative text (and token ids) after every new token; the last one carries the
+        final text with the stop strings applied, exactly what the blocking call returns."""
+        import asyncio
+        loop = asyncio.get_running_loop()
+        q = asyncio.Queue()
+        req = {"prompt": prompt} if isinstance(prompt, str) else prompt
+        sp = sampling_params or SamplingParams()
+        done = object()
+
+        def work():
+            with self._busy:
+                try:
+                    out = self.llm.generate([req], sp, streamer=_AsyncStreamer(loop, q))[0]
+                    loop.call_soon_threadsafe(q.put_nowait, (done, out))
+                except BaseException as e:          # surfaced in the consumer, not lost in the worker thread
+                    loop.call_soon_threadsafe(q.put_nowait, (done, e))
+
+        fut = loop.run_in_executor(None, work)
+        toks = []
+        stops = [sp.stop] if isinstance(sp.stop, str) else list(sp.stop or [])
+        while True:
+            item = await q.get()
+            if isinstance(item, tuple) and item[0] is done:
+                await fut
+                if isinstance(item[1], BaseException):
+                    raise item[1]
+                yield item[1]
+                return
+            toks += item
+            text = self.llm.tokenizer.decode(toks)
+            if any(st and st in text for st in stops):
+                continue                               # the final output carries the text cut at the stop string
+            yield RequestOutput(req["prompt"], [CompletionOutput(text, list(toks))])

@@ -205,3 +205,40 @@ def test_fused_decode_gemms_generate_the_same_tokens(cabi_double, split, qwen3):
             assert torch.equal(fused.kv, model.kv)
         else:                                  # the row statistic is summed tile by tile: at most an ulp of bf16 in the cache
             assert float((fused.kv.float() - model.kv.float()).abs().max()) <= 2 ** -6 * float(model.kv.float().abs().max())
+
+
+def test_async_engine_streams_cumulative_text(cabi_double):
+    """AsyncLLMEngine.generate as chatts/utils/vllm_stream_qa.py:52-59 drives it: an async generator whose outputs[0].text grows
+    token by token and ends with exactly what the blocking call returns."""
+    import asyncio
+
+    from chatts_b200.vllm_compat import LLM, AsyncEngineArgs, AsyncLLMEngine, SamplingParams
+
+    cfg, sd, model, proc = _build(cabi_double)
+    a, _ = _series()
+    llm = LLM(model=model)
+    eng = AsyncLLMEngine.from_engine_args(AsyncEngineArgs(model=None, max_model_len=512, limit_mm_per_prompt={"timeseries": 15}), llm=llm)
+    req = {"prompt": "one: <ts><ts/> ?", "multi_modal_data": {"timeseries": [a]}}
+    sp = SamplingParams(max_tokens=7, ignore_eos=True)
+    want = llm.generate([req], sp)[0].outputs[0]
+
+    async def run():
+        seen = []
+        async for out in eng.generate(req, sp, request_id=1.0):
+            seen.append((out.outputs[0].text, list(out.outputs[0].token_ids)))
+        return seen
+
+    seen = asyncio.run(run())
+    assert len(seen) == 8                                    # 7 partial outputs + the final one
+    for (t0, k0), (t1, k1) in zip(seen[:-2], seen[1:-1]):
+        assert t1.startswith(t0) and k1[: len(k0)] == k0 and len(k1) == len(k0) + 1
+    assert seen[-1] == (want.text, want.token_ids) and seen[-2][1] == want.token_ids
+    # a plain string prompt, and an error inside the worker reaches the consumer
+    assert len(asyncio.run(_collect(eng.generate("plain text", SamplingParams(max_tokens=2, ignore_eos=True))))) == 3
+    with pytest.raises(TypeError):
+        asyncio.run(_collect(eng.generate({"prompt": "x <ts><ts/>", "multi_modal_data": {"timeseries": ["bad"]}}, sp)))
+
+
+async def _collect(agen):
+    return [x async for x in agen]
+
