@@ -9,7 +9,7 @@ Runs only where /root/reference exists (the build container, never the GPU box):
   vllm 0.8.5 and fails on the installed 0.22) and EXECUTED on CPU with seeded weights/inputs.
 * ``sp_encoding`` / ``eval_prompt_to_encoding`` are imported from chatts.utils.encoding_utils.
 
-Outputs (small .npz files, committed):  ts_encoder_{posemb,posidx,plain}.npz, sp_encoding.npz.
+Outputs (small files, committed):  ts_encoder_{posemb,posidx,plain}.npz, sp_encoding.npz, encoding_utils.json.
 Nothing from the reference's sources is copied into the repo -- only its numeric outputs.
 """
 import ast
@@ -83,6 +83,36 @@ def main():
     rec["batch_out"] = batch
     rec["n"] = np.array(len(series))
     np.savez_compressed(os.path.join(HERE, "sp_encoding.npz"), **rec)
+
+    # ---------------- the rest of encoding_utils (every method, ragged batches, the text helpers) ----------------
+    import json
+    cases = []
+    pool = [series[0], series[4], series[2], series[11], series[12], series[13]]
+    for method in ("sp", "minmax_scale", "no"):
+        for pick in ([0], [1, 2], [3, 4, 5], [0, 1, 2, 3]):
+            tss = [pool[i].tolist() for i in pick]
+            prompt = "Q" + "".join(f" s{j}: <ts><ts/>" for j in range(len(pick))) + " end."
+            if method == "no" and len({len(t) for t in tss}) > 1:
+                tss = [t[:20] for t in tss]              # 'no' keeps 1-D series: np.pad over 3 axes needs [1, L, 1]-shaped input
+                tss = [[[v] for v in t] for t in tss]
+            elif method == "no":
+                tss = [[[v] for v in t] for t in tss]
+            rp, batch = eu.eval_prompt_to_encoding(prompt, tss, method)
+            cases.append({"fn": "eval_prompt_to_encoding", "method": method, "prompt": prompt, "timeseries": tss, "out_prompt": rp,
+                          "out_batch": batch.tolist(), "out_shape": list(batch.shape)})
+    for s_ in (series[0], series[13]):
+        for method in ("sp", "minmax_scale"):
+            enc, pr, meta = eu.timeseries_encoding(np.array(s_), method)
+            cases.append({"fn": "timeseries_encoding", "method": method, "timeseries": s_.tolist(), "out": enc.tolist(), "out_prompt": pr, "meta": meta})
+    two = [[[1.23456, 2.0], [3.14159, -4.5]], [[0.0005, 1e-7], [7.0, 8.12345678]]]
+    cases.append({"fn": "timeseries_prompt", "prompt": "a <ts><ts/> b <ts><ts/> c", "timeseries": two,
+                  "out": eu.timeseries_prompt("a <ts><ts/> b <ts><ts/> c", two)})
+    cases.append({"fn": "timeseries_prompt", "prompt": "a <ts><ts/> b <ts><ts/> c", "timeseries": two, "as_array": True,
+                  "out": eu.timeseries_prompt("a <ts><ts/> b <ts><ts/> c", np.array(two))})
+    for obj in ([0.123456789, 2.5, -1e-9], [[1.00000049, 2.0], [3.3333333333, 4.0]], np.array([[0.1234567891, 5.0]]).tolist()):
+        cases.append({"fn": "timeseries_to_list", "in": obj, "out": eu.timeseries_to_list(obj)})
+    cases.append({"fn": "timeseries_to_list", "in": [[0.1234567891, 5.0]], "as_array": True, "out": eu.timeseries_to_list(np.array([[0.1234567891, 5.0]]))})
+    json.dump(cases, open(os.path.join(HERE, "encoding_utils.json"), "w"))
 
     # ---------------- TS encoder, three position modes ----------------
     def run(tag, cfg, lengths, seed):
