@@ -37,6 +37,25 @@ constexpr int kLLMaxRanks = 8;
 constexpr int kLLMaxC = 8;
 constexpr unsigned kLLSpinLimit = 1u << 24;
 
+#ifdef CTS_HOST_SHIM
+// tests/cuda_on_cpu: the same wire format on the host -- two 8-byte halves written and read separately (a scheduling point in
+// between, so that a torn unit is actually observable), ranks are processes sharing the regions
+__device__ __forceinline__ void st_ll(void* p, uint32_t d0, uint32_t d1, uint32_t epoch) {
+  volatile uint64_t* q = reinterpret_cast<volatile uint64_t*>(p);
+  q[0] = (uint64_t)d0 | ((uint64_t)epoch << 32);
+  sched_yield();
+  q[1] = (uint64_t)d1 | ((uint64_t)epoch << 32);
+}
+__device__ __forceinline__ uint4 ld_ll(const void* p) {
+  const volatile uint64_t* q = reinterpret_cast<const volatile uint64_t*>(p);
+  const uint64_t a = q[0], b = q[1];
+  uint4 v = {(uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32)};
+  shim_yield();                                            // pollers must let the other threads of the block (and the peers) run
+  static unsigned n = 0;
+  if ((++n & 1023u) == 0) sched_yield();
+  return v;
+}
+#else
 __device__ __forceinline__ void st_ll(void* p, uint32_t d0, uint32_t d1, uint32_t epoch) {
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(d0), "r"(epoch), "r"(d1), "r"(epoch) : "memory");
 }
@@ -45,6 +64,7 @@ __device__ __forceinline__ uint4 ld_ll(const void* p) {
   asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+#endif
 __device__ __forceinline__ bool ll_ok(const uint4& v, uint32_t epoch) { return v.y == epoch && v.w == epoch; }
 
 __device__ void ll_timeout(const char* what, int rank) {
@@ -247,16 +267,16 @@ extern "C" int cts_peer_allreduce_ll(cts_ctx* ctx, const float* local_partial, i
   CTS_CHECK_ARG(ctx, t > 0 && t <= max_tokens && t <= 65535, "t must be in 1..max_tokens");
   CTS_CHECK_ARG(ctx, h > 0 && h % (4LL * world) == 0, "h must be a multiple of 4 * world");
   CTS_CHECK_ARG(ctx, region_bytes >= cts_peer_ll_region_bytes(world, max_tokens, h), "symmetric region too small for the LL layout");
-  // C sub-slices per owner chunk: as many as keep >= 32 four-column groups per CTA (and <= 256: one per thread in phase B)
+  // C sub-slices per owner chunk: the largest C that keeps >= 32 four-column groups per CTA (and <= 256: one per thread in phase B);
+  // a chunk too small for that is not split at all
   const long long hw = h / world;
   unsigned C = 0;
   for (unsigned cand : {8u, 4u, 2u, 1u}) {
     if (hw % (4LL * cand) != 0) continue;
     const long long groups = hw / (4LL * cand);
-    if (groups > kLLThreads) continue;
-    if (C == 0 || groups >= 32) C = cand;
-    if (groups >= 32) break;
+    if (groups >= 32 && groups <= kLLThreads) { C = cand; break; }
   }
+  if (C == 0 && hw / 4 <= kLLThreads) C = 1;
   CTS_CHECK_ARG(ctx, C != 0, "h / world too large for one CTA row (needs h / (world * 8 * 4) <= 256)");
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = dtype == CTS_BF16

@@ -1,0 +1,224 @@
+// TEST INFRASTRUCTURE ONLY -- "CUDA on CPU": stands in for chatts_b200/csrc/common.cuh when a kernel source file is compiled with g++
+// (tests/cuda_on_cpu/build.py copies the .cu next to this header, so its `#include "common.cuh"` lands here).  It provides the CUDA
+// vocabulary those files use -- thread / block indices, __shared__, __syncthreads, warp shuffles, atomics, bf16 / fp16 storage types,
+// vector types, launch_pdl -- with the execution model
+//     one OS thread per CUDA thread, the threads of ONE block at a time, blocks of a grid one after the other,
+// and the library's own host helpers (cts_ctx, error macros, DT<>, rnd, pack8, warp_sum ...) restated for the host.  The KERNEL
+// BODIES and the C-ABI entry points are the product's, untouched: what runs here is the same source nvcc compiles for sm_100a,
+// which turns "this kernel has never executed" into "its source executes and passes its GPU test on CPU" for the kernels that need
+// no tensor core, TMA or cluster (sampling, AdamW / clip / adapter packing, the elementwise backward kernels, the LL all-reduce).
+// Not a performance model, not a memory-model checker (x86 is stronger than PTX), never part of the product.
+#pragma once
+#include <math.h>
+#include <sched.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <functional>
+#include <tuple>
+#include <type_traits>
+#include <vector>
+
+#include "chatts_b200.h"
+
+#define CTS_HOST_SHIM 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __grid_constant__
+
+// ---------------------------------------------------------------------------------------------- vector types
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline uint2 make_uint2(uint32_t a, uint32_t b) { return {a, b}; }
+static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return {a, b, c, d}; }
+static inline float2 make_float2(float a, float b) { return {a, b}; }
+static inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
+
+// ---------------------------------------------------------------------------------------------- bf16 / fp16 storage types
+struct __nv_bfloat16 { uint16_t bits; };
+struct __half { uint16_t bits; };
+static inline float shim_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t shim_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float __bfloat162float(__nv_bfloat16 v) { return shim_u2f((uint32_t)v.bits << 16); }
+static inline __nv_bfloat16 __float2bfloat16_rn(float f) {
+  uint32_t u = shim_f2u(f);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return {(uint16_t)0x7FFF};                     // NaN
+  u += 0x7FFFu + ((u >> 16) & 1u);                                                    // round to nearest even
+  return {(uint16_t)(u >> 16)};
+}
+static inline float __half2float(__half v) { _Float16 h; memcpy(&h, &v.bits, 2); return (float)h; }
+static inline __half __float2half_rn(float f) { _Float16 h = (_Float16)f; __half r; memcpy(&r.bits, &h, 2); return r; }
+
+// ---------------------------------------------------------------------------------------------- execution model
+// The CUDA threads of a block are FIBERS of one OS thread (hand-rolled x86-64 context switch, shim_runtime.cpp), scheduled round
+// robin; a fiber leaves the CPU only at a barrier, a shuffle or an explicit shim_yield().  No locks anywhere: the block state below is
+// only ever touched by the fiber that is running.  Blocks of a grid run one after the other.
+struct ShimBlock {
+  int alive = 0, arrived = 0;
+  unsigned long gen = 0;
+  int named_arrived[16] = {0};                             // named barriers (bar.sync id, n)
+  unsigned long named_gen[16] = {0};
+  struct Warp { int alive = 0, arrived = 0; unsigned long gen = 0; uint64_t slot[32]; } warp[64];   // shuffles / __syncwarp
+};
+extern ShimBlock g_blk;
+struct ShimIdx { unsigned x, y, z; };
+extern ShimIdx g_tid, g_bid, g_bdim, g_gdim;               // g_tid is swapped by the scheduler with every fiber switch
+#define threadIdx g_tid
+#define blockIdx g_bid
+#define blockDim g_bdim
+#define gridDim g_gdim
+void shim_yield();                                         // give the other fibers of the block a turn
+
+static inline int shim_linear_tid() { return (int)(g_tid.x + g_bdim.x * (g_tid.y + g_bdim.y * g_tid.z)); }
+
+static inline void __syncthreads() {
+  const unsigned long my = g_blk.gen;
+  if (++g_blk.arrived >= g_blk.alive) { g_blk.arrived = 0; ++g_blk.gen; return; }
+  while (g_blk.gen == my) shim_yield();
+}
+static inline void named_bar_sync(int id, int n) {        // bar.sync id, n : the first n arrivals of a generation release each other
+  const unsigned long my = g_blk.named_gen[id];
+  if (++g_blk.named_arrived[id] >= n) { g_blk.named_arrived[id] = 0; ++g_blk.named_gen[id]; return; }
+  while (g_blk.named_gen[id] == my) shim_yield();
+}
+static inline void shim_warp_rendezvous() {
+  ShimBlock::Warp& w = g_blk.warp[shim_linear_tid() >> 5];
+  const unsigned long my = w.gen;
+  if (++w.arrived >= w.alive) { w.arrived = 0; ++w.gen; return; }
+  while (w.gen == my) shim_yield();
+}
+static inline void __syncwarp(unsigned = 0xffffffffu) { shim_warp_rendezvous(); }
+template <typename V> static inline V shim_shfl(V v, int src_lane) {
+  static_assert(sizeof(V) <= 8, "shuffle of at most 64 bits");
+  ShimBlock::Warp& w = g_blk.warp[shim_linear_tid() >> 5];
+  const int lane = shim_linear_tid() & 31;
+  uint64_t bits = 0;
+  memcpy(&bits, &v, sizeof(V));
+  w.slot[lane] = bits;
+  shim_warp_rendezvous();                                  // everybody has written
+  V out = v;
+  if (src_lane >= 0 && src_lane < 32) { const uint64_t b = w.slot[src_lane]; memcpy(&out, &b, sizeof(V)); }
+  shim_warp_rendezvous();                                  // everybody has read: the slots may be rewritten
+  return out;
+}
+template <typename V> static inline V __shfl_xor_sync(unsigned, V v, int m) { return shim_shfl(v, (shim_linear_tid() & 31) ^ m); }
+template <typename V> static inline V __shfl_down_sync(unsigned, V v, int d) { const int l = shim_linear_tid() & 31; return shim_shfl(v, l + d < 32 ? l + d : l); }
+template <typename V> static inline V __shfl_up_sync(unsigned, V v, int d) { const int l = shim_linear_tid() & 31; return shim_shfl(v, l - d >= 0 ? l - d : l); }
+template <typename V> static inline V __shfl_sync(unsigned, V v, int src) { return shim_shfl(v, src & 31); }
+
+void shim_run_block(const std::function<void()>& body, dim3 block);
+
+template <typename... KArgs, typename... Args>
+static inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t, void*, unsigned, Args... args) {
+  auto tup = std::make_tuple(static_cast<KArgs>(args)...);
+  g_gdim = {grid.x, grid.y, grid.z};
+  g_bdim = {block.x, block.y, block.z};
+  for (unsigned z = 0; z < grid.z; ++z)
+    for (unsigned y = 0; y < grid.y; ++y)
+      for (unsigned x = 0; x < grid.x; ++x) {
+        g_bid = {x, y, z};
+        shim_run_block([&] { std::apply(kern, tup); }, block);
+      }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- intrinsics
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline float atomicAdd(float* p, float v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(p);
+  uint32_t old = __atomic_load_n(u, __ATOMIC_SEQ_CST);
+  for (;;) {
+    const uint32_t want = shim_f2u(shim_u2f(old) + v);
+    if (__atomic_compare_exchange_n(u, &old, want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) return shim_u2f(old);
+  }
+}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __trap() { fflush(stdout); abort(); }
+#define __expf(x) expf(x)        // glibc declares a __expf of its own
+static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline float __fdividef(float a, float b) { return a / b; }
+static inline float __uint_as_float(uint32_t u) { return shim_u2f(u); }
+static inline uint32_t __float_as_uint(float f) { return shim_f2u(f); }
+static inline float __int_as_float(int i) { return shim_u2f((uint32_t)i); }
+static inline int __float_as_int(float f) { return (int)shim_f2u(f); }
+template <typename V> static inline V __ldg(const V* p) { return *p; }
+template <typename V> static inline V __ldcv(const V* p) { return *p; }
+template <typename V> static inline V __ldcs(const V* p) { return *p; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline long long min(long long a, long long b) { return a < b ? a : b; }
+static inline long long max(long long a, long long b) { return a > b ? a : b; }
+
+// ---------------------------------------------------------------------------------------------- the library's host helpers
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+#define cudaSuccess 0
+#define cudaErrorInvalidValue 1
+static inline const char* cudaGetErrorString(int) { return "shim"; }
+
+struct cts_ctx {
+  int device;
+  int sm_count;
+  char err[512];
+};
+int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);
+
+#define CTS_CHECK_ARG(ctx, cond, msg)                                         \
+  do {                                                                        \
+    if (!(cond)) return cts_set_error((ctx), CTS_ERR_BAD_ARG, "%s: %s", __func__, (msg)); \
+  } while (0)
+#define CTS_CUDA(ctx, expr)                                                   \
+  do {                                                                        \
+    cudaError_t _e = (expr);                                                  \
+    if (_e != cudaSuccess) return cts_set_error((ctx), CTS_ERR_CUDA, "%s: %s", __func__, #expr); \
+  } while (0)
+#define CTS_LAUNCH_CHECK(ctx) do { } while (0)
+
+static inline long long cdiv_ll(long long a, long long b) { return (a + b - 1) / b; }
+static inline void pdl_wait() {}
+static inline void pdl_trigger() {}
+
+template <typename T> struct DT;
+template <> struct DT<__nv_bfloat16> {
+  static inline float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static inline __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct DT<__half> {
+  static inline float to_f(__half v) { return __half2float(v); }
+  static inline __half from_f(float v) { return __float2half_rn(v); }
+};
+template <typename T> static inline float rnd(float v) { return DT<T>::to_f(DT<T>::from_f(v)); }
+template <typename T> static inline void unpack8(const uint4& u, float* f) {
+  const T* p = reinterpret_cast<const T*>(&u);
+  for (int i = 0; i < 8; ++i) f[i] = DT<T>::to_f(p[i]);
+}
+template <typename T> static inline uint4 pack8(const float* f) {
+  uint4 u;
+  T* p = reinterpret_cast<T*>(&u);
+  for (int i = 0; i < 8; ++i) p[i] = DT<T>::from_f(f[i]);
+  return u;
+}
+static inline float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+static inline float warp_max(float v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+static inline float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+static inline float silu_f(float x) { return x / (1.0f + expf(-x)); }

@@ -1,0 +1,134 @@
+// TEST INFRASTRUCTURE ONLY -- runtime of the "CUDA on CPU" shim (see common.cuh in this directory).
+#include "common.cuh"
+
+#include <sys/mman.h>
+
+ShimBlock g_blk;
+ShimIdx g_tid, g_bid, g_bdim, g_gdim;
+
+// ---- fibers: swap the callee-saved registers and the stack pointer (System V x86-64)
+extern "C" void shim_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl shim_switch
+.type shim_switch,@function
+shim_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size shim_switch,.-shim_switch
+)");
+
+namespace {
+struct Fiber { void* sp; ShimIdx tid; bool done; };
+constexpr size_t kStack = 256 << 10;
+std::vector<Fiber> g_fibers;
+void* g_sched_sp = nullptr;
+int g_cur = -1;
+const std::function<void()>* g_body = nullptr;
+
+void fiber_main() {
+  (*g_body)();
+  // a thread that has returned no longer takes part in barriers (CUDA semantics): release anybody it would have kept waiting
+  --g_blk.alive;
+  if (g_blk.arrived > 0 && g_blk.arrived >= g_blk.alive) { g_blk.arrived = 0; ++g_blk.gen; }
+  ShimBlock::Warp& w = g_blk.warp[g_cur >> 5];
+  --w.alive;
+  if (w.arrived > 0 && w.arrived >= w.alive) { w.arrived = 0; ++w.gen; }
+  g_fibers[g_cur].done = true;
+  shim_switch(&g_fibers[g_cur].sp, g_sched_sp);
+  abort();                                                 // a finished fiber is never resumed
+}
+}  // namespace
+
+void shim_yield() {
+  Fiber& f = g_fibers[g_cur];
+  f.tid = g_tid;
+  shim_switch(&f.sp, g_sched_sp);
+}
+
+void shim_run_block(const std::function<void()>& body, dim3 block) {
+  const int n = (int)(block.x * block.y * block.z);
+  static char* arena = nullptr;
+  static size_t arena_fibers = 0;
+  if ((size_t)n > arena_fibers) {
+    if (arena) munmap(arena, arena_fibers * kStack);
+    arena = (char*)mmap(nullptr, (size_t)n * kStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (arena == MAP_FAILED) { perror("shim: mmap of the fiber stacks"); abort(); }
+    arena_fibers = (size_t)n;
+  }
+  g_blk.alive = n;
+  g_blk.arrived = 0;
+  for (int i = 0; i < 16; ++i) g_blk.named_arrived[i] = 0;
+  for (int w = 0; w < 64; ++w) {
+    const int lanes = n - w * 32;
+    g_blk.warp[w].alive = lanes <= 0 ? 0 : (lanes > 32 ? 32 : lanes);
+    g_blk.warp[w].arrived = 0;
+  }
+  g_body = &body;
+  g_fibers.assign((size_t)n, Fiber{});
+  for (int i = 0; i < n; ++i) {
+    Fiber& f = g_fibers[i];
+    f.tid = {(unsigned)(i % (int)block.x), (unsigned)((i / (int)block.x) % (int)block.y), (unsigned)(i / (int)(block.x * block.y))};
+    f.done = false;
+    uintptr_t top = ((uintptr_t)arena + (size_t)(i + 1) * kStack) & ~(uintptr_t)15;
+    void** sp = (void**)top;
+    *--sp = nullptr;                                       // the "return address" fiber_main would see (never used)
+    *--sp = (void*)&fiber_main;                            // popped by the `ret` of the first switch into this fiber
+    for (int r = 0; r < 6; ++r) *--sp = nullptr;           // rbp rbx r12 r13 r14 r15
+    f.sp = sp;
+  }
+  int left = n;
+  while (left > 0) {
+    for (int i = 0; i < n; ++i) {
+      Fiber& f = g_fibers[i];
+      if (f.done) continue;
+      g_cur = i;
+      g_tid = f.tid;
+      shim_switch(&g_sched_sp, f.sp);
+      if (f.done) --left;
+    }
+  }
+  g_cur = -1;
+}
+
+int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+extern "C" int cts_version(void) { return 100; }
+extern "C" const char* cts_arch(void) { return "host-shim"; }
+extern "C" int cts_ctx_create(int device, cts_ctx** out) {
+  cts_ctx* c = new cts_ctx();
+  c->device = device;
+  c->sm_count = 148;
+  c->err[0] = 0;
+  *out = c;
+  return CTS_OK;
+}
+extern "C" void cts_ctx_destroy(cts_ctx* ctx) { delete ctx; }
+extern "C" const char* cts_last_error(const cts_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+// the tensor-core weight-gradient variant lives in lora_wgrad_mma.cu (mma.sync: not part of the shim build)
+bool cts_lora_wgrad_mma_enabled() { return false; }
+bool cts_lora_wgrad_mma_ok(const void*, long long, long long, int, long long, const void*, long long, long long, int) { return false; }
+int cts_lora_wgrad_mma_launch(cts_ctx*, const void*, long long, long long, int, long long, const void*, long long, long long, int, long long,
+                              float, float*, long long, long long, int, void*) { return CTS_ERR_UNSUPPORTED; }
