@@ -21,12 +21,20 @@ namespace {
 
 using namespace nvcuda;
 
+#ifdef CTS_HOST_SHIM      // tests/cuda_on_cpu: the asynchronous copy is a copy
+__device__ __forceinline__ void bw_cp_async16(void* smem, const void* gmem, bool valid) {
+  if (valid) memcpy(smem, gmem, 16); else memset(smem, 0, 16);
+}
+__device__ __forceinline__ void bw_cp_async_commit() {}
+template <int N> __device__ __forceinline__ void bw_cp_async_wait() {}
+#else
 __device__ __forceinline__ void bw_cp_async16(void* smem, const void* gmem, bool valid) {
   const int sz = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void bw_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bw_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 constexpr int kBwTile = 64;       // query rows per CTA (dq) / kv rows per CTA (dkv); also the tile of the streamed operand
 constexpr int kBwThreads = 128;   // 4 warps x 16 rows
@@ -87,7 +95,7 @@ attn_bwd_dq_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
                    int nkv, float scale, T* __restrict__ dq) {
   using SM = BwSmem<HD>;
   constexpr int LD = SM::LD, SLD = SM::SLD;
-  extern __shared__ __align__(128) uint8_t bw_smem[];
+  CTS_DYN_SMEM(bw_smem);
   T* q_s = reinterpret_cast<T*>(bw_smem);
   T* do_s = reinterpret_cast<T*>(bw_smem + SM::tile_bytes);
   T* ring = reinterpret_cast<T*>(bw_smem + SM::off_ring);                      // [2][K|V][64][LD]
@@ -226,7 +234,7 @@ attn_bwd_dkv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
                     int nkv, float scale, T* __restrict__ dk, T* __restrict__ dv) {
   using SM = BwSmem<HD>;
   constexpr int LD = SM::LD, SLD = SM::SLD;
-  extern __shared__ __align__(128) uint8_t bw_smem[];
+  CTS_DYN_SMEM(bw_smem);
   T* k_s = reinterpret_cast<T*>(bw_smem);
   T* v_s = reinterpret_cast<T*>(bw_smem + SM::tile_bytes);
   T* ring = reinterpret_cast<T*>(bw_smem + SM::off_ring);                      // [2][Q|dO][64][LD]

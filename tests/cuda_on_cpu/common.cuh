@@ -119,10 +119,17 @@ template <typename V> static inline V __shfl_up_sync(unsigned, V v, int d) { con
 template <typename V> static inline V __shfl_sync(unsigned, V v, int src) { return shim_shfl(v, src & 31); }
 
 void shim_run_block(const std::function<void()>& body, dim3 block);
+extern uint8_t* g_dyn_smem;                                // dynamic shared memory of the running launch
+void shim_set_dyn_smem(size_t bytes);
+#define CTS_DYN_SMEM(name) uint8_t* name = g_dyn_smem
+#define __align__(x)
+#define cudaFuncAttributeMaxDynamicSharedMemorySize 8
+template <typename F> static inline int cudaFuncSetAttribute(F, int, int) { return 0; }
 
 template <typename... KArgs, typename... Args>
-static inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t, void*, unsigned, Args... args) {
+static inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, void*, unsigned, Args... args) {
   auto tup = std::make_tuple(static_cast<KArgs>(args)...);
+  shim_set_dyn_smem(smem);
   g_gdim = {grid.x, grid.y, grid.z};
   g_bdim = {block.x, block.y, block.z};
   for (unsigned z = 0; z < grid.z; ++z)

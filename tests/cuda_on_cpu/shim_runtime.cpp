@@ -4,6 +4,12 @@
 #include <sys/mman.h>
 
 ShimBlock g_blk;
+uint8_t* g_dyn_smem = nullptr;
+void shim_set_dyn_smem(size_t bytes) {
+  static std::vector<uint8_t> buf;
+  buf.assign(bytes + 256, 0xCD);                           // poisoned: a kernel must not rely on zeroed shared memory
+  g_dyn_smem = (uint8_t*)(((uintptr_t)buf.data() + 127) & ~(uintptr_t)127);
+}
 ShimIdx g_tid, g_bid, g_bdim, g_gdim;
 
 // ---- fibers: swap the callee-saved registers and the stack pointer (System V x86-64)
@@ -132,3 +138,7 @@ bool cts_lora_wgrad_mma_enabled() { return false; }
 bool cts_lora_wgrad_mma_ok(const void*, long long, long long, int, long long, const void*, long long, long long, int) { return false; }
 int cts_lora_wgrad_mma_launch(cts_ctx*, const void*, long long, long long, int, long long, const void*, long long, long long, int, long long,
                               float, float*, long long, long long, int, void*) { return CTS_ERR_UNSUPPORTED; }
+
+// tcgen05 attention backward (attention_bwd_tc5.cu): not part of the shim build
+int cts_attn_bwd_tc5_launch(cts_ctx*, const void*, const void*, const void*, const void*, const float*, const float*, const int*, int, int,
+                            long long, int, int, float, void*, void*, void*, int, cudaStream_t) { return CTS_ERR_UNSUPPORTED; }

@@ -125,7 +125,10 @@ def test_attention_backward(d, lens):
     torch.cuda.synchronize()
     rq, rk, rv = torch.empty(T, nh * d, dtype=DT), torch.empty(T, nkv * d, dtype=DT), torch.empty(T, nkv * d, dtype=DT)
     DBL.attn_bwd(q, k, v, None, do, None, cu, len(lens), max(lens), nh, nkv, d, sc, None, rq, rk, rv)
-    eq, ek, ev = rel_err(dq, rq), rel_err(dk, rk), rel_err(dv, rv)
+    # a length-1 sequence has dQ = dK = 0 exactly (one key: P = 1, dP = delta); the kernels leave rounding noise of ~1e-7 there, so
+    # the denominator gets an absolute floor
+    err = lambda a, r: float((a.float().cpu() - r.float()).abs().max() / r.float().abs().max().clamp_min(1e-4))
+    eq, ek, ev = err(dq, rq), err(dk, rk), err(dv, rv)
     record("attn_bwd", d=d, lens=str(lens), dq=eq, dk=ek, dv=ev)
     for t_ in (dq, dk, dv):
         assert torch.isfinite(t_.float()).all()

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from tests.cabi_double import TorchDouble
-from tests.gpu_util import ctx, record, rel_err
+from tests.gpu_util import ctx, record
 
 DT = torch.bfloat16
 DBL = TorchDouble()
@@ -57,8 +57,10 @@ def test_attention_backward_tcgen05(lens, nh, nkv, dtype, monkeypatch):
         outs[flag] = (dq, dk, dv)
     rq, rk, rv = torch.empty(T, nh * d, dtype=dtype), torch.empty(T, nkv * d, dtype=dtype), torch.empty(T, nkv * d, dtype=dtype)
     DBL.attn_bwd(q, k, v, None, do, None, cu, len(lens), max(lens), nh, nkv, d, sc, None, rq, rk, rv)
-    errs = [rel_err(a, r_) for a, r_ in zip(outs["1"], (rq, rk, rv))]
-    cross = [rel_err(a, b_) for a, b_ in zip(outs["1"], outs["0"])]
+    # absolute floor in the denominator: a length-1 sequence has dQ = dK = 0 exactly and the kernels leave ~1e-7 of rounding noise there
+    err = lambda a, r_: float((a.float().cpu() - r_.float().cpu()).abs().max() / r_.float().abs().max().clamp_min(1e-4))
+    errs = [err(a, r_) for a, r_ in zip(outs["1"], (rq, rk, rv))]
+    cross = [err(a, b_) for a, b_ in zip(outs["1"], outs["0"])]
     record("attn_bwd_tc5", lens=str(lens), nh=nh, nkv=nkv, dq=errs[0], dk=errs[1], dv=errs[2], vs_hmma=max(cross))
     for t_ in outs["1"]:
         assert torch.isfinite(t_.float()).all()

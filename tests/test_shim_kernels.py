@@ -2,9 +2,11 @@
 "CUDA on CPU" shim (CUDA threads = fibers, __syncthreads / shuffles / atomics provided, blocks one after the other) and the
 product's own ctypes wrappers drive them on host memory:
 
-  * tools/shim_gpu_tests.py runs the GPU test cases of the sampling kernel, AdamW + clip, adapter packing (all still pending on a
-    B200) and -- as calibration of the shim itself -- the elementwise / cross-entropy / weight-gradient tests that already passed
-    on a B200;
+  * tools/shim_gpu_tests.py runs the GPU test cases of the sampling kernel, AdamW + clip, adapter packing, the attention backward
+    (attention_bwd.cu: wmma through a fragment shim) and -- in a HYBRID context where the tcgen05 GEMMs and the attention forward are
+    answered by the torch double -- the whole LoRA training step against the oracle (all still pending on a B200), plus, as
+    calibration of the shim itself, the elementwise / cross-entropy / weight-gradient tests that already passed on a B200
+    (the CPU suite runs the --quick subset; the full selection is 56 cases in about 4 minutes);
   * the low-latency all-reduce (allreduce_ll.cu) runs with its ranks as PROCESSES sharing the symmetric regions: real concurrency
     between ranks, torn 16-byte units, consecutive calls without any barrier in between.
 
@@ -21,10 +23,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_pending_and_validated_kernels_pass_their_gpu_tests_on_the_shim():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "shim_gpu_tests.py")], capture_output=True, text=True, timeout=850, cwd=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "shim_gpu_tests.py"), "--quick"], capture_output=True, text=True, timeout=850,
+                       cwd=ROOT)
     tail = r.stdout[-3000:] + r.stderr[-2000:]
     assert r.returncode == 0, tail
-    assert "17 passed" in r.stdout and "2 passed" in r.stdout and "21 passed" in r.stdout, tail
+    import re
+    passed = [int(n) for n in re.findall(r"(\d+) passed", r.stdout)]
+    assert len(passed) == 3 and min(passed) >= 7 and "failed" not in r.stdout, tail      # sampling, training (incl. one whole step), validated kernels
+    native = r.stdout.split("entry points running from kernel source:")[1].split("\n")[0].split()
+    assert {"sample_advance", "attn_bwd", "adamw", "grad_norm_clip", "lora_pack", "lora_wgrad", "ce_loss_grad", "rmsnorm_bwd", "swiglu_bwd",
+            "qkv_rope_bwd"} <= set(native), native
 
 
 def _expected(parts, split, resid, dt):
