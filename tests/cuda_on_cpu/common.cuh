@@ -10,6 +10,7 @@
 // Not a performance model, not a memory-model checker (x86 is stronger than PTX), never part of the product.
 #pragma once
 #include <math.h>
+#include <pthread.h>
 #include <sched.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -18,6 +19,7 @@
 #include <string.h>
 
 #include <functional>
+#include <thread>
 #include <tuple>
 #include <type_traits>
 #include <vector>
@@ -30,7 +32,8 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __cvta_generic_to_shared(p) ((uintptr_t)(p))
+#define __shared__ static thread_local          // one OS thread per CTA (its CUDA threads are fibers of that thread)
 #define __grid_constant__
 
 // ---------------------------------------------------------------------------------------------- vector types
@@ -72,9 +75,10 @@ struct ShimBlock {
   unsigned long named_gen[16] = {0};
   struct Warp { int alive = 0, arrived = 0; unsigned long gen = 0; uint64_t slot[32]; } warp[64];   // shuffles / __syncwarp
 };
-extern ShimBlock g_blk;
+extern thread_local ShimBlock g_blk;
 struct ShimIdx { unsigned x, y, z; };
-extern ShimIdx g_tid, g_bid, g_bdim, g_gdim;               // g_tid is swapped by the scheduler with every fiber switch
+extern thread_local ShimIdx g_tid, g_bid;                  // g_tid is swapped by the scheduler with every fiber switch
+extern ShimIdx g_bdim, g_gdim;
 #define threadIdx g_tid
 #define blockIdx g_bid
 #define blockDim g_bdim
@@ -119,25 +123,64 @@ template <typename V> static inline V __shfl_up_sync(unsigned, V v, int d) { con
 template <typename V> static inline V __shfl_sync(unsigned, V v, int src) { return shim_shfl(v, src & 31); }
 
 void shim_run_block(const std::function<void()>& body, dim3 block);
-extern uint8_t* g_dyn_smem;                                // dynamic shared memory of the running launch
+extern thread_local uint8_t* g_dyn_smem;                   // dynamic shared memory of the running CTA
+extern thread_local size_t g_dyn_bytes;
 void shim_set_dyn_smem(size_t bytes);
 #define CTS_DYN_SMEM(name) uint8_t* name = g_dyn_smem
 #define __align__(x)
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 8
 template <typename F> static inline int cudaFuncSetAttribute(F, int, int) { return 0; }
 
+// ---- thread-block clusters: the CTAs of one cluster run concurrently (one OS thread each); distributed shared memory is the
+// other CTAs' DYNAMIC shared memory (static __shared__ variables are not mappable here -- none of the shimmed kernels needs that)
+struct ShimCluster {
+  int size = 1;
+  uint8_t* dyn_base[16] = {nullptr};
+  pthread_barrier_t bar;
+};
+extern thread_local ShimCluster* g_cluster;
+extern thread_local int g_cluster_rank;
+namespace cooperative_groups {
+struct cluster_group {
+  void sync() const {                                      // every thread of every CTA: the CTA's fibers meet first, then the CTAs
+    __syncthreads();
+    if (g_cluster && g_cluster->size > 1 && shim_linear_tid() == 0) pthread_barrier_wait(&g_cluster->bar);
+    __syncthreads();
+  }
+  unsigned num_blocks() const { return g_cluster ? (unsigned)g_cluster->size : 1u; }
+  unsigned block_rank() const { return (unsigned)g_cluster_rank; }
+  template <typename V> V* map_shared_rank(V* p, unsigned r) const {
+    uint8_t* q = (uint8_t*)p;
+    if (q < g_dyn_smem || q >= g_dyn_smem + g_dyn_bytes + 1024) { fprintf(stderr, "shim: map_shared_rank of a non-dynamic shared address\n"); abort(); }
+    return (V*)(g_cluster->dyn_base[r] + (q - g_dyn_smem));
+  }
+};
+static inline cluster_group this_cluster() { return cluster_group(); }
+}  // namespace cooperative_groups
+
+void shim_launch(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem, dim3 cluster);
+
+// cudaLaunchKernelEx with the two attributes the library uses
+enum { cudaLaunchAttributeProgrammaticStreamSerialization = 1, cudaLaunchAttributeClusterDimension = 2 };
+struct cudaLaunchAttribute {
+  int id;
+  union { int programmaticStreamSerializationAllowed; struct { unsigned x, y, z; } clusterDim; } val;
+};
+struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes = 0; void* stream = nullptr; cudaLaunchAttribute* attrs = nullptr; unsigned numAttrs = 0; };
 template <typename... KArgs, typename... Args>
-static inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, void*, unsigned, Args... args) {
+static inline int cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kern)(KArgs...), Args... args) {
   auto tup = std::make_tuple(static_cast<KArgs>(args)...);
-  shim_set_dyn_smem(smem);
-  g_gdim = {grid.x, grid.y, grid.z};
-  g_bdim = {block.x, block.y, block.z};
-  for (unsigned z = 0; z < grid.z; ++z)
-    for (unsigned y = 0; y < grid.y; ++y)
-      for (unsigned x = 0; x < grid.x; ++x) {
-        g_bid = {x, y, z};
-        shim_run_block([&] { std::apply(kern, tup); }, block);
-      }
+  dim3 cl(1, 1, 1);
+  for (unsigned i = 0; i < cfg->numAttrs; ++i)
+    if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension) cl = dim3(cfg->attrs[i].val.clusterDim.x, cfg->attrs[i].val.clusterDim.y, cfg->attrs[i].val.clusterDim.z);
+  shim_launch([&] { std::apply(kern, tup); }, cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, cl);
+  return 0;
+}
+
+template <typename... KArgs, typename... Args>
+static inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, void*, unsigned cluster_x, Args... args) {
+  auto tup = std::make_tuple(static_cast<KArgs>(args)...);
+  shim_launch([&] { std::apply(kern, tup); }, grid, block, smem, dim3(cluster_x ? cluster_x : 1, 1, 1));
   return 0;
 }
 
@@ -196,6 +239,8 @@ int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);
 #define CTS_LAUNCH_CHECK(ctx) do { } while (0)
 
 static inline long long cdiv_ll(long long a, long long b) { return (a + b - 1) / b; }
+static inline uint32_t smem_u32(const void* p) { return (uint32_t)(uintptr_t)p; }
+struct CUtensorMap { const void* base; long long rows, cols, ld; int box_rows, is_bf16; };    // what the shimmed mainloop needs of a tensor map
 static inline void pdl_wait() {}
 static inline void pdl_trigger() {}
 

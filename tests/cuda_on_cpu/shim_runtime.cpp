@@ -3,14 +3,20 @@
 
 #include <sys/mman.h>
 
-ShimBlock g_blk;
-uint8_t* g_dyn_smem = nullptr;
+thread_local ShimBlock g_blk;
+thread_local uint8_t* g_dyn_smem = nullptr;
+thread_local size_t g_dyn_bytes = 0;
+thread_local ShimCluster* g_cluster = nullptr;
+thread_local int g_cluster_rank = 0;
+thread_local ShimIdx g_tid, g_bid;
+ShimIdx g_bdim, g_gdim;
+
 void shim_set_dyn_smem(size_t bytes) {
-  static std::vector<uint8_t> buf;
-  buf.assign(bytes + 256, 0xCD);                           // poisoned: a kernel must not rely on zeroed shared memory
+  static thread_local std::vector<uint8_t> buf;
+  buf.assign(bytes + 2048 + 256, 0xCD);                    // poisoned: a kernel must not rely on zeroed shared memory
   g_dyn_smem = (uint8_t*)(((uintptr_t)buf.data() + 127) & ~(uintptr_t)127);
+  g_dyn_bytes = bytes;
 }
-ShimIdx g_tid, g_bid, g_bdim, g_gdim;
 
 // ---- fibers: swap the callee-saved registers and the stack pointer (System V x86-64)
 extern "C" void shim_switch(void** save_sp, void* load_sp);
@@ -40,10 +46,10 @@ shim_switch:
 namespace {
 struct Fiber { void* sp; ShimIdx tid; bool done; };
 constexpr size_t kStack = 256 << 10;
-std::vector<Fiber> g_fibers;
-void* g_sched_sp = nullptr;
-int g_cur = -1;
-const std::function<void()>* g_body = nullptr;
+thread_local std::vector<Fiber> g_fibers;
+thread_local void* g_sched_sp = nullptr;
+thread_local int g_cur = -1;
+thread_local const std::function<void()>* g_body = nullptr;
 
 void fiber_main() {
   (*g_body)();
@@ -67,8 +73,8 @@ void shim_yield() {
 
 void shim_run_block(const std::function<void()>& body, dim3 block) {
   const int n = (int)(block.x * block.y * block.z);
-  static char* arena = nullptr;
-  static size_t arena_fibers = 0;
+  static thread_local char* arena = nullptr;
+  static thread_local size_t arena_fibers = 0;
   if ((size_t)n > arena_fibers) {
     if (arena) munmap(arena, arena_fibers * kStack);
     arena = (char*)mmap(nullptr, (size_t)n * kStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
@@ -108,6 +114,45 @@ void shim_run_block(const std::function<void()>& body, dim3 block) {
     }
   }
   g_cur = -1;
+}
+
+// grid = clusters one after the other; the CTAs of a cluster concurrently (one OS thread each; a cluster of 1 runs in the caller)
+void shim_launch(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem, dim3 cl) {
+  g_gdim = {grid.x, grid.y, grid.z};
+  g_bdim = {block.x, block.y, block.z};
+  const int csize = (int)(cl.x * cl.y * cl.z);
+  for (unsigned z = 0; z < grid.z; z += cl.z)
+    for (unsigned y = 0; y < grid.y; y += cl.y)
+      for (unsigned x = 0; x < grid.x; x += cl.x) {
+        if (csize == 1) {
+          g_bid = {x, y, z};
+          g_cluster = nullptr;
+          g_cluster_rank = 0;
+          shim_set_dyn_smem(smem);
+          shim_run_block(body, block);
+          continue;
+        }
+        ShimCluster cluster;
+        cluster.size = csize;
+        pthread_barrier_init(&cluster.bar, nullptr, (unsigned)csize);
+        pthread_barrier_t ready;                           // every CTA publishes its shared-memory base before any of them runs
+        pthread_barrier_init(&ready, nullptr, (unsigned)csize);
+        std::vector<std::thread> th;
+        for (int r = 0; r < csize; ++r)
+          th.emplace_back([&, r] {
+            const unsigned rx = (unsigned)r % cl.x, ry = ((unsigned)r / cl.x) % cl.y, rz = (unsigned)r / (cl.x * cl.y);
+            g_bid = {x + rx, y + ry, z + rz};
+            g_cluster = &cluster;
+            g_cluster_rank = r;
+            shim_set_dyn_smem(smem);
+            cluster.dyn_base[r] = g_dyn_smem;
+            pthread_barrier_wait(&ready);
+            shim_run_block(body, block);
+          });
+        for (auto& t : th) t.join();
+        pthread_barrier_destroy(&cluster.bar);
+        pthread_barrier_destroy(&ready);
+      }
 }
 
 int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...) {
