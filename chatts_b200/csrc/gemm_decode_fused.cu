@@ -53,6 +53,32 @@ struct FusedParams {
 
 // ---- wire format of the in-kernel all-reduce (shared with allreduce_ll.cu): the epoch travels inside every 8-byte word
 constexpr unsigned kPeerSpinLimit = 1u << 24;
+#ifdef CTS_HOST_SHIM      // tests/cuda_on_cpu: the same wire format on the host (8-byte halves written / read separately; ranks are processes)
+__device__ __forceinline__ void st_ll16(void* p, uint32_t d0, uint32_t d1, uint32_t epoch) {
+  volatile uint64_t* q = reinterpret_cast<volatile uint64_t*>(p);
+  q[0] = (uint64_t)d0 | ((uint64_t)epoch << 32);
+  sched_yield();
+  q[1] = (uint64_t)d1 | ((uint64_t)epoch << 32);
+}
+__device__ __forceinline__ uint4 ld_ll16(const void* p) {
+  const volatile uint64_t* q = reinterpret_cast<const volatile uint64_t*>(p);
+  const uint64_t a = q[0], b = q[1];
+  shim_yield();
+  static thread_local unsigned n = 0;
+  if ((++n & 255u) == 0) sched_yield();
+  return uint4{(uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32)};
+}
+__device__ __forceinline__ void st_ll8(void* p, uint32_t d, uint32_t epoch) {
+  *reinterpret_cast<volatile uint64_t*>(p) = (uint64_t)d | ((uint64_t)epoch << 32);
+}
+__device__ __forceinline__ uint2 ld_ll8(const void* p) {
+  const uint64_t a = *reinterpret_cast<const volatile uint64_t*>(p);
+  shim_yield();
+  static thread_local unsigned n = 0;
+  if ((++n & 255u) == 0) sched_yield();
+  return uint2{(uint32_t)a, (uint32_t)(a >> 32)};
+}
+#else
 __device__ __forceinline__ void st_ll16(void* p, uint32_t d0, uint32_t d1, uint32_t epoch) {
   asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(d0), "r"(epoch), "r"(d1), "r"(epoch) : "memory");
 }
@@ -69,6 +95,7 @@ __device__ __forceinline__ uint2 ld_ll8(const void* p) {
   asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
+#endif
 __device__ void peer_timeout(const char* what, int rank) {
   printf("chatts_b200: fused GEMM + all-reduce timed out in %s on rank %d (block %d,%d thread %d)\n", what, rank, blockIdx.x, blockIdx.z,
          threadIdx.x);
@@ -82,7 +109,7 @@ template <typename T> __device__ __forceinline__ uint32_t pack_pair(float a, flo
 template <typename T, int BN, bool NORM_IN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const FusedParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  CTS_DYN_SMEM(smem_raw);
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
   __shared__ uint64_t acc_bar;
@@ -112,6 +139,41 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
   const int nkb = kb1 - kb0;
   const int T_ = (int)p.t;
 
+#ifdef CTS_HOST_SHIM
+  // tests/cuda_on_cpu: the TMA -> tcgen05 -> TMEM mainloop and the TMEM read-back (part A) cannot run on a CPU; they are replaced by
+  // the value they produce -- this split's fp32 partial tile in part_s, accumulated over ITS K range -- so that everything from the
+  // cluster barrier on (the distributed-shared-memory reduction, the three tails, the in-kernel all-reduce) runs as written.
+  pdl_trigger();
+  pdl_wait();
+  (void)stages;
+  if (warp >= 2) {
+    const int ft = (warp & 3) * 32 + lane;
+    const long long f = (long long)f0 + ft;
+    const T* wrow = reinterpret_cast<const T*>(tm_w.base) + f * tm_w.ld;
+    const long long k0 = (long long)kb0 * kBK, k1 = (long long)kb1 * kBK < p.k ? (long long)kb1 * kBK : p.k;
+    for (int t = 0; t < T_; ++t) {
+      float acc = 0.f;
+      if (f < p.n) {
+        float rstd = 0.f;
+        if (NORM_IN) {
+          float tot = 0.f;
+          for (int j = 0; j < p.ssq_tiles; ++j) tot += p.ssq_in[(long long)t * p.ssq_tiles + j];
+          rstd = 1.0f / sqrtf(tot / (float)p.k + p.norm_eps);
+        }
+        for (long long k = k0; k < k1; ++k) {
+          float x;
+          if (NORM_IN)
+            x = rnd<T>(DT<T>::to_f(reinterpret_cast<const T*>(p.norm_w)[k]) *
+                       rnd<T>(DT<T>::to_f(reinterpret_cast<const T*>(p.norm_h)[(long long)t * p.k + k]) * rstd));
+          else
+            x = DT<T>::to_f(reinterpret_cast<const T*>(tm_x.base)[(long long)t * tm_x.ld + k]);
+          acc += DT<T>::to_f(wrow[k]) * x;
+        }
+      }
+      part_s[t * kBM + ft] = acc;
+    }
+  }
+#else
   pdl_trigger();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_w);
@@ -232,6 +294,7 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
     }
     tc_fence_before();
   }
+#endif
   __syncthreads();
   cluster.sync();                                            // every split's tile is in its CTA's shared memory
 
@@ -434,9 +497,11 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
     }
   }
   cluster.sync();                                            // nobody leaves while a peer still reads its tile
+#ifndef CTS_HOST_SHIM
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<kCols>(tmem_base);
+#endif
   if (p.peer_region != nullptr && threadIdx.x == 0) {        // the last CTA of the grid to finish publishes the next epoch
     __threadfence();
     const int done = atomicAdd(&p.peer_state[1], 1) + 1;

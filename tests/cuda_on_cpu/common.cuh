@@ -150,6 +150,7 @@ struct cluster_group {
   unsigned num_blocks() const { return g_cluster ? (unsigned)g_cluster->size : 1u; }
   unsigned block_rank() const { return (unsigned)g_cluster_rank; }
   template <typename V> V* map_shared_rank(V* p, unsigned r) const {
+    if (g_cluster == nullptr || g_cluster->size == 1) return p;           // a cluster of one: rank 0 is this CTA
     uint8_t* q = (uint8_t*)p;
     if (q < g_dyn_smem || q >= g_dyn_smem + g_dyn_bytes + 1024) { fprintf(stderr, "shim: map_shared_rank of a non-dynamic shared address\n"); abort(); }
     return (V*)(g_cluster->dyn_base[r] + (q - g_dyn_smem));
@@ -223,6 +224,7 @@ static inline const char* cudaGetErrorString(int) { return "shim"; }
 struct cts_ctx {
   int device;
   int sm_count;
+  int decode_stages;
   char err[512];
 };
 int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);

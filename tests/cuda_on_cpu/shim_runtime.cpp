@@ -13,8 +13,10 @@ ShimIdx g_bdim, g_gdim;
 
 void shim_set_dyn_smem(size_t bytes) {
   static thread_local std::vector<uint8_t> buf;
-  buf.assign(bytes + 2048 + 256, 0xCD);                    // poisoned: a kernel must not rely on zeroed shared memory
-  g_dyn_smem = (uint8_t*)(((uintptr_t)buf.data() + 127) & ~(uintptr_t)127);
+  buf.assign(bytes + 4096, 0xCD);                          // poisoned: a kernel must not rely on zeroed shared memory
+  // 1024-aligned in EVERY CTA: on the GPU all CTAs see the same shared-memory window, so a kernel's own alignment arithmetic gives the
+  // same offset everywhere -- distributed-shared-memory addressing relies on that
+  g_dyn_smem = (uint8_t*)(((uintptr_t)buf.data() + 1023) & ~(uintptr_t)1023);
   g_dyn_bytes = bytes;
 }
 
@@ -171,6 +173,7 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
   cts_ctx* c = new cts_ctx();
   c->device = device;
   c->sm_count = 148;
+  c->decode_stages = 96;
   c->err[0] = 0;
   *out = c;
   return CTS_OK;

@@ -93,3 +93,151 @@ def test_ll_allreduce_kernel_with_ranks_as_processes(W, T, h, split, dt):
             assert torch.equal(log_n[r][n], log_n[0][n]), f"call {n}: norm_out differs between ranks 0 and {r}"
         assert float((log_n[0][n].float() - want).abs().max() / want.abs().max()) < 1.2e-2
     assert [int(s[0]) for s in state] == [len(calls)] * W    # the epoch advanced once per call on every rank
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# gemm_decode_fused.cu through the shim: the TMA -> tcgen05 -> TMEM mainloop is replaced (inside the kernel, #ifdef CTS_HOST_SHIM) by
+# the fp32 partial tile it produces; from the cluster barrier on the kernel runs AS WRITTEN: the K splits of a tile as the CTAs of
+# one cluster (threads here), the distributed-shared-memory reduction in split order, the three tails, the fused RMSNorm operand,
+# and the in-kernel all-reduce with ranks as processes.  Reference: the torch double's statement of the two-launch path.  The
+# partial sums are accumulated in a different order than torch's matmul, so outputs may differ by one ulp of the model dtype.
+# ---------------------------------------------------------------------------------------------------------------------------
+DT = torch.bfloat16
+
+
+def _rn(g, *shape, std=1.0):
+    return (torch.randn(*shape, generator=g) * std).to(DT)
+
+
+def _close(a, r, ulps=2.0):
+    a, r = a.float(), r.float()
+    return float((a - r).abs().max()) <= ulps * 2 ** -8 * float(r.abs().max()) + 1e-6
+
+
+@pytest.fixture(scope="module")
+def shim_ctx():
+    from tests.cuda_on_cpu.shim import shim_context
+    return shim_context()
+
+
+@pytest.mark.parametrize("t,n,k,s", [(1, 256, 512, 2), (8, 640, 1024, 7), (32, 384, 704, 4), (17, 200, 640, 3)])
+def test_fused_residual_tail_and_tile_statistics(shim_ctx, t, n, k, s):
+    from tests.cabi_double import TorchDouble
+    g = torch.Generator().manual_seed(t + n + k)
+    x, w, h0 = _rn(g, t, k, std=0.5), _rn(g, n, k, std=0.05), _rn(g, t, n, std=0.5)
+    tiles = (n + 127) // 128
+    out, ssq = h0.clone(), torch.full((t, tiles), float("nan"))
+    shim_ctx.gemm_decode_fused(x, w, 0, s, t, h=out, ssq_out=ssq)
+    ref, rssq = h0.clone(), torch.zeros(t, tiles)
+    TorchDouble().gemm_decode_fused(x, w, 0, s, t, h=ref, ssq_out=rssq)
+    assert _close(out, ref)
+    pad = torch.zeros(t, tiles * 128)
+    pad[:, :n] = out.float() ** 2
+    assert torch.allclose(ssq, pad.view(t, tiles, 128).sum(-1), rtol=1e-5, atol=1e-6)      # the statistic of what was actually written
+
+
+@pytest.mark.parametrize("t,inter,k,s", [(1, 128, 256, 1), (8, 704, 512, 2), (32, 192, 640, 5)])
+def test_fused_swiglu_tail(shim_ctx, t, inter, k, s):
+    from tests.cabi_double import TorchDouble
+    g = torch.Generator().manual_seed(t + inter)
+    x, w = _rn(g, t, k, std=0.5), _rn(g, 2 * inter, k, std=0.05)
+    out, ref = torch.full((t, inter), float("nan"), dtype=DT), torch.empty(t, inter, dtype=DT)
+    shim_ctx.gemm_decode_fused(x, w, 1, s, t, act=out)
+    TorchDouble().gemm_decode_fused(x, w, 1, s, t, act=ref)
+    assert _close(out, ref, ulps=3.0)
+
+
+@pytest.mark.parametrize("d,nh,nkv,qk,bias", [(128, 4, 2, False, True), (128, 2, 1, True, False), (64, 4, 2, False, True), (64, 5, 1, True, False)])
+@pytest.mark.parametrize("t,s", [(1, 5), (9, 3)])
+def test_fused_qkv_rope_tail(shim_ctx, d, nh, nkv, qk, bias, t, s):
+    from tests.cabi_double import TorchDouble
+    g = torch.Generator().manual_seed(d + nh + t)
+    H, page, pages = 512, 16, 4
+    N = (nh + 2 * nkv) * d
+    x, w = _rn(g, t, H, std=0.5), _rn(g, N, H, std=0.05)
+    b = _rn(g, N, std=0.2) if bias else None
+    qn = (torch.rand(d, generator=g) + 0.5).to(DT) if qk else None
+    kn = (torch.rand(d, generator=g) + 0.5).to(DT) if qk else None
+    pos = torch.randint(0, 100, (t,), generator=g).to(torch.int32)
+    ang = torch.rand(128, d // 2, generator=g) * 6.28
+    cos, sin = ang.cos().to(DT), ang.sin().to(DT)
+    slot = torch.randperm(pages * page, generator=g)[:t].to(torch.int32)
+    if t > 2:
+        slot[1] = -1
+    outs = []
+    for c in (shim_ctx, TorchDouble()):
+        q = torch.full((t, nh * d), float("nan"), dtype=DT)
+        kc, vc = torch.zeros(pages, nkv, page, d, dtype=DT), torch.zeros(pages, nkv, page, d, dtype=DT)
+        c.gemm_decode_fused(x, w, 2, s, t, bias=b, positions=pos, cos=cos, sin=sin, slot_map=slot, q_out=q, k_cache=kc, v_cache=vc, q_norm=qn,
+                            k_norm=kn, eps=1e-6, nh=nh, nkv=nkv, head_dim=d, page_size=page)
+        outs.append((q, kc, vc))
+    for a, r in zip(outs[0], outs[1]):
+        assert _close(a, r, ulps=4.0)
+    assert bool((outs[0][1] != 0).any()) and bool((outs[0][2] != 0).any())               # the KV pages were written
+
+
+def test_fused_rmsnorm_operand(shim_ctx):
+    """NORM_IN: the token operand is RMSNorm(h) built from the per-tile sums of squares of the previous RESIDUAL call."""
+    from tests.cabi_double import TorchDouble
+    g = torch.Generator().manual_seed(5)
+    t, H, inter = 6, 256, 192
+    h = _rn(g, t, H, std=0.7)
+    nw = (1.0 + 0.1 * torch.randn(H, generator=g)).to(DT)
+    w = _rn(g, 2 * inter, H, std=0.05)
+    ssq = (h.float() ** 2).view(t, H // 128, 128).sum(-1)
+    out, ref = torch.empty(t, inter, dtype=DT), torch.empty(t, inter, dtype=DT)
+    shim_ctx.gemm_decode_fused(None, w, 1, 2, t, act=out, norm_h=h, norm_w=nw, ssq_in=ssq, norm_eps=1e-6)
+    TorchDouble().gemm_decode_fused(None, w, 1, 2, t, act=ref, norm_h=h, norm_w=nw, ssq_in=ssq, norm_eps=1e-6)
+    assert _close(out, ref, ulps=3.0)
+
+
+@pytest.mark.parametrize("W,T,N,Kr,S", [(2, 3, 256, 128, 1), (2, 7, 512, 320, 2), (4, 5, 512, 256, 3)])
+def test_fused_gemm_allreduce_tail_with_ranks_as_processes(shim_ctx, W, T, N, Kr, S):
+    """The tensor-parallel tail of CTS_FUSED_RESIDUAL: every rank's cluster scatters its (tile, token) partial to the tile's owner, the
+    owner adds in rank order + residual and broadcasts h and the tile statistic.  Ranks = processes sharing the regions, the CTAs of
+    a cluster = threads, CUDA threads = fibers; three calls back to back over alternating buffer sets."""
+    c = shim_ctx
+    tmax = 8
+    nbytes = tmax * N * 12 + tmax * (N // 128) * 8 + 64
+    g = torch.Generator().manual_seed(W * 10 + T)
+    share = lambda x: x.share_memory_()
+    regions = [[share(torch.zeros((nbytes + 3) // 4, dtype=torch.int32)) for _ in range(W)] for _ in range(2)]
+    ptrs = [share(torch.tensor([r.data_ptr() for r in regions[b]], dtype=torch.int64)) for b in range(2)]
+    state = [share(torch.zeros(2, dtype=torch.int32)) for _ in range(W)]
+    calls = [0, 1, 0]
+    h0 = _rn(g, T, N, std=0.5)
+    xs = [[share(_rn(g, T, Kr, std=0.5)) for _ in range(W)] for _ in calls]
+    ws = [[share(_rn(g, N, Kr, std=0.05)) for _ in range(W)] for _ in calls]
+    hs = [share(h0.clone()) for _ in range(W)]
+    ssq = [share(torch.zeros(T, N // 128)) for _ in range(W)]
+    log_h = [share(torch.zeros(len(calls), T, N, dtype=DT)) for _ in range(W)]
+    log_s = [share(torch.zeros(len(calls), T, N // 128)) for _ in range(W)]
+    pids = []
+    for r in range(W):
+        pid = os.fork()
+        if pid == 0:
+            try:
+                import signal
+                signal.alarm(150)
+                for n, which in enumerate(calls):
+                    c.gemm_decode_fused(xs[n][r], ws[n][r], 0, S, T, h=hs[r], ssq_out=ssq[r], peer=(ptrs[which], nbytes, state[r], r, W, tmax))
+                    log_h[r][n].copy_(hs[r])
+                    log_s[r][n].copy_(ssq[r])
+                os._exit(0)
+            except BaseException:
+                import traceback
+                traceback.print_exc()
+                os._exit(1)
+        pids.append(pid)
+    codes = [os.waitpid(p, 0)[1] for p in pids]
+    assert codes == [0] * W, codes
+    cur = h0.clone()
+    for n in range(len(calls)):
+        acc = sum(xs[n][r].float() @ ws[n][r].float().t() for r in range(W))
+        cur_ref = (cur.float() + acc.to(DT).float()).to(DT)
+        for r in range(W):
+            assert torch.equal(log_h[r][n], log_h[0][n]) and torch.equal(log_s[r][n], log_s[0][n]), f"call {n}: rank {r} differs from rank 0"
+        assert _close(log_h[0][n], cur_ref, ulps=3.0), f"call {n}"
+        assert torch.allclose(log_s[0][n], (log_h[0][n].float() ** 2).view(T, N // 128, 128).sum(-1), rtol=1e-5)
+        cur = log_h[0][n].clone()                            # follow the kernel's own h (an ulp may differ from the reference chain)
+    assert [int(s_[0]) for s_ in state] == [len(calls)] * W
