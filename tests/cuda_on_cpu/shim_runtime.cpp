@@ -118,11 +118,31 @@ void shim_run_block(const std::function<void()>& body, dim3 block) {
   g_cur = -1;
 }
 
+// kernels whose CTAs wait for each other WITHOUT being a cluster (the low-latency all-reduce with several sub-slices per token): the
+// test asks for the whole grid to run concurrently, one OS thread per CTA
+static int g_concurrent_grid = 0;
+extern "C" void shim_concurrent_grid(int on) { g_concurrent_grid = on; }
+
 // grid = clusters one after the other; the CTAs of a cluster concurrently (one OS thread each; a cluster of 1 runs in the caller)
 void shim_launch(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem, dim3 cl) {
   g_gdim = {grid.x, grid.y, grid.z};
   g_bdim = {block.x, block.y, block.z};
   const int csize = (int)(cl.x * cl.y * cl.z);
+  if (g_concurrent_grid && csize == 1 && grid.x * grid.y * grid.z <= 64) {
+    std::vector<std::thread> th;
+    for (unsigned z = 0; z < grid.z; ++z)
+      for (unsigned y = 0; y < grid.y; ++y)
+        for (unsigned x = 0; x < grid.x; ++x)
+          th.emplace_back([&, x, y, z] {
+            g_bid = {x, y, z};
+            g_cluster = nullptr;
+            g_cluster_rank = 0;
+            shim_set_dyn_smem(smem);
+            shim_run_block(body, block);
+          });
+    for (auto& t : th) t.join();
+    return;
+  }
   for (unsigned z = 0; z < grid.z; z += cl.z)
     for (unsigned y = 0; y < grid.y; y += cl.y)
       for (unsigned x = 0; x < grid.x; x += cl.x) {

@@ -45,10 +45,14 @@ def _expected(parts, split, resid, dt):
     return (resid.float() + acc.to(dt).float()).to(dt)
 
 
-@pytest.mark.parametrize("W,T,h,split,dt", [(2, 3, 256, 2, torch.bfloat16), (4, 2, 512, 1, torch.float16), (2, 1, 128, 3, torch.bfloat16)])
+@pytest.mark.parametrize("W,T,h,split,dt", [(2, 3, 256, 2, torch.bfloat16), (4, 2, 512, 1, torch.float16), (2, 1, 128, 3, torch.bfloat16),
+                                            (2, 2, 1024, 2, torch.bfloat16), (4, 3, 1024, 1, torch.bfloat16)])
 def test_ll_allreduce_kernel_with_ranks_as_processes(W, T, h, split, dt):
     from tests.cuda_on_cpu.shim import shim_context
     c = shim_context()
+    # h / W >= 256 columns: the kernel splits every owner's chunk over several CTAs per token, which wait for each other's statistics
+    # (not a cluster) -> the shim runs the whole grid concurrently
+    c.lib.shim_concurrent_grid(1 if h // W >= 256 else 0)
     tmax, calls = 4, [0, 1, 0, 0, 1]                         # buffer set per call (one repeated set: allowed, see the protocol test)
     nbytes = c.peer_ll_region_bytes(W, tmax, h)
     g = torch.Generator().manual_seed(W * 100 + h)
@@ -82,6 +86,7 @@ def test_ll_allreduce_kernel_with_ranks_as_processes(W, T, h, split, dt):
                 os._exit(1)
         pids.append(pid)
     codes = [os.waitpid(p, 0)[1] for p in pids]
+    c.lib.shim_concurrent_grid(0)
     assert codes == [0] * W, codes
     cur = h0.clone()
     for n in range(len(calls)):
