@@ -139,41 +139,6 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
   const int nkb = kb1 - kb0;
   const int T_ = (int)p.t;
 
-#ifdef CTS_HOST_SHIM
-  // tests/cuda_on_cpu: the TMA -> tcgen05 -> TMEM mainloop and the TMEM read-back (part A) cannot run on a CPU; they are replaced by
-  // the value they produce -- this split's fp32 partial tile in part_s, accumulated over ITS K range -- so that everything from the
-  // cluster barrier on (the distributed-shared-memory reduction, the three tails, the in-kernel all-reduce) runs as written.
-  pdl_trigger();
-  pdl_wait();
-  (void)stages;
-  if (warp >= 2) {
-    const int ft = (warp & 3) * 32 + lane;
-    const long long f = (long long)f0 + ft;
-    const T* wrow = reinterpret_cast<const T*>(tm_w.base) + f * tm_w.ld;
-    const long long k0 = (long long)kb0 * kBK, k1 = (long long)kb1 * kBK < p.k ? (long long)kb1 * kBK : p.k;
-    for (int t = 0; t < T_; ++t) {
-      float acc = 0.f;
-      if (f < p.n) {
-        float rstd = 0.f;
-        if (NORM_IN) {
-          float tot = 0.f;
-          for (int j = 0; j < p.ssq_tiles; ++j) tot += p.ssq_in[(long long)t * p.ssq_tiles + j];
-          rstd = 1.0f / sqrtf(tot / (float)p.k + p.norm_eps);
-        }
-        for (long long k = k0; k < k1; ++k) {
-          float x;
-          if (NORM_IN)
-            x = rnd<T>(DT<T>::to_f(reinterpret_cast<const T*>(p.norm_w)[k]) *
-                       rnd<T>(DT<T>::to_f(reinterpret_cast<const T*>(p.norm_h)[(long long)t * p.k + k]) * rstd));
-          else
-            x = DT<T>::to_f(reinterpret_cast<const T*>(tm_x.base)[(long long)t * tm_x.ld + k]);
-          acc += DT<T>::to_f(wrow[k]) * x;
-        }
-      }
-      part_s[t * kBM + ft] = acc;
-    }
-  }
-#else
   pdl_trigger();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_w);
@@ -294,7 +259,6 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
     }
     tc_fence_before();
   }
-#endif
   __syncthreads();
   cluster.sync();                                            // every split's tile is in its CTA's shared memory
 
@@ -497,11 +461,9 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
     }
   }
   cluster.sync();                                            // nobody leaves while a peer still reads its tile
-#ifndef CTS_HOST_SHIM
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<kCols>(tmem_base);
-#endif
   if (p.peer_region != nullptr && threadIdx.x == 0) {        // the last CTA of the grid to finish publishes the next epoch
     __threadfence();
     const int done = atomicAdd(&p.peer_state[1], 1) + 1;

@@ -209,6 +209,9 @@ static inline int __float_as_int(float f) { return (int)shim_f2u(f); }
 template <typename V> static inline V __ldg(const V* p) { return *p; }
 template <typename V> static inline V __ldcv(const V* p) { return *p; }
 template <typename V> static inline V __ldcs(const V* p) { return *p; }
+template <typename V> static inline V __ldcg(const V* p) { return *p; }
+template <typename V> static inline void __stcg(V* p, V v) { *p = v; }
+template <typename V> static inline void __stcs(V* p, V v) { *p = v; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline long long min(long long a, long long b) { return a < b ? a : b; }
@@ -224,7 +227,7 @@ static inline const char* cudaGetErrorString(int) { return "shim"; }
 struct cts_ctx {
   int device;
   int sm_count;
-  int decode_stages;
+  int decode_stages, l2_prefetch_mb, no_persistent_gemm, force_wmma_attention, norm_cluster, max_smem_optin;
   char err[512];
 };
 int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);
@@ -241,8 +244,6 @@ int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);
 #define CTS_LAUNCH_CHECK(ctx) do { } while (0)
 
 static inline long long cdiv_ll(long long a, long long b) { return (a + b - 1) / b; }
-static inline uint32_t smem_u32(const void* p) { return (uint32_t)(uintptr_t)p; }
-struct CUtensorMap { const void* base; long long rows, cols, ld; int box_rows, is_bf16; };    // what the shimmed mainloop needs of a tensor map
 static inline void pdl_wait() {}
 static inline void pdl_trigger() {}
 
@@ -276,3 +277,115 @@ static inline float warp_max(float v) {
 }
 static inline float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 static inline float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+// ================================================================================================================================
+// Functional emulation of the Blackwell pieces the tensor-core kernels use: mbarrier (arrive / expect_tx / complete_tx / parity wait),
+// TMA tile loads and stores (128-byte swizzle or dense boxes, zero fill / clipping at the tensor edge), TMEM (128 lanes x 512 fp32
+// columns per CTA), tcgen05.mma kind::f16 with cta_group::1 (shared-memory matrix descriptors decoded: K-major and MN-major operands,
+// 128-byte swizzle applied on the ADDRESS bits as the hardware does), tcgen05.ld 32x32b and tcgen05.commit.  Everything completes
+// synchronously at issue, so this checks what the kernels COMPUTE and that their barrier protocols are live, not asynchrony hazards.
+// The semantics encoded here are calibrated by running the GPU-validated kernels of gemm_tcgen05.cu through them.
+// ================================================================================================================================
+#include <unordered_map>
+static inline uint32_t smem_u32(const void* p) { return (uint32_t)(uintptr_t)p; }
+struct CUtensorMap { const void* base; long long rows, cols, ld; int box_rows, box_cols, swizzled, is_bf16; };
+
+struct ShimMbar { int count = 0, pending = 0; long long tx = 0; unsigned long phases = 0; };
+extern thread_local std::unordered_map<const void*, ShimMbar> g_mbar;
+static inline void shim_mbar_check(ShimMbar& b) { if (b.pending == 0 && b.tx == 0) { ++b.phases; b.pending = b.count; } }
+static inline void mbar_init(uint64_t* bar, uint32_t count) { ShimMbar& b = g_mbar[bar]; b = ShimMbar(); b.count = b.pending = (int)count; }
+static inline void fence_mbar_init() {}
+static inline void fence_proxy_async_smem() {}
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { ShimMbar& b = g_mbar[bar]; b.tx += bytes; --b.pending; shim_mbar_check(b); }
+static inline void mbar_arrive(uint64_t* bar) { ShimMbar& b = g_mbar[bar]; --b.pending; shim_mbar_check(b); }
+static inline void shim_mbar_complete_tx(uint64_t* bar, long long bytes) { ShimMbar& b = g_mbar[bar]; b.tx -= bytes; shim_mbar_check(b); }
+static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return (g_mbar[bar].phases & 1u) != parity; }
+#define CTS_WAIT_LIMIT (1u << 22)
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++n > CTS_WAIT_LIMIT) { printf("shim: mbarrier wait timed out (block %u,%u,%u thread %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+    shim_yield();
+  }
+}
+#define CTS_L2_EVICT_NORMAL 0x1000000000000000ull
+#define CTS_L2_EVICT_FIRST 0x12F0000000000000ull
+#define CTS_L2_EVICT_LAST 0x14F0000000000000ull
+
+static inline uint8_t* shim_swz128(uint8_t* p) { return (uint8_t*)((uintptr_t)p ^ ((((uintptr_t)p >> 7) & 7) << 4)); }
+static inline void shim_tma_copy(uint8_t* smem, const CUtensorMap* tm, int c0, int c1, bool to_smem) {
+  for (int r = 0; r < tm->box_rows; ++r)
+    for (int c = 0; c < tm->box_cols; ++c) {
+      const long long row = (long long)c1 + r, col = (long long)c0 + c;
+      const bool in = row >= 0 && row < tm->rows && col >= 0 && col < tm->cols;
+      uint8_t* sp = tm->swizzled ? shim_swz128(smem + (size_t)r * 128 + (size_t)c * 2) : smem + ((size_t)r * tm->box_cols + c) * 2;
+      uint16_t* gp = (uint16_t*)tm->base + row * tm->ld + col;
+      if (to_smem) *(uint16_t*)sp = in ? *gp : (uint16_t)0;
+      else if (in) *gp = *(uint16_t*)sp;
+    }
+}
+static inline void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint64_t) {
+  shim_tma_copy((uint8_t*)smem_dst, tm, c0, c1, true);
+  shim_mbar_complete_tx(bar, (long long)tm->box_rows * tm->box_cols * 2);
+}
+static inline void tma_load_2d_nohint(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) { tma_load_2d(smem_dst, tm, bar, c0, c1, 0); }
+static inline void tma_prefetch_l2_2d(const CUtensorMap*, int, int) {}
+static inline void tma_prefetch_desc(const CUtensorMap*) {}
+static inline void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) { shim_tma_copy((uint8_t*)smem_src, tm, c0, c1, false); }
+static inline void tma_store_commit() {}
+static inline void tma_store_wait_read0() {}
+static inline void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { memcpy(smem_dst, gsrc, bytes); shim_mbar_complete_tx(bar, bytes); }
+static inline bool elect_one() { return (shim_linear_tid() & 31) == 0; }
+static inline void tc_fence_before() {}
+static inline void tc_fence_after() {}
+
+extern thread_local float g_tmem[128][512];
+template <int kCols> static inline void tmem_alloc(uint32_t* smem_slot) { *smem_slot = 0; }
+template <int kCols> static inline void tmem_dealloc(uint32_t) {}
+static inline uint8_t* shim_smem_ptr(uint32_t addr18) {                           // 18-bit shared-window address -> this CTA's dynamic shared memory
+  return g_dyn_smem + ((addr18 - ((uint32_t)(uintptr_t)g_dyn_smem & 0x3FFFFu)) & 0x3FFFFu);
+}
+static inline float shim_ld_elem(const uint8_t* p, bool bf16) {
+  uint16_t v = *(const uint16_t*)shim_swz128((uint8_t*)p);
+  if (bf16) return shim_u2f((uint32_t)v << 16);
+  __half h; h.bits = v; return __half2float(h);
+}
+// operand element (r, k): r = row of A (M) or of B (N); major 0 = K-major (rows of 128 B), 1 = MN-major (the r index is contiguous)
+static inline float shim_operand(uint64_t desc, int major, int r, int k, bool bf16) {
+  const uint32_t start = (uint32_t)(desc & 0x3FFF) << 4, lbo = (uint32_t)((desc >> 16) & 0x3FFF) << 4, sbo = (uint32_t)((desc >> 32) & 0x3FFF) << 4;
+  if (((desc >> 61) & 7) != 2) { printf("shim: only SWIZZLE_128B shared-memory descriptors are emulated\n"); __trap(); }
+  const uint8_t* base = shim_smem_ptr(start);
+  const size_t off = major == 0 ? (size_t)(r / 8) * sbo + (size_t)(r % 8) * 128 + (size_t)k * 2
+                                : (size_t)(r / 64) * lbo + (size_t)(k / 8) * sbo + (size_t)(k % 8) * 128 + (size_t)(r % 64) * 2;
+  return shim_ld_elem(base + off, bf16);
+}
+static inline void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
+  const int a_major = (int)((idesc >> 15) & 1), b_major = (int)((idesc >> 16) & 1);
+  const bool bf16 = ((idesc >> 7) & 7) == 1;
+  if (M != 128) { printf("shim: tcgen05.mma with M = %d is not emulated\n", M); __trap(); }
+  const int lane0 = (int)(d_tmem >> 16), col0 = (int)(d_tmem & 0xFFFF);
+  static thread_local float A[128][16], B[256][16];
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < 16; ++k) A[m][k] = shim_operand(a_desc, a_major, m, k, bf16);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < 16; ++k) B[n][k] = shim_operand(b_desc, b_major, n, k, bf16);
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float acc = accumulate ? g_tmem[lane0 + m][col0 + n] : 0.f;
+      for (int k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
+      g_tmem[lane0 + m][col0 + n] = acc;
+    }
+}
+static inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }            // every MMA has completed at issue
+static inline void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) {
+  const int lane = (int)(taddr >> 16) + (shim_linear_tid() & 31), col = (int)(taddr & 0xFFFF);
+  for (int j = 0; j < 16; ++j) v[j] = shim_f2u(g_tmem[lane][col + j]);
+}
+static inline void tmem_ld_wait() {}
+static inline uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+constexpr uint32_t umma_idesc_f16(int is_bf16, int n, int m) {
+  return (1u << 4) | ((uint32_t)(is_bf16 ? 1 : 0) << 7) | ((uint32_t)(is_bf16 ? 1 : 0) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}

@@ -4,6 +4,8 @@
 #include <sys/mman.h>
 
 thread_local ShimBlock g_blk;
+thread_local std::unordered_map<const void*, ShimMbar> g_mbar;
+thread_local float g_tmem[128][512];
 thread_local uint8_t* g_dyn_smem = nullptr;
 thread_local size_t g_dyn_bytes = 0;
 thread_local ShimCluster* g_cluster = nullptr;
@@ -194,6 +196,11 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
   c->device = device;
   c->sm_count = 148;
   c->decode_stages = 96;
+  c->l2_prefetch_mb = 0;
+  c->no_persistent_gemm = 0;
+  c->force_wmma_attention = 0;
+  c->norm_cluster = 8;
+  c->max_smem_optin = 232448;
   c->err[0] = 0;
   *out = c;
   return CTS_OK;
@@ -206,7 +213,3 @@ bool cts_lora_wgrad_mma_enabled() { return false; }
 bool cts_lora_wgrad_mma_ok(const void*, long long, long long, int, long long, const void*, long long, long long, int) { return false; }
 int cts_lora_wgrad_mma_launch(cts_ctx*, const void*, long long, long long, int, long long, const void*, long long, long long, int, long long,
                               float, float*, long long, long long, int, void*) { return CTS_ERR_UNSUPPORTED; }
-
-// tcgen05 attention backward (attention_bwd_tc5.cu): not part of the shim build
-int cts_attn_bwd_tc5_launch(cts_ctx*, const void*, const void*, const void*, const void*, const float*, const float*, const int*, int, int,
-                            long long, int, int, float, void*, void*, void*, int, cudaStream_t) { return CTS_ERR_UNSUPPORTED; }

@@ -1,5 +1,6 @@
-"""GPU tests of the kernels that need no tensor core / TMA / cluster, executed on a machine WITHOUT a GPU through the "CUDA on CPU" shim
-(tests/cuda_on_cpu): `ctx()` returns a Context whose library is the kernels' own source compiled by g++, `.cuda()` is the identity.
+"""GPU tests executed on a machine WITHOUT a GPU through the "CUDA on CPU" shim (tests/cuda_on_cpu): `ctx()` returns a Context whose library
+is the kernels' own source compiled by g++ -- CUDA threads as fibers, clusters as threads, and a functional emulation of mbarrier / TMA /
+TMEM / tcgen05.mma that is calibrated by the GPU-validated GEMM kernels passing their own test file -- and `.cuda()` is the identity.
 Unlike tools/dryrun_train_gpu_tests.py (which checks the TEST LOGIC against the torch double), this executes the KERNEL SOURCE.
 TEST INFRASTRUCTURE ONLY.
 
@@ -75,14 +76,22 @@ gu.record = lambda *a, **k: None
 SELECT = {
     "test_gpu_zz_b_sampling.py": None,
     "test_gpu_zz_c_train.py": "adamw_and_clip or lora_pack or test_attention_backward or train_step_matches_oracle or training_reduces_loss or (directional and False)",
-    "test_gpu_train_kernels.py": "swiglu or rmsnorm_bwd or qkv_rope_bwd or ce_loss or cross_entropy or gather or wgrad",
+    "test_gpu_train_kernels.py": None,
+    # the cluster-fused decode GEMMs against the two-launch path, BIT FOR BIT: both GEMM kernels run from source through the tcgen05 /
+    # TMA / mbarrier emulation of the shim (same accumulation order), the reduce kernels of the two-launch path come from the double
+    "test_gpu_zz_e_fused_decode.py": None,
+    "test_gpu_gemm.py": None,                            # calibration of the emulation: the GPU-validated GEMM kernels themselves
+    "test_gpu_zz_d_attn_bwd_tc5.py": None,               # tcgen05 attention backward (K-major and MN-major operands, TMEM-resident dQ / dK / dV)
 }
 
 # --quick: a subset that finishes in about a minute (what tests/test_shim_kernels.py runs inside the CPU suite)
 QUICK = {
     "test_gpu_zz_b_sampling.py": "matches_reference and (1000 or 4096)",
     "test_gpu_zz_c_train.py": "adamw_and_clip or lora_pack or (test_attention_backward and (lens1 or lens4 or gqa)) or (train_step_matches_oracle and True-64)",
-    "test_gpu_train_kernels.py": SELECT["test_gpu_train_kernels.py"],
+    "test_gpu_train_kernels.py": None,
+    "test_gpu_zz_e_fused_decode.py": None,
+    "test_gpu_gemm.py": "not deterministic_under_repetition",
+    "test_gpu_zz_d_attn_bwd_tc5.py": "lens0 or lens1 or lens4",
 }
 
 if __name__ == "__main__":
