@@ -287,7 +287,11 @@ static inline float silu_f(float x) { return x / (1.0f + expf(-x)); }
 // The semantics encoded here are calibrated by running the GPU-validated kernels of gemm_tcgen05.cu through them.
 // ================================================================================================================================
 #include <unordered_map>
-static inline uint32_t smem_u32(const void* p) { return (uint32_t)(uintptr_t)p; }
+// 32-bit shared-window addresses: the low half of the host pointer; the high half is remembered per CTA (all shared objects a kernel
+// takes the address of this way -- its dynamic shared memory or its static arrays -- live in one region)
+extern thread_local uint64_t g_smem_hi;
+static inline uint32_t smem_u32(const void* p) { g_smem_hi = (uint64_t)(uintptr_t)p >> 32; return (uint32_t)(uintptr_t)p; }
+static inline uint8_t* shim_smem_from_u32(uint32_t a) { return (uint8_t*)(uintptr_t)((g_smem_hi << 32) | a); }
 struct CUtensorMap { const void* base; long long rows, cols, ld; int box_rows, box_cols, swizzled, is_bf16; };
 
 struct ShimMbar { int count = 0, pending = 0; long long tx = 0; unsigned long phases = 0; };
@@ -388,4 +392,56 @@ static inline uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 }
 constexpr uint32_t umma_idesc_f16(int is_bf16, int n, int m) {
   return (1u << 4) | ((uint32_t)(is_bf16 ? 1 : 0) << 7) | ((uint32_t)(is_bf16 ? 1 : 0) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- warp-level matrix instructions of the pre-Blackwell path (ldmatrix, mma.sync m16n8k16), emulated over the fibers of a warp:
+// every lane publishes its operands, then computes its own result registers from the documented fragment layouts
+static inline void shim_warp_allgather(uint64_t v, uint64_t* out) {
+  ShimBlock::Warp& w = g_blk.warp[shim_linear_tid() >> 5];
+  w.slot[shim_linear_tid() & 31] = v;
+  shim_warp_rendezvous();
+  for (int i = 0; i < 32; ++i) out[i] = w.slot[i];
+  shim_warp_rendezvous();
+}
+static inline void shim_ldmatrix_x4(uint32_t addr, uint32_t* r, bool trans) {
+  uint64_t rows[32];
+  shim_warp_allgather((uint64_t)(uintptr_t)shim_smem_from_u32(addr), rows);      // lane 8j+i supplies row i of matrix j
+  const int l = shim_linear_tid() & 31;
+  for (int j = 0; j < 4; ++j) {
+    if (!trans) {
+      memcpy(&r[j], (const uint8_t*)(uintptr_t)rows[8 * j + l / 4] + (l % 4) * 4, 4);
+    } else {
+      uint16_t lo, hi;
+      memcpy(&lo, (const uint8_t*)(uintptr_t)rows[8 * j + 2 * (l % 4)] + (l / 4) * 2, 2);
+      memcpy(&hi, (const uint8_t*)(uintptr_t)rows[8 * j + 2 * (l % 4) + 1] + (l / 4) * 2, 2);
+      r[j] = (uint32_t)lo | ((uint32_t)hi << 16);
+    }
+  }
+}
+static inline float shim_half_of(uint32_t word, int half, bool bf16) {
+  const uint16_t v = (uint16_t)(half ? word >> 16 : word & 0xFFFFu);
+  if (bf16) return shim_u2f((uint32_t)v << 16);
+  __half h; h.bits = v; return __half2float(h);
+}
+static inline void shim_mma_m16n8k16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1, bool bf16) {
+  uint64_t a01[32], a23[32], bb[32];
+  shim_warp_allgather((uint64_t)a[0] | ((uint64_t)a[1] << 32), a01);
+  shim_warp_allgather((uint64_t)a[2] | ((uint64_t)a[3] << 32), a23);
+  shim_warp_allgather((uint64_t)b0 | ((uint64_t)b1 << 32), bb);
+  const int l = shim_linear_tid() & 31, g = l / 4, t = l % 4;
+  auto A = [&](int i, int k) {               // a0: (g, 2t..) a1: (g+8, 2t..) a2: (g, 2t+8..) a3: (g+8, 2t+8..)
+    const int lane = (i % 8) * 4 + (k % 8) / 2;
+    const uint64_t pr = k >= 8 ? a23[lane] : a01[lane];
+    return shim_half_of((uint32_t)(i >= 8 ? pr >> 32 : pr), k % 2, bf16);
+  };
+  auto B = [&](int k, int n) {               // b0: (k = 2t.., n = g) b1: (k = 2t+8.., n = g)
+    const uint64_t pr = bb[n * 4 + (k % 8) / 2];
+    return shim_half_of((uint32_t)(k >= 8 ? pr >> 32 : pr), k % 2, bf16);
+  };
+  for (int idx = 0; idx < 4; ++idx) {
+    const int row = g + (idx >= 2 ? 8 : 0), col = 2 * t + (idx & 1);
+    float acc = c[idx];
+    for (int k = 0; k < 16; ++k) acc += A(row, k) * B(k, col);
+    c[idx] = acc;
+  }
 }

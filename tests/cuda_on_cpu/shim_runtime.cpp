@@ -4,6 +4,7 @@
 #include <sys/mman.h>
 
 thread_local ShimBlock g_blk;
+thread_local uint64_t g_smem_hi = 0;
 thread_local std::unordered_map<const void*, ShimMbar> g_mbar;
 thread_local float g_tmem[128][512];
 thread_local uint8_t* g_dyn_smem = nullptr;
@@ -207,9 +208,3 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
 }
 extern "C" void cts_ctx_destroy(cts_ctx* ctx) { delete ctx; }
 extern "C" const char* cts_last_error(const cts_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
-
-// the tensor-core weight-gradient variant lives in lora_wgrad_mma.cu (mma.sync: not part of the shim build)
-bool cts_lora_wgrad_mma_enabled() { return false; }
-bool cts_lora_wgrad_mma_ok(const void*, long long, long long, int, long long, const void*, long long, long long, int) { return false; }
-int cts_lora_wgrad_mma_launch(cts_ctx*, const void*, long long, long long, int, long long, const void*, long long, long long, int, long long,
-                              float, float*, long long, long long, int, void*) { return CTS_ERR_UNSUPPORTED; }

@@ -36,11 +36,8 @@ from tests.cuda_on_cpu.shim import shim_context  # noqa: E402
 import tests.gpu_util as gu  # noqa: E402
 
 _ctx = shim_context()
-# the forward that feeds the attention backward lives in attention.cu (tcgen05 / TMA: not shim material): O and LSE come from the torch
-# double, so the backward kernels run in isolation on reference inputs
 from tests.cabi_double import TorchDouble as _TD  # noqa: E402
 _dbl = _TD()
-_ctx.attn_prefill_lse = _dbl.attn_prefill_lse
 # HYBRID context for the whole-step tests: every entry point whose source is in the shim build runs that source; the others (tcgen05
 # GEMMs, attention forward, the decode-side kernels) are answered by the torch double.  What this adds over the double-only dry run:
 # train.py's argument plumbing (strides, interleaved layouts, arena offsets, packing descriptors) meets the REAL backward / loss /
@@ -75,12 +72,13 @@ gu.record = lambda *a, **k: None
 # the cases whose every entry point is part of the shim build
 SELECT = {
     "test_gpu_zz_b_sampling.py": None,
-    "test_gpu_zz_c_train.py": "adamw_and_clip or lora_pack or test_attention_backward or train_step_matches_oracle or training_reduces_loss or (directional and False)",
+    "test_gpu_zz_c_train.py": "adamw_and_clip or lora_pack or prefill_lse or test_attention_backward or train_step_matches_oracle or training_reduces_loss or (directional and False) or wgrad_tensor_core",
     "test_gpu_train_kernels.py": None,
     # the cluster-fused decode GEMMs against the two-launch path, BIT FOR BIT: both GEMM kernels run from source through the tcgen05 /
     # TMA / mbarrier emulation of the shim (same accumulation order), the reduce kernels of the two-launch path come from the double
     "test_gpu_zz_e_fused_decode.py": None,
     "test_gpu_gemm.py": None,                            # calibration of the emulation: the GPU-validated GEMM kernels themselves
+    "test_gpu_attention.py": None,                       # calibration: tcgen05 prefill attention (MN-major V operand), HMMA prefill, TMA paged decode (ldmatrix / mma.sync)
     "test_gpu_zz_d_attn_bwd_tc5.py": None,               # tcgen05 attention backward (K-major and MN-major operands, TMEM-resident dQ / dK / dV)
 }
 
