@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "chatts_b200", "csrc")
-SOURCES = ["sampling.cu", "train_elementwise.cu", "allreduce_ll.cu", "attention_bwd.cu", "gemm_decode_fused.cu", "gemm_tcgen05.cu", "attention_bwd_tc5.cu", "lora_wgrad_mma.cu", "attention.cu"]
+SOURCES = ["sampling.cu", "train_elementwise.cu", "allreduce_ll.cu", "attention_bwd.cu", "gemm_decode_fused.cu", "gemm_tcgen05.cu", "attention_bwd_tc5.cu", "lora_wgrad_mma.cu", "attention.cu", "elementwise.cu", "ts_frontend.cu", "decoder_step.cu"]
 OUT = os.path.join(HERE, "_build", "libchatts_shim.so")
 # Files that are GPU-validated are not edited for the shim's sake (not even a spelling): their two non-portable spellings are replaced
 # in the COPY.  Everything else in the copy is the product source, byte for byte.
@@ -46,6 +46,9 @@ SUBSTITUTIONS = {
         ("extern __shared__ uint8_t tc_raw[];", "uint8_t* tc_raw = g_dyn_smem;"),
         ("extern __shared__ uint8_t dec_raw[];", "uint8_t* dec_raw = g_dyn_smem;"),
     ],
+    "elementwise.cu": [("    ss_cta = v;\n  }\n  cluster.sync();", "    ss_cta = v;\n    shim_publish_static(&ss_cta);\n  }\n  cluster.sync();"),
+                       ("*cluster.map_shared_rank(&ss_cta, r)", "*(float*)shim_static_peer((unsigned)r)")],
+    "ts_frontend.cu": [("extern __shared__ uint8_t sm_raw[];", "uint8_t* sm_raw = g_dyn_smem;")],
     "attention_bwd_tc5.cu": [("extern __shared__ uint8_t dq_raw[];", "uint8_t* dq_raw = g_dyn_smem;"),
                              ("extern __shared__ uint8_t dkv_raw[];", "uint8_t* dkv_raw = g_dyn_smem;")],
     "gemm_tcgen05.cu": [("extern __shared__ uint8_t smem_raw[];", "uint8_t* smem_raw = g_dyn_smem;"),

@@ -136,6 +136,7 @@ template <typename F> static inline int cudaFuncSetAttribute(F, int, int) { retu
 struct ShimCluster {
   int size = 1;
   uint8_t* dyn_base[16] = {nullptr};
+  void* static_ptr[16] = {nullptr};                        // a STATIC shared variable published for the peers (shim_publish_static)
   pthread_barrier_t bar;
 };
 extern thread_local ShimCluster* g_cluster;
@@ -158,6 +159,12 @@ struct cluster_group {
 };
 static inline cluster_group this_cluster() { return cluster_group(); }
 }  // namespace cooperative_groups
+
+// distributed shared memory on a static __shared__ variable (one per kernel is enough for the library): the owner publishes its
+// address before the cluster barrier, the peers look it up after it
+extern thread_local void* g_static_self;
+static inline void shim_publish_static(void* p) { if (g_cluster) g_cluster->static_ptr[g_cluster_rank] = p; g_static_self = p; }
+static inline void* shim_static_peer(unsigned r) { return g_cluster ? g_cluster->static_ptr[r] : g_static_self; }
 
 void shim_launch(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem, dim3 cluster);
 
@@ -196,6 +203,18 @@ static inline float atomicAdd(float* p, float v) {
     if (__atomic_compare_exchange_n(u, &old, want, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) return shim_u2f(old);
   }
 }
+static inline int atomicMax(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+static inline int atomicMin(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+static inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicCAS(int* p, int cmp, int v) { __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
 static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void __trap() { fflush(stdout); abort(); }

@@ -5,6 +5,7 @@
 
 thread_local ShimBlock g_blk;
 thread_local uint64_t g_smem_hi = 0;
+thread_local void* g_static_self = nullptr;
 thread_local std::unordered_map<const void*, ShimMbar> g_mbar;
 thread_local float g_tmem[128][512];
 thread_local uint8_t* g_dyn_smem = nullptr;

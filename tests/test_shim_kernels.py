@@ -33,7 +33,7 @@ def test_pending_and_validated_kernels_pass_their_gpu_tests_on_the_shim():
     assert len(passed) == 6 and min(passed) >= 1 and sum(passed) >= 110 and "failed" not in r.stdout, tail
     native = r.stdout.split("entry points running from kernel source:")[1].split("\n")[0].split()
     assert {"sample_advance", "attn_bwd", "adamw", "grad_norm_clip", "lora_pack", "lora_wgrad", "ce_loss_grad", "rmsnorm_bwd", "swiglu_bwd",
-            "qkv_rope_bwd", "gemm", "gemm_decode_fused"} <= set(native), native
+            "qkv_rope_bwd", "gemm", "gemm_decode_fused", "attn_prefill_lse", "attn_decode", "decoder_step", "reduce_residual_rmsnorm"} <= set(native), native
 
 
 def _expected(parts, split, resid, dt):
