@@ -50,9 +50,6 @@ int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);
 
 static inline long long cdiv_ll(long long a, long long b) { return (a + b - 1) / b; }
 
-// the kernel's dynamic shared memory as a byte array (one spelling, so that tests/cuda_on_cpu can supply its own)
-#define CTS_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
-
 // ----------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  Every kernel of the library is launched with the
 // programmatic-stream-serialization attribute, calls pdl_trigger() first thing (so its successor may be

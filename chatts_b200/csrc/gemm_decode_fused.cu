@@ -25,6 +25,12 @@
 #include <type_traits>
 
 #include "common.cuh"
+
+// the kernel's dynamic shared memory as a byte array (one spelling, so that tests/cuda_on_cpu can supply its own; defined here and not
+// in common.cuh so that the header the GPU-validated kernels were compiled with stays byte-identical)
+#ifndef CTS_DYN_SMEM
+#define CTS_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#endif
 #include "tensormap.cuh"
 
 namespace {
