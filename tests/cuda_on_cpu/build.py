@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "chatts_b200", "csrc")
-SOURCES = ["sampling.cu", "train_elementwise.cu", "allreduce_ll.cu", "attention_bwd.cu", "gemm_decode_fused.cu", "gemm_tcgen05.cu", "attention_bwd_tc5.cu", "lora_wgrad_mma.cu", "attention.cu", "elementwise.cu", "ts_frontend.cu", "decoder_step.cu"]
+SOURCES = ["sampling.cu", "train_elementwise.cu", "allreduce_ll.cu", "attention_bwd.cu", "gemm_decode_fused.cu", "gemm_tcgen05.cu", "attention_bwd_tc5.cu", "lora_wgrad_mma.cu", "attention.cu", "elementwise.cu", "ts_frontend.cu", "decoder_step.cu", "allreduce.cu"]
 OUT = os.path.join(HERE, "_build", "libchatts_shim.so")
 # Files that are GPU-validated are not edited for the shim's sake (not even a spelling): their two non-portable spellings are replaced
 # in the COPY.  Everything else in the copy is the product source, byte for byte.
@@ -48,6 +48,18 @@ SUBSTITUTIONS = {
     ],
     "elementwise.cu": [("    ss_cta = v;\n  }\n  cluster.sync();", "    ss_cta = v;\n    shim_publish_static(&ss_cta);\n  }\n  cluster.sync();"),
                        ("*cluster.map_shared_rank(&ss_cta, r)", "*(float*)shim_static_peer((unsigned)r)")],
+    "allreduce.cu": [
+        ('asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");', "shim_st_release(p, v);"),
+        ('asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");', "v = shim_ld_acquire(p);"),
+        ('asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");',
+         "{ const volatile float* s_ = reinterpret_cast<const volatile float*>(p); v.x = s_[0]; v.y = s_[1]; v.z = s_[2]; v.w = s_[3]; }"),
+        ('asm volatile("st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(dst), "f"(best), "f"(gidx) : "memory");',
+         "{ volatile float* d_ = reinterpret_cast<volatile float*>(dst); d_[0] = best; d_[1] = gidx; }"),
+        ('asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(c) : "l"(src) : "memory");',
+         "{ const volatile float* s_ = reinterpret_cast<const volatile float*>(src); a = s_[0]; c = s_[1]; }"),
+        ("    ss_cta = v;\n  }\n  cluster.sync();", "    ss_cta = v;\n    shim_publish_static(&ss_cta);\n  }\n  cluster.sync();"),
+        ("*cluster.map_shared_rank(&ss_cta, r)", "*(float*)shim_static_peer((unsigned)r)"),
+    ],
     "ts_frontend.cu": [("extern __shared__ uint8_t sm_raw[];", "uint8_t* sm_raw = g_dyn_smem;")],
     "attention_bwd_tc5.cu": [("extern __shared__ uint8_t dq_raw[];", "uint8_t* dq_raw = g_dyn_smem;"),
                              ("extern __shared__ uint8_t dkv_raw[];", "uint8_t* dkv_raw = g_dyn_smem;")],
@@ -74,7 +86,7 @@ def build(force=False):
         cpps.append(dst)
     for f in ("common.cuh", "mma.h", "cooperative_groups.h", "tensormap.cuh", "shim_runtime.cpp"):
         shutil.copyfile(os.path.join(HERE, f), os.path.join(bdir, f))
-    cmd = ["g++", "-std=c++17", "-O2", "-fno-strict-aliasing", "-g", "-fPIC", "-shared", "-pthread", "-w", "-I", bdir, "-I", os.path.join(ROOT, "include"), "-o", OUT,
+    cmd = ["g++", "-std=c++17", "-O2", "-fno-strict-aliasing", "-g", "-fPIC", "-shared", "-pthread", "-lrt", "-w", "-I", bdir, "-I", os.path.join(ROOT, "include"), "-o", OUT,
            os.path.join(bdir, "shim_runtime.cpp")] + cpps
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -464,3 +464,22 @@ static inline void shim_mma_m16n8k16(float* c, const uint32_t* a, uint32_t b0, u
     c[idx] = acc;
   }
 }
+
+// ---- device allocations that other PROCESSES map (cudaMalloc + cudaIpc*): POSIX shared memory; the 64-byte handle carries the name
+struct cudaIpcMemHandle_t { char reserved[64]; };
+#define cudaIpcMemLazyEnablePeerAccess 1
+int cudaMalloc(void** p, size_t bytes);
+int cudaFree(void* p);
+static inline int cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return 0; }
+int cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
+int cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
+int cudaIpcCloseMemHandle(void* p);
+// system-scope flag traffic of the one-shot all-reduce / vocab-parallel argmax: plain atomics; pollers give way to the other fibers and ranks
+static inline void shim_st_release(int* p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static inline int shim_ld_acquire(const int* p) {
+  const int v = __atomic_load_n(p, __ATOMIC_ACQUIRE);
+  shim_yield();
+  static thread_local unsigned n = 0;
+  if ((++n & 255u) == 0) sched_yield();
+  return v;
+}

@@ -209,3 +209,57 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
 }
 extern "C" void cts_ctx_destroy(cts_ctx* ctx) { delete ctx; }
 extern "C" const char* cts_last_error(const cts_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+// ---- cudaMalloc / cudaIpc* over POSIX shared memory
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <map>
+#include <string>
+namespace {
+struct ShmBlock { std::string name; size_t bytes; bool owner; };
+std::map<void*, ShmBlock> g_shm;
+}
+int cudaMalloc(void** p, size_t bytes) {
+  static int counter = 0;
+  char name[64];
+  snprintf(name, sizeof(name), "/cts_shim_%d_%d", (int)getpid(), counter++);
+  const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) return 2;
+  void* q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (q == MAP_FAILED) return 2;
+  g_shm[q] = ShmBlock{name, bytes, true};
+  *p = q;
+  return 0;
+}
+int cudaFree(void* p) {
+  auto it = g_shm.find(p);
+  if (it == g_shm.end()) return 1;
+  munmap(p, it->second.bytes);
+  if (it->second.owner) shm_unlink(it->second.name.c_str());
+  g_shm.erase(it);
+  return 0;
+}
+int cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  auto it = g_shm.find(p);
+  if (it == g_shm.end()) return 1;
+  memset(h->reserved, 0, 64);
+  snprintf(h->reserved, 48, "%s", it->second.name.c_str());
+  const unsigned long long n = it->second.bytes;
+  memcpy(h->reserved + 48, &n, 8);
+  return 0;
+}
+int cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  unsigned long long n = 0;
+  memcpy(&n, h.reserved + 48, 8);
+  const int fd = shm_open(h.reserved, O_RDWR, 0600);
+  if (fd < 0) return 2;
+  void* q = mmap(nullptr, (size_t)n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (q == MAP_FAILED) return 2;
+  g_shm[q] = ShmBlock{h.reserved, (size_t)n, false};
+  *p = q;
+  return 0;
+}
+int cudaIpcCloseMemHandle(void* p) { return cudaFree(p); }

@@ -247,3 +247,21 @@ def test_fused_gemm_allreduce_tail_with_ranks_as_processes(shim_ctx, W, T, N, Kr
         assert torch.allclose(log_s[0][n], (log_h[0][n].float() ** 2).view(T, N // 128, 128).sum(-1), rtol=1e-5)
         cur = log_h[0][n].clone()                            # follow the kernel's own h (an ulp may differ from the reference chain)
     assert [int(s_[0]) for s_ in state] == [len(calls)] * W
+
+
+@pytest.mark.parametrize("variant", ["CTS_PEER_LL=1", "CTS_PEER_LL=1 CTS_DECODE_FUSED=2"])
+def test_tensor_parallel_model_with_ranks_as_processes(variant):
+    """tools/shim_tp_check.py: the tensor-parallel MODEL (2 ranks = 2 processes under torchrun, gloo for the host-side collectives, the
+    symmetric buffers as shared memory behind cts_ipc_*), every kernel from source -- with the low-latency all-reduce kernel, and with the
+    all-reduce inside the decode GEMMs (5 launches per layer).  Logits against the single-rank model, greedy agreement, identical tokens
+    on both ranks."""
+    import random
+    env = dict(os.environ, TP_CHECK_NEW="8")
+    env.update(kv.split("=") for kv in variant.split())
+    port = 29800 + random.randrange(150)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tools", "shim_tp_check.py")], capture_output=True, text=True, timeout=600,
+                       cwd=ROOT, env=env)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert "identical tokens on all ranks: True" in out and "greedy agreement [8, 8]/8" in out, out[-2000:]
