@@ -108,10 +108,23 @@ void shim_run_block(const std::function<void()>& body, dim3 block) {
     for (int r = 0; r < 6; ++r) *--sp = nullptr;           // rbp rbx r12 r13 r14 r15
     f.sp = sp;
   }
+  // CTS_SHIM_ORDER = reverse | random: the order in which the fibers of a block get the CPU.  A kernel that is correct only for one
+  // interleaving (a missing __syncthreads / __syncwarp, an assumed warp-synchronous step) gives different results under another one.
+  static const char* order_env = getenv("CTS_SHIM_ORDER");
+  const int order = !order_env ? 0 : (order_env[0] == 'r' && order_env[1] == 'e' ? 1 : (order_env[0] == 'r' ? 2 : 0));
+  static thread_local uint64_t rng = 0x9E3779B97F4A7C15ull;
+  std::vector<int> perm((size_t)n);
+  for (int i = 0; i < n; ++i) perm[(size_t)i] = order == 1 ? n - 1 - i : i;
   int left = n;
   while (left > 0) {
-    for (int i = 0; i < n; ++i) {
-      Fiber& f = g_fibers[i];
+    if (order == 2)
+      for (int i = n - 1; i > 0; --i) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        std::swap(perm[(size_t)i], perm[(size_t)(rng % (uint64_t)(i + 1))]);
+      }
+    for (int j = 0; j < n; ++j) {
+      const int i = perm[(size_t)j];
+      Fiber& f = g_fibers[(size_t)i];
       if (f.done) continue;
       g_cur = i;
       g_tid = f.tid;
