@@ -313,6 +313,18 @@ static inline uint32_t smem_u32(const void* p) { g_smem_hi = (uint64_t)(uintptr_
 static inline uint8_t* shim_smem_from_u32(uint32_t a) { return (uint8_t*)(uintptr_t)((g_smem_hi << 32) | a); }
 struct CUtensorMap { const void* base; long long rows, cols, ld; int box_rows, box_cols, swizzled, is_bf16; };
 
+// CTS_SHIM_ASYNC=1 -- adversarially LATE completion of the asynchronous operations: a TMA load / store, a tcgen05.mma and the arrive of a
+// tcgen05.commit are queued at issue and performed (in issue order) only when some thread of the CTA is blocked in an mbarrier wait or
+// in one of the explicit completion waits, and at the latest when the CTA ends.  A consumer that reads shared memory, TMEM or global
+// memory without having waited for the producing operation, or a producer that overwrites an operand buffer an outstanding MMA has not
+// read yet, then sees stale or clobbered data and its test fails.  (Off: everything completes at issue.)
+#include <deque>
+extern thread_local std::deque<std::function<void()>> g_async;
+extern int g_async_mode;
+static inline void shim_async(std::function<void()> fn) { if (g_async_mode) g_async.push_back(std::move(fn)); else fn(); }
+static inline bool shim_async_one() { if (g_async.empty()) return false; auto fn = std::move(g_async.front()); g_async.pop_front(); fn(); return true; }
+static inline void shim_async_all() { while (shim_async_one()) {} }
+
 struct ShimMbar { int count = 0, pending = 0; long long tx = 0; unsigned long phases = 0; };
 extern thread_local std::unordered_map<const void*, ShimMbar> g_mbar;
 static inline void shim_mbar_check(ShimMbar& b) { if (b.pending == 0 && b.tx == 0) { ++b.phases; b.pending = b.count; } }
@@ -328,7 +340,7 @@ static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t n = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++n > CTS_WAIT_LIMIT) { printf("shim: mbarrier wait timed out (block %u,%u,%u thread %u)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
-    shim_yield();
+    if (!shim_async_one()) shim_yield();                   // somebody is waiting: the oldest outstanding asynchronous operation completes now
   }
 }
 #define CTS_L2_EVICT_NORMAL 0x1000000000000000ull
@@ -348,16 +360,21 @@ static inline void shim_tma_copy(uint8_t* smem, const CUtensorMap* tm, int c0, i
     }
 }
 static inline void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint64_t) {
-  shim_tma_copy((uint8_t*)smem_dst, tm, c0, c1, true);
-  shim_mbar_complete_tx(bar, (long long)tm->box_rows * tm->box_cols * 2);
+  const CUtensorMap t = *tm;
+  shim_async([=] { shim_tma_copy((uint8_t*)smem_dst, &t, c0, c1, true); shim_mbar_complete_tx(bar, (long long)t.box_rows * t.box_cols * 2); });
 }
 static inline void tma_load_2d_nohint(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) { tma_load_2d(smem_dst, tm, bar, c0, c1, 0); }
 static inline void tma_prefetch_l2_2d(const CUtensorMap*, int, int) {}
 static inline void tma_prefetch_desc(const CUtensorMap*) {}
-static inline void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) { shim_tma_copy((uint8_t*)smem_src, tm, c0, c1, false); }
+static inline void tma_store_2d(const CUtensorMap* tm, const void* smem_src, int c0, int c1) {
+  const CUtensorMap t = *tm;
+  shim_async([=] { shim_tma_copy((uint8_t*)smem_src, &t, c0, c1, false); });
+}
 static inline void tma_store_commit() {}
-static inline void tma_store_wait_read0() {}
-static inline void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { memcpy(smem_dst, gsrc, bytes); shim_mbar_complete_tx(bar, bytes); }
+static inline void tma_store_wait_read0() { shim_async_all(); }
+static inline void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  shim_async([=] { memcpy(smem_dst, gsrc, bytes); shim_mbar_complete_tx(bar, bytes); });
+}
 static inline bool elect_one() { return (shim_linear_tid() & 31) == 0; }
 static inline void tc_fence_before() {}
 static inline void tc_fence_after() {}
@@ -382,7 +399,7 @@ static inline float shim_operand(uint64_t desc, int major, int r, int k, bool bf
                                 : (size_t)(r / 64) * lbo + (size_t)(k / 8) * sbo + (size_t)(k % 8) * 128 + (size_t)(r % 64) * 2;
   return shim_ld_elem(base + off, bf16);
 }
-static inline void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+static inline void shim_umma_now(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
   const int a_major = (int)((idesc >> 15) & 1), b_major = (int)((idesc >> 16) & 1);
   const bool bf16 = ((idesc >> 7) & 7) == 1;
@@ -400,12 +417,15 @@ static inline void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, u
       g_tmem[lane0 + m][col0 + n] = acc;
     }
 }
-static inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }            // every MMA has completed at issue
+static inline void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  shim_async([=] { shim_umma_now(d_tmem, a_desc, b_desc, idesc, accumulate); });
+}
+static inline void umma_commit(uint64_t* bar) { shim_async([=] { mbar_arrive(bar); }); }      // arrives once the MMAs issued before it have been performed
 static inline void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) {
   const int lane = (int)(taddr >> 16) + (shim_linear_tid() & 31), col = (int)(taddr & 0xFFFF);
   for (int j = 0; j < 16; ++j) v[j] = shim_f2u(g_tmem[lane][col + j]);
 }
-static inline void tmem_ld_wait() {}
+static inline void tmem_ld_wait() {}                     // completes the LOADS only: outstanding MMAs are not performed here
 static inline uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }

@@ -5,6 +5,8 @@
 
 thread_local ShimBlock g_blk;
 thread_local uint64_t g_smem_hi = 0;
+thread_local std::deque<std::function<void()>> g_async;
+int g_async_mode = 0;
 thread_local void* g_static_self = nullptr;
 thread_local std::unordered_map<const void*, ShimMbar> g_mbar;
 thread_local float g_tmem[128][512];
@@ -132,6 +134,7 @@ void shim_run_block(const std::function<void()>& body, dim3 block) {
       if (f.done) --left;
     }
   }
+  shim_async_all();                                        // whatever is still outstanding completes before the CTA retires
   g_cur = -1;
 }
 
@@ -142,6 +145,7 @@ extern "C" void shim_concurrent_grid(int on) { g_concurrent_grid = on; }
 
 // grid = clusters one after the other; the CTAs of a cluster concurrently (one OS thread each; a cluster of 1 runs in the caller)
 void shim_launch(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem, dim3 cl) {
+  { const char* e = getenv("CTS_SHIM_ASYNC"); g_async_mode = e && e[0] == '1'; }
   g_gdim = {grid.x, grid.y, grid.z};
   g_bdim = {block.x, block.y, block.z};
   const int csize = (int)(cl.x * cl.y * cl.z);
