@@ -291,6 +291,48 @@ def workload_config(batch, gpus):
             "l2_policy": "inputs larger than L2: 28 GB of weights streamed per step vs 126 MB L2"}
 
 
+# ------------------------------------------------------------------------------------------------ decode-variant probe
+def _probe_run(level, args, timeout=360):
+    """One guarded run of this script in a child process (its own CUDA context): 4 decoder layers of the 14B shape, the benchmark batch,
+    decode timing only.  Returns the child's JSON line or a dict with 'error'."""
+    import subprocess
+    env = dict(os.environ, CTS_DECODE_FUSED=str(level))
+    cmd = [sys.executable, os.path.abspath(__file__), "--layers", "4", "--steps", "24", "--warmup", "3", "--batch", str(args.batch),
+           "--no-cpu-baseline", "--sweep-only", "--no-probe"]            # all side batches too (1 and 8 use the other token-tile instantiation)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+        lines = [ln for ln in r.stdout.split("\n") if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": f"rc={r.returncode}: {(r.stderr or r.stdout)[-300:]}"}
+        d = json.loads(lines[-1])
+        sha = "/".join(f"{b}:{v.get('tokens_sha1')}" for b, v in sorted(d.get("by_batch", {}).items())) or d.get("tokens_sha1")
+        if "None" in str(sha):
+            sha = None
+        return {"ms_per_step": d["ms_per_step"], "tokens_sha1": sha, "launches_per_step": d.get("launches_per_step")}
+    except BaseException as e:  # noqa: BLE001  (a probe must never take the benchmark down)
+        return {"error": repr(e)[:300]}
+
+
+def probe_decode_variant(args):
+    """The cluster-fused decode GEMMs (CTS_DECODE_FUSED=1: 7 launches per layer instead of 9, bit-identical results by construction) are
+    selected for the measured run ONLY IF a guarded child run of both variants on a 4-layer model of the same shapes shows the SAME
+    greedy tokens (hash over every token of the batch) and a shorter step.  Anything else -- a fault, a timeout, different tokens, no
+    gain -- leaves the default path in place.  The outcome is recorded in the JSON line."""
+    rec = {"candidates": {}, "selected": 0}
+    try:
+        base = _probe_run(0, args)
+        rec["candidates"]["0"] = base
+        if "error" in base:
+            return rec
+        fused = _probe_run(1, args)
+        rec["candidates"]["1"] = fused
+        if "error" not in fused and fused["tokens_sha1"] and fused["tokens_sha1"] == base["tokens_sha1"] and fused["ms_per_step"] < 0.98 * base["ms_per_step"]:
+            rec["selected"] = 1
+    except BaseException as e:  # noqa: BLE001
+        rec["error"] = repr(e)[:300]
+    return rec
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch.distributed as dist
@@ -303,6 +345,11 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    probe_record = None
+    if world == 1 and not args.sweep_only and not args.no_probe and not args.layers and "CTS_DECODE_FUSED" not in os.environ:
+        probe_record = probe_decode_variant(args)
+        if probe_record.get("selected"):
+            os.environ["CTS_DECODE_FUSED"] = str(probe_record["selected"])          # read by the model constructor below
     cfg = ChatTSConfig.chatts_14b()
     if args.layers:
         cfg.num_hidden_layers = args.layers
@@ -351,17 +398,20 @@ def run_b200(args):
                 t = torch.tensor([ms], device="cuda")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms = float(t)
-            ctx_end = int(lay.lens.max()) + int(st.step_ptr[0].item())
+            n_tok = int(st.step_ptr[0].item())
+            ctx_end = int(lay.lens.max()) + n_tok
+            import hashlib
+            tok_sha = hashlib.sha1(st.out_tokens[:, :n_tok].to(torch.int32).cpu().numpy().tobytes()).hexdigest()[:16]
         finally:
             model.pool.release(held)
-        return ms, per_step_launches, ctx_end
+        return ms, per_step_launches, ctx_end, tok_sha
 
     results = {}
     with ClockSampler(local) as clk:
         batches = [args.batch] if args.only_batch else sorted(set(b for b in (1, 8, args.batch) if b <= args.batch))
         for b in batches:
-            ms, launches, ctx_end = measure_decode(b)
-            results[b] = dict(ms_total=ms, ms_per_step=ms / args.steps, tokens_per_s=b * args.steps / (ms / 1e3), launches=launches,
+            ms, launches, ctx_end, tok_sha = measure_decode(b)
+            results[b] = dict(ms_total=ms, ms_per_step=ms / args.steps, tokens_per_s=b * args.steps / (ms / 1e3), launches=launches, tokens_sha1=tok_sha,
                               ctx_end=ctx_end)
     clocks = clk.summary()
     main = results[args.batch]
@@ -409,6 +459,25 @@ def run_b200(args):
                 "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "us_per_launch": us, "algorithmic_bytes": alg,
                 "peak_source": peak_src, "split_k": sp,
                 "whole_step": {"bytes": step_bytes, "achieved_gbs": step_gbs, "frac": step_gbs / hbm_peak}}
+        if getattr(model, "use_fused_decode", 0):
+            # the measured step ran the cluster-fused variant of this projection (same TMA -> tcgen05 mainloop per K split, reduction and
+            # SwiGLU in the epilogue): time THAT kernel too, same weights, same algorithmic bytes
+            try:
+                fs = min(sp, 8)
+                for l in range(L):
+                    ctx.gemm_decode_fused(st.xn, model.wgu[l], _cabi.FUSED_SWIGLU, fs, B, act=st.act)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(n_rep):
+                    for l in range(L):
+                        ctx.gemm_decode_fused(st.xn, model.wgu[l], _cabi.FUSED_SWIGLU, fs, B, act=st.act)
+                e1.record()
+                torch.cuda.synchronize()
+                fus = e0.elapsed_time(e1) * 1e3 / (n_rep * L)
+                roof["fused_variant"] = {"kernel": "gemm_decode_fused_kernel (gate_up + cluster split-K reduction + SwiGLU)", "us_per_launch": fus,
+                                         "achieved": alg / (fus * 1e-6) / 1e9, "frac": alg / (fus * 1e-6) / 1e9 / hbm_peak, "split_k": fs}
+            except Exception as e:  # pragma: no cover
+                roof["fused_variant"] = {"error": repr(e)[:200]}
 
     # ---- TS encoder alone (north_star: reported against the HBM roofline): N = 8*B series x 256 points -> 128*B patch rows,
     # L2 flushed (256 MB write) before every timed call, CUDA events around the encode (patchify + 5 tcgen05 GEMM layers)
@@ -484,10 +553,13 @@ def run_b200(args):
         line = {"metric": "decode_tokens_per_s", "value": main["tokens_per_s"], "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args.batch, world),
-                "by_batch": {str(b): {"tokens_per_s": r["tokens_per_s"], "ms_per_step": r["ms_per_step"]} for b, r in results.items()},
+                "by_batch": {str(b): {"tokens_per_s": r["tokens_per_s"], "ms_per_step": r["ms_per_step"], "tokens_sha1": r.get("tokens_sha1")} for b, r in results.items()},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(main["launches"] * args.steps), "launches_per_step": main["launches"],
                 "roofline": roof, "ts_encoder": ts_roof, "attention": attn_roof, "cpu_baseline": cpu, "arch": ctx.arch, "lib": os.path.relpath(_cabi.LIB_PATH, ROOT)}
         # which opt-in variants of the decode path this line was measured with (all off = the validated default path)
+        line["tokens_sha1"] = main.get("tokens_sha1")          # hash of every greedy token the measured batch produced (probe: equality across variants)
+        if probe_record is not None:
+            line["config"]["decode_variant_probe"] = probe_record
         line["config"]["variants"] = {k: int(getattr(model, a, 0) or 0) for k, a in (("decode_fused", "use_fused_decode"), ("peer_ll", "use_peer_ll"),
                                                                                    ("native_step", "use_native_step"), ("decode_chain", "use_chain"))}
         print(json.dumps(line), flush=True)
@@ -508,6 +580,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run decode steps eagerly (for ncu launch lists)")
     ap.add_argument("--sweep-only", action="store_true", help="decode timing only (skip e2e)")
+    ap.add_argument("--no-probe", action="store_true", help="do not probe the cluster-fused decode variant (the default path is measured as is)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

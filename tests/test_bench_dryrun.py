@@ -38,3 +38,49 @@ def test_bench_driver_prints_the_contract_line(which):
     else:
         assert d["metric"] == "lora_finetune_positions_per_s" and d["scaling"] == "weak"
         assert 11.0 < d["loss"] < 13.0          # ln(vocab) at initialisation (LoRA B = 0)
+
+
+def test_decode_variant_probe_selects_only_on_equal_tokens_and_a_gain(monkeypatch):
+    """bench.py's guarded probe: the cluster-fused decode GEMMs are used for the measured run only if a child run shows identical greedy
+    tokens AND a shorter step; every other outcome keeps the default path."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    args = argparse.Namespace(batch=32)
+
+    def fake(outcomes):
+        return lambda level, a, timeout=360: dict(outcomes[level])
+
+    cases = [
+        ({0: {"ms_per_step": 1.00, "tokens_sha1": "ab"}, 1: {"ms_per_step": 0.90, "tokens_sha1": "ab"}}, 1),      # same tokens, faster
+        ({0: {"ms_per_step": 1.00, "tokens_sha1": "ab"}, 1: {"ms_per_step": 0.90, "tokens_sha1": "cd"}}, 0),      # different tokens
+        ({0: {"ms_per_step": 1.00, "tokens_sha1": "ab"}, 1: {"ms_per_step": 0.995, "tokens_sha1": "ab"}}, 0),     # no real gain
+        ({0: {"ms_per_step": 1.00, "tokens_sha1": "ab"}, 1: {"error": "rc=-6: trap"}}, 0),                         # the variant faulted
+        ({0: {"error": "timeout"}, 1: {"ms_per_step": 0.5, "tokens_sha1": "ab"}}, 0),                              # no baseline
+        ({0: {"ms_per_step": 1.00, "tokens_sha1": None}, 1: {"ms_per_step": 0.5, "tokens_sha1": None}}, 0),        # nothing to compare
+    ]
+    for outcomes, want in cases:
+        monkeypatch.setattr(bench, "_probe_run", fake(outcomes))
+        rec = bench.probe_decode_variant(args)
+        assert rec["selected"] == want, (outcomes, rec)
+    monkeypatch.setattr(bench, "_probe_run", lambda *a, **k: (_ for _ in ()).throw(RuntimeError("boom")))
+    assert bench.probe_decode_variant(args)["selected"] == 0                # the probe itself failing is not fatal either
+
+
+def test_probe_child_run_parses_the_json_line_and_survives_failures(tmp_path, monkeypatch):
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    good = tmp_path / "good.py"
+    good.write_text("import os, sys\nprint('NCCL noise')\nprint('{\"ms_per_step\": 0.5, \"by_batch\": {\"1\": {\"tokens_sha1\": \"a' + os.environ['CTS_DECODE_FUSED'] + '\"}, \"32\": {\"tokens_sha1\": \"b\"}}, \"launches_per_step\": 7}')\n")
+    bad = tmp_path / "bad.py"
+    bad.write_text("import sys\nprint('about to die', file=sys.stderr)\nsys.exit(134)\n")
+    slow = tmp_path / "slow.py"
+    slow.write_text("import time\ntime.sleep(30)\n")
+    args = argparse.Namespace(batch=4)
+    monkeypatch.setattr(bench, "__file__", str(good))
+    assert bench._probe_run(1, args) == {"ms_per_step": 0.5, "tokens_sha1": "1:a1/32:b", "launches_per_step": 7}
+    monkeypatch.setattr(bench, "__file__", str(bad))
+    assert "error" in bench._probe_run(1, args) and "rc=134" in bench._probe_run(1, args)["error"]
+    monkeypatch.setattr(bench, "__file__", str(slow))
+    assert "error" in bench._probe_run(1, args, timeout=1)
