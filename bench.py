@@ -10,6 +10,8 @@ prefill of prompts that each carry 8 series x 256 points (8 x (46 prefix ids + <
 resident in HBM; the 28 GB weight stream is far larger than the 126 MB L2).  `e2e` = the same metric through
 the public generate() call with HOST tensors (processor output on the CPU, H2D of ids/series, prefill, K new
 tokens streamed back D2H every step).  N>1: tensor parallel over N GPUs (strong scaling, total work fixed).
+At N=1 a guarded probe (two child runs of this script on 4 layers) decides whether the measured run uses the cluster-fused decode GEMMs:
+only if they reproduce the default path's greedy tokens for every batch, faster (probe_decode_variant; --no-probe skips it).
 """
 import argparse
 import json
