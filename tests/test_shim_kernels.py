@@ -255,10 +255,12 @@ def test_tensor_parallel_model_with_ranks_as_processes(variant):
     symmetric buffers as shared memory behind cts_ipc_*), every kernel from source -- with the low-latency all-reduce kernel, and with the
     all-reduce inside the decode GEMMs (5 launches per layer).  Logits against the single-rank model, greedy agreement, identical tokens
     on both ranks."""
-    import random
+    import socket
     env = dict(os.environ, TP_CHECK_NEW="8")
     env.update(kv.split("=") for kv in variant.split())
-    port = 29800 + random.randrange(150)
+    with socket.socket() as sk:                              # a port that is free right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(ROOT, "tools", "shim_tp_check.py")], capture_output=True, text=True, timeout=600,
                        cwd=ROOT, env=env)
