@@ -86,11 +86,25 @@ def build(force=False):
         cpps.append(dst)
     for f in ("common.cuh", "mma.h", "cooperative_groups.h", "tensormap.cuh", "shim_runtime.cpp"):
         shutil.copyfile(os.path.join(HERE, f), os.path.join(bdir, f))
-    cmd = ["g++", "-std=c++17", "-O2", "-fno-strict-aliasing", "-g", "-fPIC", "-shared", "-pthread", "-lrt", "-w", "-I", bdir, "-I", os.path.join(ROOT, "include"), "-o", OUT,
-           os.path.join(bdir, "shim_runtime.cpp")] + cpps
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    flags = ["-std=c++17", "-O2", "-fno-strict-aliasing", "-g", "-fPIC", "-pthread", "-w", "-I", bdir, "-I", os.path.join(ROOT, "include")]
+    units = [os.path.join(bdir, "shim_runtime.cpp")] + cpps
+
+    def compile_one(src):
+        obj = src[:-4] + ".o"
+        r = subprocess.run(["g++"] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+        return obj, r
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, units))
+    for obj, r in results:
+        if r.returncode != 0:
+            raise RuntimeError("shim build failed:\n" + r.stderr[-6000:])
+    tmp = OUT + f".{os.getpid()}.tmp"
+    r = subprocess.run(["g++", "-shared", "-pthread", "-o", tmp] + [o for o, _ in results] + ["-lrt"], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("shim build failed:\n" + r.stderr[-6000:])
+        raise RuntimeError("shim link failed:\n" + r.stderr[-6000:])
+    os.replace(tmp, OUT)                                      # atomic: a concurrent reader never sees a half-written library
     return OUT
 
 
