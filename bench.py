@@ -310,7 +310,8 @@ def _probe_run(level, args, timeout=360):
         sha = "/".join(f"{b}:{v.get('tokens_sha1')}" for b, v in sorted(d.get("by_batch", {}).items())) or d.get("tokens_sha1")
         if "None" in str(sha):
             sha = None
-        return {"ms_per_step": d["ms_per_step"], "tokens_sha1": sha, "launches_per_step": d.get("launches_per_step")}
+        return {"ms_per_step": d["ms_per_step"], "tokens_sha1": sha, "launches_per_step": d.get("launches_per_step"),
+                "ms_by_batch": {b: v.get("ms_per_step") for b, v in sorted(d.get("by_batch", {}).items())}}
     except BaseException as e:  # noqa: BLE001  (a probe must never take the benchmark down)
         return {"error": repr(e)[:300]}
 
@@ -329,7 +330,10 @@ def probe_decode_variant(args):
         fused = _probe_run(1, args)
         rec["candidates"]["1"] = fused
         if "error" not in fused and fused["tokens_sha1"] and fused["tokens_sha1"] == base["tokens_sha1"] and fused["ms_per_step"] < 0.98 * base["ms_per_step"]:
-            rec["selected"] = 1
+            # ... and no side batch may get slower
+            fb, bb = fused.get("ms_by_batch") or {}, base.get("ms_by_batch") or {}
+            if all(fb.get(b) is not None and bb.get(b) is not None and fb[b] <= 1.02 * bb[b] for b in bb):
+                rec["selected"] = 1
     except BaseException as e:  # noqa: BLE001
         rec["error"] = repr(e)[:300]
     return rec

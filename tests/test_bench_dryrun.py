@@ -58,6 +58,10 @@ def test_decode_variant_probe_selects_only_on_equal_tokens_and_a_gain(monkeypatc
         ({0: {"ms_per_step": 1.00, "tokens_sha1": "ab"}, 1: {"error": "rc=-6: trap"}}, 0),                         # the variant faulted
         ({0: {"error": "timeout"}, 1: {"ms_per_step": 0.5, "tokens_sha1": "ab"}}, 0),                              # no baseline
         ({0: {"ms_per_step": 1.00, "tokens_sha1": None}, 1: {"ms_per_step": 0.5, "tokens_sha1": None}}, 0),        # nothing to compare
+        ({0: {"ms_per_step": 1.00, "tokens_sha1": "ab", "ms_by_batch": {"1": 0.5, "32": 1.0}},
+          1: {"ms_per_step": 0.90, "tokens_sha1": "ab", "ms_by_batch": {"1": 0.6, "32": 0.9}}}, 0),                # a side batch got slower
+        ({0: {"ms_per_step": 1.00, "tokens_sha1": "ab", "ms_by_batch": {"1": 0.5, "32": 1.0}},
+          1: {"ms_per_step": 0.90, "tokens_sha1": "ab", "ms_by_batch": {"1": 0.45, "32": 0.9}}}, 1),
     ]
     for outcomes, want in cases:
         monkeypatch.setattr(bench, "_probe_run", fake(outcomes))
@@ -79,7 +83,7 @@ def test_probe_child_run_parses_the_json_line_and_survives_failures(tmp_path, mo
     slow.write_text("import time\ntime.sleep(30)\n")
     args = argparse.Namespace(batch=4)
     monkeypatch.setattr(bench, "__file__", str(good))
-    assert bench._probe_run(1, args) == {"ms_per_step": 0.5, "tokens_sha1": "1:a1/32:b", "launches_per_step": 7}
+    assert bench._probe_run(1, args) == {"ms_per_step": 0.5, "tokens_sha1": "1:a1/32:b", "launches_per_step": 7, "ms_by_batch": {"1": None, "32": None}}
     monkeypatch.setattr(bench, "__file__", str(bad))
     assert "error" in bench._probe_run(1, args) and "rc=134" in bench._probe_run(1, args)["error"]
     monkeypatch.setattr(bench, "__file__", str(slow))
