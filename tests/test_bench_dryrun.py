@@ -63,10 +63,23 @@ def test_decode_variant_probe_selects_only_on_equal_tokens_and_a_gain(monkeypatc
         ({0: {"ms_per_step": 1.00, "tokens_sha1": "ab", "ms_by_batch": {"1": 0.5, "32": 1.0}},
           1: {"ms_per_step": 0.90, "tokens_sha1": "ab", "ms_by_batch": {"1": 0.45, "32": 0.9}}}, 1),
     ]
+    monkeypatch.setattr(bench, "_probe_compare", lambda level, a, timeout=420: {"error": "not probed in this case"})
     for outcomes, want in cases:
         monkeypatch.setattr(bench, "_probe_run", fake(outcomes))
         rec = bench.probe_decode_variant(args)
         assert rec["selected"] == want, (outcomes, rec)
+    # level 2: only after level 1 was adopted, only within the numeric bound, only if faster again
+    lvl = {0: {"ms_per_step": 1.00, "tokens_sha1": "ab"}, 1: {"ms_per_step": 0.90, "tokens_sha1": "ab"}, 2: {"ms_per_step": 0.80, "tokens_sha1": "zz"}}
+    for cmp, want in (({"max_rel": 3e-3, "finite": True}, 2), ({"max_rel": 5e-2, "finite": True}, 1), ({"max_rel": 1e-3, "finite": False}, 1),
+                      ({"error": "rc=1"}, 1)):
+        monkeypatch.setattr(bench, "_probe_run", fake(lvl))
+        monkeypatch.setattr(bench, "_probe_compare", lambda level, a, timeout=420, c=cmp: dict(c))
+        assert bench.probe_decode_variant(args)["selected"] == want, cmp
+    slow2 = dict(lvl)
+    slow2[2] = {"ms_per_step": 0.89, "tokens_sha1": "zz"}
+    monkeypatch.setattr(bench, "_probe_run", fake(slow2))
+    monkeypatch.setattr(bench, "_probe_compare", lambda level, a, timeout=420: {"max_rel": 1e-3, "finite": True})
+    assert bench.probe_decode_variant(args)["selected"] == 1
     monkeypatch.setattr(bench, "_probe_run", lambda *a, **k: (_ for _ in ()).throw(RuntimeError("boom")))
     assert bench.probe_decode_variant(args)["selected"] == 0                # the probe itself failing is not fatal either
 

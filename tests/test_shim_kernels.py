@@ -11,6 +11,7 @@ product's own ctypes wrappers drive them on host memory:
     between ranks, torn 16-byte units, consecutive calls without any barrier in between.
 
 Only kernels without tensor cores / TMA / clusters can run this way.  Not a memory-model check (x86 is stronger than PTX)."""
+import json
 import os
 import subprocess
 import sys
@@ -267,3 +268,28 @@ def test_tensor_parallel_model_with_ranks_as_processes(variant):
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-3000:]
     assert "identical tokens on all ranks: True" in out and "greedy agreement [8, 8]/8" in out, out[-2000:]
+
+
+def test_numeric_guard_of_the_decode_variant_probe_runs_from_source():
+    """tools/probe_decode_variant.py (the child bench.py runs before it adopts fusion level 2): default path and variant on the same weights,
+    teacher-forced, logits compared at every step -- executed here through the shim with a toy configuration."""
+    code = r'''
+import sys
+sys.path.insert(0, "tools")
+import shim_gpu_tests                                    # host patches + shim context
+import torch
+import chatts_b200.model as mm
+from chatts_b200 import ChatTSConfig
+import probe_decode_variant as P
+fs = mm.ChatTSForCausalLM.from_synthetic.__func__
+mm.ChatTSForCausalLM.from_synthetic = classmethod(lambda cls, config=None, seed=1234, device="cpu", dtype=torch.bfloat16, gen_device=None, **kw: fs(cls, config, seed, "cpu", dtype, "cpu", **kw))
+c = ChatTSConfig.chatts_14b()
+c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.head_dim = 512, 1024, 4, 2, 128
+c.ts["hidden_size"] = 512                                  # the TS encoder projects into the decoder width
+import json
+print(json.dumps(P.compare(2, [2], 2, 2, cfg=c)))
+'''
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    d = json.loads([ln for ln in r.stdout.split("\n") if ln.startswith("{")][-1])
+    assert d["finite"] and d["steps"] == 3 and d["max_rel"] <= 1e-2, d
