@@ -26,6 +26,21 @@ for name in ("empty", "full", "zeros", "ones", "randn", "tensor", "empty_like", 
             return orig(*a, **k)
         return f
     setattr(torch, name, mk(orig))
+if os.environ.get("CTS_SHIM_POISON") == "1":
+    # "initcheck": every torch.empty / empty_like of a floating type comes back full of NaN, so a kernel that reads memory nobody wrote shows
+    # up as NaN in a result that is compared with a reference
+    for _n in ("empty", "empty_like"):
+        _o = getattr(torch, _n)
+
+        def _mk(_o):
+            @functools.wraps(_o)
+            def f(*a, **k):
+                t = _o(*a, **k)
+                if t.is_floating_point():
+                    t.fill_(float("nan"))
+                return t
+            return f
+        setattr(torch, _n, _mk(_o))
 torch.Tensor.cuda = lambda self, *a, **k: self
 _to = torch.Tensor.to
 
