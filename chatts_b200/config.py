@@ -31,6 +31,9 @@ class ChatTSConfig:
     ts_token_start_index: int = 151665          # <ts>; <ts/> = +1 (chatts_vllm.py:441)
     eos_token_id: int = 151645                  # stop ids 151643/151645 (chatts/utils/llm_utils.py:153)
     pad_token_id: int = 151643
+    # HF-surface merge of the patch rows at <ts><ts/> (layout.py): "insert" keeps both special tokens, "overwrite" replaces the pair.
+    # The checkpoint's remote code is not in the reference repo, so this cannot be pinned offline.
+    ts_merge_mode: str = "insert"
     model_type: str = "chatts"                  # scripts/start_vllm_server.sh:5
     torch_dtype: str = "bfloat16"
 

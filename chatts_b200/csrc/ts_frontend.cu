@@ -130,7 +130,9 @@ __global__ void ts_patchify_kernel(const T* __restrict__ x, int row_len, int nf,
       } else {
         const int e = j - patch;
         const int pt = p0 + e / emb_dim;
-        const int id = pt < vl ? pt : max_seq_len;   // padding id (:76,:128)
+        // padding id (:76,:128); a point index beyond the table is rejected on the host (IndexError, as nn.Embedding raises) and
+        // clamped here so that the kernel can never read past pos_table [max_seq_len + 1, emb_dim]
+        const int id = pt < vl ? min(pt, max_seq_len) : max_seq_len;
         out[j] = pos_table[(size_t)id * emb_dim + (e % emb_dim)];
       }
     }

@@ -34,6 +34,7 @@ class Request:
     slot: int = -1
     pages: list = field(default_factory=list)
     done: bool = False
+    error: Exception = None            # set when the request could not be admitted (over-long, or larger than the whole KV pool)
 
 
 class ContinuousEngine:
@@ -123,13 +124,38 @@ class ContinuousEngine:
                     o += p.shape[0]
             else:
                 ts = None
-            _, _, counts, lay = m._prepare_inputs(ids, am, ts)
             try:
+                _, _, counts, lay = m._prepare_inputs(ids, am, ts)
                 pts, held = m._alloc_pages(lay.lens, max(r.max_new_tokens for r in group) + self.k)
-            except RuntimeError:                           # KV cache full: put the group back and wait for a release
-                for r in reversed(group):
-                    self.waiting.appendleft(r)
-                return
+            except RuntimeError as e:                      # KV cache full (_alloc_pages takes nothing when it fails)
+                if self.active:                            # pages will come back: put the group back and wait for a release
+                    for r in reversed(group):
+                        self.waiting.appendleft(r)
+                    return
+                if len(group) > 1:                         # nothing in flight: retry with the head of the queue alone
+                    for r in reversed(group):
+                        self.waiting.appendleft(r)
+                    self._admit_one()
+                    return
+                # a single request that does not fit an EMPTY pool can never run: fail it instead of retrying forever
+                self._fail(group[0], e)
+                continue
+            except (ValueError, AssertionError) as e:      # an invalid request (over-long, <ts>/series mismatch) fails alone
+                if len(group) == 1:
+                    self._fail(group[0], e)
+                else:                                      # find the offender(s) by admitting the group one request at a time
+                    for r in reversed(group):
+                        self.waiting.appendleft(r)
+                    saved, self.max_prefill = self.max_prefill, 1
+                    try:
+                        for _ in range(len(group)):
+                            if not self._free_slots():
+                                break
+                            self._admit_one()
+                    finally:
+                        self.max_prefill = saved
+                    free = self._free_slots()
+                continue
             logits = m._prefill(lay, counts, ts, pts)
             # first token + advanced per-sequence state through the greedy kernel on a group-sized scratch state
             g = len(group)
@@ -158,6 +184,21 @@ class ContinuousEngine:
             for r in [q for q in group if q.done]:
                 self._retire(r)
             free = self._free_slots()
+
+    def _admit_one(self):
+        """Admit exactly the request at the head of the queue (used to isolate an invalid request of a failed group)."""
+        if not self.waiting:
+            return
+        head = self.waiting.popleft()
+        rest, self.waiting = self.waiting, deque([head])
+        try:
+            self._admit()
+        finally:
+            self.waiting.extend(rest)
+
+    def _fail(self, r, err):
+        r.error, r.done = err, True
+        self.finished.append(r)
 
     # ------------------------------------------------------------------------------------------ decode
     def _decode_round(self):

@@ -3,8 +3,14 @@ in the merged embedding sequence.  Pure integer work on the (CPU) input_ids; the
 resulting int32 maps (embedding gather ids, patch-row scatter map, positions, cu_seqlens, KV slots).
 
 Layouts (see oracle/merge.py for the slow statement these are checked against, bit-exact):
-  * "hf"   -- input_ids keep the un-expanded ``<ts><ts/>`` pair; the P_i patch rows of the i-th series are
-              INSERTED after the i-th ``<ts>`` (README.md:103; chatts/utils/inference_tsmllm_deepspeed.py:86,110).
+  * "hf"   -- input_ids keep the un-expanded ``<ts><ts/>`` pair.  Two merge modes, because the checkpoint's remote code
+              (``_merge_input_ids_with_time_series_features``) is NOT in the reference repo and cannot be pinned offline:
+              mode "insert" (default): both special tokens keep their embeddings and the P_i patch rows
+              of the i-th series are INSERTED between them -> P_i + 2 positions per series (README.md:103;
+              chatts/utils/inference_tsmllm_deepspeed.py:86,110);
+              mode "overwrite": the pair is REPLACED by the P_i patch rows (the two special-token slots are consumed,
+              P_i - 2 new positions) -- the LLaVA-style merge, and what the reference's own vLLM path does with the pair
+              (chatts_vllm.py:438-444).  ``config.ts_merge_mode`` / ``CTS_TS_MERGE_MODE`` selects it.
   * "vllm" -- the prompt already holds P_i copies of ``<ts>``; those positions are OVERWRITTEN in order
               (chatts/vllm/chatts_vllm.py:405-415,569-573).
 """
@@ -30,7 +36,9 @@ class MergedLayout:
         return np.diff(self.cu_seqlens)
 
 
-def hf_layout(input_ids, attention_mask, patch_cnt, ts_start):
+def hf_layout(input_ids, attention_mask, patch_cnt, ts_start, mode="insert"):
+    if mode not in ("insert", "overwrite"):
+        raise ValueError(f"ts merge mode must be 'insert' or 'overwrite', got {mode!r}")
     ids = np.asarray(input_ids)
     if ids.ndim == 1:
         ids = ids[None]
@@ -48,21 +56,30 @@ def hf_layout(input_ids, attention_mask, patch_cnt, ts_start):
     if n_ts != patch_cnt.shape[0]:
         # the reference asserts the same thing (chatts/utils/encoding_utils.py:58,68)
         raise AssertionError(f"{n_ts} <ts> placeholders in the batch but {patch_cnt.shape[0]} time series were given")
-    extra = np.zeros(flat_ids.shape[0], dtype=np.int64)
-    extra[is_ts] = patch_cnt
-    span = 1 + extra
-    tok_pos = np.cumsum(span) - span                       # merged flat position of every text token
+    if mode == "insert":
+        extra = np.zeros(flat_ids.shape[0], dtype=np.int64)
+        extra[is_ts] = patch_cnt
+        span = 1 + extra
+        is_text = np.ones(flat_ids.shape[0], dtype=bool)
+        first = 1                                           # the rows start right after the kept <ts> token
+    else:
+        # "overwrite": <ts> and <ts/> give up their slots; the i-th <ts> position expands to P_i rows, <ts/> to nothing
+        is_text = ~(is_ts | (flat_ids == ts_start + 1))
+        span = is_text.astype(np.int64)
+        span[is_ts] = patch_cnt
+        first = 0
+    tok_pos = np.cumsum(span) - span                       # merged flat position of every input token (start of its span)
     T = int(span.sum())
     out_ids = np.full(T, -1, dtype=np.int32)
-    out_ids[tok_pos] = flat_ids.astype(np.int32)
+    out_ids[tok_pos[is_text]] = flat_ids[is_text].astype(np.int32)
     src_col = np.full(T, -1, dtype=np.int32)
-    src_col[tok_pos] = flat_col.astype(np.int32)
-    # patch rows: global row r of series k sits at tok_pos[<ts>_k] + 1 + (r - first_row_k)
+    src_col[tok_pos[is_text]] = flat_col[is_text].astype(np.int32)
+    # patch rows: global row r of series k sits at tok_pos[<ts>_k] + first + (r - first_row_k)
     first_row = np.cumsum(patch_cnt) - patch_cnt
     total_rows = int(patch_cnt.sum())
     series_of_row = np.repeat(np.arange(n_ts), patch_cnt)
     within = np.arange(total_rows) - first_row[series_of_row]
-    row_map = (tok_pos[is_ts][series_of_row] + 1 + within).astype(np.int32)
+    row_map = (tok_pos[is_ts][series_of_row] + first + within).astype(np.int32)
     # per-sample lengths
     sample_of_tok = np.repeat(np.arange(B), n_real)
     lens = np.bincount(sample_of_tok, weights=span, minlength=B).astype(np.int64)

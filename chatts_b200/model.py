@@ -100,7 +100,9 @@ class ChatTSForCausalLM:
         # run on a B200 (written after the round-1 GPU budget was spent); CTS_SAMPLE_KERNEL=1 / use_sample_kernel=True turns it on
         self.use_sample_kernel = bool(int(_os.environ.get("CTS_SAMPLE_KERNEL", "0"))) if use_sample_kernel is None else bool(use_sample_kernel)
         self._load(state_dict)
-        n_pos = min(cfg.max_position_embeddings, max(max_seq_len, 16))
+        # every position the page table can address has a row in the rotary tables (max_pages * page_size >= max_seq_len), capped by
+        # the model's max_position_embeddings; _alloc_pages rejects sequences beyond it (no silent out-of-bounds cos/sin read)
+        n_pos = min(cfg.max_position_embeddings, max(self.max_pages * page_size, 16))
         self.cos, self.sin = rope_tables(cfg, n_pos, dtype, self.device)
         self.n_pos = n_pos
         num_pages = max_batch * self.max_pages
@@ -418,7 +420,9 @@ class ChatTSForCausalLM:
             self._host_counts = (host[0], host[1])
             cnt_h = host[1].numpy().astype(np.int64)
         if layout_kind == "hf":
-            lay = layout.hf_layout(ids_cpu, am_cpu, cnt_h, cfg.ts_token_start_index)
+            import os as _os
+            mode = _os.environ.get("CTS_TS_MERGE_MODE") or getattr(cfg, "ts_merge_mode", "insert")
+            lay = layout.hf_layout(ids_cpu, am_cpu, cnt_h, cfg.ts_token_start_index, mode)
         else:
             lay = layout.vllm_layout(ids_cpu, int(cnt_h.sum()), cfg.ts_token_start_index)
         return ids_cpu, am_cpu, counts, lay
@@ -490,14 +494,29 @@ class ChatTSForCausalLM:
         if B > self.max_batch:
             raise ValueError(f"batch {B} exceeds max_batch {self.max_batch}")
         pt = np.zeros((B, self.max_pages), dtype=np.int32)
-        held = []
+        # all-or-nothing: every need is checked before the first page leaves the pool, so a failure can never strand pages
+        # (ContinuousEngine._admit retries a RuntimeError; a leak there would shrink the pool for good)
+        needs = []
         for b in range(B):
-            need = (int(lens[b]) + extra + self.page_size - 1) // self.page_size
+            n_tok = int(lens[b]) + extra
+            if n_tok > self.n_pos:
+                raise ValueError(f"sequence of {n_tok} tokens exceeds the {self.n_pos} positions of the rotary table "
+                                 f"(min(max_position_embeddings, max_seq_len))")
+            need = (n_tok + self.page_size - 1) // self.page_size
             if need > self.max_pages:
-                raise ValueError(f"sequence of {int(lens[b]) + extra} tokens exceeds max_seq_len {self.max_seq_len}")
-            pg = self.pool.alloc(need)
-            held += pg
-            pt[b, :need] = pg
+                raise ValueError(f"sequence of {n_tok} tokens exceeds max_seq_len {self.max_seq_len}")
+            needs.append(need)
+        if sum(needs) > len(self.pool.free):
+            raise RuntimeError(f"KV cache exhausted: need {sum(needs)} pages, {len(self.pool.free)} free of {self.pool.num_pages}")
+        held = []
+        try:
+            for b, need in enumerate(needs):
+                pg = self.pool.alloc(need)
+                held += pg
+                pt[b, :need] = pg
+        except BaseException:
+            self.pool.release(held)
+            raise
         return pt, held
 
     # ------------------------------------------------------------------------------------------ decode
@@ -654,7 +673,17 @@ class ChatTSForCausalLM:
         eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
         eos_set = set(eos) if isinstance(eos, (list, tuple, set)) else {int(eos)}
         pad = cfg.pad_token_id if pad_token_id is None else pad_token_id
-        greedy = not (do_sample and temperature is not None and temperature > 0)
+        if do_sample and temperature is None:
+            temperature = 1.0                                   # HF GenerationConfig default when do_sample=True names no temperature
+        greedy = not (do_sample and temperature > 0)
+        if not greedy and seed is None:
+            # an unseeded call draws a fresh seed (a fresh torch.Generator would start from the same default seed every time);
+            # under tensor parallelism rank 0's seed is broadcast so every rank picks the same tokens
+            seed = int.from_bytes(__import__("os").urandom(7), "little")
+            if self.tp_size > 1:
+                box = [seed]
+                torch.distributed.broadcast_object_list(box, src=0, group=self.comm)
+                seed = int(box[0])
         page_tables, held = self._alloc_pages(lay.lens, max_new_tokens)
         try:
             with span("cts.prefill"):
@@ -667,8 +696,8 @@ class ChatTSForCausalLM:
             st.step_ptr.zero_()
             gen = torch.Generator(device=dev)
             if seed is not None:
-                gen.manual_seed(seed)
-            kseed = int(seed) if seed is not None else int.from_bytes(__import__("os").urandom(8), "little")
+                gen.manual_seed(int(seed))
+            kseed = int(seed) if seed is not None else 0
 
             def sample(lg, step):
                 if self.use_sample_kernel:

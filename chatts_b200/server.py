@@ -22,6 +22,8 @@ import uuid
 from concurrent.futures import Future
 from dataclasses import dataclass, field
 
+from .vllm_compat import IncrementalDecoder, eos_ids
+
 MAX_TS_DEFAULT = 15          # scripts/start_vllm_server.sh:9  (--limit-mm-per-prompt timeseries=15)
 
 
@@ -124,7 +126,9 @@ class Engine:
                 sp = SamplingParams(**job.params)
                 reqs = [{"prompt": j.prompt, "multi_modal_data": {"timeseries": j.series}} if j.series else {"prompt": j.prompt} for j in batch]
                 if job.stream_q is not None:
-                    outs = self.llm.generate(reqs, sp, streamer=_QueueStreamer(job.stream_q, self.llm.tokenizer))
+                    gd = getattr(self.llm.model, "generation_defaults", None) or {}
+                    stop_ids = [] if sp.ignore_eos else eos_ids(self.llm.model.config, sp.stop_token_ids, gd.get("eos_token_id"))
+                    outs = self.llm.generate(reqs, sp, streamer=_QueueStreamer(job.stream_q, self.llm.tokenizer, stop_ids))
                 else:
                     outs = self.llm.generate(reqs, sp)
                 for j, o in zip(batch, outs):
@@ -143,7 +147,7 @@ class Engine:
         """Iteration-level batching (engine.ContinuousEngine): requests join the static decode slots between graph replays and
         leave them at EOS / max_tokens; streaming requests get their new tokens after every round."""
         from .engine import ContinuousEngine
-        from .vllm_compat import CompletionOutput, RequestOutput
+        from .vllm_compat import CompletionOutput, RequestOutput, cut_at_stop, cut_at_stop_string, decode_text
         llm = self.llm
         eng = ContinuousEngine(llm.model, steps_per_round=self.steps_per_round)
         jobs, sent = {}, {}
@@ -152,20 +156,22 @@ class Engine:
             try:
                 enc = llm.processor(text=[job.prompt], timeseries=job.series, padding=True, return_tensors="pt")
                 p = job.params
+                gd = getattr(llm.model, "generation_defaults", None) or {}
+                job.stop_ids = eos_ids(llm.model.config, p.get("stop_token_ids"), gd.get("eos_token_id"))
                 rid = eng.add_request(enc["input_ids"][0], enc["timeseries"], max_new_tokens=p.get("max_tokens", 16),
-                                      eos_token_id=(list(p["stop_token_ids"]) if p.get("stop_token_ids") else None),
-                                      ignore_eos=p.get("ignore_eos", False))
+                                      eos_token_id=job.stop_ids, ignore_eos=p.get("ignore_eos", False))
                 jobs[rid], sent[rid] = job, 0
+                if job.stream_q is not None:
+                    job.decoder = IncrementalDecoder(llm.tokenizer)
             except Exception as e:
                 job.future.set_exception(e)
                 if job.stream_q is not None:
                     job.stream_q.put(None)
 
-        def text_of(job, toks):
-            text = llm.tokenizer.decode(toks)
-            stops = job.params.get("stop") or []
-            cut = min([text.find(st) for st in stops if st and st in text], default=-1)
-            return text[:cut] if cut >= 0 else text
+        def finish(job, tokens):
+            toks, fin = cut_at_stop(tokens, job.stop_ids, job.params.get("ignore_eos", False))
+            text, hit = cut_at_stop_string(decode_text(llm.tokenizer, toks), job.params.get("stop") or [])
+            return CompletionOutput(text, toks, "stop" if hit else fin)
 
         while not self.stop:
             if not eng.has_work():
@@ -197,18 +203,28 @@ class Engine:
             for r in list(eng.active.values()) + list(finished):       # streaming: hand over what the round produced
                 job = jobs.get(r.rid)
                 if job is not None and job.stream_q is not None:
-                    for t in r.tokens[sent[r.rid]:]:
-                        job.stream_q.put(llm.tokenizer.decode([t]))
-                    sent[r.rid] = len(r.tokens)
+                    new, _ = cut_at_stop(r.tokens, job.stop_ids, job.params.get("ignore_eos", False))
+                    piece = job.decoder.push(new[sent[r.rid]:])          # cumulative decode, new suffix only; the stop token is never streamed
+                    if piece:
+                        job.stream_q.put(piece)
+                    sent[r.rid] = len(new)
             for r in finished:
                 job = jobs.pop(r.rid, None)
                 sent.pop(r.rid, None)
                 if job is None:
                     continue
+                if r.error is not None:                       # not admitted (over-long prompt, series mismatch, larger than the pool)
+                    job.future.set_exception(r.error)
+                    if job.stream_q is not None:
+                        job.stream_q.put(None)
+                    continue
                 n = max(1, int(job.params.get("n", 1)))
-                out = CompletionOutput(text_of(job, r.tokens), list(r.tokens))
+                out = finish(job, r.tokens)
                 job.future.set_result(RequestOutput(job.prompt, [out] * n))
                 if job.stream_q is not None:
+                    tail = job.decoder.flush()
+                    if tail:
+                        job.stream_q.put(tail)
                     job.stream_q.put(None)
         eng.close()
 
@@ -216,15 +232,22 @@ class Engine:
 class _QueueStreamer:
     """HF-streamer protocol (put / end) -> per-token text pieces on a queue (single-request batches)."""
 
-    def __init__(self, q, tokenizer):
-        self.q, self.tok = q, tokenizer
+    def __init__(self, q, tokenizer, stop_ids=()):
+        self.q, self.dec, self.stop, self.ended = q, IncrementalDecoder(tokenizer), set(int(t) for t in stop_ids), False
 
     def put(self, ids):
         t = int(ids.reshape(-1)[0])
-        self.q.put(self.tok.decode([t]))
+        if self.ended or t in self.stop:          # the stop token (and the pad fill after it) is not text
+            self.ended = True
+            return
+        piece = self.dec.push([t])                # cumulative decode: multi-byte characters arrive whole
+        if piece:
+            self.q.put(piece)
 
     def end(self):
-        pass
+        tail = self.dec.flush()
+        if tail:
+            self.q.put(tail)
 
 
 def _sampling_from_body(body):
@@ -300,7 +323,7 @@ def create_app(llm, served_model_name="chatts", batch_window_ms=5.0, max_ts_per_
             raise HTTPException(400, str(e))
         choices = []
         for i, c in enumerate(out.outputs):
-            fin = "length" if len(c.token_ids) >= params["max_tokens"] else "stop"
+            fin = c.finish_reason or ("length" if len(c.token_ids) >= params["max_tokens"] else "stop")
             choices.append({"index": i, "message": {"role": "assistant", "content": c.text}, "finish_reason": fin} if chat else
                            {"index": i, "text": c.text, "finish_reason": fin})
         return JSONResponse({"id": rid, "object": "chat.completion" if chat else "text_completion", "created": created,

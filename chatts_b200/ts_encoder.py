@@ -73,6 +73,11 @@ class TimeSeriesEmbedding:
             # reference behaviour: self.padding_idx is read at :128 but defined only under
             # use_position_embedding (:76) -> AttributeError for ragged lengths
             raise AttributeError("'TimeSeriesEmbedding' object has no attribute 'padding_idx'")
+        if self.mode == 1 and n > 0 and int(valid_h.max()) > self.max_sequence_length:
+            # reference behaviour: position ids 0..valid-1 index nn.Embedding(max_sequence_length + 1, emb) (chatts_vllm.py:76-80,
+            # 119,163-165) -> IndexError for a series longer than the table; the kernel must never read past pos_table
+            raise IndexError(f"index out of range in self: series of {int(valid_h.max())} points exceeds "
+                             f"max_sequence_length {self.max_sequence_length} of the position embedding")
         if total == 0:
             feats = torch.empty(0, self.hidden_size, device=self.device)      # :191 (default dtype)
             return (feats if out is None else None), cnt_h.to(torch.int64)

@@ -35,6 +35,66 @@ class SamplingParams:
 class CompletionOutput:
     text: str
     token_ids: list
+    finish_reason: str = None     # "stop" (EOS / stop id / stop string) or "length"
+
+
+def eos_ids(config, stop_token_ids=None, extra=None):
+    """Stop ids of a request: the UNION of the model's EOS ids (config / generation_config) and the request's stop_token_ids
+    (vLLM adds stop_token_ids to the EOS stop, it does not replace it; llm_utils.py:153 passes both Qwen ids explicitly)."""
+    out = []
+    for src in (getattr(config, "eos_token_id", None), extra, stop_token_ids):
+        if src is None:
+            continue
+        out += [int(t) for t in (src if isinstance(src, (list, tuple, set)) else [src])]
+    return sorted(set(out))
+
+
+def cut_at_stop(tokens, stop_ids, ignore_eos=False):
+    """(tokens before the first stop id, finish_reason).  The stop token itself is not part of the completion (vLLM strips it; the
+    reference decodes with skip_special_tokens=True); whatever generate() padded a finished row with is dropped with it."""
+    toks = [int(t) for t in tokens]
+    if not ignore_eos:
+        stop = set(int(t) for t in stop_ids)
+        for i, t in enumerate(toks):
+            if t in stop:
+                return toks[:i], "stop"
+    return toks, "length"
+
+
+def decode_text(tokenizer, tokens):
+    """tokenizer.decode(..., skip_special_tokens=True) (inference_tsmllm_deepspeed.py:104-106), for tokenizers that take the flag."""
+    try:
+        return tokenizer.decode(tokens, skip_special_tokens=True)
+    except TypeError:
+        return tokenizer.decode(tokens)
+
+
+def cut_at_stop_string(text, stops):
+    cut = min([text.find(st) for st in stops if st and st in text], default=-1)
+    return (text[:cut], True) if cut >= 0 else (text, False)
+
+
+class IncrementalDecoder:
+    """Streaming detokeniser: decodes the CUMULATIVE ids and emits only the new suffix, holding back a trailing U+FFFD (an
+    incomplete multi-byte character, e.g. half of a Chinese character) until the bytes that complete it arrive."""
+
+    def __init__(self, tokenizer):
+        self.tok, self.ids, self.sent = tokenizer, [], 0
+
+    def push(self, token_ids):
+        self.ids += [int(t) for t in token_ids]
+        text = decode_text(self.tok, self.ids)
+        while text.endswith("\ufffd"):
+            text = text[:-1]
+        piece = text[self.sent:]
+        self.sent = max(self.sent, len(text))
+        return piece
+
+    def flush(self):
+        text = decode_text(self.tok, self.ids)
+        piece = text[self.sent:]
+        self.sent = len(text)
+        return piece
 
 
 @dataclass
@@ -81,6 +141,8 @@ class LLM:
         outs = []
         bs = self.model.max_batch
         stops = [sp.stop] if isinstance(sp.stop, str) else list(sp.stop or [])
+        gd = getattr(self.model, "generation_defaults", None) or {}
+        stop_ids = eos_ids(self.model.config, sp.stop_token_ids, gd.get("eos_token_id"))
         for i0 in range(0, len(inputs), bs):
             chunk = inputs[i0:i0 + bs]
             prompts, series = [], []
@@ -98,14 +160,12 @@ class LLM:
             ids = self.model.generate(**enc, max_new_tokens=sp.max_tokens, do_sample=sp.temperature > 0,
                                       temperature=sp.temperature, top_p=sp.top_p, top_k=(sp.top_k if sp.top_k and sp.top_k > 0 else None),
                                       ignore_eos=sp.ignore_eos, seed=(None if sp.seed is None else sp.seed + i0),
-                                      eos_token_id=(list(sp.stop_token_ids) or None), streamer=streamer)
+                                      eos_token_id=stop_ids, streamer=streamer)
             for b, req in enumerate(chunk):
-                toks = ids[b, S:].tolist()
-                text = self.tokenizer.decode(toks)
-                cut = min([text.find(st) for st in stops if st and st in text], default=-1)
-                if cut >= 0:
-                    text = text[:cut]
-                outs.append(RequestOutput(req["prompt"], [CompletionOutput(text, toks)]))
+                # a row ends at ITS first stop id (the batch-wide tail after it is the pad fill of generate())
+                toks, fin = cut_at_stop(ids[b, S:].tolist(), stop_ids, sp.ignore_eos)
+                text, hit = cut_at_stop_string(decode_text(self.tokenizer, toks), stops)
+                outs.append(RequestOutput(req["prompt"], [CompletionOutput(text, toks, "stop" if hit else fin)]))
         return outs
 
 
@@ -175,6 +235,9 @@ class AsyncLLMEngine:
         fut = loop.run_in_executor(None, work)
         toks = []
         stops = [sp.stop] if isinstance(sp.stop, str) else list(sp.stop or [])
+        gd = getattr(self.llm.model, "generation_defaults", None) or {}
+        stop_ids = set(eos_ids(self.llm.model.config, sp.stop_token_ids, gd.get("eos_token_id")))
+        ended = False
         while True:
             item = await q.get()
             if isinstance(item, tuple) and item[0] is done:
@@ -183,8 +246,13 @@ class AsyncLLMEngine:
                     raise item[1]
                 yield item[1]
                 return
+            if ended or (not sp.ignore_eos and any(t in stop_ids for t in item)):
+                ended = True                           # the stop token and anything after it never reach the stream
+                continue
             toks += item
-            text = self.llm.tokenizer.decode(toks)
+            text = decode_text(self.llm.tokenizer, toks)
             if any(st and st in text for st in stops):
                 continue                               # the final output carries the text cut at the stop string
+            if text.endswith("\ufffd"):
+                continue                               # incomplete multi-byte character: wait for the bytes that complete it
             yield RequestOutput(req["prompt"], [CompletionOutput(text, list(toks))])

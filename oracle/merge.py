@@ -12,6 +12,10 @@ chatts/vllm/chatts_vllm.py:441):
   INSERTS the P_i patch rows of the i-th series between them, so the merged length is
   S_text + sum(P) (token accounting in chatts/utils/inference_tsmllm_deepspeed.py:86,110).  Series are
   consumed in prompt order across the flattened batch (inference_tsmllm_deepspeed.py:75-80).
+  ``mode="overwrite"`` states the other candidate for the absent remote code: the ``<ts><ts/>`` pair gives up its two
+  slots and the P_i rows take their place (P_i - 2 new positions; every ``<ts>`` / ``<ts/>`` token is dropped), which is
+  also what the reference's vLLM path does with the pair (chatts_vllm.py:438-444).  Which of the two the released
+  checkpoints use can only be settled against a real checkpoint -- both are kept, ``insert`` is the default.
 
 Pure-Python loops on purpose: this is the slow, obviously-right statement the vectorised host code in
 chatts_b200/layout.py is checked against (bit-exact indices).
@@ -19,7 +23,7 @@ chatts_b200/layout.py is checked against (bit-exact indices).
 import torch
 
 
-def hf_layout(input_ids, attention_mask, patch_cnt, ts_start):
+def hf_layout(input_ids, attention_mask, patch_cnt, ts_start, mode="insert"):
     """input_ids/attention_mask: [B,S] (any padding side); patch_cnt: list[int], one per ``<ts>`` in
     batch-major prompt order.  Returns per sample a list of entries, one per merged position:
         ("tok", column_in_input_ids)  or  ("ts", global_patch_row)
@@ -33,7 +37,8 @@ def hf_layout(input_ids, attention_mask, patch_cnt, ts_start):
         for s in range(len(ids[b])):
             if not am[b][s]:
                 continue
-            ent.append(("tok", s))
+            if mode == "insert" or ids[b][s] not in (ts_start, ts_start + 1):
+                ent.append(("tok", s))
             if ids[b][s] == ts_start:
                 assert series < len(patch_cnt), "more <ts> tokens than series"   # encoding_utils.py:58,68
                 for _ in range(int(patch_cnt[series])):
@@ -45,9 +50,9 @@ def hf_layout(input_ids, attention_mask, patch_cnt, ts_start):
     return out
 
 
-def hf_merge(input_ids, attention_mask, embed_table, ts_feats, patch_cnt, ts_start):
-    """Per-sample merged embeddings [T_b, H] in the HF insert layout."""
-    lay = hf_layout(input_ids, attention_mask, patch_cnt, ts_start)
+def hf_merge(input_ids, attention_mask, embed_table, ts_feats, patch_cnt, ts_start, mode="insert"):
+    """Per-sample merged embeddings [T_b, H] in the HF layout (``mode``: insert | overwrite)."""
+    lay = hf_layout(input_ids, attention_mask, patch_cnt, ts_start, mode)
     ids = torch.as_tensor(input_ids)
     res = []
     for b, ent in enumerate(lay):

@@ -1,14 +1,13 @@
 """cts_decoder_step / cts_rmsnorm / cts_lm_head (csrc/decoder_step.cu: host-side executors over the validated kernels) against
 the per-kernel Python orchestration: the same launches in the same order must give bit-identical tokens and logits.
-PENDING: written after the round-1 GPU budget was spent -- xfail(strict=False) until it has run on a B200."""
+First executed on a B200 by the round-1 driver run (GPUTEST_r01.json); plain tests since round 2 (no xfail markers)."""
 import numpy as np
 import pytest
 import torch
 
 from tests.gpu_util import ctx
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first B200 execution pending (round-1 GPU budget exhausted before this code could run)")]
+pytestmark = pytest.mark.gpu
 DT = torch.bfloat16
 
 

@@ -1,6 +1,6 @@
 """cts_sample_advance (csrc/sampling.cu) against its CPU statement (tests/cabi_double.py ``sample_reference``, itself checked
-against transformers' logits warpers in tests/test_host_sampling.py).  PENDING: the kernel was written after the round-1 GPU
-budget was spent and has not executed on a B200 yet -- xfail(strict=False) until it has (XPASS = validated)."""
+against transformers' logits warpers in tests/test_host_sampling.py).  Validated on a B200 by the round-1
+driver run (GPUTEST_r01.json: every case passed); plain tests since round 2."""
 import numpy as np
 import pytest
 import torch
@@ -8,8 +8,7 @@ import torch
 from tests.cabi_double import TorchDouble
 from tests.gpu_util import ctx, record
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first B200 execution pending (round-1 GPU budget exhausted before this kernel could run)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("vocab,dtype", [(1000, torch.bfloat16), (151936, torch.bfloat16), (1003, torch.bfloat16), (4096, torch.float16)])

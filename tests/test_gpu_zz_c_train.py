@@ -1,10 +1,10 @@
-"""The part of the LoRA fine-tune step (row A9) that has NOT yet executed on a B200: the attention LSE flag, the attention
+"""The part of the LoRA fine-tune step (row A9) that was written after the round-1 GPU budget was spent: the attention LSE flag, the attention
 backward (HMMA), AdamW + clip, adapter packing and the whole-step tests against oracle/lora.py -- compiled for sm_100a,
 orchestration parity-checked on CPU through the double (tools/dryrun_train_gpu_tests.py runs this file's logic on CPU), written
-after the round-1 GPU budget was spent.  PENDING = xfail(strict=False): an XPASS in the report means "validated on
-hardware", an XFAIL names a kernel to fix.  The validated kernels are in tests/test_gpu_train_kernels.py.  The zz files
+after the round-1 GPU budget was spent and validated by the round-1 driver run on a B200 (every case passed); plain tests
+since round 2.  The kernels validated earlier are in tests/test_gpu_train_kernels.py.  The zz files
 sort last on purpose (a sticky CUDA error here cannot poison validated tests); none of the kernels exercised here spins on a
-flag.  Remove the markers once green (tools/gpu_train_checks.sh runs them with --runxfail)."""
+flag."""
 import math
 
 import numpy as np
@@ -27,11 +27,9 @@ def _rn(g, *shape, std=1.0, dtype=DT):
 
 
 pytestmark = pytest.mark.gpu
-PENDING = pytest.mark.xfail(strict=False, reason="first B200 execution pending (round-1 GPU budget exhausted before this kernel could run)")
 
 
 # ------------------------------------------------------------------------------------------------ optimiser + packing
-@PENDING
 def test_adamw_and_clip_match_torch():
     c = ctx()
     g = _g(1)
@@ -56,7 +54,6 @@ def test_adamw_and_clip_match_torch():
     assert float(out[1]) == 1.0
 
 
-@PENDING
 def test_lora_pack_matches_double():
     from chatts_b200._cabi import PACK_DESC_LONGS
     c = ctx()
@@ -87,7 +84,6 @@ def _attn_inputs(d, lens, nh=4, nkv=2, dtype=DT):
     return T, q, k, v, do, cu
 
 
-@PENDING
 @pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("lens", [[1], [5, 64, 65], [130, 17, 200, 1], [577]])
 def test_prefill_lse_matches_prefill_and_logsumexp(d, lens):
@@ -108,7 +104,6 @@ def test_prefill_lse_matches_prefill_and_logsumexp(d, lens):
     assert e < 2e-3
 
 
-@PENDING
 @pytest.mark.parametrize("d", [64, 128])
 @pytest.mark.parametrize("lens", [[1], [5, 64, 65], [130, 17, 200, 1], [577], [64, 128]])
 def test_attention_backward(d, lens):
@@ -140,7 +135,6 @@ def test_attention_backward(d, lens):
     assert torch.equal(dq, dq2) and torch.equal(dk, dk2) and torch.equal(dv, dv2)
 
 
-@PENDING
 def test_attention_backward_gqa_group_of_8_fp16():
     c = ctx()
     d, nh, nkv, lens = 128, 8, 1, [100, 260]
@@ -176,7 +170,6 @@ def _trainer_case(qwen3, head_dim=64):
     return cfg, sd, model, proc, RECORDS
 
 
-@PENDING
 @pytest.mark.parametrize("qwen3,head_dim", [(False, 64), (True, 64), (True, 128)])
 def test_train_step_matches_oracle(qwen3, head_dim):
     from chatts_b200.train import LoraTrainer, encode_records
@@ -205,7 +198,6 @@ def test_train_step_matches_oracle(qwen3, head_dim):
     assert worst < 8e-2 and cos > 0.998, (worst, cos)
 
 
-@PENDING
 def test_training_reduces_loss_and_merge_roundtrip(tmp_path):
     from chatts_b200.train import LoraTrainer, encode_records
 
@@ -248,7 +240,6 @@ def _id_batch(cfg, samples, seed, n_series=2, series_len=256, prefix=20, prompt=
             "timeseries": torch.from_numpy(ts).to(torch.float32)}
 
 
-@PENDING
 @pytest.mark.parametrize("full_dims", [False, True])
 def test_gradient_is_the_directional_derivative_of_the_loss(full_dims):
     """Size-independent property of the whole backward (no oracle needed, so it also runs at the ChatTS-8B layer shape of
@@ -309,7 +300,6 @@ def test_gradient_is_the_directional_derivative_of_the_loss(full_dims):
     assert abs(fd - slope) < 0.15 * abs(slope) + 1e-4, (fd, slope)
 
 
-@PENDING
 @pytest.mark.parametrize("t,m,r,il", [(37, 256, 8, 0), (5000, 704, 16, 0), (300, 128, 16, 1), (300, 128, 16, 2), (9000, 64, 16, 0),
                                       (100, 4096, 16, 0), (513, 200, 24, 0)])
 def test_lora_wgrad_tensor_core_variant(t, m, r, il, monkeypatch):

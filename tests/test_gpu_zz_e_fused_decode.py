@@ -1,15 +1,14 @@
 """cts_gemm_decode_fused (csrc/gemm_decode_fused.cu: the K splits of a tile reduce over distributed shared memory inside one
 cluster and apply the projection's tail) against the two-launch path it replaces -- cts_gemm(CTS_EPI_PARTIAL_F32) + cts_reduce_* /
 cts_qkv_rope_cache -- which must be reproduced BIT FOR BIT (same summation order), and through generate().
-PENDING: never executed on a B200 (written after the round-1 GPU budget was spent); xfail(strict=False) until it has."""
+Validated on a B200 by the round-1 driver run (GPUTEST_r01.json: every case passed); plain tests since round 2."""
 import numpy as np
 import pytest
 import torch
 
 from tests.gpu_util import ctx, record
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first B200 execution pending (round-1 GPU budget exhausted before this kernel could run)")]
+pytestmark = pytest.mark.gpu
 DT = torch.bfloat16
 EPI_PARTIAL = 3
 

@@ -34,11 +34,12 @@ def _rand_case(rng, B, S, left_pad):
 
 @pytest.mark.parametrize("seed", range(8))
 @pytest.mark.parametrize("left_pad", [True, False])
-def test_hf_layout_matches_oracle(seed, left_pad):
+@pytest.mark.parametrize("mode", ["insert", "overwrite"])
+def test_hf_layout_matches_oracle(seed, left_pad, mode):
     rng = np.random.default_rng(seed)
     ids, am, pc = _rand_case(rng, B=int(rng.integers(1, 5)), S=40, left_pad=left_pad)
-    lay = L.hf_layout(ids, am, pc, TS)
-    ref = om.hf_layout(ids, am, pc.tolist(), TS)
+    lay = L.hf_layout(ids, am, pc, TS, mode)
+    ref = om.hf_layout(ids, am, pc.tolist(), TS, mode)
     flat = [e for sample in ref for e in sample]
     assert lay.total == len(flat)
     assert lay.cu_seqlens.tolist() == np.cumsum([0] + [len(s) for s in ref]).tolist()
@@ -59,6 +60,18 @@ def test_hf_layout_count_mismatch_raises():
         L.hf_layout(ids, None, [3, 4], TS)
     with pytest.raises(AssertionError):
         om.hf_layout(ids, np.ones_like(ids), [3, 4], TS)
+
+
+def test_hf_layout_overwrite_mode_replaces_the_pair():
+    """mode "overwrite": <ts><ts/> give up their two slots, the P rows take their place (P - 2 new positions per series)."""
+    ids = np.array([[5, TS, TS + 1, 6, TS, TS + 1]])
+    lay = L.hf_layout(ids, None, [3, 1], TS, "overwrite")
+    assert lay.ids.tolist() == [5, -1, -1, -1, 6, -1] and lay.row_map.tolist() == [1, 2, 3, 5]
+    assert lay.src_col.tolist() == [0, -1, -1, -1, 3, -1] and lay.total == 6 + (3 - 2) + (1 - 2)
+    ins = L.hf_layout(ids, None, [3, 1], TS, "insert")
+    assert ins.total == 6 + 3 + 1 and ins.ids.tolist() == [5, TS, -1, -1, -1, TS + 1, 6, TS, -1, TS + 1]
+    with pytest.raises(ValueError):
+        L.hf_layout(ids, None, [3, 1], TS, "replace")
 
 
 def test_hf_layout_empty_series_and_no_series():
