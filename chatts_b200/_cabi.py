@@ -29,7 +29,7 @@ SYMBOLS = [
     "cts_ce_loss_grad", "cts_gather_rows", "cts_lora_wgrad", "cts_adamw", "cts_grad_norm_ws_floats", "cts_grad_norm_clip",
     "cts_lora_pack",
     "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step", "cts_ts_encode", "cts_gemm_decode_fused",
-    "cts_peer_ll_region_bytes", "cts_peer_allreduce_ll",
+    "cts_peer_ll_region_bytes", "cts_peer_allreduce_ll", "cts_trace_enable",
 ]
 FUSED_RESIDUAL, FUSED_SWIGLU, FUSED_QKV_ROPE = 0, 1, 2
 PACK_DESC_LONGS = 12
@@ -47,6 +47,8 @@ class GemmArgs(C.Structure):
         ("w_ld", C.c_longlong), ("x_ld", C.c_longlong), ("out_ld", C.c_longlong),
         ("dtype", C.c_int), ("epilogue", C.c_int), ("split_k", C.c_int), ("reserved", C.c_int),
         ("splitk_ws", C.c_void_p), ("tile_counters", C.c_void_p),
+        ("next_w", C.c_void_p), ("next_n", C.c_longlong), ("next_k", C.c_longlong), ("next_ld", C.c_longlong),
+        ("next_split", C.c_int), ("next_reserved", C.c_int), ("next_prefetch_bytes", C.c_longlong),
     ]
 
 
@@ -138,6 +140,7 @@ def load_library():
     lib.cts_peer_ll_region_bytes.restype = ll
     lib.cts_peer_allreduce_ll.argtypes = [vp, vp, i, vp, ll, vp, i, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
     lib.cts_peer_allreduce_ll.restype = i
+    lib.cts_trace_enable.argtypes = [vp, vp]
     lib.cts_decode_chain.argtypes = [vp, C.POINTER(ChainArgs), vp]
     lib.cts_decode_chain.restype = i
     lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
@@ -234,6 +237,25 @@ class Context:
                 import sys
                 raise CtsError(f"kernel fault inside Context.{sys._getframe(1).f_code.co_name}: {e}") from e
 
+    # ------------------------------------------------------------------ device-side timeline (debug aid, csrc/trace.cuh)
+    def trace_begin(self, capacity=1 << 20):
+        buf = torch.zeros(2 + 2 * capacity, dtype=torch.int64, device=f"cuda:{self.device}")
+        buf[1] = capacity
+        torch.cuda.synchronize()
+        rc = self.lib.cts_trace_enable(self.h, _p(buf))
+        if rc != OK:
+            raise CtsError(self.lib.cts_last_error(self.h).decode())
+        self._trace = buf
+        return buf
+
+    def trace_end(self):
+        """-> int64 array [n, 2] of {tag, globaltimer ns} records; tracing is switched off."""
+        torch.cuda.synchronize()
+        self.lib.cts_trace_enable(self.h, None)
+        buf, self._trace = self._trace, None
+        n = min(int(buf[0]), int(buf[1]))
+        return buf[2: 2 + 2 * n].view(n, 2).cpu().numpy()
+
     # ------------------------------------------------------------------ TS front end
     def ts_patch_count(self, x, num_features, patch_size):
         n = x.shape[0]
@@ -260,9 +282,13 @@ class Context:
         return int(self.lib.cts_gemm_suggest_split(self.h, n, k, t, int(dual)))
 
     def gemm(self, x, w, out, *, w2=None, bias=None, residual=None, row_map=None, epilogue=EPI_NONE, split_k=1, t=None,
-             splitk_ws=None, tile_counters=None):
-        """out[T,N] (or fp32 partial [S,T,N]) = x[T,K] @ w[N,K]^T with the fused epilogue."""
+             splitk_ws=None, tile_counters=None, next_w=None, next_split=1, next_bytes=0):
+        """out[T,N] (or fp32 partial [S,T,N]) = x[T,K] @ w[N,K]^T with the fused epilogue.
+        next_w / next_split / next_bytes: the weight the next GEMM of the chain streams (L2 prefetch hint, decode-sized t)."""
         a = GemmArgs()
+        if next_w is not None and next_bytes > 0:
+            a.next_w, a.next_n, a.next_k, a.next_ld = next_w.data_ptr(), next_w.shape[0], next_w.shape[1], next_w.stride(0)
+            a.next_split, a.next_prefetch_bytes = int(next_split), int(next_bytes)
         a.w, a.w2, a.x = w.data_ptr(), (w2.data_ptr() if w2 is not None else None), x.data_ptr()
         a.bias = bias.data_ptr() if bias is not None else None
         a.residual = residual.data_ptr() if residual is not None else None

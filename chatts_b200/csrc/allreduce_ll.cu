@@ -29,6 +29,7 @@
 //   SQ  [owner  ][max_tokens][8]   one float per unit               at max_tokens*h*12
 // grid (C, T): CTA (c, t) handles, of token t, sub-slice c (h/(W*C) columns) of EVERY owner's chunk.
 #include "common.cuh"
+#include "trace.cuh"
 
 namespace {
 
@@ -89,7 +90,9 @@ peer_allreduce_ll_kernel(const float* __restrict__ local_part, int S, long long 
                          int* __restrict__ state, int rank, int max_tokens, const T* __restrict__ resid_in, T* __restrict__ resid_out,
                          const T* __restrict__ norm_w, float eps, T* __restrict__ norm_out, int h) {
   pdl_trigger();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_OTHER, 0);
   pdl_wait();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_OTHER, 1);
   const int C = (int)gridDim.x, c = (int)blockIdx.x;
   const long long t = blockIdx.y;
   const int hw = h / W, wc = hw / C;                     // owner chunk, sub-slice of this CTA (wc % 4 == 0, host-checked)
@@ -110,11 +113,21 @@ peer_allreduce_ll_kernel(const float* __restrict__ local_part, int S, long long 
     for (int u = threadIdx.x; u < W * upo; u += kLLThreads) {
       const int j = u / upo, k = (u - j * upo) * 2;
       const float* p = local_part + t * h + (long long)j * hw + c * wc + k;
+      // all partial loads of a batch in flight before the first add (a run-time-bounded loop of dependent adds pays one L2 round
+      // trip per split); the sum still runs in split order
       float2 a = *reinterpret_cast<const float2*>(p);
-      for (int s = 1; s < S; ++s) {
-        const float2 b = *reinterpret_cast<const float2*>(p + s * stride);
-        a.x += b.x;
-        a.y += b.y;
+      constexpr int kB = 8;
+      for (int s0 = 1; s0 < S; s0 += kB) {
+        float2 b[kB];
+#pragma unroll
+        for (int u = 0; u < kB; ++u)
+          if (s0 + u < S) b[u] = *reinterpret_cast<const float2*>(p + (long long)(s0 + u) * stride);
+#pragma unroll
+        for (int u = 0; u < kB; ++u)
+          if (s0 + u < S) {
+            a.x += b[u].x;
+            a.y += b[u].y;
+          }
       }
       uint8_t* dst = reg[j] + ((((long long)rank * max_tokens + t) * hw + c * wc + k) >> 1) * 16;
       st_ll(dst, __float_as_uint(a.x), __float_as_uint(a.y), epoch);
@@ -219,6 +232,7 @@ peer_allreduce_ll_kernel(const float* __restrict__ local_part, int S, long long 
   // ---- the last CTA of the grid to finish publishes the new epoch for the next call
   __syncthreads();
   if (threadIdx.x == 0) {
+    CTS_TRACE(CTS_TK_OTHER, 3);
     __threadfence();
     const int done = atomicAdd(&state[1], 1) + 1;
     if (done == (int)(gridDim.x * gridDim.y)) {
@@ -287,3 +301,5 @@ extern "C" int cts_peer_allreduce_ll(cts_ctx* ctx, const float* local_partial, i
   CTS_CUDA(ctx, e);
   return CTS_OK;
 }
+
+CTS_TRACE_SETTER(cts_trace_set_allreduce_ll)

@@ -15,6 +15,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "trace.cuh"
 #include "tensormap.cuh"
 
 namespace {
@@ -477,6 +478,7 @@ constexpr int kDecConsumers = 128;
 constexpr int kDecThreads = 160;
 constexpr int kDecStages = 3;
 constexpr int kDecTile = 64;
+constexpr int kDecMaxPagesSm = 256;   // page ids a CTA keeps in shared memory (tiles x pages per tile; beyond that: global reads)
 constexpr int kMaxGroup = 8;    // q heads per kv head (rows 8..15 of the MMA tile are padding)
 
 __host__ __device__ inline long long dec_ws_stride(int hd) { return hd + 2; }
@@ -538,14 +540,49 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
     fence_mbar_init();
   }
   __syncthreads();
-  pdl_wait();          // q, the freshly written KV row, seq_lens and the workspace all come from predecessors
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_ATTN_DECODE, 0);
 
+  // seq_lens / page_table are STEP STATE: written by the advance kernel at the end of the previous step (or by the host before
+  // the step) and by nobody inside a step, whose first kernel (embed_gather) waits for everything before it BEFORE it lets its
+  // successors start -- so they may be read ahead of the dependency wait.  So may every KV row of an earlier position: the
+  // predecessor (RoPE / KV write of THIS layer) writes only row seq_len - 1.
   const int seq_len = seq_lens[b];
   const int n_tiles = (seq_len + kDecTile - 1) / kDecTile;
   const int tps = (n_tiles + num_splits - 1) / num_splits;
   const int tl0 = split * tps, tl1 = min(n_tiles, tl0 + tps);
   const int ntl = max(tl1 - tl0, 0);
   const int npp = kDecTile / page_size;          // pages per tile
+  const int t_new = (seq_len - 1) / kDecTile;    // the tile that holds the row written by the predecessor
+  // page ids of this CTA's tiles, fetched once by the producer warp (one L2 round trip instead of one per tile inside the ring loop)
+  __shared__ int pg_s[kDecMaxPagesSm];
+  int n_pre = 0;                                 // tiles whose loads were issued before the dependency wait
+  if (warp == kDecConsumers / 32) {
+    const int n_pg = min(ntl * npp, kDecMaxPagesSm);
+    for (int i = lane; i < n_pg; i += 32) {
+      int pg = tl0 * npp + i;
+      pg = pg < max_pages ? pg : max_pages - 1;
+      pg_s[i] = page_table[(long long)b * max_pages + pg];
+    }
+    __syncwarp();
+    if (lane == 0) {
+      for (int it = 0; it < ntl && it < kDecStages && tl0 + it < t_new; ++it) {       // stage it is free: first use of the ring
+        mbar_expect_tx(&full_bar[it], (uint32_t)(2 * TILE_BYTES));
+        uint8_t* ks = smem + (size_t)it * 2 * TILE_BYTES;
+        uint8_t* vs = ks + TILE_BYTES;
+        for (int j = 0; j < npp; ++j) {
+          const int row0 = (pg_s[it * npp + j] * nkv + kvh) * page_size;
+#pragma unroll
+          for (int h = 0; h < NHALF; ++h) {
+            tma_load_2d(ks + h * HALF_BYTES + j * page_size * 128, &tm_k, &full_bar[it], h * 64, row0, CTS_L2_EVICT_FIRST);
+            tma_load_2d(vs + h * HALF_BYTES + j * page_size * 128, &tm_v, &full_bar[it], h * 64, row0, CTS_L2_EVICT_FIRST);
+          }
+        }
+        n_pre = it + 1;
+      }
+    }
+  }
+  pdl_wait();          // q and the freshly written KV row come from the predecessor; the split workspace from the previous launch
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_ATTN_DECODE, 1);
 
   // accumulators of this warp (rows g = lane/4 are real heads when g < G)
   const int g = lane >> 2, tq = lane & 3;
@@ -557,7 +594,7 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   if (warp == kDecConsumers / 32) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
-      for (int it = 0; it < ntl; ++it) {
+      for (int it = n_pre; it < ntl; ++it) {
         const int s = it % kDecStages;
         const uint32_t ph = (uint32_t)(it / kDecStages) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -565,9 +602,14 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         uint8_t* ks = smem + (size_t)s * 2 * TILE_BYTES;
         uint8_t* vs = ks + TILE_BYTES;
         for (int j = 0; j < npp; ++j) {
-          int pg = (tl0 + it) * npp + j;
-          pg = pg < max_pages ? pg : max_pages - 1;          // pages past the sequence are masked; keep the read in bounds
-          const int page = page_table[(long long)b * max_pages + pg];
+          int page;
+          if (it * npp + j < kDecMaxPagesSm) {
+            page = pg_s[it * npp + j];
+          } else {
+            int pg = (tl0 + it) * npp + j;
+            pg = pg < max_pages ? pg : max_pages - 1;        // pages past the sequence are masked; keep the read in bounds
+            page = page_table[(long long)b * max_pages + pg];
+          }
           const int row0 = (page * nkv + kvh) * page_size;
 #pragma unroll
           for (int h = 0; h < NHALF; ++h) {
@@ -704,14 +746,34 @@ attn_decode_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   for (int i = tid; i < G * HD; i += kDecThreads) {
     const int gg = i / HD, d = i % HD;
     const float* w = ws + (head0 + gg) * num_splits * wstride;
+    // all loads of a batch of splits are issued before the first use: a run-time-bounded loop of dependent uses costs one L2 round
+    // trip per split (16 splits at b = 1: ~20 us of pure latency, measured with csrc/trace.cuh).  Same arithmetic, same order.
+    constexpr int kMB = 8;
     float M = -INFINITY;
-    for (int s2 = 0; s2 < num_splits; ++s2) M = fmaxf(M, __ldcg(w + s2 * wstride));
+    for (int s0 = 0; s0 < num_splits; s0 += kMB) {
+      float mv[kMB];
+#pragma unroll
+      for (int u = 0; u < kMB; ++u) mv[u] = s0 + u < num_splits ? __ldcg(w + (s0 + u) * wstride) : -INFINITY;
+#pragma unroll
+      for (int u = 0; u < kMB; ++u) M = fmaxf(M, mv[u]);
+    }
     float L = 0.f, O = 0.f;
-    for (int s2 = 0; s2 < num_splits; ++s2) {
-      const float ms = __ldcg(w + s2 * wstride);
-      const float f = ms > -INFINITY ? exp2f(ms - M) : 0.f;
-      L += __ldcg(w + s2 * wstride + 1) * f;
-      O += __ldcg(w + s2 * wstride + 2 + d) * f;
+    for (int s0 = 0; s0 < num_splits; s0 += kMB) {
+      float mv[kMB], lv[kMB], ov[kMB];
+#pragma unroll
+      for (int u = 0; u < kMB; ++u) {
+        const bool ok = s0 + u < num_splits;
+        mv[u] = ok ? __ldcg(w + (s0 + u) * wstride) : -INFINITY;
+        lv[u] = ok ? __ldcg(w + (s0 + u) * wstride + 1) : 0.f;
+        ov[u] = ok ? __ldcg(w + (s0 + u) * wstride + 2 + d) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kMB; ++u)
+        if (s0 + u < num_splits) {
+          const float f = mv[u] > -INFINITY ? exp2f(mv[u] - M) : 0.f;
+          L += lv[u] * f;
+          O += ov[u] * f;
+        }
     }
     out[(head0 + gg) * HD + d] = DT<T>::from_f(L > 0.f ? O / L : 0.f);
   }
@@ -840,3 +902,5 @@ extern "C" int cts_attn_decode(cts_ctx* ctx, const void* q, const void* k_cache,
 #undef DEC_LAUNCH
   return CTS_OK;
 }
+
+CTS_TRACE_SETTER(cts_trace_set_attention)

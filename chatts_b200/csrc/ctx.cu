@@ -72,6 +72,10 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
   ctx->norm_cluster = e5 ? atoi(e5) : 8;
   const char* e2 = getenv("CTS_DECODE_SMEM_KB");
   ctx->decode_stages = e2 ? atoi(e2) : 75;   // 3 CTAs/SM x 3-4 stages measured best on B200 (profiles/r1_sweep_decode_gemm.txt)
+  const char* e6 = getenv("CTS_NEXT_PREFETCH");
+  ctx->no_next_prefetch = (e6 && atoi(e6) == 0) ? 1 : 0;
+  const char* e7 = getenv("CTS_NEXT_PREFETCH_MB");
+  ctx->next_prefetch_mb = e7 ? atoi(e7) : 48;
   *out = ctx;
   return CTS_OK;
 }
@@ -115,5 +119,19 @@ int cts_make_tmap_2d_dense(cts_ctx* ctx, CUtensorMap* tm, const void* base, long
                                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cts_set_error(ctx, CTS_ERR_CUDA, "cuTensorMapEncodeTiled (dense) failed: CUresult %d", (int)r);
+  return CTS_OK;
+}
+
+// Optional device-side timeline (csrc/trace.cuh): installs `buf` ([0] cursor = 0, [1] capacity in records, then {tag, time} pairs;
+// NULL switches tracing off) in every instrumented translation unit.  A debugging / profiling aid; never on in a measurement.
+extern "C" int cts_trace_set_gemm(unsigned long long* buf);
+extern "C" int cts_trace_set_elementwise(unsigned long long* buf);
+extern "C" int cts_trace_set_attention(unsigned long long* buf);
+extern "C" int cts_trace_set_allreduce_ll(unsigned long long* buf);
+extern "C" int cts_trace_set_fused(unsigned long long* buf);
+extern "C" int cts_trace_enable(cts_ctx* ctx, unsigned long long* buf) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  if (cts_trace_set_gemm(buf) || cts_trace_set_elementwise(buf) || cts_trace_set_attention(buf) || cts_trace_set_allreduce_ll(buf) || cts_trace_set_fused(buf))
+    return cts_set_error(ctx, CTS_ERR_CUDA, "cts_trace_enable: cudaMemcpyToSymbol failed");
   return CTS_OK;
 }

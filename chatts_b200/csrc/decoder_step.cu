@@ -31,14 +31,21 @@ extern "C" int cts_lm_head(cts_ctx* ctx, const void* hidden, const void* w, void
   return cts_gemm(ctx, &a, stream);
 }
 
+// the weight the NEXT GEMM of the chain streams (L2 prefetch hint of cts_gemm_args, as chatts_b200/model.py passes it)
+struct NextW { const void* w; long long n, k; int split; };
+
 static int step_gemm_partial(cts_ctx* ctx, const void* x, const void* w, long long n, long long k, long long t, int split, float* ws,
-                             int dtype, void* stream) {
+                             int dtype, void* stream, NextW nx = NextW{nullptr, 0, 0, 0}) {
   cts_gemm_args a;
   memset(&a, 0, sizeof(a));
   a.w = w; a.x = x; a.out = ws;
   a.n = n; a.k = k; a.t = t;
   a.w_ld = k; a.x_ld = k; a.out_ld = n;
   a.dtype = dtype; a.epilogue = CTS_EPI_PARTIAL_F32; a.split_k = split;
+  if (nx.w != nullptr && t <= 32 && ctx->next_prefetch_mb > 0) {
+    a.next_w = nx.w; a.next_n = nx.n; a.next_k = nx.k; a.next_ld = nx.k; a.next_split = nx.split;
+    a.next_prefetch_bytes = (long long)ctx->next_prefetch_mb << 20;
+  }
   return cts_gemm(ctx, &a, stream);
 }
 
@@ -74,20 +81,21 @@ extern "C" int cts_decoder_step(cts_ctx* ctx, const cts_decoder_step_args* a, vo
     const cts_layer_weights* w = &a->layers[l];
     CTS_CHECK_ARG(ctx, w->wqkv && w->wo && w->wgu && w->wd && w->ln1 && w->ln2 && w->k_cache && w->v_cache, "null layer tensor");
     // QKV projection (+bias, +Qwen3 q/k norm) + RoPE + paged KV write
-    STEP(step_gemm_partial(ctx, a->xn, w->wqkv, QKV, H, T, a->split_qkv, a->ws, dt, stream));
+    STEP(step_gemm_partial(ctx, a->xn, w->wqkv, QKV, H, T, a->split_qkv, a->ws, dt, stream, NextW{w->wo, H, (long long)nh * d, a->split_o}));
     STEP(cts_qkv_rope_cache(ctx, a->ws, 1, a->split_qkv, w->bqkv, a->positions, a->cos_tab, a->sin_tab, a->slot_map, a->q, w->k_cache,
                             w->v_cache, nullptr, nullptr, T, nh, nkv, d, a->page_size, w->q_norm, w->k_norm, a->eps, dt, stream));
     STEP(cts_attn_decode(ctx, a->q, w->k_cache, w->v_cache, a->num_pages, a->page_table, a->max_pages, a->seq_lens, (int)T, nh, nkv, d,
                          a->page_size, scale, a->attn_splits, a->attn_ws, a->ao, dt, stream));
     // o_proj + residual + post-attention RMSNorm
-    STEP(step_gemm_partial(ctx, a->ao, w->wo, H, (long long)nh * d, T, a->split_o, a->ws, dt, stream));
+    STEP(step_gemm_partial(ctx, a->ao, w->wo, H, (long long)nh * d, T, a->split_o, a->ws, dt, stream, NextW{w->wgu, 2 * I, H, a->split_gu}));
     STEP(cts_reduce_residual_rmsnorm(ctx, a->ws, a->split_o, a->h, a->h, w->ln2, a->eps, a->xn, T, H, dt, stream));
     // gate/up (interleaved weight) + SwiGLU
-    STEP(step_gemm_partial(ctx, a->xn, w->wgu, 2 * I, H, T, a->split_gu, a->ws, dt, stream));
+    STEP(step_gemm_partial(ctx, a->xn, w->wgu, 2 * I, H, T, a->split_gu, a->ws, dt, stream, NextW{w->wd, H, I, a->split_d}));
     STEP(cts_reduce_swiglu(ctx, a->ws, a->split_gu, T, I, a->act, 1, dt, stream));
     // down_proj + residual + the next layer's input RMSNorm (or the final norm)
     const void* nw = l + 1 < a->n_layers ? a->layers[l + 1].ln1 : a->final_norm;
-    STEP(step_gemm_partial(ctx, a->act, w->wd, H, I, T, a->split_d, a->ws, dt, stream));
+    STEP(step_gemm_partial(ctx, a->act, w->wd, H, I, T, a->split_d, a->ws, dt, stream,
+                           l + 1 < a->n_layers ? NextW{a->layers[l + 1].wqkv, QKV, H, a->split_qkv} : NextW{a->lm_head, a->vocab, H, 1}));
     STEP(cts_reduce_residual_rmsnorm(ctx, a->ws, a->split_d, a->h, a->h, nw, a->eps, a->xn, T, H, dt, stream));
   }
   STEP(cts_lm_head(ctx, a->xn, a->lm_head, a->logits, T, H, a->vocab, dt, stream));

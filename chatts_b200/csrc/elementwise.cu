@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "trace.cuh"
 
 namespace {
 
@@ -54,6 +55,54 @@ __global__ void reduce_bias_act_kernel(const float* __restrict__ part, int S, lo
   }
 }
 
+
+// Split-K partials are read S at a time with ALL loads of a batch issued before the first add: a `for (s < S)` loop with a run-time
+// bound issues one load, waits a full L2 round trip (~0.7 us) for the add, and only then issues the next -- 7 partials cost ~5 us of
+// pure latency in a kernel that moves a few megabytes (measured with csrc/trace.cuh: 5.5 us per RMSNorm launch).  The additions still
+// run in split order (s = 0, 1, ..., S-1), so results are bit-identical to the sequential loop.
+constexpr int kPartBatch = 8;
+__device__ __forceinline__ void sum_partials8(const float* __restrict__ p, long long stride, int S, float* a) {
+  float4 lo[kPartBatch], hi[kPartBatch];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  for (int s0 = 0; s0 < S; s0 += kPartBatch) {
+#pragma unroll
+    for (int u = 0; u < kPartBatch; ++u)
+      if (s0 + u < S) {
+        lo[u] = *reinterpret_cast<const float4*>(p + (long long)(s0 + u) * stride);
+        hi[u] = *reinterpret_cast<const float4*>(p + (long long)(s0 + u) * stride + 4);
+      }
+#pragma unroll
+    for (int u = 0; u < kPartBatch; ++u)
+      if (s0 + u < S) {
+        if (s0 + u == 0) {            // the first partial initialises the sum (x + 0.f would turn -0.f into +0.f)
+          a[0] = lo[u].x; a[1] = lo[u].y; a[2] = lo[u].z; a[3] = lo[u].w; a[4] = hi[u].x; a[5] = hi[u].y; a[6] = hi[u].z; a[7] = hi[u].w;
+        } else {
+          a[0] += lo[u].x; a[1] += lo[u].y; a[2] += lo[u].z; a[3] += lo[u].w; a[4] += hi[u].x; a[5] += hi[u].y; a[6] += hi[u].z; a[7] += hi[u].w;
+        }
+      }
+  }
+}
+__device__ __forceinline__ void sum_partials2(const float* __restrict__ p0, const float* __restrict__ p1, long long stride, int S,
+                                              float& a0, float& a1) {
+  float v0[kPartBatch], v1[kPartBatch];
+  a0 = a1 = 0.f;
+  for (int s0 = 0; s0 < S; s0 += kPartBatch) {
+#pragma unroll
+    for (int u = 0; u < kPartBatch; ++u)
+      if (s0 + u < S) {
+        v0[u] = p0[(long long)(s0 + u) * stride];
+        v1[u] = p1[(long long)(s0 + u) * stride];
+      }
+#pragma unroll
+    for (int u = 0; u < kPartBatch; ++u)
+      if (s0 + u < S) {
+        a0 = (s0 + u == 0) ? v0[u] : a0 + v0[u];
+        a1 = (s0 + u == 0) ? v1[u] : a1 + v1[u];
+      }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // one CTA per token; H elements kept in registers between the two passes (H <= 8 * 8 * blockDim)
 constexpr int kNormThreads = 256;
@@ -79,14 +128,7 @@ reduce_residual_rmsnorm_kernel(const float* __restrict__ part, int S, const T* _
       unpack8<T>(*reinterpret_cast<const uint4*>(resid_in + t * h + (long long)v * 8), r);
       if (S > 0) {
         float a[8];
-        const float* p = part + t * h + (long long)v * 8;
-        float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
-        a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
-        for (int s = 1; s < S; ++s) {
-          lo = *reinterpret_cast<const float4*>(p + s * stride);
-          hi = *reinterpret_cast<const float4*>(p + s * stride + 4);
-          a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w; a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
-        }
+        sum_partials8(part + t * h + (long long)v * 8, stride, S, a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = rnd<T>(r[j] + rnd<T>(a[j]));   // residual + dtype(proj)  (:302,:308)
         if (resid_out) *reinterpret_cast<uint4*>(resid_out + t * h + (long long)v * 8) = pack8<T>(r);
@@ -135,7 +177,9 @@ reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ part, int S, co
                                        T* __restrict__ resid_out, const T* __restrict__ norm_w, float eps,
                                        T* __restrict__ norm_out, long long t_total, int h) {
   pdl_trigger();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_NORM, 0);
   pdl_wait();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_NORM, 1);
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks();
@@ -154,14 +198,7 @@ reduce_residual_rmsnorm_cluster_kernel(const float* __restrict__ part, int S, co
       unpack8<T>(*reinterpret_cast<const uint4*>(resid_in + off), r);
       if (S > 0) {
         float a[8];
-        const float* p = part + off;
-        float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
-        a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
-        for (int s = 1; s < S; ++s) {
-          lo = *reinterpret_cast<const float4*>(p + s * stride);
-          hi = *reinterpret_cast<const float4*>(p + s * stride + 4);
-          a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w; a[4] += hi.x; a[5] += hi.y; a[6] += hi.z; a[7] += hi.w;
-        }
+        sum_partials8(part + off, stride, S, a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) r[j] = rnd<T>(r[j] + rnd<T>(a[j]));
         if (resid_out) *reinterpret_cast<uint4*>(resid_out + off) = pack8<T>(r);
@@ -207,7 +244,9 @@ template <typename T>
 __global__ void reduce_swiglu_kernel(const float* __restrict__ part, int S, long long t_total, long long inter,
                                      T* __restrict__ out, int interleaved) {
   pdl_trigger();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_SWIGLU, 0);
   pdl_wait();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_SWIGLU, 1);
   const long long t = blockIdx.y;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= inter) return;
@@ -226,6 +265,35 @@ __global__ void reduce_swiglu_kernel(const float* __restrict__ part, int S, long
   out[t * inter + i] = DT<T>::from_f(r);
 }
 
+// Vector variant (inter % 8 == 0): a thread owns 8 consecutive outputs -- 8 gate and the 8 matching up columns are contiguous in both
+// layouts (the interleaved one keeps 64-column runs) -- so a split costs four 16-byte loads, all splits' loads are in flight together
+// (sum_partials8) and the store is one 16-byte vector.  448 CTAs of 128 threads at the 14B shape instead of 1728 of 256: the
+// scalar kernel's CTAs filled every thread slot of the SMs and kept the next GEMM's CTAs (and their weight prefetch) out for ~10 us.
+constexpr int kSwiThreads = 128;
+template <typename T>
+__global__ void __launch_bounds__(kSwiThreads)
+reduce_swiglu_vec_kernel(const float* __restrict__ part, int S, long long t_total, long long inter, T* __restrict__ out,
+                         int interleaved) {
+  pdl_trigger();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_SWIGLU, 0);
+  pdl_wait();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_SWIGLU, 1);
+  const long long t = blockIdx.y;
+  const long long i = ((long long)blockIdx.x * kSwiThreads + threadIdx.x) * 8;
+  if (i >= inter) return;
+  const long long n = 2 * inter;
+  const long long gi = interleaved ? (i >> 6) * 128 + (i & 63) : i;
+  const long long ui = interleaved ? gi + 64 : inter + i;
+  const float* p = part + t * n;
+  const long long stride = t_total * n;
+  float g[8], u[8], r[8];
+  sum_partials8(p + gi, stride, S, g);
+  sum_partials8(p + ui, stride, S, u);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = rnd<T>(silu_f(rnd<T>(g[j]))) * rnd<T>(u[j]);
+  *reinterpret_cast<uint4*>(out + t * inter + i) = pack8<T>(r);
+}
+
 // ------------------------------------------------------------------------------------------------
 constexpr int kRopeHeadsPerBlock = 4;
 // Scalar variant, used for split-K partial input (decode): many small CTAs pull the fp32 partials from L2 in parallel.
@@ -240,7 +308,9 @@ __global__ void qkv_rope_cache_scalar_kernel(const void* __restrict__ src, int s
                                       int d, int page_size, const T* __restrict__ q_norm_w, const T* __restrict__ k_norm_w,
                                       float norm_eps) {
   pdl_trigger();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_ROPE, 0);
   pdl_wait();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_ROPE, 1);
   const int half = d >> 1;
   const int hl = threadIdx.x / half;                    // head slot inside the block (kRopeHeadsPerBlock heads per CTA)
   const int head = blockIdx.x * kRopeHeadsPerBlock + hl;
@@ -253,8 +323,7 @@ __global__ void qkv_rope_cache_scalar_kernel(const void* __restrict__ src, int s
   if (src_is_partial) {
     const float* p = reinterpret_cast<const float*>(src) + t * width;
     const long long stride = t_total * width;
-    x0 = p[c0]; x1 = p[c1];
-    for (int s = 1; s < S; ++s) { x0 += p[c0 + s * stride]; x1 += p[c1 + s * stride]; }
+    sum_partials2(p + c0, p + c1, stride, S, x0, x1);
     if (bias) { x0 += DT<T>::to_f(bias[c0]); x1 += DT<T>::to_f(bias[c1]); }
     x0 = rnd<T>(x0); x1 = rnd<T>(x1);                 // nn.Linear output in the model dtype
   } else {
@@ -432,8 +501,12 @@ qkv_rope_cache_kernel(const void* __restrict__ src, int src_is_partial, int S, c
 template <typename T>
 __global__ void embed_gather_kernel(const T* __restrict__ table, const int* __restrict__ ids, T* __restrict__ out,
                                     long long h, long long vocab) {
-  pdl_trigger();
+  // STEP BARRIER: the first kernel of a decode step (and of a prefill) waits for everything before it -- the previous step's advance
+  // kernel, host-side state updates -- BEFORE it lets its successors start.  Every later kernel of the step may therefore read the
+  // step state (seq_lens, page table, positions, slots) and the KV rows of earlier positions ahead of its own dependency wait
+  // (attn_decode_kernel prefetches its KV tiles that way).
   pdl_wait();
+  pdl_trigger();
   const long long t = blockIdx.x;
   const int id = ids[t];
   if (id < 0 || id >= vocab) return;
@@ -591,6 +664,12 @@ extern "C" int cts_reduce_swiglu(cts_ctx* ctx, const float* partial, int split_k
   CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
   CTS_CHECK_ARG(ctx, t <= 65535, "t > 65535");
   if (t == 0) return CTS_OK;
+  if (inter % 8 == 0 && ((uintptr_t)partial & 15) == 0 && ((uintptr_t)out & 15) == 0) {
+    dim3 vgrid((unsigned)cdiv_ll(inter / 8, kSwiThreads), (unsigned)t);
+    DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_swiglu_vec_kernel<T>, vgrid, dim3(kSwiThreads), 0, (cudaStream_t)stream, 1, partial,
+                                                split_k, t, inter, (T*)out, interleaved)));
+    return CTS_OK;
+  }
   dim3 grid((unsigned)cdiv_ll(inter, 256), (unsigned)t);
   DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_swiglu_kernel<T>, grid, dim3(256), 0, (cudaStream_t)stream, 1, partial, split_k, t,
                                               inter, (T*)out, interleaved)));
@@ -671,3 +750,5 @@ extern "C" int cts_greedy_advance(cts_ctx* ctx, const void* logits, long long vo
                                               slot_map, page_table, max_pages, page_size > 0 ? page_size : 1)));
   return CTS_OK;
 }
+
+CTS_TRACE_SETTER(cts_trace_set_elementwise)

@@ -32,6 +32,7 @@
 #define CTS_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
 #endif
 #include "tensormap.cuh"
+#include "trace.cuh"
 
 namespace {
 
@@ -165,11 +166,13 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
     if (lane == 0) {
       const int npre = nkb < stages ? nkb : stages;
       constexpr uint32_t kTx = NORM_IN ? (uint32_t)kABytes : (uint32_t)kStage;
+      CTS_TRACE(CTS_TK_FUSED, 0);
       for (int i = 0; i < npre; ++i) {
         mbar_expect_tx(&full_bar[i], kTx);
         tma_load_2d(smem + (size_t)i * kStage, &tm_w, &full_bar[i], (kb0 + i) * kBK, f0, CTS_L2_EVICT_FIRST);
       }
       pdl_wait();
+      CTS_TRACE(CTS_TK_FUSED, 1);
       if (!NORM_IN)
         for (int i = 0; i < npre; ++i)
           tma_load_2d(smem + (size_t)i * kStage + kABytes, &tm_x, &full_bar[i], (kb0 + i) * kBK, 0, CTS_L2_EVICT_LAST);
@@ -181,6 +184,7 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
         tma_load_2d(st, &tm_w, &full_bar[s], (kb0 + i) * kBK, f0, CTS_L2_EVICT_FIRST);
         if (!NORM_IN) tma_load_2d(st + kABytes, &tm_x, &full_bar[s], (kb0 + i) * kBK, 0, CTS_L2_EVICT_LAST);
       }
+      CTS_TRACE(CTS_TK_FUSED, 2);
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
@@ -470,6 +474,7 @@ gemm_decode_fused_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<kCols>(tmem_base);
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_FUSED, 3);
   if (p.peer_region != nullptr && threadIdx.x == 0) {        // the last CTA of the grid to finish publishes the next epoch
     __threadfence();
     const int done = atomicAdd(&p.peer_state[1], 1) + 1;
@@ -573,3 +578,5 @@ extern "C" int cts_gemm_decode_fused(cts_ctx* ctx, const cts_fused_gemm_args* a,
   FUSED_GO(__half)
 #undef FUSED_GO
 }
+
+CTS_TRACE_SETTER(cts_trace_set_fused)

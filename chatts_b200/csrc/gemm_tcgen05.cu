@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "tensormap.cuh"
+#include "trace.cuh"
 
 namespace {
 
@@ -43,6 +44,9 @@ struct GemmParams {
   int* tile_cnt;     // CTS_EPI_SPLITK_F32: arrival counter per output tile (zero-initialised, self-resetting)
   int l2_prefetch;   // K blocks of W this CTA prefetches into L2 beyond the shared-memory ring while it waits (decode)
   int staged;        // 1: epilogue goes TMEM -> registers -> shared-memory tile -> TMA store (big tiles)
+  // next-GEMM weight prefetch (cts_gemm_args.next_*): units of the next launch = next_tiles x next_split, each reads K blocks
+  // [kb_total' * z / split', ...) of the 128-row tile x; this grid prefetches the first next_pf blocks of every unit into L2
+  int next_tiles, next_split, next_kb_total, next_pf;
 };
 
 template <int BN, bool DUAL> __host__ __device__ constexpr int stage_bytes() { return kBM * kBK * 2 * (DUAL ? 2 : 1) + BN * kBK * 2; }
@@ -54,7 +58,7 @@ template <int BN, bool DUAL> __host__ __device__ constexpr int tmem_cols() {
 template <typename T, int BN, bool DUAL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w2,
-               const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_out,
+               const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_next, const __grid_constant__ CUtensorMap tm_out,
                const __grid_constant__ CUtensorMap tm_res, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
@@ -110,6 +114,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
       // Phase 1 (before the dependency wait): the WEIGHT tiles of the first `stages` K blocks.  Nobody writes
       // weights, so this stream may start while the predecessor kernel is still running (PDL).
       const int npre = nkb < stages ? nkb : stages;
+      CTS_TRACE(CTS_TK_GEMM, 0);
       for (int i = 0; i < npre; ++i) {
         mbar_expect_tx(&full_bar[i], (uint32_t)kStage);
         uint8_t* st = smem + (size_t)i * kStage;
@@ -127,6 +132,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         }
       }
       pdl_wait();   // activations are produced by the predecessor
+      CTS_TRACE(CTS_TK_GEMM, 1);
       for (int i = 0; i < npre; ++i) {
         uint8_t* st = smem + (size_t)i * kStage;
         tma_load_2d(st + kABytes * (DUAL ? 2 : 1), &tm_x, &full_bar[i], (kb0 + i) * kBK, t0, CTS_L2_EVICT_LAST);
@@ -141,6 +147,21 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
         tma_load_2d(st, &tm_w, &full_bar[s], kc, f0, CTS_L2_EVICT_FIRST);
         if (DUAL) tma_load_2d(st + kABytes, &tm_w2, &full_bar[s], kc, f0, CTS_L2_EVICT_FIRST);
         tma_load_2d(st + kABytes * (DUAL ? 2 : 1), &tm_x, &full_bar[s], kc, t0, CTS_L2_EVICT_LAST);
+      }
+      CTS_TRACE(CTS_TK_GEMM, 2);
+      // This CTA's own stream is fully requested: keep HBM busy through the drain / kernel boundary / small dependent kernel by
+      // pulling the first blocks the NEXT GEMM will read into L2 (fire-and-forget, no shared memory, no barrier).
+      if (p.next_pf > 0) {
+        const int units = p.next_tiles * p.next_split;
+        const int n_ours = (int)(gridDim.x * gridDim.y * gridDim.z);
+        const int c = (int)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+        for (int u = c; u < units; u += n_ours) {
+          const int x2 = u % p.next_tiles, z2 = u / p.next_tiles;
+          const int kbn0 = (int)(((long long)p.next_kb_total * z2) / p.next_split);
+          const int kbn1 = (int)(((long long)p.next_kb_total * (z2 + 1)) / p.next_split);
+          const int cnt = (kbn1 - kbn0) < p.next_pf ? (kbn1 - kbn0) : p.next_pf;
+          for (int i = 0; i < cnt; ++i) tma_prefetch_l2_2d(&tm_next, (kbn0 + i) * kBK, x2 * kBM);
+        }
       }
     }
   } else if (warp == 1) {
@@ -309,6 +330,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<kCols>(tmem_base);
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_GEMM, 3);
 }
 
 // =================================================================================================================
@@ -575,6 +597,21 @@ int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   p.kb_total = (int)cdiv_ll(a->k, kBK);
   p.split_k = a->split_k;
   p.epilogue = a->epilogue;
+  // next-GEMM weight prefetch (decode-sized launches only; CTS_NEXT_PREFETCH=0 switches the hint off for A/B runs)
+  CUtensorMap tm_next = tm_w;
+  p.next_tiles = p.next_split = p.next_kb_total = p.next_pf = 0;
+  if (BN <= 32 && a->next_w != nullptr && a->next_prefetch_bytes > 0 && a->next_n > 0 && a->next_k > 0 && a->next_split >= 1 && !ctx->no_next_prefetch) {
+    rc = cts_make_tmap_2d(ctx, &tm_next, a->next_w, a->next_n, a->next_k, a->next_ld > 0 ? a->next_ld : a->next_k, kBM, is_bf16);
+    if (rc) return rc;
+    p.next_tiles = (int)cdiv_ll(a->next_n, kBM);
+    p.next_split = a->next_split;
+    p.next_kb_total = (int)cdiv_ll(a->next_k, kBK);
+    const long long units = (long long)p.next_tiles * p.next_split;
+    long long pf = a->next_prefetch_bytes / (units * kBM * kBK * 2);
+    const long long per_unit = cdiv_ll(p.next_kb_total, p.next_split);
+    if (pf > per_unit) pf = per_unit;
+    p.next_pf = (int)pf;
+  }
   constexpr int kStage = stage_bytes<BN, DUAL>();
   // small-N (decode / short-prompt / TS-encoder) tiles: leave room for two or three CTAs per SM so one CTA's prologue/epilogue overlaps the
   // other's stream; large-N (prefill) tiles take the whole SM.
@@ -595,7 +632,7 @@ int launch(cts_ctx* ctx, const cts_gemm_args* a, cudaStream_t stream) {
   auto kern = gemm_tn_kernel<T, BN, DUAL>;
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)cdiv_ll(a->n, kBM), (unsigned)cdiv_ll(a->t, BN), (unsigned)a->split_k);
-  CTS_CUDA(ctx, launch_pdl(kern, grid, dim3(kThreads), smem, stream, 1, tm_w, tm_w2, tm_x, tm_out, tm_res, p));
+  CTS_CUDA(ctx, launch_pdl(kern, grid, dim3(kThreads), smem, stream, 1, tm_w, tm_w2, tm_x, tm_next, tm_out, tm_res, p));
   return CTS_OK;
 }
 
@@ -650,15 +687,19 @@ extern "C" int cts_gemm(cts_ctx* ctx, const cts_gemm_args* a, void* stream) {
 extern "C" int cts_gemm_suggest_split(cts_ctx* ctx, long long n, long long k, long long t, int dual) {
   if (!ctx || n <= 0 || k <= 0 || t <= 0) return 1;
   const int bn = t <= 16 ? 16 : t <= 32 ? 32 : t <= 64 ? 64 : t <= 128 ? 128 : 256;
-  const long long tiles = cdiv_ll(n, kBM) * cdiv_ll(t, bn);
+  // dual = 1: the caller passes n = intermediate size of an INTERLEAVED gate/up weight, whose GEMM has 2 n / 128 tiles; that grid is
+  // sized against the three decode CTAs an SM holds (432 of 444 slots at the 14B shape, and one wave again under tensor parallelism,
+  // where the old 2-per-SM rule applied to n / 128 tiles gave 540 CTAs = two waves at TP2: csrc/trace.cuh timeline)
+  const long long tiles = cdiv_ll(dual ? 2 * n : n, kBM) * cdiv_ll(t, bn);
   const long long kb = cdiv_ll(k, kBK);
-  const long long slots = (long long)ctx->sm_count * (bn <= 128 ? 2 : 1);
+  const long long slots = (long long)ctx->sm_count * (bn <= 128 ? (dual && bn <= 32 ? 3 : 2) : 1);
   if (tiles >= slots) return 1;
   long long s = slots / tiles;
   const long long max_by_k = kb / 8 > 0 ? kb / 8 : 1;   // keep >= 8 K blocks (1 KiB of each weight row) per split
   if (s > max_by_k) s = max_by_k;
   if (s > 16) s = 16;
   if (s < 1) s = 1;
-  (void)dual;
   return (int)s;
 }
+
+CTS_TRACE_SETTER(cts_trace_set_gemm)

@@ -95,10 +95,15 @@ class ChatTSForCausalLM:
         #      token operand itself (5 stages; single GPU only)
         self.use_fused_decode = int(_os.environ.get("CTS_DECODE_FUSED", "0")) if use_fused_decode is None else int(use_fused_decode)
         # tensor parallelism: low-latency two-shot all-reduce (cts_peer_allreduce_ll) instead of the one-shot push kernel
-        self.use_peer_ll = (_os.environ.get("CTS_PEER_LL", "0") == "1") if use_peer_ll is None else bool(use_peer_ll)
-        # sampled decoding through cts_sample_advance (csrc/sampling.cu) instead of torch ops: off by default until the kernel has
-        # run on a B200 (written after the round-1 GPU budget was spent); CTS_SAMPLE_KERNEL=1 / use_sample_kernel=True turns it on
-        self.use_sample_kernel = bool(int(_os.environ.get("CTS_SAMPLE_KERNEL", "0"))) if use_sample_kernel is None else bool(use_sample_kernel)
+        # (default since round 2: validated across 2 B200s -- same logits, same tokens on every rank -- and 19-25 % faster per step
+        #  than the one-shot kernel at TP2, profiles/r2_tp2_variants.txt; CTS_PEER_LL=0 selects the one-shot kernel)
+        self.use_peer_ll = (_os.environ.get("CTS_PEER_LL", "1") == "1") if use_peer_ll is None else bool(use_peer_ll)
+        # sampled decoding through cts_sample_advance (csrc/sampling.cu): temperature / top-k / top-p / multinomial / advance in ONE
+        # launch per step, no torch op on the path (validated on a B200: 17 cases against the CPU statement that is itself checked
+        # against transformers' logits warpers).  Default since round 2; CTS_SAMPLE_KERNEL=0 selects the torch-op fallback.
+        self.use_sample_kernel = bool(int(_os.environ.get("CTS_SAMPLE_KERNEL", "1"))) if use_sample_kernel is None else bool(use_sample_kernel)
+        # bytes of the NEXT GEMM's weight a decode GEMM prefetches into L2 once its own stream is requested (0 = off)
+        self.next_prefetch_bytes = int(float(_os.environ.get("CTS_NEXT_PREFETCH_MB", "48")) * (1 << 20))
         self._load(state_dict)
         # every position the page table can address has a row in the rotary tables (max_pages * page_size >= max_seq_len), capped by
         # the model's max_position_embeddings; _alloc_pages rejects sequences beyond it (no silent out-of-bounds cos/sin read)
@@ -269,6 +274,12 @@ class ChatTSForCausalLM:
         I, H = self.I, self.H
         c.reduce_residual_rmsnorm(None, 0, st.h, None, self.ln1[0], eps, st.xn, t=T)
         fused = self.use_fused_decode and T <= 32 and st.k_lin is None                            # decode states only
+        # decode-sized steps: every weight-streaming GEMM names the weight its successor will stream, and prefetches the head of it
+        # into L2 once its own last tile is requested (cts_gemm_args.next_*): HBM keeps streaming through the kernel boundaries
+        nb = self.next_prefetch_bytes if (T <= 32 and st.k_lin is None) else 0
+
+        def nxt(w, split):
+            return dict(next_w=w, next_split=split, next_bytes=nb) if nb > 0 else {}
         for l in range(self.L):
             kc, vc = self.kv[l, 0], self.kv[l, 1]
             if fused:
@@ -323,47 +334,48 @@ class ChatTSForCausalLM:
                 continue
             # ---- QKV projection + bias + RoPE + KV write
             if sp["qkv"] > 1:
-                c.gemm(st.xn, self.wqkv[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["qkv"], t=T)
+                c.gemm(st.xn, self.wqkv[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["qkv"], t=T, **nxt(self.wo[l], sp["o"]))
                 c.qkv_rope_cache(st.ws, True, sp["qkv"], self.bqkv[l], st.positions, self.cos, self.sin, st.slot_map, st.q, kc, vc,
                                  st.k_lin, st.v_lin, T, self.nh, self.nkv, self.d, self.page_size, self.qn[l], self.kn[l], eps)
             else:
-                c.gemm(st.xn, self.wqkv[l], st.qkv, bias=self.bqkv[l], epilogue=EPI_NONE, t=T)
+                c.gemm(st.xn, self.wqkv[l], st.qkv, bias=self.bqkv[l], epilogue=EPI_NONE, t=T, **nxt(self.wo[l], sp["o"]))
                 c.qkv_rope_cache(st.qkv, False, 1, None, st.positions, self.cos, self.sin, st.slot_map, st.q, kc, vc,
                                  st.k_lin, st.v_lin, T, self.nh, self.nkv, self.d, self.page_size, self.qn[l], self.kn[l], eps)
             attend(l)
             # ---- o_proj + residual + post-attention RMSNorm
             if self.tp_size > 1:
-                self._tp_row_parallel(st, T, st.ao, self.wo[l], self.ln2[l], 0, sp["o"])
+                self._tp_row_parallel(st, T, st.ao, self.wo[l], self.ln2[l], 0, sp["o"], nxt(self.wgu[l], sp["gu"]))
             elif sp["o"] > 1:
-                c.gemm(st.ao, self.wo[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["o"], t=T)
+                c.gemm(st.ao, self.wo[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["o"], t=T, **nxt(self.wgu[l], sp["gu"]))
                 c.reduce_residual_rmsnorm(st.ws, sp["o"], st.h, st.h, self.ln2[l], eps, st.xn, t=T)
             else:
-                c.gemm(st.ao, self.wo[l], st.h, residual=st.h, epilogue=EPI_RESIDUAL, t=T)
+                c.gemm(st.ao, self.wo[l], st.h, residual=st.h, epilogue=EPI_RESIDUAL, t=T, **nxt(self.wgu[l], sp["gu"]))
                 c.reduce_residual_rmsnorm(None, 0, st.h, None, self.ln2[l], eps, st.xn, t=T)
             # ---- gate/up + SwiGLU
             if T > 128:
                 c.gemm(st.xn, self.wgu[l], st.act, epilogue=EPI_SWIGLU_IL, t=T)          # persistent, SwiGLU fused in the tile
             else:
-                c.gemm(st.xn, self.wgu[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["gu"], t=T)
+                c.gemm(st.xn, self.wgu[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["gu"], t=T, **nxt(self.wd[l], sp["d"]))
                 c.reduce_swiglu(st.ws, sp["gu"], T, I, st.act, interleaved=True)
             # ---- down_proj + residual + next layer's input RMSNorm (or the final norm)
             nw = self.ln1[l + 1] if l + 1 < self.L else self.final_norm
+            after = nxt(self.wqkv[l + 1], sp["qkv"]) if l + 1 < self.L else nxt(self.lm_head, 1)
             if self.tp_size > 1:
-                self._tp_row_parallel(st, T, st.act, self.wd[l], nw, 1, sp["d"])
+                self._tp_row_parallel(st, T, st.act, self.wd[l], nw, 1, sp["d"], after)
             elif sp["d"] > 1:
-                c.gemm(st.act, self.wd[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["d"], t=T)
+                c.gemm(st.act, self.wd[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["d"], t=T, **after)
                 c.reduce_residual_rmsnorm(st.ws, sp["d"], st.h, st.h, nw, eps, st.xn, t=T)
             else:
-                c.gemm(st.act, self.wd[l], st.h, residual=st.h, epilogue=EPI_RESIDUAL, t=T)
+                c.gemm(st.act, self.wd[l], st.h, residual=st.h, epilogue=EPI_RESIDUAL, t=T, **after)
                 c.reduce_residual_rmsnorm(None, 0, st.h, None, nw, eps, st.xn, t=T)
 
-    def _tp_row_parallel(self, st, T, x, w, norm_w, which, split):
+    def _tp_row_parallel(self, st, T, x, w, norm_w, which, split, nxt=None):
         """Row-parallel projection under tensor parallelism: local split-K partials -> sum over splits and ranks ->
         residual + norm.  Decode-sized T: ONE kernel over NVLink peer memory (cts_peer_allreduce_residual_rmsnorm: each
         CTA reduces its token's local split-K partials into the symmetric buffer, signals, pulls the peers' rows; the
         buffers alternate between o_proj (0) and down_proj (1)).  Large prefill T: NCCL all-reduce (bandwidth-bound)."""
         c = self.ctx
-        c.gemm(x, w, st.ws, epilogue=EPI_PARTIAL_F32, split_k=split, t=T)
+        c.gemm(x, w, st.ws, epilogue=EPI_PARTIAL_F32, split_k=split, t=T, **(nxt or {}))
         if self.peer is not None and T <= self.peer_tokens and self.use_peer_ll:
             c.peer_allreduce_ll(st.ws, split, self.peer.partials[which], self.peer.part_bytes, self.peer.state, self.tp_rank, self.tp_size,
                                 self.peer.max_batch, st.h, st.h, norm_w, self.eps, st.xn, T)
@@ -535,7 +547,8 @@ class ChatTSForCausalLM:
         st.step_ptr = torch.zeros(2, device=dev, dtype=torch.int32)      # {step, arrival counter}
         st.logits = torch.empty(B, self.V, device=dev, dtype=self.dtype)
         # flash-decode split: fill the SMs with (split x kv head x batch) CTAs, at least 2 pages per split
-        per = max(1, (3 * 148) // max(1, B * self.nkv))
+        # (the kernel holds a 3-stage ring of 32 KB K+V tiles: TWO CTAs per SM; sizing for three gave 384 CTAs = two waves at TP2)
+        per = max(1, (2 * 148) // max(1, B * self.nkv))
         max_tiles = max(1, (self.max_seq_len + 63) // 64)
         st.attn_splits = int(max(1, min(per, max_tiles, 32)))
         import os
@@ -604,7 +617,9 @@ class ChatTSForCausalLM:
             self._decode_layers_chain(st, attend)
         else:
             self._layers(st, B, attend)
-        c.gemm(st.xn, self.lm_head, st.logits, epilogue=EPI_NONE, t=B)
+        nb = self.next_prefetch_bytes if B <= 32 else 0
+        c.gemm(st.xn, self.lm_head, st.logits, epilogue=EPI_NONE, t=B,
+               **(dict(next_w=self.wqkv[0], next_split=st.splits["qkv"], next_bytes=nb) if nb > 0 else {}))
         if sample and self.peer is not None:
             # vocab-parallel greedy over peer memory: no collective call, graph-capturable
             c.peer_greedy_advance(st.logits, B, self.tp_rank, self.tp_size, self.peer.cand, self.peer.cand_flags, self.peer.cand_state,

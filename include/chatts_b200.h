@@ -100,6 +100,15 @@ typedef struct {
   int reserved;
   void* splitk_ws;      /* CTS_EPI_SPLITK_F32, split_k > 1: fp32 [split_k, t, n] scratch */
   int* tile_counters;   /* CTS_EPI_SPLITK_F32, split_k > 1: int32 [ceil(n/128) * ceil(t/BN)] zero-filled once (self-resetting) */
+  /* Optional hint (decode-sized t only): the weight the NEXT weight-streaming GEMM of the chain will read.  A CTA whose own last
+   * weight tile has been requested prefetches a share of that matrix into L2 (the first K blocks of every (128-row tile, K split)
+   * unit of the next launch, next_prefetch_bytes in total), so HBM keeps streaming through this kernel's drain, the kernel
+   * boundary and the small dependent kernel in between instead of idling (csrc/trace.cuh timeline).  NULL / 0 = no hint. */
+  const void* next_w;   /* [next_n, next_k] row-major, leading dimension next_ld, same dtype */
+  long long next_n, next_k, next_ld;
+  int next_split;       /* split_k of the next launch (its K ranges decide which blocks it reads first) */
+  int next_reserved;
+  long long next_prefetch_bytes;
 } cts_gemm_args;
 
 int cts_gemm(cts_ctx* ctx, const cts_gemm_args* args, void* stream);
@@ -476,6 +485,11 @@ int cts_grad_norm_clip(cts_ctx* ctx, const float* g, long long n, float max_norm
 #define CTS_PACK_DESC_LONGS 12
 int cts_lora_pack(cts_ctx* ctx, const float* master, const long long* desc, int n_desc, long long max_elems, void* work,
                   int dtype, void* stream);
+
+/* Debug / profiling aid (csrc/trace.cuh): instrumented kernels append {tag, %globaltimer} records to `buf` (unsigned long long
+ * [2 + 2*capacity]: [0] cursor, [1] capacity, then the records) -- the overlapped timeline of a CUDA-graph replay that ncu, which
+ * serialises kernels, cannot show (tools/trace_decode_step.py).  buf = NULL switches it off (the default). */
+int cts_trace_enable(cts_ctx* ctx, unsigned long long* buf);
 
 #ifdef __cplusplus
 }

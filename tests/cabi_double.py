@@ -35,7 +35,8 @@ class TorchDouble:
                         idx = pt if pt < vl else maxseq
                         rows[r, p + j * emb: p + (j + 1) * emb] = pos_table[idx]
     def suggest_split(self, n, k, t, dual=False): return self.split if k >= 64 * self.split else 1
-    def gemm(self, x, w, out, *, w2=None, bias=None, residual=None, row_map=None, epilogue=0, split_k=1, t=None, splitk_ws=None, tile_counters=None):
+    def gemm(self, x, w, out, *, w2=None, bias=None, residual=None, row_map=None, epilogue=0, split_k=1, t=None, splitk_ws=None, tile_counters=None,
+             next_w=None, next_split=1, next_bytes=0):          # next_*: L2 prefetch hint, no effect on the result
         t = x.shape[0] if t is None else t
         xx = x[:t].float(); acc = xx @ w.float().T
         dt = x.dtype

@@ -247,6 +247,7 @@ struct cts_ctx {
   int device;
   int sm_count;
   int decode_stages, l2_prefetch_mb, no_persistent_gemm, force_wmma_attention, norm_cluster, max_smem_optin;
+  int no_next_prefetch, next_prefetch_mb;          // next-GEMM L2 prefetch hint (a no-op on the host: tma_prefetch_l2_2d does nothing)
   char err[512];
 };
 int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);
