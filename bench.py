@@ -277,9 +277,10 @@ def run_reference(args):
             break
     v = float(np.median(vals))
     base["value"] = v
+    kept = "fp32" if "float32" in base.get("sample", "")[:120] else "bf16"          # the setting the search kept (stated first in `sample`)
     line = {"impl": "reference", "metric": "decode_tokens_per_s", "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": args.batch / v * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": kept, "data": "synthetic",
             "config": workload_config(args.batch, args.gpus), "cpu_baseline": base,
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -369,6 +370,52 @@ def probe_decode_variant(args):
     return rec
 
 
+
+# ------------------------------------------------------------------------------------------------ tensor-parallel parity gate
+def tp_parity_gate(world, rank, layers=4, batch=8, seed=77):
+    """N > 1: the tensor-parallel path against the single-GPU path on the SAME weights (a `layers`-layer model of the 14B shapes, so
+    that rank 0 can hold both): next-token logits of the prefill (NCCL all-reduce path) and of one decode step (peer-memory all-reduce
+    path, rows whose first token agrees), greedy agreement over 8 tokens, identical tokens on every rank.  Printed in the JSON line."""
+    import torch.distributed as dist
+    from chatts_b200 import ChatTSConfig
+    from chatts_b200.model import ChatTSForCausalLM
+    cfg = ChatTSConfig.chatts_14b()
+    cfg.num_hidden_layers = layers
+    kw = dict(max_batch=batch, max_seq_len=1024, page_size=64)
+    tp = ChatTSForCausalLM.from_synthetic(cfg, seed=seed, tp_rank=rank, tp_size=world, **kw)
+    enc = make_batch(cfg, batch, seed=3)
+    S = enc["input_ids"].shape[1]
+    lg_tp = tp.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"]).logits[:, 0].float()
+    ids2 = tp.generate(**enc, max_new_tokens=2, ignore_eos=True)                 # prefill + ONE decode step: its logits are still in the state
+    shard = tp._steps[batch].logits[:batch].float().contiguous()
+    parts = [torch.empty_like(shard) for _ in range(world)]
+    dist.all_gather(parts, shard)
+    dec_tp = torch.cat(parts, dim=-1)
+    ids_tp = tp.generate(**enc, max_new_tokens=8, ignore_eos=True)
+    t = ids_tp.cuda()
+    lst = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(lst, t)
+    same = all(torch.equal(lst[0], x) for x in lst)
+    out = None
+    if rank == 0:
+        ref = ChatTSForCausalLM.from_synthetic(cfg, seed=seed, **kw)
+        lg = ref.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"]).logits[:, 0].float()
+        r2 = ref.generate(**enc, max_new_tokens=2, ignore_eos=True)
+        dec = ref._steps[batch].logits[:batch].float()
+        ids = ref.generate(**enc, max_new_tokens=8, ignore_eos=True)
+        rows = (r2[:, S] == ids2[:, S]).nonzero().reshape(-1).to(dec.device)
+        e_pre = float((lg_tp - lg).abs().max() / lg.abs().max())
+        e_dec = float((dec_tp[rows] - dec[rows]).abs().max() / dec[rows].abs().max()) if rows.numel() else None
+        agree = [int(next((i for i in range(8) if ids[b, S + i] != ids_tp[b, S + i]), 8)) for b in range(batch)]
+        out = {"layers": layers, "batch": batch, "prefill_logits_max_rel": e_pre, "decode_logits_max_rel": e_dec, "decode_rows_compared": int(rows.numel()),
+               "greedy_agreement_of_8": agree, "identical_tokens_on_all_ranks": bool(same),
+               "pass": bool(same and e_pre < 2e-2 and (e_dec is None or e_dec < 2e-2))}
+        del ref
+    del tp
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return out
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch.distributed as dist
@@ -386,6 +433,12 @@ def run_b200(args):
         probe_record = probe_decode_variant(args)
         if probe_record.get("selected"):
             os.environ["CTS_DECODE_FUSED"] = str(probe_record["selected"])          # read by the model constructor below
+    tp_gate = None
+    if world > 1 and not args.sweep_only and not args.layers:
+        try:
+            tp_gate = tp_parity_gate(world, rank)
+        except Exception as e:  # pragma: no cover  (reported, never fatal for the measurement)
+            tp_gate = {"error": repr(e)[:300], "pass": False}
     cfg = ChatTSConfig.chatts_14b()
     if args.layers:
         cfg.num_hidden_layers = args.layers
@@ -519,38 +572,46 @@ def run_b200(args):
     # L2 flushed (256 MB write) before every timed call, CUDA events around the encode (patchify + 5 tcgen05 GEMM layers)
     ts_roof = None
     if world == 1:
-        from chatts_b200._cabi import CtsError  # noqa: F401
-        enc_b = make_batch(cfg, args.batch, seed=2)
-        x_ts = enc_b["timeseries"].to("cuda", torch.bfloat16)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-        tse = model.ts_encoder
-        counts = tse.patch_counts(x_ts)
-        host = torch.stack([counts[1], counts[2]]).cpu()
-        hc = (host[0], host[1])
-        feats, pc = tse.encode(x_ts, counts=counts, host_counts=hc)             # warm (kernel attributes, allocator)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()                                               # launch-overhead-free: 11 kernels, ~100 us
-        with torch.cuda.graph(g):
-            feats, pc = tse.encode(x_ts, counts=counts, host_counts=hc)
-        reps, tot_ms, rows = 8, 0.0, int(feats.shape[0])
-        for it in range(reps + 2):
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            g.replay()
-            e1.record()
+        def ts_case(nb):
+            enc_b = make_batch(cfg, nb, seed=2)
+            x_ts = enc_b["timeseries"].to("cuda", torch.bfloat16)
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            tse = model.ts_encoder
+            counts = tse.patch_counts(x_ts)
+            host = torch.stack([counts[1], counts[2]]).cpu()
+            hc = (host[0], host[1])
+            l0 = ctx.launches
+            feats, pc = tse.encode(x_ts, counts=counts, host_counts=hc)             # warm (kernel attributes, allocator)
+            n_launch = ctx.launches - l0
             torch.cuda.synchronize()
-            if it >= 2:
-                tot_ms += e0.elapsed_time(e1)
-        us = tot_ms * 1e3 / reps
-        H, in0, nl = tse.hidden_size, tse.input_size, tse.num_layers
-        w_bytes = 2 * (in0 * H + (nl - 1) * H * H + nl * H)
-        alg = w_bytes + x_ts.numel() * 2 + rows * in0 * 2 * 2 + rows * H * 2 * (2 * nl - 1)
-        flops = 2.0 * rows * (in0 * H + (nl - 1) * H * H)
-        ach = alg / (us * 1e-6) / 1e9
-        ts_roof = {"series": int(x_ts.shape[0]), "points": SERIES_LEN, "patch_rows": rows, "us": us, "algorithmic_bytes": alg,
-                   "achieved_gbs": ach, "hbm_frac": ach / hbm_peak, "tflops": flops / (us * 1e-6) / 1e12,
-                   "bound": "hbm (weight stream)" if rows <= 280 else "tensor", "launches": 1 + 2 * nl, "timed": "CUDA-graph replay of patchify + MLP, L2 flushed before each replay"}
+            g = torch.cuda.CUDAGraph()                                               # launch-overhead-free replay of the encoder's kernels
+            with torch.cuda.graph(g):
+                feats, pc = tse.encode(x_ts, counts=counts, host_counts=hc)
+            reps, tot_ms, rows = 8, 0.0, int(feats.shape[0])
+            for it in range(reps + 2):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 2:
+                    tot_ms += e0.elapsed_time(e1)
+            us = tot_ms * 1e3 / reps
+            H, in0, nl = tse.hidden_size, tse.input_size, tse.num_layers
+            w_bytes = 2 * (in0 * H + (nl - 1) * H * H + nl * H)
+            alg = w_bytes + x_ts.numel() * 2 + rows * in0 * 2 * 2 + rows * H * 2 * (2 * nl - 1)
+            flops = 2.0 * rows * (in0 * H + (nl - 1) * H * H)
+            ach = alg / (us * 1e-6) / 1e9
+            del g, flush
+            return {"series": int(x_ts.shape[0]), "points": SERIES_LEN, "patch_rows": rows, "us": us, "algorithmic_bytes": alg,
+                    "achieved_gbs": ach, "hbm_frac": ach / hbm_peak, "tflops": flops / (us * 1e-6) / 1e12,
+                    "bound": "hbm (weight stream)" if rows <= 280 else "tensor", "launches": n_launch,
+                    "timed": "CUDA-graph replay of patchify + MLP, L2 flushed before each replay"}
+
+        # the metric prompt (b = 1: 8 series -> 128 patch rows, HBM-bound on the 212 MB weight stream) AND the benchmark batch
+        ts_roof = dict(ts_case(args.batch))
+        ts_roof["cases"] = {"b1": ts_case(1), f"b{args.batch}": {k: v for k, v in ts_roof.items()}}
 
     # ---- attention kernels alone (north_star: attention reported as achieved fraction of its roofline)
     attn_roof = None
@@ -562,16 +623,21 @@ def run_b200(args):
 
     # ---- e2e through the public API with host tensors
     e2e = None
-    if world == 1 and not args.sweep_only:
+    if not args.sweep_only:
+        # every rank runs the same public call on the same host tensors (TP ranks are SPMD); the wall time is the max over ranks
         enc = make_batch(cfg, args.batch, seed=1)
         enc = {k: v.pin_memory() for k, v in enc.items()}
         new = args.steps
         model.generate(**enc, max_new_tokens=4, ignore_eos=True, sync_every=1)          # warm
-        torch.cuda.synchronize()
+        sync_all()
         t0 = time.perf_counter()
         out = model.generate(**enc, max_new_tokens=new, ignore_eos=True, sync_every=1)  # D2H of the new ids every step
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt)
         h2d = (enc["timeseries"].numel() * 2 + 4 * 576 * args.batch * 4 + args.batch * N_SERIES * 16 * 4)
         d2h = args.batch * new * 4 + args.batch * N_SERIES * 8
         e2e = {"value": args.batch * new / dt, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -596,6 +662,12 @@ def run_b200(args):
         line["tokens_sha1"] = main.get("tokens_sha1")          # hash of every greedy token the measured batch produced (probe: equality across variants)
         if probe_record is not None:
             line["config"]["decode_variant_probe"] = probe_record
+        if world > 1:
+            line["tp_parity"] = tp_gate
+            # per rank and step: 2 row-parallel tails per layer, each a two-shot exchange with the flags inside the data (LL):
+            # reduce-scatter of fp32 pairs (8 B on the wire per element incl. epochs) to the owners + all-gather of the rounded h
+            # (4 B per element incl. epochs), (world-1)/world of it leaving the GPU
+            line["nvlink_bytes_per_step_per_rank"] = int(2 * L * args.batch * cfg.hidden_size * 12 * (world - 1) / world)
         line["config"]["variants"] = {k: int(getattr(model, a, 0) or 0) for k, a in (("decode_fused", "use_fused_decode"), ("peer_ll", "use_peer_ll"),
                                                                                    ("native_step", "use_native_step"), ("decode_chain", "use_chain"))}
         print(json.dumps(line), flush=True)

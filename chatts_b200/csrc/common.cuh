@@ -26,7 +26,7 @@ struct cts_ctx {
   int norm_cluster;           // CTS_NORM_CLUSTER: max thread-block-cluster size of the decode RMSNorm kernel (default 8)
   int decode_stages;    // tuning knob (CTS_DECODE_SMEM_KB): shared-memory budget per CTA of the decode GEMM
   int no_next_prefetch; // CTS_NEXT_PREFETCH=0: ignore the next-GEMM weight prefetch hints (A/B testing)
-  int next_prefetch_mb; // CTS_NEXT_PREFETCH_MB (default 48): budget of the hint the C++ step executor passes (model.py passes its own)
+  int next_prefetch_mb; // CTS_NEXT_PREFETCH_MB (default 0 = off): budget of the hint the C++ step executor passes (model.py passes its own)
 };
 
 int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);

@@ -75,7 +75,7 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
   const char* e6 = getenv("CTS_NEXT_PREFETCH");
   ctx->no_next_prefetch = (e6 && atoi(e6) == 0) ? 1 : 0;
   const char* e7 = getenv("CTS_NEXT_PREFETCH_MB");
-  ctx->next_prefetch_mb = e7 ? atoi(e7) : 48;
+  ctx->next_prefetch_mb = e7 ? atoi(e7) : 0;     // off by default: measured slower on a B200 (profiles/r2_next_prefetch_ab.txt)
   *out = ctx;
   return CTS_OK;
 }

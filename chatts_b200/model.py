@@ -102,8 +102,11 @@ class ChatTSForCausalLM:
         # launch per step, no torch op on the path (validated on a B200: 17 cases against the CPU statement that is itself checked
         # against transformers' logits warpers).  Default since round 2; CTS_SAMPLE_KERNEL=0 selects the torch-op fallback.
         self.use_sample_kernel = bool(int(_os.environ.get("CTS_SAMPLE_KERNEL", "1"))) if use_sample_kernel is None else bool(use_sample_kernel)
-        # bytes of the NEXT GEMM's weight a decode GEMM prefetches into L2 once its own stream is requested (0 = off)
-        self.next_prefetch_bytes = int(float(_os.environ.get("CTS_NEXT_PREFETCH_MB", "48")) * (1 << 20))
+        # bytes of the NEXT GEMM's weight a decode GEMM prefetches into L2 once its own stream is requested.  OFF by default: measured
+        # on a B200 (profiles/r2_next_prefetch_ab.txt) it fills the gaps between the weight streams but makes the step SLOWER
+        # (b=32: 6.59 ms without, 6.83 / 7.00 / 7.08 ms with 24 / 48 / 80 MB) -- the prefetched lines do not survive the current
+        # GEMM's stream through L2, so the bytes are read twice.  CTS_NEXT_PREFETCH_MB=<n> turns it on for experiments.
+        self.next_prefetch_bytes = int(float(_os.environ.get("CTS_NEXT_PREFETCH_MB", "0")) * (1 << 20))
         self._load(state_dict)
         # every position the page table can address has a row in the rotary tables (max_pages * page_size >= max_seq_len), capped by
         # the model's max_position_embeddings; _alloc_pages rejects sequences beyond it (no silent out-of-bounds cos/sin read)

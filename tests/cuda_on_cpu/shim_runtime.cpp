@@ -220,7 +220,7 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
   c->force_wmma_attention = 0;
   c->norm_cluster = 8;
   c->no_next_prefetch = 0;
-  c->next_prefetch_mb = 48;
+  c->next_prefetch_mb = 0;
   c->max_smem_optin = 232448;
   c->err[0] = 0;
   *out = c;

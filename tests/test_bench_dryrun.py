@@ -34,7 +34,7 @@ def test_bench_driver_prints_the_contract_line(which):
         assert d["metric"] == "decode_tokens_per_s" and d["scaling"] == "strong"
         assert set(d["attention"]) >= {"decode", "prefill"} and "error" not in d["attention"]
         assert d["ts_encoder"]["patch_rows"] > 0
-        assert d["config"]["variants"] == {"decode_fused": 0, "peer_ll": 0, "native_step": 0, "decode_chain": 0}
+        assert d["config"]["variants"] == {"decode_fused": 0, "peer_ll": 1, "native_step": 0, "decode_chain": 0}      # peer_ll: default since round 2 (only acts under TP)
     else:
         assert d["metric"] == "lora_finetune_positions_per_s" and d["scaling"] == "weak"
         assert 11.0 < d["loss"] < 13.0          # ln(vocab) at initialisation (LoRA B = 0)
