@@ -8,7 +8,7 @@ import torch
 from oracle import decoder as od
 from oracle import merge as om
 from oracle import ts_encoder as ote
-from tests.gpu_util import record, rel_err
+from tests.gpu_util import parity_gate, record, rel_err
 
 pytestmark = pytest.mark.gpu
 DT = torch.bfloat16
@@ -70,54 +70,36 @@ def test_forward_logits_all_positions_match_oracle():
         assert out[b].shape == ref.shape                       # merged length = S_text + sum(P): index placement
         worst = max(worst, rel_err(out[b], ref))
     record("model_forward_all_positions", err=worst)
-    assert worst < 2e-2      # bf16 vs bf16 with different accumulation order, every position
+    assert worst < 1.85e-2      # bf16 vs bf16 with different accumulation order, every position (measured on a B200: 1.23e-2)
 
 
-def test_next_token_logits_and_fp32_reference():
-    """north_star metric: max|d|/max|ref| on the next-token logits; reported against the bf16 oracle and the fp32 oracle."""
-    cfg, sd, model, proc = _setup(seed=1)
-    ts1, _ = _demo_series()
-    enc = proc(text=["Describe <ts><ts/> please, in detail, with numbers and dates"], timeseries=[ts1], return_tensors="pt")
-    lg = model.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"]).logits[:, 0]
-    embeds, _ = _oracle_embeds(cfg, sd, enc)
-    st = od.State(cfg.num_hidden_layers)
-    ref16 = od.logits(od.forward_hidden(embeds[0], sd, _oracle_cfg(cfg), st)[-1:], sd)
-    sd32 = {k: v.float() for k, v in sd.items()}
-    st = od.State(cfg.num_hidden_layers)
-    ref32 = od.logits(od.forward_hidden(embeds[0].float(), sd32, _oracle_cfg(cfg), st)[-1:], sd32)
-    e16, e32, o32 = rel_err(lg, ref16), rel_err(lg, ref32), rel_err(ref16, ref32)
-    record("model_next_token_logits", err_vs_bf16_oracle=e16, err_vs_fp32_oracle=e32, bf16_oracle_vs_fp32_oracle=o32)
-    # bf16 has a 2^-8 mantissa: two correct bf16 evaluations with different accumulation order differ by ~1e-2 of
-    # max|logit| here, which is also the bf16 CPU oracle's own distance to fp32 (measured 1.09e-2 on B200 round 1).
-    # The gate: the B200 path is no farther from the fp32 truth than the reference's bf16 CPU path is, and within
-    # 2e-2 of that path.  The north_star's 1e-3 is checked in fp16 (test below), where the dtype allows it.
-    assert e32 <= 1.25 * o32 + 1e-3
-    assert e16 < 2e-2
-
-
-def test_next_token_logits_fp16():
-    """fp16 (the dtype the reference actually runs): 10-bit mantissa -> the 1e-3-class tolerance."""
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_next_token_logits_comparative_gate(dt):
+    """BASELINE.json configs[0] in both 16-bit dtypes (fp16 is what the reference runs): the north_star metric
+    max|d|/max|ref| on the next-token logits against the oracle in the same dtype AND against the fp32 oracle, gated comparatively
+    (tests/gpu_util.py:parity_gate -- the same-dtype CPU oracle is itself 1.1e-2 (bf16) / 1.5e-3 (fp16) from fp32)."""
     from chatts_b200 import ChatTSConfig, ChatTSProcessor, SimpleTokenizer
     from chatts_b200.model import ChatTSForCausalLM
     from chatts_b200.weights import synthetic_state_dict
-    dt = torch.float16
     cfg = ChatTSConfig.tiny()
-    sd = synthetic_state_dict(cfg, seed=99, device="cpu", dtype=dt, std=0.05)
+    sd = synthetic_state_dict(cfg, seed=1235, device="cpu", dtype=dt, std=0.05)
     model = ChatTSForCausalLM(cfg, sd, dtype=dt, max_batch=4, max_seq_len=512, page_size=16)
     proc = ChatTSProcessor(SimpleTokenizer(cfg.ts_token_start_index, cfg.pad_token_id, cfg.eos_token_id), cfg)
     ts1, _ = _demo_series()
-    enc = proc(text=["Describe <ts><ts/> please"], timeseries=[ts1], return_tensors="pt")
+    # configs[0]: one 256-point sine series + a 64-token prompt
+    enc = proc(text=["Describe <ts><ts/> please, in detail, with numbers and dates: " + "x" * 20], timeseries=[ts1], return_tensors="pt")
     lg = model.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"]).logits[:, 0]
-    ts_w = {k[len("ts_encoder."):]: v.float() for k, v in sd.items() if k.startswith("ts_encoder.")}
-    sd32 = {k: v.float() for k, v in sd.items()}
-    feats, pc = ote.forward(enc["timeseries"].to(dt).float(), cfg.ts, ts_w)
-    emb = om.hf_merge(enc["input_ids"], enc["attention_mask"], sd32["model.embed_tokens.weight"], feats, pc.tolist(),
-                      cfg.ts_token_start_index)[0]
-    st = od.State(cfg.num_hidden_layers)
-    ref32 = od.logits(od.forward_hidden(emb, sd32, _oracle_cfg(cfg), st)[-1:], sd32)
-    e = rel_err(lg, ref32)
-    record("model_next_token_logits_fp16", err_vs_fp32_oracle=e)
-    assert e < 3e-3
+    refs = []
+    for fp32 in (False, True):
+        w = {k: v.float() for k, v in sd.items()} if fp32 else sd
+        ts_w = {k[len("ts_encoder."):]: v for k, v in w.items() if k.startswith("ts_encoder.")}
+        x = enc["timeseries"].to(dt)
+        feats, pc = ote.forward(x.float() if fp32 else x, cfg.ts, ts_w)
+        emb = om.hf_merge(enc["input_ids"], enc["attention_mask"], w["model.embed_tokens.weight"], feats, pc.tolist(),
+                          cfg.ts_token_start_index)[0]
+        refs.append(od.logits(od.forward_hidden(emb, w, _oracle_cfg(cfg), od.State(cfg.num_hidden_layers))[-1:], w))
+    # fixed bounds: 1.5 x the B200 measurements (bf16 1.0e-2; fp16 ~1.3e-3 against fp32, same order against the fp16 oracle)
+    parity_gate("model_next_token_logits", lg, refs[0], refs[1], dt, 1.5e-2 if dt == torch.bfloat16 else 2.5e-3)
 
 
 @pytest.mark.parametrize("use_graph", [True, False])
@@ -150,7 +132,7 @@ def test_generate_greedy_matches_oracle(use_graph):
             lg = od.logits(od.forward_hidden(sd["model.embed_tokens.weight"][tok][None, :], sd, _oracle_cfg(cfg), st), sd)[0].float()
     record("generate_greedy_agreement", use_graph=use_graph, free_running_first_divergence=str(agree), steps=new,
            teacher_forced_exact=exact, teacher_forced_total=2 * new, worst_gap_rel=worst_gap)
-    assert worst_gap < 2e-2            # every produced token is (within bf16 noise) the oracle's choice
+    assert worst_gap < 1e-2            # every produced token is (within bf16 noise) the oracle's choice (measured on a B200: 6.0e-3)
     assert exact >= int(0.9 * 2 * new)
 
 
