@@ -29,7 +29,7 @@ SYMBOLS = [
     "cts_ce_loss_grad", "cts_gather_rows", "cts_lora_wgrad", "cts_adamw", "cts_grad_norm_ws_floats", "cts_grad_norm_clip",
     "cts_lora_pack",
     "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step", "cts_ts_encode", "cts_gemm_decode_fused",
-    "cts_peer_ll_region_bytes", "cts_peer_allreduce_ll", "cts_trace_enable",
+    "cts_peer_ll_region_bytes", "cts_peer_allreduce_ll", "cts_trace_enable", "cts_ts_encode_fused_ok", "cts_ts_encode_fused",
 ]
 FUSED_RESIDUAL, FUSED_SWIGLU, FUSED_QKV_ROPE = 0, 1, 2
 PACK_DESC_LONGS = 12
@@ -141,6 +141,8 @@ def load_library():
     lib.cts_peer_allreduce_ll.argtypes = [vp, vp, i, vp, ll, vp, i, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
     lib.cts_peer_allreduce_ll.restype = i
     lib.cts_trace_enable.argtypes = [vp, vp]
+    lib.cts_ts_encode_fused_ok.argtypes = [C.POINTER(TsEncodeArgs)]
+    lib.cts_ts_encode_fused.argtypes = [vp, C.POINTER(TsEncodeArgs), vp]
     lib.cts_decode_chain.argtypes = [vp, C.POINTER(ChainArgs), vp]
     lib.cts_decode_chain.restype = i
     lib.cts_peer_greedy_advance.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp, i, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp]
@@ -404,6 +406,40 @@ class Context:
         a.row_map = row_map.data_ptr() if row_map is not None else None
         self._chk(self.lib.cts_ts_encode(self.h, C.byref(a), _stream()), 3 + 2 * len(weights))
         return valid, cnt, off
+
+    def ts_mlp_fused(self, x, num_features, patch_size, mode, pos_table, emb_dim, max_seq_len, weights, biases, valid, off, mx,
+                     total_rows, out, row_map=None):
+        """cts_ts_encode_fused: patchify + the whole MLP + the row scatter in ONE launch (<= 256 patch rows; the count stage has run:
+        ``valid`` / ``off`` / ``mx`` are its outputs).  Returns False when the shape is outside the fused kernel's range."""
+        n = x.shape[0]
+        xx = x.reshape(n, -1)
+        dev, dt = xx.device, xx.dtype
+        hidden, in0 = weights[0].shape[0], weights[0].shape[1]
+        a = TsEncodeArgs()
+        a.x, a.dtype, a.n_series, a.row_len = xx.data_ptr(), dtype_code(dt), n, xx.shape[1]
+        a.num_features, a.patch_size, a.mode = num_features, patch_size, mode
+        a.pos_table = pos_table.data_ptr() if pos_table is not None else None
+        a.emb_dim, a.max_seq_len, a.num_layers, a.hidden, a.in0 = emb_dim, max_seq_len, len(weights), hidden, in0
+        a.total_rows = total_rows
+        if not self.lib.cts_ts_encode_fused_ok(C.byref(a)):
+            return False
+        key = (total_rows, in0, hidden, str(dt), str(dev))
+        cache = self.__dict__.setdefault("_ts_fused_ws", {})
+        ws = cache.get(key)
+        if ws is None:                                  # persistent workspaces: stable addresses under CUDA-graph capture
+            ws = (torch.empty(total_rows, in0, device=dev, dtype=dt), [torch.empty(total_rows, hidden, device=dev, dtype=dt) for _ in range(2)])
+            cache[key] = ws
+        rows, act = ws
+        wt = (C.c_void_p * len(weights))(*[w.data_ptr() for w in weights])
+        bt = (C.c_void_p * len(biases))(*[b.data_ptr() for b in biases])
+        a.weights, a.biases = wt, bt
+        a.valid_len, a.row_offset, a.max_valid = valid.data_ptr(), off.data_ptr(), mx.data_ptr()
+        a.rows_ws = rows.data_ptr()
+        a.act_ws[0], a.act_ws[1] = act[0].data_ptr(), act[1].data_ptr()
+        a.out, a.out_ld = out.data_ptr(), out.stride(0)
+        a.row_map = row_map.data_ptr() if row_map is not None else None
+        self._chk(self.lib.cts_ts_encode_fused(self.h, C.byref(a), _stream()), 1)
+        return True
 
     def rmsnorm(self, x, w, eps, out, t=None):
         t = x.shape[0] if t is None else t

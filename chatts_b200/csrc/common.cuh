@@ -25,6 +25,7 @@ struct cts_ctx {
   int no_persistent_gemm;     // CTS_NO_PERSISTENT_GEMM=1: A/B switch back to the one-tile-per-CTA kernel for big T
   int norm_cluster;           // CTS_NORM_CLUSTER: max thread-block-cluster size of the decode RMSNorm kernel (default 8)
   int decode_stages;    // tuning knob (CTS_DECODE_SMEM_KB): shared-memory budget per CTA of the decode GEMM
+  int no_ts_fused;      // CTS_TS_FUSED=0: the TS encoder always takes the multi-launch path (A/B testing)
   int no_next_prefetch; // CTS_NEXT_PREFETCH=0: ignore the next-GEMM weight prefetch hints (A/B testing)
   int next_prefetch_mb; // CTS_NEXT_PREFETCH_MB (default 0 = off): budget of the hint the C++ step executor passes (model.py passes its own)
 };

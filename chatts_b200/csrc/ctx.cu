@@ -72,6 +72,22 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
   ctx->norm_cluster = e5 ? atoi(e5) : 8;
   const char* e2 = getenv("CTS_DECODE_SMEM_KB");
   ctx->decode_stages = e2 ? atoi(e2) : 75;   // 3 CTAs/SM x 3-4 stages measured best on B200 (profiles/r1_sweep_decode_gemm.txt)
+  // a few zero-initialised device words for kernels that synchronise through global counters (the fused TS encoder's grid barrier);
+  // allocated here so that nothing is allocated inside a CUDA-graph capture
+  {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 4096;
+    if (cudaMalloc(&ctx->scratch, ctx->scratch_bytes) != cudaSuccess || cudaMemset(ctx->scratch, 0, ctx->scratch_bytes) != cudaSuccess) {
+      fprintf(stderr, "chatts_b200: cannot allocate the context scratch\n");
+      ctx->scratch = nullptr;
+    }
+    cudaSetDevice(cur);
+  }
+  const char* e8 = getenv("CTS_TS_FUSED");
+  ctx->no_ts_fused = (e8 && atoi(e8) == 0) ? 1 : 0;
   const char* e6 = getenv("CTS_NEXT_PREFETCH");
   ctx->no_next_prefetch = (e6 && atoi(e6) == 0) ? 1 : 0;
   const char* e7 = getenv("CTS_NEXT_PREFETCH_MB");
@@ -82,6 +98,7 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
 
 extern "C" void cts_ctx_destroy(cts_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->scratch) cudaFree(ctx->scratch);
   free(ctx);
 }
 
@@ -129,9 +146,10 @@ extern "C" int cts_trace_set_elementwise(unsigned long long* buf);
 extern "C" int cts_trace_set_attention(unsigned long long* buf);
 extern "C" int cts_trace_set_allreduce_ll(unsigned long long* buf);
 extern "C" int cts_trace_set_fused(unsigned long long* buf);
+extern "C" int cts_trace_set_ts_fused(unsigned long long* buf);
 extern "C" int cts_trace_enable(cts_ctx* ctx, unsigned long long* buf) {
   if (!ctx) return CTS_ERR_BAD_ARG;
-  if (cts_trace_set_gemm(buf) || cts_trace_set_elementwise(buf) || cts_trace_set_attention(buf) || cts_trace_set_allreduce_ll(buf) || cts_trace_set_fused(buf))
+  if (cts_trace_set_gemm(buf) || cts_trace_set_elementwise(buf) || cts_trace_set_attention(buf) || cts_trace_set_allreduce_ll(buf) || cts_trace_set_fused(buf) || cts_trace_set_ts_fused(buf))
     return cts_set_error(ctx, CTS_ERR_CUDA, "cts_trace_enable: cudaMemcpyToSymbol failed");
   return CTS_OK;
 }

@@ -122,6 +122,7 @@ extern "C" int cts_ts_encode(cts_ctx* ctx, const cts_ts_encode_args* a, void* st
                           a->row_offset, a->max_valid, stream));
   if (a->total_rows == 0 || a->n_series == 0) return CTS_OK;
   CTS_CHECK_ARG(ctx, a->rows_ws && a->act_ws[0] && a->act_ws[1] && a->out, "null workspace / out");
+  if (cts_ts_encode_fused_ok(a) && !ctx->no_ts_fused) return cts_ts_encode_fused(ctx, a, stream);      // metric-sized prompts: ONE launch
   const int max_patches = (a->row_len / a->num_features + a->patch_size - 1) / a->patch_size;
   STEP(cts_ts_patchify(ctx, a->x, a->dtype, a->n_series, a->row_len, a->num_features, a->patch_size, a->mode, a->pos_table, a->emb_dim,
                        a->max_seq_len, a->valid_len, a->row_offset, a->max_valid, max_patches, a->rows_ws, a->in0, stream));

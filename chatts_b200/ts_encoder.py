@@ -41,6 +41,9 @@ class TimeSeriesEmbedding:
             self.w.append(w.contiguous())
             self.b.append(weights[f"{prefix}mlp.{2 * li}.bias"].to(self.device, dtype).contiguous())
         self.ctx = _cabi.get_context(self.device)
+        import os
+        # prompts of up to 256 patch rows run as ONE launch (csrc/ts_encoder_fused.cu); CTS_TS_FUSED=0 keeps the multi-launch path
+        self.use_fused = os.environ.get("CTS_TS_FUSED", "1") != "0" and hasattr(self.ctx, "ts_mlp_fused")
 
     # -- A3: patch counts -------------------------------------------------------------------------
     def patch_counts(self, x):
@@ -81,6 +84,13 @@ class TimeSeriesEmbedding:
         if total == 0:
             feats = torch.empty(0, self.hidden_size, device=self.device)      # :191 (default dtype)
             return (feats if out is None else None), cnt_h.to(torch.int64)
+        if self.use_fused and total <= 256:
+            # metric-sized prompts (8 series x 256 points = 128 rows): patchify + MLP + row scatter in ONE launch (csrc/ts_encoder_fused.cu)
+            dst = out if out is not None else torch.empty(total, self.hidden_size, device=self.device, dtype=self.dtype)
+            if self.ctx.ts_mlp_fused(x, self.num_features, self.patch_size, self.mode, self.pos_table, self.embedding_dim,
+                                     self.max_sequence_length, self.w, self.b, valid, off, mx, total, dst,
+                                     row_map=row_map if out is not None else None):
+                return (None if out is not None else dst), cnt_h.to(torch.int64)
         row_len = x.shape[1]
         max_patches = (row_len // self.num_features + self.patch_size - 1) // self.patch_size
         rows = torch.empty(total, self.input_size, device=self.device, dtype=self.dtype)

@@ -355,6 +355,16 @@ typedef struct {
 } cts_ts_encode_args;
 int cts_ts_encode(cts_ctx* ctx, const cts_ts_encode_args* args, void* stream);
 
+/* The same encoder as ONE launch (csrc/ts_encoder_fused.cu) for prompts of up to 256 patch rows -- the BASELINE.json metric prompt is
+ * 8 series x 256 points = 128 rows: patchify + last-value pad + position-embedding gather (chatts_vllm.py:107-183), every MLP layer
+ * (tcgen05, the K splits of a 128-feature tile reduced over distributed shared memory inside a thread-block cluster, bias + exact-erf
+ * GELU, chatts_vllm.py:83-91,186-188) and the row scatter into inputs_embeds (chatts_vllm.py:569-573), grid barriers between the
+ * layers, the next layer's weight tiles requested while a CTA waits.  HBM-bound on the weight stream (212 MB at the 14B shape).
+ * valid_len / row_offset / max_valid are INPUTS (cts_ts_patch_count ran: the host sizes the merged sequence from the counts);
+ * splitk_ws is unused.  cts_ts_encode_fused_ok: 1 when the shape is in range (cts_ts_encode then takes this path by itself). */
+int cts_ts_encode_fused_ok(const cts_ts_encode_args* args);
+int cts_ts_encode_fused(cts_ctx* ctx, const cts_ts_encode_args* args, void* stream);
+
 typedef struct {
   const void* wqkv;   /* [(nh+2nkv)*d, hidden]                                       */
   const void* bqkv;   /* [(nh+2nkv)*d] or NULL (Qwen3)                               */

@@ -135,8 +135,8 @@ template <typename F> static inline int cudaFuncSetAttribute(F, int, int) { retu
 // other CTAs' DYNAMIC shared memory (static __shared__ variables are not mappable here -- none of the shimmed kernels needs that)
 struct ShimCluster {
   int size = 1;
-  uint8_t* dyn_base[16] = {nullptr};
-  void* static_ptr[16] = {nullptr};                        // a STATIC shared variable published for the peers (shim_publish_static)
+  uint8_t* dyn_base[1024] = {nullptr};                     // 1024: a cooperative launch runs its WHOLE grid as one "cluster" (grid barriers need every CTA live)
+  void* static_ptr[1024] = {nullptr};                        // a STATIC shared variable published for the peers (shim_publish_static)
   pthread_barrier_t bar;
 };
 extern thread_local ShimCluster* g_cluster;
@@ -169,11 +169,16 @@ static inline void* shim_static_peer(unsigned r) { return g_cluster ? g_cluster-
 void shim_launch(const std::function<void()>& body, dim3 grid, dim3 block, size_t smem, dim3 cluster);
 
 // cudaLaunchKernelEx with the two attributes the library uses
-enum { cudaLaunchAttributeProgrammaticStreamSerialization = 1, cudaLaunchAttributeClusterDimension = 2 };
+enum { cudaLaunchAttributeProgrammaticStreamSerialization = 1, cudaLaunchAttributeClusterDimension = 2, cudaLaunchAttributeCooperative = 3 };
 struct cudaLaunchAttribute {
   int id;
-  union { int programmaticStreamSerializationAllowed; struct { unsigned x, y, z; } clusterDim; } val;
+  union { int programmaticStreamSerializationAllowed; int cooperative; struct { unsigned x, y, z; } clusterDim; } val;
 };
+// a kernel that synchronises its whole grid (grid barriers through a global counter) asks for it with this flag on the host shim:
+// every CTA of the grid then runs concurrently (one OS thread each), i.e. the grid is scheduled as ONE cluster whose ranks are the
+// linear CTA indices -- the kernel maps its real cluster ranks to those under CTS_HOST_SHIM
+extern thread_local bool g_whole_grid_next;
+static inline void shim_next_launch_whole_grid() { g_whole_grid_next = true; }
 struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes = 0; void* stream = nullptr; cudaLaunchAttribute* attrs = nullptr; unsigned numAttrs = 0; };
 template <typename... KArgs, typename... Args>
 static inline int cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kern)(KArgs...), Args... args) {
@@ -181,6 +186,9 @@ static inline int cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kern)
   dim3 cl(1, 1, 1);
   for (unsigned i = 0; i < cfg->numAttrs; ++i)
     if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension) cl = dim3(cfg->attrs[i].val.clusterDim.x, cfg->attrs[i].val.clusterDim.y, cfg->attrs[i].val.clusterDim.z);
+  for (unsigned i = 0; i < cfg->numAttrs; ++i)
+    if (cfg->attrs[i].id == cudaLaunchAttributeCooperative && cfg->attrs[i].val.cooperative) g_whole_grid_next = true;
+  if (g_whole_grid_next) { cl = cfg->gridDim; g_whole_grid_next = false; }
   shim_launch([&] { std::apply(kern, tup); }, cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, cl);
   return 0;
 }
@@ -247,7 +255,8 @@ struct cts_ctx {
   int device;
   int sm_count;
   int decode_stages, l2_prefetch_mb, no_persistent_gemm, force_wmma_attention, norm_cluster, max_smem_optin;
-  int no_next_prefetch, next_prefetch_mb;          // next-GEMM L2 prefetch hint (a no-op on the host: tma_prefetch_l2_2d does nothing)
+  int no_next_prefetch, next_prefetch_mb, no_ts_fused;
+  void* scratch;                                           // zero-initialised counters (grid barrier of the fused TS encoder)          // next-GEMM L2 prefetch hint (a no-op on the host: tma_prefetch_l2_2d does nothing)
   char err[512];
 };
 int cts_set_error(cts_ctx* ctx, int code, const char* fmt, ...);

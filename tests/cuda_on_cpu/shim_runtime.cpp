@@ -12,6 +12,7 @@ thread_local std::unordered_map<const void*, ShimMbar> g_mbar;
 thread_local float g_tmem[128][512];
 thread_local uint8_t* g_dyn_smem = nullptr;
 thread_local size_t g_dyn_bytes = 0;
+thread_local bool g_whole_grid_next = false;
 thread_local ShimCluster* g_cluster = nullptr;
 thread_local int g_cluster_rank = 0;
 thread_local ShimIdx g_tid, g_bid;
@@ -221,6 +222,8 @@ extern "C" int cts_ctx_create(int device, cts_ctx** out) {
   c->norm_cluster = 8;
   c->no_next_prefetch = 0;
   c->next_prefetch_mb = 0;
+  c->no_ts_fused = 0;
+  c->scratch = calloc(1, 4096);
   c->max_smem_optin = 232448;
   c->err[0] = 0;
   *out = c;

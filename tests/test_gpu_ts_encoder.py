@@ -106,3 +106,100 @@ def test_large_batch_many_series():
     e = rel_err(feats, ref)
     record("ts_encoder_300_series", err=e)
     assert e < 1e-2
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# The fused encoder (csrc/ts_encoder_fused.cu: patchify + every MLP layer + the row scatter in ONE launch, <= 256 patch rows)
+# --------------------------------------------------------------------------------------------------------------------
+def _series_batch(lens, seed=0):
+    from chatts_b200.processor import sp_encoding
+    rng = np.random.default_rng(seed)
+    enc = [sp_encoding(np.cumsum(rng.normal(size=L)) * rng.uniform(0.2, 20))[0] for L in lens]
+    Lmax = max(e.shape[0] for e in enc)
+    x = np.zeros((len(lens), Lmax, 1))
+    for i, e in enumerate(enc):
+        x[i, : e.shape[0]] = e
+    return torch.from_numpy(x).to(torch.float32)
+
+
+def _tiny_encoder(dtype, hidden=256, mode=1, layers=5, seed=3):
+    from chatts_b200.ts_encoder import TimeSeriesEmbedding
+    cfg = dict(patch_size=16, num_layers=layers, hidden_size=hidden, num_features=2, max_sequence_length=1024,
+               use_position_embedding=mode == 1, use_position_idx=mode == 2, embedding_dim=16)
+    in0 = 16 * (1 + 16) if mode == 1 else (32 if mode == 2 else 16)
+    g = torch.Generator().manual_seed(seed)
+    w = {}
+    if mode == 1:
+        w["ts_encoder.position_embedding.weight"] = torch.randn(1025, 16, generator=g) * 0.5
+    k = in0
+    for li in range(layers):
+        w[f"ts_encoder.mlp.{2 * li}.weight"] = torch.randn(hidden, k, generator=g) * (1.5 / k ** 0.5)
+        w[f"ts_encoder.mlp.{2 * li}.bias"] = torch.randn(hidden, generator=g) * 0.1
+        k = hidden
+    return cfg, w, TimeSeriesEmbedding(cfg, w, dtype=dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("lens", [[256] * 8, [16], [256, 100, 37, 1000], [256] * 16, [1], [64] * 4 + [48]])
+def test_fused_encoder_matches_the_multi_launch_path_and_the_oracle(lens, dtype):
+    """Same rows, same rounding points; the K partition of the sums differs (cluster split vs the GEMM's own split), so the two
+    paths agree to fp32 summation order.  Row counts 128 (the metric prompt), 1, 89 (ragged), 256 (the upper limit), ..."""
+    cfg, w, enc = _tiny_encoder(dtype)
+    x = _series_batch(lens)
+    assert enc.use_fused
+    l0 = enc.ctx.launches
+    fused, pc = enc.encode(x.cuda())
+    n_fused = enc.ctx.launches - l0
+    enc.use_fused = False
+    l0 = enc.ctx.launches
+    multi, pc2 = enc.encode(x.cuda())
+    n_multi = enc.ctx.launches - l0
+    torch.cuda.synchronize()
+    assert pc.tolist() == pc2.tolist() == [(L + 15) // 16 for L in lens]
+    assert n_fused == 3 and n_multi > n_fused            # count + scan + ONE launch for everything else
+    wo = {k[len("ts_encoder."):]: v.to(dtype) for k, v in w.items()}
+    ref, _ = ote.forward(x.to(dtype), cfg, wo)
+    e_paths, e_oracle = rel_err(fused, multi), rel_err(fused, ref)
+    record("ts_encoder_fused", rows=int(pc.sum()), dtype=str(dtype), fused_vs_multi_launch=e_paths, fused_vs_oracle=e_oracle,
+           multi_launch_vs_oracle=rel_err(multi, ref))
+    tol = 6e-3 if dtype == torch.bfloat16 else 8e-4
+    assert e_paths < tol and e_oracle < 1.5 * tol and torch.isfinite(fused.float()).all()
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_fused_encoder_other_position_modes(mode):
+    cfg, w, enc = _tiny_encoder(torch.bfloat16, mode=mode, layers=3)
+    x = _series_batch([256, 64, 128], seed=5)                # multiples of the patch size (the reference raises otherwise, :128)
+    fused, pc = enc.encode(x.cuda())
+    wo = {k[len("ts_encoder."):]: v.to(torch.bfloat16) for k, v in w.items()}
+    ref, _ = ote.forward(x.to(torch.bfloat16), cfg, wo)
+    assert pc.tolist() == [16, 4, 8] and rel_err(fused, ref) < 9e-3
+
+
+def test_fused_encoder_scatters_rows_through_row_map():
+    """The last layer writes row i to out[row_map[i]] (the sp-mask scatter into inputs_embeds, chatts_vllm.py:569-573): mapped rows
+    hold the features, every other row of the destination is untouched, a negative entry drops its row."""
+    cfg, w, enc = _tiny_encoder(torch.bfloat16)
+    x = _series_batch([256, 100, 37])
+    feats, pc = enc.encode(x.cuda())
+    total = int(pc.sum())
+    g = torch.Generator().manual_seed(1)
+    perm = torch.randperm(total + 9, generator=g)[:total].to(torch.int32)
+    perm[3] = -1
+    big = torch.full((total + 9, enc.hidden_size), 7.0, device="cuda", dtype=torch.bfloat16)
+    counts = enc.patch_counts(x.cuda())
+    enc.encode(x.cuda(), out=big, row_map=perm.cuda(), counts=counts)
+    torch.cuda.synchronize()
+    keep = perm >= 0
+    assert torch.equal(big[perm[keep].long().cuda()], feats[keep.cuda()])
+    untouched = torch.ones(total + 9, dtype=torch.bool)
+    untouched[perm[keep].long()] = False
+    assert bool((big[untouched.cuda()] == 7.0).all())
+
+
+def test_more_than_256_rows_take_the_multi_launch_path():
+    cfg, w, enc = _tiny_encoder(torch.bfloat16)
+    x = _series_batch([256] * 17)                            # 272 rows
+    l0 = enc.ctx.launches
+    feats, pc = enc.encode(x.cuda())
+    assert feats.shape[0] == 272 and enc.ctx.launches - l0 > 3
