@@ -11,6 +11,7 @@
 //                        point (padding id = max_sequence_length, :76,:128) and writes the [P, in0] row coalesced.
 // HBM-bound: bytes = N*2L*elt (read once) + sum(P)*in0*elt (written once) + the touched pos-table rows.
 #include "common.cuh"
+#include "ts_rows.cuh"
 
 namespace {
 
@@ -96,7 +97,7 @@ __global__ void ts_scan_kernel(const int* __restrict__ valid_len, const int* __r
   }
 }
 
-// one CTA per (patch, series)
+// one CTA per (patch, series); in0 % 8 == 0: the row goes out in 16-byte chunks (ts_rows.cuh), else element by element
 template <typename T>
 __global__ void ts_patchify_kernel(const T* __restrict__ x, int row_len, int nf, int patch, int mode,
                                    const T* __restrict__ pos_table, int emb_dim, int max_seq_len,
@@ -109,41 +110,31 @@ __global__ void ts_patchify_kernel(const T* __restrict__ x, int row_len, int nf,
   const int vl = valid_len[s];
   const int cnt = (vl + patch - 1) / patch;
   if (pidx >= cnt) return;
-  extern __shared__ uint8_t sm_raw[];
-  T* vals = reinterpret_cast<T*>(sm_raw);   // [patch]
   const T* row = x + (size_t)s * row_len;
   const int p0 = pidx * patch;
-  for (int j = threadIdx.x; j < patch; j += blockDim.x) {
-    const int pt = p0 + j;
-    const int src = pt < vl ? pt : vl - 1;           // pad with the last valid value (:121-125)
-    vals[j] = row[(size_t)src * nf];
-  }
-  __syncthreads();
   T* out = rows_out + (size_t)(row_offset[s] + pidx) * in0;
-  if (mode == 0) {
-    for (int j = threadIdx.x; j < patch; j += blockDim.x) out[j] = vals[j];
-  } else if (mode == 1) {
-    // [patch values | patch x emb_dim position embeddings (point-major, dim-minor)]   (:178-182)
-    for (int j = threadIdx.x; j < in0; j += blockDim.x) {
-      if (j < patch) {
-        out[j] = vals[j];
-      } else {
-        const int e = j - patch;
-        const int pt = p0 + e / emb_dim;
-        // padding id (:76,:128); a point index beyond the table is rejected on the host (IndexError, as nn.Embedding raises) and
-        // clamped here so that the kernel can never read past pos_table [max_seq_len + 1, emb_dim]
-        const int id = pt < vl ? min(pt, max_seq_len) : max_seq_len;
-        out[j] = pos_table[(size_t)id * emb_dim + (e % emb_dim)];
-      }
+  const float denom = (float)max(1, max_valid[0] - 1);
+  if ((in0 & 7) == 0 && (((uintptr_t)rows_out) & 15) == 0 && (mode != 1 || (((uintptr_t)pos_table) & 15) == 0)) {
+    for (int j = threadIdx.x; j < (in0 >> 3); j += blockDim.x)
+      *reinterpret_cast<uint4*>(out + j * 8) = ts_row_chunk<T>(row, nf, patch, mode, pos_table, emb_dim, max_seq_len, vl, p0, j * 8, denom);
+    return;
+  }
+  for (int col = threadIdx.x; col < in0; col += blockDim.x) {
+    T v;
+    if (mode == 2) {
+      const int pt = p0 + (col >> 1);
+      v = (col & 1) == 0 ? row[(size_t)(pt < vl ? pt : vl - 1) * nf] : DT<T>::from_f(pt < vl ? (float)pt / denom : -1.0f);
+    } else if (col < patch) {
+      const int pt = p0 + col;
+      v = row[(size_t)(pt < vl ? pt : vl - 1) * nf];           // pad with the last valid value (:121-125)
+    } else {
+      const int e = col - patch;
+      const int pt = p0 + e / emb_dim;
+      // padding id (:76,:128); a point index beyond the table is rejected on the host (IndexError, as nn.Embedding raises) and clamped here
+      const int id = pt < vl ? min(pt, max_seq_len) : max_seq_len;
+      v = pos_table[(size_t)id * emb_dim + (e % emb_dim)];
     }
-  } else {
-    // use_position_idx: interleave (value, pos / max(1, max_valid-1)), padding position = -1  (:145-153)
-    const float denom = (float)max(1, max_valid[0] - 1);
-    for (int j = threadIdx.x; j < 2 * patch; j += blockDim.x) {
-      const int pt = p0 + (j >> 1);
-      if ((j & 1) == 0) out[j] = vals[j >> 1];
-      else out[j] = DT<T>::from_f(pt < vl ? (float)pt / denom : -1.0f);
-    }
+    out[col] = v;
   }
 }
 
@@ -191,7 +182,7 @@ extern "C" int cts_ts_patchify(cts_ctx* ctx, const void* x, int dtype, int n_ser
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)max_patches, (unsigned)n_series);
   const int threads = in0 >= 256 ? 128 : 64;
-  const size_t smem = (size_t)patch_size * 2;
+  const size_t smem = 0;
   if (dtype == CTS_BF16)
     CTS_CUDA(ctx, launch_pdl(ts_patchify_kernel<__nv_bfloat16>, grid, dim3(threads), smem, st, 1, (const __nv_bfloat16*)x, row_len,
                              num_features, patch_size, mode, (const __nv_bfloat16*)pos_table, emb_dim, max_seq_len, valid_len,

@@ -60,7 +60,6 @@ SUBSTITUTIONS = {
         ("    ss_cta = v;\n  }\n  cluster.sync();", "    ss_cta = v;\n    shim_publish_static(&ss_cta);\n  }\n  cluster.sync();"),
         ("*cluster.map_shared_rank(&ss_cta, r)", "*(float*)shim_static_peer((unsigned)r)"),
     ],
-    "ts_frontend.cu": [("extern __shared__ uint8_t sm_raw[];", "uint8_t* sm_raw = g_dyn_smem;")],
     "attention_bwd_tc5.cu": [("extern __shared__ uint8_t dq_raw[];", "uint8_t* dq_raw = g_dyn_smem;"),
                              ("extern __shared__ uint8_t dkv_raw[];", "uint8_t* dkv_raw = g_dyn_smem;")],
     "gemm_tcgen05.cu": [("extern __shared__ uint8_t smem_raw[];", "uint8_t* smem_raw = g_dyn_smem;"),
@@ -73,6 +72,7 @@ def build(force=False):
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, f) for f in ("common.cuh", "mma.h", "cooperative_groups.h", "tensormap.cuh", "shim_runtime.cpp", "build.py")]
     deps.append(os.path.join(ROOT, "include", "chatts_b200.h"))
     deps.append(os.path.join(CSRC, "trace.cuh"))
+    deps.append(os.path.join(CSRC, "ts_rows.cuh"))
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
         return OUT
     os.makedirs(bdir, exist_ok=True)
@@ -87,6 +87,7 @@ def build(force=False):
         cpps.append(dst)
     for f in ("common.cuh", "mma.h", "cooperative_groups.h", "tensormap.cuh", "shim_runtime.cpp"):
         shutil.copyfile(os.path.join(HERE, f), os.path.join(bdir, f))
+    shutil.copyfile(os.path.join(CSRC, "ts_rows.cuh"), os.path.join(bdir, "ts_rows.cuh"))
     shutil.copyfile(os.path.join(CSRC, "trace.cuh"), os.path.join(bdir, "trace.cuh"))      # the real header: its CTS_HOST_SHIM branch makes every mark a no-op
     flags = ["-std=c++17", "-O2", "-fno-strict-aliasing", "-g", "-fPIC", "-pthread", "-w", "-I", bdir, "-I", os.path.join(ROOT, "include")]
     units = [os.path.join(bdir, "shim_runtime.cpp")] + cpps
