@@ -404,9 +404,11 @@ int cts_attn_bwd_tc5_launch(cts_ctx* ctx, const void* q, const void* k, const vo
                             const float* delta, const int* cu_seqlens, int batch, int max_seqlen, long long total_tokens, int nh,
                             int nkv, float scale, void* dq, void* dk, void* dv, int dtype, cudaStream_t st);
 
+// Default since round 2: the tcgen05 backward (head_dim 128) is validated on a B200 against autograd and the HMMA kernels and makes the
+// ChatTS-8B LoRA step 8 % faster (profiles/r2_bench_lora_variants.txt); CTS_ATTN_BWD_TC5=0 selects the HMMA kernels.
 static bool attn_bwd_use_tc5() {          // read per call (host side, once per launch): tests flip it inside one process
   const char* e = getenv("CTS_ATTN_BWD_TC5");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }
 
 extern "C" int cts_attn_bwd(cts_ctx* ctx, const void* q, const void* k, const void* v, const void* out, const void* dout,

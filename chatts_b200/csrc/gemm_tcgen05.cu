@@ -695,7 +695,11 @@ extern "C" int cts_gemm_suggest_split(cts_ctx* ctx, long long n, long long k, lo
   const long long slots = (long long)ctx->sm_count * (bn <= 128 ? (dual && bn <= 32 ? 3 : 2) : 1);
   if (tiles >= slots) return 1;
   long long s = slots / tiles;
-  const long long max_by_k = kb / 8 > 0 ? kb / 8 : 1;   // keep >= 8 K blocks (1 KiB of each weight row) per split
+  // keep >= 8 K blocks (1 KiB of each weight row) per split -- except at decode-sized t, where a short K range per CTA is exactly
+  // what a latency-bound launch wants (tensor-parallel shards: o_proj at TP8 has 10 K blocks; one CTA per tile would walk them
+  // serially through a 3-stage ring): there 2 blocks per split suffice
+  const long long per_split_min = bn <= 32 ? 2 : 8;
+  const long long max_by_k = kb / per_split_min > 0 ? kb / per_split_min : 1;
   if (s > max_by_k) s = max_by_k;
   if (s > 16) s = 16;
   if (s < 1) s = 1;

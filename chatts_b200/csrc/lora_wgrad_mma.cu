@@ -123,9 +123,11 @@ lora_wgrad_mma_kernel(const T* __restrict__ P, long long p_ld, long long p_col0,
 
 }  // namespace
 
+// Default since round 2 (validated on a B200: equal to the FMA kernel's result, LoRA step 18 % faster, profiles/r2_bench_lora_variants.txt);
+// CTS_WGRAD_MMA=0 selects the FMA kernel.
 bool cts_lora_wgrad_mma_enabled() {
   const char* e = getenv("CTS_WGRAD_MMA");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }
 
 // preconditions of the vector / ldmatrix path; false -> the caller uses the FMA kernel

@@ -70,7 +70,7 @@ def test_config2_batch32_variable_length_series_prefill(dt):
     lens_all = [len(s) for s in series]
     lg = model.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"]).logits[:, 0]
     # measured on a B200: 1.24e-2 (bf16) against the same-dtype oracle -> fixed bound 1.5 x that; fp16 bound 1.5 x its measured value
-    ref, pc = _gate("config2_batch32_varlen_prefill", lg, cfg, sd, enc, [0, 13, 31], dt, 1.85e-2 if dt == torch.bfloat16 else 3e-3)
+    ref, pc = _gate("config2_batch32_varlen_prefill", lg, cfg, sd, enc, [0, 13, 31], dt, 1.85e-2 if dt == torch.bfloat16 else 2.1e-3)
     assert pc.tolist() == [(n + 15) // 16 for n in lens_all]                 # bit-exact patch counts for 256 ragged series
 
 
@@ -219,7 +219,7 @@ def test_chatts_8b_qwen3_variant_matches_oracle(dt):
     x = np.arange(200)
     enc = proc(text=["Q3 <ts><ts/> end", "no ts"], timeseries=[np.cos(x / 7) * 3], padding=True, return_tensors="pt")
     lg = model.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"]).logits[:, 0]
-    _gate("chatts_8b_qwen3_variant", lg, cfg, sd, enc, [0, 1], dt, 1.8e-2 if dt == torch.bfloat16 else 3e-3)      # measured (bf16): 1.18e-2
+    _gate("chatts_8b_qwen3_variant", lg, cfg, sd, enc, [0, 1], dt, 1.8e-2 if dt == torch.bfloat16 else 2.2e-3)      # measured: 1.18e-2 (bf16), 1.45e-3 (fp16)
     ids = model.generate(**enc, max_new_tokens=10, ignore_eos=True)
     assert ids.shape[1] == enc["input_ids"].shape[1] + 10
 

@@ -99,7 +99,7 @@ def test_next_token_logits_comparative_gate(dt):
                           cfg.ts_token_start_index)[0]
         refs.append(od.logits(od.forward_hidden(emb, w, _oracle_cfg(cfg), od.State(cfg.num_hidden_layers))[-1:], w))
     # fixed bounds: 1.5 x the B200 measurements (bf16 1.0e-2; fp16 ~1.3e-3 against fp32, same order against the fp16 oracle)
-    parity_gate("model_next_token_logits", lg, refs[0], refs[1], dt, 1.5e-2 if dt == torch.bfloat16 else 2.5e-3)
+    parity_gate("model_next_token_logits", lg, refs[0], refs[1], dt, 1.57e-2 if dt == torch.bfloat16 else 1.6e-3)          # measured: 1.05e-2 / 1.04e-3
 
 
 @pytest.mark.parametrize("use_graph", [True, False])
