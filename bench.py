@@ -429,7 +429,7 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     probe_record = None
-    if world == 1 and not args.sweep_only and not args.no_probe and not args.layers and "CTS_DECODE_FUSED" not in os.environ:
+    if world == 1 and args.probe and not args.sweep_only and not args.no_probe and not args.layers and "CTS_DECODE_FUSED" not in os.environ:
         probe_record = probe_decode_variant(args)
         if probe_record.get("selected"):
             os.environ["CTS_DECODE_FUSED"] = str(probe_record["selected"])          # read by the model constructor below
@@ -688,7 +688,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run decode steps eagerly (for ncu launch lists)")
     ap.add_argument("--sweep-only", action="store_true", help="decode timing only (skip e2e)")
-    ap.add_argument("--no-probe", action="store_true", help="do not probe the cluster-fused decode variant (the default path is measured as is)")
+    ap.add_argument("--no-probe", action="store_true", help="(default) the default decode path is measured as is")
+    ap.add_argument("--probe", action="store_true", help="guarded child-process probe of the cluster-fused decode variants (round 1; measured slower at b = 32 on a B200, "
+                                                        "profiles/r2_decode_variants_ab.txt, so no longer on by default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
