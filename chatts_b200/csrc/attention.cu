@@ -249,7 +249,8 @@ attn_prefill_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
 constexpr int kTcQ = 128, kTcKV = 64, kTcThreads = 192;
 constexpr int kTcQHalf = kTcQ * 128;            // one [128 q rows x 128 B] swizzled half of the Q tile (16 KiB)
 constexpr int kTcKHalf = kTcKV * 128;           // one [64 kv rows x 128 B] half of a K or V tile (8 KiB)
-constexpr int kTcSmem = 2 * kTcQHalf + kTcQ * 128 + 2 * 2 * kTcKHalf;   // Q 32 + P 16 + K 16 + V 16 = 80 KiB -> 2 CTAs / SM
+constexpr int kTcStages = 3;                    // K/V ring: tiles of 2 x 8 KiB, consumed in the order they are loaded
+constexpr int kTcSmem = 2 * kTcQHalf + kTcQ * 128 + kTcStages * 2 * kTcKHalf;   // Q 32 + P 16 + ring 48 = 96 KiB -> 2 CTAs / SM
 
 // MN-major (N contiguous) B operand, 128B swizzle: atoms of [8 K-rows x 64 N-elements]; LBO = stride between the
 // 64-element N atoms (the two d-halves of the V tile), SBO = stride between consecutive 8-row K groups.
@@ -263,9 +264,11 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
-// Pipeline (per CTA; two CTAs share an SM): K and V are single-buffered with independent full/empty barriers, S is
-// double-buffered in TMEM (2 x 64 columns) and the MMA warp issues QK^T of tile i BEFORE P.V of tile i-1, so the softmax
-// warps work on tile i while the tensor core runs P.V(i-1); P is single-buffered behind a p_free barrier.
+// Pipeline (per CTA; two CTAs share an SM): K and V tiles travel through ONE ring of kTcStages slots in exactly the order the MMA
+// warp consumes them (pass 1: K_0 .. K_{n-1}; pass 2: K_0, K_1, V_0, K_2, V_1, ..., V_{n-1}), so the TMA producer runs up to
+// three tiles ahead instead of exposing one L2/HBM round trip per tile (round 1: K and V single-buffered, 22 % tensor-pipe
+// active); S is double-buffered in TMEM (2 x 64 columns) and the MMA warp issues QK^T of tile i BEFORE P.V of tile i-1, so the
+// softmax warps work on tile i while the tensor core runs P.V(i-1); P is single-buffered behind a p_free barrier.
 template <typename T, bool LSE>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -273,14 +276,13 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                         float scale, T* __restrict__ out, float* __restrict__ lse) {
   constexpr int HD = 128;
   extern __shared__ uint8_t tc_raw[];
-  __shared__ uint64_t q_bar, k_full, k_empty, v_full, v_empty, s_full[2], s_free[2], p_full, p_free, o_done;
+  __shared__ uint64_t q_bar, kv_full[kTcStages], kv_empty[kTcStages], s_full[2], s_free[2], p_full, p_free, o_done;
   __shared__ uint32_t tmem_slot;
   const uint32_t raw = smem_u32(tc_raw);
   uint8_t* smem = tc_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* q_s = smem;                               // 32 KiB: 2 d-halves x [128 x 128 B]
   uint8_t* p_s = q_s + 2 * kTcQHalf;                 // 16 KiB: [128 x 128 B] (64 kv columns)
-  uint8_t* k_s = p_s + kTcQ * 128;                   // 16 KiB: 2 d-halves x [64 x 128 B]
-  uint8_t* v_s = k_s + 2 * kTcKHalf;                 // 16 KiB
+  uint8_t* ring = p_s + kTcQ * 128;                  // kTcStages x 16 KiB: a K or V tile = 2 d-halves x [64 x 128 B]
 
   const int b = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -288,7 +290,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(&q_bar, 1);
-    mbar_init(&k_full, 1); mbar_init(&k_empty, 1); mbar_init(&v_full, 1); mbar_init(&v_empty, 1);
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 4); }
     mbar_init(&p_full, 4);
     mbar_init(&p_free, 1);
@@ -316,20 +318,23 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       mbar_expect_tx(&q_bar, (uint32_t)(2 * kTcQHalf));
       tma_load_2d(q_s, &tm_q, &q_bar, head * HD, seq0 + q0, CTS_L2_EVICT_FIRST);
       tma_load_2d(q_s + kTcQHalf, &tm_q, &q_bar, head * HD + 64, seq0 + q0, CTS_L2_EVICT_FIRST);
-      for (int i = 0; i < total; ++i) {
-        const int j = i < nt ? i : i - nt;
+      int n = 0;                                        // loads issued so far (ring slot n % kTcStages)
+      auto load_tile = [&](const CUtensorMap* tm, int j) {
+        const int sl = n % kTcStages;
+        mbar_wait(&kv_empty[sl], (((uint32_t)(n / kTcStages)) & 1u) ^ 1u);
+        mbar_expect_tx(&kv_full[sl], (uint32_t)(2 * kTcKHalf));
+        uint8_t* dst = ring + (size_t)sl * 2 * kTcKHalf;
         const int row = seq0 + j * kTcKV;
-        mbar_wait(&k_empty, ((uint32_t)i & 1u) ^ 1u);
-        mbar_expect_tx(&k_full, (uint32_t)(2 * kTcKHalf));
-        tma_load_2d(k_s, &tm_k, &k_full, kvh * HD, row, CTS_L2_EVICT_LAST);
-        tma_load_2d(k_s + kTcKHalf, &tm_k, &k_full, kvh * HD + 64, row, CTS_L2_EVICT_LAST);
-        if (i >= nt) {
-          mbar_wait(&v_empty, ((uint32_t)j & 1u) ^ 1u);
-          mbar_expect_tx(&v_full, (uint32_t)(2 * kTcKHalf));
-          tma_load_2d(v_s, &tm_v, &v_full, kvh * HD, row, CTS_L2_EVICT_LAST);
-          tma_load_2d(v_s + kTcKHalf, &tm_v, &v_full, kvh * HD + 64, row, CTS_L2_EVICT_LAST);
-        }
+        tma_load_2d(dst, tm, &kv_full[sl], kvh * HD, row, CTS_L2_EVICT_LAST);
+        tma_load_2d(dst + kTcKHalf, tm, &kv_full[sl], kvh * HD + 64, row, CTS_L2_EVICT_LAST);
+        ++n;
+      };
+      for (int j = 0; j < nt; ++j) load_tile(&tm_k, j);                  // pass 1
+      for (int j = 0; j < nt; ++j) {                                     // pass 2: K_0, K_1, V_0, K_2, V_1, ..., V_{nt-1}
+        load_tile(&tm_k, j);
+        if (j > 0) load_tile(&tm_v, j - 1);
       }
+      if (nt > 0) load_tile(&tm_v, nt - 1);
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
@@ -337,23 +342,32 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
       const uint32_t idesc_qk = umma_idesc_f16(kBf16 ? 1 : 0, kTcKV, 128);
       const uint32_t idesc_pv = umma_idesc_f16(kBf16 ? 1 : 0, 128, 128) | (1u << 16);   // B (= V) is MN-major
-      const uint32_t q_addr = smem_u32(q_s), p_addr = smem_u32(p_s), k_addr = smem_u32(k_s), v_addr = smem_u32(v_s);
+      const uint32_t q_addr = smem_u32(q_s), p_addr = smem_u32(p_s), ring_addr = smem_u32(ring);
+      int c = 0;                                          // ring tiles consumed so far (same sequence as the producer's)
+      auto take = [&]() {
+        const int sl = c % kTcStages;
+        mbar_wait(&kv_full[sl], ((uint32_t)(c / kTcStages)) & 1u);
+        ++c;
+        return sl;
+      };
       auto issue_pv = [&](int j) {                        // O += P(j) V(j)
         mbar_wait(&p_full, (uint32_t)j & 1u);
-        mbar_wait(&v_full, (uint32_t)j & 1u);
+        const int sl = take();
+        const uint32_t v_addr = ring_addr + (uint32_t)sl * 2 * kTcKHalf;
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kTcKV / 16; ++kk) {
           const uint64_t bdesc = umma_desc_mn_sw128(v_addr + (uint32_t)kk * 16 * 128, 2 * kTcKHalf / 2, 1024);
           umma_f16(tmem_base + 128, umma_desc_k_sw128(p_addr + (uint32_t)kk * 32), bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         }
-        umma_commit(&v_empty);
+        umma_commit(&kv_empty[sl]);
         umma_commit(&p_free);
       };
       mbar_wait(&q_bar, 0);
       for (int i = 0; i < total; ++i) {
         const uint32_t sb = (uint32_t)i & 1u;
-        mbar_wait(&k_full, (uint32_t)i & 1u);
+        const int sl = take();
+        const uint32_t k_addr = ring_addr + (uint32_t)sl * 2 * kTcKHalf;
         if (i >= 2) mbar_wait(&s_free[sb], (uint32_t)((i - 2) >> 1) & 1u);     // softmax warps finished reading S[sb]
         tc_fence_after();
 #pragma unroll
@@ -364,7 +378,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
                    kk > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[sb]);
-        umma_commit(&k_empty);
+        umma_commit(&kv_empty[sl]);
         if (i > nt) issue_pv(i - 1 - nt);                 // P.V of the previous pass-2 tile, behind this tile's QK^T
       }
       if (nt > 0) issue_pv(nt - 1);
