@@ -94,6 +94,9 @@ def measure_attention(model, st, batch, ctx_len, prompt_len, hbm_peak, timer=_ev
                       "bound": "tensor", "us_per_launch": us, "causal_flops": flops, "achieved_tflops": flops / (us * 1e-6) / 1e12,
                       "frac": flops / (us * 1e-6) / 1e12 / peak, "peak_tflops": peak, "peak_source": src, "tokens": T,
                       "tensor_pipe_active_pct_ncu": None}
+    # ---- the same prefill shape through the attention kernels INSTALLED on the box ("the kernel to beat"): a stated
+    # comparison only -- library code, never on the product path.  Each candidate is optional (import / arch support may be missing).
+    out["prefill"]["vs_installed"] = installed_attention(q, k, v, batch, prompt_len, nh, nkv, d, scale, flops, timer)
     try:       # tensor-pipe utilisation of the same kernel from the committed `ncu --set full` capture (a profiler number, never a timing)
         cap = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
         out["prefill"]["tensor_pipe_active_pct_ncu"] = float(cap["prefill_attention_tcgen05_b32x576"][0]["tensor_pipe_active_pct"])
@@ -102,6 +105,45 @@ def measure_attention(model, st, batch, ctx_len, prompt_len, hbm_peak, timer=_ev
     except Exception:
         pass
     return out
+
+
+
+def installed_attention(q, k, v, batch, seqlen, nh, nkv, d, scale, flops, timer):
+    """Causal GQA prefill attention of the benchmark shape through the library kernels present in the image -- torch SDPA (its
+    flash / cuDNN back ends) and flash_attn -- timed like our kernel (CUDA events, 8 calls after a warm-up).  Returns
+    {name: {"us", "tflops"} | {"error"}}; a reference point for `attention.prefill`, never part of the product path."""
+    res = {}
+    T = batch * seqlen
+    q4 = q.view(batch, seqlen, nh, d)
+    k4 = k.view(batch, seqlen, nkv, d)
+    v4 = v.view(batch, seqlen, nkv, d)
+
+    def run(name, fn):
+        try:
+            fn()
+            torch.cuda.synchronize()
+            us = timer(lambda i: fn(), 8)
+            res[name] = {"us": us, "tflops": flops / (us * 1e-6) / 1e12}
+        except Exception as e:  # noqa: BLE001
+            res[name] = {"error": repr(e)[:160]}
+
+    try:
+        import torch.nn.functional as F
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        qt, kt, vt = q4.transpose(1, 2), k4.transpose(1, 2), v4.transpose(1, 2)
+        for nm, be in (("torch_sdpa_flash", SDPBackend.FLASH_ATTENTION), ("torch_sdpa_cudnn", SDPBackend.CUDNN_ATTENTION)):
+            def f(be=be):
+                with sdpa_kernel(be):
+                    return F.scaled_dot_product_attention(qt, kt, vt, is_causal=True, scale=scale, enable_gqa=True)
+            run(nm, f)
+    except Exception as e:  # noqa: BLE001
+        res["torch_sdpa"] = {"error": repr(e)[:160]}
+    try:
+        from flash_attn import flash_attn_func
+        run("flash_attn_2", lambda: flash_attn_func(q4, k4, v4, causal=True, softmax_scale=scale))
+    except Exception as e:  # noqa: BLE001
+        res["flash_attn_2"] = {"error": repr(e)[:160]}
+    return res
 
 
 def make_series(i, k, length=SERIES_LEN):

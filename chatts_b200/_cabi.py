@@ -30,6 +30,7 @@ SYMBOLS = [
     "cts_lora_pack",
     "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step", "cts_ts_encode", "cts_gemm_decode_fused",
     "cts_peer_ll_region_bytes", "cts_peer_allreduce_ll", "cts_trace_enable", "cts_ts_encode_fused_ok", "cts_ts_encode_fused",
+    "cts_rep_penalty_mark", "cts_rep_penalty_apply",
 ]
 FUSED_RESIDUAL, FUSED_SWIGLU, FUSED_QKV_ROPE = 0, 1, 2
 PACK_DESC_LONGS = 12
@@ -141,6 +142,8 @@ def load_library():
     lib.cts_peer_allreduce_ll.argtypes = [vp, vp, i, vp, ll, vp, i, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
     lib.cts_peer_allreduce_ll.restype = i
     lib.cts_trace_enable.argtypes = [vp, vp]
+    lib.cts_rep_penalty_mark.argtypes = [vp, vp, vp, i, vp, i, ll, vp]
+    lib.cts_rep_penalty_apply.argtypes = [vp, vp, ll, ll, i, vp, i, f, i, vp]
     lib.cts_ts_encode_fused_ok.argtypes = [C.POINTER(TsEncodeArgs)]
     lib.cts_ts_encode_fused.argtypes = [vp, C.POINTER(TsEncodeArgs), vp]
     lib.cts_decode_chain.argtypes = [vp, C.POINTER(ChainArgs), vp]
@@ -492,6 +495,14 @@ class Context:
                                               _p(positions), _p(seq_lens), _p(slot_map), _p(page_table),
                                               page_table.shape[1] if page_table is not None else 0, page_size,
                                               dtype_code(logits.dtype), _stream()))
+
+    def rep_penalty_mark(self, tokens, rows, seen, vocab):
+        """Set the bits of (row, token) pairs in seen [B, words]; rows None: pair i belongs to row i."""
+        self._chk(self.lib.cts_rep_penalty_mark(self.h, _p(tokens), _p(rows), tokens.numel(), _p(seen), seen.shape[1], vocab, _stream()))
+
+    def rep_penalty_apply(self, logits, batch, seen, penalty):
+        self._chk(self.lib.cts_rep_penalty_apply(self.h, _p(logits), logits.shape[-1], logits.stride(0), batch, _p(seen), seen.shape[1],
+                                                 float(penalty), dtype_code(logits.dtype), _stream()))
 
     # ------------------------------------------------------------------ A9: LoRA fine-tune step
     def attn_prefill_lse(self, q, k, v, cu_seqlens, batch, max_seqlen, nh, nkv, head_dim, scale, out, lse):

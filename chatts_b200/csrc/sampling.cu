@@ -225,3 +225,73 @@ extern "C" int cts_sample_advance(cts_ctx* ctx, const void* logits, long long vo
   }
   return CTS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Repetition penalty (transformers RepetitionPenaltyLogitsProcessor; the checkpoint's generation_config.json may set it): for every
+// token id that already occurs in the row's sequence -- prompt and generated part -- logit = logit / penalty if logit > 0 else
+// logit * penalty, applied ONCE however often the token occurred.  The occurrence set is a bit mask [batch, ceil(vocab / 32)]:
+//   cts_rep_penalty_mark  sets the bits of (row, token) pairs (the prompt once, then the new token of every step)
+//   cts_rep_penalty_apply rewrites the logits of the marked tokens in place, before the argmax / sampling kernel reads them.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void rep_mark_kernel(const int* __restrict__ tokens, const int* __restrict__ rows, int n, unsigned* __restrict__ seen,
+                                int words_per_row, long long vocab) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = tokens[i];
+  const int r = rows != nullptr ? rows[i] : i;
+  if (t < 0 || t >= vocab || r < 0) return;
+  atomicOr(&seen[(long long)r * words_per_row + (t >> 5)], 1u << (t & 31));
+}
+
+template <typename T>
+__global__ void rep_apply_kernel(T* __restrict__ logits, long long vocab, long long ld, const unsigned* __restrict__ seen,
+                                 int words_per_row, float penalty) {
+  pdl_trigger();
+  pdl_wait();
+  const long long b = blockIdx.y;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words_per_row) return;
+  unsigned bits = seen[b * words_per_row + w];
+  while (bits) {
+    const int j = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const long long t = (long long)w * 32 + j;
+    if (t < vocab) {
+      const float v = DT<T>::to_f(logits[b * ld + t]);
+      logits[b * ld + t] = DT<T>::from_f(v > 0.f ? v / penalty : v * penalty);      // the processor works in the logits' dtype
+    }
+  }
+}
+}  // namespace
+
+extern "C" int cts_rep_penalty_mark(cts_ctx* ctx, const int* tokens, const int* rows, int n, unsigned* seen, int words_per_row,
+                                    long long vocab, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, n >= 0 && words_per_row > 0 && vocab > 0 && vocab <= 32LL * words_per_row, "n / words_per_row / vocab");
+  if (n == 0) return CTS_OK;
+  CTS_CHECK_ARG(ctx, tokens != nullptr && seen != nullptr, "null tokens / seen");
+  CTS_CUDA(ctx, launch_pdl(rep_mark_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 1, tokens, rows, n, seen,
+                           words_per_row, vocab));
+  return CTS_OK;
+}
+
+extern "C" int cts_rep_penalty_apply(cts_ctx* ctx, void* logits, long long vocab, long long ld, int batch, const unsigned* seen,
+                                     int words_per_row, float penalty, int dtype, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, batch >= 0 && batch <= 65535 && vocab > 0 && ld >= vocab && words_per_row > 0 && vocab <= 32LL * words_per_row, "shape");
+  CTS_CHECK_ARG(ctx, penalty > 0.f, "penalty must be > 0");
+  CTS_CHECK_ARG(ctx, dtype == CTS_BF16 || dtype == CTS_F16, "dtype");
+  if (batch == 0) return CTS_OK;
+  CTS_CHECK_ARG(ctx, logits != nullptr && seen != nullptr, "null logits / seen");
+  dim3 grid((unsigned)((words_per_row + 255) / 256), (unsigned)batch);
+  if (dtype == CTS_BF16)
+    CTS_CUDA(ctx, launch_pdl(rep_apply_kernel<__nv_bfloat16>, grid, dim3(256), 0, (cudaStream_t)stream, 1, (__nv_bfloat16*)logits, vocab, ld, seen,
+                             words_per_row, penalty));
+  else
+    CTS_CUDA(ctx, launch_pdl(rep_apply_kernel<__half>, grid, dim3(256), 0, (cudaStream_t)stream, 1, (__half*)logits, vocab, ld, seen, words_per_row,
+                             penalty));
+  return CTS_OK;
+}

@@ -195,6 +195,7 @@ ts_encoder_fused_kernel(const __grid_constant__ TsMaps maps, const TsFusedParams
     }
   }
   grid_barrier();
+  if (threadIdx.x == 0) CTS_TRACE(CTS_TK_OTHER, 4);       // rows assembled, layer 0 may start
 
   uint32_t acc_uses = 0;                                    // completed accumulator phases of THIS CTA (layers with nkb > 0)
   int it_c = 0;                                             // consumer (MMA) iteration counter, mirrors it_p
@@ -219,6 +220,7 @@ ts_encoder_fused_kernel(const __grid_constant__ TsMaps maps, const TsFusedParams
         }
         it_p += nkb;
         pre = 0;
+        CTS_TRACE(CTS_TK_OTHER, 5);                         // this layer's last load requested
       }
     } else if (warp == 1) {
       // ------------------------------ MMA issuer ------------------------------
@@ -247,6 +249,7 @@ ts_encoder_fused_kernel(const __grid_constant__ TsMaps maps, const TsFusedParams
         mbar_wait(&acc_bar, acc_uses & 1u);
         tc_fence_after();
       }
+      if (threadIdx.x == 64) CTS_TRACE(CTS_TK_OTHER, 6);    // accumulator complete
       const int q = warp & 3;
       const int ft = q * 32 + lane;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -269,6 +272,7 @@ ts_encoder_fused_kernel(const __grid_constant__ TsMaps maps, const TsFusedParams
     if (nkb > 0) ++acc_uses;                                // CTA-uniform bookkeeping (every thread keeps its own copy)
     __syncthreads();
     cluster.sync();                                         // every split's tile is in its CTA's shared memory
+    if (threadIdx.x == 64) CTS_TRACE(CTS_TK_OTHER, 7);
 
     if (warp >= 2) {
       // ------------------------------ epilogue, part B: rows r = split, split + S, ...: reduce over DSMEM in split order, apply the tail ------------------------------
@@ -304,8 +308,10 @@ ts_encoder_fused_kernel(const __grid_constant__ TsMaps maps, const TsFusedParams
         }
       }
     }
+    if (threadIdx.x == 64) CTS_TRACE(CTS_TK_OTHER, 8);      // tail done
     __syncthreads();
     cluster.sync();                                         // nobody reuses its ring while a peer still reads the parked tile
+    if (threadIdx.x == 64) CTS_TRACE(CTS_TK_OTHER, 9);
     if (l + 1 < p.num_layers) {
       // the ring is idle and weights depend on nothing: request the next layer's first weight tiles BEFORE waiting for the grid
       int kb0n, nkbn;
@@ -315,6 +321,7 @@ ts_encoder_fused_kernel(const __grid_constant__ TsMaps maps, const TsFusedParams
         issue_weights(l + 1, kb0n, 0, pre);
       }
       grid_barrier();                                       // every row of this layer's output is written (and visible to TMA)
+      if (threadIdx.x == 0) CTS_TRACE(CTS_TK_OTHER, 4);
     }
   }
 

@@ -192,7 +192,8 @@ class ChatTSForCausalLM:
         gc = _os2.path.join(path, "generation_config.json") if _os2.path.isdir(path) else ""
         if gc and _os2.path.exists(gc):
             model.generation_defaults = {k: v for k, v in _json2.load(open(gc)).items()
-                                         if k in ("do_sample", "temperature", "top_p", "top_k", "eos_token_id", "pad_token_id", "max_new_tokens")}
+                                         if k in ("do_sample", "temperature", "top_p", "top_k", "eos_token_id", "pad_token_id", "max_new_tokens",
+                                                  "repetition_penalty")}
         return model
 
     # ------------------------------------------------------------------------------------------ LoRA
@@ -664,7 +665,7 @@ class ChatTSForCausalLM:
     @torch.no_grad()
     def generate(self, input_ids=None, attention_mask=None, timeseries=None, max_new_tokens=None, max_length=None,
                  do_sample=None, temperature=None, top_p=None, top_k=None, streamer=None, eos_token_id=None, pad_token_id=None,
-                 synced_gpus=False, sync_every=16, ignore_eos=False, seed=None, **_):
+                 synced_gpus=False, sync_every=16, ignore_eos=False, seed=None, repetition_penalty=None, **_):
         """model.generate(**processor_out, max_new_tokens=...) -> LongTensor [B, S + new] whose first S columns are
         the ORIGINAL (un-expanded) input ids (README.md:102-103)."""
         cfg, dev = self.config, self.device
@@ -681,6 +682,8 @@ class ChatTSForCausalLM:
                 pad_token_id = gd["pad_token_id"]
             if max_new_tokens is None and max_length is None and gd.get("max_new_tokens"):
                 max_new_tokens = gd["max_new_tokens"]
+            if repetition_penalty is None and gd.get("repetition_penalty") is not None:
+                repetition_penalty = gd["repetition_penalty"]
         ids_cpu, am_cpu, counts, lay = self._prepare_inputs(input_ids, attention_mask, timeseries)
         B, S = ids_cpu.shape
         if max_new_tokens is None:
@@ -726,11 +729,30 @@ class ChatTSForCausalLM:
                 else:
                     self._sample_advance(st, lg, step, temperature, top_p, gen, top_k)
 
-            if greedy:
-                self.ctx.greedy_advance(logits, B, st.out_tokens, st.step_ptr, st.cur_ids, st.positions, st.seq_lens, st.slot_map,
-                                        st.page_table, self.page_size)
-            else:
-                sample(logits, 0)
+            # repetition penalty (transformers RepetitionPenaltyLogitsProcessor, e.g. from generation_config.json): the ids that occur in
+            # a row -- prompt (the un-expanded input_ids, as HF sees them) and generated -- live in a device bit mask; every step's
+            # logits are rewritten by cts_rep_penalty_apply before the argmax / sampling kernel, the new token is marked after it
+            rep = float(repetition_penalty) if repetition_penalty not in (None, 1, 1.0) else None
+            seen = None
+            if rep is not None:
+                Vfull = self.config.vocab_size
+                seen = torch.zeros(B, (Vfull + 31) // 32, dtype=torch.int32, device=dev)
+                am = np.ones_like(ids_cpu) if am_cpu is None else am_cpu
+                rr, cc = np.nonzero(am)
+                self.ctx.rep_penalty_mark(torch.from_numpy(ids_cpu[rr, cc].astype(np.int32)).to(dev), torch.from_numpy(rr.astype(np.int32)).to(dev),
+                                          seen, Vfull)
+                self.ctx.rep_penalty_apply(logits, B, seen, rep)
+
+            def advance(lg, step):
+                if greedy:
+                    self.ctx.greedy_advance(lg, B, st.out_tokens, st.step_ptr, st.cur_ids, st.positions, st.seq_lens, st.slot_map,
+                                            st.page_table, self.page_size)
+                else:
+                    sample(lg, step)
+                if seen is not None:
+                    self.ctx.rep_penalty_mark(st.cur_ids, None, seen, self.config.vocab_size)
+
+            advance(logits, 0)
             done = np.zeros(B, dtype=bool)
             out = np.full((B, max_new_tokens), pad, dtype=np.int64)
             emitted = 0
@@ -751,11 +773,13 @@ class ChatTSForCausalLM:
                     if produced >= max_new_tokens or done.all():
                         break
                 with span("cts.decode_step"):
-                    if greedy:
+                    if greedy and seen is None:
                         self._decode_step(st, sample=True)
                     else:
                         self._decode_step(st, sample=False)
-                        sample(st.full_logits, produced)
+                        if seen is not None:
+                            self.ctx.rep_penalty_apply(st.full_logits, B, seen, rep)
+                        advance(st.full_logits, produced)
                 produced += 1
             if streamer is not None:
                 streamer.end()

@@ -29,6 +29,7 @@ class SamplingParams:
     n: int = 1                                        # completions per request (temperature > 0: independent seeds)
     ignore_eos: bool = False
     seed: int = None
+    repetition_penalty: float = 1.0                   # vLLM SamplingParams.repetition_penalty (prompt + generated tokens)
 
 
 @dataclass
@@ -160,7 +161,8 @@ class LLM:
             ids = self.model.generate(**enc, max_new_tokens=sp.max_tokens, do_sample=sp.temperature > 0,
                                       temperature=sp.temperature, top_p=sp.top_p, top_k=(sp.top_k if sp.top_k and sp.top_k > 0 else None),
                                       ignore_eos=sp.ignore_eos, seed=(None if sp.seed is None else sp.seed + i0),
-                                      eos_token_id=stop_ids, streamer=streamer)
+                                      eos_token_id=stop_ids, streamer=streamer,
+                                      repetition_penalty=(sp.repetition_penalty if sp.repetition_penalty not in (None, 1.0) else None))
             for b, req in enumerate(chunk):
                 # a row ends at ITS first stop id (the batch-wide tail after it is the pad fill of generate())
                 toks, fin = cut_at_stop(ids[b, S:].tolist(), stop_ids, sp.ignore_eos)

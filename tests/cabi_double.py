@@ -6,6 +6,7 @@ restated with plain torch ops in the same rounding discipline (fp32 accumulate, 
 It is injected by the `cabi_double` fixture (monkeypatch of `_cabi.get_context`); the package never imports it and has
 no CPU fallback of its own -- without the fixture `get_context()` raises when the CUDA library or the GPU is missing.
 """
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -284,6 +285,22 @@ class TorchDouble:
                 if sl is not None: sl[b] += 1
                 if slot is not None and pt is not None: slot[b] = pt[b, int(pos[b]) // page] * page + int(pos[b]) % page
         step_ptr[0] += 1
+
+    # ------------------------------------------------------------------ repetition penalty (csrc/sampling.cu)
+    def rep_penalty_mark(self, tokens, rows, seen, vocab):
+        tk = tokens.reshape(-1).tolist()
+        rw = rows.reshape(-1).tolist() if rows is not None else list(range(len(tk)))
+        u = seen.numpy().view(np.uint32)                     # same memory: bits set in place
+        for t, r in zip(tk, rw):
+            if 0 <= t < vocab and r >= 0:
+                u[r, t >> 5] |= np.uint32(1 << (t & 31))
+
+    def rep_penalty_apply(self, logits, batch, seen, penalty):
+        V = logits.shape[-1]
+        bits = seen[:batch].to(torch.int64) & 0xFFFFFFFF
+        mask = ((bits[:, :, None] >> torch.arange(32)[None, None, :]) & 1).reshape(batch, -1)[:, :V].bool()
+        lg = logits[:batch].float()
+        logits[:batch] = torch.where(mask, torch.where(lg > 0, lg / penalty, lg * penalty), lg).to(logits.dtype)
 
     # ------------------------------------------------------------------ host executors (csrc/decoder_step.cu)
     def rmsnorm(self, x, w, eps, out, t=None): self.reduce_residual_rmsnorm(None, 0, x, None, w, eps, out, t=t)

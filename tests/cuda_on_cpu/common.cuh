@@ -202,6 +202,8 @@ static inline int launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size
 
 // ---------------------------------------------------------------------------------------------- intrinsics
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline float atomicAdd(float* p, float v) {
   uint32_t* u = reinterpret_cast<uint32_t*>(p);

@@ -68,3 +68,30 @@ def test_sample_advance_is_reproducible_and_distributed_right():
     top = int(np.argmax(p))
     n = d.shape[0]
     assert abs((d == top).mean() - p[top]) < 4 * np.sqrt(p[top] * (1 - p[top]) / n) + 0.01
+
+
+@pytest.mark.parametrize("vocab,dtype", [(1000, torch.bfloat16), (151936, torch.float16), (1003, torch.bfloat16)])
+def test_repetition_penalty_kernels_match_the_statement(vocab, dtype):
+    """cts_rep_penalty_mark / _apply against tests/cabi_double.py (itself equal to transformers' RepetitionPenaltyLogitsProcessor,
+    tests/test_host_sampling.py): bit-exact logits, repeated tokens penalised once, rows independent."""
+    c, dbl = ctx(), TorchDouble()
+    g = torch.Generator().manual_seed(vocab)
+    B, W = 4, (vocab + 31) // 32
+    logits = (torch.randn(B, vocab, generator=g) * 4).to(dtype)
+    toks = torch.randint(0, vocab, (B * 40,), generator=g).to(torch.int32)
+    toks[:5] = toks[5]                                            # repeats
+    toks[7] = vocab - 1
+    rows = torch.arange(B).repeat_interleave(40).to(torch.int32)
+    seen_ref = torch.zeros(B, W, dtype=torch.int32)
+    dbl.rep_penalty_mark(toks, rows, seen_ref, vocab)
+    new = torch.randint(0, vocab, (B,), generator=g).to(torch.int32)
+    dbl.rep_penalty_mark(new, None, seen_ref, vocab)
+    want = logits.clone()
+    dbl.rep_penalty_apply(want, B, seen_ref, 1.25)
+    seen = torch.zeros(B, W, dtype=torch.int32, device="cuda")
+    c.rep_penalty_mark(toks.cuda(), rows.cuda(), seen, vocab)
+    c.rep_penalty_mark(new.cuda(), None, seen, vocab)
+    got = logits.clone().cuda()
+    c.rep_penalty_apply(got, B, seen, 1.25)
+    torch.cuda.synchronize()
+    assert torch.equal(seen.cpu(), seen_ref) and torch.equal(got.cpu(), want)

@@ -63,3 +63,43 @@ def test_generate_with_sampling_kernel(cabi_double):
     model.use_sample_kernel = False
     d = model.generate(**enc, seed=5, **kw)
     assert d.shape == a.shape
+
+
+def test_repetition_penalty_matches_transformers_processor(cabi_double):
+    """generate(repetition_penalty=...) == greedy decoding through transformers' RepetitionPenaltyLogitsProcessor on the same logits:
+    the double's apply/mark statement against the library class, then the generate() plumbing (prompt ids marked once, every new
+    token marked, the penalty applied before every argmax)."""
+    import numpy as np
+    from transformers import RepetitionPenaltyLogitsProcessor
+    from tests.cabi_double import TorchDouble
+    g = torch.Generator().manual_seed(3)
+    V, B = 1000, 3
+    logits = (torch.randn(B, V, generator=g) * 3).to(torch.bfloat16)
+    ids = torch.randint(0, V, (B, 17), generator=g)
+    want = RepetitionPenaltyLogitsProcessor(penalty=1.3)(ids, logits.clone().float()).to(torch.bfloat16)
+    dbl = TorchDouble()
+    seen = torch.zeros(B, (V + 31) // 32, dtype=torch.int32)
+    dbl.rep_penalty_mark(ids.reshape(-1).to(torch.int32), torch.arange(B).repeat_interleave(17).to(torch.int32), seen, V)
+    got = logits.clone()
+    dbl.rep_penalty_apply(got, B, seen, 1.3)
+    assert torch.equal(got, want)
+
+    from tests.test_host_model import _build, _series
+    cfg, sd, model, proc = _build(cabi_double)
+    enc = proc(text=["A <ts><ts/> ? " + "ab" * 6], timeseries=[_series()[0]], return_tensors="pt")
+    S = enc["input_ids"].shape[1]
+    plain = model.generate(**enc, max_new_tokens=12, ignore_eos=True)[0, S:].tolist()
+    pen = model.generate(**enc, max_new_tokens=12, ignore_eos=True, repetition_penalty=1.8)[0, S:].tolist()
+    assert model.generate(**enc, max_new_tokens=12, ignore_eos=True, repetition_penalty=1.0)[0, S:].tolist() == plain
+    # reference loop: the model's own next-token logits, penalised by the HF processor over (prompt + generated) before the argmax
+    proc_hf = RepetitionPenaltyLogitsProcessor(penalty=1.8)
+    hist = enc["input_ids"].clone()
+    ref = []
+    for _ in range(12):
+        run = model.generate(input_ids=hist, attention_mask=torch.ones_like(hist), timeseries=enc["timeseries"], max_new_tokens=1, ignore_eos=True)
+        # logits of this step: recompute through forward (same kernels) and penalise
+        lg = model.forward(hist, torch.ones_like(hist), enc["timeseries"]).logits[:, 0].float()
+        tok = int(proc_hf(hist, lg.clone()).to(torch.bfloat16).float().argmax(-1))
+        ref.append(tok)
+        hist = torch.cat([hist, torch.tensor([[tok]])], 1)
+    assert pen == ref and pen != plain

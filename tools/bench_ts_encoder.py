@@ -19,6 +19,7 @@ import bench  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batches", type=int, nargs="+", default=[1, 2, 32])
+    ap.add_argument("--trace", action="store_true")
     a = ap.parse_args()
     from chatts_b200 import ChatTSConfig
     from chatts_b200.ts_encoder import TimeSeriesEmbedding
@@ -64,6 +65,35 @@ def main():
             del gr
         out[f"b{nb}"] = res
     print(json.dumps(out))
+    if a.trace:
+        # per-phase timeline of ONE fused launch (csrc/trace.cuh marks: 1 wait released, 4 layer start (after a grid barrier), 5 last
+        # load requested, 6 accumulator complete, 7 cluster synchronised, 8 tail done, 9 second cluster sync, 3 exit)
+        import numpy as np
+        x = bench.make_batch(cfg, 1, seed=2)["timeseries"].to("cuda", torch.bfloat16)
+        counts = tse.patch_counts(x)
+        host = torch.stack([counts[1], counts[2]]).cpu()
+        tse.use_fused = True
+        tse.encode(x, counts=counts, host_counts=(host[0], host[1]))
+        torch.cuda.synchronize()
+        tse.ctx.trace_begin(1 << 18)
+        tse.encode(x, counts=counts, host_counts=(host[0], host[1]))
+        rec = tse.ctx.trace_end()
+        np.save(os.path.join(ROOT, "gpurun_out", "trace_ts_fused.npy"), rec)
+        tag = rec[:, 0].astype(np.uint64)
+        ph = ((tag >> np.uint64(52)) & np.uint64(0xf)).astype(int)
+        t = rec[:, 1].astype(np.int64)
+        t0 = t.min()
+        gz = int((tag[0] >> np.uint64(32)) & np.uint64(0xff))
+        print(f"fused launch traced: {rec.shape[0]} records, split {gz}, span {(t.max() - t0) / 1e3:.1f} us")
+        for code in (0, 1, 4, 5, 6, 7, 8, 9, 3):
+            tt = np.sort(t[ph == code]) - t0
+            if tt.size == 0:
+                continue
+            # the marks of one phase come in bursts (one per layer): show first / median / last of every burst
+            order = np.argsort(tt)
+            n_b = max(1, round(tt.size / max(1, (ph == 0).sum())))
+            chunks = np.array_split(tt, n_b) if tt.size >= n_b else [tt]
+            print(f"  phase {code}: " + " | ".join(f"{c[0] / 1e3:6.1f}..{np.median(c) / 1e3:6.1f}..{c[-1] / 1e3:6.1f}" for c in chunks))
 
 
 if __name__ == "__main__":
