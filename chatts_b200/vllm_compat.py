@@ -104,25 +104,121 @@ class RequestOutput:
     outputs: list
 
 
+def _free_port():
+    import socket
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        return so.getsockname()[1]
+
+
+def _tp_worker(rank, world, port, backend, factory, factory_kw):
+    """Body of a spawned tensor-parallel rank (rank >= 1): join the group, build the same engine on this rank's shard, then mirror
+    every call the driver (rank 0) broadcasts -- the ranks of a tensor-parallel model run the same program (SPMD)."""
+    import os
+    import torch.distributed as dist
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    else:
+        dist.init_process_group(backend, rank=rank, world_size=world)
+    engine = factory(**factory_kw)
+    while True:
+        box = [None]
+        dist.broadcast_object_list(box, src=0)
+        cmd = box[0]
+        if cmd[0] == "stop":
+            break
+        if cmd[0] == "generate":
+            engine._generate(cmd[1], cmd[2])
+    dist.destroy_process_group()
+
+
+def _make_llm(**kw):
+    return LLM(**kw)
+
+
 class LLM:
     def __init__(self, model=None, tokenizer=None, config=None, state_dict=None, tensor_parallel_size=1, dtype="bfloat16",
-                 max_model_len=2048, max_num_seqs=32, limit_mm_per_prompt=None, trust_remote_code=True, seed=1234, **kw):
-        if tensor_parallel_size != 1:
-            raise NotImplementedError("launch one process per GPU with torchrun for tensor parallelism (bench.py --gpus N)")
+                 max_model_len=2048, max_num_seqs=32, limit_mm_per_prompt=None, trust_remote_code=True, seed=1234,
+                 distributed_backend="nccl", **kw):
+        """tensor_parallel_size = k > 1 (every caller of the reference passes it: demo/demo_vllm.py:30, llm_utils.py:153-154):
+          * under torchrun / an initialised process group of k ranks the engine ATTACHES: every rank constructs the LLM and makes the
+            same generate() calls (rank r holds shard r);
+          * otherwise the constructor SPAWNS k - 1 worker processes (one per GPU, as vLLM's multiprocessing executor does,
+            README.md:141) that build their shards and mirror every generate() call of this process (rank 0) -- the model must then
+            be named by a path or by config + seed (a ChatTSForCausalLM instance cannot be sent to another process)."""
+        import os
+        self._tp_procs, self._tp_driver = [], False
+        tp = int(tensor_parallel_size or 1)
+        tp_kw = {}
+        if tp > 1:
+            import torch.distributed as dist
+            attach = dist.is_available() and dist.is_initialized()
+            if not attach and int(os.environ.get("WORLD_SIZE", "1")) == tp:          # torchrun started us: join its group
+                local = int(os.environ.get("LOCAL_RANK", "0"))
+                if distributed_backend == "nccl":
+                    torch.cuda.set_device(local)
+                    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+                else:
+                    dist.init_process_group(distributed_backend)
+                attach = True
+            if attach:
+                if dist.get_world_size() != tp:
+                    raise ValueError(f"tensor_parallel_size={tp} but the process group has {dist.get_world_size()} ranks")
+                tp_kw = dict(tp_rank=dist.get_rank(), tp_size=tp)
+            else:
+                if isinstance(model, ChatTSForCausalLM) or state_dict is not None:
+                    raise ValueError("spawning tensor-parallel ranks needs a model PATH or config + seed (launch with torchrun to pass "
+                                     "a constructed model or a state dict on every rank)")
+                import torch.multiprocessing as mp
+                port = _free_port()
+                child_kw = dict(model=model, tokenizer=tokenizer, config=config, tensor_parallel_size=tp, dtype=dtype, max_model_len=max_model_len,
+                                max_num_seqs=max_num_seqs, limit_mm_per_prompt=limit_mm_per_prompt, seed=seed,
+                                distributed_backend=distributed_backend, **kw)
+                ctx = mp.get_context("spawn")
+                for r in range(1, tp):
+                    pr = ctx.Process(target=_tp_worker, args=(r, tp, port, distributed_backend, _make_llm, child_kw), daemon=True)
+                    pr.start()
+                    self._tp_procs.append(pr)
+                os.environ.update(RANK="0", LOCAL_RANK="0", WORLD_SIZE=str(tp), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+                if distributed_backend == "nccl":
+                    torch.cuda.set_device(0)
+                    dist.init_process_group("nccl", rank=0, world_size=tp, device_id=torch.device("cuda:0"))
+                else:
+                    dist.init_process_group(distributed_backend, rank=0, world_size=tp)
+                self._tp_driver = True
+                tp_kw = dict(tp_rank=0, tp_size=tp)
         dt = torch.bfloat16 if str(dtype) in ("bfloat16", "torch.bfloat16") else torch.float16
         if isinstance(model, ChatTSForCausalLM):
             self.model = model
         elif isinstance(model, str):
-            self.model = ChatTSForCausalLM.from_pretrained(model, torch_dtype=dt, max_seq_len=max_model_len, max_batch=max_num_seqs)
+            self.model = ChatTSForCausalLM.from_pretrained(model, torch_dtype=dt, max_seq_len=max_model_len, max_batch=max_num_seqs, **tp_kw)
         else:
             cfg = config or ChatTSConfig.chatts_14b()
-            self.model = (ChatTSForCausalLM(cfg, state_dict, dtype=dt, max_seq_len=max_model_len, max_batch=max_num_seqs)
+            self.model = (ChatTSForCausalLM(cfg, state_dict, dtype=dt, max_seq_len=max_model_len, max_batch=max_num_seqs, **tp_kw)
                           if state_dict is not None else
-                          ChatTSForCausalLM.from_synthetic(cfg, seed=seed, dtype=dt, max_seq_len=max_model_len, max_batch=max_num_seqs))
+                          ChatTSForCausalLM.from_synthetic(cfg, seed=seed, dtype=dt, max_seq_len=max_model_len, max_batch=max_num_seqs, **tp_kw))
         cfg = self.model.config
         self.tokenizer = tokenizer or SimpleTokenizer(cfg.ts_token_start_index, cfg.pad_token_id, cfg.eos_token_id)
         self.processor = ChatTSProcessor(self.tokenizer, cfg, dtype=torch.float32)
         self.limit = (limit_mm_per_prompt or {}).get("timeseries", MAX_TS_PER_PROMPT)
+
+    def shutdown(self):
+        """Stop the spawned tensor-parallel workers (no-op otherwise)."""
+        if self._tp_driver:
+            import torch.distributed as dist
+            dist.broadcast_object_list([("stop",)], src=0)
+            for pr in self._tp_procs:
+                pr.join(timeout=30)
+            dist.destroy_process_group()
+            self._tp_driver, self._tp_procs = False, []
+
+    def __del__(self):
+        try:
+            self.shutdown()
+        except Exception:  # noqa: BLE001  (interpreter teardown)
+            pass
 
     def generate(self, inputs, sampling_params=None, use_tqdm=False, streamer=None):
         sp = sampling_params or SamplingParams()
@@ -139,6 +235,9 @@ class LLM:
         return self._generate(inputs, sp, streamer)
 
     def _generate(self, inputs, sp, streamer=None):
+        if self._tp_driver:                                  # the spawned ranks run the same call on their shards
+            import torch.distributed as dist
+            dist.broadcast_object_list([("generate", inputs, sp)], src=0)
         outs = []
         bs = self.model.max_batch
         stops = [sp.stop] if isinstance(sp.stop, str) else list(sp.stop or [])
