@@ -221,6 +221,14 @@ ts_encoder_fused_kernel(const __grid_constant__ TsMaps maps, const TsFusedParams
         it_p += nkb;
         pre = 0;
         CTS_TRACE(CTS_TK_OTHER, 5);                         // this layer's last load requested
+        // This CTA's stream of layer l is fully requested: pull ITS unit of layer l + 1 into L2 now (fire-and-forget), so HBM keeps
+        // streaming through the drain, the cluster barrier, the DSMEM tail and the grid barrier (~10 us per layer on the first B200
+        // timeline -- as long as a whole layer's 52 MB stream); a layer is 52 MB, the L2 126 MB, and nothing else streams meanwhile.
+        if (l + 1 < p.num_layers) {
+          int kb0n, nkbn;
+          unit(l + 1, kb0n, nkbn);
+          for (int i = 0; i < nkbn; ++i) tma_prefetch_l2_2d(&maps.w[l + 1], (kb0n + i) * kBK, f0);
+        }
       }
     } else if (warp == 1) {
       // ------------------------------ MMA issuer ------------------------------
@@ -276,52 +284,71 @@ ts_encoder_fused_kernel(const __grid_constant__ TsMaps maps, const TsFusedParams
 
     if (warp >= 2) {
       // ------------------------------ epilogue, part B: rows r = split, split + S, ...: reduce over DSMEM in split order, apply the tail ------------------------------
-      const int ft = (warp & 3) * 32 + lane;
-      const long long f = (long long)f0 + ft;
-      const bool f_ok = f < p.hidden;
+      // Work item = (one of this CTA's rows, 4 consecutive features): S 16-byte loads from the peers' parked tiles, issued for TWO items
+      // before the first add (the first B200 timeline showed a scalar, one-row-at-a-time tail costing 17 us per layer -- DSMEM round
+      // trips, not arithmetic), then bias + GELU on four values and ONE 8-byte store.
+      const int et = (int)threadIdx.x - 64;                  // 0..127
       const bool last = l + 1 == p.num_layers;
-      const float bias = (p.bias[l] != nullptr && f_ok) ? DT<T>::to_f(reinterpret_cast<const T*>(p.bias[l])[f]) : 0.f;
+      const T* bias_p = reinterpret_cast<const T*>(p.bias[l]);
       T* dst_act = reinterpret_cast<T*>(p.act[l & 1]);
-      constexpr int kGroup = 4;
-      for (int rb = split; rb < R; rb += kGroup * S) {
-        float accs[kGroup];
+      const int n_my = R > split ? (R - split + S - 1) / S : 0;
+      const int n_items = n_my * 32;
+      constexpr int kBatch = 2;
+      for (int it0 = et; it0 < n_items; it0 += 128 * kBatch) {
+        float4 acc[kBatch];
 #pragma unroll
-        for (int u = 0; u < kGroup; ++u) {
-          const int r2 = rb + u * S;
-          float a2 = 0.f;
-          if (r2 < R)
-            for (int s2 = 0; s2 < S; ++s2) a2 += *cluster.map_shared_rank(&part_s[r2 * kBM + ft], peer(s2));      // split order
-          accs[u] = a2;
+        for (int u = 0; u < kBatch; ++u) {
+          const int it = it0 + u * 128;
+          acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (it < n_items) {
+            const int r = split + S * (it >> 5), c4 = it & 31;
+            float4 v[8];
+#pragma unroll
+            for (int s2 = 0; s2 < 8; ++s2)
+              if (s2 < S) v[s2] = *reinterpret_cast<const float4*>(cluster.map_shared_rank(&part_s[r * kBM + c4 * 4], peer(s2)));
+#pragma unroll
+            for (int s2 = 0; s2 < 8; ++s2)                    // split order
+              if (s2 < S) { acc[u].x += v[s2].x; acc[u].y += v[s2].y; acc[u].z += v[s2].z; acc[u].w += v[s2].w; }
+          }
         }
 #pragma unroll
-        for (int u = 0; u < kGroup; ++u) {
-          const int r = rb + u * S;
-          if (r >= R || !f_ok) continue;
-          float v = accs[u] + bias;
+        for (int u = 0; u < kBatch; ++u) {
+          const int it = it0 + u * 128;
+          if (it >= n_items) continue;
+          const int r = split + S * (it >> 5), c4 = it & 31;
+          const long long f = (long long)f0 + c4 * 4;
+          if (f >= p.hidden) continue;                       // hidden % 8 == 0: a 4-feature chunk is entirely inside or outside
+          float o[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
+          if (bias_p != nullptr) {
+            const uint2 bv = *reinterpret_cast<const uint2*>(bias_p + f);
+            const T* bp = reinterpret_cast<const T*>(&bv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] += DT<T>::to_f(bp[e]);
+          }
+          T ov[4];
           if (!last) {
-            v = gelu_erf(rnd<T>(v));                        // nn.Linear output in the model dtype, exact-erf GELU on it (:87)
-            dst_act[(long long)r * p.hidden + f] = DT<T>::from_f(v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ov[e] = DT<T>::from_f(gelu_erf(rnd<T>(o[e])));      // Linear output in the model dtype, exact-erf GELU on it (:87)
+            *reinterpret_cast<uint2*>(dst_act + (long long)r * p.hidden + f) = *reinterpret_cast<const uint2*>(ov);
           } else {
-            const int dr = p.row_map != nullptr ? p.row_map[r] : r;       // the sp-mask scatter into the embedding sequence (:569-573)
-            if (dr >= 0) reinterpret_cast<T*>(p.out)[(long long)dr * p.out_ld + f] = DT<T>::from_f(v);
+            const int dr = p.row_map != nullptr ? p.row_map[r] : r;                        // the sp-mask scatter into the embedding sequence (:569-573)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ov[e] = DT<T>::from_f(o[e]);
+            if (dr >= 0) *reinterpret_cast<uint2*>(reinterpret_cast<T*>(p.out) + (long long)dr * p.out_ld + f) = *reinterpret_cast<const uint2*>(ov);
           }
         }
       }
     }
     if (threadIdx.x == 64) CTS_TRACE(CTS_TK_OTHER, 8);      // tail done
-    __syncthreads();
-    cluster.sync();                                         // nobody reuses its ring while a peer still reads the parked tile
-    if (threadIdx.x == 64) CTS_TRACE(CTS_TK_OTHER, 9);
     if (l + 1 < p.num_layers) {
-      // the ring is idle and weights depend on nothing: request the next layer's first weight tiles BEFORE waiting for the grid
-      int kb0n, nkbn;
-      unit(l + 1, kb0n, nkbn);
-      if (warp == 0 && lane == 0) {
-        pre = nkbn < stages ? nkbn : stages;
-        issue_weights(l + 1, kb0n, 0, pre);
-      }
-      grid_barrier();                                       // every row of this layer's output is written (and visible to TMA)
+      // The grid barrier doubles as the second cluster barrier: when it opens, every CTA has finished reading its peers' parked
+      // tiles (so the rings may be refilled) and every row of this layer's output is written and visible to TMA.
+      grid_barrier();
       if (threadIdx.x == 0) CTS_TRACE(CTS_TK_OTHER, 4);
+    } else {
+      __syncthreads();
+      cluster.sync();                                       // nobody leaves while a peer still reads its parked tile
+      if (threadIdx.x == 64) CTS_TRACE(CTS_TK_OTHER, 9);
     }
   }
 
@@ -379,6 +406,10 @@ int launch_ts_fused(cts_ctx* ctx, const cts_ts_encode_args* a, int* sync, cudaSt
   const size_t smem = (size_t)stages * kStage + 1024;
   auto kern = ts_encoder_fused_kernel<T, BN>;
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifndef CTS_HOST_SHIM
+  // without the maximum carve-out the driver places ONE 97 KB CTA per SM (first B200 run: 120 resident CTAs, split 3)
+  CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+#endif
   const int tiles = (int)cdiv_ll(a->hidden, kBM);
   // K splits per tile = cluster size: the largest S <= 8 for which ALL tiles' clusters are resident at once (the kernel synchronises
   // with grid barriers) -- asked of the driver for the real launch configuration (clusters must fit a GPC), not estimated
