@@ -30,7 +30,7 @@ SYMBOLS = [
     "cts_lora_pack",
     "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step", "cts_ts_encode", "cts_gemm_decode_fused",
     "cts_peer_ll_region_bytes", "cts_peer_allreduce_ll", "cts_trace_enable", "cts_ts_encode_fused_ok", "cts_ts_encode_fused",
-    "cts_rep_penalty_mark", "cts_rep_penalty_apply",
+    "cts_rep_penalty_mark", "cts_rep_penalty_apply", "cts_gemm_w4", "cts_gemm_w4_suggest_split",
 ]
 FUSED_RESIDUAL, FUSED_SWIGLU, FUSED_QKV_ROPE = 0, 1, 2
 PACK_DESC_LONGS = 12
@@ -89,6 +89,12 @@ class FusedGemmArgs(C.Structure):
                 [(k, C.c_int) for k in ("peer_rank", "peer_world", "peer_max_tokens", "peer_reserved")] + [("peer_region_bytes", C.c_longlong)])
 
 
+class GemmW4Args(C.Structure):
+    _fields_ = [("qw", C.c_void_p), ("scales", C.c_void_p), ("zeros", C.c_void_p), ("x", C.c_void_p), ("out", C.c_void_p),
+                ("n", C.c_longlong), ("k", C.c_longlong), ("t", C.c_longlong), ("x_ld", C.c_longlong),
+                ("group_size", C.c_int), ("split_k", C.c_int), ("dtype", C.c_int), ("reserved", C.c_int)]
+
+
 class TsEncodeArgs(C.Structure):
     _fields_ = ([("x", C.c_void_p)] + [(k, C.c_int) for k in ("dtype", "n_series", "row_len", "num_features", "patch_size", "mode")] +
                 [("pos_table", C.c_void_p)] + [(k, C.c_int) for k in ("emb_dim", "max_seq_len", "num_layers", "hidden", "in0")] +
@@ -142,6 +148,8 @@ def load_library():
     lib.cts_peer_allreduce_ll.argtypes = [vp, vp, i, vp, ll, vp, i, i, i, vp, vp, vp, f, vp, ll, ll, i, vp]
     lib.cts_peer_allreduce_ll.restype = i
     lib.cts_trace_enable.argtypes = [vp, vp]
+    lib.cts_gemm_w4.argtypes = [vp, C.POINTER(GemmW4Args), vp]
+    lib.cts_gemm_w4_suggest_split.argtypes = [vp, ll, ll]
     lib.cts_rep_penalty_mark.argtypes = [vp, vp, vp, i, vp, i, ll, vp]
     lib.cts_rep_penalty_apply.argtypes = [vp, vp, ll, ll, i, vp, i, f, i, vp]
     lib.cts_ts_encode_fused_ok.argtypes = [C.POINTER(TsEncodeArgs)]
@@ -307,6 +315,19 @@ class Context:
         a.tile_counters = tile_counters.data_ptr() if tile_counters is not None else None
         a.dtype, a.epilogue, a.split_k = dtype_code(x.dtype), epilogue, split_k
         self._chk(self.lib.cts_gemm(self.h, C.byref(a), _stream()))
+
+    def gemm_w4(self, x, qw, scales, zeros, group_size, out, split_k, t=None):
+        """fp32 split-K partials [S, T, N] of x[T, K] @ W^T with W = scales * (codes - zeros) dequantised in the operand path
+        (cts_gemm_w4; decode-sized T).  qw uint8 [N, K/2], scales [N, K/g] (x's dtype), zeros uint8 [N, K/g]."""
+        a = GemmW4Args()
+        a.qw, a.scales, a.zeros, a.x, a.out = qw.data_ptr(), scales.data_ptr(), zeros.data_ptr(), x.data_ptr(), out.data_ptr()
+        a.n, a.k = qw.shape[0], qw.shape[1] * 2
+        a.t = x.shape[0] if t is None else t
+        a.x_ld, a.group_size, a.split_k, a.dtype = x.stride(0), int(group_size), int(split_k), dtype_code(x.dtype)
+        self._chk(self.lib.cts_gemm_w4(self.h, C.byref(a), _stream()))
+
+    def gemm_w4_suggest_split(self, n, k):
+        return int(self.lib.cts_gemm_w4_suggest_split(self.h, n, k))
 
     # ------------------------------------------------------------------ fused split-K tails
     def reduce_bias_act(self, partial, split_k, t, n, bias, act, out, row_map=None):

@@ -147,9 +147,10 @@ extern "C" int cts_trace_set_attention(unsigned long long* buf);
 extern "C" int cts_trace_set_allreduce_ll(unsigned long long* buf);
 extern "C" int cts_trace_set_fused(unsigned long long* buf);
 extern "C" int cts_trace_set_ts_fused(unsigned long long* buf);
+extern "C" int cts_trace_set_w4(unsigned long long* buf);
 extern "C" int cts_trace_enable(cts_ctx* ctx, unsigned long long* buf) {
   if (!ctx) return CTS_ERR_BAD_ARG;
-  if (cts_trace_set_gemm(buf) || cts_trace_set_elementwise(buf) || cts_trace_set_attention(buf) || cts_trace_set_allreduce_ll(buf) || cts_trace_set_fused(buf) || cts_trace_set_ts_fused(buf))
+  if (cts_trace_set_gemm(buf) || cts_trace_set_elementwise(buf) || cts_trace_set_attention(buf) || cts_trace_set_allreduce_ll(buf) || cts_trace_set_fused(buf) || cts_trace_set_ts_fused(buf) || cts_trace_set_w4(buf))
     return cts_set_error(ctx, CTS_ERR_CUDA, "cts_trace_enable: cudaMemcpyToSymbol failed");
   return CTS_OK;
 }

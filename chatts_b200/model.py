@@ -107,6 +107,7 @@ class ChatTSForCausalLM:
         # (b=32: 6.59 ms without, 6.83 / 7.00 / 7.08 ms with 24 / 48 / 80 MB) -- the prefetched lines do not survive the current
         # GEMM's stream through L2, so the bytes are read twice.  CTS_NEXT_PREFETCH_MB=<n> turns it on for experiments.
         self.next_prefetch_bytes = int(float(_os.environ.get("CTS_NEXT_PREFETCH_MB", "0")) * (1 << 20))
+        self.w4 = None               # W4A16 decode weights (csrc/gemm_w4.cu): set by attach_w4 / quantize_w4_synthetic / from_pretrained(GPTQ)
         self._load(state_dict)
         # every position the page table can address has a row in the rotary tables (max_pages * page_size >= max_seq_len), capped by
         # the model's max_position_embeddings; _alloc_pages rejects sequences beyond it (no silent out-of-bounds cos/sin read)
@@ -177,14 +178,22 @@ class ChatTSForCausalLM:
               torch.bfloat16: torch.bfloat16, None: getattr(torch, cfg.torch_dtype, torch.bfloat16)}[torch_dtype]
         dev = device if device is not None else (f"cuda:{device_map}" if isinstance(device_map, int) else (device_map or "cuda"))
         sd = load_checkpoint(path, device="cpu")
-        if any(k.endswith(".qweight") for k in sd):                # GPTQ-Int4 checkpoint: dequantise at load time (weights.py)
+        w4_packed, w4_gs = None, 0
+        if any(k.endswith(".qweight") for k in sd):                # GPTQ-Int4 checkpoint (README.md:52,262-263)
             import json as _json
             import os as _os
-            from .weights import dequantize_gptq
+            from .weights import dequantize_gptq, gptq_w4_pack
             cj = _os.path.join(path, "config.json") if _os.path.isdir(path) else path
             qc = _json.load(open(cj)).get("quantization_config", {})
-            sd = dequantize_gptq(sd, qc, dtype=dt)
+            # decode streams the 4-bit codes (csrc/gemm_w4.cu); prefill runs on a dequantised copy holding the same values (the scales
+            # rounded to the model dtype, which is what the kernel multiplies with).  Act-order checkpoints, tensor parallelism and
+            # CTS_W4=0 keep the dequantised weights only.
+            if _os.environ.get("CTS_W4", "1") != "0" and kw.get("tp_size", 1) == 1:
+                w4_packed, w4_gs = gptq_w4_pack(sd, qc, dtype=dt)
+            sd = dequantize_gptq(sd, qc, dtype=dt, scale_dtype=dt if w4_packed is not None else None)
         model = cls(cfg, sd, device=dev, dtype=dt, **kw)
+        if w4_packed is not None:
+            model.attach_w4(w4_packed, w4_gs)
         # generation_config.json: the defaults HF's generate() applies when the caller passes none (README.md:102 calls
         # model.generate(**inputs, max_new_tokens=300) with no sampling arguments)
         import json as _json2
@@ -257,6 +266,73 @@ class ChatTSForCausalLM:
             merged += 1
         return merged          # in-place update: captured decode graphs keep reading the same (now merged) buffers
 
+    # ------------------------------------------------------------------------------------------ W4A16 (GPTQ-Int4, README.md:52,262-263)
+    def attach_w4(self, packed, group_size):
+        """Switch the DECODE step to the 4-bit weight stream.  ``packed``: {HF linear name (e.g. 'model.layers.3.mlp.up_proj'):
+        (qw uint8 [out, in/2], scales [out, in/g], zeros uint8 [out, in/g])} in the layout of weights.py:repack_gptq_w4, for all
+        seven projections of every layer.  The dense weights stay (prefill and every T > 32 step use them): they must hold the SAME
+        values, i.e. weights.py:dequantize_gptq(..., scale_dtype=model dtype) -- 180 GB of HBM keep both copies.  Fused operands
+        are assembled exactly like the dense ones: q|k|v stacked, gate/up interleaved per 64 rows.  Single GPU (a tensor-parallel
+        row split would cut groups: down_proj's 13824 / 8 = 1728 inputs are not a multiple of the group size)."""
+        if self.tp_size != 1:
+            raise ValueError("W4A16 decode weights are single-GPU (tensor parallelism uses the dequantised weights)")
+        dev = self.device
+        gs = int(group_size)
+        w4 = dict(group_size=gs, qkv=[], o=[], gu=[], d=[])
+
+        def get(name):
+            qw, sc, zp = packed[name]
+            return qw.to(dev).contiguous(), sc.to(dev, self.dtype).contiguous(), zp.to(dev).contiguous()
+
+        def il(a, b):                     # gate/up interleaved per 64 output rows, as _load does for the dense weight
+            return torch.stack([a.view(-1, 64, a.shape[1]), b.view(-1, 64, b.shape[1])], 1).reshape(2 * a.shape[0], a.shape[1]).contiguous()
+
+        for l in range(self.L):
+            p = f"model.layers.{l}."
+            q, k, v = (get(p + f"self_attn.{n}_proj") for n in "qkv")
+            w4["qkv"].append(tuple(torch.cat([a, b, c], 0).contiguous() for a, b, c in zip(q, k, v)))
+            w4["o"].append(get(p + "self_attn.o_proj"))
+            g, u = get(p + "mlp.gate_proj"), get(p + "mlp.up_proj")
+            w4["gu"].append(tuple(il(a, b) for a, b in zip(g, u)))
+            w4["d"].append(get(p + "mlp.down_proj"))
+        c = self.ctx
+        w4["splits"] = dict(qkv=c.gemm_w4_suggest_split(self.wqkv[0].shape[0], self.H), o=c.gemm_w4_suggest_split(self.H, self.nh * self.d),
+                            gu=c.gemm_w4_suggest_split(2 * self.I, self.H), d=c.gemm_w4_suggest_split(self.H, self.I))
+        self.w4 = w4
+        self._steps = {}                  # decode states (workspaces, captured graphs) are rebuilt for the new launches
+        return self
+
+    def quantize_w4_synthetic(self, group_size=128, seed=7):
+        """Benchmark / test helper (no GPTQ checkpoint exists offline): draw random 4-bit codes, scales and zero points at the model's
+        shapes, REPLACE the dense weights by their dequantised values and attach the packed copy -- a W4A16 model whose prefill and
+        decode paths see the same weights."""
+        from .weights import dequantize_w4, W4_NIBBLE_OF_K  # noqa: F401
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        packed = {}
+
+        def make(n_out, n_in):
+            qw = torch.randint(0, 256, (n_out, n_in // 2), generator=g, device=self.device, dtype=torch.uint8)
+            sc = ((torch.rand(n_out, n_in // group_size, generator=g, device=self.device) * 0.5 + 0.75) * (0.02 * 3.46 / 7.5)).to(self.dtype)
+            zp = torch.randint(7, 10, (n_out, n_in // group_size), generator=g, device=self.device, dtype=torch.uint8)
+            return qw, sc, zp
+
+        d, H, I = self.d, self.H, self.I
+        for l in range(self.L):
+            p = f"model.layers.{l}."
+            parts = {}
+            for name, (n_out, n_in) in (("self_attn.q_proj", (self.nh * d, H)), ("self_attn.k_proj", (self.nkv * d, H)), ("self_attn.v_proj", (self.nkv * d, H)),
+                                        ("self_attn.o_proj", (H, self.nh * d)), ("mlp.gate_proj", (I, H)), ("mlp.up_proj", (I, H)), ("mlp.down_proj", (H, I))):
+                t = make(n_out, n_in)
+                packed[p + name] = t
+                parts[name] = dequantize_w4(*t, group_size)
+            self.wqkv[l].copy_(torch.cat([parts["self_attn.q_proj"], parts["self_attn.k_proj"], parts["self_attn.v_proj"]], 0))
+            self.wo[l].copy_(parts["self_attn.o_proj"])
+            gp, up = parts["mlp.gate_proj"], parts["mlp.up_proj"]
+            self.wgu[l].copy_(torch.stack([gp.view(-1, 64, H), up.view(-1, 64, H)], 1).reshape(2 * I, H))
+            self.wd[l].copy_(parts["mlp.down_proj"])
+            del parts
+        return self.attach_w4(packed, group_size)
+
     # ------------------------------------------------------------------------------------------ layers
     def _splits(self, T):
         c = self.ctx
@@ -281,6 +357,18 @@ class ChatTSForCausalLM:
         # decode-sized steps: every weight-streaming GEMM names the weight its successor will stream, and prefetches the head of it
         # into L2 once its own last tile is requested (cts_gemm_args.next_*): HBM keeps streaming through the kernel boundaries
         nb = self.next_prefetch_bytes if (T <= 32 and st.k_lin is None) else 0
+        # W4A16: decode-sized steps stream the 4-bit codes (every projection through the split-K partial path with the W4 split factors)
+        w4 = self.w4 if (self.w4 is not None and T <= 32 and st.k_lin is None and not fused) else None
+        if w4 is not None:
+            sp = w4["splits"]
+
+        def proj(kind, l, x, w, split, **kw):
+            """fp32 split-K partials of one projection into st.ws: from the packed 4-bit weight when attached, else from the dense one."""
+            if w4 is not None:
+                qw, sc, zp = w4[kind][l]
+                c.gemm_w4(x, qw, sc, zp, w4["group_size"], st.ws, split, t=T)
+            else:
+                c.gemm(x, w, st.ws, epilogue=EPI_PARTIAL_F32, split_k=split, t=T, **kw)
 
         def nxt(w, split):
             return dict(next_w=w, next_split=split, next_bytes=nb) if nb > 0 else {}
@@ -337,8 +425,8 @@ class ChatTSForCausalLM:
                     c.reduce_residual_rmsnorm(None, 0, st.h, None, nw, eps, st.xn, t=T)
                 continue
             # ---- QKV projection + bias + RoPE + KV write
-            if sp["qkv"] > 1:
-                c.gemm(st.xn, self.wqkv[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["qkv"], t=T, **nxt(self.wo[l], sp["o"]))
+            if sp["qkv"] > 1 or w4 is not None:
+                proj("qkv", l, st.xn, self.wqkv[l], sp["qkv"], **nxt(self.wo[l], sp["o"]))
                 c.qkv_rope_cache(st.ws, True, sp["qkv"], self.bqkv[l], st.positions, self.cos, self.sin, st.slot_map, st.q, kc, vc,
                                  st.k_lin, st.v_lin, T, self.nh, self.nkv, self.d, self.page_size, self.qn[l], self.kn[l], eps)
             else:
@@ -349,8 +437,8 @@ class ChatTSForCausalLM:
             # ---- o_proj + residual + post-attention RMSNorm
             if self.tp_size > 1:
                 self._tp_row_parallel(st, T, st.ao, self.wo[l], self.ln2[l], 0, sp["o"], nxt(self.wgu[l], sp["gu"]))
-            elif sp["o"] > 1:
-                c.gemm(st.ao, self.wo[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["o"], t=T, **nxt(self.wgu[l], sp["gu"]))
+            elif sp["o"] > 1 or w4 is not None:
+                proj("o", l, st.ao, self.wo[l], sp["o"], **nxt(self.wgu[l], sp["gu"]))
                 c.reduce_residual_rmsnorm(st.ws, sp["o"], st.h, st.h, self.ln2[l], eps, st.xn, t=T)
             else:
                 c.gemm(st.ao, self.wo[l], st.h, residual=st.h, epilogue=EPI_RESIDUAL, t=T, **nxt(self.wgu[l], sp["gu"]))
@@ -359,15 +447,15 @@ class ChatTSForCausalLM:
             if T > 128:
                 c.gemm(st.xn, self.wgu[l], st.act, epilogue=EPI_SWIGLU_IL, t=T)          # persistent, SwiGLU fused in the tile
             else:
-                c.gemm(st.xn, self.wgu[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["gu"], t=T, **nxt(self.wd[l], sp["d"]))
+                proj("gu", l, st.xn, self.wgu[l], sp["gu"], **nxt(self.wd[l], sp["d"]))
                 c.reduce_swiglu(st.ws, sp["gu"], T, I, st.act, interleaved=True)
             # ---- down_proj + residual + next layer's input RMSNorm (or the final norm)
             nw = self.ln1[l + 1] if l + 1 < self.L else self.final_norm
             after = nxt(self.wqkv[l + 1], sp["qkv"]) if l + 1 < self.L else nxt(self.lm_head, 1)
             if self.tp_size > 1:
                 self._tp_row_parallel(st, T, st.act, self.wd[l], nw, 1, sp["d"], after)
-            elif sp["d"] > 1:
-                c.gemm(st.act, self.wd[l], st.ws, epilogue=EPI_PARTIAL_F32, split_k=sp["d"], t=T, **after)
+            elif sp["d"] > 1 or w4 is not None:
+                proj("d", l, st.act, self.wd[l], sp["d"], **after)
                 c.reduce_residual_rmsnorm(st.ws, sp["d"], st.h, st.h, nw, eps, st.xn, t=T)
             else:
                 c.gemm(st.act, self.wd[l], st.h, residual=st.h, epilogue=EPI_RESIDUAL, t=T, **after)
@@ -404,6 +492,9 @@ class ChatTSForCausalLM:
         st.act = torch.empty(T, self.I, device=dev, dtype=dt)
         st.qkv = torch.empty(T, self.wqkv[0].shape[0], device=dev, dtype=dt) if st.splits["qkv"] == 1 else None
         ws_n = max(self._ws_floats(T, st.splits), T * self.H)
+        if decode and self.w4 is not None:            # W4A16 decode: every projection through the partial path with the W4 split factors
+            sp = self.w4["splits"]
+            ws_n = max(ws_n, sp["qkv"] * T * self.wqkv[0].shape[0], sp["o"] * T * self.H, sp["gu"] * T * 2 * self.I, sp["d"] * T * self.H)
         if decode and self.use_native_step:          # cts_decoder_step always takes the split-K partial path (also at factor 1)
             sp = st.splits
             ws_n = max(ws_n, sp["qkv"] * T * self.wqkv[0].shape[0], sp["o"] * T * self.H, sp["gu"] * T * 2 * self.I, sp["d"] * T * self.H)
@@ -570,10 +661,10 @@ class ChatTSForCausalLM:
         return st
 
     def _native_ok(self, B):
-        return self.use_native_step and self.tp_size == 1 and B <= 128 and not self._chain_ok(B)
+        return self.use_native_step and self.tp_size == 1 and B <= 128 and not self._chain_ok(B) and self.w4 is None
 
     def _chain_ok(self, B):
-        return (self.use_chain and self.tp_size == 1 and B <= 32 and self.H % 64 == 0 and self.H // 64 <= 192 and self.I % 64 == 0)
+        return (self.w4 is None and self.use_chain and self.tp_size == 1 and B <= 32 and self.H % 64 == 0 and self.H // 64 <= 192 and self.I % 64 == 0)
 
     def _decode_layers_chain(self, st, attend):
         """Decode layers with the persistent chain kernel: per layer ONE attention launch + ONE chain launch

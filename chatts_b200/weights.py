@@ -116,16 +116,54 @@ def _unpack_nibbles(t, axis):
     return v.reshape(t.shape[0], t.shape[1] * 8)
 
 
-def dequantize_gptq_linear(qweight, qzeros, scales, g_idx=None, group_size=128, zero_offset=1, dtype=torch.bfloat16):
+def dequantize_gptq_linear(qweight, qzeros, scales, g_idx=None, group_size=128, zero_offset=1, dtype=torch.bfloat16, scale_dtype=None):
+    """scale_dtype: round the fp16 scales to this dtype first -- what the W4A16 decode kernel multiplies with (csrc/gemm_w4.cu), so that
+    the dequantised copy the prefill uses and the on-the-fly dequantisation of the decode step are the same numbers (fp16: no-op)."""
     q = _unpack_nibbles(qweight.to(torch.int32), 0)                       # [in, out]
     z = _unpack_nibbles(qzeros.to(torch.int32), 1)[:, : scales.shape[1]] + int(zero_offset)   # [groups, out]
     n_in = q.shape[0]
     g = (torch.arange(n_in, device=q.device) // int(group_size)) if g_idx is None else g_idx.to(torch.long)
-    w = scales.to(torch.float32)[g] * (q - z[g]).to(torch.float32)        # [in, out]
+    sc = scales if scale_dtype is None else scales.to(scale_dtype)
+    w = sc.to(torch.float32)[g] * (q - z[g]).to(torch.float32)            # [in, out]
     return w.t().contiguous().to(dtype)
 
 
-def dequantize_gptq(sd, quant_cfg=None, dtype=torch.bfloat16):
+# nibble position of K element j (0..7) inside a 32-bit word of the B200 layout: ((w >> 4 i) & 0x000F000F) yields the pair
+# (k_2i, k_2i+1) in the low / high half-word, i.e. one 16-bit-pair per shift -- the form the magic-number int4 -> bf16/fp16
+# conversion wants (csrc/gemm_w4.cu)
+W4_NIBBLE_OF_K = (0, 4, 1, 5, 2, 6, 3, 7)
+
+
+def repack_gptq_w4(qweight, qzeros, scales, group_size=128, zero_offset=1, dtype=torch.bfloat16):
+    """GPTQ tensors of one Linear -> the K-major layout the W4A16 decode GEMM streams:
+         qw  uint8 [out, in/2]   row n = the 4-bit codes of W[n, :], 8 consecutive K per 32-bit word in W4_NIBBLE_OF_K order
+         sc  dtype [out, groups] scale of (row, group), rounded to the model dtype
+         zp  uint8 [out, groups] integer zero point incl. the checkpoint's offset (W = sc * (q - zp))
+       act-order checkpoints (a non-monotonic g_idx) are not representable here: the caller keeps the dequantised weight for them."""
+    q = _unpack_nibbles(qweight.to(torch.int32), 0).t().contiguous()      # [out, in]
+    n_out, n_in = q.shape
+    assert n_in % 8 == 0
+    q8 = q.view(n_out, n_in // 8, 8).to(torch.int64)
+    word = torch.zeros(n_out, n_in // 8, dtype=torch.int64, device=q.device)
+    for j, nib in enumerate(W4_NIBBLE_OF_K):
+        word |= q8[:, :, j] << (4 * nib)
+    qw = torch.stack([(word >> (8 * b)) & 0xFF for b in range(4)], dim=-1).to(torch.uint8).reshape(n_out, n_in // 2).contiguous()
+    z = (_unpack_nibbles(qzeros.to(torch.int32), 1)[:, :n_out] + int(zero_offset)).t().contiguous()   # [out, groups]
+    return qw, scales.t().contiguous().to(dtype), z.to(torch.uint8)
+
+
+def dequantize_w4(qw, sc, zp, group_size=128):
+    """Host statement of the kernel's on-the-fly dequantisation (tests): [out, in] in sc's dtype."""
+    n_out, half = qw.shape
+    b = qw.view(n_out, half // 4, 4).to(torch.int64)
+    word = b[:, :, 0] | (b[:, :, 1] << 8) | (b[:, :, 2] << 16) | (b[:, :, 3] << 24)
+    q = torch.stack([(word >> (4 * nib)) & 0xF for nib in W4_NIBBLE_OF_K], dim=-1).reshape(n_out, half * 2)
+    g = torch.arange(half * 2, device=qw.device) // int(group_size)
+    w = sc.to(torch.float32)[:, g] * (q - zp.to(torch.int64)[:, g]).to(torch.float32)
+    return w.to(sc.dtype)
+
+
+def dequantize_gptq(sd, quant_cfg=None, dtype=torch.bfloat16, scale_dtype=None):
     """Replace every ``<name>.{qweight,qzeros,scales[,g_idx]}`` group of a GPTQ checkpoint by ``<name>.weight``."""
     quant_cfg = quant_cfg or {}
     bits = int(quant_cfg.get("bits", 4))
@@ -140,12 +178,37 @@ def dequantize_gptq(sd, quant_cfg=None, dtype=torch.bfloat16):
             n_in = t.shape[0] * 8
             group = gs if gs > 0 else n_in                              # group_size -1: one group per column
             out[base + ".weight"] = dequantize_gptq_linear(t, sd[base + ".qzeros"], sd[base + ".scales"], sd.get(base + ".g_idx"),
-                                                            group, zo, dtype)
+                                                            group, zo, dtype, scale_dtype)
         elif k.endswith((".qzeros", ".scales", ".g_idx")) and (k.rsplit(".", 1)[0] + ".qweight") in sd:
             continue
         else:
             out[k] = t
     return out
+
+
+def gptq_w4_pack(sd, quant_cfg=None, dtype=torch.bfloat16):
+    """({linear name: (qw, scales, zeros)} in the W4A16 kernel's layout, group size) for a GPTQ checkpoint's decoder projections, or
+    (None, 0) when the checkpoint cannot use the kernel: not 4-bit, an act-order g_idx, or a group size that is not a multiple of 64."""
+    quant_cfg = quant_cfg or {}
+    if int(quant_cfg.get("bits", 4)) != 4:
+        return None, 0
+    gs = int(quant_cfg.get("group_size", 128))
+    zo = 0 if str(quant_cfg.get("checkpoint_format", "gptq")) == "gptq_v2" else 1
+    out = {}
+    for k, t in sd.items():
+        if not k.endswith(".qweight") or ".layers." not in k:
+            continue
+        base = k[: -len(".qweight")]
+        n_in = t.shape[0] * 8
+        group = gs if gs > 0 else n_in
+        if group % 64 != 0 or n_in % group != 0:
+            return None, 0
+        gi = sd.get(base + ".g_idx")
+        if gi is not None and not torch.equal(gi.to(torch.int64).cpu(), torch.arange(n_in) // group):
+            return None, 0                                                # act-order: rows of one group are scattered over K
+        out[base] = repack_gptq_w4(t, sd[base + ".qzeros"], sd[base + ".scales"], group, zo, dtype)
+        gs_used = group
+    return (out, gs_used) if out else (None, 0)
 
 
 def pack_gptq_linear(w, group_size=128, zero_offset=1):

@@ -496,6 +496,21 @@ int cts_grad_norm_clip(cts_ctx* ctx, const float* g, long long n, float max_norm
 int cts_lora_pack(cts_ctx* ctx, const float* master, const long long* desc, int n_desc, long long max_elems, void* work,
                   int dtype, void* stream);
 
+/* W4A16 decode GEMM for GPTQ-Int4 checkpoints (README.md:52,262-263): partial[s][t][n] = sum over split s of x[t][k] * W[n][k] with
+ * W[n][k] = scales[n][k / g] * (q[n][k] - zeros[n][k / g]) dequantised inside the TMA -> shared memory -> tcgen05 operand path
+ * (csrc/gemm_w4.cu), so a decode step streams the 4-bit codes -- a quarter of the bf16 bytes.  1 <= t <= 32; out = fp32 split-K
+ * partials [split_k, t, n] exactly as cts_gemm(CTS_EPI_PARTIAL_F32) writes them (the cts_reduce_* / cts_qkv_rope_cache tails finish
+ * the projection); results are bit-identical to cts_gemm on the dequantised weight.
+ *   qw     uint8 [n, k/2]  4-bit codes, 8 consecutive k per 32-bit word in the order chatts_b200/weights.py:repack_gptq_w4 writes
+ *   scales [n, k/group_size] model dtype;  zeros uint8 [n, k/group_size] integer zero points (checkpoint offset included) */
+typedef struct {
+  const void* qw; const void* scales; const void* zeros; const void* x; float* out;
+  long long n, k, t, x_ld;
+  int group_size, split_k, dtype, reserved;
+} cts_gemm_w4_args;
+int cts_gemm_w4(cts_ctx* ctx, const cts_gemm_w4_args* args, void* stream);
+int cts_gemm_w4_suggest_split(cts_ctx* ctx, long long n, long long k);
+
 /* Repetition penalty (transformers RepetitionPenaltyLogitsProcessor; generation_config.json of a checkpoint may set it): the set of
  * token ids that occur in a row's sequence is a bit mask seen[batch][words_per_row] (words_per_row >= ceil(vocab / 32), zeroed by the
  * caller).  _mark sets the bits of n (row, token) pairs (rows NULL: pair i belongs to row i -- the new token of every sequence after

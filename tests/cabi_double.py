@@ -286,6 +286,13 @@ class TorchDouble:
                 if slot is not None and pt is not None: slot[b] = pt[b, int(pos[b]) // page] * page + int(pos[b]) % page
         step_ptr[0] += 1
 
+    # ------------------------------------------------------------------ W4A16 decode GEMM (csrc/gemm_w4.cu)
+    def gemm_w4_suggest_split(self, n, k): return self.split if k >= 128 * self.split else 1
+    def gemm_w4(self, x, qw, scales, zeros, group_size, out, split_k, t=None):
+        from chatts_b200.weights import dequantize_w4
+        w = dequantize_w4(qw, scales, zeros, group_size)
+        self.gemm(x, w, out, epilogue=3, split_k=split_k, t=t)
+
     # ------------------------------------------------------------------ repetition penalty (csrc/sampling.cu)
     def rep_penalty_mark(self, tokens, rows, seen, vocab):
         tk = tokens.reshape(-1).tolist()

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "chatts_b200", "csrc")
-SOURCES = ["sampling.cu", "train_elementwise.cu", "allreduce_ll.cu", "attention_bwd.cu", "gemm_decode_fused.cu", "gemm_tcgen05.cu", "attention_bwd_tc5.cu", "lora_wgrad_mma.cu", "attention.cu", "elementwise.cu", "ts_frontend.cu", "decoder_step.cu", "allreduce.cu", "ts_encoder_fused.cu"]
+SOURCES = ["sampling.cu", "train_elementwise.cu", "allreduce_ll.cu", "attention_bwd.cu", "gemm_decode_fused.cu", "gemm_tcgen05.cu", "attention_bwd_tc5.cu", "lora_wgrad_mma.cu", "attention.cu", "elementwise.cu", "ts_frontend.cu", "decoder_step.cu", "allreduce.cu", "ts_encoder_fused.cu", "gemm_w4.cu"]
 OUT = os.path.join(HERE, "_build", "libchatts_shim.so")
 # Files that are GPU-validated are not edited for the shim's sake (not even a spelling): their two non-portable spellings are replaced
 # in the COPY.  Everything else in the copy is the product source, byte for byte.

@@ -52,6 +52,7 @@ static inline float4 make_float4(float a, float b, float c, float d) { return {a
 // ---------------------------------------------------------------------------------------------- bf16 / fp16 storage types
 struct __nv_bfloat16 { uint16_t bits; };
 struct __half { uint16_t bits; };
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
 static inline float shim_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 static inline uint32_t shim_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float __bfloat162float(__nv_bfloat16 v) { return shim_u2f((uint32_t)v.bits << 16); }
@@ -61,8 +62,14 @@ static inline __nv_bfloat16 __float2bfloat16_rn(float f) {
   u += 0x7FFFu + ((u >> 16) & 1u);                                                    // round to nearest even
   return {(uint16_t)(u >> 16)};
 }
+static inline __nv_bfloat162 __hsub2(__nv_bfloat162 a, __nv_bfloat162 b);
+static inline __nv_bfloat162 __hmul2(__nv_bfloat162 a, __nv_bfloat162 b);
 static inline float __half2float(__half v) { _Float16 h; memcpy(&h, &v.bits, 2); return (float)h; }
 static inline __half __float2half_rn(float f) { _Float16 h = (_Float16)f; __half r; memcpy(&r.bits, &h, 2); return r; }
+// packed pairs (csrc/gemm_w4.cu): element-wise, the exact result rounded ONCE to the 16-bit type, like the hardware instructions
+struct __half2 { __half x, y; };
+static inline __half2 __hsub2(__half2 a, __half2 b) { return {__float2half_rn(__half2float(a.x) - __half2float(b.x)), __float2half_rn(__half2float(a.y) - __half2float(b.y))}; }
+static inline __half2 __hmul2(__half2 a, __half2 b) { return {__float2half_rn(__half2float(a.x) * __half2float(b.x)), __float2half_rn(__half2float(a.y) * __half2float(b.y))}; }
 
 // ---------------------------------------------------------------------------------------------- execution model
 // The CUDA threads of a block are FIBERS of one OS thread (hand-rolled x86-64 context switch, shim_runtime.cpp), scheduled round
@@ -514,4 +521,11 @@ static inline int shim_ld_acquire(const int* p) {
   static thread_local unsigned n = 0;
   if ((++n & 255u) == 0) sched_yield();
   return v;
+}
+
+static inline __nv_bfloat162 __hsub2(__nv_bfloat162 a, __nv_bfloat162 b) {
+  return {__float2bfloat16_rn(__bfloat162float(a.x) - __bfloat162float(b.x)), __float2bfloat16_rn(__bfloat162float(a.y) - __bfloat162float(b.y))};
+}
+static inline __nv_bfloat162 __hmul2(__nv_bfloat162 a, __nv_bfloat162 b) {
+  return {__float2bfloat16_rn(__bfloat162float(a.x) * __bfloat162float(b.x)), __float2bfloat16_rn(__bfloat162float(a.y) * __bfloat162float(b.y))};
 }

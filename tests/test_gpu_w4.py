@@ -1,0 +1,74 @@
+"""cts_gemm_w4 (csrc/gemm_w4.cu: W4A16 decode GEMM, the 4-bit codes dequantised inside the TMA -> shared memory -> tcgen05 operand
+path) against cts_gemm on the dequantised weight -- the same values through the same MMA order, so the fp32 split-K partials must be
+BIT-IDENTICAL -- and the whole model decoding through the packed weights against decoding through the dense copy."""
+import numpy as np
+import pytest
+import torch
+
+from tests.gpu_util import ctx, record
+
+pytestmark = pytest.mark.gpu
+EPI_PARTIAL = 3
+
+
+def _rand_w4(n, k, gs, dtype, seed):
+    from chatts_b200.weights import dequantize_w4
+    g = torch.Generator().manual_seed(seed)
+    qw = torch.randint(0, 256, (n, k // 2), generator=g, dtype=torch.uint8)
+    sc = ((torch.rand(n, k // gs, generator=g) + 0.5) * 0.01).to(dtype)
+    zp = torch.randint(1, 17, (n, k // gs), generator=g, dtype=torch.uint8)
+    return qw, sc, zp, dequantize_w4(qw, sc, zp, gs)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,k,gs,t,split", [(256, 512, 128, 1, 1), (256, 512, 128, 5, 2), (384, 1024, 128, 17, 3), (128, 256, 64, 32, 4),
+                                            (200, 768, 128, 8, 2), (1024, 2560, 128, 32, 7), (7168, 5120, 128, 32, 7), (5120, 13824, 128, 1, 11)])
+def test_w4_partials_bit_identical_to_the_dense_gemm(n, k, gs, t, split, dtype):
+    c = ctx()
+    qw, sc, zp, w = _rand_w4(n, k, gs, dtype, seed=n + k + t)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(t, k, generator=g) * 0.5).to(dtype).cuda()
+    ref = torch.full((split, t, n), float("nan"), device="cuda")
+    got = torch.full((split, t, n), float("nan"), device="cuda")
+    c.gemm(x, w.cuda(), ref, epilogue=EPI_PARTIAL, split_k=split, t=t)
+    c.gemm_w4(x, qw.cuda(), sc.cuda(), zp.cuda(), gs, got, split, t=t)
+    torch.cuda.synchronize()
+    same = torch.equal(got, ref)
+    record("gemm_w4", n=n, k=k, t=t, split=split, dtype=str(dtype), bit_identical=int(same),
+           max_abs_diff=float((got - ref).abs().max()) if not same else 0.0)
+    assert same
+
+
+def test_w4_suggested_split_keeps_the_group_table_in_range():
+    c = ctx()
+    for n, k in ((7168, 5120), (5120, 5120), (27648, 5120), (5120, 13824), (256, 256)):
+        s = c.gemm_w4_suggest_split(n, k)
+        blocks = -(-(-(-k // 64)) // s) + 1
+        assert 1 <= s <= 16 and blocks * 64 // 128 + 2 <= 24
+
+
+@pytest.mark.parametrize("qwen3", [False, True])
+def test_model_decodes_through_the_packed_weights(qwen3):
+    """quantize_w4_synthetic: dense weights = the dequantised values, packed copy attached; the decode step through cts_gemm_w4 (its own
+    split factors) must pick the tokens the dense decode picks (same weights; fp32 summation order differs with the split)."""
+    from chatts_b200 import ChatTSConfig, ChatTSProcessor, SimpleTokenizer
+    from chatts_b200.model import ChatTSForCausalLM
+    from chatts_b200.weights import synthetic_state_dict
+    cfg = ChatTSConfig.tiny(intermediate_size=768)
+    if qwen3:
+        cfg.qk_norm, cfg.attention_bias = True, False
+    sd = synthetic_state_dict(cfg, seed=5, device="cpu", dtype=torch.bfloat16, std=0.05)
+    model = ChatTSForCausalLM(cfg, sd, dtype=torch.bfloat16, max_batch=4, max_seq_len=256, page_size=16)
+    model.quantize_w4_synthetic(group_size=64)
+    proc = ChatTSProcessor(SimpleTokenizer(cfg.ts_token_start_index, cfg.pad_token_id, cfg.eos_token_id), cfg)
+    x = np.arange(200)
+    enc = proc(text=["A <ts><ts/> ?", "text only, a longer prompt"], timeseries=[np.sin(x / 9) * 4], padding=True, return_tensors="pt")
+    l0 = model.ctx.launches
+    a = model.generate(**enc, max_new_tokens=16, ignore_eos=True)
+    assert model.w4 is not None and model.ctx.launches > l0
+    w4, model.w4, model._steps = model.w4, None, {}
+    b = model.generate(**enc, max_new_tokens=16, ignore_eos=True)
+    S = enc["input_ids"].shape[1]
+    agree = [int(next((i for i in range(16) if a[r, S + i] != b[r, S + i]), 16)) for r in range(2)]
+    record("w4_model_decode", qwen3=int(qwen3), greedy_agreement=str(agree))
+    assert min(agree) >= 12          # same weights; only the K partition of the fp32 sums differs
