@@ -435,6 +435,34 @@ int launch_ts_fused(cts_ctx* ctx, const cts_ts_encode_args* a, int* sync, cudaSt
     if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q) == cudaSuccess && n_clusters >= tiles) S = cand;
   }
   (void)cudaGetLastError();
+  if (const char* dbg = getenv("CTS_TS_FUSED_DEBUG")) {
+    if (atoi(dbg) == 1) {
+      int per_sm = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, kern);
+      fprintf(stderr, "[ts_fused] BN=%d smem dyn %zu static %zu regs %d: blocks/SM (api) %d, chosen split %d, tiles %d\n", BN, smem,
+              (size_t)fa.sharedSizeBytes, fa.numRegs, per_sm, S, tiles);
+      for (int cand = 8; cand >= 1; --cand) {
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3((unsigned)tiles, 1, (unsigned)cand);
+        q.blockDim = dim3(kThreads);
+        q.dynamicSmemBytes = smem;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = 1; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = (unsigned)cand;
+        q.attrs = qa; q.numAttrs = 1;
+        int n_clusters = -1;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q);
+        fprintf(stderr, "[ts_fused]   cluster %d: max active clusters %d (%s)\n", cand, n_clusters, cudaGetErrorString(e));
+      }
+      (void)cudaGetLastError();
+    }
+  }
+  if (const char* fs = getenv("CTS_TS_FUSED_SPLIT")) {          // experiment switch: a split the grid cannot hold traps at the first barrier
+    const int f = atoi(fs);
+    if (f >= 1 && f <= 8 && f <= kb_max) S = f;
+  }
 #endif
   if (S < 1) return cts_set_error(ctx, CTS_ERR_UNSUPPORTED, "cts_ts_encode_fused: %d feature tiles cannot all be resident", tiles);
   p.split = S;
