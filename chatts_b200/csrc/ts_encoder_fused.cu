@@ -418,21 +418,36 @@ int launch_ts_fused(cts_ctx* ctx, const cts_ts_encode_args* a, int* sync, cudaSt
 #ifdef CTS_HOST_SHIM
   S = kb_max < 4 ? kb_max : 4;
 #else
-  for (int cand = 8; cand >= 1 && S == 0; --cand) {
-    if (cand > kb_max) continue;
+  // The driver's cluster-occupancy query counts ONE CTA of this kernel per SM on a B200 (first runs: 148 single-CTA clusters, 45 of
+  // size 3) although two fit by every resource (97 KB of shared memory, 108 registers x 192 threads, 2 x 128 TMEM columns) and 240
+  // CTAs in clusters of 6 do run co-resident.  Sound bound from what the query does answer: the SMs that hold a cluster of c CTAs
+  // at one CTA per SM hold a cluster of 2c at two per SM, so  clusters(2c at 2/SM) >= clusters(c at 1/SM).
+  auto api_clusters = [&](int c) {
     cudaLaunchConfig_t q = {};
-    q.gridDim = dim3((unsigned)tiles, 1, (unsigned)cand);
+    q.gridDim = dim3((unsigned)tiles, 1, (unsigned)c);
     q.blockDim = dim3(kThreads);
     q.dynamicSmemBytes = smem;
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension;
     qa[0].val.clusterDim.x = 1;
     qa[0].val.clusterDim.y = 1;
-    qa[0].val.clusterDim.z = (unsigned)cand;
+    qa[0].val.clusterDim.z = (unsigned)c;
     q.attrs = qa;
     q.numAttrs = 1;
-    int n_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q) == cudaSuccess && n_clusters >= tiles) S = cand;
+    int n = 0;
+    return cudaOccupancyMaxActiveClusters(&n, kern, &q) == cudaSuccess ? n : 0;
+  };
+  int per_sm_api = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_api, kern, kThreads, smem);
+  cudaFuncAttributes fattr;
+  CTS_CUDA(ctx, cudaFuncGetAttributes(&fattr, kern));
+  const long long smem_cta = (long long)smem + (long long)fattr.sharedSizeBytes + 1024;
+  const long long regs_cta = (long long)((fattr.numRegs + 7) / 8 * 8) * kThreads;
+  const bool two_fit = per_sm_api >= 2 || (2 * smem_cta <= 227LL * 1024 && 2 * regs_cta <= 65536 && 2 * BN <= 512 && 2 * kThreads <= 2048);
+  for (int cand = 8; cand >= 1 && S == 0; --cand) {
+    if (cand > kb_max) continue;
+    if (api_clusters(cand) >= tiles) { S = cand; break; }
+    if (per_sm_api < 2 && two_fit && cand % 2 == 0 && api_clusters(cand / 2) >= tiles) S = cand;
   }
   (void)cudaGetLastError();
   if (const char* dbg = getenv("CTS_TS_FUSED_DEBUG")) {
