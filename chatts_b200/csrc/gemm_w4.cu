@@ -25,7 +25,8 @@
 namespace {
 
 constexpr int kBM = 128, kBK = 64, kUmmaK = 16, kThreads = 192;
-constexpr int kStg = 5;                 // staging ring of packed tiles (4 KB each)
+constexpr int kStg = 12;                // staging ring of packed tiles (4 KB each): 48 KB of weight stream in flight per CTA, two CTAs per SM
+                                        // (the first runs had 5 slots = 20 KB: the 4-bit stream was latency-bound at ~1.6 TB/s)
 constexpr int kMs = 2;                  // MMA stages (dequantised A tile 16 KB + token tile)
 constexpr int kPacked = kBM * kBK / 2;  // 4096 bytes
 constexpr int kMaxGroups = 24;          // groups a CTA's K range may touch (scale 2 B + zero point 1 B per row kept in shared memory: 9 KB)
@@ -246,6 +247,9 @@ int launch_w4(cts_ctx* ctx, const cts_gemm_w4_args* a, cudaStream_t stream) {
   const size_t smem = (size_t)kMs * kMStage + (size_t)kStg * kPacked + 1024;
   auto kern = gemm_w4_kernel<T, BN>;
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifndef CTS_HOST_SHIM
+  CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+#endif
   dim3 grid((unsigned)cdiv_ll(a->n, kBM), 1, (unsigned)a->split_k);
   CTS_CUDA(ctx, launch_pdl(kern, grid, dim3(kThreads), smem, stream, 1, tm_q, tm_x, p));
   return CTS_OK;
@@ -253,11 +257,11 @@ int launch_w4(cts_ctx* ctx, const cts_gemm_w4_args* a, cudaStream_t stream) {
 
 }  // namespace
 
-// split-K factor for the W4 stream: one wave of the CTAs an SM holds (the tile is 72 KB of shared memory -> 3 per SM)
+// split-K factor for the W4 stream: one wave of the CTAs an SM holds (~98 KB of shared memory per CTA -> 2 per SM)
 extern "C" int cts_gemm_w4_suggest_split(cts_ctx* ctx, long long n, long long k) {
   if (!ctx || n <= 0 || k <= 0) return 1;
   const long long tiles = cdiv_ll(n, kBM), kb = cdiv_ll(k, kBK);
-  long long s = (3LL * ctx->sm_count) / tiles;
+  long long s = (2LL * ctx->sm_count) / tiles;
   if (s > kb / 2) s = kb / 2;
   if (s > 16) s = 16;
   if (s < 1) s = 1;
