@@ -29,7 +29,8 @@ constexpr int kStg = 12;                // staging ring of packed tiles (4 KB ea
                                         // (the first runs had 5 slots = 20 KB: the 4-bit stream was latency-bound at ~1.6 TB/s)
 constexpr int kMs = 2;                  // MMA stages (dequantised A tile 16 KB + token tile)
 constexpr int kPacked = kBM * kBK / 2;  // 4096 bytes
-constexpr int kMaxGroups = 24;          // groups a CTA's K range may touch (scale 2 B + zero point 1 B per row kept in shared memory: 9 KB)
+constexpr int kMaxGroups = 44;          // groups a CTA's K range may touch (scale 2 B + zero point 1 B per row kept in shared memory: 16.5 KB;
+                                        // 44 covers an unsplit K = 5120 at group size 128)
 
 struct W4Params {
   long long n, k, t;
@@ -279,7 +280,7 @@ extern "C" int cts_gemm_w4(cts_ctx* ctx, const cts_gemm_w4_args* a, void* stream
   CTS_CHECK_ARG(ctx, a->x_ld >= a->k, "x_ld smaller than k");
   // groups one CTA may touch: its K range is at most ceil(kb_total / split) + 1 blocks
   const long long blocks = cdiv_ll(cdiv_ll(a->k, kBK), a->split_k) + 1;
-  CTS_CHECK_ARG(ctx, blocks * kBK / a->group_size + 2 <= kMaxGroups, "K range per split touches more than 24 groups: raise split_k");
+  CTS_CHECK_ARG(ctx, blocks * kBK / a->group_size + 2 <= kMaxGroups, "K range per split touches more than 44 groups: raise split_k");
   cudaStream_t st = (cudaStream_t)stream;
   if (a->dtype == CTS_BF16) return a->t <= 16 ? launch_w4<__nv_bfloat16, 16>(ctx, a, st) : launch_w4<__nv_bfloat16, 32>(ctx, a, st);
   return a->t <= 16 ? launch_w4<__half, 16>(ctx, a, st) : launch_w4<__half, 32>(ctx, a, st);
