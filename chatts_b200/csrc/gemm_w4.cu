@@ -179,8 +179,6 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       uint32_t wv[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) wv[it] = stg32[(it * 16 + wq * 4 + (lane >> 3)) * 8 + (lane & 7)];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&stg_empty[ss]);                         // this warp's share of the packed tile is in registers
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int rr = it * 16 + wq * 4 + (lane >> 3), ch = lane & 7;
@@ -194,7 +192,12 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       }
       fence_proxy_async_smem();                                           // generic-proxy writes -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive(&mma_full[ms]);
+      if (lane == 0) {
+        // the staging slot is released only now, after every word read from it has been USED: the TMA that refills it runs in the
+        // async proxy, and a slot released right after issuing the loads (5-slot version) produced one stale block in ~1 of 50 runs
+        mbar_arrive(&stg_empty[ss]);
+        mbar_arrive(&mma_full[ms]);
+      }
     }
     // ------------------------------ epilogue: fp32 partial of this split ------------------------------
     if (nkb > 0) {

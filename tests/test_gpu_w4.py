@@ -22,7 +22,8 @@ def _rand_w4(n, k, gs, dtype, seed):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("n,k,gs,t,split", [(256, 512, 128, 1, 1), (256, 512, 128, 5, 2), (384, 1024, 128, 17, 3), (128, 256, 64, 32, 4),
-                                            (200, 768, 128, 8, 2), (1024, 2560, 128, 32, 7), (7168, 5120, 128, 32, 7), (5120, 13824, 128, 1, 11)])
+                                            (200, 768, 128, 8, 2), (1024, 2560, 128, 32, 7), (7168, 5120, 128, 32, 7), (5120, 13824, 128, 1, 11),
+                                            (256, 5120, 128, 8, 1), (27648, 5120, 128, 32, 1)])          # unsplit K: every staging slot reused 6 times
 def test_w4_partials_bit_identical_to_the_dense_gemm(n, k, gs, t, split, dtype):
     c = ctx()
     qw, sc, zp, w = _rand_w4(n, k, gs, dtype, seed=n + k + t)
