@@ -24,7 +24,11 @@
 
 namespace {
 
-constexpr int kBM = 128, kBK = 64, kUmmaK = 16, kThreads = 192;
+constexpr int kBM = 128, kBK = 64, kUmmaK = 16;
+constexpr int kDqWarps = 8;             // dequantising warps per CTA: the int4 -> 16-bit conversion is instruction-issue bound (ncu: 39 % issue
+                                        // active with 4 warps and 1.5 CTAs per SM), so it gets as many warps as the shared memory budget allows CTAs
+constexpr int kDqThreads = kDqWarps * 32;
+constexpr int kThreads = 64 + kDqThreads;
 constexpr int kStg = 12;                // staging ring of packed tiles (4 KB each): 48 KB of weight stream in flight per CTA, two CTAs per SM
                                         // (the first runs had 5 slots = 20 KB: the 4-bit stream was latency-bound at ~1.6 TB/s)
 constexpr int kMs = 2;                  // MMA stages (dequantised A tile 16 KB + token tile)
@@ -94,8 +98,8 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_x);
-    for (int s = 0; s < kStg; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], 4); }
-    for (int s = 0; s < kMs; ++s) { mbar_init(&mma_full[s], 5); mbar_init(&mma_empty[s], 1); }
+    for (int s = 0; s < kStg; ++s) { mbar_init(&stg_full[s], 1); mbar_init(&stg_empty[s], kDqWarps); }
+    for (int s = 0; s < kMs; ++s) { mbar_init(&mma_full[s], 1 + kDqWarps); mbar_init(&mma_empty[s], 1); }
     mbar_init(&acc_bar, 1);
     fence_mbar_init();
   }
@@ -138,10 +142,10 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     }
   } else {
     // ------------------------------ dequantisers (thread = weight row), then the epilogue ------------------------------
-    const int r = (int)threadIdx.x - 64;                    // 0..127: row of the tile
+    const int r = (int)threadIdx.x - 64;                    // 0..kDqThreads-1; the first 128 also own a row of the (group, row) table
     const long long f = (long long)f0 + r;
-    const bool f_ok = f < p.n;
-    {
+    const bool f_ok = f < p.n && r < kBM;
+    if (r < kBM) {
       // scale / zero point of this row for every group the CTA's K range touches (static data: before the dependency wait)
       const int g1 = nkb > 0 ? ((kb1 * kBK - 1) / p.group_size) : g0;
       const T* sc = reinterpret_cast<const T*>(p.sc);
@@ -157,7 +161,7 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         zp_s[g - g0][r] = zv;
       }
     }
-    named_bar_sync(1, 128);                                 // the (group, row) table is read by other threads than the ones that wrote it
+    named_bar_sync(1, kDqThreads);                          // the (group, row) table is read by other threads than the ones that wrote it
     pdl_wait();                                             // the token operand comes from the predecessor
     if (threadIdx.x == 64) CTS_TRACE(CTS_TK_GEMM, 1);
     for (int i = 0; i < nkb; ++i) {
@@ -175,13 +179,14 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       // 16 wavefronts each, and the kernel ran at the speed of the shared-memory store pipe: 1.06x over bf16 on the first B200 run).
       const uint32_t* stg32 = reinterpret_cast<const uint32_t*>(stg_s + (size_t)ss * kPacked);
       const int g = ((kb0 + i) * kBK) / p.group_size - g0;
-      const int wq = warp - 2;                                            // 0..3
-      uint32_t wv[8];
+      const int wq = warp - 2;                                            // 0..kDqWarps-1
+      constexpr int kIts = kBM / (4 * kDqWarps);                          // 4 rows per warp and iteration
+      uint32_t wv[kIts];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) wv[it] = stg32[(it * 16 + wq * 4 + (lane >> 3)) * 8 + (lane & 7)];
+      for (int it = 0; it < kIts; ++it) wv[it] = stg32[(it * 4 * kDqWarps + wq * 4 + (lane >> 3)) * 8 + (lane & 7)];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 16 + wq * 4 + (lane >> 3), ch = lane & 7;
+      for (int it = 0; it < kIts; ++it) {
+        const int rr = it * 4 * kDqWarps + wq * 4 + (lane >> 3), ch = lane & 7;
         const uint32_t s2 = (uint32_t)sc_s[g][rr] * 0x00010001u, b2 = Magic<T>::bias((uint32_t)zp_s[g][rr]);
         uint4 o;
         o.x = Magic<T>::cvt(wv[it] & 0x000F000Fu, b2, s2);
@@ -204,13 +209,14 @@ gemm_w4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       mbar_wait(&acc_bar, 0);
       tc_fence_after();
     }
-    const int q = warp & 3;
-    const int ft = q * 32 + lane;                          // TMEM lane = output feature (warp & 3 is a permutation of 0..3)
+    const int q = warp & 3;                                // TMEM lane quarter this warp may read (32x32b: lanes 32 (warp % 4) ..)
+    const int ch2 = (warp - 2) >> 2;                       // the two warps of a quarter split the token columns
+    const int ft = q * 32 + lane;                          // TMEM lane = output feature
     const long long fo = (long long)f0 + ft;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     float* dst = p.out + (long long)split * p.t * p.n;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
+    for (int c = ch2 * 16; c < BN; c += 16 * (kDqWarps / 4)) {
       if (c >= p.t) break;
       uint32_t v[16];
       if (nkb > 0) {
