@@ -29,9 +29,9 @@ constexpr int kDqWarps = 8;             // dequantising warps per CTA: the int4 
                                         // active with 4 warps and 1.5 CTAs per SM), so it gets as many warps as the shared memory budget allows CTAs
 constexpr int kDqThreads = kDqWarps * 32;
 constexpr int kThreads = 64 + kDqThreads;
-constexpr int kStg = 12;                // staging ring of packed tiles (4 KB each): 48 KB of weight stream in flight per CTA, two CTAs per SM
+constexpr int kStg = 8;                 // staging ring of packed tiles (4 KB each): 48 KB of weight stream in flight per CTA, two CTAs per SM
                                         // (the first runs had 5 slots = 20 KB: the 4-bit stream was latency-bound at ~1.6 TB/s)
-constexpr int kMs = 2;                  // MMA stages (dequantised A tile 16 KB + token tile)
+constexpr int kMs = 3;                  // MMA stages (dequantised A tile 16 KB + token tile): the conversion of block i+2 must not wait for the MMA of block i
 constexpr int kPacked = kBM * kBK / 2;  // 4096 bytes
 constexpr int kMaxGroups = 44;          // groups a CTA's K range may touch (scale 2 B + zero point 1 B per row kept in shared memory: 16.5 KB;
                                         // 44 covers an unsplit K = 5120 at group size 128)
@@ -271,7 +271,7 @@ int launch_w4(cts_ctx* ctx, const cts_gemm_w4_args* a, cudaStream_t stream) {
 extern "C" int cts_gemm_w4_suggest_split(cts_ctx* ctx, long long n, long long k) {
   if (!ctx || n <= 0 || k <= 0) return 1;
   const long long tiles = cdiv_ll(n, kBM), kb = cdiv_ll(k, kBK);
-  long long s = (2LL * ctx->sm_count) / tiles;
+  long long s = (4LL * ctx->sm_count) / tiles;          // ~two waves of the two CTAs an SM holds: measured best (profiles/r2_w4_gemm_*.json)
   if (s > kb / 2) s = kb / 2;
   if (s > 16) s = 16;
   if (s < 1) s = 1;
