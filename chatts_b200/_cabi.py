@@ -30,7 +30,7 @@ SYMBOLS = [
     "cts_lora_pack",
     "cts_sample_advance", "cts_rmsnorm", "cts_lm_head", "cts_decoder_step_ws_floats", "cts_decoder_step", "cts_ts_encode", "cts_gemm_decode_fused",
     "cts_peer_ll_region_bytes", "cts_peer_allreduce_ll", "cts_trace_enable", "cts_ts_encode_fused_ok", "cts_ts_encode_fused",
-    "cts_rep_penalty_mark", "cts_rep_penalty_apply", "cts_gemm_w4", "cts_gemm_w4_suggest_split",
+    "cts_rep_penalty_mark", "cts_rep_penalty_apply", "cts_gemm_w4", "cts_gemm_w4_suggest_split", "cts_gemm_w4_mma", "cts_gemm_w4_mma_suggest_split",
 ]
 FUSED_RESIDUAL, FUSED_SWIGLU, FUSED_QKV_ROPE = 0, 1, 2
 PACK_DESC_LONGS = 12
@@ -95,6 +95,12 @@ class GemmW4Args(C.Structure):
                 ("group_size", C.c_int), ("split_k", C.c_int), ("dtype", C.c_int), ("reserved", C.c_int)]
 
 
+class GemmW4fArgs(C.Structure):
+    _fields_ = [("qw", C.c_void_p), ("szp", C.c_void_p), ("x", C.c_void_p), ("out", C.c_void_p),
+                ("n", C.c_longlong), ("k", C.c_longlong), ("t", C.c_longlong), ("x_ld", C.c_longlong),
+                ("group_size", C.c_int), ("split_k", C.c_int), ("dtype", C.c_int), ("reserved", C.c_int)]
+
+
 class TsEncodeArgs(C.Structure):
     _fields_ = ([("x", C.c_void_p)] + [(k, C.c_int) for k in ("dtype", "n_series", "row_len", "num_features", "patch_size", "mode")] +
                 [("pos_table", C.c_void_p)] + [(k, C.c_int) for k in ("emb_dim", "max_seq_len", "num_layers", "hidden", "in0")] +
@@ -150,6 +156,8 @@ def load_library():
     lib.cts_trace_enable.argtypes = [vp, vp]
     lib.cts_gemm_w4.argtypes = [vp, C.POINTER(GemmW4Args), vp]
     lib.cts_gemm_w4_suggest_split.argtypes = [vp, ll, ll]
+    lib.cts_gemm_w4_mma.argtypes = [vp, C.POINTER(GemmW4fArgs), vp]
+    lib.cts_gemm_w4_mma_suggest_split.argtypes = [vp, ll, ll, ll]
     lib.cts_rep_penalty_mark.argtypes = [vp, vp, vp, i, vp, i, ll, vp]
     lib.cts_rep_penalty_apply.argtypes = [vp, vp, ll, ll, i, vp, i, f, i, vp]
     lib.cts_ts_encode_fused_ok.argtypes = [C.POINTER(TsEncodeArgs)]
@@ -328,6 +336,19 @@ class Context:
 
     def gemm_w4_suggest_split(self, n, k):
         return int(self.lib.cts_gemm_w4_suggest_split(self.h, n, k))
+
+    def gemm_w4_mma(self, x, qwf, szp, n, group_size, out, split_k, t=None):
+        """The same partials with the weight operand dequantised in registers (cts_gemm_w4_mma).  qwf uint8 [ceil(N/256) * K/64 * 8192]
+        fragment-major codes, szp int32 [ceil(N/256), K/g, 256] (weights.py:repack_w4_mma); n = the true number of features."""
+        a = GemmW4fArgs()
+        a.qw, a.szp, a.x, a.out = qwf.data_ptr(), szp.data_ptr(), x.data_ptr(), out.data_ptr()
+        a.n, a.k = int(n), szp.shape[1] * int(group_size)
+        a.t = x.shape[0] if t is None else t
+        a.x_ld, a.group_size, a.split_k, a.dtype = x.stride(0), int(group_size), int(split_k), dtype_code(x.dtype)
+        self._chk(self.lib.cts_gemm_w4_mma(self.h, C.byref(a), _stream()))
+
+    def gemm_w4_mma_suggest_split(self, n, k, t=1):
+        return int(self.lib.cts_gemm_w4_mma_suggest_split(self.h, n, k, t))
 
     # ------------------------------------------------------------------ fused split-K tails
     def reduce_bias_act(self, partial, split_k, t, n, bias, act, out, row_map=None):

@@ -1,0 +1,326 @@
+// chatts_b200 -- W4A16 decode GEMM, register-operand version (GPTQ-Int4 checkpoints, README.md:52,262-263):
+//     partial[s][t][n] = sum_{k in split s} x[t][k] * sc[n][k / g] * (q[n][k] - zp[n][k / g])        (fp32 accumulate)
+// Why a second kernel: gemm_w4.cu keeps the tcgen05 structure and writes the dequantised 16-bit tile to shared memory for the tensor
+// core to read back; per 128 x 64 block that is 16 KB written + 18 KB read by the MMA + the 4-bit tile in and out = 44 KB through a
+// 128 B/clk shared-memory port, i.e. at most ~24 weights per clock and SM where HBM delivers 46 -- the kernel measured NO faster than
+// the bf16 GEMM (profiles/r2_w4_gemm_tcgen05_final.json).  Here the weight operand never touches shared memory as 16-bit data:
+//   * load-time layout (weights.py:repack_w4_mma): for every (256-feature tile, 64-K block) one contiguous 8 KB chunk whose 32-bit
+//     words ARE the A fragments of mma.sync.m16n8k16 -- lane (g, t) of m-tile j finds, for each of the block's four k16 steps, one
+//     word holding the 8 codes {rows g / g+8} x {k 2t, 2t+1, 2t+8, 2t+9} in the nibble order that `(w >> 4i) & 0x000F000F` turns
+//     into fragment register a_i; next to it 1 KB of {scale, 128+zero-point} pairs of the block's group
+//   * warp 8, one lane: cp.async.bulk of those chunks into a deep ring (10-11 x 9 KB per CTA, two CTAs per SM = what keeps HBM busy),
+//     issued BEFORE the dependency wait (nobody writes weights); warp 9, one lane: the token tile [8 NT rows x 64 K] by TMA (128B
+//     swizzle) after the wait
+//   * warps 0..7: one LDS.128 per m-tile = the fragments of four k16 steps; int4 -> bf16/fp16 in registers with the magic-number trick
+//     of gemm_w4.cu (exactly the value dequantize_w4 stores for the prefill copy); B fragments by ldmatrix from the swizzled token
+//     tile; mma.sync with the fp32 accumulators of 2 m-tiles x NT n-tiles in registers
+//   * persistent CTAs over (tile, K split) units, the producers run ahead across unit boundaries
+// Output: the fp32 split-K partials [split, t, n] of CTS_EPI_PARTIAL_F32, so the decode step's reduce tails are unchanged.  The A
+// operand holds the same 16-bit values as the dense copy; the fp32 summation order differs from the tcgen05 GEMM (parity is a
+// tolerance, tests/test_gpu_w4.py), unlike gemm_w4.cu which is bit-identical and stays as the checker for this kernel.
+#include <type_traits>
+
+#include "common.cuh"
+#ifndef CTS_DYN_SMEM
+#define CTS_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#endif
+#include "tensormap.cuh"
+
+namespace {
+
+constexpr int kTileN = 256, kBK = 64, kWarps = 8;
+constexpr int kWBytes = kTileN * kBK / 2;            // 8192: the codes of one (tile, K block)
+constexpr int kSzBytes = kTileN * 4;                 // 1024: {scale bits | (magic + zero point) << 16} per feature
+constexpr int kStageBytes = kWBytes + kSzBytes;      // 9216
+constexpr int kThreads = (kWarps + 2) * 32;
+constexpr int kMaxStagesW = 24, kMaxStagesX = 8;
+
+struct W4mParams {
+  long long n, k, t;
+  int kb_total, split_k, kb_per_group, n_groups, tiles, stages_w, stages_x;
+  const uint8_t* qw;       // [tiles][kb_total][8192]
+  const uint8_t* szp;      // [tiles][n_groups][1024]
+  float* out;              // fp32 [split_k, t, n]
+};
+
+template <typename T> struct MagicM;
+template <> struct MagicM<__nv_bfloat16> {
+  static constexpr uint32_t kOr = 0x43004300u;                       // bf16 128.0 in both halves: 128 + code (ulp 1 in [128, 256))
+  static __device__ __forceinline__ uint32_t cvt(uint32_t codes, uint32_t b2, uint32_t s2) {
+    const uint32_t y = codes | kOr;
+    __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&y), *reinterpret_cast<const __nv_bfloat162*>(&b2));   // exact small ints
+    __nv_bfloat162 w = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&s2));                                              // one rounding
+    return *reinterpret_cast<uint32_t*>(&w);
+  }
+};
+template <> struct MagicM<__half> {
+  static constexpr uint32_t kOr = 0x64006400u;                       // fp16 1024.0: 1024 + code
+  static __device__ __forceinline__ uint32_t cvt(uint32_t codes, uint32_t b2, uint32_t s2) {
+    const uint32_t y = codes | kOr;
+    __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&y), *reinterpret_cast<const __half2*>(&b2));
+    __half2 w = __hmul2(d, *reinterpret_cast<const __half2*>(&s2));
+    return *reinterpret_cast<uint32_t*>(&w);
+  }
+};
+
+__device__ __forceinline__ void w4m_ldsm_x4(uint32_t addr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+template <typename T> __device__ __forceinline__ void w4m_mma(float* c, const uint32_t* a, uint32_t b0, uint32_t b1);
+template <> __device__ __forceinline__ void w4m_mma<__nv_bfloat16>(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <> __device__ __forceinline__ void w4m_mma<__half>(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// the weight stream is read once: evict-first, as the TMA tiles of the dense GEMM
+__device__ __forceinline__ void w4m_bulk_stream(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+#ifndef CTS_HOST_SHIM
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(CTS_L2_EVICT_FIRST)
+               : "memory");
+#else
+  bulk_load_1d(smem_dst, gsrc, bytes, bar);
+#endif
+}
+
+// unit u of the persistent schedule -> (tile, split, K block range)
+__device__ __forceinline__ void w4m_unit(const W4mParams& p, int u, int& tile, int& split, int& kb0, int& kb1) {
+  tile = u % p.tiles;
+  split = u / p.tiles;
+  kb0 = (int)(((long long)p.kb_total * split) / p.split_k);
+  kb1 = (int)(((long long)p.kb_total * (split + 1)) / p.split_k);
+}
+
+template <typename T, int NT>
+__global__ void __launch_bounds__(kThreads, 2)
+gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) {
+  CTS_DYN_SMEM(smem_raw);
+  __shared__ uint64_t w_full[kMaxStagesW], w_empty[kMaxStagesW], x_full[kMaxStagesX], x_empty[kMaxStagesX];
+
+  constexpr int kXBytes = NT * 8 * kBK * 2;                 // token tile: 8 NT rows of 128 bytes
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* x_s = smem;                                       // stages_x x kXBytes (1024-byte aligned: the swizzle pattern repeats every 8 rows)
+  uint8_t* w_s = smem + (size_t)p.stages_x * kXBytes;        // stages_w x 9216
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int SW = p.stages_w, SX = p.stages_x;
+  const int units = p.tiles * p.split_k;
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_x);
+    for (int s = 0; s < SW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kWarps); }
+    for (int s = 0; s < SX; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], kWarps); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == kWarps) {
+    // ------------------------------ weight producer (static data: no dependency wait) ------------------------------
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 1u;                                      // parity of the "slot is empty" phase being waited for (fresh barrier: passes)
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int tile, split, kb0, kb1;
+        w4m_unit(p, u, tile, split, kb0, kb1);
+        const uint8_t* src = p.qw + ((size_t)tile * p.kb_total + kb0) * kWBytes;
+        int grp = kb0 / p.kb_per_group, in_grp = kb0 % p.kb_per_group;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&w_empty[s], ph);
+          uint8_t* dst = w_s + (size_t)s * kStageBytes;
+          mbar_expect_tx(&w_full[s], (uint32_t)kStageBytes);
+          w4m_bulk_stream(dst, src, (uint32_t)kWBytes, &w_full[s]);
+          bulk_load_1d(dst + kWBytes, p.szp + ((size_t)tile * p.n_groups + grp) * kSzBytes, (uint32_t)kSzBytes, &w_full[s]);
+          src += kWBytes;
+          if (++in_grp == p.kb_per_group) { in_grp = 0; ++grp; }
+          if (++s == SW) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == kWarps + 1) {
+    // ------------------------------ token-tile producer (the predecessor's output) ------------------------------
+    if (lane == 0) {
+      pdl_wait();
+      int s = 0;
+      uint32_t ph = 1u;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int tile, split, kb0, kb1;
+        w4m_unit(p, u, tile, split, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&x_empty[s], ph);
+          mbar_expect_tx(&x_full[s], (uint32_t)kXBytes);
+          tma_load_2d(x_s + (size_t)s * kXBytes, &tm_x, &x_full[s], kb * kBK, 0, CTS_L2_EVICT_LAST);
+          if (++s == SX) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ dequantise in registers + mma.sync ------------------------------
+    const int g = lane >> 2, tq = lane & 3;
+    const int lrow = lane & 7, lmat = lane >> 3;             // ldmatrix: this lane supplies row `lrow` of matrix `lmat`
+    float acc[2][NT][4];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[mi][nt][j] = 0.f;
+    uint32_t sA[2] = {0, 0}, bA[2] = {0, 0}, sB[2] = {0, 0}, bB[2] = {0, 0};   // {scale, magic + zp} of rows g / g + 8 of the two m-tiles
+    int s = 0, sx = 0;
+    uint32_t ph = 0u, phx = 0u;                              // parities of the "slot is full" phases
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int tile, split, kb0, kb1;
+      w4m_unit(p, u, tile, split, kb0, kb1);
+      int in_grp = 0;                                        // 0 -> this block starts a group (or the unit): fetch its scales / zero points
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&w_full[s], ph);
+        const uint8_t* ws = w_s + (size_t)s * kStageBytes;
+        uint4 wv[2];
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) wv[mi] = *reinterpret_cast<const uint4*>(ws + (size_t)(((warp * 2 + mi) * 32 + lane) * 16));
+        if (in_grp == 0) {
+          in_grp = p.kb_per_group - (kb == kb0 ? kb0 % p.kb_per_group : 0);
+          const uint32_t* sz = reinterpret_cast<const uint32_t*>(ws + kWBytes);
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const uint32_t va = sz[(warp * 2 + mi) * 16 + g], vb = sz[(warp * 2 + mi) * 16 + g + 8];
+            sA[mi] = (va & 0xFFFFu) * 0x00010001u; bA[mi] = (va >> 16) * 0x00010001u;      // both halves of a packed pair
+            sB[mi] = (vb & 0xFFFFu) * 0x00010001u; bB[mi] = (vb >> 16) * 0x00010001u;
+          }
+        }
+        --in_grp;
+        mbar_wait(&x_full[sx], phx);
+        const uint32_t xs = smem_u32(x_s + (size_t)sx * kXBytes);
+        uint32_t rq[4] = {0u, 0u, 0u, 0u};                    // NT == 1: the fragments of a pair of k16 steps
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint32_t bf[NT][2];                                 // B fragments of this k16 step
+          if constexpr (NT == 1) {
+            // one ldmatrix.x4 = two k16 steps of the single 8-token tile: matrices (ks, half) = (2q, 0), (2q, 1), (2q + 1, 0), (2q + 1, 1)
+            if ((ks & 1) == 0) {
+              const int chunk = 2 * (ks + (lmat >> 1)) + (lmat & 1);
+              w4m_ldsm_x4(xs + (uint32_t)(lrow * 128 + ((chunk ^ lrow) << 4)), rq);
+            }
+            bf[0][0] = (ks & 1) ? rq[2] : rq[0]; bf[0][1] = (ks & 1) ? rq[3] : rq[1];
+          } else {
+            // one ldmatrix.x4 = one k16 step of two 8-token tiles: matrices (nt, half) = (2p, 0), (2p, 1), (2p + 1, 0), (2p + 1, 1)
+#pragma unroll
+            for (int pr = 0; pr < NT / 2; ++pr) {
+              const int row = (2 * pr + (lmat >> 1)) * 8 + lrow, chunk = 2 * ks + (lmat & 1);
+              uint32_t r[4];
+              w4m_ldsm_x4(xs + (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)), r);
+              bf[2 * pr][0] = r[0]; bf[2 * pr][1] = r[1]; bf[2 * pr + 1][0] = r[2]; bf[2 * pr + 1][1] = r[3];
+            }
+          }
+#pragma unroll
+          for (int mi = 0; mi < 2; ++mi) {
+            const uint32_t w = ks == 0 ? wv[mi].x : ks == 1 ? wv[mi].y : ks == 2 ? wv[mi].z : wv[mi].w;
+            uint32_t a[4];
+            a[0] = MagicM<T>::cvt(w & 0x000F000Fu, bA[mi], sA[mi]);
+            a[1] = MagicM<T>::cvt((w >> 4) & 0x000F000Fu, bB[mi], sB[mi]);
+            a[2] = MagicM<T>::cvt((w >> 8) & 0x000F000Fu, bA[mi], sA[mi]);
+            a[3] = MagicM<T>::cvt((w >> 12) & 0x000F000Fu, bB[mi], sB[mi]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) w4m_mma<T>(acc[mi][nt], a, bf[nt][0], bf[nt][1]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {            // every word of both slots has been consumed into registers by all lanes of this warp
+          mbar_arrive(&w_empty[s]);
+          mbar_arrive(&x_empty[sx]);
+        }
+        if (++s == SW) { s = 0; ph ^= 1u; }
+        if (++sx == SX) { sx = 0; phx ^= 1u; }
+      }
+      // ---- the unit's fp32 partial: c0/c1 = (row g, tokens 2t, 2t+1), c2/c3 = (row g + 8, same tokens)
+      float* dst = p.out + (long long)split * p.t * p.n;
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const long long f = (long long)tile * kTileN + (warp * 2 + mi) * 16 + g;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const long long tk = nt * 8 + 2 * tq;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const long long ff = f + (j >> 1) * 8, tt = tk + (j & 1);
+            if (tt < p.t && ff < p.n) dst[tt * p.n + ff] = kb1 > kb0 ? acc[mi][nt][j] : 0.f;
+            acc[mi][nt][j] = 0.f;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int NT>
+int launch_w4m(cts_ctx* ctx, const cts_gemm_w4f_args* a, cudaStream_t stream) {
+  const bool is_bf16 = a->dtype == CTS_BF16;
+  CUtensorMap tm_x;
+  int rc = cts_make_tmap_2d(ctx, &tm_x, a->x, a->t, a->k, a->x_ld, NT * 8, is_bf16);
+  if (rc) return rc;
+  W4mParams p;
+  p.n = a->n; p.k = a->k; p.t = a->t;
+  p.kb_total = (int)(a->k / kBK);
+  p.split_k = a->split_k;
+  p.kb_per_group = a->group_size / kBK;
+  p.n_groups = (int)(a->k / a->group_size);
+  p.tiles = (int)cdiv_ll(a->n, kTileN);
+  p.qw = (const uint8_t*)a->qw; p.szp = (const uint8_t*)a->szp; p.out = a->out;
+  constexpr int kXBytes = NT * 8 * kBK * 2;
+  // two CTAs per SM: the ring of each takes what half the shared memory leaves after the token ring and the static part
+  const int budget = (ctx->max_smem_optin > 0 ? ctx->max_smem_optin : 227 * 1024) / 2 - 3 * 1024;
+  p.stages_x = NT == 4 ? 4 : 8;
+  int sw = (budget - 1024 - p.stages_x * kXBytes) / kStageBytes;
+  if (sw > kMaxStagesW) sw = kMaxStagesW;
+  if (sw < 2) return cts_set_error(ctx, CTS_ERR_BAD_ARG, "cts_gemm_w4_mma: shared memory budget too small");
+  p.stages_w = sw;
+  const size_t smem = (size_t)p.stages_x * kXBytes + (size_t)sw * kStageBytes + 1024;
+  auto kern = gemm_w4_mma_kernel<T, NT>;
+  CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifndef CTS_HOST_SHIM
+  CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+#endif
+  const long long units = (long long)p.tiles * p.split_k;
+  long long grid = 2LL * ctx->sm_count;
+  if (grid > units) grid = units;
+  CTS_CUDA(ctx, launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem, stream, 1, tm_x, p));
+  return CTS_OK;
+}
+
+}  // namespace
+
+// split-K factor of the persistent schedule: units = tiles x split are dealt round-robin to 2 x SMs CTAs; the cost of a choice is the
+// longest CTA's stream in 8 KB stages plus the partial it writes per unit (t KB of fp32 = t / 8 stage equivalents)
+extern "C" int cts_gemm_w4_mma_suggest_split(cts_ctx* ctx, long long n, long long k, long long t) {
+  if (!ctx || n <= 0 || k <= 0) return 1;
+  const long long tiles = cdiv_ll(n, kTileN), kb = k / kBK, ctas = 2LL * ctx->sm_count;
+  long long best = 1;
+  double best_cost = 1e30;
+  for (long long s = 1; s <= 16 && s * 4 <= kb; ++s) {
+    const long long waves = cdiv_ll(tiles * s, ctas);
+    const double cost = (double)waves * ((double)cdiv_ll(kb, s) + (double)(t < 1 ? 1 : t) / 8.0 + 1.0);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return (int)best;
+}
+
+extern "C" int cts_gemm_w4_mma(cts_ctx* ctx, const cts_gemm_w4f_args* a, void* stream) {
+  if (!ctx) return CTS_ERR_BAD_ARG;
+  CTS_CHECK_ARG(ctx, a != nullptr && a->qw && a->szp && a->x && a->out, "null pointer");
+  CTS_CHECK_ARG(ctx, a->n > 0 && a->k > 0 && a->t > 0 && a->t <= 32, "n, k > 0 and 1 <= t <= 32 (decode-sized step; prefill uses the dequantised weight)");
+  CTS_CHECK_ARG(ctx, a->dtype == CTS_BF16 || a->dtype == CTS_F16, "dtype");
+  CTS_CHECK_ARG(ctx, a->k % 64 == 0, "k must be a multiple of 64");
+  CTS_CHECK_ARG(ctx, a->group_size >= 64 && a->group_size % 64 == 0 && a->k % a->group_size == 0, "group_size must be a multiple of 64 dividing k");
+  CTS_CHECK_ARG(ctx, a->split_k >= 1 && a->split_k <= a->k / kBK, "split_k");
+  CTS_CHECK_ARG(ctx, a->x_ld >= a->k, "x_ld smaller than k");
+  CTS_CHECK_ARG(ctx, (((uintptr_t)a->qw | (uintptr_t)a->szp) & 15) == 0, "qw / szp must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a->dtype == CTS_BF16)
+    return a->t <= 8 ? launch_w4m<__nv_bfloat16, 1>(ctx, a, st) : a->t <= 16 ? launch_w4m<__nv_bfloat16, 2>(ctx, a, st) : launch_w4m<__nv_bfloat16, 4>(ctx, a, st);
+  return a->t <= 8 ? launch_w4m<__half, 1>(ctx, a, st) : a->t <= 16 ? launch_w4m<__half, 2>(ctx, a, st) : launch_w4m<__half, 4>(ctx, a, st);
+}

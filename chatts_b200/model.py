@@ -296,8 +296,21 @@ class ChatTSForCausalLM:
             w4["gu"].append(tuple(il(a, b) for a, b in zip(g, u)))
             w4["d"].append(get(p + "mlp.down_proj"))
         c = self.ctx
-        w4["splits"] = dict(qkv=c.gemm_w4_suggest_split(self.wqkv[0].shape[0], self.H), o=c.gemm_w4_suggest_split(self.H, self.nh * self.d),
-                            gu=c.gemm_w4_suggest_split(2 * self.I, self.H), d=c.gemm_w4_suggest_split(self.H, self.I))
+        import os as _os
+        # kernel of the decode step: "mma" (default) = csrc/gemm_w4_mma.cu, the codes dequantised in registers from the fragment-major copy
+        # built here (the row layout is dropped per layer once it is converted); "tc5" = csrc/gemm_w4.cu (tcgen05, bit-identical to the
+        # dense GEMM, no faster than it: kept as the checker)
+        w4["kernel"] = _os.environ.get("CTS_W4_KERNEL", "mma")
+        if w4["kernel"] == "mma":
+            from .weights import repack_w4_mma
+            for kind in ("qkv", "o", "gu", "d"):
+                for l in range(self.L):
+                    qw, sc, zp = w4[kind][l]
+                    w4[kind][l] = repack_w4_mma(qw, sc, zp, gs) + (int(qw.shape[0]),)
+            w4["splits"] = None           # per batch size: _w4_splits
+        else:
+            w4["splits"] = dict(qkv=c.gemm_w4_suggest_split(self.wqkv[0].shape[0], self.H), o=c.gemm_w4_suggest_split(self.H, self.nh * self.d),
+                                gu=c.gemm_w4_suggest_split(2 * self.I, self.H), d=c.gemm_w4_suggest_split(self.H, self.I))
         self.w4 = w4
         self._steps = {}                  # decode states (workspaces, captured graphs) are rebuilt for the new launches
         return self
@@ -348,6 +361,14 @@ class ChatTSForCausalLM:
         return max(sp["qkv"] * T * self.wqkv[0].shape[0] if sp["qkv"] > 1 else 0, sp["o"] * T * self.H if sp["o"] > 1 else 0,
                    sp["gu"] * T * 2 * self.I if T <= 128 else 0, sp["d"] * T * self.H if sp["d"] > 1 else 0, 1)
 
+    def _w4_splits(self, T):
+        """Split-K factors of the four projections for a W4A16 decode step of T tokens."""
+        w4, c = self.w4, self.ctx
+        if w4["splits"] is not None:
+            return w4["splits"]
+        return dict(qkv=c.gemm_w4_mma_suggest_split(self.wqkv[0].shape[0], self.H, T), o=c.gemm_w4_mma_suggest_split(self.H, self.nh * self.d, T),
+                    gu=c.gemm_w4_mma_suggest_split(2 * self.I, self.H, T), d=c.gemm_w4_mma_suggest_split(self.H, self.I, T))
+
     def _layers(self, st, T, attend):
         """Runs every decoder layer on st.h [T,H] in place; leaves RMSNorm_final(h) in st.xn."""
         c, sp, eps = self.ctx, st.splits, self.eps
@@ -360,11 +381,14 @@ class ChatTSForCausalLM:
         # W4A16: decode-sized steps stream the 4-bit codes (every projection through the split-K partial path with the W4 split factors)
         w4 = self.w4 if (self.w4 is not None and T <= 32 and st.k_lin is None and not fused) else None
         if w4 is not None:
-            sp = w4["splits"]
+            sp = self._w4_splits(T)
 
         def proj(kind, l, x, w, split, **kw):
             """fp32 split-K partials of one projection into st.ws: from the packed 4-bit weight when attached, else from the dense one."""
-            if w4 is not None:
+            if w4 is not None and w4["kernel"] == "mma":
+                qwf, szp, n_out = w4[kind][l]
+                c.gemm_w4_mma(x, qwf, szp, n_out, w4["group_size"], st.ws, split, t=T)
+            elif w4 is not None:
                 qw, sc, zp = w4[kind][l]
                 c.gemm_w4(x, qw, sc, zp, w4["group_size"], st.ws, split, t=T)
             else:
@@ -492,8 +516,8 @@ class ChatTSForCausalLM:
         st.act = torch.empty(T, self.I, device=dev, dtype=dt)
         st.qkv = torch.empty(T, self.wqkv[0].shape[0], device=dev, dtype=dt) if st.splits["qkv"] == 1 else None
         ws_n = max(self._ws_floats(T, st.splits), T * self.H)
-        if decode and self.w4 is not None:            # W4A16 decode: every projection through the partial path with the W4 split factors
-            sp = self.w4["splits"]
+        if decode and self.w4 is not None and T <= 32:   # W4A16 decode: every projection through the partial path with the W4 split factors
+            sp = self._w4_splits(T)
             ws_n = max(ws_n, sp["qkv"] * T * self.wqkv[0].shape[0], sp["o"] * T * self.H, sp["gu"] * T * 2 * self.I, sp["d"] * T * self.H)
         if decode and self.use_native_step:          # cts_decoder_step always takes the split-K partial path (also at factor 1)
             sp = st.splits

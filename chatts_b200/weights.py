@@ -163,6 +163,51 @@ def dequantize_w4(qw, sc, zp, group_size=128):
     return w.to(sc.dtype)
 
 
+def _w4_codes(qw):
+    """[out, in] integer codes of the row layout repack_gptq_w4 writes."""
+    n_out, half = qw.shape
+    b = qw.view(n_out, half // 4, 4).to(torch.int64)
+    word = b[:, :, 0] | (b[:, :, 1] << 8) | (b[:, :, 2] << 16) | (b[:, :, 3] << 24)
+    return torch.stack([(word >> (4 * nib)) & 0xF for nib in W4_NIBBLE_OF_K], dim=-1).reshape(n_out, half * 2)
+
+
+W4_MMA_TILE = 256          # features per chunk of the fragment-major layout (csrc/gemm_w4_mma.cu: kTileN)
+
+
+def repack_w4_mma(qw, sc, zp, group_size=128):
+    """Row layout (repack_gptq_w4: qw uint8 [out, in/2], sc [out, groups], zp uint8 [out, groups]) -> the fragment-major layout the
+    register-operand W4A16 kernel streams (include/chatts_b200.h: cts_gemm_w4f_args):
+         qwf uint8 [ceil(out/256) * in/64 * 8192]  chunk (tile, kb) = 16 m-tiles x 32 lanes x 4 words; word (m, lane = 4 g + t, ks) holds the codes of
+                                                   rows {g, g+8} of m-tile m at k = 64 kb + 16 ks + {2t, 2t+1, 2t+8, 2t+9}: nibble i < 4 is the
+                                                   LOWER k of fragment register a_i (a_0: row g, k 2t; a_1: row g+8, k 2t; a_2: row g, k 2t+8;
+                                                   a_3: row g+8, k 2t+8), nibble i + 4 the upper one
+         szp int32 [ceil(out/256), groups, 256]    scale bits | (magic + zp) << 16  (magic: bf16 0x4300 = 128.0, fp16 0x6400 = 1024.0)
+       Features beyond `out` are zero (scale 0)."""
+    q = _w4_codes(qw)                                              # [out, in]
+    n_out, n_in = q.shape
+    assert n_in % 64 == 0 and n_in % int(group_size) == 0
+    tiles = -(-n_out // W4_MMA_TILE)
+    pad = tiles * W4_MMA_TILE - n_out
+    if pad:
+        q = torch.cat([q, torch.zeros(pad, n_in, dtype=q.dtype, device=q.device)], 0)
+    # feature n = 256 tile + 16 m + 8 hi_row + g ; k = 64 kb + 16 ks + 8 k_hi + 2 t + k_odd
+    v = q.view(tiles, 16, 2, 8, n_in // 64, 4, 2, 4, 2)            # [tile, m, hi_row, g, kb, ks, k_hi, t, k_odd]
+    v = v.permute(0, 4, 1, 3, 7, 5, 8, 6, 2).contiguous()          # [tile, kb, m, g, t, ks, k_odd, k_hi, hi_row]: nibble = 4 k_odd + 2 k_hi + hi_row
+    v = v.view(tiles, n_in // 64, 16, 32, 4, 8)
+    word = torch.zeros(v.shape[:-1], dtype=torch.int64, device=q.device)
+    for nib in range(8):
+        word |= v[..., nib] << (4 * nib)
+    qwf = torch.stack([(word >> (8 * b)) & 0xFF for b in range(4)], dim=-1).to(torch.uint8).reshape(-1).contiguous()
+    magic = 0x4300 if sc.dtype == torch.bfloat16 else 0x6400
+    sbits = sc.contiguous().view(torch.int16).to(torch.int64) & 0xFFFF           # [out, groups]
+    pair = sbits | ((zp.to(torch.int64) + magic) << 16)
+    if pad:
+        pair = torch.cat([pair, torch.zeros(pad, pair.shape[1], dtype=pair.dtype, device=pair.device)], 0)
+    pair = pair.view(tiles, W4_MMA_TILE, -1).permute(0, 2, 1).contiguous()      # [tile, group, 256]
+    pair = torch.where(pair >= (1 << 31), pair - (1 << 32), pair).to(torch.int32)
+    return qwf, pair
+
+
 def dequantize_gptq(sd, quant_cfg=None, dtype=torch.bfloat16, scale_dtype=None):
     """Replace every ``<name>.{qweight,qzeros,scales[,g_idx]}`` group of a GPTQ checkpoint by ``<name>.weight``."""
     quant_cfg = quant_cfg or {}

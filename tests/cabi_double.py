@@ -293,6 +293,31 @@ class TorchDouble:
         w = dequantize_w4(qw, scales, zeros, group_size)
         self.gemm(x, w, out, epilogue=3, split_k=split_k, t=t)
 
+    def gemm_w4_mma_suggest_split(self, n, k, t=1): return self.split if k >= 128 * self.split else 1
+    def gemm_w4_mma(self, x, qwf, szp, n, group_size, out, split_k, t=None):
+        """The fragment-major layout decoded back to a dense weight (the inverse of weights.py:repack_w4_mma, written independently)."""
+        k = szp.shape[1] * int(group_size)
+        tiles = szp.shape[0]
+        b = qwf.view(tiles, k // 64, 16, 32, 4, 4).to(torch.int64)
+        word = b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16) | (b[..., 3] << 24)           # [tile, kb, m, lane, ks]
+        q = torch.zeros(tiles * 256, k, dtype=torch.int64)
+        for m in range(16):
+            for lane in range(32):
+                g, tq = lane >> 2, lane & 3
+                for nib in range(8):
+                    row = m * 16 + g + 8 * (nib & 1)
+                    kk = 2 * tq + 8 * ((nib >> 1) & 1) + (nib >> 2)
+                    v = (word[:, :, m, lane, :] >> (4 * nib)) & 0xF                         # [tile, kb, ks]
+                    for ks in range(4):
+                        q.view(tiles, 256, k // 64, 64)[:, row, :, 16 * ks + kk] = v[:, :, ks]
+        u = szp.to(torch.int64) & 0xFFFFFFFF                                                   # [tile, group, 256]
+        sc = (u & 0xFFFF).to(torch.int16).view(x.dtype).permute(0, 2, 1).reshape(tiles * 256, -1)
+        magic = 0x4300 if x.dtype == torch.bfloat16 else 0x6400
+        zp = ((u >> 16) - magic).permute(0, 2, 1).reshape(tiles * 256, -1)
+        grp = torch.arange(k) // int(group_size)
+        w = (sc.to(torch.float32)[:, grp] * (q - zp[:, grp]).to(torch.float32)).to(x.dtype)[:n]
+        self.gemm(x, w, out, epilogue=3, split_k=split_k, t=t)
+
     # ------------------------------------------------------------------ repetition penalty (csrc/sampling.cu)
     def rep_penalty_mark(self, tokens, rows, seen, vocab):
         tk = tokens.reshape(-1).tolist()

@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "chatts_b200", "csrc")
-SOURCES = ["sampling.cu", "train_elementwise.cu", "allreduce_ll.cu", "attention_bwd.cu", "gemm_decode_fused.cu", "gemm_tcgen05.cu", "attention_bwd_tc5.cu", "lora_wgrad_mma.cu", "attention.cu", "elementwise.cu", "ts_frontend.cu", "decoder_step.cu", "allreduce.cu", "ts_encoder_fused.cu", "gemm_w4.cu"]
+SOURCES = ["sampling.cu", "train_elementwise.cu", "allreduce_ll.cu", "attention_bwd.cu", "gemm_decode_fused.cu", "gemm_tcgen05.cu", "attention_bwd_tc5.cu", "lora_wgrad_mma.cu", "attention.cu", "elementwise.cu", "ts_frontend.cu", "decoder_step.cu", "allreduce.cu", "ts_encoder_fused.cu", "gemm_w4.cu", "gemm_w4_mma.cu"]
 OUT = os.path.join(HERE, "_build", "libchatts_shim.so")
 # Files that are GPU-validated are not edited for the shim's sake (not even a spelling): their two non-portable spellings are replaced
 # in the COPY.  Everything else in the copy is the product source, byte for byte.
@@ -59,6 +59,16 @@ SUBSTITUTIONS = {
          "{ const volatile float* s_ = reinterpret_cast<const volatile float*>(src); a = s_[0]; c = s_[1]; }"),
         ("    ss_cta = v;\n  }\n  cluster.sync();", "    ss_cta = v;\n    shim_publish_static(&ss_cta);\n  }\n  cluster.sync();"),
         ("*cluster.map_shared_rank(&ss_cta, r)", "*(float*)shim_static_peer((unsigned)r)"),
+    ],
+    "gemm_w4_mma.cu": [
+        ('''asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));''', "shim_ldmatrix_x4(addr, r, false);"),
+        ('''asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));''',
+         "shim_mma_m16n8k16(c, a, b0, b1, true);"),
+        ('''asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));''',
+         "shim_mma_m16n8k16(c, a, b0, b1, false);"),
     ],
     "attention_bwd_tc5.cu": [("extern __shared__ uint8_t dq_raw[];", "uint8_t* dq_raw = g_dyn_smem;"),
                              ("extern __shared__ uint8_t dkv_raw[];", "uint8_t* dkv_raw = g_dyn_smem;")],

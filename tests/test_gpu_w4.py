@@ -40,6 +40,32 @@ def test_w4_partials_bit_identical_to_the_dense_gemm(n, k, gs, t, split, dtype):
     assert same
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,k,gs,t,split", [(256, 512, 128, 1, 1), (256, 512, 128, 5, 2), (384, 1024, 128, 17, 3), (128, 256, 64, 32, 4),
+                                            (200, 768, 128, 8, 2), (1024, 2560, 128, 32, 7), (7168, 5120, 128, 32, 5), (5120, 13824, 128, 1, 11),
+                                            (256, 5120, 128, 9, 1), (27648, 5120, 128, 32, 2), (27648, 5120, 128, 3, 8), (5120, 13824, 256, 16, 7),
+                                            (528, 1536, 64, 24, 3)])
+def test_w4_mma_partials_match_the_dense_gemm(n, k, gs, t, split, dtype):
+    """cts_gemm_w4_mma (registers + mma.sync, persistent CTAs over (tile, split) units, every ring slot reused many times at the big
+    shapes): the same 16-bit operand values as the dense copy, so each fp32 split-K partial may differ from cts_gemm's only by the
+    summation order -- bound 2e-5 of the partial's largest magnitude (measured: a few 1e-7)."""
+    from chatts_b200.weights import repack_w4_mma
+    c = ctx()
+    qw, sc, zp, w = _rand_w4(n, k, gs, dtype, seed=n + k + t)
+    qwf, szp = repack_w4_mma(qw, sc, zp, gs)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(t, k, generator=g) * 0.5).to(dtype).cuda()
+    ref = torch.full((split, t, n), float("nan"), device="cuda")
+    got = torch.full((split, t, n), float("nan"), device="cuda")
+    c.gemm(x, w.cuda(), ref, epilogue=EPI_PARTIAL, split_k=split, t=t)
+    c.gemm_w4_mma(x, qwf.cuda(), szp.cuda(), n, gs, got, split, t=t)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(got).all())
+    err = float((got - ref).abs().max() / ref.abs().max())
+    record("gemm_w4_mma", n=n, k=k, t=t, split=split, dtype=str(dtype), rel_err=err)
+    assert err <= 2e-5
+
+
 def test_w4_suggested_split_keeps_the_group_table_in_range():
     c = ctx()
     for n, k in ((7168, 5120), (5120, 5120), (27648, 5120), (5120, 13824), (256, 256)):
@@ -48,13 +74,15 @@ def test_w4_suggested_split_keeps_the_group_table_in_range():
         assert 1 <= s <= 16 and blocks * 64 // 128 + 2 <= 44
 
 
+@pytest.mark.parametrize("kernel", ["mma", "tc5"])
 @pytest.mark.parametrize("qwen3", [False, True])
-def test_model_decodes_through_the_packed_weights(qwen3):
+def test_model_decodes_through_the_packed_weights(qwen3, kernel, monkeypatch):
     """quantize_w4_synthetic: dense weights = the dequantised values, packed copy attached; the decode step through cts_gemm_w4 (its own
     split factors) must pick the tokens the dense decode picks (same weights; fp32 summation order differs with the split)."""
     from chatts_b200 import ChatTSConfig, ChatTSProcessor, SimpleTokenizer
     from chatts_b200.model import ChatTSForCausalLM
     from chatts_b200.weights import synthetic_state_dict
+    monkeypatch.setenv("CTS_W4_KERNEL", kernel)
     cfg = ChatTSConfig.tiny(intermediate_size=768)
     if qwen3:
         cfg.qk_norm, cfg.attention_bias = True, False
@@ -66,10 +94,10 @@ def test_model_decodes_through_the_packed_weights(qwen3):
     enc = proc(text=["A <ts><ts/> ?", "text only, a longer prompt"], timeseries=[np.sin(x / 9) * 4], padding=True, return_tensors="pt")
     l0 = model.ctx.launches
     a = model.generate(**enc, max_new_tokens=16, ignore_eos=True)
-    assert model.w4 is not None and model.ctx.launches > l0
+    assert model.w4 is not None and model.w4["kernel"] == kernel and model.ctx.launches > l0
     w4, model.w4, model._steps = model.w4, None, {}
     b = model.generate(**enc, max_new_tokens=16, ignore_eos=True)
     S = enc["input_ids"].shape[1]
     agree = [int(next((i for i in range(16) if a[r, S + i] != b[r, S + i]), 16)) for r in range(2)]
-    record("w4_model_decode", qwen3=int(qwen3), greedy_agreement=str(agree))
+    record("w4_model_decode", qwen3=int(qwen3), kernel=kernel, greedy_agreement=str(agree))
     assert min(agree) >= 12          # same weights; only the K partition of the fp32 sums differs

@@ -48,8 +48,10 @@ def _gptq_checkpoint(tmp_path, cfg, sd, act_order=False):
     return str(d)
 
 
-def test_gptq_checkpoint_decodes_through_the_packed_weights(cabi_double, tmp_path, monkeypatch):
+@pytest.mark.parametrize("kernel", ["mma", "tc5"])
+def test_gptq_checkpoint_decodes_through_the_packed_weights(cabi_double, tmp_path, monkeypatch, kernel):
     from chatts_b200.model import ChatTSForCausalLM
+    monkeypatch.setenv("CTS_W4_KERNEL", kernel)
     cfg, sd, _, proc = _build(cabi_double)
     cfg.intermediate_size = 704
     path = _gptq_checkpoint(tmp_path, cfg, sd)
@@ -61,8 +63,9 @@ def test_gptq_checkpoint_decodes_through_the_packed_weights(cabi_double, tmp_pat
     assert md.w4 is None
     enc = proc(text=["A <ts><ts/> and B <ts><ts/> ?", "text only"], timeseries=list(_series()), padding=True, return_tensors="pt")
     calls = []
-    orig = cabi_double.gemm_w4
-    monkeypatch.setattr(cabi_double, "gemm_w4", lambda *a, **k: (calls.append(1), orig(*a, **k))[1])
+    entry = "gemm_w4_mma" if kernel == "mma" else "gemm_w4"
+    orig = getattr(cabi_double, entry)
+    monkeypatch.setattr(cabi_double, entry, lambda *a, **k: (calls.append(1), orig(*a, **k))[1])
     a = m4.generate(**enc, max_new_tokens=10, ignore_eos=True)
     assert len(calls) == 4 * cfg.num_hidden_layers * 9          # every projection of every decode step (9 steps after the prefill token)
     # the dense weights of the W4 model are the dequantised values the kernel uses: decoding through them gives the same tokens
@@ -84,3 +87,23 @@ def test_attach_w4_rejects_tensor_parallel_models(cabi_double):
     model.tp_size = 2
     with pytest.raises(ValueError):
         model.attach_w4({}, 128)
+
+
+def test_fragment_major_repack_round_trips(cabi_double):
+    """weights.py:repack_w4_mma against the independent inverse of tests/cabi_double.py (the layout include/chatts_b200.h states for
+    cts_gemm_w4f_args): the decoded dense weight equals dequantize_w4 of the row layout, for a feature count that needs padding."""
+    from chatts_b200.weights import dequantize_w4, repack_w4_mma
+    g = torch.Generator().manual_seed(11)
+    for dt in (torch.bfloat16, torch.float16):
+        for n, k, gs in ((200, 256, 64), (512, 384, 128)):
+            qw = torch.randint(0, 256, (n, k // 2), generator=g, dtype=torch.uint8)
+            sc = ((torch.rand(n, k // gs, generator=g) + 0.5) * 0.01).to(dt)
+            zp = torch.randint(0, 17, (n, k // gs), generator=g, dtype=torch.uint8)
+            qwf, szp = repack_w4_mma(qw, sc, zp, gs)
+            tiles = -(-n // 256)
+            assert qwf.shape == (tiles * (k // 64) * 8192,) and szp.shape == (tiles, k // gs, 256) and szp.dtype == torch.int32
+            x = torch.eye(k, dtype=dt)[:32]                               # the first 32 unit vectors: out[t] = column t of W
+            out = torch.zeros(1, 32, n)
+            cabi_double.gemm_w4_mma(x, qwf, szp, n, gs, out, 1, t=32)
+            want = dequantize_w4(qw, sc, zp, gs).float()[:, :32].t()
+            assert torch.equal(out[0], want)

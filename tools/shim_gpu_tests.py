@@ -112,6 +112,7 @@ SELECT = {
     "test_gpu_model.py": "not full_size",                # calibration: the whole model (prefill, paged decode, generate, LoRA merge ...) from kernel source
     "test_gpu_attention.py": None,                       # calibration: tcgen05 prefill attention (MN-major V operand), HMMA prefill, TMA paged decode (ldmatrix / mma.sync)
     "test_gpu_zz_d_attn_bwd_tc5.py": None,               # tcgen05 attention backward (K-major and MN-major operands, TMEM-resident dQ / dK / dV)
+    "test_gpu_w4.py": "not (27648 or 13824 or 7168)",    # both W4A16 kernels (tcgen05 operand path; registers + mma.sync over the persistent schedule), small shapes
 }
 
 # --quick: a subset that finishes in about a minute (what tests/test_shim_kernels.py runs inside the CPU suite)
