@@ -156,7 +156,7 @@ def make_series(i, k, length=SERIES_LEN):
     return s
 
 
-def make_batch(cfg, batch, seed=0):
+def make_batch(cfg, batch, seed=0, n_series=N_SERIES, series_len=SERIES_LEN):
     """Host-side request batch in the reference's processor output format (input_ids, attention_mask, timeseries)."""
     from chatts_b200.processor import sp_encoding
     rng = np.random.default_rng(seed)
@@ -164,9 +164,9 @@ def make_batch(cfg, batch, seed=0):
     series = []
     for b in range(batch):
         row = []
-        for k in range(N_SERIES):
+        for k in range(n_series):
             row += rng.integers(0, 150000, PREFIX_IDS).tolist() + [cfg.ts_token_start_index, cfg.ts_token_start_index + 1]
-            series.append(sp_encoding(make_series(b, k))[0])
+            series.append(sp_encoding(make_series(b, k, series_len))[0])
         row += rng.integers(0, 150000, PROMPT_IDS).tolist()
         ids.append(row)
     ids = torch.tensor(ids, dtype=torch.long)
@@ -459,6 +459,78 @@ def tp_parity_gate(world, rank, layers=4, batch=8, seed=77):
     return out
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def measure_config4(cfg, rank, world, steps, warmup, sync_all, batch=8, n_series=30, series_len=512):
+    """BASELINE.json configs[3]: batch-8 decode with 30 series x 512 points per prompt (30 x (46 prefix ids + <ts> + 32 patch rows + <ts/>)
+    + 64 prompt ids = 2 464 merged positions), tensor-parallel over however many GPUs the run has (the config names 8).  A second model
+    instance of the same synthetic weights with a 4 096-position cache: the headline model's buffers stay as measured.  Device-timed graph
+    replays as the headline, plus the same public generate() call with pinned host tensors."""
+    import torch.distributed as dist
+    from chatts_b200.model import ChatTSForCausalLM
+    model = ChatTSForCausalLM.from_synthetic(cfg, seed=1234, tp_rank=rank, tp_size=world, max_batch=batch, max_seq_len=4096, page_size=64)
+    enc = make_batch(cfg, batch, seed=4, n_series=n_series, series_len=series_len)
+    max_new = steps + warmup + 8
+    ids_cpu, am_cpu, counts, lay = model._prepare_inputs(enc["input_ids"], enc["attention_mask"], enc["timeseries"])
+    pts, held = model._alloc_pages(lay.lens, max_new)
+    try:
+        sync_all()
+        t0 = time.perf_counter()
+        logits = model._prefill(lay, counts, enc["timeseries"], pts)
+        torch.cuda.synchronize()
+        prefill_s = time.perf_counter() - t0
+        st = model._decode_state(batch, max_new)
+        lens32 = torch.from_numpy(lay.lens.astype(np.int32))
+        st.page_table.copy_(torch.from_numpy(pts)); st.positions.copy_(lens32 - 1); st.seq_lens.copy_(lens32); st.step_ptr.zero_()
+        model.ctx.greedy_advance(logits, batch, st.out_tokens, st.step_ptr, st.cur_ids, st.positions, st.seq_lens, st.slot_map, st.page_table, model.page_size)
+        for _ in range(max(warmup, 3)):
+            model._decode_step(st)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            model._decode_step(st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        n_tok = int(st.step_ptr[0].item())
+        import hashlib
+        toks = st.out_tokens[:, :n_tok].to(torch.int32).cpu().numpy()
+        tok_sha = hashlib.sha1(toks.tobytes()).hexdigest()[:16]
+        same = True
+        if world > 1:                                   # every rank must have picked the same tokens
+            tt = torch.from_numpy(toks.astype(np.int64)).cuda()
+            ref = tt.clone()
+            dist.broadcast(ref, src=0)
+            flag = torch.tensor([int(torch.equal(tt, ref))], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            same = bool(int(flag))
+    finally:
+        model.pool.release(held)
+    encp = {k: v.pin_memory() for k, v in enc.items()}
+    model.generate(**encp, max_new_tokens=4, ignore_eos=True, sync_every=1)
+    sync_all()
+    t0 = time.perf_counter()
+    model.generate(**encp, max_new_tokens=steps, ignore_eos=True, sync_every=1)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt)
+    positions = int(lay.lens.max())
+    out = {"workload": f"BASELINE.json configs[3]: batch {batch} decode, {n_series} series x {series_len} points per prompt -> {positions} merged positions, tp{world}",
+           "batch": batch, "context": positions, "n_gpus": world, "steps": steps, "ms_per_step": ms / steps, "tokens_per_s": batch * steps / (ms / 1e3),
+           "prefill_s": prefill_s, "prefill_positions": int(lay.lens.sum()), "tokens_sha1": tok_sha, "identical_tokens_on_all_ranks": same,
+           "e2e": {"value": batch * steps / dt, "unit": "tokens/s", "seconds": dt,
+                   "definition": f"model.generate(**pinned_host_tensors, max_new_tokens={steps}, sync_every=1): H2D, TS encode of {batch * n_series} series, prefill, {steps} decode steps with per-step D2H"}}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     from chatts_b200 import ChatTSConfig, _cabi
@@ -687,6 +759,14 @@ def run_b200(args):
                              f"{args.batch}x576 positions and {new} decode steps with per-step D2H of the new ids; value = B*new/wall",
                "seconds": dt, "out_shape": list(out.shape)}
 
+    # ---- BASELINE.json configs[3] (batch-8 decode, 30 series x 512 points) on this run's GPUs: a side block, never fatal for the headline
+    config4 = None
+    if not args.sweep_only and not args.layers and not args.no_config4:
+        try:
+            config4 = measure_config4(cfg, rank, world, args.steps, args.warmup, sync_all)
+        except Exception as e:  # pragma: no cover
+            config4 = {"error": repr(e)[:300]}              # shape / capacity errors are the same on every rank: all of them land here
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -701,6 +781,7 @@ def run_b200(args):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(main["launches"] * args.steps), "launches_per_step": main["launches"],
                 "roofline": roof, "ts_encoder": ts_roof, "attention": attn_roof, "cpu_baseline": cpu, "arch": ctx.arch, "lib": os.path.relpath(_cabi.LIB_PATH, ROOT)}
         # which opt-in variants of the decode path this line was measured with (all off = the validated default path)
+        line["config4"] = config4
         line["tokens_sha1"] = main.get("tokens_sha1")          # hash of every greedy token the measured batch produced (probe: equality across variants)
         if probe_record is not None:
             line["config"]["decode_variant_probe"] = probe_record
@@ -730,6 +811,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run decode steps eagerly (for ncu launch lists)")
     ap.add_argument("--sweep-only", action="store_true", help="decode timing only (skip e2e)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE configs[3] side block (second model instance, 30 x 512-point prompts)")
     ap.add_argument("--no-probe", action="store_true", help="(default) the default decode path is measured as is")
     ap.add_argument("--probe", action="store_true", help="guarded child-process probe of the cluster-fused decode variants (round 1; measured slower at b = 32 on a B200, "
                                                         "profiles/r2_decode_variants_ab.txt, so no longer on by default)")

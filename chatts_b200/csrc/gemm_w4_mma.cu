@@ -46,23 +46,41 @@ struct W4mParams {
 template <typename T> struct MagicM;
 template <> struct MagicM<__nv_bfloat16> {
   static constexpr uint32_t kOr = 0x43004300u;                       // bf16 128.0 in both halves: 128 + code (ulp 1 in [128, 256))
-  static __device__ __forceinline__ uint32_t cvt(uint32_t codes, uint32_t b2, uint32_t s2) {
-    const uint32_t y = codes | kOr;
-    __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&y), *reinterpret_cast<const __nv_bfloat162*>(&b2));   // exact small ints
-    __nv_bfloat162 w = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&s2));                                              // one rounding
+  // y = the pair 128 + code; (y - (128 + zp)) is an exact small integer, times the scale = ONE rounding = dequantize_w4's value
+  static __device__ __forceinline__ uint32_t sub_mul(uint32_t y, uint32_t b2, uint32_t s2) {
+    __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&y), *reinterpret_cast<const __nv_bfloat162*>(&b2));
+    __nv_bfloat162 w = __hmul2(d, *reinterpret_cast<const __nv_bfloat162*>(&s2));
     return *reinterpret_cast<uint32_t*>(&w);
   }
 };
 template <> struct MagicM<__half> {
   static constexpr uint32_t kOr = 0x64006400u;                       // fp16 1024.0: 1024 + code
-  static __device__ __forceinline__ uint32_t cvt(uint32_t codes, uint32_t b2, uint32_t s2) {
-    const uint32_t y = codes | kOr;
+  static __device__ __forceinline__ uint32_t sub_mul(uint32_t y, uint32_t b2, uint32_t s2) {
     __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&y), *reinterpret_cast<const __half2*>(&b2));
     __half2 w = __hmul2(d, *reinterpret_cast<const __half2*>(&s2));
     return *reinterpret_cast<uint32_t*>(&w);
   }
 };
 
+// a constant the compiler must keep in a register (so that (w & mask) | magic is ONE lop3 with three register operands)
+__device__ __forceinline__ uint32_t w4m_opaque(uint32_t v) {
+#ifndef CTS_HOST_SHIM
+  uint32_t r;
+  asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+#else
+  return v;
+#endif
+}
+__device__ __forceinline__ uint32_t w4m_and_or(uint32_t a, uint32_t m, uint32_t k) {
+#ifndef CTS_HOST_SHIM
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(m), "r"(k));       // (a & m) | k
+  return d;
+#else
+  return (a & m) | k;
+#endif
+}
 __device__ __forceinline__ void w4m_ldsm_x4(uint32_t addr, uint32_t* r) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -161,6 +179,10 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
     }
   } else {
     // ------------------------------ dequantise in registers + mma.sync ------------------------------
+    // The loop below is instruction-issue bound (ncu of the first version: 363 SASS instructions per stage and warp, 56 % issue-active,
+    // the 4-bit stream at 36 % of the HBM roof), so everything that does not depend on the stage is hoisted: the lane's offsets into
+    // the weight chunk / the scale table / the swizzled token tile, the mask and magic constants as REGISTER operands of one lop3
+    // ((w & mask) | magic; with immediates the compiler needs two), ring addresses advanced by addition.
     const int g = lane >> 2, tq = lane & 3;
     const int lrow = lane & 7, lmat = lane >> 3;             // ldmatrix: this lane supplies row `lrow` of matrix `lmat`
     float acc[2][NT][4];
@@ -171,49 +193,56 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[mi][nt][j] = 0.f;
     uint32_t sA[2] = {0, 0}, bA[2] = {0, 0}, sB[2] = {0, 0}, bB[2] = {0, 0};   // {scale, magic + zp} of rows g / g + 8 of the two m-tiles
+    const uint32_t kMask = w4m_opaque(0x000F000Fu), kMagic = w4m_opaque(MagicM<T>::kOr);
+    const uint32_t w_off = (uint32_t)((warp * 2 * 32 + lane) * 16);           // this lane's word quadruple of m-tile 2 warp (+ 512: m-tile 2 warp + 1)
+    const uint32_t sz_off = (uint32_t)(kWBytes + (warp * 2 * 16 + g) * 4);
+    // ldmatrix row addresses inside a token tile for k16 step 0; step ks: XOR with ks << 5 (the chunk index 2 ks + h enters the 128B swizzle by XOR)
+    uint32_t x_off[NT == 1 ? 1 : NT / 2];
+    if constexpr (NT == 1) {
+      x_off[0] = (uint32_t)(lrow * 128 + (((2 * (lmat >> 1) + (lmat & 1)) ^ lrow) << 4));          // matrices (ks, half) = (0,0), (0,1), (1,0), (1,1); pair q: XOR q << 6
+    } else {
+#pragma unroll
+      for (int pr = 0; pr < NT / 2; ++pr) x_off[pr] = (uint32_t)(((2 * pr + (lmat >> 1)) * 8 + lrow) * 128 + (((lmat & 1) ^ lrow) << 4));
+    }
     int s = 0, sx = 0;
     uint32_t ph = 0u, phx = 0u;                              // parities of the "slot is full" phases
+    const uint8_t* ws = w_s;                                 // slot s of the weight ring
+    uint32_t xs = smem_u32(x_s);                             // slot sx of the token ring
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       int tile, split, kb0, kb1;
       w4m_unit(p, u, tile, split, kb0, kb1);
-      int in_grp = 0;                                        // 0 -> this block starts a group (or the unit): fetch its scales / zero points
+      int in_grp = kb0 % p.kb_per_group;                     // blocks of the current group already behind kb; the unit's first block always fetches
+      bool fetch = true;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&w_full[s], ph);
-        const uint8_t* ws = w_s + (size_t)s * kStageBytes;
         uint4 wv[2];
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi) wv[mi] = *reinterpret_cast<const uint4*>(ws + (size_t)(((warp * 2 + mi) * 32 + lane) * 16));
-        if (in_grp == 0) {
-          in_grp = p.kb_per_group - (kb == kb0 ? kb0 % p.kb_per_group : 0);
-          const uint32_t* sz = reinterpret_cast<const uint32_t*>(ws + kWBytes);
+        wv[0] = *reinterpret_cast<const uint4*>(ws + w_off);
+        wv[1] = *reinterpret_cast<const uint4*>(ws + w_off + 512);
+        if (fetch) {
+          const uint8_t* sz = ws + sz_off;
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
-            const uint32_t va = sz[(warp * 2 + mi) * 16 + g], vb = sz[(warp * 2 + mi) * 16 + g + 8];
+            const uint32_t va = *reinterpret_cast<const uint32_t*>(sz + mi * 64), vb = *reinterpret_cast<const uint32_t*>(sz + mi * 64 + 32);
             sA[mi] = (va & 0xFFFFu) * 0x00010001u; bA[mi] = (va >> 16) * 0x00010001u;      // both halves of a packed pair
             sB[mi] = (vb & 0xFFFFu) * 0x00010001u; bB[mi] = (vb >> 16) * 0x00010001u;
           }
         }
-        --in_grp;
+        fetch = (++in_grp == p.kb_per_group);
+        if (fetch) in_grp = 0;
         mbar_wait(&x_full[sx], phx);
-        const uint32_t xs = smem_u32(x_s + (size_t)sx * kXBytes);
         uint32_t rq[4] = {0u, 0u, 0u, 0u};                    // NT == 1: the fragments of a pair of k16 steps
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           uint32_t bf[NT][2];                                 // B fragments of this k16 step
           if constexpr (NT == 1) {
-            // one ldmatrix.x4 = two k16 steps of the single 8-token tile: matrices (ks, half) = (2q, 0), (2q, 1), (2q + 1, 0), (2q + 1, 1)
-            if ((ks & 1) == 0) {
-              const int chunk = 2 * (ks + (lmat >> 1)) + (lmat & 1);
-              w4m_ldsm_x4(xs + (uint32_t)(lrow * 128 + ((chunk ^ lrow) << 4)), rq);
-            }
+            if ((ks & 1) == 0) w4m_ldsm_x4((xs + x_off[0]) ^ (uint32_t)((ks >> 1) << 6), rq);
             bf[0][0] = (ks & 1) ? rq[2] : rq[0]; bf[0][1] = (ks & 1) ? rq[3] : rq[1];
           } else {
             // one ldmatrix.x4 = one k16 step of two 8-token tiles: matrices (nt, half) = (2p, 0), (2p, 1), (2p + 1, 0), (2p + 1, 1)
 #pragma unroll
             for (int pr = 0; pr < NT / 2; ++pr) {
-              const int row = (2 * pr + (lmat >> 1)) * 8 + lrow, chunk = 2 * ks + (lmat & 1);
               uint32_t r[4];
-              w4m_ldsm_x4(xs + (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)), r);
+              w4m_ldsm_x4((xs + x_off[pr]) ^ (uint32_t)(ks << 5), r);
               bf[2 * pr][0] = r[0]; bf[2 * pr][1] = r[1]; bf[2 * pr + 1][0] = r[2]; bf[2 * pr + 1][1] = r[3];
             }
           }
@@ -221,10 +250,10 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
           for (int mi = 0; mi < 2; ++mi) {
             const uint32_t w = ks == 0 ? wv[mi].x : ks == 1 ? wv[mi].y : ks == 2 ? wv[mi].z : wv[mi].w;
             uint32_t a[4];
-            a[0] = MagicM<T>::cvt(w & 0x000F000Fu, bA[mi], sA[mi]);
-            a[1] = MagicM<T>::cvt((w >> 4) & 0x000F000Fu, bB[mi], sB[mi]);
-            a[2] = MagicM<T>::cvt((w >> 8) & 0x000F000Fu, bA[mi], sA[mi]);
-            a[3] = MagicM<T>::cvt((w >> 12) & 0x000F000Fu, bB[mi], sB[mi]);
+            a[0] = MagicM<T>::sub_mul(w4m_and_or(w, kMask, kMagic), bA[mi], sA[mi]);
+            a[1] = MagicM<T>::sub_mul(w4m_and_or(w >> 4, kMask, kMagic), bB[mi], sB[mi]);
+            a[2] = MagicM<T>::sub_mul(w4m_and_or(w >> 8, kMask, kMagic), bA[mi], sA[mi]);
+            a[3] = MagicM<T>::sub_mul(w4m_and_or(w >> 12, kMask, kMagic), bB[mi], sB[mi]);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) w4m_mma<T>(acc[mi][nt], a, bf[nt][0], bf[nt][1]);
           }
@@ -234,8 +263,9 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
           mbar_arrive(&w_empty[s]);
           mbar_arrive(&x_empty[sx]);
         }
-        if (++s == SW) { s = 0; ph ^= 1u; }
-        if (++sx == SX) { sx = 0; phx ^= 1u; }
+        ws += kStageBytes; xs += (uint32_t)kXBytes;
+        if (++s == SW) { s = 0; ph ^= 1u; ws = w_s; }
+        if (++sx == SX) { sx = 0; phx ^= 1u; xs = smem_u32(x_s); }
       }
       // ---- the unit's fp32 partial: c0/c1 = (row g, tokens 2t, 2t+1), c2/c3 = (row g + 8, same tokens)
       float* dst = p.out + (long long)split * p.t * p.n;
