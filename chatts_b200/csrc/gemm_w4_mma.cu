@@ -8,7 +8,7 @@
 //     words ARE the A fragments of mma.sync.m16n8k16 -- lane (g, t) of m-tile j finds, for each of the block's four k16 steps, one
 //     word holding the 8 codes {rows g / g+8} x {k 2t, 2t+1, 2t+8, 2t+9} in the nibble order that `(w >> 4i) & 0x000F000F` turns
 //     into fragment register a_i; next to it 1 KB of {scale, 128+zero-point} pairs of the block's group
-//   * warp 8, one lane: cp.async.bulk of those chunks into a deep ring (10-11 x 9 KB per CTA, two CTAs per SM = what keeps HBM busy),
+//   * warp 8, one lane: cp.async.bulk of those chunks into a deep ring (7-11 x 9 KB per CTA, two or three CTAs per SM = what keeps HBM busy),
 //     issued BEFORE the dependency wait (nobody writes weights); warp 9, one lane: the token tile [8 NT rows x 64 K] by TMA (128B
 //     swizzle) after the wait
 //   * warps 0..7: one LDS.128 per m-tile = the fragments of four k16 steps; int4 -> bf16/fp16 in registers with the magic-number trick
@@ -114,7 +114,7 @@ __device__ __forceinline__ void w4m_unit(const W4mParams& p, int u, int& tile, i
 }
 
 template <typename T, int NT>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, NT == 1 ? 3 : 2)
 gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) {
   CTS_DYN_SMEM(smem_raw);
   __shared__ uint64_t w_full[kMaxStagesW], w_empty[kMaxStagesW], x_full[kMaxStagesX], x_empty[kMaxStagesX];
@@ -302,8 +302,10 @@ int launch_w4m(cts_ctx* ctx, const cts_gemm_w4f_args* a, cudaStream_t stream) {
   p.tiles = (int)cdiv_ll(a->n, kTileN);
   p.qw = (const uint8_t*)a->qw; p.szp = (const uint8_t*)a->szp; p.out = a->out;
   constexpr int kXBytes = NT * 8 * kBK * 2;
-  // two CTAs per SM: the ring of each takes what half the shared memory leaves after the token ring and the static part
-  const int budget = (ctx->max_smem_optin > 0 ? ctx->max_smem_optin : 227 * 1024) / 2 - 3 * 1024;
+  // CTAs per SM (kCtasPerSm: three of the 64-register NT = 1 kernel, else two): the ring of each takes what its share of the shared
+  // memory leaves after the token ring and the static part
+  constexpr int kCtas = NT == 1 ? 3 : 2;
+  const int budget = (ctx->max_smem_optin > 0 ? ctx->max_smem_optin + 1024 : 228 * 1024) / kCtas - 3 * 1024;
   p.stages_x = NT == 4 ? 4 : 8;
   int sw = (budget - 1024 - p.stages_x * kXBytes) / kStageBytes;
   if (sw > kMaxStagesW) sw = kMaxStagesW;
@@ -316,7 +318,7 @@ int launch_w4m(cts_ctx* ctx, const cts_gemm_w4f_args* a, cudaStream_t stream) {
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
 #endif
   const long long units = (long long)p.tiles * p.split_k;
-  long long grid = 2LL * ctx->sm_count;
+  long long grid = (long long)kCtas * ctx->sm_count;
   if (grid > units) grid = units;
   CTS_CUDA(ctx, launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem, stream, 1, tm_x, p));
   return CTS_OK;
@@ -324,11 +326,11 @@ int launch_w4m(cts_ctx* ctx, const cts_gemm_w4f_args* a, cudaStream_t stream) {
 
 }  // namespace
 
-// split-K factor of the persistent schedule: units = tiles x split are dealt round-robin to 2 x SMs CTAs; the cost of a choice is the
+// split-K factor of the persistent schedule: units = tiles x split are dealt round-robin to the resident CTAs (3 per SM for t <= 8, else 2); the cost of a choice is the
 // longest CTA's stream in 8 KB stages plus the partial it writes per unit (t KB of fp32 = t / 8 stage equivalents)
 extern "C" int cts_gemm_w4_mma_suggest_split(cts_ctx* ctx, long long n, long long k, long long t) {
   if (!ctx || n <= 0 || k <= 0) return 1;
-  const long long tiles = cdiv_ll(n, kTileN), kb = k / kBK, ctas = 2LL * ctx->sm_count;
+  const long long tiles = cdiv_ll(n, kTileN), kb = k / kBK, ctas = (t <= 8 ? 3LL : 2LL) * ctx->sm_count;
   long long best = 1;
   double best_cost = 1e30;
   for (long long s = 1; s <= 16 && s * 4 <= kb; ++s) {
