@@ -98,7 +98,7 @@ class GemmW4Args(C.Structure):
 class GemmW4fArgs(C.Structure):
     _fields_ = [("qw", C.c_void_p), ("szp", C.c_void_p), ("x", C.c_void_p), ("out", C.c_void_p),
                 ("n", C.c_longlong), ("k", C.c_longlong), ("t", C.c_longlong), ("x_ld", C.c_longlong),
-                ("group_size", C.c_int), ("split_k", C.c_int), ("dtype", C.c_int), ("flags", C.c_int)]
+                ("group_size", C.c_int), ("split_k", C.c_int), ("dtype", C.c_int), ("reserved", C.c_int)]
 
 
 class TsEncodeArgs(C.Structure):
@@ -337,16 +337,14 @@ class Context:
     def gemm_w4_suggest_split(self, n, k):
         return int(self.lib.cts_gemm_w4_suggest_split(self.h, n, k))
 
-    def gemm_w4_mma(self, x, qwf, szp, n, group_size, out, split_k, t=None, exact=False):
+    def gemm_w4_mma(self, x, qwf, szp, n, group_size, out, split_k, t=None):
         """The same partials with the weight operand dequantised in registers (cts_gemm_w4_mma).  qwf uint8 [ceil(N/256) * K/64 * 8192]
-        fragment-major codes, szp int32 [ceil(N/256), K/g, 256] (weights.py:repack_w4_mma); n = the true number of features.
-        exact: weights rounded to the model dtype as in the dense copy (CTS_W4F_EXACT); default: the unrounded s (q - z) for t <= 16."""
+        fragment-major codes, szp int32 [ceil(N/256), K/g, 256] (weights.py:repack_w4_mma); n = the true number of features."""
         a = GemmW4fArgs()
         a.qw, a.szp, a.x, a.out = qwf.data_ptr(), szp.data_ptr(), x.data_ptr(), out.data_ptr()
         a.n, a.k = int(n), szp.shape[1] * int(group_size)
         a.t = x.shape[0] if t is None else t
         a.x_ld, a.group_size, a.split_k, a.dtype = x.stride(0), int(group_size), int(split_k), dtype_code(x.dtype)
-        a.flags = 1 if exact else 0
         self._chk(self.lib.cts_gemm_w4_mma(self.h, C.byref(a), _stream()))
 
     def gemm_w4_mma_suggest_split(self, n, k, t=1):

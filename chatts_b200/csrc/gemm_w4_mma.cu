@@ -15,6 +15,12 @@
 //     of gemm_w4.cu (exactly the value dequantize_w4 stores for the prefill copy); B fragments by ldmatrix from the swizzled token
 //     tile; mma.sync with the fp32 accumulators of 2 m-tiles x NT n-tiles in registers
 //   * persistent CTAs over (tile, K split) units, the producers run ahead across unit boundaries
+// Measured and rejected (profiles/r2_w4_mma_gemm_sweep_fast.json, git b975740): feeding the MMA the pairs (128 + code) themselves and
+// applying the group's scale / zero point in fp32 once per group and accumulator (no subtraction / multiplication per weight, one more
+// MMA per k16 step with an all-ones A operand for sum_k x_k) removes a quarter of the loop's instructions and is NOT faster (gate_up at
+// t = 1: 26.7 us against 25.8): ncu of either variant shows 57-59 % issue-active with `wait` (fixed-latency dependency) as the top stall
+// and 23 of 64 warp slots filled -- the loop is bound by per-warp dependent-issue latency at the occupancy 64-96 registers allow, not
+// by its instruction count.
 // Output: the fp32 split-K partials [split, t, n] of CTS_EPI_PARTIAL_F32, so the decode step's reduce tails are unchanged.  The A
 // operand holds the same 16-bit values as the dense copy; the fp32 summation order differs from the tcgen05 GEMM (parity is a
 // tolerance, tests/test_gpu_w4.py), unlike gemm_w4.cu which is bit-identical and stays as the checker for this kernel.
@@ -46,10 +52,6 @@ struct W4mParams {
 template <typename T> struct MagicM;
 template <> struct MagicM<__nv_bfloat16> {
   static constexpr uint32_t kOr = 0x43004300u;                       // bf16 128.0 in both halves: 128 + code (ulp 1 in [128, 256))
-  static constexpr uint32_t kOnes = 0x3F803F80u;                     // the pair (1.0, 1.0)
-  static constexpr float kFastBase = 128.f;                          // FAST: the A operand is the pair 128 + code itself
-  static constexpr uint32_t kFastOr = 0x43004300u, kFastMask = 0x000F000Fu;
-  static constexpr int kFastShift = 0;                               // codes sit at bits 0..3 of each half
   // y = the pair 128 + code; (y - (128 + zp)) is an exact small integer, times the scale = ONE rounding = dequantize_w4's value
   static __device__ __forceinline__ uint32_t sub_mul(uint32_t y, uint32_t b2, uint32_t s2) {
     __nv_bfloat162 d = __hsub2(*reinterpret_cast<const __nv_bfloat162*>(&y), *reinterpret_cast<const __nv_bfloat162*>(&b2));
@@ -59,12 +61,6 @@ template <> struct MagicM<__nv_bfloat16> {
 };
 template <> struct MagicM<__half> {
   static constexpr uint32_t kOr = 0x64006400u;                       // fp16 1024.0: 1024 + code
-  static constexpr uint32_t kOnes = 0x3C003C00u;
-  // FAST: fp16 has 10 mantissa bits, so the code may sit at bits 4..7 under the exponent of 64.0 (ulp 1/16): the operand is 64 + code,
-  // a sixteenth of the 1024 + code the exact path needs -- the subtracted constant term shrinks with it
-  static constexpr float kFastBase = 64.f;
-  static constexpr uint32_t kFastOr = 0x54005400u, kFastMask = 0x00F000F0u;
-  static constexpr int kFastShift = 4;
   static __device__ __forceinline__ uint32_t sub_mul(uint32_t y, uint32_t b2, uint32_t s2) {
     __half2 d = __hsub2(*reinterpret_cast<const __half2*>(&y), *reinterpret_cast<const __half2*>(&b2));
     __half2 w = __hmul2(d, *reinterpret_cast<const __half2*>(&s2));
@@ -123,7 +119,7 @@ __device__ __forceinline__ void w4m_unit(const W4mParams& p, int u, int& tile, i
   kb1 = (int)(((long long)p.kb_total * (split + 1)) / p.split_k);
 }
 
-template <typename T, int NT, bool FAST>
+template <typename T, int NT>
 __global__ void __launch_bounds__(kThreads, NT == 1 ? 3 : 2)
 gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) {
   CTS_DYN_SMEM(smem_raw);
@@ -203,22 +199,7 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[mi][nt][j] = 0.f;
     uint32_t sA[2] = {0, 0}, bA[2] = {0, 0}, sB[2] = {0, 0}, bB[2] = {0, 0};   // {scale, magic + zp} of rows g / g + 8 of the two m-tiles
-    // FAST (t <= 16): the A operand is the pair (base + code) straight out of one lop3 -- no subtraction, no multiplication per weight.
-    // With s and z constant over a group, sum_k x_k s (q_k - z) = s (sum_k x_k (base + q_k) - (base + z) sum_k x_k): the first sum is
-    // the MMA into a per-group accumulator, the second comes from one more MMA per k16 step whose A operand is all ones, and the
-    // group's fp32 scale is applied ONCE per accumulator at the group's end.  The weight is then the exact product s (q - z) in fp32
-    // (the GPTQ definition), not its rounding to the model dtype that the dense copy and the exact path use: the two agree to the
-    // 16-bit rounding of the weights (~1e-3 of an output), the FAST path agrees with the fp32 statement of the formula to ~1e-5.
-    float accg[2][NT][4], xsum[NT][4];
-    uint32_t szw[2][2] = {{0u, 0u}, {0u, 0u}};               // FAST: the group's packed {scale, magic + zp} words of rows g / g + 8, unpacked at the group's end
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { accg[0][nt][j] = 0.f; accg[1][nt][j] = 0.f; xsum[nt][j] = 0.f; }
-    const uint32_t kMask = w4m_opaque(FAST ? MagicM<T>::kFastMask : 0x000F000Fu), kMagic = w4m_opaque(FAST ? MagicM<T>::kFastOr : MagicM<T>::kOr);
-    uint32_t ones[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ones[j] = MagicM<T>::kOnes;
+    const uint32_t kMask = w4m_opaque(0x000F000Fu), kMagic = w4m_opaque(MagicM<T>::kOr);
     const uint32_t w_off = (uint32_t)((warp * 2 * 32 + lane) * 16);           // this lane's word quadruple of m-tile 2 warp (+ 512: m-tile 2 warp + 1)
     const uint32_t sz_off = (uint32_t)(kWBytes + (warp * 2 * 16 + g) * 4);
     // ldmatrix row addresses inside a token tile for k16 step 0; step ks: XOR with ks << 5 (the chunk index 2 ks + h enters the 128B swizzle by XOR)
@@ -248,12 +229,8 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
 #pragma unroll
           for (int mi = 0; mi < 2; ++mi) {
             const uint32_t va = *reinterpret_cast<const uint32_t*>(sz + mi * 64), vb = *reinterpret_cast<const uint32_t*>(sz + mi * 64 + 32);
-            if constexpr (FAST) {
-              szw[mi][0] = va; szw[mi][1] = vb;
-            } else {
-              sA[mi] = (va & 0xFFFFu) * 0x00010001u; bA[mi] = (va >> 16) * 0x00010001u;      // both halves of a packed pair
-              sB[mi] = (vb & 0xFFFFu) * 0x00010001u; bB[mi] = (vb >> 16) * 0x00010001u;
-            }
+            sA[mi] = (va & 0xFFFFu) * 0x00010001u; bA[mi] = (va >> 16) * 0x00010001u;      // both halves of a packed pair
+            sB[mi] = (vb & 0xFFFFu) * 0x00010001u; bB[mi] = (vb >> 16) * 0x00010001u;
           }
         }
         fetch = (++in_grp == p.kb_per_group);
@@ -279,50 +256,12 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
           for (int mi = 0; mi < 2; ++mi) {
             const uint32_t w = ks == 0 ? wv[mi].x : ks == 1 ? wv[mi].y : ks == 2 ? wv[mi].z : wv[mi].w;
             uint32_t a[4];
-            if constexpr (FAST) {
-              constexpr int sh = MagicM<T>::kFastShift;          // the codes of register a_i sit at bits 4 i of each half; the mask wants them at bits sh
-              a[0] = w4m_and_or(sh ? (w << sh) : w, kMask, kMagic);
-              a[1] = w4m_and_or(sh ? w : (w >> 4), kMask, kMagic);
-              a[2] = w4m_and_or(w >> (8 - sh), kMask, kMagic);
-              a[3] = w4m_and_or(w >> (12 - sh), kMask, kMagic);
+            a[0] = MagicM<T>::sub_mul(w4m_and_or(w, kMask, kMagic), bA[mi], sA[mi]);
+            a[1] = MagicM<T>::sub_mul(w4m_and_or(w >> 4, kMask, kMagic), bB[mi], sB[mi]);
+            a[2] = MagicM<T>::sub_mul(w4m_and_or(w >> 8, kMask, kMagic), bA[mi], sA[mi]);
+            a[3] = MagicM<T>::sub_mul(w4m_and_or(w >> 12, kMask, kMagic), bB[mi], sB[mi]);
 #pragma unroll
-              for (int nt = 0; nt < NT; ++nt) w4m_mma<T>(accg[mi][nt], a, bf[nt][0], bf[nt][1]);
-            } else {
-              a[0] = MagicM<T>::sub_mul(w4m_and_or(w, kMask, kMagic), bA[mi], sA[mi]);
-              a[1] = MagicM<T>::sub_mul(w4m_and_or(w >> 4, kMask, kMagic), bB[mi], sB[mi]);
-              a[2] = MagicM<T>::sub_mul(w4m_and_or(w >> 8, kMask, kMagic), bA[mi], sA[mi]);
-              a[3] = MagicM<T>::sub_mul(w4m_and_or(w >> 12, kMask, kMagic), bB[mi], sB[mi]);
-#pragma unroll
-              for (int nt = 0; nt < NT; ++nt) w4m_mma<T>(acc[mi][nt], a, bf[nt][0], bf[nt][1]);
-            }
-          }
-          if constexpr (FAST) {                               // sum_k x_k of this k16 step, per token: rows of the result are identical
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) w4m_mma<T>(xsum[nt], ones, bf[nt][0], bf[nt][1]);
-          }
-        }
-        if constexpr (FAST) {
-          if (fetch || kb + 1 == kb1) {                       // the group (or the unit's share of it) ends with this block: scale it into the total
-#pragma unroll
-            for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-              for (int row = 0; row < 2; ++row) {
-                const uint16_t hs = (uint16_t)(szw[mi][row] & 0xFFFFu);
-                const float sc = DT<T>::to_f(*reinterpret_cast<const T*>(&hs));
-                const float nbz = -(MagicM<T>::kFastBase + (float)((szw[mi][row] >> 16) & 0xFFu));     // -(base + zero point)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                  for (int tk = 0; tk < 2; ++tk) {
-                    const int j = row * 2 + tk;
-                    acc[mi][nt][j] = fmaf(sc, fmaf(nbz, xsum[nt][tk], accg[mi][nt][j]), acc[mi][nt][j]);
-                    accg[mi][nt][j] = 0.f;
-                  }
-              }
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) xsum[nt][j] = 0.f;
+            for (int nt = 0; nt < NT; ++nt) w4m_mma<T>(acc[mi][nt], a, bf[nt][0], bf[nt][1]);
           }
         }
         __syncwarp();
@@ -359,7 +298,7 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
 // tiles) 15.1 -> 18.2 us (profiles/r2_w4_mma_gemm_sweep*.json)
 static inline int w4m_ctas_per_sm(long long tiles, long long t) { return (t <= 8 && tiles >= 64) ? 3 : 2; }
 
-template <typename T, int NT, bool FAST>
+template <typename T, int NT>
 int launch_w4m(cts_ctx* ctx, const cts_gemm_w4f_args* a, cudaStream_t stream) {
   const bool is_bf16 = a->dtype == CTS_BF16;
   CUtensorMap tm_x;
@@ -383,7 +322,7 @@ int launch_w4m(cts_ctx* ctx, const cts_gemm_w4f_args* a, cudaStream_t stream) {
   if (sw < 2) return cts_set_error(ctx, CTS_ERR_BAD_ARG, "cts_gemm_w4_mma: shared memory budget too small");
   p.stages_w = sw;
   const size_t smem = (size_t)p.stages_x * kXBytes + (size_t)sw * kStageBytes + 1024;
-  auto kern = gemm_w4_mma_kernel<T, NT, FAST>;
+  auto kern = gemm_w4_mma_kernel<T, NT>;
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #ifndef CTS_HOST_SHIM
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
@@ -423,13 +362,7 @@ extern "C" int cts_gemm_w4_mma(cts_ctx* ctx, const cts_gemm_w4f_args* a, void* s
   CTS_CHECK_ARG(ctx, a->x_ld >= a->k, "x_ld smaller than k");
   CTS_CHECK_ARG(ctx, (((uintptr_t)a->qw | (uintptr_t)a->szp) & 15) == 0, "qw / szp must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const bool exact = (a->flags & CTS_W4F_EXACT) != 0;
-#define W4M_GO(TT)                                                                                              \
-  {                                                                                                             \
-    if (a->t <= 8) return exact ? launch_w4m<TT, 1, false>(ctx, a, st) : launch_w4m<TT, 1, true>(ctx, a, st);   \
-    if (a->t <= 16) return exact ? launch_w4m<TT, 2, false>(ctx, a, st) : launch_w4m<TT, 2, true>(ctx, a, st);  \
-    return launch_w4m<TT, 4, false>(ctx, a, st);                                                                \
-  }
-  if (a->dtype == CTS_BF16) W4M_GO(__nv_bfloat16) else W4M_GO(__half)
-#undef W4M_GO
+  if (a->dtype == CTS_BF16)
+    return a->t <= 8 ? launch_w4m<__nv_bfloat16, 1>(ctx, a, st) : a->t <= 16 ? launch_w4m<__nv_bfloat16, 2>(ctx, a, st) : launch_w4m<__nv_bfloat16, 4>(ctx, a, st);
+  return a->t <= 8 ? launch_w4m<__half, 1>(ctx, a, st) : a->t <= 16 ? launch_w4m<__half, 2>(ctx, a, st) : launch_w4m<__half, 4>(ctx, a, st);
 }

@@ -298,13 +298,9 @@ class ChatTSForCausalLM:
         c = self.ctx
         import os as _os
         # kernel of the decode step: "mma" (default) = csrc/gemm_w4_mma.cu, the codes dequantised in registers from the fragment-major copy
-        # built here (the row layout is dropped per layer once it is converted) -- for steps of up to 16 tokens with the group's scale
-        # applied in fp32 after the MMA (the unrounded s (q - z)), "mma_exact" = the same kernel with every weight rounded to the model
-        # dtype as in the dense copy; "tc5" = csrc/gemm_w4.cu (tcgen05, bit-identical to the dense GEMM, no faster than it: the checker)
+        # built here (the row layout is dropped per layer once it is converted); "tc5" = csrc/gemm_w4.cu (tcgen05, bit-identical to the
+        # dense GEMM, no faster than it: kept as the checker)
         w4["kernel"] = _os.environ.get("CTS_W4_KERNEL", "mma")
-        w4["exact"] = w4["kernel"] == "mma_exact"       # "mma_exact": weights rounded to the model dtype as in the dense copy, at every batch size
-        if w4["kernel"] == "mma_exact":
-            w4["kernel"] = "mma"
         if w4["kernel"] == "mma":
             from .weights import repack_w4_mma
             for kind in ("qkv", "o", "gu", "d"):
@@ -391,7 +387,7 @@ class ChatTSForCausalLM:
             """fp32 split-K partials of one projection into st.ws: from the packed 4-bit weight when attached, else from the dense one."""
             if w4 is not None and w4["kernel"] == "mma":
                 qwf, szp, n_out = w4[kind][l]
-                c.gemm_w4_mma(x, qwf, szp, n_out, w4["group_size"], st.ws, split, t=T, exact=w4["exact"])
+                c.gemm_w4_mma(x, qwf, szp, n_out, w4["group_size"], st.ws, split, t=T)
             elif w4 is not None:
                 qw, sc, zp = w4[kind][l]
                 c.gemm_w4(x, qw, sc, zp, w4["group_size"], st.ws, split, t=T)

@@ -519,15 +519,10 @@ int cts_gemm_w4_suggest_split(cts_ctx* ctx, long long n, long long k);
  *        nibble i < 4 / i + 4 = the codes at k = 16 ks + 2t + 8 (i / 2) + {0 / 1} of feature row g + 8 (i % 2)   (chatts_b200/weights.py:repack_w4_mma)
  *   szp  uint32 [ceil(n / 256), k / group_size, 256]: scale bits (model dtype) | (magic + zero point) << 16, magic = 0x4300 (bf16) / 0x6400 (fp16);
  *        features beyond n: 0 */
-/* flags: CTS_W4F_EXACT = every weight is rounded to the model dtype before the MMA -- the values of the dequantised dense copy (what
- * cts_gemm_w4 and the prefill use).  Default (0), for t <= 16: the MMA runs on (base + code) pairs and the group's scale / zero point are
- * applied in fp32 once per group and accumulator, i.e. the weight is the unrounded s * (q - z) of the GPTQ definition: half the
- * instructions per weight; differs from the dense copy's result by the 16-bit rounding of the weights. */
-#define CTS_W4F_EXACT 1
 typedef struct {
   const void* qw; const void* szp; const void* x; float* out;
   long long n, k, t, x_ld;
-  int group_size, split_k, dtype, flags;
+  int group_size, split_k, dtype, reserved;
 } cts_gemm_w4f_args;
 int cts_gemm_w4_mma(cts_ctx* ctx, const cts_gemm_w4f_args* args, void* stream);
 int cts_gemm_w4_mma_suggest_split(cts_ctx* ctx, long long n, long long k, long long t);

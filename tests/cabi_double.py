@@ -294,7 +294,7 @@ class TorchDouble:
         self.gemm(x, w, out, epilogue=3, split_k=split_k, t=t)
 
     def gemm_w4_mma_suggest_split(self, n, k, t=1): return self.split if k >= 128 * self.split else 1
-    def gemm_w4_mma(self, x, qwf, szp, n, group_size, out, split_k, t=None, exact=False):
+    def gemm_w4_mma(self, x, qwf, szp, n, group_size, out, split_k, t=None):
         """The fragment-major layout decoded back to a dense weight (the inverse of weights.py:repack_w4_mma, written independently)."""
         k = szp.shape[1] * int(group_size)
         tiles = szp.shape[0]
@@ -315,17 +315,8 @@ class TorchDouble:
         magic = 0x4300 if x.dtype == torch.bfloat16 else 0x6400
         zp = ((u >> 16) - magic).permute(0, 2, 1).reshape(tiles * 256, -1)
         grp = torch.arange(k) // int(group_size)
-        w32 = (sc.to(torch.float32)[:, grp] * (q - zp[:, grp]).to(torch.float32))[:n]
-        tt = x.shape[0] if t is None else t
-        if exact or tt > 16:
-            self.gemm(x, w32.to(x.dtype), out, epilogue=3, split_k=split_k, t=t)
-            return
-        # default for t <= 16: the unrounded weights, fp32 arithmetic, the K ranges of the split-K partials (in 64-wide blocks)
-        kb = k // 64
-        o = out.view(-1)[: split_k * tt * n].view(split_k, tt, n)
-        for sp in range(split_k):
-            k0, k1 = (kb * sp) // split_k * 64, (kb * (sp + 1)) // split_k * 64
-            o[sp] = x[:tt, k0:k1].float() @ w32[:, k0:k1].t()
+        w = (sc.to(torch.float32)[:, grp] * (q - zp[:, grp]).to(torch.float32)).to(x.dtype)[:n]
+        self.gemm(x, w, out, epilogue=3, split_k=split_k, t=t)
 
     # ------------------------------------------------------------------ repetition penalty (csrc/sampling.cu)
     def rep_penalty_mark(self, tokens, rows, seen, vocab):

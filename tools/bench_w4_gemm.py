@@ -30,7 +30,7 @@ def main():
         wd = [torch.randn(n, k, generator=g, device=dev).to(torch.bfloat16) for _ in range(min(L, 4))]
         byts = n * k / 2 + n * (k // 128) * 4
         out = {}
-        for T in ((32,) if once else (1, 8, 16, 32)):
+        for T in ((int(os.environ.get('W4_ONCE_T', '32')),) if once else (1, 8, 16, 32)):
             x = (torch.randn(T, k, generator=g, device=dev) * 0.5).to(torch.bfloat16)
             sug = c.gemm_w4_mma_suggest_split(n, k, T)
             row = {}
@@ -43,10 +43,6 @@ def main():
             best = min(row, key=lambda kk: row[kk]["us"])
             out[f"mma_T{T}"] = {"suggested": f"split{sug}", "best": best, "best_us": row[best]["us"], "suggested_us": row[f"split{sug}"]["us"],
                                 "best_packed_gbs": row[best]["packed_gbs"], "all": row}
-            if T <= 16 and not once:                     # the same launch with every weight rounded to the model dtype (CTS_W4F_EXACT)
-                ws = torch.empty(sug * T * n, device=dev, dtype=torch.float32)
-                us = bench._event_timer(lambda i: c.gemm_w4_mma(x, frag[i % L][0], frag[i % L][1], n, 128, ws, sug, t=T, exact=True), 2 * L)
-                out[f"mma_T{T}"]["exact_suggested_us"] = round(us, 2)
             if not once:
                 sp = c.suggest_split(n if name != "gate_up" else n // 2, k, T, name == "gate_up")
                 ws = torch.empty(sp * T * n, device=dev, dtype=torch.float32)
