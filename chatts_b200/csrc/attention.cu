@@ -239,13 +239,17 @@ attn_prefill_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
 // prefill on tcgen05 (head_dim 128): S = Q K^T and O += P V on the 5th-gen tensor cores, accumulators in TMEM
 // ================================================================================================
 // One CTA = 128 query rows of one (sequence, head).  Q, K, V tiles arrive by TMA (128-byte swizzle); the MMA warp
-// issues tcgen05.mma (M=128, N=128, K=16) for S[128 x 128] = Q K^T into TMEM columns 0..127; the four softmax warps
-// (thread = query row, lane-aligned with TMEM) read S with tcgen05.ld, and
-//   pass 1: keep the running row maximum                                 (K tiles only)
-//   pass 2: write P = exp2((s - m) * scale*log2e) as bf16/fp16 into a swizzled K-major shared tile, accumulate the row
-//           sum, and the MMA warp issues O[128 x 128] += P V into TMEM columns 128..255 (V is the MN-major B operand).
-// Two passes mean the O accumulator never needs a rescale (QK^T costs 2x, the softmax/PV path 1x).  Causal masking only
-// touches the diagonal tile (query and KV tiles are both 128 and aligned).  Epilogue: O / l from TMEM to global.
+// issues tcgen05.mma (M=128, N=64, K=16) for S[128 x 64] = Q K^T into one of two TMEM buffers; the four softmax warps
+// (thread = query row, lane-aligned with TMEM) read S with tcgen05.ld and run a SINGLE-PASS online softmax:
+//   * the row maximum used for the exponent is refreshed lazily -- only when the tile's maximum exceeds it by more than 8
+//     (in log2 units; P then stays below 2^8, far inside bf16 / fp16 / fp32 range) -- so the O accumulator in TMEM needs a
+//     rescale only in the first tiles of a row block; when any row of a warp needs one, the warp multiplies its 32 TMEM
+//     lanes of O in place (tcgen05.ld -> scale -> tcgen05.st) between P.V of the previous tile and P.V of this one;
+//   * P = exp2(s * scale*log2e - m) as bf16/fp16 into a swizzled K-major shared tile, the row sum kept in fp32, and the
+//     MMA warp issues O[128 x 128] += P V into TMEM columns 128..255 (V is the MN-major B operand).
+// Round 1-2 ran two passes (row maxima first, so that O never needed a rescale): 1.5 x the tensor work and twice the
+// TMEM reads of S per tile; 254 TFLOP/s at 32 x 576 (profiles/r2_prefill_attention_vs_installed.json).  Causal masking
+// only touches the tiles on the diagonal (query tiles are 128, key tiles 64, both aligned).  Epilogue: O / l from TMEM to global.
 constexpr int kTcQ = 128, kTcKV = 64, kTcThreads = 192;
 constexpr int kTcQHalf = kTcQ * 128;            // one [128 q rows x 128 B] swizzled half of the Q tile (16 KiB)
 constexpr int kTcKHalf = kTcKV * 128;           // one [64 kv rows x 128 B] half of a K or V tile (8 KiB)
@@ -265,10 +269,10 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 }
 
 // Pipeline (per CTA; two CTAs share an SM): K and V tiles travel through ONE ring of kTcStages slots in exactly the order the MMA
-// warp consumes them (pass 1: K_0 .. K_{n-1}; pass 2: K_0, K_1, V_0, K_2, V_1, ..., V_{n-1}), so the TMA producer runs up to
-// three tiles ahead instead of exposing one L2/HBM round trip per tile (round 1: K and V single-buffered, 22 % tensor-pipe
-// active); S is double-buffered in TMEM (2 x 64 columns) and the MMA warp issues QK^T of tile i BEFORE P.V of tile i-1, so the
-// softmax warps work on tile i while the tensor core runs P.V(i-1); P is single-buffered behind a p_free barrier.
+// warp consumes them (K_0, K_1, V_0, K_2, V_1, ..., V_{n-1}), so the TMA producer runs up to three tiles ahead; S is double-buffered
+// in TMEM (2 x 64 columns) and the MMA warp issues QK^T of tile i BEFORE P.V of tile i-1, so the softmax warps work on tile i while
+// the tensor core runs P.V(i-1); P is single-buffered behind a p_free barrier, which is also what orders an O rescale (done by the
+// softmax warps after p_free = "P.V(i-1) has completed" and before their p_full arrival = "P.V(i) may be issued").
 template <typename T, bool LSE>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -310,7 +314,6 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   const int kvh = head / (nh / nkv);
   const int kv_end = min(len, q0 + kTcQ);             // causal: keys 0 .. kv_end-1
   const int nt = live ? (kv_end + kTcKV - 1) / kTcKV : 0;
-  const int total = 2 * nt;                           // pass 1 (row max) then pass 2 (P, O)
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -329,8 +332,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         tma_load_2d(dst + kTcKHalf, tm, &kv_full[sl], kvh * HD + 64, row, CTS_L2_EVICT_LAST);
         ++n;
       };
-      for (int j = 0; j < nt; ++j) load_tile(&tm_k, j);                  // pass 1
-      for (int j = 0; j < nt; ++j) {                                     // pass 2: K_0, K_1, V_0, K_2, V_1, ..., V_{nt-1}
+      for (int j = 0; j < nt; ++j) {                                     // K_0, K_1, V_0, K_2, V_1, ..., V_{nt-1}
         load_tile(&tm_k, j);
         if (j > 0) load_tile(&tm_v, j - 1);
       }
@@ -364,7 +366,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         umma_commit(&p_free);
       };
       mbar_wait(&q_bar, 0);
-      for (int i = 0; i < total; ++i) {
+      for (int i = 0; i < nt; ++i) {
         const uint32_t sb = (uint32_t)i & 1u;
         const int sl = take();
         const uint32_t k_addr = ring_addr + (uint32_t)sl * 2 * kTcKHalf;
@@ -379,7 +381,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         }
         umma_commit(&s_full[sb]);
         umma_commit(&kv_empty[sl]);
-        if (i > nt) issue_pv(i - 1 - nt);                 // P.V of the previous pass-2 tile, behind this tile's QK^T
+        if (i > 0) issue_pv(i - 1);                       // P.V of the previous tile, behind this tile's QK^T
       }
       if (nt > 0) issue_pv(nt - 1);
       umma_commit(&o_done);
@@ -391,61 +393,75 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const int qi = q0 + r;                                // query index inside the sequence
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = scale * 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f;
-    for (int i = 0; i < total; ++i) {
-      const bool pass2 = i >= nt;
-      const int j = pass2 ? i - nt : i;
+    float m_run = -INFINITY, l_run = 0.f;                 // m_run: the (lazily refreshed) maximum the exponents are taken against, in log2 units
+    for (int j = 0; j < nt; ++j) {
       const int kv0 = j * kTcKV;
       const bool need_mask = kv0 + kTcKV - 1 > q0;        // CTA-uniform: the tile reaches past the first query row
-      const uint32_t sb = (uint32_t)i & 1u;
+      const uint32_t sb = (uint32_t)j & 1u;
       const uint32_t s_addr = lane_base + sb * kTcKV;
-      mbar_wait(&s_full[sb], (uint32_t)(i >> 1) & 1u);
+      mbar_wait(&s_full[sb], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
-      if (!pass2) {
-        float mx = m_run;
-#pragma unroll 1
-        for (int c = 0; c < kTcKV; c += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(s_addr + (uint32_t)c, v);
-          tmem_ld_wait();
+      uint32_t sv[kTcKV];
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (!need_mask || kv0 + c + e <= qi) mx = fmaxf(mx, __uint_as_float(v[e]));
-        }
-        m_run = mx;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[sb]);
-      } else {
-        const float mneg = m_run > -INFINITY ? m_run * sl2 : 0.f;
-        uint4 pk[kTcKV / 8];
+      for (int c = 0; c < kTcKV; c += 16) tmem_ld_32x32b_x16(s_addr + (uint32_t)c, sv + c);     // all four loads in flight, ONE wait
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[sb]);            // S[sb] is in registers: QK^T of tile j+2 may overwrite it
+      float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < kTcKV; c += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(s_addr + (uint32_t)c, v);
-          tmem_ld_wait();
-          float pv[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const bool ok = !need_mask || kv0 + c + e <= qi;
-            pv[e] = ok ? exp2f(__uint_as_float(v[e]) * sl2 - mneg) : 0.f;
-            l_run += pv[e];
-          }
-          pk[c / 8] = pack8<T>(pv);
-          pk[c / 8 + 1] = pack8<T>(pv + 8);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[sb]);          // S[sb] is free for QK^T of tile i+2
-        if (j > 0) mbar_wait(&p_free, (uint32_t)(j - 1) & 1u);   // P.V(j-1) has consumed the previous P tile
-        // P[r][0..63] -> K-major swizzled tile (row r, 16-byte chunk ch at ch ^ (r & 7))
-#pragma unroll
-        for (int ch = 0; ch < kTcKV / 8; ++ch)
-          *reinterpret_cast<uint4*>(p_s + (uint32_t)r * 128 + ((ch ^ (r & 7)) << 4)) = pk[ch];
-        fence_proxy_async_smem();                         // P must be visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full);
+      for (int e = 0; e < kTcKV; ++e) {
+        const float v = __uint_as_float(sv[e]) * sl2;
+        const bool ok = !need_mask || kv0 + e <= qi;
+        mx = fmaxf(mx, ok ? v : -INFINITY);
       }
+      // lazy maximum: keep the old one unless the tile exceeds it by more than 8 (then P <= 2^8 everywhere)
+      float alpha = 1.f;
+      bool rescale = false;
+      if (mx > m_run + 8.f) {
+        rescale = m_run > -INFINITY;                      // the first finite maximum needs no rescale: l and O are still zero
+        alpha = rescale ? exp2f(m_run - mx) : 1.f;
+        m_run = mx;
+      }
+      const float mneg = m_run > -INFINITY ? m_run : 0.f;
+      l_run *= alpha;
+      uint4 pk[kTcKV / 8];
+#pragma unroll
+      for (int c = 0; c < kTcKV; c += 8) {
+        float pv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const bool ok = !need_mask || kv0 + c + e <= qi;
+          pv[e] = ok ? exp2f(__uint_as_float(sv[c + e]) * sl2 - mneg) : 0.f;
+          l_run += pv[e];
+        }
+        pk[c / 8] = pack8<T>(pv);
+      }
+      if (j > 0) mbar_wait(&p_free, (uint32_t)(j - 1) & 1u);     // P.V(j-1) has completed: P may be overwritten, O may be rescaled
+      int any_rescale = rescale ? 1 : 0;                  // (shuffle tree instead of __any_sync: also runs on tests/cuda_on_cpu)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) any_rescale |= __shfl_xor_sync(0xffffffffu, any_rescale, o);
+      if (any_rescale) {                                  // warp-collective: rows that keep their maximum multiply by 1
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < HD; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+          tmem_st_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      // P[r][0..63] -> K-major swizzled tile (row r, 16-byte chunk ch at ch ^ (r & 7))
+#pragma unroll
+      for (int ch = 0; ch < kTcKV / 8; ++ch)
+        *reinterpret_cast<uint4*>(p_s + (uint32_t)r * 128 + ((ch ^ (r & 7)) << 4)) = pk[ch];
+      fence_proxy_async_smem();                           // P must be visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full);
     }
     // ---- epilogue: O / l   (tcgen05.ld is warp-collective: every lane loads, rows inside the sequence are stored)
     mbar_wait(&o_done, 0);
@@ -467,7 +483,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         }
       }
       if constexpr (LSE) {
-        if (qi < len) lse[((long long)seq0 + qi) * nh + head] = l_run > 0.f ? m_run * scale + logf(l_run) : -INFINITY;
+        if (qi < len) lse[((long long)seq0 + qi) * nh + head] = l_run > 0.f ? m_run * 0.6931471805599453f + logf(l_run) : -INFINITY;   // m_run is in log2 units
       }
     }
   }

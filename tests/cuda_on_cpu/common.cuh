@@ -445,6 +445,11 @@ static inline void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* v) {
   for (int j = 0; j < 16; ++j) v[j] = shim_f2u(g_tmem[lane][col + j]);
 }
 static inline void tmem_ld_wait() {}                     // completes the LOADS only: outstanding MMAs are not performed here
+static inline void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t* v) {
+  const int lane = (int)(taddr >> 16) + (shim_linear_tid() & 31), col = (int)(taddr & 0xFFFF);
+  for (int j = 0; j < 16; ++j) g_tmem[lane][col + j] = shim_u2f(v[j]);
+}
+static inline void tmem_st_wait() {}
 static inline uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }

@@ -22,7 +22,17 @@ def test_prefill_fp16(d):
     _prefill_case(d, [129, 64, 300], torch.float16)
 
 
-def _prefill_case(d, lens, DT):
+@pytest.mark.parametrize("DT", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("lens", [[577], [300, 129, 64]])
+def test_prefill_growing_scores_force_the_lazy_rescale(lens, DT):
+    """The tcgen05 kernel keeps a row's exponent maximum until a tile exceeds it by more than 8 (log2 units) and then rescales l and the
+    O accumulator in TMEM in place.  Random data rarely moves the maximum after the first tile; here the scores grow along the sequence
+    (keys scaled by their position), so every 64-key tile raises the maximum by far more than the threshold for most rows -- the rescale
+    path runs in nearly every tile, for some rows of a warp and not for others."""
+    _prefill_case(128, lens, DT, ramp=True)
+
+
+def _prefill_case(d, lens, DT, ramp=False):
     c = ctx()
     nh, nkv = 4, 2
     T = sum(lens)
@@ -30,6 +40,12 @@ def _prefill_case(d, lens, DT):
     q = torch.randn(T, nh, d, generator=g).to(DT)
     k = torch.randn(T, nkv, d, generator=g).to(DT)
     v = torch.randn(T, nkv, d, generator=g).to(DT)
+    if ramp:
+        # q = |q| and k = position-dependent positive multiple of |k|: q.k grows roughly linearly with the key position (~ +0.6 per key
+        # after the 1/sqrt(d) scale, i.e. ~ +55 log2 units per 64-key tile), rows with a small |q| grow slower than the threshold
+        pos = torch.cat([torch.arange(n) for n in lens]).float()
+        q = (q.float().abs() * torch.linspace(0.02, 1.0, nh * d).view(1, nh, d)).to(DT)
+        k = (k.float().abs() * (0.05 + pos / 64.0).view(-1, 1, 1)).to(DT)
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
     out = torch.full((T, nh * d), float("nan"), device="cuda", dtype=DT)
     c.attn_prefill(q.cuda().contiguous(), k.cuda().contiguous(), v.cuda().contiguous(), cu.cuda(), len(lens), max(lens), nh, nkv, d,
