@@ -273,6 +273,18 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 // in TMEM (2 x 64 columns) and the MMA warp issues QK^T of tile i BEFORE P.V of tile i-1, so the softmax warps work on tile i while
 // the tensor core runs P.V(i-1); P is single-buffered behind a p_free barrier, which is also what orders an O rescale (done by the
 // softmax warps after p_free = "P.V(i-1) has completed" and before their p_full arrival = "P.V(i) may be issued").
+// 2^x on the MUFU (ex2.approx.ftz: relative error 2^-22, flushes denormal results -- P values that small do not matter); exp2f()
+// without fast-math wraps the same instruction in a denormal range fix-up of three more
+__device__ __forceinline__ float tc_ex2(float x) {
+#ifndef CTS_HOST_SHIM
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  return exp2f(x);
+#endif
+}
+
 template <typename T, bool LSE>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -408,35 +420,52 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[sb]);            // S[sb] is in registers: QK^T of tile j+2 may overwrite it
+      // The softmax warps are instruction-issue bound (ncu of the first single-pass version: ~1 500 instructions per warp and tile,
+      // 45 % issue-active, tensor pipe 15 %), so the per-element work is what the arithmetic needs and no more: FMNMX on the raw score,
+      // one FFMA + one MUFU.EX2 + one FADD, half a conversion; the causal select only in the (CTA-uniform) diagonal tiles.
       float mx = -INFINITY;
+      if (need_mask) {
 #pragma unroll
-      for (int e = 0; e < kTcKV; ++e) {
-        const float v = __uint_as_float(sv[e]) * sl2;
-        const bool ok = !need_mask || kv0 + e <= qi;
-        mx = fmaxf(mx, ok ? v : -INFINITY);
+        for (int e = 0; e < kTcKV; ++e) mx = fmaxf(mx, kv0 + e <= qi ? __uint_as_float(sv[e]) : -INFINITY);
+      } else {
+#pragma unroll
+        for (int e = 0; e < kTcKV; ++e) mx = fmaxf(mx, __uint_as_float(sv[e]));
       }
+      mx *= sl2;                                          // sl2 > 0: scaling commutes with the maximum
       // lazy maximum: keep the old one unless the tile exceeds it by more than 8 (then P <= 2^8 everywhere)
       float alpha = 1.f;
       bool rescale = false;
       if (mx > m_run + 8.f) {
         rescale = m_run > -INFINITY;                      // the first finite maximum needs no rescale: l and O are still zero
-        alpha = rescale ? exp2f(m_run - mx) : 1.f;
+        alpha = rescale ? tc_ex2(m_run - mx) : 1.f;
         m_run = mx;
       }
-      const float mneg = m_run > -INFINITY ? m_run : 0.f;
+      const float mneg = m_run > -INFINITY ? -m_run : 0.f;
       l_run *= alpha;
       uint4 pk[kTcKV / 8];
+      float ls0 = 0.f, ls1 = 0.f;                         // two partial row sums: half the length of the dependent FADD chain
+      if (need_mask) {
 #pragma unroll
-      for (int c = 0; c < kTcKV; c += 8) {
-        float pv[8];
+        for (int c = 0; c < kTcKV; c += 8) {
+          float pv[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const bool ok = !need_mask || kv0 + c + e <= qi;
-          pv[e] = ok ? exp2f(__uint_as_float(sv[c + e]) * sl2 - mneg) : 0.f;
-          l_run += pv[e];
+          for (int e = 0; e < 8; ++e) pv[e] = kv0 + c + e <= qi ? tc_ex2(fmaf(__uint_as_float(sv[c + e]), sl2, mneg)) : 0.f;
+          ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+          ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+          pk[c / 8] = pack8<T>(pv);
         }
-        pk[c / 8] = pack8<T>(pv);
+      } else {
+#pragma unroll
+        for (int c = 0; c < kTcKV; c += 8) {
+          float pv[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pv[e] = tc_ex2(fmaf(__uint_as_float(sv[c + e]), sl2, mneg));
+          ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+          ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+          pk[c / 8] = pack8<T>(pv);
+        }
       }
+      l_run += ls0 + ls1;
       if (j > 0) mbar_wait(&p_free, (uint32_t)(j - 1) & 1u);     // P.V(j-1) has completed: P may be overwritten, O may be rescaled
       int any_rescale = rescale ? 1 : 0;                  // (shuffle tree instead of __any_sync: also runs on tests/cuda_on_cpu)
 #pragma unroll
