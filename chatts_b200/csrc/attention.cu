@@ -285,14 +285,38 @@ __device__ __forceinline__ float tc_ex2(float x) {
 #endif
 }
 
+// Persistent CTAs (two per SM) over the (query tile, head, sequence) work items, heaviest query tiles first: at the benchmark shape an
+// item is 2..9 key tiles, and with one CTA per item (round 2's first single-pass version) barrier set-up, the 256-column TMEM
+// allocation, the first Q / K round trips and the O epilogue were ~45 % of a CTA's life.  Here the pipeline state simply carries on
+// from item to item: the producer requests the next item's Q as soon as the last QK^T of the current one has completed (q_free) and its
+// K tiles as ring slots free up; the MMA warp starts the next item's QK^T while the softmax warps still store the current O, and only
+// the first P.V of an item waits for those warps to have read O (o_free).
+struct TcItem {
+  int seq0, len, q0, head, kvh, nt;
+};
+__device__ __forceinline__ bool tc_item(int idx, int nqt, int nh, int nkv, int batch, const int* __restrict__ cu_seqlens, TcItem& it) {
+  const int per_qt = nh * batch;
+  const int qt = nqt - 1 - idx / per_qt;              // long rows of work first
+  const int rem = idx - (idx / per_qt) * per_qt;
+  const int b = rem / nh;
+  it.head = rem - b * nh;
+  it.seq0 = cu_seqlens[b];
+  it.len = cu_seqlens[b + 1] - it.seq0;
+  it.q0 = qt * kTcQ;
+  it.kvh = it.head / (nh / nkv);
+  const int kv_end = min(it.len, it.q0 + kTcQ);       // causal: keys 0 .. kv_end-1
+  it.nt = it.q0 < it.len ? (kv_end + kTcKV - 1) / kTcKV : 0;
+  return it.nt > 0;
+}
+
 template <typename T, bool LSE>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                        const __grid_constant__ CUtensorMap tm_v, const int* __restrict__ cu_seqlens, int nh, int nkv,
+                        const __grid_constant__ CUtensorMap tm_v, const int* __restrict__ cu_seqlens, int nh, int nkv, int batch, int nqt,
                         float scale, T* __restrict__ out, float* __restrict__ lse) {
   constexpr int HD = 128;
   extern __shared__ uint8_t tc_raw[];
-  __shared__ uint64_t q_bar, kv_full[kTcStages], kv_empty[kTcStages], s_full[2], s_free[2], p_full, p_free, o_done;
+  __shared__ uint64_t q_bar, q_free, kv_full[kTcStages], kv_empty[kTcStages], s_full[2], s_free[2], p_full, p_free, o_done, o_free;
   __shared__ uint32_t tmem_slot;
   const uint32_t raw = smem_u32(tc_raw);
   uint8_t* smem = tc_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -300,17 +324,19 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint8_t* p_s = q_s + 2 * kTcQHalf;                 // 16 KiB: [128 x 128 B] (64 kv columns)
   uint8_t* ring = p_s + kTcQ * 128;                  // kTcStages x 16 KiB: a K or V tile = 2 d-halves x [64 x 128 B]
 
-  const int b = blockIdx.z, head = blockIdx.y, qt = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_items = nqt * nh * batch;
   pdl_trigger();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_k); tma_prefetch_desc(&tm_v);
     mbar_init(&q_bar, 1);
+    mbar_init(&q_free, 1);
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 4); }
     mbar_init(&p_full, 4);
     mbar_init(&p_free, 1);
     mbar_init(&o_done, 1);
+    mbar_init(&o_free, 4);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<256>(&tmem_slot);
@@ -320,200 +346,225 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   const uint32_t tmem_base = tmem_slot;               // S0: cols 0..63, S1: 64..127, O: 128..255
   pdl_wait();
 
-  const int seq0 = cu_seqlens[b], len = cu_seqlens[b + 1] - seq0;
-  const int q0 = qt * kTcQ;
-  const bool live = q0 < len;                         // CTA-uniform
-  const int kvh = head / (nh / nkv);
-  const int kv_end = min(len, q0 + kTcQ);             // causal: keys 0 .. kv_end-1
-  const int nt = live ? (kv_end + kTcKV - 1) / kTcKV : 0;
-
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0 && live) {
-      mbar_expect_tx(&q_bar, (uint32_t)(2 * kTcQHalf));
-      tma_load_2d(q_s, &tm_q, &q_bar, head * HD, seq0 + q0, CTS_L2_EVICT_FIRST);
-      tma_load_2d(q_s + kTcQHalf, &tm_q, &q_bar, head * HD + 64, seq0 + q0, CTS_L2_EVICT_FIRST);
-      int n = 0;                                        // loads issued so far (ring slot n % kTcStages)
-      auto load_tile = [&](const CUtensorMap* tm, int j) {
-        const int sl = n % kTcStages;
-        mbar_wait(&kv_empty[sl], (((uint32_t)(n / kTcStages)) & 1u) ^ 1u);
-        mbar_expect_tx(&kv_full[sl], (uint32_t)(2 * kTcKHalf));
-        uint8_t* dst = ring + (size_t)sl * 2 * kTcKHalf;
-        const int row = seq0 + j * kTcKV;
-        tma_load_2d(dst, tm, &kv_full[sl], kvh * HD, row, CTS_L2_EVICT_LAST);
-        tma_load_2d(dst + kTcKHalf, tm, &kv_full[sl], kvh * HD + 64, row, CTS_L2_EVICT_LAST);
-        ++n;
-      };
-      for (int j = 0; j < nt; ++j) {                                     // K_0, K_1, V_0, K_2, V_1, ..., V_{nt-1}
-        load_tile(&tm_k, j);
-        if (j > 0) load_tile(&tm_v, j - 1);
+    if (lane == 0) {
+      uint32_t n = 0;                                   // K / V tiles requested so far (ring slot n % kTcStages), over all items
+      uint32_t k = 0;                                   // live items started by this CTA
+      for (int idx = blockIdx.x; idx < total_items; idx += gridDim.x) {
+        TcItem it;
+        if (!tc_item(idx, nqt, nh, nkv, batch, cu_seqlens, it)) continue;
+        if (k > 0) mbar_wait(&q_free, (k - 1) & 1u);     // every QK^T of the previous item has read the Q tile
+        mbar_expect_tx(&q_bar, (uint32_t)(2 * kTcQHalf));
+        tma_load_2d(q_s, &tm_q, &q_bar, it.head * HD, it.seq0 + it.q0, CTS_L2_EVICT_FIRST);
+        tma_load_2d(q_s + kTcQHalf, &tm_q, &q_bar, it.head * HD + 64, it.seq0 + it.q0, CTS_L2_EVICT_FIRST);
+        auto load_tile = [&](const CUtensorMap* tm, int j) {
+          const uint32_t sl = n % kTcStages;
+          mbar_wait(&kv_empty[sl], ((n / kTcStages) & 1u) ^ 1u);
+          mbar_expect_tx(&kv_full[sl], (uint32_t)(2 * kTcKHalf));
+          uint8_t* dst = ring + (size_t)sl * 2 * kTcKHalf;
+          const int row = it.seq0 + j * kTcKV;
+          tma_load_2d(dst, tm, &kv_full[sl], it.kvh * HD, row, CTS_L2_EVICT_LAST);
+          tma_load_2d(dst + kTcKHalf, tm, &kv_full[sl], it.kvh * HD + 64, row, CTS_L2_EVICT_LAST);
+          ++n;
+        };
+        for (int j = 0; j < it.nt; ++j) {                // K_0, K_1, V_0, K_2, V_1, ..., V_{nt-1}
+          load_tile(&tm_k, j);
+          if (j > 0) load_tile(&tm_v, j - 1);
+        }
+        load_tile(&tm_v, it.nt - 1);
+        ++k;
       }
-      if (nt > 0) load_tile(&tm_v, nt - 1);
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0 && live) {
+    if (lane == 0) {
       constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
       const uint32_t idesc_qk = umma_idesc_f16(kBf16 ? 1 : 0, kTcKV, 128);
       const uint32_t idesc_pv = umma_idesc_f16(kBf16 ? 1 : 0, 128, 128) | (1u << 16);   // B (= V) is MN-major
       const uint32_t q_addr = smem_u32(q_s), p_addr = smem_u32(p_s), ring_addr = smem_u32(ring);
-      int c = 0;                                          // ring tiles consumed so far (same sequence as the producer's)
+      uint32_t c = 0;                                     // ring tiles consumed so far (same sequence as the producer's)
+      uint32_t t = 0;                                     // S tiles issued so far, over all items (S buffer t & 1)
+      uint32_t pv = 0;                                    // P.V products issued so far, over all items
+      uint32_t k = 0;                                     // live items started
       auto take = [&]() {
-        const int sl = c % kTcStages;
-        mbar_wait(&kv_full[sl], ((uint32_t)(c / kTcStages)) & 1u);
+        const uint32_t sl = c % kTcStages;
+        mbar_wait(&kv_full[sl], (c / kTcStages) & 1u);
         ++c;
         return sl;
       };
-      auto issue_pv = [&](int j) {                        // O += P(j) V(j)
-        mbar_wait(&p_full, (uint32_t)j & 1u);
-        const int sl = take();
-        const uint32_t v_addr = ring_addr + (uint32_t)sl * 2 * kTcKHalf;
+      auto issue_pv = [&](bool first_of_item) {           // O (+)= P V for the oldest P not yet multiplied
+        mbar_wait(&p_full, pv & 1u);
+        const uint32_t sl = take();
+        const uint32_t v_addr = ring_addr + sl * 2 * kTcKHalf;
+        if (first_of_item && k > 0) mbar_wait(&o_free, (k - 1) & 1u);      // the epilogue warps have read the previous item's O
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kTcKV / 16; ++kk) {
           const uint64_t bdesc = umma_desc_mn_sw128(v_addr + (uint32_t)kk * 16 * 128, 2 * kTcKHalf / 2, 1024);
-          umma_f16(tmem_base + 128, umma_desc_k_sw128(p_addr + (uint32_t)kk * 32), bdesc, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_f16(tmem_base + 128, umma_desc_k_sw128(p_addr + (uint32_t)kk * 32), bdesc, idesc_pv, (!first_of_item || kk > 0) ? 1u : 0u);
         }
         umma_commit(&kv_empty[sl]);
         umma_commit(&p_free);
+        ++pv;
       };
-      mbar_wait(&q_bar, 0);
-      for (int i = 0; i < nt; ++i) {
-        const uint32_t sb = (uint32_t)i & 1u;
-        const int sl = take();
-        const uint32_t k_addr = ring_addr + (uint32_t)sl * 2 * kTcKHalf;
-        if (i >= 2) mbar_wait(&s_free[sb], (uint32_t)((i - 2) >> 1) & 1u);     // softmax warps finished reading S[sb]
-        tc_fence_after();
+      for (int idx = blockIdx.x; idx < total_items; idx += gridDim.x) {
+        TcItem it;
+        if (!tc_item(idx, nqt, nh, nkv, batch, cu_seqlens, it)) continue;
+        mbar_wait(&q_bar, k & 1u);
+        for (int i = 0; i < it.nt; ++i, ++t) {
+          const uint32_t sb = t & 1u;
+          const uint32_t sl = take();
+          const uint32_t k_addr = ring_addr + sl * 2 * kTcKHalf;
+          if (t >= 2) mbar_wait(&s_free[sb], ((t - 2) >> 1) & 1u);      // softmax warps finished reading S[sb]
+          tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint32_t qoff = (uint32_t)(kk >> 2) * kTcQHalf + (uint32_t)(kk & 3) * 32;
-          const uint32_t koff = (uint32_t)(kk >> 2) * kTcKHalf + (uint32_t)(kk & 3) * 32;
-          umma_f16(tmem_base + sb * kTcKV, umma_desc_k_sw128(q_addr + qoff), umma_desc_k_sw128(k_addr + koff), idesc_qk,
-                   kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < HD / 16; ++kk) {
+            const uint32_t qoff = (uint32_t)(kk >> 2) * kTcQHalf + (uint32_t)(kk & 3) * 32;
+            const uint32_t koff = (uint32_t)(kk >> 2) * kTcKHalf + (uint32_t)(kk & 3) * 32;
+            umma_f16(tmem_base + sb * kTcKV, umma_desc_k_sw128(q_addr + qoff), umma_desc_k_sw128(k_addr + koff), idesc_qk,
+                     kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[sb]);
+          umma_commit(&kv_empty[sl]);
+          if (i + 1 == it.nt) umma_commit(&q_free);        // the Q tile may be replaced once these MMAs have completed
+          if (i > 0) issue_pv(i == 1);                     // P.V of the previous tile, behind this tile's QK^T
         }
-        umma_commit(&s_full[sb]);
-        umma_commit(&kv_empty[sl]);
-        if (i > 0) issue_pv(i - 1);                       // P.V of the previous tile, behind this tile's QK^T
+        issue_pv(it.nt == 1);
+        umma_commit(&o_done);
+        ++k;
       }
-      if (nt > 0) issue_pv(nt - 1);
-      umma_commit(&o_done);
     }
-  } else if (live) {
+  } else {
     // ------------------------------ softmax / epilogue warps (thread = query row) ------------------------------
     const int q = warp & 3;
     const int r = q * 32 + lane;                          // row inside the tile == TMEM lane
-    const int qi = q0 + r;                                // query index inside the sequence
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = scale * 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f;                 // m_run: the (lazily refreshed) maximum the exponents are taken against, in log2 units
-    for (int j = 0; j < nt; ++j) {
-      const int kv0 = j * kTcKV;
-      const bool need_mask = kv0 + kTcKV - 1 > q0;        // CTA-uniform: the tile reaches past the first query row
-      const uint32_t sb = (uint32_t)j & 1u;
-      const uint32_t s_addr = lane_base + sb * kTcKV;
-      mbar_wait(&s_full[sb], (uint32_t)(j >> 1) & 1u);
-      tc_fence_after();
-      uint32_t sv[kTcKV];
-#pragma unroll
-      for (int c = 0; c < kTcKV; c += 16) tmem_ld_32x32b_x16(s_addr + (uint32_t)c, sv + c);     // all four loads in flight, ONE wait
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[sb]);            // S[sb] is in registers: QK^T of tile j+2 may overwrite it
-      // The softmax warps are instruction-issue bound (ncu of the first single-pass version: ~1 500 instructions per warp and tile,
-      // 45 % issue-active, tensor pipe 15 %), so the per-element work is what the arithmetic needs and no more: FMNMX on the raw score,
-      // one FFMA + one MUFU.EX2 + one FADD, half a conversion; the causal select only in the (CTA-uniform) diagonal tiles.
-      float mx = -INFINITY;
-      if (need_mask) {
-#pragma unroll
-        for (int e = 0; e < kTcKV; ++e) mx = fmaxf(mx, kv0 + e <= qi ? __uint_as_float(sv[e]) : -INFINITY);
-      } else {
-#pragma unroll
-        for (int e = 0; e < kTcKV; ++e) mx = fmaxf(mx, __uint_as_float(sv[e]));
-      }
-      mx *= sl2;                                          // sl2 > 0: scaling commutes with the maximum
-      // lazy maximum: keep the old one unless the tile exceeds it by more than 8 (then P <= 2^8 everywhere)
-      float alpha = 1.f;
-      bool rescale = false;
-      if (mx > m_run + 8.f) {
-        rescale = m_run > -INFINITY;                      // the first finite maximum needs no rescale: l and O are still zero
-        alpha = rescale ? tc_ex2(m_run - mx) : 1.f;
-        m_run = mx;
-      }
-      const float mneg = m_run > -INFINITY ? -m_run : 0.f;
-      l_run *= alpha;
-      uint4 pk[kTcKV / 8];
-      float ls0 = 0.f, ls1 = 0.f;                         // two partial row sums: half the length of the dependent FADD chain
-      if (need_mask) {
-#pragma unroll
-        for (int c = 0; c < kTcKV; c += 8) {
-          float pv[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) pv[e] = kv0 + c + e <= qi ? tc_ex2(fmaf(__uint_as_float(sv[c + e]), sl2, mneg)) : 0.f;
-          ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-          ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
-          pk[c / 8] = pack8<T>(pv);
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < kTcKV; c += 8) {
-          float pv[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) pv[e] = tc_ex2(fmaf(__uint_as_float(sv[c + e]), sl2, mneg));
-          ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-          ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
-          pk[c / 8] = pack8<T>(pv);
-        }
-      }
-      l_run += ls0 + ls1;
-      if (j > 0) mbar_wait(&p_free, (uint32_t)(j - 1) & 1u);     // P.V(j-1) has completed: P may be overwritten, O may be rescaled
-      int any_rescale = rescale ? 1 : 0;                  // (shuffle tree instead of __any_sync: also runs on tests/cuda_on_cpu)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) any_rescale |= __shfl_xor_sync(0xffffffffu, any_rescale, o);
-      if (any_rescale) {                                  // warp-collective: rows that keep their maximum multiply by 1
+    uint32_t t = 0;                                       // S tiles consumed so far, over all items
+    uint32_t k = 0;                                       // live items started
+    for (int idx = blockIdx.x; idx < total_items; idx += gridDim.x) {
+      TcItem it;
+      if (!tc_item(idx, nqt, nh, nkv, batch, cu_seqlens, it)) continue;
+      const int q0 = it.q0, qi = q0 + r;                  // query index inside the sequence
+      float m_run = -INFINITY, l_run = 0.f;               // m_run: the (lazily refreshed) maximum the exponents are taken against, in log2 units
+      for (int j = 0; j < it.nt; ++j, ++t) {
+        const int kv0 = j * kTcKV;
+        const bool need_mask = kv0 + kTcKV - 1 > q0;      // CTA-uniform: the tile reaches past the first query row
+        const uint32_t sb = t & 1u;
+        const uint32_t s_addr = lane_base + sb * kTcKV;
+        mbar_wait(&s_full[sb], (t >> 1) & 1u);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < HD; c += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
-          tmem_ld_wait();
+        uint32_t sv[kTcKV];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-          tmem_st_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-      }
-      // P[r][0..63] -> K-major swizzled tile (row r, 16-byte chunk ch at ch ^ (r & 7))
-#pragma unroll
-      for (int ch = 0; ch < kTcKV / 8; ++ch)
-        *reinterpret_cast<uint4*>(p_s + (uint32_t)r * 128 + ((ch ^ (r & 7)) << 4)) = pk[ch];
-      fence_proxy_async_smem();                           // P must be visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full);
-    }
-    // ---- epilogue: O / l   (tcgen05.ld is warp-collective: every lane loads, rows inside the sequence are stored)
-    mbar_wait(&o_done, 0);
-    tc_fence_after();
-    {
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      T* o_g = out + ((long long)seq0 + (qi < len ? qi : 0)) * nh * HD + (long long)head * HD;
-#pragma unroll 1
-      for (int c = 0; c < HD; c += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
+        for (int c = 0; c < kTcKV; c += 16) tmem_ld_32x32b_x16(s_addr + (uint32_t)c, sv + c);     // all four loads in flight, ONE wait
         tmem_ld_wait();
-        if (qi < len) {
-          float f[16];
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[sb]);          // S[sb] is in registers: QK^T of tile t+2 may overwrite it
+        // The softmax warps are instruction-issue bound (ncu of the first single-pass version: ~1 500 instructions per warp and tile,
+        // 45 % issue-active, tensor pipe 15 %), so the per-element work is what the arithmetic needs and no more: FMNMX on the raw score,
+        // one FFMA + one MUFU.EX2 + one FADD, half a conversion; the causal select only in the (CTA-uniform) diagonal tiles.
+        float mx = -INFINITY;
+        if (need_mask) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) * inv;
-          *reinterpret_cast<uint4*>(o_g + c) = pack8<T>(f);
-          *reinterpret_cast<uint4*>(o_g + c + 8) = pack8<T>(f + 8);
+          for (int e = 0; e < kTcKV; ++e) mx = fmaxf(mx, kv0 + e <= qi ? __uint_as_float(sv[e]) : -INFINITY);
+        } else {
+#pragma unroll
+          for (int e = 0; e < kTcKV; ++e) mx = fmaxf(mx, __uint_as_float(sv[e]));
+        }
+        mx *= sl2;                                        // sl2 > 0: scaling commutes with the maximum
+        // lazy maximum: keep the old one unless the tile exceeds it by more than 8 (then P <= 2^8 everywhere)
+        float alpha = 1.f;
+        bool rescale = false;
+        if (mx > m_run + 8.f) {
+          rescale = m_run > -INFINITY;                    // the first finite maximum needs no rescale: l and O are still zero
+          alpha = rescale ? tc_ex2(m_run - mx) : 1.f;
+          m_run = mx;
+        }
+        const float mneg = m_run > -INFINITY ? -m_run : 0.f;
+        l_run *= alpha;
+        uint4 pk[kTcKV / 8];
+        float ls0 = 0.f, ls1 = 0.f;                       // two partial row sums: half the length of the dependent FADD chain
+        if (need_mask) {
+#pragma unroll
+          for (int c = 0; c < kTcKV; c += 8) {
+            float pv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pv[e] = kv0 + c + e <= qi ? tc_ex2(fmaf(__uint_as_float(sv[c + e]), sl2, mneg)) : 0.f;
+            ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+            ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+            pk[c / 8] = pack8<T>(pv);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kTcKV; c += 8) {
+            float pv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) pv[e] = tc_ex2(fmaf(__uint_as_float(sv[c + e]), sl2, mneg));
+            ls0 += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+            ls1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+            pk[c / 8] = pack8<T>(pv);
+          }
+        }
+        l_run += ls0 + ls1;
+        if (t > 0) mbar_wait(&p_free, (t - 1) & 1u);      // the previous P.V (of this item or the one before) has completed: P may be overwritten, O rescaled
+        int any_rescale = rescale ? 1 : 0;                // (shuffle tree instead of __any_sync: also runs on tests/cuda_on_cpu)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) any_rescale |= __shfl_xor_sync(0xffffffffu, any_rescale, o);
+        if (any_rescale) {                                // warp-collective: rows that keep their maximum multiply by 1
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < HD; c += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+            tmem_st_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        // P[r][0..63] -> K-major swizzled tile (row r, 16-byte chunk ch at ch ^ (r & 7))
+#pragma unroll
+        for (int ch = 0; ch < kTcKV / 8; ++ch)
+          *reinterpret_cast<uint4*>(p_s + (uint32_t)r * 128 + ((ch ^ (r & 7)) << 4)) = pk[ch];
+        fence_proxy_async_smem();                         // P must be visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full);
+      }
+      // ---- epilogue: O / l   (tcgen05.ld is warp-collective: every lane loads, rows inside the sequence are stored)
+      mbar_wait(&o_done, k & 1u);
+      tc_fence_after();
+      {
+        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+        const bool row_ok = qi < it.len;
+        T* o_g = out + ((long long)it.seq0 + (row_ok ? qi : 0)) * nh * HD + (long long)it.head * HD;
+#pragma unroll 1
+        for (int c = 0; c < HD; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
+          tmem_ld_32x32b_x16(lane_base + 128u + (uint32_t)c + 16u, v + 16);
+          tmem_ld_wait();
+          if (c + 32 == HD) {                             // O is in registers: the next item's first P.V may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free);
+          }
+          if (row_ok) {
+            float f[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]) * inv;
+#pragma unroll
+            for (int e = 0; e < 32; e += 8) *reinterpret_cast<uint4*>(o_g + c + e) = pack8<T>(f + e);
+          }
+        }
+        if constexpr (LSE) {
+          if (row_ok) lse[((long long)it.seq0 + qi) * nh + it.head] = l_run > 0.f ? m_run * 0.6931471805599453f + logf(l_run) : -INFINITY;   // m_run is in log2 units
         }
       }
-      if constexpr (LSE) {
-        if (qi < len) lse[((long long)seq0 + qi) * nh + head] = l_run > 0.f ? m_run * 0.6931471805599453f + logf(l_run) : -INFINITY;   // m_run is in log2 units
-      }
+      ++k;
     }
   }
   tc_fence_before();
@@ -862,13 +913,18 @@ static int attn_prefill_impl(cts_ctx* ctx, const void* q, const void* k, const v
     if (rc) return rc;
     rc = cts_make_tmap_2d(ctx, &tm_v, v, total_tokens, (long long)nkv * 128, (long long)nkv * 128, kTcKV, dtype == CTS_BF16);
     if (rc) return rc;
-    dim3 g5((unsigned)((max_seqlen + kTcQ - 1) / kTcQ), (unsigned)nh, (unsigned)batch);
+    const int nqt = (max_seqlen + kTcQ - 1) / kTcQ;
+    long long items = (long long)nqt * nh * batch;
+    CTS_CHECK_ARG(ctx, items < 2147483647LL, "too many (query tile, head, sequence) items");
+    long long ctas = 2LL * ctx->sm_count;                 // persistent: two CTAs per SM (shared memory and TMEM columns allow exactly two)
+    if (ctas > items) ctas = items;
+    dim3 g5((unsigned)ctas, 1, 1);
     const size_t smem5 = (size_t)kTcSmem + 1024;
 #define TC5_LAUNCH(TT, LSEV)                                                                                 \
   {                                                                                                          \
     auto kern = attn_prefill_tc5_kernel<TT, LSEV>;                                                           \
     CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));      \
-    CTS_CUDA(ctx, launch_pdl(kern, g5, dim3(kTcThreads), smem5, st, 1, tm_q, tm_k, tm_v, cu_seqlens, nh, nkv, scale, (TT*)out, lse)); \
+    CTS_CUDA(ctx, launch_pdl(kern, g5, dim3(kTcThreads), smem5, st, 1, tm_q, tm_k, tm_v, cu_seqlens, nh, nkv, batch, nqt, scale, (TT*)out, lse)); \
   }
     if (dtype == CTS_BF16) {
       if (lse) TC5_LAUNCH(__nv_bfloat16, true) else TC5_LAUNCH(__nv_bfloat16, false)

@@ -32,9 +32,18 @@ def test_prefill_growing_scores_force_the_lazy_rescale(lens, DT):
     _prefill_case(128, lens, DT, ramp=True)
 
 
-def _prefill_case(d, lens, DT, ramp=False):
+@pytest.mark.parametrize("DT", [torch.bfloat16, torch.float16])
+def test_prefill_many_items_per_persistent_cta(DT):
+    """The tcgen05 kernel runs 2 x SMs persistent CTAs over the (query tile, head, sequence) items.  40 sequences x 8 heads x 3 query
+    tiles = 960 items: every CTA walks through three or four of them -- dead ones (sequences shorter than the longest) included -- so the
+    barrier phases, the Q hand-over (q_free) and the O hand-over (o_free) carry across items."""
+    lens = [300, 17, 129, 256, 1, 64, 200, 299, 128, 65] * 4
+    _prefill_case(128, lens, DT, nh=8)
+
+
+def _prefill_case(d, lens, DT, ramp=False, nh=4):
     c = ctx()
-    nh, nkv = 4, 2
+    nkv = 2
     T = sum(lens)
     g = torch.Generator().manual_seed(T + d)
     q = torch.randn(T, nh, d, generator=g).to(DT)
