@@ -250,7 +250,7 @@ attn_prefill_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* _
 // Round 1-2 ran two passes (row maxima first, so that O never needed a rescale): 1.5 x the tensor work and twice the
 // TMEM reads of S per tile; 254 TFLOP/s at 32 x 576 (profiles/r2_prefill_attention_vs_installed.json).  Causal masking
 // only touches the tiles on the diagonal (query tiles are 128, key tiles 64, both aligned).  Epilogue: O / l from TMEM to global.
-constexpr int kTcQ = 128, kTcKV = 64, kTcThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 softmax: TWO warps per 32-row block (each half of the key columns)
+constexpr int kTcQ = 128, kTcKV = 64, kTcThreads = 192;
 constexpr int kTcQHalf = kTcQ * 128;            // one [128 q rows x 128 B] swizzled half of the Q tile (16 KiB)
 constexpr int kTcKHalf = kTcKV * 128;           // one [64 kv rows x 128 B] half of a K or V tile (8 KiB)
 constexpr int kTcStages = 3;                    // K/V ring: tiles of 2 x 8 KiB, consumed in the order they are loaded
@@ -321,6 +321,10 @@ __device__ __forceinline__ bool tc_warp_any(bool p) {
 #endif
 }
 
+// Measured and rejected (profiles/r2_attention_two_warps_per_row_block_rejected.json, git history): two softmax warps per 32-row block,
+// each taking half of a tile's key columns and exchanging the half-row maxima over a 64-thread named barrier -- half the instructions per
+// warp and tile, and 5 % SLOWER (301 vs 286 us at 32 x 576, 891 vs 853 us at 4 x 4096): the softmax instruction stream is not the
+// critical path any more; what remains is the chain of barrier round trips (S ready -> P ready -> P.V done) per 64-key tile.
 template <typename T, bool LSE>
 __global__ void __launch_bounds__(kTcThreads, 2)
 attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -330,8 +334,6 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   extern __shared__ uint8_t tc_raw[];
   __shared__ uint64_t q_bar, q_free, kv_full[kTcStages], kv_empty[kTcStages], s_full[2], s_free[2], p_full, p_free, o_done, o_free;
   __shared__ uint32_t tmem_slot;
-  __shared__ float mx_s[2][2][kTcQ];                 // [tile parity][column half][row]: the two warps of a row block exchange their half-row maxima
-  __shared__ float l_s[2][kTcQ];                     // [column half][row]: row sums of the two halves, combined in the epilogue
   const uint32_t raw = smem_u32(tc_raw);
   uint8_t* smem = tc_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* q_s = smem;                               // 32 KiB: 2 d-halves x [128 x 128 B]
@@ -346,11 +348,11 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     mbar_init(&q_bar, 1);
     mbar_init(&q_free, 1);
     for (int s = 0; s < kTcStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 8); }
-    mbar_init(&p_full, 8);
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 4); }
+    mbar_init(&p_full, 4);
     mbar_init(&p_free, 1);
     mbar_init(&o_done, 1);
-    mbar_init(&o_free, 8);
+    mbar_init(&o_free, 4);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<256>(&tmem_slot);
@@ -450,15 +452,8 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       }
     }
   } else {
-    // ------------------------------ softmax / epilogue warps ------------------------------
-    // thread = (query row, half of the tile's key columns): warps w and w + 4 own the same 32 TMEM lanes (a warp may only touch lanes
-    // 32 (w % 4) ..) and split the 64 columns of S, the 64 + 64 columns of O and the 4 + 4 chunks of a P row.  The softmax warps were the
-    // critical path (one thread per row: ~350 dependent-ish instructions per tile, tensor pipe 27 %); two threads per row halve it for
-    // the price of one 64-thread named barrier per tile, over which the halves exchange their maxima so that both take the same lazy
-    // decision; the row sums stay per half (same exponent base) and meet in the epilogue.
-    constexpr int kHalfCols = kTcKV / 2;                  // 32
+    // ------------------------------ softmax / epilogue warps (thread = query row) ------------------------------
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;                     // 0: key columns 0..31 of a tile, O columns 0..63; 1: the others
     const int r = q * 32 + lane;                          // row inside the tile == TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const float sl2 = scale * 1.4426950408889634f;
@@ -468,35 +463,34 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       TcItem it;
       if (!tc_item(idx, nqt, nh, nkv, batch, cu_seqlens, it)) continue;
       const int q0 = it.q0, qi = q0 + r;                  // query index inside the sequence
-      float m_run = -INFINITY, l_run = 0.f;               // m_run: the (lazily refreshed) maximum the exponents are taken against, in log2 units; l_run: this half's sum
+      float m_run = -INFINITY, l_run = 0.f;               // m_run: the (lazily refreshed) maximum the exponents are taken against, in log2 units
       for (int j = 0; j < it.nt; ++j, ++t) {
-        const int kv0 = j * kTcKV + half * kHalfCols;     // first key of this thread's columns
-        const bool need_mask = j * kTcKV + kTcKV - 1 > q0;   // CTA-uniform: the tile reaches past the first query row
+        const int kv0 = j * kTcKV;
+        const bool need_mask = kv0 + kTcKV - 1 > q0;      // CTA-uniform: the tile reaches past the first query row
         const uint32_t sb = t & 1u;
-        const uint32_t s_addr = lane_base + sb * kTcKV + (uint32_t)(half * kHalfCols);
+        const uint32_t s_addr = lane_base + sb * kTcKV;
         mbar_wait(&s_full[sb], (t >> 1) & 1u);
         tc_fence_after();
-        uint32_t sv[kHalfCols];
-        tmem_ld_32x32b_x16(s_addr, sv);                   // both loads in flight, ONE wait
-        tmem_ld_32x32b_x16(s_addr + 16u, sv + 16);
+        uint32_t sv[kTcKV];
+#pragma unroll
+        for (int c = 0; c < kTcKV; c += 16) tmem_ld_32x32b_x16(s_addr + (uint32_t)c, sv + c);     // all four loads in flight, ONE wait
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[sb]);          // this half of S[sb] is in registers (QK^T of tile t+2 waits for all eight warps)
-        // per element: FMNMX on the raw score, one FFMA + one MUFU.EX2 + one FADD, half a conversion; the causal select only in the
-        // (CTA-uniform) diagonal tiles
+        if (lane == 0) mbar_arrive(&s_free[sb]);          // S[sb] is in registers: QK^T of tile t+2 may overwrite it
+        // The softmax warps are instruction-issue bound (ncu of the first single-pass version: ~1 500 instructions per warp and tile,
+        // 45 % issue-active, tensor pipe 15 %), so the per-element work is what the arithmetic needs and no more: FMNMX on the raw score,
+        // one FFMA + one MUFU.EX2 + one FADD, half a conversion; the causal select only in the (CTA-uniform) diagonal tiles.
         float mx = -INFINITY;
         if (need_mask) {
 #pragma unroll
-          for (int e = 0; e < kHalfCols; ++e) mx = fmaxf(mx, kv0 + e <= qi ? __uint_as_float(sv[e]) : -INFINITY);
+          for (int e = 0; e < kTcKV; ++e) mx = fmaxf(mx, kv0 + e <= qi ? __uint_as_float(sv[e]) : -INFINITY);
         } else {
 #pragma unroll
-          for (int e = 0; e < kHalfCols; ++e) mx = fmaxf(mx, __uint_as_float(sv[e]));
+          for (int e = 0; e < kTcKV; ++e) mx = fmaxf(mx, __uint_as_float(sv[e]));
         }
-        mx_s[t & 1u][half][r] = mx;
-        named_bar_sync(1 + q, 64);                        // the two warps of this row block (buffer t & 1 is rewritten two barriers later)
-        mx = fmaxf(mx, mx_s[t & 1u][half ^ 1][r]) * sl2;  // sl2 > 0: scaling commutes with the maximum
-        // lazy maximum: keep the old one unless the tile exceeds it by more than 8 (then P <= 2^8 everywhere); identical in both halves
+        mx *= sl2;                                        // sl2 > 0: scaling commutes with the maximum
+        // lazy maximum: keep the old one unless the tile exceeds it by more than 8 (then P <= 2^8 everywhere)
         float alpha = 1.f;
         bool rescale = false;
         if (mx > m_run + 8.f) {
@@ -506,11 +500,11 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         }
         const float mneg = m_run > -INFINITY ? -m_run : 0.f;
         l_run *= alpha;
-        uint4 pk[kHalfCols / 8];
-        float ls0 = 0.f, ls1 = 0.f;                       // two partial sums: half the length of the dependent FADD chain
+        uint4 pk[kTcKV / 8];
+        float ls0 = 0.f, ls1 = 0.f;                       // two partial row sums: half the length of the dependent FADD chain
         if (need_mask) {
 #pragma unroll
-          for (int c = 0; c < kHalfCols; c += 8) {
+          for (int c = 0; c < kTcKV; c += 8) {
             float pv[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) pv[e] = kv0 + c + e <= qi ? tc_ex2(fmaf(__uint_as_float(sv[c + e]), sl2, mneg)) : 0.f;
@@ -520,7 +514,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < kHalfCols; c += 8) {
+          for (int c = 0; c < kTcKV; c += 8) {
             float pv[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) pv[e] = tc_ex2(fmaf(__uint_as_float(sv[c + e]), sl2, mneg));
@@ -534,7 +528,7 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         if (tc_warp_any(rescale)) {                       // warp-collective: rows that keep their maximum multiply by 1
           tc_fence_after();
 #pragma unroll 1
-          for (int c = half * (HD / 2); c < (half + 1) * (HD / 2); c += 16) {
+          for (int c = 0; c < HD; c += 16) {
             uint32_t v[16];
             tmem_ld_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
             tmem_ld_wait();
@@ -545,48 +539,44 @@ attn_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
           tmem_st_wait();
           tc_fence_before();
         }
-        // this half of P[r] -> K-major swizzled tile (row r, 16-byte chunk ch at ch ^ (r & 7))
+        // P[r][0..63] -> K-major swizzled tile (row r, 16-byte chunk ch at ch ^ (r & 7))
 #pragma unroll
-        for (int ch = 0; ch < kHalfCols / 8; ++ch) {
-          const int gch = half * (kHalfCols / 8) + ch;
-          *reinterpret_cast<uint4*>(p_s + (uint32_t)r * 128 + ((gch ^ (r & 7)) << 4)) = pk[ch];
-        }
+        for (int ch = 0; ch < kTcKV / 8; ++ch)
+          *reinterpret_cast<uint4*>(p_s + (uint32_t)r * 128 + ((ch ^ (r & 7)) << 4)) = pk[ch];
         fence_proxy_async_smem();                         // P must be visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full);
       }
-      // ---- epilogue: O / l, this warp's 64 columns   (tcgen05.ld is warp-collective: every lane loads, rows inside the sequence are stored)
-      l_s[half][r] = l_run;
+      // ---- epilogue: O / l   (tcgen05.ld is warp-collective: every lane loads, rows inside the sequence are stored)
       mbar_wait(&o_done, k & 1u);
       tc_fence_after();
-      named_bar_sync(1 + q, 64);                          // the partner's half sum is visible (and its tile loop has finished with mx_s)
       {
-        const float l_tot = l_s[0][r] + l_s[1][r];
-        const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
         const bool row_ok = qi < it.len;
         T* o_g = out + ((long long)it.seq0 + (row_ok ? qi : 0)) * nh * HD + (long long)it.head * HD;
-        uint32_t v[64];
-        const uint32_t o_addr = lane_base + 128u + (uint32_t)(half * (HD / 2));
+#pragma unroll 1
+        for (int c = 0; c < HD; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x16(lane_base + 128u + (uint32_t)c, v);
+          tmem_ld_32x32b_x16(lane_base + 128u + (uint32_t)c + 16u, v + 16);
+          tmem_ld_wait();
+          if (c + 32 == HD) {                             // O is in registers: the next item's first P.V may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free);
+          }
+          if (row_ok) {
+            float f[32];
 #pragma unroll
-        for (int c = 0; c < HD / 2; c += 16) tmem_ld_32x32b_x16(o_addr + (uint32_t)c, v + c);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_free);              // this warp's half of O is in registers: the next item's first P.V waits for all eight
-        if (row_ok) {
+            for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]) * inv;
 #pragma unroll
-          for (int c = 0; c < HD / 2; c += 8) {
-            float f[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c + e]) * inv;
-            *reinterpret_cast<uint4*>(o_g + half * (HD / 2) + c) = pack8<T>(f);
+            for (int e = 0; e < 32; e += 8) *reinterpret_cast<uint4*>(o_g + c + e) = pack8<T>(f + e);
           }
         }
         if constexpr (LSE) {
-          if (row_ok && half == 0) lse[((long long)it.seq0 + qi) * nh + it.head] = l_tot > 0.f ? m_run * 0.6931471805599453f + logf(l_tot) : -INFINITY;   // m_run is in log2 units
+          if (row_ok) lse[((long long)it.seq0 + qi) * nh + it.head] = l_run > 0.f ? m_run * 0.6931471805599453f + logf(l_run) : -INFINITY;   // m_run is in log2 units
         }
       }
-      named_bar_sync(1 + q, 64);                          // both have read l_s: the next item may overwrite it
       ++k;
     }
   }
