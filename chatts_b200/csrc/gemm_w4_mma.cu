@@ -8,10 +8,11 @@
 //     words ARE the A fragments of mma.sync.m16n8k16 -- lane (g, t) of m-tile j finds, for each of the block's four k16 steps, one
 //     word holding the 8 codes {rows g / g+8} x {k 2t, 2t+1, 2t+8, 2t+9} in the nibble order that `(w >> 4i) & 0x000F000F` turns
 //     into fragment register a_i; next to it 1 KB of {scale, 128+zero-point} pairs of the block's group
-//   * warp 8, one lane: cp.async.bulk of those chunks into a deep ring (7-11 x 9 KB per CTA, two or three CTAs per SM = what keeps HBM busy),
-//     issued BEFORE the dependency wait (nobody writes weights); warp 9, one lane: the token tile [8 NT rows x 64 K] by TMA (128B
-//     swizzle) after the wait
-//   * warps 0..7: one LDS.128 per m-tile = the fragments of four k16 steps; int4 -> bf16/fp16 in registers with the magic-number trick
+//   * warp 8, one lane: per 128-K pipeline stage one cp.async.bulk of 16 KB of codes (evict-first) + the group's scales, issued for the
+//     whole ring BEFORE the dependency wait (nobody writes weights), and -- after the wait -- the two token tiles [8 NT rows x 64 K] by
+//     TMA (128B swizzle) onto the SAME barrier: one wait and one arrival per stage and warp (3-5 stages of 19-25 KB per CTA, two or
+//     three CTAs per SM = 150-200 KB in flight per SM)
+//   * warps 0..7: one LDS.128 per m-tile and 64-K block = the fragments of four k16 steps; int4 -> bf16/fp16 in registers with the magic-number trick
 //     of gemm_w4.cu (exactly the value dequantize_w4 stores for the prefill copy); B fragments by ldmatrix from the swizzled token
 //     tile; mma.sync with the fp32 accumulators of 2 m-tiles x NT n-tiles in registers
 //   * persistent CTAs over (tile, K split) units, the producers run ahead across unit boundaries
@@ -35,16 +36,16 @@
 namespace {
 
 constexpr int kTileN = 256, kBK = 64, kWarps = 8;
+constexpr int kKS = 2;                               // K blocks per pipeline stage: one barrier round trip, one ring step, one scale fetch per 128 K
 constexpr int kWBytes = kTileN * kBK / 2;            // 8192: the codes of one (tile, K block)
-constexpr int kSzBytes = kTileN * 4;                 // 1024: {scale bits | (magic + zero point) << 16} per feature
-constexpr int kStageBytes = kWBytes + kSzBytes;      // 9216
-constexpr int kThreads = (kWarps + 2) * 32;
-constexpr int kMaxStagesW = 24, kMaxStagesX = 8;
+constexpr int kSzBytes = kTileN * 4;                 // 1024: {scale bits | (magic + zero point) << 16} per feature of one group
+constexpr int kThreads = (kWarps + 1) * 32;          // eight compute warps + one producer warp
+constexpr int kMaxStages = 12;
 
 struct W4mParams {
   long long n, k, t;
-  int kb_total, split_k, kb_per_group, n_groups, tiles, stages_w, stages_x;
-  const uint8_t* qw;       // [tiles][kb_total][8192]
+  int ks_total, split_k, kb_per_group, n_groups, tiles, stages, sz_groups;   // ks_total = K / 128; sz_groups = group entries a stage carries (2 at group size 64, else 1)
+  const uint8_t* qw;       // [tiles][K / 64][8192]
   const uint8_t* szp;      // [tiles][n_groups][1024]
   float* out;              // fp32 [split_k, t, n]
 };
@@ -111,84 +112,88 @@ __device__ __forceinline__ void w4m_bulk_stream(void* smem_dst, const void* gsrc
 #endif
 }
 
-// unit u of the persistent schedule -> (tile, split, K block range)
-__device__ __forceinline__ void w4m_unit(const W4mParams& p, int u, int& tile, int& split, int& kb0, int& kb1) {
+// unit u of the persistent schedule -> (tile, split, range of 128-K stages)
+__device__ __forceinline__ void w4m_unit(const W4mParams& p, int u, int& tile, int& split, int& ks0, int& ks1) {
   tile = u % p.tiles;
   split = u / p.tiles;
-  kb0 = (int)(((long long)p.kb_total * split) / p.split_k);
-  kb1 = (int)(((long long)p.kb_total * (split + 1)) / p.split_k);
+  ks0 = (int)(((long long)p.ks_total * split) / p.split_k);
+  ks1 = (int)(((long long)p.ks_total * (split + 1)) / p.split_k);
 }
 
+// One pipeline stage in shared memory: [token tile of K block 0 | token tile of K block 1 | 16 KB of codes | sz_groups KB of scales / zero
+// points], 1 KB aligned (the 128B swizzle of the token tiles repeats every 8 rows).
 template <typename T, int NT>
 __global__ void __launch_bounds__(kThreads, NT == 1 ? 3 : 2)
 gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) {
   CTS_DYN_SMEM(smem_raw);
-  __shared__ uint64_t w_full[kMaxStagesW], w_empty[kMaxStagesW], x_full[kMaxStagesX], x_empty[kMaxStagesX];
+  __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
 
-  constexpr int kXBytes = NT * 8 * kBK * 2;                 // token tile: 8 NT rows of 128 bytes
+  constexpr int kXBytes = NT * 8 * kBK * 2;                 // token tile of one K block: 8 NT rows of 128 bytes
+  constexpr int kXStage = kKS * kXBytes;
+  const int stage_bytes = kXStage + kKS * kWBytes + p.sz_groups * kSzBytes;
   const uint32_t raw = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-  uint8_t* x_s = smem;                                       // stages_x x kXBytes (1024-byte aligned: the swizzle pattern repeats every 8 rows)
-  uint8_t* w_s = smem + (size_t)p.stages_x * kXBytes;        // stages_w x 9216
+  uint8_t* ring = smem_raw + (((raw + 1023u) & ~1023u) - raw);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int SW = p.stages_w, SX = p.stages_x;
+  const int S = p.stages;
   const int units = p.tiles * p.split_k;
 
   pdl_trigger();
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_x);
-    for (int s = 0; s < SW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], kWarps); }
-    for (int s = 0; s < SX; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], kWarps); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kWarps); }
     fence_mbar_init();
   }
   __syncthreads();
 
   if (warp == kWarps) {
-    // ------------------------------ weight producer (static data: no dependency wait) ------------------------------
+    // ------------------------------ producer: codes + scales (static: requested BEFORE the dependency wait), token tiles after it ------------------------------
     if (lane == 0) {
-      int s = 0;
+      auto issue_static = [&](int s, int tile, int ks) {
+        uint8_t* dst = ring + (size_t)s * stage_bytes + kXStage;
+        mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+        w4m_bulk_stream(dst, p.qw + ((size_t)tile * (p.ks_total * kKS) + (size_t)ks * kKS) * kWBytes, (uint32_t)(kKS * kWBytes), &full_bar[s]);
+        const int grp = (ks * kKS) / p.kb_per_group;          // first group the stage touches (sz_groups = 2: the two blocks are two groups)
+        bulk_load_1d(dst + kKS * kWBytes, p.szp + ((size_t)tile * p.n_groups + grp) * kSzBytes, (uint32_t)(p.sz_groups * kSzBytes), &full_bar[s]);
+      };
+      auto issue_tokens = [&](int s, int ks) {
+        uint8_t* dst = ring + (size_t)s * stage_bytes;
+#pragma unroll
+        for (int b = 0; b < kKS; ++b) tma_load_2d(dst + b * kXBytes, &tm_x, &full_bar[s], (ks * kKS + b) * kBK, 0, CTS_L2_EVICT_LAST);
+      };
+      // the first S stages of this CTA's schedule: static part now, token tiles once the predecessor has finished
+      int pre = 0;
+      {
+        int s = 0;
+        for (int u = blockIdx.x; u < units && s < S; u += gridDim.x) {
+          int tile, split, ks0, ks1;
+          w4m_unit(p, u, tile, split, ks0, ks1);
+          for (int ks = ks0; ks < ks1 && s < S; ++ks, ++s) issue_static(s, tile, ks);
+        }
+        pre = s;
+      }
+      pdl_wait();
+      int s = 0, n = 0;
       uint32_t ph = 1u;                                      // parity of the "slot is empty" phase being waited for (fresh barrier: passes)
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        int tile, split, kb0, kb1;
-        w4m_unit(p, u, tile, split, kb0, kb1);
-        const uint8_t* src = p.qw + ((size_t)tile * p.kb_total + kb0) * kWBytes;
-        int grp = kb0 / p.kb_per_group, in_grp = kb0 % p.kb_per_group;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&w_empty[s], ph);
-          uint8_t* dst = w_s + (size_t)s * kStageBytes;
-          mbar_expect_tx(&w_full[s], (uint32_t)kStageBytes);
-          w4m_bulk_stream(dst, src, (uint32_t)kWBytes, &w_full[s]);
-          bulk_load_1d(dst + kWBytes, p.szp + ((size_t)tile * p.n_groups + grp) * kSzBytes, (uint32_t)kSzBytes, &w_full[s]);
-          src += kWBytes;
-          if (++in_grp == p.kb_per_group) { in_grp = 0; ++grp; }
-          if (++s == SW) { s = 0; ph ^= 1u; }
-        }
-      }
-    }
-  } else if (warp == kWarps + 1) {
-    // ------------------------------ token-tile producer (the predecessor's output) ------------------------------
-    if (lane == 0) {
-      pdl_wait();
-      int s = 0;
-      uint32_t ph = 1u;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        int tile, split, kb0, kb1;
-        w4m_unit(p, u, tile, split, kb0, kb1);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&x_empty[s], ph);
-          mbar_expect_tx(&x_full[s], (uint32_t)kXBytes);
-          tma_load_2d(x_s + (size_t)s * kXBytes, &tm_x, &x_full[s], kb * kBK, 0, CTS_L2_EVICT_LAST);
-          if (++s == SX) { s = 0; ph ^= 1u; }
+        int tile, split, ks0, ks1;
+        w4m_unit(p, u, tile, split, ks0, ks1);
+        for (int ks = ks0; ks < ks1; ++ks, ++n) {
+          if (n >= pre) {
+            mbar_wait(&empty_bar[s], ph);
+            issue_static(s, tile, ks);
+          }
+          issue_tokens(s, ks);
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else {
     // ------------------------------ dequantise in registers + mma.sync ------------------------------
-    // The loop below is instruction-issue bound (ncu of the first version: 363 SASS instructions per stage and warp, 56 % issue-active,
-    // the 4-bit stream at 36 % of the HBM roof), so everything that does not depend on the stage is hoisted: the lane's offsets into
-    // the weight chunk / the scale table / the swizzled token tile, the mask and magic constants as REGISTER operands of one lop3
-    // ((w & mask) | magic; with immediates the compiler needs two), ring addresses advanced by addition.
+    // The loop is instruction-issue bound (ncu: 57-59 % issue-active with six warps per scheduler, `wait` the top stall), so per 64-K
+    // block only what the arithmetic needs is left -- 2 LDS.128, 8 x (3 shifts + 4 lop3 + 4 HADD2 + 4 HMUL2), the ldmatrix of the token
+    // fragments, the MMAs -- and everything else is paid once per 128-K stage: ONE barrier wait and ONE arrival (codes, scales and both
+    // token tiles share the stage's barrier), one scale fetch, one ring step.
     const int g = lane >> 2, tq = lane & 3;
     const int lrow = lane & 7, lmat = lane >> 3;             // ldmatrix: this lane supplies row `lrow` of matrix `lmat`
     float acc[2][NT][4];
@@ -200,8 +205,8 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
         for (int j = 0; j < 4; ++j) acc[mi][nt][j] = 0.f;
     uint32_t sA[2] = {0, 0}, bA[2] = {0, 0}, sB[2] = {0, 0}, bB[2] = {0, 0};   // {scale, magic + zp} of rows g / g + 8 of the two m-tiles
     const uint32_t kMask = w4m_opaque(0x000F000Fu), kMagic = w4m_opaque(MagicM<T>::kOr);
-    const uint32_t w_off = (uint32_t)((warp * 2 * 32 + lane) * 16);           // this lane's word quadruple of m-tile 2 warp (+ 512: m-tile 2 warp + 1)
-    const uint32_t sz_off = (uint32_t)(kWBytes + (warp * 2 * 16 + g) * 4);
+    const uint32_t w_off = (uint32_t)(kXStage + (warp * 2 * 32 + lane) * 16);   // this lane's word quadruple of m-tile 2 warp (+ 512: m-tile 2 warp + 1)
+    const uint32_t sz_off = (uint32_t)(kXStage + kKS * kWBytes + (warp * 2 * 16 + g) * 4);
     // ldmatrix row addresses inside a token tile for k16 step 0; step ks: XOR with ks << 5 (the chunk index 2 ks + h enters the 128B swizzle by XOR)
     uint32_t x_off[NT == 1 ? 1 : NT / 2];
     if constexpr (NT == 1) {
@@ -210,68 +215,63 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
 #pragma unroll
       for (int pr = 0; pr < NT / 2; ++pr) x_off[pr] = (uint32_t)(((2 * pr + (lmat >> 1)) * 8 + lrow) * 128 + (((lmat & 1) ^ lrow) << 4));
     }
-    int s = 0, sx = 0;
-    uint32_t ph = 0u, phx = 0u;                              // parities of the "slot is full" phases
-    const uint8_t* ws = w_s;                                 // slot s of the weight ring
-    uint32_t xs = smem_u32(x_s);                             // slot sx of the token ring
+    const bool per_block_groups = p.sz_groups == 2;          // group size 64: each K block of a stage has its own scales
+    int s = 0;
+    uint32_t ph = 0u;                                        // parity of the "slot is full" phase
+    const uint8_t* st = ring;                                // slot s
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      int tile, split, kb0, kb1;
-      w4m_unit(p, u, tile, split, kb0, kb1);
-      int in_grp = kb0 % p.kb_per_group;                     // blocks of the current group already behind kb; the unit's first block always fetches
-      bool fetch = true;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&w_full[s], ph);
-        uint4 wv[2];
-        wv[0] = *reinterpret_cast<const uint4*>(ws + w_off);
-        wv[1] = *reinterpret_cast<const uint4*>(ws + w_off + 512);
-        if (fetch) {
-          const uint8_t* sz = ws + sz_off;
+      int tile, split, ks0, ks1;
+      w4m_unit(p, u, tile, split, ks0, ks1);
+      for (int ks = ks0; ks < ks1; ++ks) {
+        mbar_wait(&full_bar[s], ph);
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
-            const uint32_t va = *reinterpret_cast<const uint32_t*>(sz + mi * 64), vb = *reinterpret_cast<const uint32_t*>(sz + mi * 64 + 32);
-            sA[mi] = (va & 0xFFFFu) * 0x00010001u; bA[mi] = (va >> 16) * 0x00010001u;      // both halves of a packed pair
-            sB[mi] = (vb & 0xFFFFu) * 0x00010001u; bB[mi] = (vb >> 16) * 0x00010001u;
-          }
-        }
-        fetch = (++in_grp == p.kb_per_group);
-        if (fetch) in_grp = 0;
-        mbar_wait(&x_full[sx], phx);
-        uint32_t rq[4] = {0u, 0u, 0u, 0u};                    // NT == 1: the fragments of a pair of k16 steps
+        for (int b = 0; b < kKS; ++b) {
+          uint4 wv[2];
+          wv[0] = *reinterpret_cast<const uint4*>(st + w_off + b * kWBytes);
+          wv[1] = *reinterpret_cast<const uint4*>(st + w_off + b * kWBytes + 512);
+          if (b == 0 || per_block_groups) {
+            const uint8_t* sz = st + sz_off + (per_block_groups ? b * kSzBytes : 0);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t bf[NT][2];                                 // B fragments of this k16 step
-          if constexpr (NT == 1) {
-            if ((ks & 1) == 0) w4m_ldsm_x4((xs + x_off[0]) ^ (uint32_t)((ks >> 1) << 6), rq);
-            bf[0][0] = (ks & 1) ? rq[2] : rq[0]; bf[0][1] = (ks & 1) ? rq[3] : rq[1];
-          } else {
-            // one ldmatrix.x4 = one k16 step of two 8-token tiles: matrices (nt, half) = (2p, 0), (2p, 1), (2p + 1, 0), (2p + 1, 1)
-#pragma unroll
-            for (int pr = 0; pr < NT / 2; ++pr) {
-              uint32_t r[4];
-              w4m_ldsm_x4((xs + x_off[pr]) ^ (uint32_t)(ks << 5), r);
-              bf[2 * pr][0] = r[0]; bf[2 * pr][1] = r[1]; bf[2 * pr + 1][0] = r[2]; bf[2 * pr + 1][1] = r[3];
+            for (int mi = 0; mi < 2; ++mi) {
+              const uint32_t va = *reinterpret_cast<const uint32_t*>(sz + mi * 64), vb = *reinterpret_cast<const uint32_t*>(sz + mi * 64 + 32);
+              sA[mi] = (va & 0xFFFFu) * 0x00010001u; bA[mi] = (va >> 16) * 0x00010001u;      // both halves of a packed pair
+              sB[mi] = (vb & 0xFFFFu) * 0x00010001u; bB[mi] = (vb >> 16) * 0x00010001u;
             }
           }
+          const uint32_t xs = smem_u32(st) + (uint32_t)(b * kXBytes);
+          uint32_t rq[4] = {0u, 0u, 0u, 0u};                  // NT == 1: the fragments of a pair of k16 steps
 #pragma unroll
-          for (int mi = 0; mi < 2; ++mi) {
-            const uint32_t w = ks == 0 ? wv[mi].x : ks == 1 ? wv[mi].y : ks == 2 ? wv[mi].z : wv[mi].w;
-            uint32_t a[4];
-            a[0] = MagicM<T>::sub_mul(w4m_and_or(w, kMask, kMagic), bA[mi], sA[mi]);
-            a[1] = MagicM<T>::sub_mul(w4m_and_or(w >> 4, kMask, kMagic), bB[mi], sB[mi]);
-            a[2] = MagicM<T>::sub_mul(w4m_and_or(w >> 8, kMask, kMagic), bA[mi], sA[mi]);
-            a[3] = MagicM<T>::sub_mul(w4m_and_or(w >> 12, kMask, kMagic), bB[mi], sB[mi]);
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t bf[NT][2];                               // B fragments of this k16 step
+            if constexpr (NT == 1) {
+              if ((kk & 1) == 0) w4m_ldsm_x4((xs + x_off[0]) ^ (uint32_t)((kk >> 1) << 6), rq);
+              bf[0][0] = (kk & 1) ? rq[2] : rq[0]; bf[0][1] = (kk & 1) ? rq[3] : rq[1];
+            } else {
+              // one ldmatrix.x4 = one k16 step of two 8-token tiles: matrices (nt, half) = (2p, 0), (2p, 1), (2p + 1, 0), (2p + 1, 1)
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) w4m_mma<T>(acc[mi][nt], a, bf[nt][0], bf[nt][1]);
+              for (int pr = 0; pr < NT / 2; ++pr) {
+                uint32_t r[4];
+                w4m_ldsm_x4((xs + x_off[pr]) ^ (uint32_t)(kk << 5), r);
+                bf[2 * pr][0] = r[0]; bf[2 * pr][1] = r[1]; bf[2 * pr + 1][0] = r[2]; bf[2 * pr + 1][1] = r[3];
+              }
+            }
+#pragma unroll
+            for (int mi = 0; mi < 2; ++mi) {
+              const uint32_t w = kk == 0 ? wv[mi].x : kk == 1 ? wv[mi].y : kk == 2 ? wv[mi].z : wv[mi].w;
+              uint32_t a[4];
+              a[0] = MagicM<T>::sub_mul(w4m_and_or(w, kMask, kMagic), bA[mi], sA[mi]);
+              a[1] = MagicM<T>::sub_mul(w4m_and_or(w >> 4, kMask, kMagic), bB[mi], sB[mi]);
+              a[2] = MagicM<T>::sub_mul(w4m_and_or(w >> 8, kMask, kMagic), bA[mi], sA[mi]);
+              a[3] = MagicM<T>::sub_mul(w4m_and_or(w >> 12, kMask, kMagic), bB[mi], sB[mi]);
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt) w4m_mma<T>(acc[mi][nt], a, bf[nt][0], bf[nt][1]);
+            }
           }
         }
         __syncwarp();
-        if (lane == 0) {            // every word of both slots has been consumed into registers by all lanes of this warp
-          mbar_arrive(&w_empty[s]);
-          mbar_arrive(&x_empty[sx]);
-        }
-        ws += kStageBytes; xs += (uint32_t)kXBytes;
-        if (++s == SW) { s = 0; ph ^= 1u; ws = w_s; }
-        if (++sx == SX) { sx = 0; phx ^= 1u; xs = smem_u32(x_s); }
+        if (lane == 0) mbar_arrive(&empty_bar[s]);          // every word of the slot has been consumed into registers by all lanes of this warp
+        st += stage_bytes;
+        if (++s == S) { s = 0; ph ^= 1u; st = ring; }
       }
       // ---- the unit's fp32 partial: c0/c1 = (row g, tokens 2t, 2t+1), c2/c3 = (row g + 8, same tokens)
       float* dst = p.out + (long long)split * p.t * p.n;
@@ -284,7 +284,7 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const long long ff = f + (j >> 1) * 8, tt = tk + (j & 1);
-            if (tt < p.t && ff < p.n) dst[tt * p.n + ff] = kb1 > kb0 ? acc[mi][nt][j] : 0.f;
+            if (tt < p.t && ff < p.n) dst[tt * p.n + ff] = acc[mi][nt][j];
             acc[mi][nt][j] = 0.f;
           }
         }
@@ -306,22 +306,23 @@ int launch_w4m(cts_ctx* ctx, const cts_gemm_w4f_args* a, cudaStream_t stream) {
   if (rc) return rc;
   W4mParams p;
   p.n = a->n; p.k = a->k; p.t = a->t;
-  p.kb_total = (int)(a->k / kBK);
+  p.ks_total = (int)(a->k / (kKS * kBK));
   p.split_k = a->split_k;
   p.kb_per_group = a->group_size / kBK;
   p.n_groups = (int)(a->k / a->group_size);
+  p.sz_groups = p.kb_per_group == 1 ? kKS : 1;
   p.tiles = (int)cdiv_ll(a->n, kTileN);
   p.qw = (const uint8_t*)a->qw; p.szp = (const uint8_t*)a->szp; p.out = a->out;
   constexpr int kXBytes = NT * 8 * kBK * 2;
-  // CTAs per SM (w4m_ctas_per_sm): the ring of each takes what its share of the shared memory leaves after the token ring and the static part
+  const int stage_bytes = kKS * kXBytes + kKS * kWBytes + p.sz_groups * kSzBytes;
+  // CTAs per SM (w4m_ctas_per_sm): the ring of each takes what its share of the shared memory leaves after the static part
   const int kCtas = w4m_ctas_per_sm(p.tiles, a->t);
   const int budget = (ctx->max_smem_optin > 0 ? ctx->max_smem_optin + 1024 : 228 * 1024) / kCtas - 3 * 1024;
-  p.stages_x = NT == 4 ? 4 : 8;
-  int sw = (budget - 1024 - p.stages_x * kXBytes) / kStageBytes;
-  if (sw > kMaxStagesW) sw = kMaxStagesW;
-  if (sw < 2) return cts_set_error(ctx, CTS_ERR_BAD_ARG, "cts_gemm_w4_mma: shared memory budget too small");
-  p.stages_w = sw;
-  const size_t smem = (size_t)p.stages_x * kXBytes + (size_t)sw * kStageBytes + 1024;
+  int st = (budget - 1024) / stage_bytes;
+  if (st > kMaxStages) st = kMaxStages;
+  if (st < 2) return cts_set_error(ctx, CTS_ERR_BAD_ARG, "cts_gemm_w4_mma: shared memory budget too small");
+  p.stages = st;
+  const size_t smem = (size_t)st * stage_bytes + 1024;
   auto kern = gemm_w4_mma_kernel<T, NT>;
   CTS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #ifndef CTS_HOST_SHIM
@@ -336,16 +337,16 @@ int launch_w4m(cts_ctx* ctx, const cts_gemm_w4f_args* a, cudaStream_t stream) {
 
 }  // namespace
 
-// split-K factor of the persistent schedule: units = tiles x split are dealt round-robin to the resident CTAs (w4m_ctas_per_sm); the cost of a choice is the
-// longest CTA's stream in 8 KB stages plus the partial it writes per unit (t KB of fp32 = t / 8 stage equivalents)
+// split-K factor of the persistent schedule: units = tiles x split are dealt round-robin to the resident CTAs (w4m_ctas_per_sm); the
+// cost of a choice is the longest CTA's stream in 16 KB stages plus the partial it writes per unit (t KB of fp32 = t / 16 stage equivalents)
 extern "C" int cts_gemm_w4_mma_suggest_split(cts_ctx* ctx, long long n, long long k, long long t) {
   if (!ctx || n <= 0 || k <= 0) return 1;
-  const long long tiles = cdiv_ll(n, kTileN), kb = k / kBK, ctas = (long long)w4m_ctas_per_sm(tiles, t) * ctx->sm_count;
+  const long long tiles = cdiv_ll(n, kTileN), ks = k / (kKS * kBK), ctas = (long long)w4m_ctas_per_sm(tiles, t) * ctx->sm_count;
   long long best = 1;
   double best_cost = 1e30;
-  for (long long s = 1; s <= 16 && s * 4 <= kb; ++s) {
+  for (long long s = 1; s <= 16 && s * 2 <= ks; ++s) {
     const long long waves = cdiv_ll(tiles * s, ctas);
-    const double cost = (double)waves * ((double)cdiv_ll(kb, s) + (double)(t < 1 ? 1 : t) / 8.0 + 1.0);
+    const double cost = (double)waves * ((double)cdiv_ll(ks, s) + (double)(t < 1 ? 1 : t) / 16.0 + 0.5);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
   }
   return (int)best;
@@ -356,9 +357,10 @@ extern "C" int cts_gemm_w4_mma(cts_ctx* ctx, const cts_gemm_w4f_args* a, void* s
   CTS_CHECK_ARG(ctx, a != nullptr && a->qw && a->szp && a->x && a->out, "null pointer");
   CTS_CHECK_ARG(ctx, a->n > 0 && a->k > 0 && a->t > 0 && a->t <= 32, "n, k > 0 and 1 <= t <= 32 (decode-sized step; prefill uses the dequantised weight)");
   CTS_CHECK_ARG(ctx, a->dtype == CTS_BF16 || a->dtype == CTS_F16, "dtype");
-  CTS_CHECK_ARG(ctx, a->k % 64 == 0, "k must be a multiple of 64");
-  CTS_CHECK_ARG(ctx, a->group_size >= 64 && a->group_size % 64 == 0 && a->k % a->group_size == 0, "group_size must be a multiple of 64 dividing k");
-  CTS_CHECK_ARG(ctx, a->split_k >= 1 && a->split_k <= a->k / kBK, "split_k");
+  CTS_CHECK_ARG(ctx, a->k % 128 == 0, "k must be a multiple of 128 (a pipeline stage is two 64-K blocks)");
+  CTS_CHECK_ARG(ctx, a->group_size >= 64 && a->group_size % 64 == 0 && a->k % a->group_size == 0 && (a->group_size == 64 || a->group_size % 128 == 0),
+                "group_size must be 64 or a multiple of 128, and divide k");
+  CTS_CHECK_ARG(ctx, a->split_k >= 1 && a->split_k <= a->k / 128, "split_k");
   CTS_CHECK_ARG(ctx, a->x_ld >= a->k, "x_ld smaller than k");
   CTS_CHECK_ARG(ctx, (((uintptr_t)a->qw | (uintptr_t)a->szp) & 15) == 0, "qw / szp must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;

@@ -301,6 +301,9 @@ class ChatTSForCausalLM:
         # built here (the row layout is dropped per layer once it is converted); "tc5" = csrc/gemm_w4.cu (tcgen05, bit-identical to the
         # dense GEMM, no faster than it: kept as the checker)
         w4["kernel"] = _os.environ.get("CTS_W4_KERNEL", "mma")
+        k_dims = (self.H, self.nh * self.d, self.I)
+        if w4["kernel"] == "mma" and not (all(kd % 128 == 0 for kd in k_dims) and (gs == 64 or gs % 128 == 0)):
+            w4["kernel"] = "tc5"          # the mma kernel's pipeline stage is 128 K wide (cts_gemm_w4f_args): odd shapes take the tcgen05 kernel
         if w4["kernel"] == "mma":
             from .weights import repack_w4_mma
             for kind in ("qkv", "o", "gu", "d"):

@@ -293,10 +293,11 @@ class TorchDouble:
         w = dequantize_w4(qw, scales, zeros, group_size)
         self.gemm(x, w, out, epilogue=3, split_k=split_k, t=t)
 
-    def gemm_w4_mma_suggest_split(self, n, k, t=1): return self.split if k >= 128 * self.split else 1
+    def gemm_w4_mma_suggest_split(self, n, k, t=1): return self.split if k >= 256 * self.split else 1
     def gemm_w4_mma(self, x, qwf, szp, n, group_size, out, split_k, t=None):
         """The fragment-major layout decoded back to a dense weight (the inverse of weights.py:repack_w4_mma, written independently)."""
         k = szp.shape[1] * int(group_size)
+        assert k % 128 == 0 and (int(group_size) == 64 or int(group_size) % 128 == 0) and 1 <= split_k <= k // 128      # cts_gemm_w4f_args
         tiles = szp.shape[0]
         b = qwf.view(tiles, k // 64, 16, 32, 4, 4).to(torch.int64)
         word = b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16) | (b[..., 3] << 24)           # [tile, kb, m, lane, ks]

@@ -53,7 +53,10 @@ def test_gptq_checkpoint_decodes_through_the_packed_weights(cabi_double, tmp_pat
     from chatts_b200.model import ChatTSForCausalLM
     monkeypatch.setenv("CTS_W4_KERNEL", kernel)
     cfg, sd, _, proc = _build(cabi_double)
-    cfg.intermediate_size = 704
+    if kernel == "mma":          # the mma kernel's pipeline stage is 128 K wide: the tiny config's 704-wide MLP (5.5 x 128) is for the tcgen05 kernel
+        from chatts_b200.weights import synthetic_state_dict
+        cfg.intermediate_size = 768
+        sd = synthetic_state_dict(cfg, seed=1234, device="cpu", dtype=torch.bfloat16, std=0.05)
     path = _gptq_checkpoint(tmp_path, cfg, sd)
     kw = dict(device="cpu", torch_dtype="bfloat16", max_batch=4, max_seq_len=512, page_size=16, use_cuda_graph=False)
     m4 = ChatTSForCausalLM.from_pretrained(path, **kw)
@@ -107,3 +110,14 @@ def test_fragment_major_repack_round_trips(cabi_double):
             cabi_double.gemm_w4_mma(x, qwf, szp, n, gs, out, 1, t=32)
             want = dequantize_w4(qw, sc, zp, gs).float()[:, :32].t()
             assert torch.equal(out[0], want)
+
+
+def test_shapes_the_mma_kernel_cannot_take_fall_back_to_the_tcgen05_kernel(cabi_double, tmp_path, monkeypatch):
+    """cts_gemm_w4_mma streams 128-K stages: a down_proj with 704 inputs (not a multiple of 128) makes attach_w4 choose cts_gemm_w4."""
+    from chatts_b200.model import ChatTSForCausalLM
+    monkeypatch.setenv("CTS_W4_KERNEL", "mma")
+    cfg, sd, _, proc = _build(cabi_double)
+    assert cfg.intermediate_size % 128 != 0
+    path = _gptq_checkpoint(tmp_path, cfg, sd)
+    m = ChatTSForCausalLM.from_pretrained(path, device="cpu", torch_dtype="bfloat16", max_batch=2, max_seq_len=256, page_size=16, use_cuda_graph=False)
+    assert m.w4 is not None and m.w4["kernel"] == "tc5"
