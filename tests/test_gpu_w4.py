@@ -130,3 +130,52 @@ def _first_step_logits(model, enc):
         return st.full_logits[:B].float().cpu().clone()
     finally:
         model.pool.release(held)
+
+
+def test_gptq_checkpoint_directory_decodes_through_the_packed_weights(tmp_path):
+    """The load path a user takes (README.md:52,262-263): a GPTQ-Int4 checkpoint DIRECTORY (qweight / qzeros / scales / g_idx per
+    projection + quantization_config) through from_pretrained -> packed decode weights attached (mma kernel), prefill on the dequantised
+    copy; the greedy continuation equals the one through the model's own dense copy; CTS_W4=0 loads the dequantised weights only."""
+    import json
+    import os
+    from safetensors.torch import save_file
+    from chatts_b200 import ChatTSConfig, ChatTSProcessor, SimpleTokenizer
+    from chatts_b200.model import ChatTSForCausalLM
+    from chatts_b200.weights import pack_gptq_linear, synthetic_state_dict
+    cfg = ChatTSConfig.tiny(intermediate_size=768)
+    sd = synthetic_state_dict(cfg, seed=9, device="cpu", dtype=torch.bfloat16, std=0.05)
+    out = {}
+    for k, v in sd.items():
+        if ".layers." in k and k.endswith("_proj.weight"):
+            qw, qz, sc, gi = pack_gptq_linear(v.float(), 128, 1)
+            base = k[: -len(".weight")]
+            out.update({base + ".qweight": qw, base + ".qzeros": qz, base + ".scales": sc, base + ".g_idx": gi})
+        else:
+            out[k] = v.contiguous()
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    conf = cfg.to_dict()
+    conf["quantization_config"] = {"bits": 4, "group_size": 128, "quant_method": "gptq"}
+    json.dump(conf, open(d / "config.json", "w"))
+    save_file(out, str(d / "model.safetensors"))
+    kw = dict(torch_dtype="bfloat16", max_batch=4, max_seq_len=256, page_size=16)
+    m4 = ChatTSForCausalLM.from_pretrained(str(d), **kw)
+    assert m4.w4 is not None and m4.w4["kernel"] == "mma" and m4.w4["group_size"] == 128
+    proc = ChatTSProcessor(SimpleTokenizer(cfg.ts_token_start_index, cfg.pad_token_id, cfg.eos_token_id), cfg)
+    x = np.arange(200)
+    enc = proc(text=["A <ts><ts/> ?", "text only, a longer prompt"], timeseries=[np.cos(x / 7) * 3], padding=True, return_tensors="pt")
+    a = m4.generate(**enc, max_new_tokens=12, ignore_eos=True)
+    # the same weights through the dequantised dense copy the prefill uses (a CTS_W4=0 load would keep the fp16 scales un-rounded:
+    # other weights, not a comparison of kernels)
+    m4.w4, m4._steps = None, {}
+    b = m4.generate(**enc, max_new_tokens=12, ignore_eos=True)
+    S = enc["input_ids"].shape[1]
+    agree = [int(next((i for i in range(12) if a[r, S + i] != b[r, S + i]), 12)) for r in range(2)]
+    record("w4_gptq_checkpoint_dir", greedy_agreement=str(agree))
+    assert min(agree) >= 9
+    os.environ["CTS_W4"] = "0"
+    try:
+        md = ChatTSForCausalLM.from_pretrained(str(d), **kw)
+    finally:
+        del os.environ["CTS_W4"]
+    assert md.w4 is None and md.generate(**enc, max_new_tokens=4, ignore_eos=True).shape[1] == S + 4
