@@ -25,6 +25,8 @@
 // Output: the fp32 split-K partials [split, t, n] of CTS_EPI_PARTIAL_F32, so the decode step's reduce tails are unchanged.  The A
 // operand holds the same 16-bit values as the dense copy; the fp32 summation order differs from the tcgen05 GEMM (parity is a
 // tolerance, tests/test_gpu_w4.py), unlike gemm_w4.cu which is bit-identical and stays as the checker for this kernel.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -296,7 +298,11 @@ gemm_w4_mma_kernel(const __grid_constant__ CUtensorMap tm_x, const W4mParams p) 
 // Resident CTAs per SM: three of the t <= 8 kernel (64 registers) when the projection has enough 256-feature tiles to give every CTA a
 // long unit (gate_up: 108 tiles), else two with deeper rings -- measured on a B200: gate_up 28.1 -> 25.8 us with three, down_proj (20
 // tiles) 15.1 -> 18.2 us (profiles/r2_w4_mma_gemm_sweep*.json)
-static inline int w4m_ctas_per_sm(long long tiles, long long t) { return (t <= 8 && tiles >= 64) ? 3 : 2; }
+static inline int w4m_ctas_per_sm(long long tiles, long long t) {
+  static const int forced = [] { const char* e = getenv("CTS_W4M_CTAS"); return e ? atoi(e) : 0; }();      // A/B knob (2 or 3)
+  if (forced == 2 || (forced == 3 && t <= 8)) return forced;
+  return (t <= 8 && tiles >= 64) ? 3 : 2;
+}
 
 template <typename T, int NT>
 int launch_w4m(cts_ctx* ctx, const cts_gemm_w4f_args* a, cudaStream_t stream) {
