@@ -532,6 +532,62 @@ def measure_config4(cfg, rank, world, steps, warmup, sync_all, batch=8, n_series
     return out
 
 
+def measure_w4(cfg, steps, warmup, hbm_peak, batches=(1, 8, 32)):
+    """GPTQ-Int4 side block (README.md:52,262-263: ChatTS-14B-GPTQ-Int4), one GPU: a third model instance whose seven projections per
+    layer are 4-bit (synthetic codes / scales / zero points at the real shapes, group size 128; embeddings, norms, lm_head and the TS
+    encoder stay bf16) decodes the benchmark prompts through the packed weights (cts_gemm_w4_mma) and through its own dequantised bf16
+    copy: ms per step of both from CUDA events over graph replays, greedy agreement between the two."""
+    from chatts_b200.model import ChatTSForCausalLM
+    model = ChatTSForCausalLM.from_synthetic(cfg, seed=1234, max_batch=max(batches), max_seq_len=1024, page_size=64)
+    model.quantize_w4_synthetic(group_size=128)
+    w4 = model.w4
+    max_new = steps + warmup + 8
+
+    def run(batch):
+        enc = make_batch(cfg, batch)
+        ids_cpu, am_cpu, counts, lay = model._prepare_inputs(enc["input_ids"], enc["attention_mask"], enc["timeseries"])
+        pts, held = model._alloc_pages(lay.lens, max_new)
+        try:
+            logits = model._prefill(lay, counts, enc["timeseries"], pts)
+            st = model._decode_state(batch, max_new)
+            lens32 = torch.from_numpy(lay.lens.astype(np.int32))
+            st.page_table.copy_(torch.from_numpy(pts)); st.positions.copy_(lens32 - 1); st.seq_lens.copy_(lens32); st.step_ptr.zero_()
+            model.ctx.greedy_advance(logits, batch, st.out_tokens, st.step_ptr, st.cur_ids, st.positions, st.seq_lens, st.slot_map, st.page_table, model.page_size)
+            for _ in range(max(warmup, 3)):
+                model._decode_step(st)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                model._decode_step(st)
+            e1.record()
+            torch.cuda.synchronize()
+            toks = st.out_tokens[:, : int(st.step_ptr[0])].cpu().numpy().copy()
+            return e0.elapsed_time(e1) / steps, toks
+        finally:
+            model.pool.release(held)
+
+    L = cfg.num_hidden_layers
+    per_layer = (cfg.hidden_size * (cfg.num_attention_heads + 2 * cfg.num_key_value_heads) * cfg.head_dim + cfg.hidden_size * cfg.num_attention_heads * cfg.head_dim +
+                 3 * cfg.hidden_size * cfg.intermediate_size)
+    out = {"workload": "ChatTS-14B with 4-bit projections (GPTQ layout, group 128, synthetic codes), the benchmark prompts, greedy decode; W4A16 through "
+                       "cts_gemm_w4_mma against the same model through its dequantised bf16 copy", "kernel": w4["kernel"], "steps": steps, "by_batch": {}}
+    for b in batches:
+        model.w4, model._steps = w4, {}
+        ms4, t4 = run(b)
+        model.w4, model._steps = None, {}
+        ms16, t16 = run(b)
+        n = min(t4.shape[1], t16.shape[1])
+        agree = [int(next((i for i in range(n) if t4[r, i] != t16[r, i]), n)) for r in range(b)]
+        w4_bytes = L * per_layer * (0.5 + 4.0 / 128) + 2 * cfg.hidden_size * cfg.vocab_size
+        kv = b * 600 * L * 2 * cfg.num_key_value_heads * cfg.head_dim * 2
+        out["by_batch"][str(b)] = {"w4_ms_per_step": ms4, "bf16_ms_per_step": ms16, "speedup": ms16 / ms4, "w4_tokens_per_s": b / (ms4 / 1e3),
+                                   "w4_whole_step_hbm_frac": (w4_bytes + kv) / (ms4 / 1e3) / 1e9 / hbm_peak, f"min_greedy_agreement_of_{n}": int(min(agree))}
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     from chatts_b200 import ChatTSConfig, _cabi
@@ -768,6 +824,14 @@ def run_b200(args):
         except Exception as e:  # pragma: no cover
             config4 = {"error": repr(e)[:300]}              # shape / capacity errors are the same on every rank: all of them land here
 
+    # ---- GPTQ-Int4 side block (one GPU: W4A16 decode weights are single-GPU)
+    w4_block = None
+    if world == 1 and not args.sweep_only and not args.layers and not args.no_w4:
+        try:
+            w4_block = measure_w4(cfg, args.steps, args.warmup, hbm_peak, batches=sorted(set(b for b in (1, 8, args.batch) if b <= args.batch)))
+        except Exception as e:  # pragma: no cover
+            w4_block = {"error": repr(e)[:300]}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -783,6 +847,7 @@ def run_b200(args):
                 "roofline": roof, "ts_encoder": ts_roof, "attention": attn_roof, "cpu_baseline": cpu, "arch": ctx.arch, "lib": os.path.relpath(_cabi.LIB_PATH, ROOT)}
         # which opt-in variants of the decode path this line was measured with (all off = the validated default path)
         line["config4"] = config4
+        line["w4a16"] = w4_block
         line["tokens_sha1"] = main.get("tokens_sha1")          # hash of every greedy token the measured batch produced (probe: equality across variants)
         if probe_record is not None:
             line["config"]["decode_variant_probe"] = probe_record
@@ -812,6 +877,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run decode steps eagerly (for ncu launch lists)")
     ap.add_argument("--sweep-only", action="store_true", help="decode timing only (skip e2e)")
+    ap.add_argument("--no-w4", action="store_true", help="skip the GPTQ-Int4 side block (third model instance with 4-bit projections)")
     ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE configs[3] side block (second model instance, 30 x 512-point prompts)")
     ap.add_argument("--no-probe", action="store_true", help="(default) the default decode path is measured as is")
     ap.add_argument("--probe", action="store_true", help="guarded child-process probe of the cluster-fused decode variants (round 1; measured slower at b = 32 on a B200, "
