@@ -262,19 +262,18 @@ ts_encoder_fused_kernel(const __grid_constant__ TsMaps maps, const TsFusedParams
       const int ft = q * 32 + lane;
       const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 64) {                    // four TMEM loads in flight behind one wait (each wait is a ~150-cycle round trip)
+      for (int c = 0; c < BN; c += 16) {
         if (c >= R) break;                                  // warp-uniform
-        uint32_t v[64];
+        uint32_t v[16];
         if (nkb > 0) {
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) tmem_ld_32x32b_x16(lane_addr + (uint32_t)(c + 16 * q4), v + 16 * q4);
+          tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = 0u;
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
         }
 #pragma unroll
-        for (int j = 0; j < 64; ++j) part_s[(c + j) * kBM + ft] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) part_s[(c + j) * kBM + ft] = __uint_as_float(v[j]);
       }
       tc_fence_before();
     }
@@ -294,7 +293,7 @@ ts_encoder_fused_kernel(const __grid_constant__ TsMaps maps, const TsFusedParams
       T* dst_act = reinterpret_cast<T*>(p.act[l & 1]);
       const int n_my = R > split ? (R - split + S - 1) / S : 0;
       const int n_items = n_my * 32;
-      constexpr int kBatch = 3;                             // three items (3 x S remote 16-byte loads) in flight per thread: the tail is DSMEM round trips, not arithmetic
+      constexpr int kBatch = 2;
       for (int it0 = et; it0 < n_items; it0 += 128 * kBatch) {
         float4 acc[kBatch];
 #pragma unroll
