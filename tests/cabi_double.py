@@ -298,6 +298,11 @@ class TorchDouble:
         """The fragment-major layout decoded back to a dense weight (the inverse of weights.py:repack_w4_mma, written independently)."""
         k = szp.shape[1] * int(group_size)
         assert k % 128 == 0 and (int(group_size) == 64 or int(group_size) % 128 == 0) and 1 <= split_k <= k // 128      # cts_gemm_w4f_args
+        key = (qwf.data_ptr(), szp.data_ptr(), int(n), int(group_size), x.dtype)
+        cache = self.__dict__.setdefault("_w4f_cache", {})
+        if key in cache:                                     # the weights of a model are static: decode the layout once per tensor
+            self.gemm(x, cache[key], out, epilogue=3, split_k=split_k, t=t)
+            return
         tiles = szp.shape[0]
         b = qwf.view(tiles, k // 64, 16, 32, 4, 4).to(torch.int64)
         word = b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16) | (b[..., 3] << 24)           # [tile, kb, m, lane, ks]
@@ -317,6 +322,7 @@ class TorchDouble:
         zp = ((u >> 16) - magic).permute(0, 2, 1).reshape(tiles * 256, -1)
         grp = torch.arange(k) // int(group_size)
         w = (sc.to(torch.float32)[:, grp] * (q - zp[:, grp]).to(torch.float32)).to(x.dtype)[:n]
+        cache[key] = w
         self.gemm(x, w, out, epilogue=3, split_k=split_k, t=t)
 
     # ------------------------------------------------------------------ repetition penalty (csrc/sampling.cu)

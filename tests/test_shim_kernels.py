@@ -250,7 +250,12 @@ def test_fused_gemm_allreduce_tail_with_ranks_as_processes(shim_ctx, W, T, N, Kr
     assert [int(s_[0]) for s_ in state] == [len(calls)] * W
 
 
-@pytest.mark.parametrize("variant", ["CTS_PEER_LL=1", "CTS_PEER_LL=1 CTS_DECODE_FUSED=2"])
+# the all-reduce-inside-the-GEMM variant is an opt-in path that measured slower on the B200: it runs here only with
+# CTS_SLOW_TESTS=1, to keep the default CPU suite within a few minutes on a busy machine
+_TP_VARIANTS = ["CTS_PEER_LL=1"] + (["CTS_PEER_LL=1 CTS_DECODE_FUSED=2"] if os.environ.get("CTS_SLOW_TESTS") == "1" else [])
+
+
+@pytest.mark.parametrize("variant", _TP_VARIANTS)
 def test_tensor_parallel_model_with_ranks_as_processes(variant):
     """tools/shim_tp_check.py: the tensor-parallel MODEL (2 ranks = 2 processes under torchrun, gloo for the host-side collectives, the
     symmetric buffers as shared memory behind cts_ipc_*), every kernel from source -- with the low-latency all-reduce kernel, and with the
@@ -270,6 +275,7 @@ def test_tensor_parallel_model_with_ranks_as_processes(variant):
     assert "identical tokens on all ranks: True" in out and "greedy agreement [8, 8]/8" in out, out[-2000:]
 
 
+@pytest.mark.skipif(os.environ.get("CTS_SLOW_TESTS") != "1", reason="the guard of bench.py's opt-in --probe (decode variants that measured slower on the B200); CTS_SLOW_TESTS=1 runs it")
 def test_numeric_guard_of_the_decode_variant_probe_runs_from_source():
     """tools/probe_decode_variant.py (the child bench.py runs before it adopts fusion level 2): default path and variant on the same weights,
     teacher-forced, logits compared at every step -- executed here through the shim with a toy configuration."""
