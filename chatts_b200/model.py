@@ -98,6 +98,7 @@ class ChatTSForCausalLM:
         # (default since round 2: validated across 2 B200s -- same logits, same tokens on every rank -- and 19-25 % faster per step
         #  than the one-shot kernel at TP2, profiles/r2_tp2_variants.txt; CTS_PEER_LL=0 selects the one-shot kernel)
         self.use_peer_ll = (_os.environ.get("CTS_PEER_LL", "1") == "1") if use_peer_ll is None else bool(use_peer_ll)
+        self.tp_prefill_16bit = _os.environ.get("CTS_TP_PREFILL_FP32", "0") != "1"     # row-parallel exchange of prefill-sized steps in the model dtype
         # sampled decoding through cts_sample_advance (csrc/sampling.cu): temperature / top-k / top-p / multinomial / advance in ONE
         # launch per step, no torch op on the path (validated on a B200: 17 cases against the CPU statement that is itself checked
         # against transformers' logits warpers).  Default since round 2; CTS_SAMPLE_KERNEL=0 selects the torch-op fallback.
@@ -494,6 +495,17 @@ class ChatTSForCausalLM:
         CTA reduces its token's local split-K partials into the symmetric buffer, signals, pulls the peers' rows; the
         buffers alternate between o_proj (0) and down_proj (1)).  Large prefill T: NCCL all-reduce (bandwidth-bound)."""
         c = self.ctx
+        if split == 1 and not (self.peer is not None and T <= self.peer_tokens) and self.tp_prefill_16bit:
+            # Prefill-sized T (bandwidth-bound exchange): every rank rounds its projection to the model dtype and the ranks' outputs are
+            # summed by NCCL in that dtype -- what vLLM's RowParallelLinear does (qwen2.py:100-116 / 168-174: GEMM output in the model
+            # dtype, tensor_model_parallel_all_reduce on it) -- half the bytes of the fp32 exchange this path used before (at TP8 the 96
+            # exchanges of a 18 432-position prefill were 75 ms of ~200).  CTS_TP_PREFILL_FP32=1 restores the fp32 exchange.
+            proj = st.tp_proj
+            c.gemm(x, w, proj, epilogue=EPI_NONE, t=T)
+            torch.distributed.all_reduce(proj[:T], group=self.comm)
+            st.h[:T].add_(proj[:T])                               # residual add in the model dtype (one rounding, as the fused tail does)
+            c.reduce_residual_rmsnorm(None, 0, st.h, st.h, norm_w, self.eps, st.xn, t=T)
+            return
         c.gemm(x, w, st.ws, epilogue=EPI_PARTIAL_F32, split_k=split, t=T, **(nxt or {}))
         if self.peer is not None and T <= self.peer_tokens and self.use_peer_ll:
             c.peer_allreduce_ll(st.ws, split, self.peer.partials[which], self.peer.part_bytes, self.peer.state, self.tp_rank, self.tp_size,
@@ -517,6 +529,7 @@ class ChatTSForCausalLM:
         st.q = torch.empty(T, self.nh * self.d, device=dev, dtype=dt)
         st.ao = torch.empty(T, self.nh * self.d, device=dev, dtype=dt)
         st.act = torch.empty(T, self.I, device=dev, dtype=dt)
+        st.tp_proj = torch.empty(T, self.H, device=dev, dtype=dt) if (self.tp_size > 1 and not decode) else None   # row-parallel output of a prefill (16-bit exchange)
         st.qkv = torch.empty(T, self.wqkv[0].shape[0], device=dev, dtype=dt) if st.splits["qkv"] == 1 else None
         ws_n = max(self._ws_floats(T, st.splits), T * self.H)
         if decode and self.w4 is not None and T <= 32:   # W4A16 decode: every projection through the partial path with the W4 split factors
