@@ -98,7 +98,15 @@ class ChatTSForCausalLM:
         # (default since round 2: validated across 2 B200s -- same logits, same tokens on every rank -- and 19-25 % faster per step
         #  than the one-shot kernel at TP2, profiles/r2_tp2_variants.txt; CTS_PEER_LL=0 selects the one-shot kernel)
         self.use_peer_ll = (_os.environ.get("CTS_PEER_LL", "1") == "1") if use_peer_ll is None else bool(use_peer_ll)
-        self.tp_prefill_16bit = _os.environ.get("CTS_TP_PREFILL_FP32", "0") != "1"     # row-parallel exchange of prefill-sized steps in the model dtype
+        # row-parallel exchange of prefill-sized steps: "rs_ag" (default: fp32 reduce-scatter + 16-bit all-gather of the result), "fp32"
+        # (one fp32 all-reduce, rounds 1-2), "16bit" (all-reduce in the model dtype: vLLM's semantics, fastest, re-rounds the running sum)
+        self.tp_prefill_exchange = _os.environ.get("CTS_TP_PREFILL_EXCHANGE", "rs_ag")
+        self._nccl = False
+        if tp_size > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+            try:
+                self._nccl = str(torch.distributed.get_backend(comm)) == "nccl"   # comm None = the default group; gloo (CPU tests) has no reduce_scatter: fp32 all-reduce there
+            except Exception:
+                self._nccl = False
         # sampled decoding through cts_sample_advance (csrc/sampling.cu): temperature / top-k / top-p / multinomial / advance in ONE
         # launch per step, no torch op on the path (validated on a B200: 17 cases against the CPU statement that is itself checked
         # against transformers' logits warpers).  Default since round 2; CTS_SAMPLE_KERNEL=0 selects the torch-op fallback.
@@ -495,15 +503,30 @@ class ChatTSForCausalLM:
         CTA reduces its token's local split-K partials into the symmetric buffer, signals, pulls the peers' rows; the
         buffers alternate between o_proj (0) and down_proj (1)).  Large prefill T: NCCL all-reduce (bandwidth-bound)."""
         c = self.ctx
-        if split == 1 and not (self.peer is not None and T <= self.peer_tokens) and self.tp_prefill_16bit:
-            # Prefill-sized T (bandwidth-bound exchange): every rank rounds its projection to the model dtype and the ranks' outputs are
-            # summed by NCCL in that dtype -- what vLLM's RowParallelLinear does (qwen2.py:100-116 / 168-174: GEMM output in the model
-            # dtype, tensor_model_parallel_all_reduce on it) -- half the bytes of the fp32 exchange this path used before (at TP8 the 96
-            # exchanges of a 18 432-position prefill were 75 ms of ~200).  CTS_TP_PREFILL_FP32=1 restores the fp32 exchange.
+        big = split == 1 and not (self.peer is not None and T <= self.peer_tokens)
+        if big and self.tp_prefill_exchange == "16bit":
+            # Opt-in (CTS_TP_PREFILL_EXCHANGE=16bit): every rank rounds its projection to the model dtype and NCCL sums the ranks' outputs
+            # in that dtype -- what vLLM's RowParallelLinear does (qwen2.py:100-116 / 168-174) -- half the bytes of the fp32 all-reduce:
+            # e2e at TP4 1 850 -> 2 466 tok/s, and the prefill logits move from 1.2e-2 to 1.8e-2 of max from the single-GPU model
+            # (profiles/r2_bench_tp4_prefill_exchange_*.json).  Not the default: the sum is re-rounded at every ring step.
             proj = st.tp_proj
             c.gemm(x, w, proj, epilogue=EPI_NONE, t=T)
             torch.distributed.all_reduce(proj[:T], group=self.comm)
             st.h[:T].add_(proj[:T])                               # residual add in the model dtype (one rounding, as the fused tail does)
+            c.reduce_residual_rmsnorm(None, 0, st.h, st.h, norm_w, self.eps, st.xn, t=T)
+            return
+        if big and self.tp_prefill_exchange == "rs_ag" and self._nccl:
+            # Default for prefill-sized T: the fp32 sum is kept (reduce-scatter of the fp32 partials over token shards, summed by NCCL in
+            # fp32) and only the RESULT travels in the model dtype (all-gather of the rounded shards): three quarters of the bytes of the
+            # fp32 all-reduce, the same numbers as the single-GPU path up to the order of the fp32 sum -- h = resid + dtype(sum).
+            W = self.tp_size
+            ct = -(-T // W)                                       # tokens per shard (the last shard is padded: st.ws / st.tp_proj hold W * ct rows)
+            c.gemm(x, w, st.ws, epilogue=EPI_PARTIAL_F32, split_k=1, t=T, **(nxt or {}))
+            part = st.ws.view(-1)[: W * ct * self.H]
+            torch.distributed.reduce_scatter_tensor(st.tp_shard32, part, group=self.comm)
+            st.tp_shard16.copy_(st.tp_shard32)                    # ONE rounding of the projection to the model dtype (cast = plumbing)
+            torch.distributed.all_gather_into_tensor(st.tp_proj.view(-1)[: W * ct * self.H], st.tp_shard16, group=self.comm)
+            st.h[:T].add_(st.tp_proj[:T])                         # residual add in the model dtype, as the fused tail does
             c.reduce_residual_rmsnorm(None, 0, st.h, st.h, norm_w, self.eps, st.xn, t=T)
             return
         c.gemm(x, w, st.ws, epilogue=EPI_PARTIAL_F32, split_k=split, t=T, **(nxt or {}))
@@ -529,9 +552,16 @@ class ChatTSForCausalLM:
         st.q = torch.empty(T, self.nh * self.d, device=dev, dtype=dt)
         st.ao = torch.empty(T, self.nh * self.d, device=dev, dtype=dt)
         st.act = torch.empty(T, self.I, device=dev, dtype=dt)
-        st.tp_proj = torch.empty(T, self.H, device=dev, dtype=dt) if (self.tp_size > 1 and not decode) else None   # row-parallel output of a prefill (16-bit exchange)
+        st.tp_proj = st.tp_shard32 = st.tp_shard16 = None
+        tp_pad = 0
+        if self.tp_size > 1 and not decode:                     # row-parallel exchange of a prefill: token shards of ceil(T / W) rows
+            ct = -(-T // self.tp_size)
+            tp_pad = self.tp_size * ct
+            st.tp_proj = torch.empty(tp_pad, self.H, device=dev, dtype=dt)
+            st.tp_shard32 = torch.empty(ct * self.H, device=dev, dtype=torch.float32)
+            st.tp_shard16 = torch.empty(ct * self.H, device=dev, dtype=dt)
         st.qkv = torch.empty(T, self.wqkv[0].shape[0], device=dev, dtype=dt) if st.splits["qkv"] == 1 else None
-        ws_n = max(self._ws_floats(T, st.splits), T * self.H)
+        ws_n = max(self._ws_floats(T, st.splits), T * self.H, tp_pad * self.H)
         if decode and self.w4 is not None and T <= 32:   # W4A16 decode: every projection through the partial path with the W4 split factors
             sp = self._w4_splits(T)
             ws_n = max(ws_n, sp["qkv"] * T * self.wqkv[0].shape[0], sp["o"] * T * self.H, sp["gu"] * T * 2 * self.I, sp["d"] * T * self.H)

@@ -1,10 +1,11 @@
 #!/bin/bash
-# Round-2 visit 32 (N B200): the tensor-parallel prefill's row-parallel exchange in the model dtype (default) against the fp32 exchange
-# (CTS_TP_PREFILL_FP32=1): bench.py line at N (e2e, config4 prefill seconds, parity gate).
+# Round-2 visit 32/33 (N B200): the tensor-parallel prefill's row-parallel exchange -- rs_ag (default: fp32 reduce-scatter + 16-bit
+# all-gather of the result), fp32 (one fp32 all-reduce), 16bit (all-reduce in the model dtype) -- bench.py line at N (e2e, config4 prefill
+# seconds, parity gate).
 cd "${GRAFT_REPO_ROOT:-/root/repo}"; mkdir -p gpurun_out
 N=${TP:-2}
-for mode in 16bit fp32; do
-  [ "$mode" = fp32 ] && export CTS_TP_PREFILL_FP32=1
+for mode in ${MODES:-rs_ag fp32 16bit}; do
+  export CTS_TP_PREFILL_EXCHANGE=$mode
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29400 + RANDOM % 100)) bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r2v32_bench_tp${N}_$mode.json 2> gpurun_out/r2v32_bench_tp${N}_$mode.err; echo "$mode rc=$?"
   python - <<PY
 import json
