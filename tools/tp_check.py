@@ -27,6 +27,17 @@ def main():
     enc = proc(text=["A <ts><ts/> then B <ts><ts/> ?", "plain text only prompt"], timeseries=[np.sin(x / 10) * 5, x[:90] * 0.1],
                padding=True, return_tensors="pt")
     tp = ChatTSForCausalLM(cfg, sd, dtype=dt, tp_rank=rank, tp_size=world, max_batch=4, max_seq_len=512, page_size=16)
+    # a prefill whose total token count is NOT a multiple of the world size and above the peer-memory path's limit: the NCCL exchange of the
+    # row-parallel projections (fp32 reduce-scatter over padded token shards + 16-bit all-gather, model.py:_tp_row_parallel)
+    filler = "the quick brown fox jumps over the lazy dog " * 3
+    for extra in range(0, 8):
+        enc = proc(text=["A <ts><ts/> then B <ts><ts/> ? " + filler + "x" * extra, "plain text only prompt " + filler], timeseries=[np.sin(x / 10) * 5, x[:90] * 0.1],
+                   padding=True, return_tensors="pt")
+        T = int(tp._prepare_inputs(enc["input_ids"], enc["attention_mask"], enc["timeseries"])[3].total)
+        if T % world != 0 and T > tp.peer_tokens:
+            break
+    if rank == 0:
+        print(f"[tp_check] prefill tokens {T} (mod world = {T % world}), exchange = {tp.tp_prefill_exchange}, nccl = {tp._nccl}", flush=True)
     lg_tp = tp.forward(enc["input_ids"], enc["attention_mask"], enc["timeseries"]).logits[:, 0].float().cpu()
     ids_tp = tp.generate(**enc, max_new_tokens=24, ignore_eos=True)
     ok = True
