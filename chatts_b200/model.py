@@ -501,7 +501,8 @@ class ChatTSForCausalLM:
         """Row-parallel projection under tensor parallelism: local split-K partials -> sum over splits and ranks ->
         residual + norm.  Decode-sized T: ONE kernel over NVLink peer memory (cts_peer_allreduce_residual_rmsnorm: each
         CTA reduces its token's local split-K partials into the symmetric buffer, signals, pulls the peers' rows; the
-        buffers alternate between o_proj (0) and down_proj (1)).  Large prefill T: NCCL all-reduce (bandwidth-bound)."""
+        buffers alternate between o_proj (0) and down_proj (1)).  Large prefill T: NCCL (bandwidth-bound) -- fp32 reduce-scatter over token
+        shards + all-gather of the rounded result by default, see the branches below."""
         c = self.ctx
         big = split == 1 and not (self.peer is not None and T <= self.peer_tokens)
         if big and self.tp_prefill_exchange == "16bit":
