@@ -30,11 +30,13 @@ def test_pending_and_validated_kernels_pass_their_gpu_tests_on_the_shim():
     assert r.returncode == 0, tail
     import re
     passed = [int(n) for n in re.findall(r"(\d+) passed", r.stdout)]
-    # sampling, training (incl. one whole step), validated elementwise kernels, cluster-fused decode GEMMs, validated GEMMs, tcgen05 backward
-    assert len(passed) == 6 and min(passed) >= 1 and sum(passed) >= 110 and "failed" not in r.stdout, tail
+    # sampling, training (incl. one whole step), validated elementwise kernels, cluster-fused decode GEMMs, validated GEMMs, tcgen05 backward,
+    # single-pass persistent prefill attention, W4A16 mma GEMM
+    assert len(passed) == 8 and min(passed) >= 1 and sum(passed) >= 118 and "failed" not in r.stdout, tail
     native = r.stdout.split("entry points running from kernel source:")[1].split("\n")[0].split()
     assert {"sample_advance", "attn_bwd", "adamw", "grad_norm_clip", "lora_pack", "lora_wgrad", "ce_loss_grad", "rmsnorm_bwd", "swiglu_bwd",
-            "qkv_rope_bwd", "gemm", "gemm_decode_fused", "attn_prefill_lse", "attn_decode", "decoder_step", "reduce_residual_rmsnorm"} <= set(native), native
+            "qkv_rope_bwd", "gemm", "gemm_decode_fused", "attn_prefill", "attn_prefill_lse", "attn_decode", "decoder_step", "reduce_residual_rmsnorm",
+            "gemm_w4", "gemm_w4_mma"} <= set(native), native
 
 
 def _expected(parts, split, resid, dt):

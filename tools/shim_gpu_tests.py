@@ -123,6 +123,10 @@ QUICK = {
     "test_gpu_zz_e_fused_decode.py": None,
     "test_gpu_gemm.py": "not deterministic_under_repetition",
     "test_gpu_zz_d_attn_bwd_tc5.py": "lens0 or lens1 or lens4",
+    # the two kernels of round 2's second session: the persistent single-pass prefill attention (the lazy-rescale and the many-items cases)
+    # and the W4A16 mma kernel (two small shapes, both dtypes)
+    "test_gpu_attention.py": "growing or many_items",
+    "test_gpu_w4.py": "mma_partials and (256-512-128-5-2 or 528-1536)",
 }
 
 if __name__ == "__main__":
