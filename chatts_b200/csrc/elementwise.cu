@@ -165,6 +165,50 @@ reduce_residual_rmsnorm_kernel(const float* __restrict__ part, int S, const T* _
   }
 }
 
+// Plain RMSNorm of many rows (prefill-sized T, no partials to reduce: the GEMM before it applied the residual in its epilogue): ONE WARP
+// per row, the row held in registers as packed 16-byte vectors between the two passes, warp shuffles only -- no block barrier.  The
+// one-CTA-per-token kernel above spends two __syncthreads and a shared-memory round trip per 10 KB row: 0.21 ms per launch at 18 432 x
+// 5 120 (1.8 TB/s; profiles/r2_prefill_summary.txt), 5 % of the prefill.
+constexpr int kRowWarps = 8;
+
+template <typename T, int NVW>
+__global__ void __launch_bounds__(kRowWarps * 32)
+rmsnorm_rows_kernel(const T* __restrict__ x, const T* __restrict__ norm_w, float eps, T* __restrict__ norm_out, long long t_total, int h) {
+  pdl_trigger();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long t = (long long)blockIdx.x * kRowWarps + warp;
+  if (t >= t_total) return;
+  const int nvec = h / 8;
+  uint4 row[NVW];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NVW; ++i) {
+    const int v = i * 32 + lane;
+    if (v < nvec) {
+      row[i] = *reinterpret_cast<const uint4*>(x + t * h + (long long)v * 8);
+      float r[8];
+      unpack8<T>(row[i], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += r[j] * r[j];
+    }
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / sqrtf(ss / (float)h + eps);                     // rsqrt(mean(x^2)+eps)  (modeling_qwen2.py:261-262)
+#pragma unroll
+  for (int i = 0; i < NVW; ++i) {
+    const int v = i * 32 + lane;
+    if (v < nvec) {
+      float r[8], w[8], o[8];
+      unpack8<T>(row[i], r);
+      unpack8<T>(*reinterpret_cast<const uint4*>(norm_w + (long long)v * 8), w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = w[j] * rnd<T>(r[j] * inv);         // weight * x.to(dtype)  (:263)
+      *reinterpret_cast<uint4*>(norm_out + t * h + (long long)v * 8) = pack8<T>(o);
+    }
+  }
+}
+
 // Cluster version: C CTAs (one thread-block cluster) share a token; each owns h/C columns, the sum of squares is
 // exchanged through distributed shared memory.  At decode (T <= 32 tokens) this turns a 32-CTA kernel into a
 // 256-CTA one, so the split-K partials are pulled from L2 by every SM instead of by 32 of them.
@@ -643,6 +687,16 @@ extern "C" int cts_reduce_residual_rmsnorm(cts_ctx* ctx, const float* partial, i
     DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(reduce_residual_rmsnorm_cluster_kernel<T>, dim3(C, (unsigned)t), dim3(kClThreads), 0,
                                                 (cudaStream_t)stream, C, partial, split_k, (const T*)resid_in, (T*)resid_out,
                                                 (const T*)norm_w, eps, (T*)norm_out, t, (int)h)));
+  } else if (split_k == 0 && norm_out != nullptr && (resid_out == nullptr || resid_out == resid_in) && t > 256 && h / 8 <= 32 * 24) {
+    // many rows, nothing to reduce: one warp per row
+    const int nvw = (int)cdiv_ll(h / 8, 32);
+    const dim3 rgrid((unsigned)cdiv_ll(t, kRowWarps));
+#define ROWS_LAUNCH(NVV)                                                                                                      \
+    DISPATCH_T(dtype, CTS_CUDA(ctx, launch_pdl(rmsnorm_rows_kernel<T, NVV>, rgrid, dim3(kRowWarps * 32), 0, (cudaStream_t)stream, 1, \
+                                                (const T*)resid_in, (const T*)norm_w, eps, (T*)norm_out, t, (int)h)))
+    if (nvw <= 4) { ROWS_LAUNCH(4); } else if (nvw <= 8) { ROWS_LAUNCH(8); } else if (nvw <= 16) { ROWS_LAUNCH(16); }
+    else if (nvw <= 20) { ROWS_LAUNCH(20); } else { ROWS_LAUNCH(24); }
+#undef ROWS_LAUNCH
   } else {
     const int nv = (int)cdiv_ll(h / 8, kNormThreads);
 #define NORM_LAUNCH(NVV)                                                                                                      \

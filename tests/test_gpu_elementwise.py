@@ -11,6 +11,19 @@ DT = torch.bfloat16
 
 @pytest.mark.parametrize("t,h,s", [(1, 256, 0), (5, 5120, 0), (3, 1024, 4), (32, 5120, 7), (40, 264, 1)])
 def test_reduce_residual_rmsnorm(t, h, s):
+    _rmsnorm_case(t, h, s, DT)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("t,h", [(257, 256), (300, 5120), (1031, 1024), (513, 4096), (260, 6144)])
+def test_plain_rmsnorm_of_many_rows(t, h, dt):
+    """t > 256 rows and nothing to reduce (the prefill after a GEMM with the residual in its epilogue): one warp per row (rmsnorm_rows_kernel),
+    rows not a multiple of the warps per CTA, widths that fill 1 .. 24 vectors per lane; also with resid_out == resid_in (the TP prefill)."""
+    _rmsnorm_case(t, h, 0, dt)
+    _rmsnorm_case(t, h, 0, dt, alias_out=True)
+
+
+def _rmsnorm_case(t, h, s, DT, alias_out=False):
     c = ctx()
     g = torch.Generator().manual_seed(t * 7 + h + s)
     resid = (torch.randn(t, h, generator=g)).to(DT)
@@ -24,8 +37,9 @@ def test_reduce_residual_rmsnorm(t, h, s):
         part, hh = None, resid
     ref_norm = od.rms_norm(hh, w, eps)
     r_out = torch.empty(t, h, device="cuda", dtype=DT)
-    n_out = torch.empty(t, h, device="cuda", dtype=DT)
-    c.reduce_residual_rmsnorm(part.cuda() if s else None, s, resid.cuda(), r_out if s else None, w.cuda(), eps, n_out)
+    n_out = torch.full((t, h), float("nan"), device="cuda", dtype=DT)
+    rin = resid.cuda()
+    c.reduce_residual_rmsnorm(part.cuda() if s else None, s, rin, (rin if alias_out else (r_out if s else None)), w.cuda(), eps, n_out)
     torch.cuda.synchronize()
     if s:
         assert rel_err(r_out, hh) < 8e-3
