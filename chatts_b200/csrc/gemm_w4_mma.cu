@@ -16,12 +16,14 @@
 //     of gemm_w4.cu (exactly the value dequantize_w4 stores for the prefill copy); B fragments by ldmatrix from the swizzled token
 //     tile; mma.sync with the fp32 accumulators of 2 m-tiles x NT n-tiles in registers
 //   * persistent CTAs over (tile, K split) units, the producers run ahead across unit boundaries
-// Measured and rejected (profiles/r2_w4_mma_gemm_sweep_fast.json, git b975740): feeding the MMA the pairs (128 + code) themselves and
-// applying the group's scale / zero point in fp32 once per group and accumulator (no subtraction / multiplication per weight, one more
-// MMA per k16 step with an all-ones A operand for sum_k x_k) removes a quarter of the loop's instructions and is NOT faster (gate_up at
-// t = 1: 26.7 us against 25.8): ncu of either variant shows 57-59 % issue-active with `wait` (fixed-latency dependency) as the top stall
-// and 23 of 64 warp slots filled -- the loop is bound by per-warp dependent-issue latency at the occupancy 64-96 registers allow, not
-// by its instruction count.
+// What the loop is bound by, measured: instruction issue on the ALU side plus barrier round trips -- 57-59 % issue-active with six warps
+// per scheduler at 64-96 registers, ALU pipe ~50 %, FMA pipe ~25 % (profiles/r2_ncu_w4_mma_summary.json).  Two experiments bracket it:
+//   * rejected (profiles/r2_w4_mma_gemm_sweep_fast.json, git b975740): feeding the MMA the pairs (128 + code) themselves and applying the
+//     group's scale / zero point in fp32 once per group and accumulator (no HADD2 / HMUL2 per weight, one more MMA per k16 step with an
+//     all-ones A operand for sum_k x_k) removed a quarter of the loop's instructions -- all of them FMA-pipe work that was overlapping for
+//     free -- and was NOT faster (gate_up at t = 1: 26.7 us against 25.8);
+//   * kept: going from 64-K stages on two rings to 128-K stages on one ring halves the waits, arrivals, ring steps and scale fetches per
+//     weight (all ALU / control work): 25.8 -> 19.9 us.
 // Output: the fp32 split-K partials [split, t, n] of CTS_EPI_PARTIAL_F32, so the decode step's reduce tails are unchanged.  The A
 // operand holds the same 16-bit values as the dense copy; the fp32 summation order differs from the tcgen05 GEMM (parity is a
 // tolerance, tests/test_gpu_w4.py), unlike gemm_w4.cu which is bit-identical and stays as the checker for this kernel.
