@@ -35,6 +35,13 @@ def test_bench_driver_prints_the_contract_line(which):
         assert set(d["attention"]) >= {"decode", "prefill"} and "error" not in d["attention"]
         assert d["ts_encoder"]["patch_rows"] > 0
         assert d["config"]["variants"] == {"decode_fused": 0, "peer_ll": 1, "native_step": 0, "decode_chain": 0}      # peer_ll: default since round 2 (only acts under TP)
+        # side blocks: BASELINE configs[3] (second model instance, 30 series x 512 points) and the GPTQ-Int4 decode (third instance, 4-bit projections)
+        c4, w4 = d["config4"], d["w4a16"]
+        assert "error" not in c4 and c4["batch"] == 8 and c4["context"] == 30 * (46 + 2 + 32) + 64 and c4["tokens_per_s"] > 0
+        assert c4["identical_tokens_on_all_ranks"] and set(c4["e2e"]) >= {"value", "unit", "seconds"}
+        assert "error" not in w4 and w4["kernel"] == "mma" and set(w4["by_batch"]) >= {"1", "2"}
+        for b in w4["by_batch"].values():
+            assert b["w4_ms_per_step"] > 0 and b["bf16_ms_per_step"] > 0 and min(v for k, v in b.items() if k.startswith("min_greedy_agreement")) >= 1
     else:
         assert d["metric"] == "lora_finetune_positions_per_s" and d["scaling"] == "weak"
         assert 11.0 < d["loss"] < 13.0          # ln(vocab) at initialisation (LoRA B = 0)
